@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the FFT hot path (BASELINE.json metric / configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch: batched complex128 c2c FFT, 65536 rows x
+1024 points per GPU (BASELINE config 2), out of place, synthetic uniform[-0.5,0.5) input.
+Per-GPU work is fixed (rows are independent: batch sharding, no collective) -> "scaling": "weak".
+
+Prints ONE JSON line (rank 0).  `value` = algorithmic GB/s with inputs resident in HBM (CUDA
+events on the launching stream, max over ranks); `e2e` = the same metric through the public
+C-ABI call with pinned HOST buffers (H2D + kernel + D2H inside the timed region); `roofline`
+= the dominant kernel against the measured HBM copy peak; `cpu_baseline` = the reference's own
+pocketfft timed on this box's host cores.  `--impl reference` times only that CPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, rows, n, dtype)  — bytes/row are the SURVEY 8(d) algorithmic figures
+    "c2c_65536x1024_c128": ("c2c", 65536, 1024, "f64"),
+    "r2c_1024x4096_f64": ("r2c", 1024, 4096, "f64"),
+    "r2c_16384x1000_f64": ("r2c", 16384, 1000, "f64"),
+    "r2c_16384x3888_f64": ("r2c", 16384, 3888, "f64"),
+    "r2c_16384x4099_f64": ("r2c", 16384, 4099, "f64"),
+    "c2r_16384x1000_f64": ("c2r", 16384, 1000, "f64"),
+    "c2r_16384x3888_f64": ("c2r", 16384, 3888, "f64"),
+    "c2r_16384x4099_f64": ("c2r", 16384, 4099, "f64"),
+    "c2c_16384x4096_c128": ("c2c", 16384, 4096, "f64"),
+    "c2c_8192x8192_c128": ("c2c", 8192, 8192, "f64"),
+    "c2c_131072x1024_c64": ("c2c", 131072, 1024, "f32"),
+}
+DEFAULT_WORKLOAD = "c2c_65536x1024_c128"
+
+
+def algorithmic_bytes(kind, rows, n, dtype):
+    r = 8 if dtype == "f64" else 4
+    if kind == "c2c":
+        return rows * n * 2 * r * 2          # read + write one complex element each
+    return rows * (n * r + (n // 2 + 1) * 2 * r)  # real side + half-spectrum side
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(p)).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.t = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.05] or [r for _, r in self.rows]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(kind, rows, n, dtype, budget_s=12.0):
+    """Time the reference's own CPU implementation (oracle/_ref, else the port) on a bounded
+    sample of the workload with all host threads.  Returns (GB/s, info dict)."""
+    from oracle import oracle
+    chk = oracle.load()
+    cores = max(1, chk.hardware_threads() if chk.kind == "reference" else 1)
+    rng = np.random.default_rng(1234)
+    srows = rows
+    # bound the sample: ~7.3 us per 1024-pt row per core measured in the survey; keep each rep <= ~2 s
+    est = rows * n * np.log2(max(n, 2)) * 0.75e-9 / cores * (1 if chk.kind == "reference" else 60)
+    while est > 2.0 and srows > 64:
+        srows //= 2
+        est /= 2
+    if dtype != "f64":
+        raise SystemExit("cpu baseline implemented for the float64 workloads")
+    if kind == "c2c":
+        x = rng.uniform(-0.5, 0.5, (srows, n)) + 1j * rng.uniform(-0.5, 0.5, (srows, n))
+        run = lambda: chk.cfft_rows(x, True, 1.0, nthreads=cores)
+    elif kind == "r2c":
+        x = rng.uniform(-0.5, 0.5, (srows, n))
+        run = lambda: chk.rfft_rows(x, True, 1.0, nthreads=cores)
+    else:
+        x = rng.uniform(-0.5, 0.5, (srows, n))
+        run = lambda: chk.rfft_rows(x, False, 1.0 / n, nthreads=cores)
+    run()  # warm-up (page faults, plan)
+    best, reps, t_all = float("inf"), 0, time.perf_counter()
+    while reps < 5 or (time.perf_counter() - t_all < budget_s and reps < 50):
+        t = time.perf_counter()
+        run()
+        best = min(best, time.perf_counter() - t)
+        reps += 1
+        if time.perf_counter() - t_all > budget_s:
+            break
+    gbs = algorithmic_bytes(kind, srows, n, dtype) / best / 1e9
+    info = {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": chk.kind,
+            "sample": f"{srows} of {rows} rows x {n} ({kind} {dtype}), in place, one shared plan, best of {reps}",
+            "ms": round(best * 1e3, 3), "elements_per_s": round(srows * n / best, 1)}
+    return gbs, info
+
+
+def run_reference(args, kind, rows, n, dtype, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    gbs, info = cpu_reference(kind, rows, n, dtype, budget_s=min(60.0, 2.0 * (steps + args.warmup)))
+    line = {"impl": "reference", "metric": "batched fp64 FFT throughput (algorithmic GB/s)", "value": info["value"],
+            "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": info["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic", "config": {"workload": args.workload, "sample": info["sample"]},
+            "cpu_baseline": info,
+            "e2e": {"value": info["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    kind, rows, n, dtype = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, kind, rows, n, dtype, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import impulse_b200 as ib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: impulse_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+
+    rdt = torch.float64 if dtype == "f64" else torch.float32
+    cdt = torch.complex128 if dtype == "f64" else torch.complex64
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    if kind == "c2c":
+        x = torch.view_as_complex(torch.rand((rows, n, 2), generator=g, device=dev, dtype=rdt) - 0.5)
+        y = torch.empty_like(x)
+    elif kind == "r2c":
+        x = torch.rand((rows, n), generator=g, device=dev, dtype=rdt) - 0.5
+        y = torch.empty((rows, n // 2 + 1), device=dev, dtype=cdt)
+    else:
+        x = torch.view_as_complex(torch.rand((rows, n // 2 + 1, 2), generator=g, device=dev, dtype=rdt) - 0.5)
+        y = torch.empty((rows, n), device=dev, dtype=rdt)
+    fdesc = ib.FFTDesc.init(axes=[1], forward=(kind != "c2r"), scalingFactor=1.0)
+    din, dout = ib.DataDesc.init(x), ib.DataDesc.init(y)
+
+    def step():
+        fdesc.apply(dout, din)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = ib.launch_count()
+    t_host0 = time.time()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    t_host1 = time.time()
+    launches = ib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / steps
+    bytes_per_gpu = algorithmic_bytes(kind, rows, n, dtype)
+    value = world * bytes_per_gpu / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: public API with pinned HOST buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+        hy = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+        hx.copy_(x)
+        hxn, hyn = hx.numpy(), hy.numpy()
+        hin, hout = ib.DataDesc.init(hxn), ib.DataDesc.init(hyn)
+        e_steps = max(2, min(steps, 5))
+        for _ in range(2):
+            fdesc.apply(hout, hin)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            fdesc.apply(hout, hin)   # synchronous for host pointers: H2D + kernel + D2H
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        chk = float(np.abs(hyn[0, :4]).sum())  # touch the result on the host
+        e2e = {"value": round(world * bytes_per_gpu / dt / 1e9, 3), "unit": "GB/s",
+               "h2d_bytes_per_step": int(hxn.nbytes), "d2h_bytes_per_step": int(hyn.nbytes),
+               "ms_per_step": round(dt * 1e3, 3), "steps": e_steps, "host_memory": "pinned", "check": chk}
+    clocks = sampler.stop(t_host0, time.time()) if sampler else None
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # dominant (only) kernel of the step: one launch per step on this stream
+        k_ms = e0.elapsed_time(e1) / max(1, launches)
+        achieved = bytes_per_gpu / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": "batched fp64 FFT throughput (algorithmic GB/s)" if dtype == "f64" else "batched fp32 FFT throughput (algorithmic GB/s)",
+            "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic",
+            "config": {"workload": args.workload, "rows_per_gpu": rows, "length": n, "kind": kind,
+                       "placement": "out of place, device resident", "l2": "input+output per step exceed the 126 MB L2"
+                       if bytes_per_gpu > 2 * 126e6 else "working set fits L2: reported as is, see DESIGN.md",
+                       "parallelism": f"batch-shard x{world}, no collective",
+                       "elements_per_s": round(world * rows * n / (ms_per_step * 1e-3), 1),
+                       "frac_of_8TBps_nominal": round(value / world / 8000.0, 4)},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": committed_traffic(args.workload),
+                         "peak_source": peak_src, "kernel": "line_fft_kernel", "algorithmic_bytes_per_launch": bytes_per_gpu},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu and world == 1:
+            try:
+                _, info = cpu_reference(kind, rows, n, dtype)
+                line["cpu_baseline"] = info
+            except Exception as ex:  # the oracle is optional for the measurement itself
+                line["cpu_baseline"] = {"unavailable": str(ex)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

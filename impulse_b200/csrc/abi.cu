@@ -1,0 +1,484 @@
+// C ABI of libimpulse_fft_b200.so (declared in include/impulse_fft_b200.h and include/pocketfft.h).
+//
+// Host-side responsibilities: per-device context (table cache, kernel attributes), plan objects,
+// pointer classification (device vs host), host staging with a chunked copy/compute pipeline,
+// the one-shot plan cache, and error reporting.  The transforms themselves run only on the GPU
+// (fft_kernels.cu); if no CUDA device is usable every entry point fails with
+// IMPULSE_FFT_ERR_NO_DEVICE — there is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/impulse_fft_b200.h"
+#include "../../include/pocketfft.h"
+#include "fft_kernels.h"
+#include "planner.h"
+
+using namespace impulse;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? IMPULSE_FFT_ERR_NO_DEVICE
+                                                                        : IMPULSE_FFT_ERR_CUDA;
+}
+
+struct CudaAlloc : TableAlloc {
+  void *upload(const void *h, size_t n) override {
+    void *d = nullptr;
+    if (cudaMalloc(&d, n ? n : 1) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    return d;
+  }
+  void release(void *d) override { cudaFree(d); }
+};
+
+struct DeviceCtx {
+  int dev = -1;
+  CudaAlloc alloc;
+  std::unique_ptr<PlanCache> cache;
+  int sm_count = 0;
+};
+
+std::mutex g_ctx_mu;
+std::map<int, std::unique_ptr<DeviceCtx>> g_ctx;
+
+int get_ctx(DeviceCtx **out) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, "no usable CUDA device (this library has no CPU path)"); }
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto it = g_ctx.find(dev);
+  if (it != g_ctx.end()) { *out = it->second.get(); return 0; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major < 10)
+    return fail(IMPULSE_FFT_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; this library is built for B200 (sm_100a) only");
+  std::unique_ptr<DeviceCtx> c(new DeviceCtx);
+  c->dev = dev;
+  c->sm_count = prop.multiProcessorCount;
+  c->cache.reset(new PlanCache(&c->alloc));
+  c->cache->max_smem = prop.sharedMemPerBlockOptin;
+  int rc = configure_kernels(prop.sharedMemPerBlockOptin);
+  if (rc) return cuda_fail((cudaError_t)rc, "cudaFuncSetAttribute");
+  *out = c.get();
+  g_ctx[dev] = std::move(c);
+  return 0;
+}
+
+bool is_device_ptr(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct impulse_fft_plan_s {
+  NdPlan nd;
+  DeviceCtx *ctx = nullptr;
+  size_t in_esz = 0, out_esz = 0;  // alignment required of the base pointers
+};
+
+namespace {
+
+size_t side_align(const NdDesc &d, bool input) {
+  const size_t r = d.dtype == DT_F64 ? 8 : 4;
+  bool real_side;
+  if (input) real_side = d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX);
+  else real_side = d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX);
+  return real_side ? r : 2 * r;
+}
+
+// run all steps with device pointers on `stream`
+int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaStream_t stream) {
+  const NdPlan &nd = p->nd;
+  if (nd.empty) return 0;
+  if (((uintptr_t)in % p->in_esz) || ((uintptr_t)out % p->out_esz))
+    return fail(IMPULSE_FFT_ERR_STRIDE, "data pointer is not aligned to its element size");
+  if (in == out && nd.desc.kind == KIND_C2C && nd.desc.stride_in != nd.desc.stride_out)
+    return fail(IMPULSE_FFT_ERR_STRIDE, "stride mismatch");  // hdronly.h:455-456
+  void *tmp = nullptr;
+  if (nd.tmp_bytes) {
+    cudaError_t e = cudaMallocAsync(&tmp, nd.tmp_bytes, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(tmp)");
+  }
+  int rc = 0;
+  for (const Step &st : nd.steps) {
+    LineJob J = st.job;
+    const unsigned char *src = st.src == BUF_IN ? (const unsigned char *)in : st.src == BUF_OUT ? (const unsigned char *)out : (const unsigned char *)tmp;
+    unsigned char *dst = st.dst == BUF_OUT ? (unsigned char *)out : (unsigned char *)tmp;
+    J.in = src + st.src_off_bytes;
+    J.out = dst + st.dst_off_bytes;
+    J.fct = st.takes_fct ? fct : 1.0;
+    const size_t r = J.dtype == 1 ? 8 : 4;
+    if ((J.flags & F_VEC_IN) && ((uintptr_t)J.in % (2 * r))) J.flags &= ~F_VEC_IN;
+    if ((J.flags & F_VEC_OUT) && ((uintptr_t)J.out % (2 * r))) J.flags &= ~F_VEC_OUT;
+    int e = launch_line_job(J, st.cfg.threads, st.cfg.smem_bytes, st.cfg.n_tiles, stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e) { rc = cuda_fail((cudaError_t)e, "kernel launch"); break; }
+  }
+  if (tmp) cudaFreeAsync(tmp, stream);
+  return rc;
+}
+
+// ---- host staging -----------------------------------------------------------
+// Pipelined path for the common case (single-step plan whose slowest batch dimension cuts both
+// arrays into disjoint slabs): chunks flow H2D -> kernel -> D2H on alternating streams so that
+// the two PCIe directions and the kernel overlap.  Anything else: whole-span staging.
+struct Staging {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  ~Staging() { for (auto &x : s) if (x) cudaStreamDestroy(x); }
+};
+
+int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
+  const NdPlan &nd = p->nd;
+  if (nd.empty) return 0;
+  const bool inplace = (in == out);
+  // ---- try the chunked pipeline
+  if (nd.steps.size() == 1 && nd.tmp_bytes == 0) {
+    const Step &st = nd.steps[0];
+    const LineJob &J0 = st.job;
+    int od = -1;  // outermost batch dim in use
+    for (int d = kMaxBatchDims - 1; d >= 0; --d) if (J0.bdim[d] > 1) { od = d; break; }
+    const size_t in_e = side_align(nd.desc, true), out_e = side_align(nd.desc, false);
+    if (od >= 0 && J0.bs_in[od] > 0 && J0.bs_out[od] > 0) {
+      const int64_t sin_b = J0.bs_in[od] * (int64_t)in_e, sout_b = J0.bs_out[od] * (int64_t)out_e;
+      // span of one slab (index fixed along od) on each side
+      const int64_t in_slab = (nd.in_hi - nd.in_lo) - (int64_t)(J0.bdim[od] - 1) * sin_b;
+      const int64_t out_slab = (nd.out_hi - nd.out_lo) - (int64_t)(J0.bdim[od] - 1) * sout_b;
+      const bool disjoint = in_slab <= sin_b && out_slab <= sout_b && nd.in_lo == 0 && nd.out_lo == 0;
+      const uint64_t total_bytes = (uint64_t)(nd.in_hi - nd.in_lo) + (uint64_t)(nd.out_hi - nd.out_lo);
+      if (disjoint && J0.bdim[od] >= 4 && total_bytes >= (8u << 20)) {
+        uint64_t inner_lines = 1;
+        for (int d = 0; d < od; ++d) inner_lines *= J0.bdim[d];
+        // ~16 MiB of traffic per chunk, at least 4 chunks
+        uint64_t per = std::max<uint64_t>(1, (16u << 20) / std::max<int64_t>(1, sin_b + sout_b));
+        per = std::min<uint64_t>(per, (J0.bdim[od] + 3) / 4);
+        const uint64_t nchunks = (J0.bdim[od] + per - 1) / per;
+        Staging sg;
+        unsigned char *dbuf_in[2] = {nullptr, nullptr}, *dbuf_out[2] = {nullptr, nullptr};
+        const size_t cin = (size_t)((per - 1) * sin_b + in_slab), cout = (size_t)((per - 1) * sout_b + out_slab);
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+          e = cudaStreamCreateWithFlags(&sg.s[i], cudaStreamNonBlocking);
+          if (e == cudaSuccess) e = cudaMalloc(&dbuf_in[i], cin);
+          if (e == cudaSuccess) e = cudaMalloc(&dbuf_out[i], cout);
+        }
+        int rc = 0;
+        if (e != cudaSuccess) rc = cuda_fail(e, "staging allocation");
+        for (uint64_t c = 0; c < nchunks && !rc; ++c) {
+          const int b = (int)(c & 1);
+          const uint64_t lo = c * per, cnt = std::min<uint64_t>(per, J0.bdim[od] - lo);
+          const size_t bin = (size_t)((cnt - 1) * sin_b + in_slab), bout = (size_t)((cnt - 1) * sout_b + out_slab);
+          const unsigned char *hin = (const unsigned char *)in + lo * sin_b;
+          unsigned char *hout = (unsigned char *)out + lo * sout_b;
+          e = cudaMemcpyAsync(dbuf_in[b], hin, bin, cudaMemcpyHostToDevice, sg.s[b]);
+          // strided output with gaps: preload so the gaps survive the write-back
+          if (e == cudaSuccess && !nd.out_dense && !inplace)
+            e = cudaMemcpyAsync(dbuf_out[b], hout, bout, cudaMemcpyHostToDevice, sg.s[b]);
+          if (e != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
+          LineJob J = J0;
+          J.bdim[od] = cnt;
+          J.n_lines = inner_lines * cnt;
+          J.in = dbuf_in[b];
+          J.out = inplace ? (void *)dbuf_in[b] : (void *)dbuf_out[b];
+          J.fct = st.takes_fct ? fct : 1.0;
+          const uint64_t C = 1ull << J.log_c;
+          int le = launch_line_job(J, st.cfg.threads, st.cfg.smem_bytes, (J.n_lines + C - 1) / C, sg.s[b]);
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          if (le) { rc = cuda_fail((cudaError_t)le, "kernel launch"); break; }
+          e = cudaMemcpyAsync(hout, inplace ? dbuf_in[b] : dbuf_out[b], inplace ? bin : bout, cudaMemcpyDeviceToHost, sg.s[b]);
+          if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy"); break; }
+        }
+        for (int i = 0; i < 2; ++i) {
+          if (sg.s[i]) { cudaError_t se = cudaStreamSynchronize(sg.s[i]); if (se != cudaSuccess && !rc) rc = cuda_fail(se, "staging sync"); }
+          if (dbuf_in[i]) cudaFree(dbuf_in[i]);
+          if (dbuf_out[i]) cudaFree(dbuf_out[i]);
+        }
+        return rc;
+      }
+    }
+  }
+  // ---- whole-span staging
+  const size_t bin = (size_t)(nd.in_hi - nd.in_lo), bout = (size_t)(nd.out_hi - nd.out_lo);
+  unsigned char *din = nullptr, *dout = nullptr;
+  cudaError_t e = cudaMalloc(&din, bin);
+  if (e != cudaSuccess) return cuda_fail(e, "staging allocation");
+  if (!inplace) {
+    e = cudaMalloc(&dout, bout);
+    if (e != cudaSuccess) { cudaFree(din); return cuda_fail(e, "staging allocation"); }
+  }
+  int rc = 0;
+  e = cudaMemcpy(din, (const unsigned char *)in + nd.in_lo, bin, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !inplace && !nd.out_dense)  // preserve what lies between strided output elements
+    e = cudaMemcpy(dout, (const unsigned char *)out + nd.out_lo, bout, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) rc = cuda_fail(e, "H2D copy");
+  if (!rc) {
+    unsigned char *o = inplace ? din : dout;
+    const ptrdiff_t olo = inplace ? nd.in_lo : nd.out_lo;
+    rc = run_device(p, din - nd.in_lo, o - olo, fct, nullptr);
+    if (!rc) {
+      e = cudaMemcpy((unsigned char *)out + olo, o, inplace ? bin : bout, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+    }
+  }
+  cudaFree(din);
+  if (dout) cudaFree(dout);
+  return rc;
+}
+
+int make_desc(NdDesc *d, int kind, int dtype, int layout, int forward, size_t ndim, const size_t *shape,
+              const ptrdiff_t *sin, const ptrdiff_t *sout, size_t naxes, const size_t *axes) {
+  if (!shape || !sin || !sout || !axes) return fail(IMPULSE_FFT_ERR_INVALID, "null descriptor array");
+  if (ndim < 1) return fail(IMPULSE_FFT_ERR_INVALID, "ndim must be >= 1");
+  if (ndim > IMPULSE_FFT_MAX_DIMS || naxes > IMPULSE_FFT_MAX_DIMS) return fail(IMPULSE_FFT_ERR_INVALID, "too many dimensions");
+  d->kind = kind; d->dtype = dtype; d->layout = layout; d->forward = forward != 0;
+  d->shape.assign(shape, shape + ndim);
+  d->stride_in.assign(sin, sin + ndim);
+  d->stride_out.assign(sout, sout + ndim);
+  d->axes.assign(axes, axes + naxes);
+  return 0;
+}
+
+int create_plan(impulse_fft_plan *out, const NdDesc &d) {
+  DeviceCtx *ctx = nullptr;
+  int rc = get_ctx(&ctx);
+  if (rc) return rc;
+  std::unique_ptr<impulse_fft_plan_s> p(new impulse_fft_plan_s);
+  p->ctx = ctx;
+  std::string err;
+  rc = ctx->cache->build_nd(d, &p->nd, &err);
+  if (rc) return fail(rc, err);
+  p->in_esz = side_align(d, true);
+  p->out_esz = side_align(d, false);
+  *out = p.release();
+  return 0;
+}
+
+// one-shot plan cache (the role of get_plan, hdronly.h:2655-2706)
+struct OneShotKey {
+  int dev, kind, dtype, layout, forward;
+  std::vector<size_t> shape, axes;
+  std::vector<ptrdiff_t> sin, sout;
+  bool operator<(const OneShotKey &o) const {
+    return std::tie(dev, kind, dtype, layout, forward, shape, axes, sin, sout) <
+           std::tie(o.dev, o.kind, o.dtype, o.layout, o.forward, o.shape, o.axes, o.sin, o.sout);
+  }
+};
+std::mutex g_os_mu;
+std::map<OneShotKey, std::shared_ptr<impulse_fft_plan_s>> g_os;
+constexpr size_t kOneShotCap = 64;
+
+int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *sin,
+             const ptrdiff_t *sout, size_t naxes, const size_t *axes, int forward, const void *in, void *out,
+             double fct, void *stream) {
+  NdDesc d;
+  int rc = make_desc(&d, kind, dtype, layout, forward, ndim, shape, sin, sout, naxes, axes);
+  if (rc) return rc;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }
+  OneShotKey key{dev, kind, dtype, layout, forward != 0, d.shape, d.axes, d.stride_in, d.stride_out};
+  std::shared_ptr<impulse_fft_plan_s> plan;
+  {
+    std::lock_guard<std::mutex> lk(g_os_mu);
+    auto it = g_os.find(key);
+    if (it != g_os.end()) plan = it->second;
+  }
+  if (!plan) {
+    impulse_fft_plan raw = nullptr;
+    rc = create_plan(&raw, d);
+    if (rc) return rc;
+    plan.reset(raw);
+    std::lock_guard<std::mutex> lk(g_os_mu);
+    if (g_os.size() >= kOneShotCap) g_os.clear();  // plans are cheap to rebuild: tables stay cached per device
+    g_os[key] = plan;
+  }
+  return impulse_fft_execute(plan.get(), in, out, fct, stream);
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+const char *impulse_fft_last_error(void) { return g_err.c_str(); }
+const char *impulse_fft_version(void) { return "impulse_fft_b200 0.1 (sm_100a)"; }
+uint64_t impulse_fft_launch_count(void) { return g_launches.load(); }
+
+int impulse_fft_plan_create(impulse_fft_plan *out, const impulse_fft_desc *desc) {
+  if (!out || !desc) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (desc->ndim > IMPULSE_FFT_MAX_DIMS || desc->naxes > IMPULSE_FFT_MAX_DIMS)
+    return fail(IMPULSE_FFT_ERR_INVALID, "too many dimensions");
+  NdDesc d;
+  int rc = make_desc(&d, desc->kind, desc->dtype, desc->real_layout, desc->forward, desc->ndim, desc->shape,
+                     desc->stride_in, desc->stride_out, desc->naxes, desc->axes);
+  if (rc) return rc;
+  return create_plan(out, d);
+}
+
+int impulse_fft_plan_destroy(impulse_fft_plan plan) {
+  delete plan;
+  return 0;
+}
+
+int impulse_fft_execute(impulse_fft_plan plan, const void *in, void *out, double fct, void *stream) {
+  if (!plan) return fail(IMPULSE_FFT_ERR_INVALID, "null plan");
+  if (plan->nd.empty) return 0;
+  if (!in || !out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev != plan->ctx->dev) return fail(IMPULSE_FFT_ERR_INVALID, "plan was created on another device");
+  const bool din = is_device_ptr(in), dout = is_device_ptr(out);
+  if (din != dout) return fail(IMPULSE_FFT_ERR_INVALID, "input and output must both be device or both be host memory");
+  if (din) return run_device(plan, in, out, fct, static_cast<cudaStream_t>(stream));
+  return run_host(plan, in, out, fct);
+}
+
+int impulse_fft_plan_get_info(impulse_fft_plan plan, impulse_fft_plan_info *info) {
+  if (!plan || !info) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
+  std::memset(info, 0, sizeof(*info));
+  info->n_steps = (uint32_t)plan->nd.steps.size();
+  info->tmp_bytes = plan->nd.tmp_bytes;
+  if (!plan->nd.steps.empty()) {
+    const Step &s = plan->nd.steps[0];
+    info->n_fft = s.job.n_fft;
+    info->lines_per_cta = 1u << s.job.log_c;
+    info->threads = (uint32_t)s.cfg.threads;
+    info->smem_bytes = (uint32_t)s.cfg.smem_bytes;
+    uint32_t n = 0;
+    for (int i = 0; i < s.job.nphases; ++i) {
+      if (s.job.ph[i].op == OP_BLUE_PRE) info->bluestein = 1;
+      if (s.job.ph[i].op == OP_PASS_DIF && n < 32) info->radices[n++] = s.job.ph[i].radix;
+    }
+    info->n_radices = n;
+  }
+  return 0;
+}
+
+int impulse_fft_c2c(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
+                    const void *data_in, void *data_out, double fct, size_t, void *stream) {
+  return one_shot(KIND_C2C, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, forward,
+                  data_in, data_out, fct, stream);
+}
+int impulse_fft_r2c(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
+                    const void *data_in, void *data_out, double fct, size_t, void *stream) {
+  return one_shot(KIND_R2C, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, forward,
+                  data_in, data_out, fct, stream);
+}
+int impulse_fft_c2r(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
+                    const void *data_in, void *data_out, double fct, size_t, void *stream) {
+  return one_shot(KIND_C2R, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, forward,
+                  data_in, data_out, fct, stream);
+}
+
+int impulse_fft_cfft_rows(double *data, size_t nrows, size_t length, int forward, double fct, void *stream) {
+  if (length == 0) return fail(IMPULSE_FFT_ERR_INVALID, "zero-length transform");
+  size_t shape[2] = {nrows, length}, axes[1] = {1};
+  ptrdiff_t st[2] = {(ptrdiff_t)(length * 16), 16};
+  return one_shot(KIND_C2C, DT_F64, RL_HERMITIAN, 2, shape, st, st, 1, axes, forward, data, data, fct, stream);
+}
+int impulse_fft_rfft_rows(double *data, size_t nrows, size_t length, int forward, double fct, void *stream) {
+  if (length == 0) return fail(IMPULSE_FFT_ERR_INVALID, "zero-length transform");
+  size_t shape[2] = {nrows, length}, axes[1] = {1};
+  ptrdiff_t st[2] = {(ptrdiff_t)(length * 8), 8};
+  return one_shot(forward ? KIND_R2C : KIND_C2R, DT_F64, RL_HALFCOMPLEX, 2, shape, st, st, 1, axes, forward != 0, data, data,
+                  fct, stream);
+}
+
+int impulse_fft_cmul(int dtype, const void *a, const void *filter, void *out, size_t n_inner, size_t n_batch,
+                     double scale, void *stream) {
+  DeviceCtx *ctx = nullptr;
+  int rc = get_ctx(&ctx);
+  if (rc) return rc;
+  if (!a || !filter || !out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
+  if (!is_device_ptr(a) || !is_device_ptr(filter) || !is_device_ptr(out))
+    return fail(IMPULSE_FFT_ERR_INVALID, "impulse_fft_cmul takes device pointers");
+  int e = launch_cmul(dtype, a, filter, out, n_inner, n_batch, scale, ctx->sm_count, stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return e ? cuda_fail((cudaError_t)e, "kernel launch") : 0;
+}
+
+int impulse_fft_transpose(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
+                          size_t batch, void *stream) {
+  DeviceCtx *ctx = nullptr;
+  int rc = get_ctx(&ctx);
+  if (rc) return rc;
+  if (!in || !out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
+  if (in == out) return fail(IMPULSE_FFT_ERR_INVALID, "transpose is out of place");
+  if (ld_in < cols || ld_out < rows) return fail(IMPULSE_FFT_ERR_STRIDE, "leading dimension smaller than the row length");
+  if (!is_device_ptr(in) || !is_device_ptr(out)) return fail(IMPULSE_FFT_ERR_INVALID, "impulse_fft_transpose takes device pointers");
+  int e = launch_transpose(dtype, in, out, rows, cols, ld_in, ld_out, batch, ctx->sm_count, stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return e ? cuda_fail((cudaError_t)e, "kernel launch") : 0;
+}
+
+// ---- the ten pocketfft symbols (include/pocketfft.h) -------------------------
+struct cfft_plan_i { size_t length; };
+struct rfft_plan_i { size_t length; };
+
+cfft_plan make_cfft_plan(size_t length) {
+  if (length == 0) { g_err = "zero-length transform"; return nullptr; }
+  DeviceCtx *ctx = nullptr;
+  if (get_ctx(&ctx)) return nullptr;
+  // build (and cache) both directions now so that execute cannot fail on planning
+  const Engine1D *e = nullptr;
+  std::string err;
+  if (length > 0xffffffffull || ctx->cache->status_engine((uint32_t)length, DT_F64, &e, &err)) { g_err = err; return nullptr; }
+  cfft_plan p = new cfft_plan_i;
+  p->length = length;
+  return p;
+}
+void destroy_cfft_plan(cfft_plan plan) { delete plan; }
+size_t cfft_length(cfft_plan plan) { return plan->length; }
+int cfft_forward(cfft_plan plan, double c[], double fct) {
+  return impulse_fft_cfft_rows(c, 1, plan->length, 1, fct, nullptr) ? -1 : 0;
+}
+int cfft_backward(cfft_plan plan, double c[], double fct) {
+  return impulse_fft_cfft_rows(c, 1, plan->length, 0, fct, nullptr) ? -1 : 0;
+}
+
+rfft_plan make_rfft_plan(size_t length) {
+  if (length == 0) { g_err = "zero-length transform"; return nullptr; }
+  DeviceCtx *ctx = nullptr;
+  if (get_ctx(&ctx)) return nullptr;
+  const Engine1D *e = nullptr;
+  std::string err;
+  const size_t L = (length % 2 == 0) ? length / 2 : length;
+  if (length > 0xffffffffull || ctx->cache->status_engine((uint32_t)L, DT_F64, &e, &err)) { g_err = err; return nullptr; }
+  rfft_plan p = new rfft_plan_i;
+  p->length = length;
+  return p;
+}
+void destroy_rfft_plan(rfft_plan plan) { delete plan; }
+size_t rfft_length(rfft_plan plan) { return plan->length; }
+int rfft_forward(rfft_plan plan, double c[], double fct) {
+  return impulse_fft_rfft_rows(c, 1, plan->length, 1, fct, nullptr) ? -1 : 0;
+}
+int rfft_backward(rfft_plan plan, double c[], double fct) {
+  return impulse_fft_rfft_rows(c, 1, plan->length, 0, fct, nullptr) ? -1 : 0;
+}
+
+}  // extern "C"

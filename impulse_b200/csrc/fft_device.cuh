@@ -1,0 +1,473 @@
+// Generic shared-memory line-FFT engine: device-side phase interpreter.
+//
+// One CTA owns a tile of C = 1<<log_c lines.  Every phase is a pure function of
+// (job, tile, thread id); the kernel (fft_kernels.cu) runs them with a block barrier
+// in between.  Because each phase is a plain function of its thread id, the same code
+// also compiles for the host (tests/emu) where a loop over thread ids replaces the CTA —
+// that is how index logic is checked in the GPU-less build container.  The emulation
+// is test infrastructure only; the product library contains no CPU transform path.
+//
+// Algorithms (what of the reference each piece replaces):
+//   * radix passes      — in-place DIF (and its transpose, DIT) on CC(i,j,k) =
+//                         s[i + ido*(j + ip*k)], twiddle W_n^(i*j*l1); replaces
+//                         pass2..pass11/passg + pass_all (pocketfft.c:300-929).
+//                         Natural order comes back through a host-built position table
+//                         at STORE time instead of pocketfft's ping-pong buffers.
+//   * real transforms   — even N: N/2-point complex FFT + Hermitian post/pre-twiddle
+//                         (replaces radf*/radb*, pocketfft.c:1082-1766); odd N: N-point
+//                         complex FFT of the zero-imag / Hermitian-extended line
+//                         (what rfftblue_* does, pocketfft.c:2019-2058).
+//   * Bluestein         — chirp, DIF FFT, multiply by pre-permuted bkf, DIT FFT, chirp:
+//                         no reordering pass at all (replaces fftblue_fft, pocketfft.c:1945-2008).
+//   * backward          — conj(FFT(conj(x))): conjugations folded into LOAD/STORE.
+#pragma once
+#include "fft_types.h"
+#include "trig_tables.h"
+
+namespace impulse {
+
+#if defined(__CUDA_ARCH__)
+#define IMP_LDG(p) __ldg(p)
+#else
+#define IMP_LDG(p) (*(p))
+#endif
+
+template <typename T> struct Vec2;
+#if defined(__CUDACC__)
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+#else
+struct alignas(16) emu_double2 { double x, y; };
+struct alignas(8) emu_float2 { float x, y; };
+template <> struct Vec2<double> { using type = emu_double2; };
+template <> struct Vec2<float> { using type = emu_float2; };
+#endif
+
+template <typename T> using cx = typename Vec2<T>::type;
+
+template <typename T> IMP_HD cx<T> mk(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
+template <typename C> IMP_HD C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> IMP_HD C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> IMP_HD C cmul(C a, C b) { C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+template <typename C> IMP_HD C cconj(C a) { a.y = -a.y; return a; }
+template <typename C> IMP_HD C cconj_if(C a, bool c) { if (c) a.y = -a.y; return a; }
+// multiply by -i / +i
+template <typename C> IMP_HD C mul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
+template <typename C> IMP_HD C mul_pi(C a) { C r; r.x = -a.y; r.y = a.x; return r; }
+
+// ---------------------------------------------------------------------------
+// Forward DFT butterflies, in registers: x[k] <- sum_j x[j] exp(-2*pi*i*j*k/R)
+// ---------------------------------------------------------------------------
+template <typename T, int R> struct Bfly;
+
+template <typename T> struct Bfly<T, 2> {
+  static IMP_HD void run(cx<T> (&x)[2]) {
+    cx<T> a = x[0], b = x[1];
+    x[0] = cadd(a, b);
+    x[1] = csub(a, b);
+  }
+};
+
+template <typename T> struct Bfly<T, 4> {
+  static IMP_HD void run(cx<T> (&x)[4]) {
+    cx<T> t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
+    cx<T> t2 = cadd(x[1], x[3]), t3 = mul_mi(csub(x[1], x[3]));
+    x[0] = cadd(t0, t2);
+    x[2] = csub(t0, t2);
+    x[1] = cadd(t1, t3);
+    x[3] = csub(t1, t3);
+  }
+};
+
+template <typename T> struct Bfly<T, 8> {
+  static IMP_HD void run(cx<T> (&x)[8]) {
+    const T h = (T)0.7071067811865475244008444;
+    cx<T> a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a[j] = cadd(x[j], x[j + 4]); b[j] = csub(x[j], x[j + 4]); }
+    // b[j] *= W8^j : W8 = (1-i)/sqrt2, W8^2 = -i, W8^3 = (-1-i)/sqrt2
+    { cx<T> t = b[1]; b[1].x = (t.x + t.y) * h; b[1].y = (t.y - t.x) * h; }
+    b[2] = mul_mi(b[2]);
+    { cx<T> t = b[3]; b[3].x = (t.y - t.x) * h; b[3].y = -(t.x + t.y) * h; }
+    Bfly<T, 4>::run(a);
+    Bfly<T, 4>::run(b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { x[2 * k] = a[k]; x[2 * k + 1] = b[k]; }
+  }
+};
+
+// any odd radix (prime or not): half-sum / half-difference form, O(R^2/2)
+template <typename T, int R> struct Bfly {
+  static_assert(R % 2 == 1, "generic butterfly is for odd radices");
+  static IMP_HD void run(cx<T> (&x)[R]) {
+    constexpr int H = (R - 1) / 2;
+    cx<T> a[H], b[H];
+#pragma unroll
+    for (int m = 0; m < H; ++m) { a[m] = cadd(x[m + 1], x[R - 1 - m]); b[m] = csub(x[m + 1], x[R - 1 - m]); }
+    cx<T> x0 = x[0];
+    cx<T> s0 = x0;
+#pragma unroll
+    for (int m = 0; m < H; ++m) s0 = cadd(s0, a[m]);
+    x[0] = s0;
+#pragma unroll
+    for (int k = 1; k <= H; ++k) {
+      cx<T> A = x0, B = mk<T>((T)0, (T)0);
+#pragma unroll
+      for (int m = 1; m <= H; ++m) {
+        const T c = (T)Trig<R>::c((k * m) % R);
+        const T s = (T)Trig<R>::s((k * m) % R);
+        A.x += c * a[m - 1].x; A.y += c * a[m - 1].y;
+        B.x += s * b[m - 1].x; B.y += s * b[m - 1].y;
+      }
+      // y_k = A - i*B ; y_{R-k} = A + i*B
+      x[k] = mk<T>(A.x + B.y, A.y - B.x);
+      x[R - k] = mk<T>(A.x - B.y, A.y + B.x);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+template <typename T> IMP_HD uint32_t phys(const LineJob &J, uint32_t a) {
+  return sizeof(T) == 8 ? swz(a, J.swz_mask) : swz16(a, J.swz_mask);
+}
+
+struct TileCtx {
+  uint64_t tile;     // tile index
+  uint32_t nlines;   // valid lines in this tile (<= C)
+};
+
+IMP_HD TileCtx tile_ctx(const LineJob &J, uint64_t tile) {
+  TileCtx t;
+  t.tile = tile;
+  uint64_t first = tile << J.log_c;
+  uint64_t left = J.n_lines - first;
+  uint64_t c = 1ull << J.log_c;
+  t.nlines = (uint32_t)(left < c ? left : c);
+  return t;
+}
+
+// PROLOG: threads < C compute the global element offsets of their line.
+IMP_HD void phase_prolog(const LineJob &J, const TileCtx &tc, uint32_t tid, int64_t *offs) {
+  if (tid < tc.nlines) {
+    uint64_t l = (tc.tile << J.log_c) + tid;
+    uint64_t i0 = l % J.bdim[0];
+    uint64_t r = l / J.bdim[0];
+    uint64_t i1 = r % J.bdim[1];
+    uint64_t i2 = r / J.bdim[1];
+    offs[2 * tid] = (int64_t)i0 * J.bs_in[0] + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
+    offs[2 * tid + 1] = (int64_t)i0 * J.bs_out[0] + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// LOAD
+// ---------------------------------------------------------------------------
+template <typename T>
+IMP_HD void load_one(const LineJob &J, cx<T> *S /*line base*/, int64_t off, uint32_t e) {
+  const bool cin = J.flags & F_CONJ_IN, cseq = J.flags & F_CONJ_SEQ;
+  const T *inr = (const T *)J.in;
+  const cx<T> *inc = (const cx<T> *)J.in;
+  const int64_t es = J.es_in;
+  switch (J.load_mode) {
+    case LD_C: {
+      cx<T> v = inc[off + (int64_t)e * es];
+      S[phys<T>(J, e)] = cconj_if(v, cin != cseq);
+    } break;
+    case LD_R_PAIRS: {
+      cx<T> v;
+      if (J.flags & F_VEC_IN) {
+        v = *(const cx<T> *)(inr + off + 2 * (int64_t)e);
+      } else {
+        v.x = inr[off + (2 * (int64_t)e) * es];
+        v.y = inr[off + (2 * (int64_t)e + 1) * es];
+      }
+      S[phys<T>(J, e)] = v;
+    } break;
+    case LD_R_ZEROIM: {
+      S[phys<T>(J, e)] = mk<T>(inr[off + (int64_t)e * es], (T)0);
+    } break;
+    case LD_HERM_EVEN: {
+      cx<T> v = inc[off + (int64_t)e * es];
+      if (e == 0 || e == J.n_seq) v.y = (T)0;
+      S[phys<T>(J, e)] = cconj_if(v, cin);  // F_CONJ_SEQ is applied by OP_C2R_PRE_EVEN
+    } break;
+    case LD_HERM_FULL: {
+      cx<T> v = inc[off + (int64_t)e * es];
+      if (e == 0) v.y = (T)0;
+      v = cconj_if(v, cin != cseq);
+      S[phys<T>(J, e)] = v;
+      if (e > 0) S[phys<T>(J, J.n_real - e)] = cconj(v);
+    } break;
+    case LD_HC_EVEN: {
+      cx<T> v;
+      v.x = inr[off + (e == 0 ? 0 : 2 * (int64_t)e - 1) * es];
+      v.y = (e == 0 || e == J.n_seq) ? (T)0 : inr[off + (2 * (int64_t)e) * es];
+      S[phys<T>(J, e)] = cconj_if(v, cin);
+    } break;
+    case LD_HC_FULL: {
+      cx<T> v;
+      v.x = inr[off + (e == 0 ? 0 : 2 * (int64_t)e - 1) * es];
+      v.y = (e == 0) ? (T)0 : inr[off + (2 * (int64_t)e) * es];
+      v = cconj_if(v, cin != cseq);
+      S[phys<T>(J, e)] = v;
+      if (e > 0) S[phys<T>(J, J.n_real - e)] = cconj(v);
+    } break;
+    default: break;
+  }
+}
+
+template <typename T>
+IMP_HD void phase_load(const LineJob &J, const TileCtx &tc, uint32_t tid, uint32_t nthr,
+                       const int64_t *offs, cx<T> *smem) {
+  const uint32_t n = J.n_load;
+  if (J.flags & F_IN_LINES_FAST) {
+    const uint32_t cmask = (1u << J.log_c) - 1;
+    const uint64_t total = (uint64_t)n << J.log_c;
+    for (uint64_t g = tid; g < total; g += nthr) {
+      uint32_t c = (uint32_t)g & cmask, e = (uint32_t)(g >> J.log_c);
+      if (c < tc.nlines) load_one<T>(J, smem + (size_t)c * J.pitch, offs[2 * c], e);
+    }
+  } else {
+    for (uint32_t c = 0; c < tc.nlines; ++c) {
+      cx<T> *S = smem + (size_t)c * J.pitch;
+      const int64_t off = offs[2 * c];
+      for (uint32_t e = tid; e < n; e += nthr) load_one<T>(J, S, off, e);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// radix passes
+// ---------------------------------------------------------------------------
+template <typename T, int IP>
+IMP_HD void pass_radix(const LineJob &J, const Phase &P, uint32_t tid, uint32_t nthr, cx<T> *smem) {
+  const uint32_t ido = P.ido, l1 = P.l1;
+  const uint32_t nb = J.n_fft / IP;
+  const uint32_t cmask = (1u << J.log_c) - 1;
+  const uint32_t total = nb << J.log_c;
+  const cx<T> *tw = (const cx<T> *)J.tw;
+  const bool dit = P.op == OP_PASS_DIT;
+  for (uint32_t g = tid; g < total; g += nthr) {
+    const uint32_t c = g & cmask, b = g >> J.log_c;
+    const uint32_t k = b / ido, i = b - k * ido;
+    const uint32_t base = i + ido * IP * k;
+    cx<T> *S = smem + (size_t)c * J.pitch;
+    cx<T> x[IP];
+#pragma unroll
+    for (int j = 0; j < IP; ++j) x[j] = S[phys<T>(J, base + j * ido)];
+    if (ido > 1) {
+      const uint32_t t1 = i * l1;
+      if (dit) {
+#pragma unroll
+        for (int j = 1; j < IP; ++j) x[j] = cmul(x[j], IMP_LDG(tw + t1 * j));
+        Bfly<T, IP>::run(x);
+      } else {
+        Bfly<T, IP>::run(x);
+#pragma unroll
+        for (int j = 1; j < IP; ++j) x[j] = cmul(x[j], IMP_LDG(tw + t1 * j));
+      }
+    } else {
+      Bfly<T, IP>::run(x);
+    }
+#pragma unroll
+    for (int j = 0; j < IP; ++j) S[phys<T>(J, base + j * ido)] = x[j];
+  }
+}
+
+template <typename T>
+IMP_HD void phase_pass(const LineJob &J, const Phase &P, uint32_t tid, uint32_t nthr, cx<T> *smem) {
+  switch (P.radix) {
+    case 2: pass_radix<T, 2>(J, P, tid, nthr, smem); break;
+    case 3: pass_radix<T, 3>(J, P, tid, nthr, smem); break;
+    case 4: pass_radix<T, 4>(J, P, tid, nthr, smem); break;
+    case 5: pass_radix<T, 5>(J, P, tid, nthr, smem); break;
+    case 7: pass_radix<T, 7>(J, P, tid, nthr, smem); break;
+    case 8: pass_radix<T, 8>(J, P, tid, nthr, smem); break;
+    case 9: pass_radix<T, 9>(J, P, tid, nthr, smem); break;
+    case 11: pass_radix<T, 11>(J, P, tid, nthr, smem); break;
+    case 13: pass_radix<T, 13>(J, P, tid, nthr, smem); break;
+    case 17: pass_radix<T, 17>(J, P, tid, nthr, smem); break;
+    case 19: pass_radix<T, 19>(J, P, tid, nthr, smem); break;
+    case 23: pass_radix<T, 23>(J, P, tid, nthr, smem); break;
+    case 29: pass_radix<T, 29>(J, P, tid, nthr, smem); break;
+    case 31: pass_radix<T, 31>(J, P, tid, nthr, smem); break;
+    default: break;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// element-wise phases (Bluestein, c2r pre-twiddle)
+// ---------------------------------------------------------------------------
+template <typename T>
+IMP_HD void phase_elementwise(const LineJob &J, const Phase &P, uint32_t tid, uint32_t nthr, cx<T> *smem) {
+  const uint32_t cmask = (1u << J.log_c) - 1;
+  const uint32_t L = J.n_seq;
+  uint32_t n;
+  switch (P.op) {
+    case OP_BLUE_PRE: n = J.n_fft; break;
+    case OP_BLUE_MUL: n = J.n_fft; break;
+    case OP_BLUE_POST: n = L; break;
+    case OP_C2R_PRE_EVEN: n = L / 2 + 1; break;
+    default: return;
+  }
+  const uint32_t total = n << J.log_c;
+  const cx<T> *bk = (const cx<T> *)J.bk;
+  const cx<T> *bkf = (const cx<T> *)J.bkf;
+  const cx<T> *twr = (const cx<T> *)J.tw_r;
+  for (uint32_t g = tid; g < total; g += nthr) {
+    const uint32_t c = g & cmask, e = g >> J.log_c;
+    cx<T> *S = smem + (size_t)c * J.pitch;
+    switch (P.op) {
+      case OP_BLUE_PRE: {
+        const uint32_t p = phys<T>(J, e);
+        S[p] = e < L ? cmul(S[p], cconj(IMP_LDG(bk + e))) : mk<T>((T)0, (T)0);
+      } break;
+      case OP_BLUE_MUL: {
+        const uint32_t p = phys<T>(J, e);
+        S[p] = cconj(cmul(S[p], IMP_LDG(bkf + e)));
+      } break;
+      case OP_BLUE_POST: {
+        const uint32_t p = phys<T>(J, e);
+        S[p] = cconj(cmul(S[p], IMP_LDG(bk + e)));
+      } break;
+      case OP_C2R_PRE_EVEN: {
+        // X[0..M] -> Z[k] = (X[k]+conj X[M-k]) + i e^{+2 pi i k/N} (X[k]-conj X[M-k])
+        const uint32_t M = L, k = e, km = M - k;
+        const uint32_t pk = phys<T>(J, k), pm = phys<T>(J, km);
+        const cx<T> a = S[pk], b = S[pm];
+        const cx<T> w = cconj(IMP_LDG(twr + k));  // e^{+2 pi i k/N}
+        const bool cs = J.flags & F_CONJ_SEQ;
+        {
+          const cx<T> s = cadd(a, cconj(b)), d = csub(a, cconj(b));
+          const cx<T> z = cadd(s, mul_pi(cmul(w, d)));
+          S[pk] = cconj_if(z, cs);
+        }
+        if (k != 0 && k != km) {
+          const cx<T> s = cadd(b, cconj(a)), d = csub(b, cconj(a));
+          // e^{+2 pi i (M-k)/N} = -conj(w)
+          const cx<T> wm = mk<T>(-w.x, w.y);
+          const cx<T> z = cadd(s, mul_pi(cmul(wm, d)));
+          S[pm] = cconj_if(z, cs);
+        }
+      } break;
+      default: break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// STORE
+// ---------------------------------------------------------------------------
+template <typename T>
+IMP_HD cx<T> read_bin(const LineJob &J, const cx<T> *S, uint32_t k) {
+  const uint32_t p = J.perm ? IMP_LDG(J.perm + k) : k;
+  return cconj_if(S[phys<T>(J, p)], (J.flags & F_CONJ_OUT) != 0);
+}
+
+// bin k (0..M) of the even-N real transform from the M-point FFT Z of the packed line
+template <typename T>
+IMP_HD cx<T> r2c_even_bin(const LineJob &J, const cx<T> *S, uint32_t k) {
+  const uint32_t M = J.n_seq;
+  const cx<T> a = read_bin<T>(J, S, k == M ? 0 : k);
+  const cx<T> b = cconj(read_bin<T>(J, S, k == 0 ? 0 : M - k));
+  const T h = (T)0.5;
+  const cx<T> E = mk<T>((a.x + b.x) * h, (a.y + b.y) * h);
+  const cx<T> D = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
+  const cx<T> O = mul_mi(D);
+  const cx<T> w = IMP_LDG((const cx<T> *)J.tw_r + k);
+  return cadd(E, cmul(w, O));
+}
+
+template <typename T>
+IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e) {
+  T *outr = (T *)J.out;
+  cx<T> *outc = (cx<T> *)J.out;
+  const int64_t es = J.es_out;
+  const T f = (T)J.fct;
+  const bool cres = J.flags & F_CONJ_RESULT;
+  switch (J.store_mode) {
+    case ST_C:
+    case ST_HERM_HALF: {
+      cx<T> v = read_bin<T>(J, S, e);
+      v.x *= f; v.y *= f;
+      outc[off + (int64_t)e * es] = cconj_if(v, cres);
+    } break;
+    case ST_HERM_SYM: {
+      cx<T> v = read_bin<T>(J, S, e);
+      v.x *= f; v.y *= f;
+      v = cconj_if(v, cres);
+      outc[off + (int64_t)e * es] = v;
+      if (e > 0) outc[off + (int64_t)(J.n_real - e) * es] = cconj(v);
+    } break;
+    case ST_R2C_EVEN: {
+      cx<T> v = r2c_even_bin<T>(J, S, e);
+      v.x *= f; v.y *= f;
+      outc[off + (int64_t)e * es] = cconj_if(v, cres);
+    } break;
+    case ST_R2C_EVEN_SYM: {
+      cx<T> v = r2c_even_bin<T>(J, S, e);
+      v.x *= f; v.y *= f;
+      v = cconj_if(v, cres);
+      outc[off + (int64_t)e * es] = v;
+      if (e > 0 && e < J.n_seq) outc[off + (int64_t)(J.n_real - e) * es] = cconj(v);
+    } break;
+    case ST_R_PAIRS: {
+      cx<T> v = read_bin<T>(J, S, e);
+      v.x *= f; v.y *= f;
+      if (J.flags & F_VEC_OUT) {
+        *(cx<T> *)(outr + off + 2 * (int64_t)e) = v;
+      } else {
+        outr[off + (2 * (int64_t)e) * es] = v.x;
+        outr[off + (2 * (int64_t)e + 1) * es] = v.y;
+      }
+    } break;
+    case ST_R_REALPART: {
+      outr[off + (int64_t)e * es] = read_bin<T>(J, S, e).x * f;
+    } break;
+    case ST_HC_EVEN: {
+      cx<T> v = r2c_even_bin<T>(J, S, e);
+      v.x *= f; v.y *= f;
+      if (e == 0) outr[off] = v.x;
+      else if (e == J.n_seq) outr[off + (int64_t)(J.n_real - 1) * es] = v.x;
+      else { outr[off + (2 * (int64_t)e - 1) * es] = v.x; outr[off + (2 * (int64_t)e) * es] = v.y; }
+    } break;
+    case ST_HC_FULL: {
+      cx<T> v = read_bin<T>(J, S, e);
+      v.x *= f; v.y *= f;
+      if (e == 0) outr[off] = v.x;
+      else { outr[off + (2 * (int64_t)e - 1) * es] = v.x; outr[off + (2 * (int64_t)e) * es] = v.y; }
+    } break;
+    default: break;
+  }
+}
+
+template <typename T>
+IMP_HD void phase_store(const LineJob &J, const TileCtx &tc, uint32_t tid, uint32_t nthr,
+                        const int64_t *offs, const cx<T> *smem) {
+  const uint32_t n = J.n_store;
+  if (J.flags & F_OUT_LINES_FAST) {
+    const uint32_t cmask = (1u << J.log_c) - 1;
+    const uint64_t total = (uint64_t)n << J.log_c;
+    for (uint64_t g = tid; g < total; g += nthr) {
+      uint32_t c = (uint32_t)g & cmask, e = (uint32_t)(g >> J.log_c);
+      if (c < tc.nlines) store_one<T>(J, smem + (size_t)c * J.pitch, offs[2 * c + 1], e);
+    }
+  } else {
+    for (uint32_t c = 0; c < tc.nlines; ++c) {
+      const cx<T> *S = smem + (size_t)c * J.pitch;
+      const int64_t off = offs[2 * c + 1];
+      for (uint32_t e = tid; e < n; e += nthr) store_one<T>(J, S, off, e);
+    }
+  }
+}
+
+// One middle phase (everything between LOAD and STORE).
+template <typename T>
+IMP_HD void phase_mid(const LineJob &J, const Phase &P, uint32_t tid, uint32_t nthr, cx<T> *smem) {
+  if (P.op == OP_PASS_DIF || P.op == OP_PASS_DIT) phase_pass<T>(J, P, tid, nthr, smem);
+  else phase_elementwise<T>(J, P, tid, nthr, smem);
+}
+
+}  // namespace impulse

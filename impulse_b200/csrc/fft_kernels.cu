@@ -1,0 +1,55 @@
+// sm_100a kernels of the generic engine: the CTA-level driver around the phase functions of
+// fft_device.cuh, and the launcher used by abi.cu.
+//
+// Per tile of C lines: PROLOG (line offsets) | LOAD global->smem | radix passes and
+// element-wise phases in smem | STORE smem->global, one __syncthreads() between phases.
+// All HBM traffic is one coalesced read and one coalesced write per element; everything in
+// between lives in shared memory (up to 227 KB per CTA on B200).
+#include <cuda_runtime.h>
+
+#include "fft_device.cuh"
+#include "fft_kernels.h"
+
+namespace impulse {
+
+template <typename T>
+__global__ void __launch_bounds__(kMaxThreads)
+line_fft_kernel(const __grid_constant__ LineJob J) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int64_t *offs = reinterpret_cast<int64_t *>(smem_raw);
+  cx<T> *smem = reinterpret_cast<cx<T> *>(smem_raw + kSmemHeaderBytes);
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  const uint64_t n_tiles = (J.n_lines + (1ull << J.log_c) - 1) >> J.log_c;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const TileCtx tc = tile_ctx(J, tile);
+    phase_prolog(J, tc, tid, offs);
+    __syncthreads();
+    phase_load<T>(J, tc, tid, nthr, offs, smem);
+    __syncthreads();
+    for (int p = 0; p < J.nphases; ++p) {
+      phase_mid<T>(J, J.ph[p], tid, nthr, smem);
+      __syncthreads();
+    }
+    phase_store<T>(J, tc, tid, nthr, offs, smem);
+    __syncthreads();
+  }
+}
+
+int configure_kernels(size_t max_dyn_smem) {
+  cudaError_t e = cudaFuncSetAttribute(line_fft_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)max_dyn_smem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(line_fft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn_smem);
+  return (int)e;
+}
+
+int launch_line_job(const LineJob &J, int threads, size_t smem_bytes, uint64_t n_tiles, void *stream) {
+  if (n_tiles == 0) return 0;
+  const unsigned grid = (unsigned)(n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (J.dtype == 1) line_fft_kernel<double><<<grid, threads, smem_bytes, s>>>(J);
+  else line_fft_kernel<float><<<grid, threads, smem_bytes, s>>>(J);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace impulse

@@ -1,0 +1,19 @@
+// Launcher interface between the ABI layer (abi.cu) and the kernels (fft_kernels.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "fft_types.h"
+
+namespace impulse {
+// raise the dynamic shared-memory limit of every kernel (once per device); returns cudaError_t
+int configure_kernels(size_t max_dyn_smem);
+// enqueue one LineJob on `stream` (a cudaStream_t); returns cudaError_t
+int launch_line_job(const LineJob &job, int threads, size_t smem_bytes, uint64_t n_tiles, void *stream);
+// out[b][i] = a[b][i] * f[i] * scale over complex arrays (i < n_inner, b < n_batch)
+int launch_cmul(int dtype, const void *a, const void *f, void *out, size_t n_inner, size_t n_batch, double scale,
+                int sm_count, void *stream);
+// out[b][c][r] = in[b][r][c], complex elements, leading dimensions in elements
+int launch_transpose(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
+                     size_t batch, int sm_count, void *stream);
+}  // namespace impulse

@@ -1,0 +1,118 @@
+// Shared host/device description of one batched line-FFT launch ("LineJob").
+//
+// A LineJob is a small phase program interpreted by every CTA of the generic engine
+// (fft_device.cuh): LOAD a tile of `C` lines into shared memory, run in-place radix
+// passes (and the Bluestein / real pre- and post-steps) there, STORE the tile.
+// The host planner (planner.cpp) builds it; the kernel receives it by value as a
+// __grid_constant__ parameter.
+//
+// Replaces, for the GPU, the reference's plan structs cfftp_plan_i / rfftp_plan_i /
+// fftblue_plan_i (c_pocketfft/pocketfft.c:267-279, 1060-1072, 1880-1887) and the
+// per-axis line iteration of general_nd (cpp_pocketfft/pocketfft_hdronly.h:3011-3050).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define IMP_HD __host__ __device__ __forceinline__
+#else
+#define IMP_HD inline
+#endif
+
+namespace impulse {
+
+constexpr int kMaxPhases = 40;
+constexpr int kMaxBatchDims = 3;
+constexpr int kSmemHeaderBytes = 1024;  // per-line global offsets (2 x int64 x 64 lines)
+constexpr int kMaxLinesPerCta = 64;
+constexpr int kMaxThreads = 512;
+constexpr uint32_t kMaxGenericRadix = 31;  // odd prime radices up to this are direct; above -> Bluestein
+
+enum PhaseOp : uint8_t {
+  OP_PASS_DIF = 1,      // in-place decimation-in-frequency radix pass (natural in -> digit-reversed out)
+  OP_PASS_DIT = 2,      // transposed pass (digit-reversed in -> natural out)
+  OP_BLUE_PRE = 3,      // s[n] = s[n]*conj(bk[n]) (n<L), 0 (L<=n<n_fft)        pocketfft.c:1954-1968
+  OP_BLUE_MUL = 4,      // s[p] = conj(s[p]*bkf[p])                              pocketfft.c:1973-1987
+  OP_BLUE_POST = 5,     // s[k] = conj(s[k]*bk[k]) (k<L)                         pocketfft.c:1993-2005
+  OP_C2R_PRE_EVEN = 6,  // half-spectrum X[0..M] -> packed complex Z[0..M-1]
+};
+
+enum LoadMode : uint8_t {
+  LD_C = 0,          // complex line, n_seq elements
+  LD_R_PAIRS = 1,    // even-N real line viewed as N/2 complex (x[2m], x[2m+1])
+  LD_R_ZEROIM = 2,   // real line as complex with zero imaginary part
+  LD_HERM_EVEN = 3,  // c2r even N: X[0..N/2] verbatim (imag of bins 0 and N/2 dropped)
+  LD_HERM_FULL = 4,  // c2r odd N: X[0..(N-1)/2] Hermitian-extended to N complex
+  LD_HC_EVEN = 5,    // FFTPACK halfcomplex reals -> X[0..N/2]   (pocketfft.nim:228-238)
+  LD_HC_FULL = 6,    // FFTPACK halfcomplex reals -> Hermitian-extended N complex
+};
+
+enum StoreMode : uint8_t {
+  ST_C = 0,          // complex line, N elements
+  ST_HERM_HALF = 1,  // bins 0..N/2 of a length-N complex result (odd-N r2c)
+  ST_R2C_EVEN = 2,   // even-N r2c: bins 0..N/2 from the N/2-point complex FFT + post-twiddle
+  ST_R_PAIRS = 3,    // c2r even: z[m] -> x[2m], x[2m+1]
+  ST_R_REALPART = 4, // c2r odd: real parts
+  ST_HC_EVEN = 5,    // even-N r2c written as FFTPACK halfcomplex reals
+  ST_HC_FULL = 6,    // odd-N r2c written as FFTPACK halfcomplex reals
+  ST_R2C_EVEN_SYM = 7,   // even-N r2c, all N bins (Hermitian half + conjugate mirror): fused `symmetrize`
+  ST_HERM_SYM = 8,       // odd-N r2c, all N bins                                   (pocketfft.nim:160-171)
+};
+
+enum JobFlags : uint32_t {
+  F_CONJ_IN = 1u << 0,      // conjugate values as read from global (c2r with forward=true)
+  F_CONJ_SEQ = 1u << 1,     // conjugate the sequence placed in smem (backward via conj trick)
+  F_CONJ_OUT = 1u << 2,     // conjugate the FFT result as read from smem (backward via conj trick)
+  F_CONJ_RESULT = 1u << 3,  // conjugate the stored spectrum (r2c with forward=false)
+  F_IN_LINES_FAST = 1u << 4,   // global reads: consecutive threads walk adjacent lines (strided axis)
+  F_OUT_LINES_FAST = 1u << 5,  // global writes: same
+  F_VEC_IN = 1u << 6,       // LD_R_PAIRS may use one 2-element vector load
+  F_VEC_OUT = 1u << 7,      // ST_R_PAIRS may use one 2-element vector store
+};
+
+struct Phase {
+  uint8_t op;
+  uint8_t radix;
+  uint16_t pad;
+  uint32_t l1;
+  uint32_t ido;
+};
+
+struct LineJob {
+  // lengths
+  uint32_t n_fft;    // complex FFT length run in shared memory (n2 for Bluestein)
+  uint32_t n_seq;    // logical complex sequence length L (N, or N/2 for even real)
+  uint32_t n_real;   // real length N (real transforms) or L
+  uint32_t n_load;   // element slots iterated by LOAD per line
+  uint32_t n_store;  // element slots iterated by STORE per line
+  // tile geometry
+  uint32_t log_c;      // lines per CTA = 1 << log_c
+  uint32_t pitch;      // shared-memory elements per line
+  uint32_t swz_mask;   // 0, 7 (16-byte elements) or 15 (8-byte elements)
+  uint32_t flags;
+  uint8_t load_mode, store_mode, dtype /*0=f32,1=f64*/, nphases;
+  uint64_t n_lines;
+  // line index -> global offset (elements of the respective side's element type)
+  uint64_t bdim[kMaxBatchDims];
+  int64_t bs_in[kMaxBatchDims], bs_out[kMaxBatchDims];
+  int64_t es_in, es_out;
+  const void *in;
+  void *out;
+  // tables (device pointers owned by the plan cache)
+  const void *tw;          // exp(-2*pi*i*m/n_fft), m < n_fft
+  const uint32_t *perm;    // position of frequency k after the DIF passes; null = identity
+  const void *tw_r;        // exp(-2*pi*i*k/N), k <= N/2 (even real transforms)
+  const void *bk;          // exp(+i*pi*n^2/L), n < L
+  const void *bkf;         // FFT_{n_fft}(wrapped bk)/n_fft at digit-reversed positions
+  double fct;
+  Phase ph[kMaxPhases];
+};
+
+// shared-memory position of logical index a within a line
+IMP_HD uint32_t swz(uint32_t a, uint32_t mask) {
+  return a ^ (((a >> 3) ^ (a >> 6) ^ (a >> 9) ^ (a >> 12)) & mask);
+}
+IMP_HD uint32_t swz16(uint32_t a, uint32_t mask) {
+  return a ^ (((a >> 4) ^ (a >> 8) ^ (a >> 12)) & mask);
+}
+
+}  // namespace impulse

@@ -1,0 +1,529 @@
+// Host planner implementation.  See planner.h for the reference counterparts.
+#include "planner.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdlib>
+#include <cstring>
+
+namespace impulse {
+
+namespace {
+
+using ld = long double;
+using cld = std::complex<long double>;
+
+// exp(+2*pi*i*m/n) in long double with exact octant reduction (the job of
+// sincos_2pibyn, pocketfft.c:36-203 / pocketfft_hdronly.h:277-349).
+cld unit_root(uint64_t m, uint64_t n) {
+  static const ld PI = 3.141592653589793238462643383279502884L;
+  m %= n;
+  const uint64_t m8 = 8 * m, oct = m8 / n, rem = m8 - oct * n;
+  const ld xa = 2 * PI * (ld)rem / (8 * (ld)n);
+  const ld xb = 2 * PI * (ld)(n - rem) / (8 * (ld)n);
+  switch (oct) {
+    default:
+    case 0: return cld(cosl(xa), sinl(xa));
+    case 1: return cld(sinl(xb), cosl(xb));
+    case 2: return cld(-sinl(xa), cosl(xa));
+    case 3: return cld(-cosl(xb), sinl(xb));
+    case 4: return cld(-cosl(xa), -sinl(xa));
+    case 5: return cld(-sinl(xb), -cosl(xb));
+    case 6: return cld(sinl(xa), -cosl(xa));
+    case 7: return cld(cosl(xb), -sinl(xb));
+  }
+}
+
+template <typename T> void *upload_cplx(TableAlloc *a, const std::vector<cld> &v) {
+  std::vector<T> h(2 * v.size());
+  for (size_t i = 0; i < v.size(); ++i) { h[2 * i] = (T)v[i].real(); h[2 * i + 1] = (T)v[i].imag(); }
+  return a->upload(h.data(), h.size() * sizeof(T));
+}
+
+void *upload_cplx(TableAlloc *a, const std::vector<cld> &v, int dtype) {
+  return dtype == DT_F64 ? upload_cplx<double>(a, v) : upload_cplx<float>(a, v);
+}
+
+// plan-time forward FFT in long double (Stockham, generic radix) — used once per Bluestein
+// plan to transform the chirp (pocketfft.c:1916-1931 does this with its own cfftp_forward).
+void host_fft(std::vector<cld> &x, const std::vector<uint32_t> &radices) {
+  const size_t n = x.size();
+  std::vector<cld> w(n), y(n);
+  for (size_t m = 0; m < n; ++m) w[m] = std::conj(unit_root(m, n));
+  size_t l1 = 1;
+  cld *p1 = x.data(), *p2 = y.data();
+  for (uint32_t ip : radices) {
+    const size_t ido = n / (l1 * ip), step = n / ip;
+    for (size_t k = 0; k < l1; ++k)
+      for (size_t i = 0; i < ido; ++i)
+        for (size_t jo = 0; jo < ip; ++jo) {
+          cld s = 0;
+          for (size_t j = 0; j < ip; ++j) s += p1[i + ido * (j + ip * k)] * w[((j * jo) % ip) * step];
+          p2[i + ido * (k + l1 * jo)] = s * w[i * jo * l1];
+        }
+    std::swap(p1, p2);
+    l1 *= ip;
+  }
+  if (p1 != x.data()) std::copy(p1, p1 + n, x.data());
+}
+
+uint32_t pow2floor(uint64_t v) {
+  uint32_t r = 1;
+  while ((uint64_t)r * 2 <= v) r *= 2;
+  return r;
+}
+uint32_t pow2ceil(uint64_t v) {
+  uint32_t r = 1;
+  while (r < v) r *= 2;
+  return r;
+}
+uint32_t ilog2(uint32_t v) {
+  uint32_t l = 0;
+  while ((1u << l) < v) ++l;
+  return l;
+}
+int env_int(const char *name, int dflt) {
+  const char *s = std::getenv(name);
+  return s && *s ? std::atoi(s) : dflt;
+}
+
+}  // namespace
+
+// Radix schedule for the GPU: 9s and 3s, 5s, 7s, other odd primes <= 31, then the power of
+// two as 8s with a 4 / 4,4 / 2 tail.  pocketfft factors into 4s, a 2, odd primes
+// (pocketfft.c:953-983); only results have to agree, the schedule is free.
+std::vector<uint32_t> choose_radices(uint32_t L) {
+  std::vector<uint32_t> odd, two;
+  uint32_t n = L, e = 0;
+  while (n % 2 == 0) { n /= 2; ++e; }
+  uint32_t threes = 0;
+  while (n % 3 == 0) { n /= 3; ++threes; }
+  for (; threes >= 2; threes -= 2) odd.push_back(9);
+  if (threes) odd.push_back(3);
+  for (uint32_t p = 5; p <= kMaxGenericRadix; p += 2) {
+    bool prime = true;
+    for (uint32_t q = 3; q * q <= p; q += 2) if (p % q == 0) prime = false;
+    if (!prime) continue;
+    while (n % p == 0) { n /= p; odd.push_back(p); }
+  }
+  if (n != 1) return {};  // large prime factor -> Bluestein
+  if (e == 1) two = {2};
+  else if (e == 2) two = {4};
+  else if (e >= 3) {
+    uint32_t n8 = e / 3, rem = e % 3;
+    if (rem == 1) { n8 -= 1; two.assign(n8, 8); two.push_back(4); two.push_back(4); }
+    else { two.assign(n8, 8); if (rem == 2) two.push_back(4); }
+  }
+  std::vector<uint32_t> r = odd;
+  r.insert(r.end(), two.begin(), two.end());
+  return r;
+}
+
+uint32_t bluestein_size(uint32_t L) {
+  const uint64_t need = 2 * (uint64_t)L - 1;
+  uint64_t best = ~0ull;
+  for (uint64_t f2 = 1; f2 < 4 * need; f2 *= 2)
+    for (uint64_t f3 = f2; f3 < 4 * need; f3 *= 3)
+      for (uint64_t f5 = f3; f5 < 4 * need; f5 *= 5)
+        for (uint64_t f7 = f5; f7 < 4 * need; f7 *= 7)
+          if (f7 >= need && f7 < best) best = f7;
+  return (uint32_t)best;
+}
+
+// pos_of_k: shared-memory position of frequency k after the in-place DIF passes.
+// With k = k1 + R1*(k2 + R2*(...)) the position is k1*(n/R1) + k2*(n/(R1*R2)) + ...
+std::vector<uint32_t> dif_positions(uint32_t n, const std::vector<uint32_t> &radices) {
+  std::vector<uint32_t> pos(n);
+  for (uint32_t k = 0; k < n; ++k) {
+    uint32_t kk = k, span = n, p = 0;
+    for (uint32_t r : radices) {
+      span /= r;
+      p += (kk % r) * span;
+      kk /= r;
+    }
+    pos[k] = p;
+  }
+  return pos;
+}
+
+PlanCache::~PlanCache() {
+  for (auto &kv : engines_) {
+    Engine1D *e = kv.second.get();
+    for (void *p : {e->d_tw, e->d_perm, e->d_bk, e->d_bkf}) if (p) alloc_->release(p);
+  }
+  for (auto &kv : real_tw_) if (kv.second) alloc_->release(kv.second);
+}
+
+int PlanCache::status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto key = std::make_pair(L, dtype);
+  auto it = engines_.find(key);
+  if (it != engines_.end()) { *out = it->second.get(); return ST_OK; }
+  if (L == 0) { *err = "zero-length transform"; return ERR_INVALID; }
+  std::unique_ptr<Engine1D> e(new Engine1D);
+  e->L = L;
+  e->radices = choose_radices(L);
+  e->blue = (L > 1 && e->radices.empty());
+  e->n_fft = L;
+  if (e->blue) {
+    e->n_fft = bluestein_size(L);
+    e->radices = choose_radices(e->n_fft);
+  }
+  const uint32_t n = e->n_fft;
+  std::vector<cld> tw(n);
+  for (uint32_t m = 0; m < n; ++m) tw[m] = std::conj(unit_root(m, n));
+  e->d_tw = upload_cplx(alloc_, tw, dtype);
+  if (!e->d_tw) { *err = "table upload failed"; return ERR_NOMEM; }
+  std::vector<uint32_t> pos = dif_positions(n, e->radices);
+  if (!e->blue) {
+    e->d_perm = alloc_->upload(pos.data(), pos.size() * sizeof(uint32_t));
+    if (!e->d_perm) { *err = "table upload failed"; return ERR_NOMEM; }
+  } else {
+    // b_k = exp(i*pi*k^2/L): k^2 mod 2L by the recurrence of pocketfft.c:1907-1914
+    std::vector<cld> bk(L), bw(n, cld(0, 0));
+    uint64_t coeff = 0;
+    for (uint32_t m = 0; m < L; ++m) {
+      if (m > 0) { coeff += 2 * (uint64_t)m - 1; if (coeff >= 2 * (uint64_t)L) coeff -= 2 * (uint64_t)L; }
+      bk[m] = unit_root(coeff, 2 * (uint64_t)L);
+    }
+    const ld xn2 = 1.0L / (ld)n;
+    bw[0] = bk[0] * xn2;
+    for (uint32_t m = 1; m < L; ++m) bw[m] = bw[n - m] = bk[m] * xn2;
+    host_fft(bw, e->radices);
+    std::vector<cld> bkf(n);
+    for (uint32_t k = 0; k < n; ++k) bkf[pos[k]] = bw[k];
+    e->d_bk = upload_cplx(alloc_, bk, dtype);
+    e->d_bkf = upload_cplx(alloc_, bkf, dtype);
+    if (!e->d_bk || !e->d_bkf) { *err = "table upload failed"; return ERR_NOMEM; }
+  }
+  *out = e.get();
+  engines_[key] = std::move(e);
+  return ST_OK;
+}
+
+int PlanCache::real_twiddle(uint32_t N, int dtype, const void **out, std::string *err) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto key = std::make_pair(N, dtype);
+  auto it = real_tw_.find(key);
+  if (it != real_tw_.end()) { *out = it->second; return ST_OK; }
+  std::vector<cld> w(N / 2 + 1);
+  for (uint32_t k = 0; k <= N / 2; ++k) w[k] = std::conj(unit_root(k, N));
+  void *d = upload_cplx(alloc_, w, dtype);
+  if (!d) { *err = "table upload failed"; return ERR_NOMEM; }
+  real_tw_[key] = d;
+  *out = d;
+  return ST_OK;
+}
+
+int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std::string *err) {
+  std::memset(J, 0, sizeof(*J));
+  const uint32_t N = s.N;
+  if (N == 0) { *err = "zero-length transform"; return ERR_INVALID; }
+  const bool f64 = s.dtype == DT_F64;
+  const bool even = (N % 2) == 0;
+  uint32_t L = N;
+  if (s.kind != KIND_C2C && even) L = N / 2;
+  const Engine1D *E = nullptr;
+  int rc = status_engine(L, s.dtype, &E, err);
+  if (rc) return rc;
+
+  J->n_fft = E->n_fft;
+  J->n_seq = L;
+  J->n_real = N;
+  J->dtype = (uint8_t)s.dtype;
+  J->tw = E->d_tw;
+  J->perm = E->blue ? nullptr : (const uint32_t *)E->d_perm;
+  J->bk = E->d_bk;
+  J->bkf = E->d_bkf;
+  J->fct = 1.0;
+  J->es_in = s.es_in;
+  J->es_out = s.es_out;
+  uint64_t n_lines = 1;
+  for (int d = 0; d < kMaxBatchDims; ++d) {
+    J->bdim[d] = s.bdim[d] ? s.bdim[d] : 1;
+    J->bs_in[d] = s.bs_in[d];
+    J->bs_out[d] = s.bs_out[d];
+    n_lines *= J->bdim[d];
+  }
+  J->n_lines = n_lines;
+
+  uint32_t need = E->n_fft;  // shared-memory element slots per line
+  uint32_t flags = 0;
+  std::vector<Phase> pre;
+  switch (s.kind) {
+    case KIND_C2C:
+      J->load_mode = LD_C; J->store_mode = ST_C;
+      J->n_load = N; J->n_store = N;
+      if (!s.forward) flags |= F_CONJ_SEQ | F_CONJ_OUT;
+      break;
+    case KIND_R2C:
+      if (even) {
+        J->load_mode = LD_R_PAIRS; J->n_load = L; J->n_store = L + 1;
+        J->store_mode = s.layout == RL_HALFCOMPLEX ? ST_HC_EVEN : s.layout == RL_FULLSYM ? ST_R2C_EVEN_SYM : ST_R2C_EVEN;
+        rc = real_twiddle(N, s.dtype, &J->tw_r, err);
+        if (rc) return rc;
+      } else {
+        J->load_mode = LD_R_ZEROIM; J->n_load = N; J->n_store = (N + 1) / 2;
+        J->store_mode = s.layout == RL_HALFCOMPLEX ? ST_HC_FULL : s.layout == RL_FULLSYM ? ST_HERM_SYM : ST_HERM_HALF;
+      }
+      if (!s.forward) flags |= F_CONJ_RESULT;
+      break;
+    case KIND_C2R:
+      flags |= F_CONJ_SEQ | F_CONJ_OUT;
+      if (s.forward) flags |= F_CONJ_IN;
+      if (even) {
+        J->load_mode = s.layout == RL_HALFCOMPLEX ? LD_HC_EVEN : LD_HERM_EVEN;
+        J->n_load = L + 1; J->n_store = L; J->store_mode = ST_R_PAIRS;
+        need = std::max(need, L + 1);
+        rc = real_twiddle(N, s.dtype, &J->tw_r, err);
+        if (rc) return rc;
+        Phase p{}; p.op = OP_C2R_PRE_EVEN; pre.push_back(p);
+      } else {
+        J->load_mode = s.layout == RL_HALFCOMPLEX ? LD_HC_FULL : LD_HERM_FULL;
+        J->n_load = (N + 1) / 2; J->n_store = N; J->store_mode = ST_R_REALPART;
+      }
+      if (s.layout == RL_FULLSYM) { *err = "FULLSYM layout is an r2c output layout"; return ERR_INVALID; }
+      break;
+    default: *err = "bad transform kind"; return ERR_INVALID;
+  }
+
+  // strided-axis detection: walk adjacent lines with consecutive threads when the fastest
+  // batch dimension is closer in memory than consecutive elements of a line
+  auto lines_fast = [&](int64_t es, int64_t bs0, uint64_t b0) {
+    if (b0 <= 1) return false;
+    return std::llabs(bs0) < std::llabs(es) || es == 0;
+  };
+  const bool in_lf = lines_fast(s.es_in, s.bs_in[0], J->bdim[0]);
+  const bool out_lf = lines_fast(s.es_out, s.bs_out[0], J->bdim[0]);
+  if (in_lf) flags |= F_IN_LINES_FAST;
+  if (out_lf) flags |= F_OUT_LINES_FAST;
+
+  // phase program
+  std::vector<Phase> prog = pre;
+  auto add_passes = [&](bool dit) {
+    const uint32_t n = E->n_fft;
+    std::vector<Phase> ps;
+    uint32_t l1 = 1;
+    for (uint32_t r : E->radices) {
+      Phase p{}; p.op = dit ? OP_PASS_DIT : OP_PASS_DIF; p.radix = (uint8_t)r; p.l1 = l1; p.ido = n / (l1 * r);
+      ps.push_back(p);
+      l1 *= r;
+    }
+    if (dit) std::reverse(ps.begin(), ps.end());
+    prog.insert(prog.end(), ps.begin(), ps.end());
+  };
+  if (E->blue) {
+    Phase p{}; p.op = OP_BLUE_PRE; prog.push_back(p);
+    add_passes(false);
+    p.op = OP_BLUE_MUL; prog.push_back(p);
+    add_passes(true);
+    p.op = OP_BLUE_POST; prog.push_back(p);
+  } else {
+    add_passes(false);
+  }
+  if (prog.size() > (size_t)kMaxPhases) { *err = "phase program too long"; return ERR_UNSUPPORTED; }
+  J->nphases = (uint8_t)prog.size();
+  for (size_t i = 0; i < prog.size(); ++i) J->ph[i] = prog[i];
+
+  // tile geometry
+  const uint32_t S = f64 ? 8 : 16;               // elements per 128-byte shared-memory row
+  const size_t esz = f64 ? 16 : 8;
+  const size_t budget = max_smem - kSmemHeaderBytes;
+  auto pitch_for = [&](uint32_t C) { return ((need + S - 1) / S) * S + (C > 1 ? 1 : 0); };
+  uint32_t target = f64 ? 4096 : 8192;
+  uint32_t C = pow2floor(std::max<uint64_t>(1, target / need));
+  if (in_lf || out_lf) C = std::max(C, S);
+  int envC = env_int("IMPULSE_FFT_LINES", 0);
+  if (envC > 0) C = pow2floor((uint64_t)envC);
+  C = std::min<uint32_t>(C, kMaxLinesPerCta);
+  while (C > 1 && (size_t)C * pitch_for(C) * esz > budget) C /= 2;
+  if ((size_t)C * pitch_for(C) * esz > budget) {
+    *err = "line of " + std::to_string(E->n_fft) + " points does not fit in shared memory (four-step path not built yet)";
+    return ERR_UNSUPPORTED;
+  }
+  C = std::min<uint32_t>(C, pow2ceil(n_lines));
+  J->log_c = ilog2(C);
+  J->pitch = pitch_for(C);
+  J->swz_mask = (C < S) ? (S - 1) : 0;
+  int threads = (int)std::min<uint64_t>(kMaxThreads, std::max<uint64_t>(64, (((uint64_t)C * E->n_fft / 8) + 31) / 32 * 32));
+  int envT = env_int("IMPULSE_FFT_THREADS", 0);
+  if (envT > 0) threads = std::min(kMaxThreads, (envT + 31) / 32 * 32);
+  cfg->threads = threads;
+  cfg->smem_bytes = kSmemHeaderBytes + (size_t)C * J->pitch * esz;
+  cfg->n_tiles = (n_lines + C - 1) / C;
+
+  // vector access for the packed-real sides (pointer alignment is re-checked at execute time)
+  auto all_even = [&](const int64_t *bs) {
+    for (int d = 0; d < kMaxBatchDims; ++d) if (J->bdim[d] > 1 && (bs[d] % 2) != 0) return false;
+    return true;
+  };
+  if (J->load_mode == LD_R_PAIRS && s.es_in == 1 && all_even(s.bs_in)) flags |= F_VEC_IN;
+  if (J->store_mode == ST_R_PAIRS && s.es_out == 1 && all_even(s.bs_out)) flags |= F_VEC_OUT;
+  J->flags = flags;
+  return ST_OK;
+}
+
+// ---------------------------------------------------------------------------
+// N-D driver
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Dim { uint64_t n; int64_t sin, sout; };
+
+// byte span [lo, hi) touched by an array relative to its base pointer
+void span_of(const std::vector<size_t> &shape, const std::vector<ptrdiff_t> &stride, size_t esz,
+             ptrdiff_t *lo, ptrdiff_t *hi) {
+  ptrdiff_t l = 0, h = 0;
+  for (size_t d = 0; d < shape.size(); ++d) {
+    ptrdiff_t ext = (ptrdiff_t)(shape[d] - 1) * stride[d];
+    if (ext < 0) l += ext; else h += ext;
+  }
+  *lo = l;
+  *hi = h + (ptrdiff_t)esz;
+}
+
+}  // namespace
+
+int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
+  plan->desc = d;
+  plan->steps.clear();
+  plan->tmp_bytes = 0;
+  const size_t nd = d.shape.size();
+  // sanity_check (pocketfft_hdronly.h:446-476)
+  if (nd < 1) { *err = "ndim must be >= 1"; return ERR_INVALID; }
+  if (d.stride_in.size() != nd || d.stride_out.size() != nd) { *err = "stride dimension mismatch"; return ERR_STRIDE; }
+  if (d.axes.empty()) { *err = "no axes given"; return ERR_INVALID; }
+  {
+    std::vector<int> seen(nd, 0);
+    for (size_t ax : d.axes) {
+      if (ax >= nd) { *err = "bad axis number"; return ERR_INVALID; }
+      if (++seen[ax] > 1) { *err = "axis specified repeatedly"; return ERR_INVALID; }
+    }
+  }
+  if (d.dtype != DT_F32 && d.dtype != DT_F64) { *err = "bad dtype"; return ERR_INVALID; }
+  if (d.layout != RL_HERMITIAN && d.axes.size() != 1) { *err = "packed/symmetric real layouts are 1-axis only"; return ERR_INVALID; }
+  size_t total = 1;
+  for (size_t s : d.shape) total *= s;
+  plan->empty = (total == 0);
+
+  const size_t rsz = d.dtype == DT_F64 ? 8 : 4, csz = 2 * rsz;
+  const size_t last = d.axes.back();
+  std::vector<size_t> cshape = d.shape;  // shape of the complex (half-spectrum) array for real transforms
+  if (d.kind != KIND_C2C) {
+    if (d.layout == RL_HERMITIAN) cshape[last] = d.shape[last] / 2 + 1;
+    else if (d.layout == RL_FULLSYM) cshape[last] = d.shape[last];
+  }
+  const size_t in_esz = (d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX)) ? rsz : csz;
+  const size_t out_esz = (d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX)) ? rsz : csz;
+  const std::vector<size_t> &in_shape = (d.kind == KIND_C2R && d.layout == RL_HERMITIAN) ? cshape : d.shape;
+  const std::vector<size_t> &out_shape = (d.kind == KIND_R2C && d.layout != RL_HALFCOMPLEX) ? cshape : d.shape;
+  for (size_t i = 0; i < nd; ++i) {
+    if (d.stride_in[i] % (ptrdiff_t)in_esz || d.stride_out[i] % (ptrdiff_t)out_esz) {
+      *err = "strides must be multiples of the element size";
+      return ERR_STRIDE;
+    }
+  }
+  span_of(in_shape, d.stride_in, in_esz, &plan->in_lo, &plan->in_hi);
+  span_of(out_shape, d.stride_out, out_esz, &plan->out_lo, &plan->out_hi);
+  {
+    size_t nout = 1;
+    for (size_t s : out_shape) nout *= s;
+    plan->out_dense = (size_t)(plan->out_hi - plan->out_lo) == nout * out_esz;
+  }
+  if (plan->empty) return ST_OK;
+
+  // one batched line transform along `axis`
+  auto add_axis = [&](int kind, int layout, bool forward, size_t axis, uint32_t N,
+                      const std::vector<size_t> &bshape, const std::vector<ptrdiff_t> &sin, size_t esz_in,
+                      const std::vector<ptrdiff_t> &sout, size_t esz_out, int src, int dst, bool takes_fct) -> int {
+    std::vector<Dim> dims;
+    for (size_t i = 0; i < nd; ++i) {
+      if (i == axis || bshape[i] == 1) continue;
+      dims.push_back({bshape[i], sin[i] / (ptrdiff_t)esz_in, sout[i] / (ptrdiff_t)esz_out});
+    }
+    std::sort(dims.begin(), dims.end(), [](const Dim &a, const Dim &b) {
+      if (std::llabs(a.sin) != std::llabs(b.sin)) return std::llabs(a.sin) < std::llabs(b.sin);
+      return std::llabs(a.sout) < std::llabs(b.sout);
+    });
+    // merge dims that are contiguous with each other on both sides
+    for (size_t i = 0; i + 1 < dims.size();) {
+      if (dims[i + 1].sin == dims[i].sin * (int64_t)dims[i].n && dims[i + 1].sout == dims[i].sout * (int64_t)dims[i].n) {
+        dims[i].n *= dims[i + 1].n;
+        dims.erase(dims.begin() + (ptrdiff_t)i + 1);
+      } else {
+        ++i;
+      }
+    }
+    LineSpec s;
+    s.kind = kind; s.dtype = d.dtype; s.layout = layout; s.forward = forward; s.N = N;
+    s.es_in = sin[axis] / (ptrdiff_t)esz_in;
+    s.es_out = sout[axis] / (ptrdiff_t)esz_out;
+    const size_t nk = std::min<size_t>(dims.size(), kMaxBatchDims);
+    for (size_t i = 0; i < nk; ++i) { s.bdim[i] = dims[i].n; s.bs_in[i] = dims[i].sin; s.bs_out[i] = dims[i].sout; }
+    // outer dims beyond three are looped on the host
+    std::vector<Dim> outer(dims.begin() + (ptrdiff_t)nk, dims.end());
+    uint64_t nouter = 1;
+    for (auto &o : outer) nouter *= o.n;
+    Step proto;
+    int rc = build_line_job(s, &proto.job, &proto.cfg, err);
+    if (rc) return rc;
+    proto.takes_fct = takes_fct;
+    proto.src = src; proto.dst = dst;
+    for (uint64_t it = 0; it < nouter; ++it) {
+      Step st = proto;
+      uint64_t r = it;
+      int64_t oi = 0, oo = 0;
+      for (auto &o : outer) { uint64_t idx = r % o.n; r /= o.n; oi += (int64_t)idx * o.sin; oo += (int64_t)idx * o.sout; }
+      st.src_off_bytes = oi * (int64_t)esz_in;
+      st.dst_off_bytes = oo * (int64_t)esz_out;
+      plan->steps.push_back(st);
+    }
+    return ST_OK;
+  };
+
+  int rc = ST_OK;
+  if (d.kind == KIND_C2C) {
+    // general_nd: first axis in -> out with fct, remaining axes in place on out (hdronly.h:3018-3048)
+    for (size_t i = 0; i < d.axes.size() && !rc; ++i) {
+      const bool first = i == 0;
+      rc = add_axis(KIND_C2C, RL_HERMITIAN, d.forward, d.axes[i], (uint32_t)d.shape[d.axes[i]], d.shape,
+                    first ? d.stride_in : d.stride_out, csz, d.stride_out, csz,
+                    first ? BUF_IN : BUF_OUT, BUF_OUT, first);
+    }
+  } else if (d.kind == KIND_R2C) {
+    // r2c on axes.back(), then c2c in place over the rest on the reduced shape (hdronly.h:3334-3349)
+    rc = add_axis(KIND_R2C, d.layout, d.forward, last, (uint32_t)d.shape[last], d.shape, d.stride_in, rsz,
+                  d.stride_out, out_esz, BUF_IN, BUF_OUT, true);
+    for (size_t i = 0; i + 1 < d.axes.size() && !rc; ++i)
+      rc = add_axis(KIND_C2C, RL_HERMITIAN, d.forward, d.axes[i], (uint32_t)cshape[d.axes[i]], cshape,
+                    d.stride_out, csz, d.stride_out, csz, BUF_OUT, BUF_OUT, false);
+  } else if (d.kind == KIND_C2R) {
+    if (d.axes.size() == 1) {
+      rc = add_axis(KIND_C2R, d.layout, d.forward, last, (uint32_t)d.shape[last], d.shape, d.stride_in, in_esz,
+                    d.stride_out, rsz, BUF_IN, BUF_OUT, true);
+    } else {
+      // c2c over axes[:-1] into a contiguous temporary, then c2r on axes.back() (hdronly.h:3366-3390)
+      std::vector<ptrdiff_t> st(nd);
+      st[nd - 1] = (ptrdiff_t)csz;
+      for (size_t i = nd - 1; i-- > 0;) st[i] = st[i + 1] * (ptrdiff_t)cshape[i + 1];
+      size_t nval = 1;
+      for (size_t s : cshape) nval *= s;
+      plan->tmp_bytes = nval * csz;
+      for (size_t i = 0; i + 1 < d.axes.size() && !rc; ++i) {
+        const bool first = i == 0;
+        rc = add_axis(KIND_C2C, RL_HERMITIAN, d.forward, d.axes[i], (uint32_t)cshape[d.axes[i]], cshape,
+                      first ? d.stride_in : st, csz, st, csz, first ? BUF_IN : BUF_TMP, BUF_TMP, false);
+      }
+      if (!rc)
+        rc = add_axis(KIND_C2R, RL_HERMITIAN, d.forward, last, (uint32_t)d.shape[last], d.shape, st, csz,
+                      d.stride_out, rsz, BUF_TMP, BUF_OUT, true);
+    }
+  } else {
+    *err = "bad transform kind";
+    return ERR_INVALID;
+  }
+  return rc;
+}
+
+}  // namespace impulse

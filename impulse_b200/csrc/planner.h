@@ -1,0 +1,118 @@
+// Host planner: factorisation, radix schedule, twiddle / permutation / Bluestein tables,
+// LineJob construction and the N-D axis driver.  Pure C++ (no CUDA runtime): tables are
+// handed to the device through the TableAlloc hook so the same planner drives the CUDA
+// engine (abi.cpp) and the host emulation used by the CPU-only tests (tests/emu).
+//
+// Reference counterparts: make_cfft_plan / make_rfft_plan / make_fftblue_plan
+// (c_pocketfft/pocketfft.c:2066-2153, 1889-1935), cfftp_factorize / comp_twiddle
+// (pocketfft.c:953-1031), general_nd / r2c / c2r composition and sanity_check
+// (cpp_pocketfft/pocketfft_hdronly.h:446-476, 3011-3050, 3320-3390) and the 16-entry
+// plan cache get_plan (pocketfft_hdronly.h:2655-2706).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fft_types.h"
+
+namespace impulse {
+
+struct TableAlloc {
+  virtual ~TableAlloc() {}
+  virtual void *upload(const void *host, size_t bytes) = 0;  // returns device pointer or null
+  virtual void release(void *dev) = 0;
+};
+
+enum Kind : int { KIND_C2C = 0, KIND_R2C = 1, KIND_C2R = 2 };
+enum DType : int { DT_F32 = 0, DT_F64 = 1 };
+enum RealLayout : int { RL_HERMITIAN = 0, RL_HALFCOMPLEX = 1, RL_FULLSYM = 2 };
+
+enum Status : int {
+  ST_OK = 0,
+  ERR_INVALID = -1,      // bad argument (ndim, axis, null pointer, zero length)
+  ERR_STRIDE = -2,       // stride mismatch / not a multiple of the element size / misaligned pointer
+  ERR_UNSUPPORTED = -3,  // valid request the engine cannot run yet (line too long for shared memory)
+  ERR_NOMEM = -4,
+  ERR_CUDA = -5,
+  ERR_NO_DEVICE = -6,
+};
+
+// Complex FFT of logical length L executed in shared memory.
+struct Engine1D {
+  uint32_t L = 0, n_fft = 0;
+  bool blue = false;
+  std::vector<uint32_t> radices;  // DIF order
+  void *d_tw = nullptr, *d_perm = nullptr, *d_bk = nullptr, *d_bkf = nullptr;
+};
+
+struct LaunchCfg {
+  int threads = 0;
+  size_t smem_bytes = 0;
+  uint64_t n_tiles = 0;
+};
+
+struct LineSpec {
+  int kind = KIND_C2C, dtype = DT_F64, layout = RL_HERMITIAN;
+  bool forward = true;
+  uint32_t N = 0;  // transform length (real length for r2c / c2r)
+  uint64_t bdim[kMaxBatchDims] = {1, 1, 1};
+  int64_t bs_in[kMaxBatchDims] = {0, 0, 0}, bs_out[kMaxBatchDims] = {0, 0, 0};
+  int64_t es_in = 1, es_out = 1;  // element units of the respective side
+};
+
+enum BufId : int { BUF_IN = 0, BUF_OUT = 1, BUF_TMP = 2 };
+
+struct Step {
+  LineJob job;
+  LaunchCfg cfg;
+  int src = BUF_IN, dst = BUF_OUT;
+  int64_t src_off_bytes = 0, dst_off_bytes = 0;  // host-looped outer dims
+  bool takes_fct = false;  // the scaling factor is applied once, in these steps (hdronly.h:3048)
+};
+
+struct NdDesc {
+  int kind = KIND_C2C, dtype = DT_F64, layout = RL_HERMITIAN;
+  bool forward = true;
+  std::vector<size_t> shape;            // c2c: array shape; r2c/c2r: shape of the REAL array
+  std::vector<ptrdiff_t> stride_in, stride_out;  // bytes
+  std::vector<size_t> axes;
+};
+
+struct NdPlan {
+  NdDesc desc;
+  std::vector<Step> steps;
+  size_t tmp_bytes = 0;
+  // byte spans touched relative to the base pointers (for host staging)
+  ptrdiff_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
+  bool empty = false;  // zero-size array: nothing to do
+  bool out_dense = true;  // the output span has no gaps between elements
+};
+
+class PlanCache {
+ public:
+  explicit PlanCache(TableAlloc *alloc) : alloc_(alloc) {}
+  ~PlanCache();
+  // max shared memory per CTA the engine may use (bytes), set by the backend
+  size_t max_smem = 227 * 1024;
+  int status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err);
+  int real_twiddle(uint32_t N, int dtype, const void **out, std::string *err);
+  int build_line_job(const LineSpec &s, LineJob *job, LaunchCfg *cfg, std::string *err);
+  int build_nd(const NdDesc &d, NdPlan *plan, std::string *err);
+
+ private:
+  TableAlloc *alloc_;
+  std::mutex mu_;
+  std::map<std::pair<uint32_t, int>, std::unique_ptr<Engine1D>> engines_;
+  std::map<std::pair<uint32_t, int>, void *> real_tw_;
+};
+
+// planner utilities exposed for tests
+std::vector<uint32_t> choose_radices(uint32_t L);      // empty when a prime factor > kMaxGenericRadix
+uint32_t bluestein_size(uint32_t L);                    // smallest 7-smooth n2 >= 2L-1
+std::vector<uint32_t> dif_positions(uint32_t n, const std::vector<uint32_t> &radices);  // pos_of_k
+
+}  // namespace impulse

@@ -1,0 +1,138 @@
+/* impulse_fft_b200.h — C ABI of libimpulse_fft_b200.so, the B200 (sm_100a) FFT engine that
+ * drops in behind the FFT path of SciNim/impulse.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) the ten pocketfft symbols the reference's C backend binds with importc
+ *      (impulse/fft/c_pocketfft/pocketfft.h:18-32, bound at
+ *      impulse/fft/c_pocketfft/pocketfft.nim:71-81) are declared in include/pocketfft.h and
+ *      exported verbatim: a Nim build links this library instead of compiling pocketfft.c.
+ *
+ *  (2) the descriptor API below, which carries what the reference's C++ backend passes to
+ *      pocketfft::c2c / r2c / c2r (impulse/fft/cpp_pocketfft/pocketfft_hdronly.h:3272-3390,
+ *      called from FFTDesc.apply at impulse/fft/cpp_pocketfft/pocketfft.nim:235-277):
+ *      shape, byte strides, axes, direction, scale factor — plus batching and the real-data
+ *      layouts of the C backend (FFTPACK halfcomplex; full symmetric spectrum).
+ *
+ * Pointers may be device pointers (asynchronous on `stream`) or host pointers (staged through
+ * the device in pipelined chunks; synchronous).  There is no CPU transform path: without a
+ * CUDA device every call returns IMPULSE_FFT_ERR_NO_DEVICE.
+ *
+ * All functions return 0 on success or a negative impulse_fft_status; the message for the last
+ * failure on the calling thread is available from impulse_fft_last_error().  These codes
+ * replace the C++ exceptions of pocketfft_hdronly.h:446-476.
+ */
+#ifndef IMPULSE_FFT_B200_H
+#define IMPULSE_FFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMPULSE_FFT_MAX_DIMS 8
+
+typedef enum {
+  IMPULSE_FFT_OK = 0,
+  IMPULSE_FFT_ERR_INVALID = -1,     /* bad ndim / axis / null pointer / zero length       */
+  IMPULSE_FFT_ERR_STRIDE = -2,      /* stride mismatch, non-element stride, misalignment   */
+  IMPULSE_FFT_ERR_UNSUPPORTED = -3, /* valid request this build cannot run                 */
+  IMPULSE_FFT_ERR_NOMEM = -4,
+  IMPULSE_FFT_ERR_CUDA = -5,
+  IMPULSE_FFT_ERR_NO_DEVICE = -6
+} impulse_fft_status;
+
+typedef enum { IMPULSE_FFT_C2C = 0, IMPULSE_FFT_R2C = 1, IMPULSE_FFT_C2R = 2 } impulse_fft_kind;
+typedef enum { IMPULSE_FFT_F32 = 0, IMPULSE_FFT_F64 = 1 } impulse_fft_dtype;
+
+/* layout of the complex side of a real transform */
+typedef enum {
+  IMPULSE_FFT_HERMITIAN = 0,   /* shape[axis]/2+1 complex bins (pocketfft_hdronly.h:3329)        */
+  IMPULSE_FFT_HALFCOMPLEX = 1, /* FFTPACK packed reals, N per line (pocketfft.nim:228-238); 1 axis */
+  IMPULSE_FFT_FULLSYM = 2      /* all N bins incl. conjugates = `symmetrize` (pocketfft.nim:160-171); r2c, 1 axis */
+} impulse_fft_real_layout;
+
+/* Transform descriptor.  `shape` is the array shape for C2C and the shape of the REAL array for
+ * R2C / C2R (as pocketfft does, README_pocketfft.md:90-92).  Strides are in BYTES and may be
+ * negative.  For R2C/C2R the real transform runs along axes[naxes-1]. */
+typedef struct {
+  int32_t kind;        /* impulse_fft_kind        */
+  int32_t dtype;       /* impulse_fft_dtype       */
+  int32_t real_layout; /* impulse_fft_real_layout */
+  int32_t forward;     /* 1: exp(-2 pi i jk/N), 0: exp(+...)  (pocketfft.c:946-951) */
+  uint32_t ndim;
+  uint32_t naxes;
+  size_t shape[IMPULSE_FFT_MAX_DIMS];
+  ptrdiff_t stride_in[IMPULSE_FFT_MAX_DIMS];
+  ptrdiff_t stride_out[IMPULSE_FFT_MAX_DIMS];
+  size_t axes[IMPULSE_FFT_MAX_DIMS];
+} impulse_fft_desc;
+
+typedef struct impulse_fft_plan_s *impulse_fft_plan;
+
+/* Plans are immutable after creation and may be executed concurrently from several threads /
+ * streams (the contract of impulse/fft/c_pocketfft/README.md:32-36).  Twiddle, permutation and
+ * Bluestein tables live in a per-device cache shared between plans. */
+int impulse_fft_plan_create(impulse_fft_plan *out, const impulse_fft_desc *desc);
+int impulse_fft_plan_destroy(impulse_fft_plan plan);
+
+/* result = fct * transform(in).  `stream` is a cudaStream_t (NULL = default stream).
+ * in == out is allowed for C2C with equal strides and for HALFCOMPLEX real transforms. */
+int impulse_fft_execute(impulse_fft_plan plan, const void *in, void *out, double fct, void *stream);
+
+/* One-shot forms with the argument list of pocketfft::c2c / r2c / c2r
+ * (pocketfft_hdronly.h:3272-3275, 3334-3337, 3366-3369); plans are cached internally the way
+ * get_plan does (pocketfft_hdronly.h:2655-2706).  nthreads is accepted and ignored. */
+int impulse_fft_c2c(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
+                    const void *data_in, void *data_out, double fct, size_t nthreads, void *stream);
+int impulse_fft_r2c(int dtype, size_t ndim, const size_t *shape_in, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
+                    const void *data_in, void *data_out, double fct, size_t nthreads, void *stream);
+int impulse_fft_c2r(int dtype, size_t ndim, const size_t *shape_out, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
+                    const void *data_in, void *data_out, double fct, size_t nthreads, void *stream);
+
+/* Batched forms of the C backend's in-place row transforms: `nrows` contiguous rows of
+ * `length` complex (cfft) or real (rfft, FFTPACK halfcomplex) doubles, device or host memory.
+ * This is what a caller looping fft() over rows should call instead. */
+int impulse_fft_cfft_rows(double *data, size_t nrows, size_t length, int forward, double fct, void *stream);
+int impulse_fft_rfft_rows(double *data, size_t nrows, size_t length, int forward, double fct, void *stream);
+
+/* Pointwise step of FFT-based filtering (r2c -> multiply -> c2r): out[b][i] = a[b][i]*filter[i]*scale
+ * over complex arrays, i < n_inner, b < n_batch.  Device pointers; out may alias a. */
+int impulse_fft_cmul(int dtype, const void *a, const void *filter, void *out, size_t n_inner, size_t n_batch,
+                     double scale, void *stream);
+
+/* Batched out-of-place transpose of complex matrices, out[b][c][r] = in[b][r][c]; leading dimensions in
+ * elements; batch b starts at b*rows*ld_in / b*cols*ld_out.  Used to re-block slabs around the all-to-all
+ * of the multi-GPU 2-D transform.  Device pointers. */
+int impulse_fft_transpose(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in,
+                          size_t ld_out, size_t batch, void *stream);
+
+/* Introspection (tests, benchmarks). */
+typedef struct {
+  uint32_t n_steps;        /* kernel launches per execute                       */
+  uint32_t n_fft;          /* shared-memory FFT length of the first step        */
+  uint32_t bluestein;      /* first step runs Bluestein                         */
+  uint32_t lines_per_cta;  /* first step                                        */
+  uint32_t threads;        /* first step                                        */
+  uint32_t smem_bytes;     /* first step                                        */
+  uint64_t tmp_bytes;      /* device scratch held by the plan                   */
+  uint32_t n_radices;
+  uint32_t radices[32];    /* first step's radix schedule                       */
+} impulse_fft_plan_info;
+int impulse_fft_plan_get_info(impulse_fft_plan plan, impulse_fft_plan_info *info);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t impulse_fft_launch_count(void);
+
+const char *impulse_fft_last_error(void);
+const char *impulse_fft_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPULSE_FFT_B200_H */

@@ -1,0 +1,87 @@
+// TEST INFRASTRUCTURE — host emulation of the CUDA engine's phase interpreter.
+//
+// Compiles impulse_b200/csrc/fft_device.cuh and planner.cpp for the CPU and replaces a CTA
+// by a loop over thread ids (one full sweep per phase = one __syncthreads()).  It exists
+// because the build container has no GPU: index logic, permutation tables, Bluestein
+// plumbing and the N-D driver are checked here before GPU time is spent.  It is NOT a
+// product code path: libimpulse_fft_b200.so does not contain it and has no CPU transform.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../impulse_b200/csrc/fft_device.cuh"
+#include "../../impulse_b200/csrc/planner.h"
+
+using namespace impulse;
+
+namespace {
+struct HostAlloc : TableAlloc {
+  void *upload(const void *h, size_t n) override { void *p = std::malloc(n ? n : 1); if (p) std::memcpy(p, h, n); return p; }
+  void release(void *p) override { std::free(p); }
+};
+HostAlloc g_alloc;
+PlanCache *g_cache = nullptr;
+std::string g_err;
+
+template <typename T> void run_job(const LineJob &J, const LaunchCfg &cfg) {
+  std::vector<unsigned char> raw(cfg.smem_bytes + 64, 0xCD);  // poison: catches reads of unwritten slots
+  unsigned char *base = raw.data();
+  base += (16 - ((uintptr_t)base & 15)) & 15;
+  int64_t *offs = (int64_t *)base;
+  cx<T> *smem = (cx<T> *)(base + kSmemHeaderBytes);
+  const uint32_t nthr = (uint32_t)cfg.threads;
+  for (uint64_t tile = 0; tile < cfg.n_tiles; ++tile) {
+    TileCtx tc = tile_ctx(J, tile);
+    for (uint32_t t = 0; t < nthr; ++t) phase_prolog(J, tc, t, offs);
+    for (uint32_t t = 0; t < nthr; ++t) phase_load<T>(J, tc, t, nthr, offs, smem);
+    for (int p = 0; p < J.nphases; ++p)
+      for (uint32_t t = 0; t < nthr; ++t) phase_mid<T>(J, J.ph[p], t, nthr, smem);
+    for (uint32_t t = 0; t < nthr; ++t) phase_store<T>(J, tc, t, nthr, offs, smem);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char *emu_last_error() { return g_err.c_str(); }
+
+// mirrors impulse_fft_nd() of the product ABI, on host memory
+int emu_nd(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+           const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
+           void *out, double fct) {
+  if (!g_cache) g_cache = new PlanCache(&g_alloc);
+  NdDesc d;
+  d.kind = kind; d.dtype = dtype; d.layout = layout; d.forward = forward != 0;
+  d.shape.assign(shape, shape + ndim);
+  d.stride_in.assign(stride_in, stride_in + ndim);
+  d.stride_out.assign(stride_out, stride_out + ndim);
+  d.axes.assign(axes, axes + naxes);
+  NdPlan plan;
+  int rc = g_cache->build_nd(d, &plan, &g_err);
+  if (rc) return rc;
+  if (plan.empty) return 0;
+  std::vector<unsigned char> tmp(plan.tmp_bytes + 16);
+  for (Step &st : plan.steps) {
+    const unsigned char *bufs_in[3] = {(const unsigned char *)in, (const unsigned char *)out, tmp.data()};
+    unsigned char *bufs_out[3] = {nullptr, (unsigned char *)out, tmp.data()};
+    st.job.in = bufs_in[st.src] + st.src_off_bytes;
+    st.job.out = bufs_out[st.dst] + st.dst_off_bytes;
+    st.job.fct = st.takes_fct ? fct : 1.0;
+    if (dtype == DT_F64) run_job<double>(st.job, st.cfg); else run_job<float>(st.job, st.cfg);
+  }
+  return 0;
+}
+
+// plan introspection for tests
+int emu_plan_info(uint32_t L, int dtype, uint32_t *n_fft, int *blue, uint32_t *radices, int max_r) {
+  if (!g_cache) g_cache = new PlanCache(&g_alloc);
+  const Engine1D *e = nullptr;
+  int rc = g_cache->status_engine(L, dtype, &e, &g_err);
+  if (rc) return rc;
+  *n_fft = e->n_fft; *blue = e->blue;
+  int n = 0;
+  for (uint32_t r : e->radices) if (n < max_r) radices[n++] = r;
+  return n;
+}
+}

@@ -1,0 +1,73 @@
+"""TEST INFRASTRUCTURE: builds and drives the host emulation of the CUDA engine (emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SO = os.path.join(HERE, "libimpulse_fft_emu.so")
+SRC = [os.path.join(HERE, "emu.cpp"), os.path.join(ROOT, "impulse_b200", "csrc", "planner.cpp")]
+DEPS = SRC + [os.path.join(ROOT, "impulse_b200", "csrc", f) for f in
+              ("fft_device.cuh", "fft_types.h", "planner.h", "trig_tables.h")]
+
+KIND = {"c2c": 0, "r2c": 1, "c2r": 2}
+LAYOUT = {"hermitian": 0, "halfcomplex": 1, "fullsym": 2}
+
+
+def build():
+    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in DEPS):
+        return
+    cmd = ["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", SO] + SRC
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode:
+        raise RuntimeError(out.stderr)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(SO)
+        _lib.emu_nd.restype = C.c_int
+        _lib.emu_nd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_size_t),
+                                C.POINTER(C.c_ssize_t), C.POINTER(C.c_ssize_t), C.c_size_t,
+                                C.POINTER(C.c_size_t), C.c_int, C.c_void_p, C.c_void_p, C.c_double]
+        _lib.emu_last_error.restype = C.c_char_p
+        _lib.emu_plan_info.restype = C.c_int
+        _lib.emu_plan_info.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_uint32), C.c_int]
+    return _lib
+
+
+class EmuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"emu rc={code}: {msg}")
+        self.code = code
+
+
+def nd(kind, a_in, a_out, shape, axes, forward=True, fct=1.0, layout="hermitian"):
+    L = lib()
+    dt = 1 if a_in.dtype in (np.float64, np.complex128) else 0
+    n = len(shape)
+    rc = L.emu_nd(KIND[kind], dt, LAYOUT[layout], n, (C.c_size_t * n)(*shape),
+                  (C.c_ssize_t * n)(*a_in.strides), (C.c_ssize_t * n)(*a_out.strides), len(axes),
+                  (C.c_size_t * len(axes))(*axes), int(forward), a_in.ctypes.data, a_out.ctypes.data, fct)
+    if rc:
+        raise EmuError(rc, L.emu_last_error().decode())
+    return a_out
+
+
+def plan_info(L_, dtype=1):
+    L = lib()
+    n_fft = C.c_uint32()
+    blue = C.c_int()
+    rad = (C.c_uint32 * 32)()
+    k = L.emu_plan_info(L_, dtype, C.byref(n_fft), C.byref(blue), rad, 32)
+    if k < 0:
+        raise EmuError(k, L.emu_last_error().decode())
+    return n_fft.value, bool(blue.value), list(rad[:k])

@@ -1,0 +1,168 @@
+"""CPU-only checks of the CUDA engine's logic through the host emulation (tests/emu):
+the same phase functions and the same planner the kernels use, against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.emu import harness as emu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "pocketfft_golden.npz"))
+
+
+def tol(n, dtype=np.float64):
+    """north_star bound: 1e-12*log2(N) fp64, 1e-5*log2(N) fp32."""
+    base = 1e-12 if dtype in (np.float64, np.complex128) else 1e-5
+    return base * max(1.0, np.log2(max(n, 2)))
+
+
+def rnd(rng, shape, dtype):
+    if dtype in (np.complex128, np.complex64):
+        return (rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)).astype(dtype)
+    return rng.uniform(-0.5, 0.5, shape).astype(dtype)
+
+
+def test_planner_schedules():
+    assert emu.plan_info(1024) == (1024, False, [8, 8, 4, 4])
+    assert emu.plan_info(4096) == (4096, False, [8, 8, 8, 8])
+    assert emu.plan_info(8192) == (8192, False, [8, 8, 8, 4, 4])
+    assert emu.plan_info(1000)[2] == [5, 5, 5, 8]
+    assert emu.plan_info(1944)[2] == [9, 9, 3, 8]
+    n_fft, blue, rad = emu.plan_info(4099)
+    assert blue and n_fft >= 2 * 4099 - 1 and np.prod(rad) == n_fft
+    assert emu.plan_info(1) == (1, False, [])
+    assert emu.plan_info(37)[1] is True   # prime > 31 -> Bluestein
+    assert emu.plan_info(31)[1] is False
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_c2c_lengths(checker, dtype):
+    rng = np.random.default_rng(5)
+    lengths = list(range(1, 131)) + [144, 169, 187, 191, 243, 256, 289, 343, 360, 361, 500, 512, 529, 625,
+                                     729, 841, 961, 1000, 1024, 1331, 2048, 2187, 3125, 3888, 4096, 4099]
+    if dtype == np.complex64:
+        lengths = lengths[::3]
+    for n in lengths:
+        x = rnd(rng, (3, n), dtype)
+        for fwd in (True, False):
+            fct = 1.0 if fwd else 1.0 / n
+            want = checker.c2c(x, [1], fwd, fct) if dtype == np.complex64 else checker.cfft_rows(x.copy(), fwd, fct)
+            got = emu.nd("c2c", x, np.empty_like(x), x.shape, [1], fwd, fct)
+            assert oracle.max_row_rel_l2(got, want) <= tol(n, dtype), (n, fwd)
+
+
+def test_c2c_inplace_and_golden(checker):
+    for key in GOLD.files:
+        if key.startswith("c2c_f64_in_"):
+            n = int(key.rsplit("_", 1)[1])
+            x = GOLD[key].copy()
+            emu.nd("c2c", x, x, x.shape, [1], True, 1.0)
+            assert oracle.max_row_rel_l2(x, GOLD[f"c2c_f64_fwd_{n}"]) <= tol(n), n
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_r2c_c2r_hermitian(checker, dtype):
+    rng = np.random.default_rng(6)
+    cdt = np.complex128 if dtype == np.float64 else np.complex64
+    lengths = list(range(1, 70)) + [74, 89, 97, 100, 121, 128, 191, 192, 243, 250, 382, 500, 1000, 1024, 2000, 3888, 4096, 4099, 4126]
+    if dtype == np.float32:
+        lengths = lengths[::2]
+    for n in lengths:
+        x = rnd(rng, (2, n), dtype)
+        for fwd in (True, False):
+            want = checker.r2c(x, [1], fwd, 0.5)
+            got = emu.nd("r2c", x, np.zeros((2, n // 2 + 1), cdt), x.shape, [1], fwd, 0.5)
+            assert oracle.max_row_rel_l2(got, want) <= tol(n, dtype), (n, fwd)
+        spec = checker.r2c(x, [1], True, 1.0)
+        for fwd in (False, True):
+            want = checker.c2r(spec, x.shape, [1], fwd, 1.0 / n)
+            got = emu.nd("c2r", spec, np.zeros_like(x), x.shape, [1], fwd, 1.0 / n)
+            assert oracle.max_row_rel_l2(got, want) <= tol(n, dtype), (n, fwd)
+        # c2r ignores imag of bin 0 (and N/2): hdronly.h:3196-3215
+        spec2 = spec.copy()
+        spec2[:, 0] += 0.25j
+        if n % 2 == 0:
+            spec2[:, -1] -= 0.5j
+        got2 = emu.nd("c2r", spec2, np.zeros_like(x), x.shape, [1], False, 1.0 / n)
+        assert oracle.max_row_rel_l2(got2, checker.c2r(spec, x.shape, [1], False, 1.0 / n)) <= tol(n, dtype)
+
+
+def test_halfcomplex_packed_roundtrip_all_classes(checker):
+    """The reference's own sweep (tests/test_fft.nim:29-49) on a subsample of lengths, through the
+    FFTPACK-packed in-place layout the C ABI uses, plus forward parity against the oracle."""
+    rng = np.random.default_rng(7)
+    odata = rng.uniform(-0.5, 0.5, 8192)
+    odata[0] = 0.340188
+    lengths = sorted(set(list(range(1, 200)) + list(range(200, 7000, 131)) + [1000, 3888, 4096, 4099]))
+    for n in lengths:
+        d = odata[:n].copy().reshape(1, n)
+        emu.nd("r2c", d, d, d.shape, [1], True, 1.0, layout="halfcomplex")
+        want = checker.rfft_rows(odata[:n].copy().reshape(1, n), True, 1.0)
+        assert oracle.rel_l2(d, want) <= tol(n), n
+        emu.nd("c2r", d, d, d.shape, [1], False, 1.0 / n, layout="halfcomplex")
+        assert oracle.rel_l2(d[0], odata[:n]) <= 2e-15 * max(1, np.log2(n)), n
+
+
+def test_fullsym_layout(checker):
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 3, 4, 5, 8, 9, 16, 30, 89, 191):
+        x = rnd(rng, (2, n), np.float64)
+        want = checker.cfft_rows(x.astype(np.complex128), True, 1.0)
+        got = emu.nd("r2c", x, np.zeros((2, n), np.complex128), x.shape, [1], True, 1.0, layout="fullsym")
+        assert oracle.max_row_rel_l2(got, want) <= tol(n), n
+
+
+def test_nd_and_strided(checker):
+    rng = np.random.default_rng(9)
+    # 2-D c2c, both axis orders, in place and out of place
+    a = rnd(rng, (12, 20), np.complex128)
+    for axes in ([0, 1], [1, 0], [0], [1]):
+        want = checker.c2c(a, axes, True, 0.5)
+        got = emu.nd("c2c", a, np.empty_like(a), a.shape, axes, True, 0.5)
+        assert oracle.rel_l2(got, want) <= tol(20)
+    b = a.copy()
+    emu.nd("c2c", b, b, b.shape, [0, 1], False, 1.0)
+    assert oracle.rel_l2(b, checker.c2c(a, [0, 1], False, 1.0)) <= tol(20)
+    # 3-D, strided views, negative stride, fp32
+    c = rnd(rng, (5, 6, 14), np.complex64)
+    v = c[::-1, :, ::2]
+    want = checker.c2c(v, [0, 2], True, 1.0)
+    got = emu.nd("c2c", v, np.empty(v.shape, np.complex64), v.shape, [0, 2], True, 1.0)
+    assert oracle.rel_l2(got, want) <= tol(7, np.float32)
+    # transposed (column-major) input: axis 1 is the strided one
+    t = rnd(rng, (16, 9), np.complex128).T
+    assert oracle.rel_l2(emu.nd("c2c", t, np.empty(t.shape, np.complex128), t.shape, [0, 1], True, 1.0),
+                         checker.c2c(t, [0, 1], True, 1.0)) <= tol(16)
+    # 5-D: more batch dims than the kernel takes -> host loop
+    e = rnd(rng, (2, 3, 2, 4, 6), np.complex128)[:, :, ::-1]
+    assert oracle.rel_l2(emu.nd("c2c", e, np.empty(e.shape, np.complex128), e.shape, [4], True, 1.0),
+                         checker.c2c(e, [4], True, 1.0)) <= tol(6)
+    assert oracle.rel_l2(emu.nd("c2c", e, np.empty(e.shape, np.complex128), e.shape, [1, 3], True, 1.0),
+                         checker.c2c(e, [1, 3], True, 1.0)) <= tol(6)
+    # N-D r2c / c2r (hdronly.h:3334-3390)
+    for shape, axes in (((8, 12), [0, 1]), ((5, 9), [0, 1]), ((5, 9), [1, 0]), ((4, 6, 10), [0, 2]), ((3, 7, 5), [0, 1, 2])):
+        r = rnd(rng, shape, np.float64)
+        want = checker.r2c(r, axes, True, 1.0)
+        got = emu.nd("r2c", r, np.zeros(want.shape, np.complex128), shape, axes, True, 1.0)
+        assert oracle.rel_l2(got, want) <= tol(12), (shape, axes)
+        back = emu.nd("c2r", want, np.zeros(shape), shape, axes, False, 1.0 / np.prod([shape[a] for a in axes]))
+        assert oracle.rel_l2(back, r) <= tol(12), (shape, axes)
+        wantb = checker.c2r(want, shape, axes, False, 1.0)
+        assert oracle.rel_l2(emu.nd("c2r", want, np.zeros(shape), shape, axes, False, 1.0), wantb) <= tol(12)
+    # golden N-D fixtures
+    a = GOLD["nd_c2c_f64_in"]
+    assert oracle.rel_l2(emu.nd("c2c", a, np.empty_like(a), a.shape, [0, 1], True, 1.0), GOLD["nd_c2c_f64_ax01"]) <= tol(10)
+    r = GOLD["nd_r2c_f32_in"]
+    assert oracle.rel_l2(emu.nd("r2c", r, np.zeros((8, 7), np.complex64), r.shape, [0, 1], True, 1.0),
+                         GOLD["nd_r2c_f32_ax01"]) <= tol(12, np.float32)
+
+
+def test_errors_like_sanity_check():
+    a = np.zeros((4, 4), np.complex128)
+    with pytest.raises(emu.EmuError):
+        emu.nd("c2c", a, a.copy(), a.shape, [2], True, 1.0)       # bad axis
+    with pytest.raises(emu.EmuError):
+        emu.nd("c2c", a, a.copy(), a.shape, [0, 0], True, 1.0)    # repeated axis
+    z = np.zeros((0, 4), np.complex128)
+    emu.nd("c2c", z, z.copy(), z.shape, [1], True, 1.0)            # empty: no-op (hdronly.h:3277)
