@@ -396,12 +396,14 @@ int impulse_fft_c2r(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t
 
 int impulse_fft_cfft_rows(double *data, size_t nrows, size_t length, int forward, double fct, void *stream) {
   if (length == 0) return fail(IMPULSE_FFT_ERR_INVALID, "zero-length transform");
+  if (length == 1) fct = 1.0;  // pocketfft.c:875: a length-1 plan returns before scaling
   size_t shape[2] = {nrows, length}, axes[1] = {1};
   ptrdiff_t st[2] = {(ptrdiff_t)(length * 16), 16};
   return one_shot(KIND_C2C, DT_F64, RL_HERMITIAN, 2, shape, st, st, 1, axes, forward, data, data, fct, stream);
 }
 int impulse_fft_rfft_rows(double *data, size_t nrows, size_t length, int forward, double fct, void *stream) {
   if (length == 0) return fail(IMPULSE_FFT_ERR_INVALID, "zero-length transform");
+  if (length == 1) fct = 1.0;  // pocketfft.c:1704: a length-1 plan returns before scaling
   size_t shape[2] = {nrows, length}, axes[1] = {1};
   ptrdiff_t st[2] = {(ptrdiff_t)(length * 8), 8};
   return one_shot(forward ? KIND_R2C : KIND_C2R, DT_F64, RL_HALFCOMPLEX, 2, shape, st, st, 1, axes, forward != 0, data, data,

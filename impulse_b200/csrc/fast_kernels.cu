@@ -1,0 +1,184 @@
+// Register-resident batched c2c kernels for the headline power-of-two row lengths (sm_100a).
+//
+// Where the generic engine (fft_kernels.cu) round-trips every radix pass through shared memory,
+// these kernels keep a whole row in the registers of TPR threads and touch shared memory only
+// for the transposes between passes:
+//
+//   two-pass  N = R1*R2 (N <= 1024 in fp64, <= 4096 in fp32), TPR = R2 threads per row, E = R1
+//             elements per thread, one exchange, warp-synchronous (a row never leaves its warp):
+//     LDG.128 x[i + R2*j]            (coalesced: lanes walk i)
+//     radix-R1 DFT in registers, twiddle W_N^(i*k1) from a per-CTA shared table
+//     STS  S[k1*(R2+1) + i]  |  __syncwarp  |  LDS  S[k1*(R2+1) + j]     (both conflict-free)
+//     radix-R2 DFT in registers, STG.128 X[k1 + R1*k2]  (coalesced: lanes walk k1)
+//
+// HBM traffic is exactly one read and one write per element; the grid is persistent
+// (CTAs/SM x 148) and each warp streams rows.  Replaces pass_all + pass2..pass11 of
+// pocketfft.c:300-929 for these lengths; same mathematics (DIF Stockham), fp64 twiddles rounded
+// from long double on the host.
+#include <cuda_runtime.h>
+
+#include "fft_device.cuh"
+#include "fft_kernels.h"
+
+namespace impulse {
+
+// v * exp(-2*pi*i*M/R) with the trivial roots folded at compile time
+template <typename T, int R, int M> __device__ __forceinline__ cx<T> mul_root(cx<T> v) {
+  constexpr int m = ((M % R) + R) % R;
+  constexpr T h = (T)0.7071067811865475244008444;
+  if constexpr (m == 0) return v;
+  else if constexpr (4 * m == R) return mul_mi(v);
+  else if constexpr (2 * m == R) return mk<T>(-v.x, -v.y);
+  else if constexpr (4 * m == 3 * R) return mul_pi(v);
+  else if constexpr (8 * m == R) return mk<T>((v.x + v.y) * h, (v.y - v.x) * h);
+  else if constexpr (8 * m == 3 * R) return mk<T>((v.y - v.x) * h, -(v.x + v.y) * h);
+  else if constexpr (8 * m == 5 * R) return mk<T>(-(v.x + v.y) * h, (v.x - v.y) * h);
+  else if constexpr (8 * m == 7 * R) return mk<T>((v.x - v.y) * h, (v.x + v.y) * h);
+  else {
+    constexpr T c = (T)Trig<R>::c(m), s = (T)Trig<R>::s(m);
+    return mk<T>(v.x * c + v.y * s, v.y * c - v.x * s);
+  }
+}
+
+// forward DFT of R points held in registers, natural order in and out
+template <typename T, int R> struct RegFFT {
+  static __device__ __forceinline__ void run(cx<T> (&x)[R]) { Bfly<T, R>::run(x); }
+};
+
+template <typename T, int RA, int RB> struct Composite {
+  static constexpr int R = RA * RB;
+  template <int J, int S> static __device__ __forceinline__ void tw_row(cx<T> (&x)[R], const cx<T> (&y)[RA]) {
+    if constexpr (S < RA) {
+      x[J + RB * S] = mul_root<T, R, J * S>(y[S]);
+      tw_row<J, S + 1>(x, y);
+    }
+  }
+  template <int J> static __device__ __forceinline__ void stage_a(cx<T> (&x)[R]) {
+    if constexpr (J < RB) {
+      cx<T> y[RA];
+#pragma unroll
+      for (int q = 0; q < RA; ++q) y[q] = x[J + RB * q];
+      RegFFT<T, RA>::run(y);
+      tw_row<J, 0>(x, y);
+      stage_a<J + 1>(x);
+    }
+  }
+  static __device__ __forceinline__ void run(cx<T> (&x)[R]) {
+    stage_a<0>(x);
+    cx<T> out[R];
+#pragma unroll
+    for (int s = 0; s < RA; ++s) {
+      cx<T> z[RB];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) z[j] = x[j + RB * s];
+      RegFFT<T, RB>::run(z);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) out[s + RA * r] = z[r];
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) x[k] = out[k];
+  }
+};
+template <typename T> struct RegFFT<T, 16> { static __device__ __forceinline__ void run(cx<T> (&x)[16]) { Composite<T, 4, 4>::run(x); } };
+template <typename T> struct RegFFT<T, 32> { static __device__ __forceinline__ void run(cx<T> (&x)[32]) { Composite<T, 4, 8>::run(x); } };
+template <typename T> struct RegFFT<T, 64> { static __device__ __forceinline__ void run(cx<T> (&x)[64]) { Composite<T, 8, 8>::run(x); } };
+
+template <typename T, int R1, int R2, int WARPS, int MINB, bool BWD>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+fast2_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nrows, int64_t rs_in, int64_t rs_out,
+             const cx<T> *__restrict__ twN, T fct) {
+  constexpr int N = R1 * R2, TPR = R2, GPW = 32 / TPR, NB2 = R1 / R2, PITCH = R2 + 1;
+  static_assert(R2 <= 32 && 32 % R2 == 0 && R1 % R2 == 0, "two-pass shape");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *tw = reinterpret_cast<cx<T> *>(smem_raw);
+  cx<T> *xbuf = tw + N;
+  for (int idx = threadIdx.x; idx < N; idx += WARPS * 32) {
+    const int k1 = idx / R2, i = idx % R2;
+    tw[idx] = twN[k1 * i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / TPR, i = lane % TPR;
+  cx<T> *S = xbuf + (size_t)(warp * GPW + g) * (R1 * PITCH);
+  constexpr uint64_t RPC = (uint64_t)WARPS * GPW;  // rows per CTA per sweep
+  for (uint64_t wrow = (uint64_t)blockIdx.x * RPC + (uint64_t)warp * GPW; wrow < nrows; wrow += (uint64_t)gridDim.x * RPC) {
+    const uint64_t row = wrow + g;
+    const bool active = row < nrows;
+    cx<T> x[R1];
+    {
+      const cx<T> *src = in + (int64_t)row * rs_in + i;
+#pragma unroll
+      for (int j = 0; j < R1; ++j) {
+        x[j] = active ? src[j * R2] : mk<T>((T)0, (T)0);
+        if (BWD) x[j].y = -x[j].y;
+      }
+    }
+    RegFFT<T, R1>::run(x);
+#pragma unroll
+    for (int k1 = 1; k1 < R1; ++k1) x[k1] = cmul(x[k1], tw[k1 * R2 + i]);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) S[k1 * PITCH + i] = x[k1];
+    __syncwarp();
+    cx<T> *dst = out + (int64_t)row * rs_out;
+#pragma unroll
+    for (int m = 0; m < NB2; ++m) {
+      const int k1 = i + R2 * m;
+      cx<T> y[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) y[j] = S[k1 * PITCH + j];
+      RegFFT<T, R2>::run(y);
+      if (active) {
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+          cx<T> v = y[k2];
+          v.x *= fct;
+          v.y *= BWD ? -fct : fct;
+          dst[k1 + R1 * k2] = v;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+namespace {
+template <typename T, int R1, int R2, int WARPS, int MINB>
+int launch_fast2(const LineJob &J, int sm_count, cudaStream_t s) {
+  constexpr int N = R1 * R2, GPW = 32 / R2;
+  const size_t smem = sizeof(cx<T>) * ((size_t)N + (size_t)WARPS * GPW * R1 * (R2 + 1));
+  const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
+  auto kf = fast2_kernel<T, R1, R2, WARPS, MINB, false>;
+  auto kb = fast2_kernel<T, R1, R2, WARPS, MINB, true>;
+  static bool configured = false;  // per process; attributes are per function (all devices of the process are B200)
+  if (!configured) {
+    for (auto k : {kf, kb}) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return (int)e;
+    }
+    configured = true;
+  }
+  const uint64_t rpc = (uint64_t)WARPS * GPW;
+  uint64_t grid = (J.n_lines + rpc - 1) / rpc;
+  const uint64_t cap = (uint64_t)sm_count * MINB;
+  if (grid > cap) grid = cap;
+  (bwd ? kb : kf)<<<(unsigned)grid, WARPS * 32, smem, s>>>((const cx<T> *)J.in, (cx<T> *)J.out, J.n_lines, J.bs_in[0],
+                                                          J.bs_out[0], (const cx<T> *)J.tw, (T)J.fct);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+
+// fast_id encodes the specialised kernel chosen by the planner (0 = generic engine)
+int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (J.fast_id) {
+    case FAST2_1024_F64: return launch_fast2<double, 32, 32, 4, 2>(J, sm_count, s);
+    case FAST2_512_F64: return launch_fast2<double, 32, 16, 4, 2>(J, sm_count, s);
+    case FAST2_256_F64: return launch_fast2<double, 16, 16, 4, 4>(J, sm_count, s);
+    case FAST2_1024_F32: return launch_fast2<float, 32, 32, 4, 4>(J, sm_count, s);
+    default: return (int)cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace impulse

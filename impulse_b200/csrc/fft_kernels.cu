@@ -40,11 +40,25 @@ int configure_kernels(size_t max_dyn_smem) {
                                        (int)max_dyn_smem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(line_fft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn_smem);
+  if (e != cudaSuccess) return (int)e;
+  // without this the driver may pick a carve-out that fits one CTA only
+  e = cudaFuncSetAttribute(line_fft_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(line_fft_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   return (int)e;
 }
 
 int launch_line_job(const LineJob &J, int threads, size_t smem_bytes, uint64_t n_tiles, void *stream) {
   if (n_tiles == 0) return 0;
+  if (J.fast_id != FAST_NONE) {
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return launch_fast_job(J, sm_count, stream);
+  }
   const unsigned grid = (unsigned)(n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (J.dtype == 1) line_fft_kernel<double><<<grid, threads, smem_bytes, s>>>(J);

@@ -10,6 +10,8 @@ namespace impulse {
 int configure_kernels(size_t max_dyn_smem);
 // enqueue one LineJob on `stream` (a cudaStream_t); returns cudaError_t
 int launch_line_job(const LineJob &job, int threads, size_t smem_bytes, uint64_t n_tiles, void *stream);
+// specialised kernels selected by LineJob::fast_id (fast_kernels.cu); returns cudaError_t
+int launch_fast_job(const LineJob &job, int sm_count, void *stream);
 // out[b][i] = a[b][i] * f[i] * scale over complex arrays (i < n_inner, b < n_batch)
 int launch_cmul(int dtype, const void *a, const void *f, void *out, size_t n_inner, size_t n_batch, double scale,
                 int sm_count, void *stream);

@@ -69,6 +69,15 @@ enum JobFlags : uint32_t {
   F_VEC_OUT = 1u << 7,      // ST_R_PAIRS may use one 2-element vector store
 };
 
+// specialised register-resident kernels (fast_kernels.cu); 0 = generic phase interpreter
+enum FastId : uint32_t {
+  FAST_NONE = 0,
+  FAST2_1024_F64 = 1,
+  FAST2_512_F64 = 2,
+  FAST2_256_F64 = 3,
+  FAST2_1024_F32 = 4,
+};
+
 struct Phase {
   uint8_t op;
   uint8_t radix;
@@ -90,6 +99,7 @@ struct LineJob {
   uint32_t swz_mask;   // 0, 7 (16-byte elements) or 15 (8-byte elements)
   uint32_t flags;
   uint8_t load_mode, store_mode, dtype /*0=f32,1=f64*/, nphases;
+  uint32_t fast_id;    // FastId
   uint64_t n_lines;
   // line index -> global offset (elements of the respective side's element type)
   uint64_t bdim[kMaxBatchDims];

@@ -361,6 +361,16 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   if (J->load_mode == LD_R_PAIRS && s.es_in == 1 && all_even(s.bs_in)) flags |= F_VEC_IN;
   if (J->store_mode == ST_R_PAIRS && s.es_out == 1 && all_even(s.bs_out)) flags |= F_VEC_OUT;
   J->flags = flags;
+
+  // specialised kernels: contiguous complex rows, one batch dimension, headline lengths
+  J->fast_id = FAST_NONE;
+  if (s.kind == KIND_C2C && !E->blue && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
+      !env_int("IMPULSE_FFT_NO_FAST", 0)) {
+    if (f64 && N == 1024) J->fast_id = FAST2_1024_F64;
+    else if (f64 && N == 512) J->fast_id = FAST2_512_F64;
+    else if (f64 && N == 256) J->fast_id = FAST2_256_F64;
+    else if (!f64 && N == 1024) J->fast_id = FAST2_1024_F32;
+  }
   return ST_OK;
 }
 

@@ -46,6 +46,12 @@ def initNormalize(kind: str, forward: bool, value: float, length: int) -> float:
     raise ValueError(f"unknown NormalizeKind {kind!r}")
 
 
+def _fct(kind: str, forward: bool, value: float, length: int) -> float:
+    """Scale factor actually applied by the C backend: its length-1 plans return before scaling
+    (pocketfft.c:875 pass_all, pocketfft.c:1704 rfftp_forward), so fct is ignored for N == 1."""
+    return 1.0 if length == 1 else initNormalize(kind, forward, value, length)
+
+
 # ---- plan cache (the reference rebuilds a plan on every call, NC:285,300; on a GPU the tables
 # ---- must be cached, SURVEY A.4-6) ---------------------------------------------------------
 _plans: dict = {}
@@ -180,7 +186,7 @@ def fft_inplace(data, forward: bool = True, normalize: str = nkBackward, normVal
     _check_len(n)
     if B.dtype_code(data) != _lib.F64:
         raise TypeError("the C-backend API is float64 only (use DataDesc/FFTDesc for float32)")
-    fct = initNormalize(normalize, forward, normValue, n)
+    fct = _fct(normalize, forward, normValue, n)
     shape = list(data.shape)
     if B.is_complex(data):
         return _execute(_lib.C2C, _lib.HERMITIAN, data, data, shape, forward, fct)
@@ -192,7 +198,7 @@ def rfft_packed(data, forward: bool = True, normalize: str = nkBackward, normVal
     x = _as_f64(data)
     n = x.shape[-1]
     _check_len(n)
-    fct = initNormalize(normalize, forward, normValue, n)
+    fct = _fct(normalize, forward, normValue, n)
     out = B.empty_like_kind(x, x.shape, False, _lib.F64)
     return _execute(_lib.R2C if forward else _lib.C2R, _lib.HALFCOMPLEX, x, out, list(x.shape), forward, fct)
 
@@ -204,7 +210,7 @@ def rfft(data, forward: bool = True, normalize: str = nkBackward, normValue: flo
     _check_len(n)
     if not forward:
         return unpackFFT(rfft_packed(x, forward, normalize, normValue))
-    fct = initNormalize(normalize, forward, normValue, n)
+    fct = _fct(normalize, forward, normValue, n)
     out = B.empty_like_kind(x, tuple(x.shape[:-1]) + (n // 2 + 1,), True, _lib.F64)
     return _execute(_lib.R2C, _lib.HERMITIAN, x, out, list(x.shape), True, fct)
 
@@ -215,7 +221,7 @@ def fft(data, forward: bool = True, normalize: str = nkBackward, normValue: floa
     x = _as_f64(data)
     n = x.shape[-1]
     _check_len(n)
-    fct = initNormalize(normalize, forward, normValue, n)
+    fct = _fct(normalize, forward, normValue, n)
     if B.is_complex(x):
         out = B.empty_like_kind(x, x.shape, True, _lib.F64)
         return _execute(_lib.C2C, _lib.HERMITIAN, x, out, list(x.shape), forward, fct)

@@ -210,6 +210,9 @@ class Port:
         res = np.array(a, copy=True)
         for n, ax in enumerate(axes):
             f = fct if n == 0 else 1.0  # fct on the first axis only: hdronly.h:3048
+            if res.shape[ax] == 1:  # the C++ engine scales length-1 lines (hdronly.h:1311), the C engine does not
+                res = (res * f).astype(res.dtype)
+                continue
             res = self._lines(res, ax, lambda r: self.cfft_rows(r, forward, f))
         if out is not None:
             out[...] = res
@@ -242,6 +245,8 @@ class Port:
 
     def r2c(self, a, axes, forward=True, fct=1.0, out=None, nthreads=1):
         def one(r):
+            if r.shape[1] == 1:
+                return (r * fct).astype(np.complex64 if r.dtype == np.float32 else np.complex128)
             r = self.rfft_rows(np.array(r, copy=True), True, fct)
             c = self._unpack_rows(r)
             return c if forward else np.conj(c)  # hdronly.h:3152-3155
@@ -260,6 +265,8 @@ class Port:
         n = real_shape[axes[-1]]
 
         def one(c):
+            if n == 1:
+                return (c.real * fct).astype(np.float32 if c.dtype == np.complex64 else np.float64)
             c = np.conj(c) if forward else c  # hdronly.h:3202-3208
             return self.rfft_rows(self._pack_rows(c, n), False, fct)
         res = self._lines(a, axes[-1], one)

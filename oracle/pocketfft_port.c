@@ -167,7 +167,7 @@ static void pass_any(size_t ido, size_t ip, size_t l1, const cpx *cc, cpx *ch, c
 
 /* pass driver: C:871-929 */
 static int cfftp(size_t n, cpx *c, real fct, int sign) {
-  if (n == 1) { c[0].r *= fct; c[0].i *= fct; return 0; }
+  if (n == 1) return 0; /* C:875 / C:1704: length-1 plans return BEFORE scaling by fct */
   size_t fctr[NFCT];
   int nf = factorize(n, fctr);
   if (nf < 0) return -1;

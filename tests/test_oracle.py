@@ -187,3 +187,13 @@ def test_ref_cpp_matches_c_engine(ref):
         a = ref.cfft_rows(x.copy(), True, 1.0)
         b = ref.c2c(x, [1], True, 1.0)
         assert oracle.max_row_rel_l2(b, a) <= 2e-15
+
+
+def test_length_one_scaling_quirk(port, ref):
+    """The C engine returns before scaling for length-1 plans (pocketfft.c:874,1703,1739); the C++
+    engine scales (pocketfft_hdronly.h:1309,2114).  Both behaviours are mirrored downstream."""
+    c = np.array([[2.0 + 1.0j]])
+    for e in (ref, port):
+        assert e.cfft_rows(c.copy(), True, 0.37)[0, 0] == 2.0 + 1.0j
+        assert e.rfft_rows(np.array([[3.0]]), True, 0.37)[0, 0] == 3.0
+        assert np.allclose(e.c2c(c, [1], True, 0.5), c * 0.5)
