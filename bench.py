@@ -296,7 +296,7 @@ def main():
                        "frac_of_8TBps_nominal": round(value / world / 8000.0, 4)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": committed_traffic(args.workload),
-                         "peak_source": peak_src, "kernel": "line_fft_kernel", "algorithmic_bytes_per_launch": bytes_per_gpu},
+                         "peak_source": peak_src, "kernel": ib.last_kernel(), "algorithmic_bytes_per_launch": bytes_per_gpu},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e:

@@ -47,6 +47,7 @@ EXPORTS = [
     "impulse_fft_plan_create", "impulse_fft_plan_destroy", "impulse_fft_execute", "impulse_fft_c2c",
     "impulse_fft_r2c", "impulse_fft_c2r", "impulse_fft_cfft_rows", "impulse_fft_rfft_rows",
     "impulse_fft_plan_get_info", "impulse_fft_launch_count", "impulse_fft_last_error", "impulse_fft_version",
+    "impulse_fft_last_kernel",
     "impulse_fft_cmul", "impulse_fft_transpose",
     # include/pocketfft.h
     "make_cfft_plan", "destroy_cfft_plan", "cfft_backward", "cfft_forward", "cfft_length",
@@ -84,6 +85,7 @@ def lib() -> C.CDLL:
     L.impulse_fft_launch_count.restype = C.c_uint64
     L.impulse_fft_last_error.restype = C.c_char_p
     L.impulse_fft_version.restype = C.c_char_p
+    L.impulse_fft_last_kernel.restype = C.c_char_p
     L.impulse_fft_cmul.restype = C.c_int
     L.impulse_fft_cmul.argtypes = [C.c_int, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_double, vp]
     L.impulse_fft_transpose.restype = C.c_int
@@ -108,6 +110,10 @@ def lib() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise FFTError(rc, lib().impulse_fft_last_error().decode(errors="replace"))
+
+
+def last_kernel() -> str:
+    return lib().impulse_fft_last_kernel().decode()
 
 
 def launch_count() -> int:

@@ -321,6 +321,7 @@ extern "C" {
 
 const char *impulse_fft_last_error(void) { return g_err.c_str(); }
 const char *impulse_fft_version(void) { return "impulse_fft_b200 0.1 (sm_100a)"; }
+const char *impulse_fft_last_kernel(void) { return impulse::g_last_kernel; }
 uint64_t impulse_fft_launch_count(void) { return g_launches.load(); }
 
 int impulse_fft_plan_create(impulse_fft_plan *out, const impulse_fft_desc *desc) {

@@ -17,6 +17,8 @@
 // from long double on the host.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "fft_device.cuh"
 #include "fft_kernels.h"
 
@@ -169,14 +171,196 @@ int launch_fast2(const LineJob &J, int sm_count, cudaStream_t s) {
 }
 }  // namespace
 
+
+// ---- TMA helpers (1-D bulk copy global -> shared, completion on an mbarrier) ------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Two-pass kernel with TMA row prefetch.  Each warp owns two shared buffers: while it computes
+// row r out of buffer b (first as the staged input, then as the exchange buffer), one elected
+// lane has already issued a cp.async.bulk for row r+1 into buffer b^1.  Global-load latency is
+// therefore hidden by one whole row of work per warp, independent of register pressure.
+template <typename T, int R1, int R2, int WARPS, bool BWD>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+fast2p_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nrows, int64_t rs_in, int64_t rs_out,
+              const cx<T> *__restrict__ twN, T fct, unsigned int *__restrict__ sched /* [0]=next row, [1]=CTAs done */) {
+  constexpr int N = R1 * R2, TPR = R2, GPW = 32 / TPR, NB2 = R1 / R2, PITCH = R2 + 1;
+  constexpr int BUF = R1 * PITCH;  // elements per group buffer (>= N)
+  static_assert(R2 <= 32 && 32 % R2 == 0 && R1 % R2 == 0, "two-pass shape");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cx<T> *tw = reinterpret_cast<cx<T> *>(smem_raw);
+  cx<T> *bufs = tw + N;                                             // [WARPS][2][GPW][BUF]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bufs + (size_t)WARPS * 2 * GPW * BUF);  // [WARPS][2]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { mbar_init(&bars[warp * 2], 1); mbar_init(&bars[warp * 2 + 1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (int idx = threadIdx.x; idx < N; idx += WARPS * 32) {
+    const int k1 = idx / R2, i = idx % R2;
+    tw[idx] = twN[k1 * i];
+  }
+  __syncthreads();
+  const int g = lane / TPR, i = lane % TPR;
+  cx<T> *wbuf = bufs + (size_t)warp * 2 * GPW * BUF;
+  uint64_t *bar = &bars[warp * 2];
+  constexpr uint64_t RPC = (uint64_t)WARPS * GPW;
+  constexpr uint32_t ROW_BYTES = N * sizeof(cx<T>);
+  auto issue = [&](uint64_t first_row, int b) {  // lane 0 only
+    uint32_t nact = 0;
+#pragma unroll
+    for (int q = 0; q < GPW; ++q) nact += (first_row + q < nrows) ? 1u : 0u;
+    fence_proxy_async();
+    mbar_expect_tx(&bar[b], nact * ROW_BYTES);
+#pragma unroll
+    for (int q = 0; q < GPW; ++q)
+      if (first_row + q < nrows)
+        bulk_g2s(wbuf + ((size_t)b * GPW + q) * BUF, in + (int64_t)(first_row + q) * rs_in, ROW_BYTES, &bar[b]);
+  };
+  // Rows are claimed dynamically (SMs do not run at equal speed: a static split left the slowest
+  // SM 1.5x behind the fastest).  The claim for iteration it+2 is issued at iteration it, so the
+  // atomic's latency never sits on the critical path.
+  uint32_t cur = 0, nxt = 0, nxt2 = 0;
+  if (lane == 0) { cur = atomicAdd(&sched[0], (unsigned)GPW); nxt = atomicAdd(&sched[0], (unsigned)GPW); }
+  cur = __shfl_sync(0xffffffffu, cur, 0);
+  nxt = __shfl_sync(0xffffffffu, nxt, 0);
+  if (cur < nrows && lane == 0) issue(cur, 0);
+  uint32_t ph0 = 0u, ph1 = 0u;
+  for (uint32_t it = 0; cur < nrows; ++it) {
+    const int b = it & 1;
+    const uint64_t wrow = cur;
+    if (lane == 0) {
+      nxt2 = atomicAdd(&sched[0], (unsigned)GPW);
+      if (nxt < nrows) issue(nxt, b ^ 1);
+    }
+    mbar_wait(&bar[b], b ? ph1 : ph0);
+    if (b) ph1 ^= 1u; else ph0 ^= 1u;
+    const uint64_t row = wrow + g;
+    const bool active = row < nrows;
+    cx<T> *S = wbuf + ((size_t)b * GPW + g) * BUF;
+    cx<T> x[R1];
+#pragma unroll
+    for (int j = 0; j < R1; ++j) {
+      x[j] = S[i + j * R2];
+      if (BWD) x[j].y = -x[j].y;
+    }
+    __syncwarp();
+    RegFFT<T, R1>::run(x);
+#pragma unroll
+    for (int k1 = 1; k1 < R1; ++k1) x[k1] = cmul(x[k1], tw[k1 * R2 + i]);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) S[k1 * PITCH + i] = x[k1];
+    __syncwarp();
+    cx<T> *dst = out + (int64_t)row * rs_out;
+#pragma unroll
+    for (int m = 0; m < NB2; ++m) {
+      const int k1 = i + R2 * m;
+      cx<T> y[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) y[j] = S[k1 * PITCH + j];
+      RegFFT<T, R2>::run(y);
+      if (active) {
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+          cx<T> v = y[k2];
+          v.x *= fct;
+          v.y *= BWD ? -fct : fct;
+          dst[k1 + R1 * k2] = v;
+        }
+      }
+    }
+    __syncwarp();
+    cur = nxt;
+    nxt = __shfl_sync(0xffffffffu, nxt2, 0);
+  }
+  // the last CTA to leave re-arms the scheduler words for the next launch that uses this slot
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(&sched[1], 1u);
+    if (done == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
+  }
+}
+
+namespace {
+// scheduler slots: zero-initialised device words, one pair per in-flight launch (ring)
+constexpr int kSchedSlots = 1024;
+unsigned int *sched_slot() {
+  static unsigned int *base = nullptr;
+  static unsigned next = 0;
+  if (!base) {
+    if (cudaMalloc(&base, sizeof(unsigned int) * 2 * kSchedSlots) != cudaSuccess) return nullptr;
+    cudaMemset(base, 0, sizeof(unsigned int) * 2 * kSchedSlots);
+  }
+  const unsigned s = __atomic_fetch_add(&next, 1u, __ATOMIC_RELAXED) % kSchedSlots;
+  return base + 2 * s;
+}
+
+template <typename T, int R1, int R2, int WARPS>
+int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
+  constexpr int N = R1 * R2, GPW = 32 / R2, BUF = R1 * (R2 + 1);
+  const size_t smem = sizeof(cx<T>) * ((size_t)N + (size_t)WARPS * 2 * GPW * BUF) + sizeof(uint64_t) * WARPS * 2;
+  const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
+  auto kf = fast2p_kernel<T, R1, R2, WARPS, false>;
+  auto kb = fast2p_kernel<T, R1, R2, WARPS, true>;
+  static bool configured = false;
+  if (!configured) {
+    for (auto k : {kf, kb}) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return (int)e;
+    }
+    configured = true;
+  }
+  const uint64_t rpc = (uint64_t)WARPS * GPW;
+  uint64_t grid = (J.n_lines + rpc - 1) / rpc;
+  if (grid > (uint64_t)sm_count) grid = (uint64_t)sm_count;
+  unsigned int *sched = sched_slot();
+  if (!sched) return (int)cudaErrorMemoryAllocation;
+  if (J.n_lines > 0xfff00000ull) return (int)cudaErrorInvalidValue;  // 32-bit row claims
+  (bwd ? kb : kf)<<<(unsigned)grid, WARPS * 32, smem, s>>>((const cx<T> *)J.in, (cx<T> *)J.out, J.n_lines, J.bs_in[0],
+                                                          J.bs_out[0], (const cx<T> *)J.tw, (T)J.fct, sched);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+
 // fast_id encodes the specialised kernel chosen by the planner (0 = generic engine)
+static int fast_variant() {  // IMPULSE_FFT_FAST_VARIANT=1 selects the non-TMA kernel (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST_VARIANT"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (J.fast_id) {
-    case FAST2_1024_F64: return launch_fast2<double, 32, 32, 4, 2>(J, sm_count, s);
-    case FAST2_512_F64: return launch_fast2<double, 32, 16, 4, 2>(J, sm_count, s);
-    case FAST2_256_F64: return launch_fast2<double, 16, 16, 4, 4>(J, sm_count, s);
-    case FAST2_1024_F32: return launch_fast2<float, 32, 32, 4, 4>(J, sm_count, s);
+    case FAST2_1024_F64:
+      if (fast_variant() == 0) { g_last_kernel = "fast2p_kernel<double,32,32,6>"; return launch_fast2p<double, 32, 32, 6>(J, sm_count, s); }
+      g_last_kernel = "fast2_kernel<double,32,32,4,2>";
+      return launch_fast2<double, 32, 32, 4, 2>(J, sm_count, s);
+    case FAST2_512_F64: g_last_kernel = "fast2_kernel<double,32,16,4,2>"; return launch_fast2<double, 32, 16, 4, 2>(J, sm_count, s);
+    case FAST2_256_F64: g_last_kernel = "fast2_kernel<double,16,16,4,4>"; return launch_fast2<double, 16, 16, 4, 4>(J, sm_count, s);
+    case FAST2_1024_F32: g_last_kernel = "fast2_kernel<float,32,32,4,4>"; return launch_fast2<float, 32, 32, 4, 4>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;
   }
 }

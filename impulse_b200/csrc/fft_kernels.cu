@@ -12,6 +12,8 @@
 
 namespace impulse {
 
+thread_local const char *g_last_kernel = "";
+
 template <typename T>
 __global__ void __launch_bounds__(kMaxThreads)
 line_fft_kernel(const __grid_constant__ LineJob J) {
@@ -61,6 +63,7 @@ int launch_line_job(const LineJob &J, int threads, size_t smem_bytes, uint64_t n
   }
   const unsigned grid = (unsigned)(n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  g_last_kernel = J.dtype == 1 ? "line_fft_kernel<double>" : "line_fft_kernel<float>";
   if (J.dtype == 1) line_fft_kernel<double><<<grid, threads, smem_bytes, s>>>(J);
   else line_fft_kernel<float><<<grid, threads, smem_bytes, s>>>(J);
   return (int)cudaGetLastError();

@@ -6,6 +6,8 @@
 #include "fft_types.h"
 
 namespace impulse {
+// name of the kernel most recently launched by this thread (introspection for bench/tests)
+extern thread_local const char *g_last_kernel;
 // raise the dynamic shared-memory limit of every kernel (once per device); returns cudaError_t
 int configure_kernels(size_t max_dyn_smem);
 // enqueue one LineJob on `stream` (a cudaStream_t); returns cudaError_t

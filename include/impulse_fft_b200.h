@@ -129,6 +129,9 @@ int impulse_fft_plan_get_info(impulse_fft_plan plan, impulse_fft_plan_info *info
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t impulse_fft_launch_count(void);
 
+/* name of the kernel most recently launched by the calling thread ("" if none) */
+const char *impulse_fft_last_kernel(void);
+
 const char *impulse_fft_last_error(void);
 const char *impulse_fft_version(void);
 

@@ -1,0 +1,55 @@
+"""Summarise an .ncu-rep (from `ncu --set full`) into a small JSON/markdown pair for profiles/.
+Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/name"""
+import csv
+import json
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes.sum.per_second",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__cycles_active.avg", "sm__cycles_active.min", "sm__cycles_active.max", "sm__cycles_elapsed.avg",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__pipe_tma_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    res = []
+    for r in data:
+        d = {"kernel": r[hdr.index("Kernel Name")]}
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                d[k] = {"value": r[i], "unit": units[i]}
+        res.append(d)
+    json.dump(res, open(out + ".json", "w"), indent=1)
+    with open(out + ".md", "w") as f:
+        f.write(f"# ncu --set full summary: {rep}\n\n")
+        for d in res:
+            f.write(f"## {d['kernel']}\n\n| metric | value | unit |\n|---|---|---|\n")
+            for k in KEYS:
+                if k in d:
+                    f.write(f"| {k} | {d[k]['value']} | {d[k]['unit']} |\n")
+            f.write("\n")
+    print("wrote", out + ".json/.md")
+
+
+if __name__ == "__main__":
+    main()
