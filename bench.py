@@ -41,6 +41,7 @@ WORKLOADS = {
     "c2c_16384x4096_c128": ("c2c", 16384, 4096, "f64"),
     "c2c_8192x8192_c128": ("c2c", 8192, 8192, "f64"),
     "c2c_131072x1024_c64": ("c2c", 131072, 1024, "f32"),
+    "fft2_8192x8192_c128": ("fft2", 8192, 8192, "f64"),
 }
 DEFAULT_WORKLOAD = "c2c_65536x1024_c128"
 
@@ -49,6 +50,8 @@ def algorithmic_bytes(kind, rows, n, dtype):
     r = 8 if dtype == "f64" else 4
     if kind == "c2c":
         return rows * n * 2 * r * 2          # read + write one complex element each
+    if kind == "fft2":
+        return 2 * rows * n * 2 * r * 2      # two passes, each one read + one write
     return rows * (n * r + (n // 2 + 1) * 2 * r)  # real side + half-spectrum side
 
 
@@ -131,7 +134,12 @@ def cpu_reference(kind, rows, n, dtype, budget_s=12.0):
         est /= 2
     if dtype != "f64":
         raise SystemExit("cpu baseline implemented for the float64 workloads")
-    if kind == "c2c":
+    if kind == "fft2":
+        srows = rows
+        x = rng.uniform(-0.5, 0.5, (rows, n)) + 1j * rng.uniform(-0.5, 0.5, (rows, n))
+        y = np.empty_like(x)
+        run = lambda: chk.c2c(x, [0, 1], True, 1.0, out=y, nthreads=0)
+    elif kind == "c2c":
         x = rng.uniform(-0.5, 0.5, (srows, n)) + 1j * rng.uniform(-0.5, 0.5, (srows, n))
         run = lambda: chk.cfft_rows(x, True, 1.0, nthreads=cores)
     elif kind == "r2c":
@@ -207,7 +215,7 @@ def main():
     rdt = torch.float64 if dtype == "f64" else torch.float32
     cdt = torch.complex128 if dtype == "f64" else torch.complex64
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    if kind == "c2c":
+    if kind in ("c2c", "fft2"):
         x = torch.view_as_complex(torch.rand((rows, n, 2), generator=g, device=dev, dtype=rdt) - 0.5)
         y = torch.empty_like(x)
     elif kind == "r2c":
@@ -216,7 +224,7 @@ def main():
     else:
         x = torch.view_as_complex(torch.rand((rows, n // 2 + 1, 2), generator=g, device=dev, dtype=rdt) - 0.5)
         y = torch.empty((rows, n), device=dev, dtype=rdt)
-    fdesc = ib.FFTDesc.init(axes=[1], forward=(kind != "c2r"), scalingFactor=1.0)
+    fdesc = ib.FFTDesc.init(axes=[0, 1] if kind == "fft2" else [1], forward=(kind != "c2r"), scalingFactor=1.0)
     din, dout = ib.DataDesc.init(x), ib.DataDesc.init(y)
 
     def step():

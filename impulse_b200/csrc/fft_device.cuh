@@ -156,8 +156,9 @@ IMP_HD void phase_prolog(const LineJob &J, const TileCtx &tc, uint32_t tid, int6
     uint64_t r = l / J.bdim[0];
     uint64_t i1 = r % J.bdim[1];
     uint64_t i2 = r / J.bdim[1];
-    offs[2 * tid] = (int64_t)i0 * J.bs_in[0] + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
-    offs[2 * tid + 1] = (int64_t)i0 * J.bs_out[0] + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
+    offs[3 * tid] = (int64_t)i0 * J.bs_in[0] + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
+    offs[3 * tid + 1] = (int64_t)i0 * J.bs_out[0] + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
+    offs[3 * tid + 2] = (int64_t)(J.tw4_dim == 0 ? i0 : J.tw4_dim == 1 ? i1 : i2);
   }
 }
 
@@ -227,12 +228,12 @@ IMP_HD void phase_load(const LineJob &J, const TileCtx &tc, uint32_t tid, uint32
     const uint64_t total = (uint64_t)n << J.log_c;
     for (uint64_t g = tid; g < total; g += nthr) {
       uint32_t c = (uint32_t)g & cmask, e = (uint32_t)(g >> J.log_c);
-      if (c < tc.nlines) load_one<T>(J, smem + (size_t)c * J.pitch, offs[2 * c], e);
+      if (c < tc.nlines) load_one<T>(J, smem + (size_t)c * J.pitch, offs[3 * c], e);
     }
   } else {
     for (uint32_t c = 0; c < tc.nlines; ++c) {
       cx<T> *S = smem + (size_t)c * J.pitch;
-      const int64_t off = offs[2 * c];
+      const int64_t off = offs[3 * c];
       for (uint32_t e = tid; e < n; e += nthr) load_one<T>(J, S, off, e);
     }
   }
@@ -249,8 +250,10 @@ IMP_HD void pass_radix(const LineJob &J, const Phase &P, uint32_t tid, uint32_t 
   const uint32_t total = nb << J.log_c;
   const cx<T> *tw = (const cx<T> *)J.tw;
   const bool dit = P.op == OP_PASS_DIT;
+  const bool bfast = J.swz_mask != 0;  // few long lines per CTA: threads walk one line (XOR-swizzled)
   for (uint32_t g = tid; g < total; g += nthr) {
-    const uint32_t c = g & cmask, b = g >> J.log_c;
+    uint32_t c, b;
+    if (bfast) { c = g / nb; b = g - c * nb; } else { c = g & cmask; b = g >> J.log_c; }
     const uint32_t k = b / ido, i = b - k * ido;
     const uint32_t base = i + ido * IP * k;
     cx<T> *S = smem + (size_t)c * J.pitch;
@@ -276,6 +279,18 @@ IMP_HD void pass_radix(const LineJob &J, const Phase &P, uint32_t tid, uint32_t 
   }
 }
 
+// Large odd radices keep up to 31 complex values live; compiled as separate functions so that their
+// register demand (and spills) stay out of the hot radix-2..9 path of the kernel.
+#if defined(__CUDACC__)
+#define IMP_NOINLINE __device__ __noinline__
+#else
+#define IMP_NOINLINE
+#endif
+template <typename T, int IP>
+IMP_NOINLINE void pass_radix_big(const LineJob &J, const Phase &P, uint32_t tid, uint32_t nthr, cx<T> *smem) {
+  pass_radix<T, IP>(J, P, tid, nthr, smem);
+}
+
 template <typename T>
 IMP_HD void phase_pass(const LineJob &J, const Phase &P, uint32_t tid, uint32_t nthr, cx<T> *smem) {
   switch (P.radix) {
@@ -286,13 +301,13 @@ IMP_HD void phase_pass(const LineJob &J, const Phase &P, uint32_t tid, uint32_t 
     case 7: pass_radix<T, 7>(J, P, tid, nthr, smem); break;
     case 8: pass_radix<T, 8>(J, P, tid, nthr, smem); break;
     case 9: pass_radix<T, 9>(J, P, tid, nthr, smem); break;
-    case 11: pass_radix<T, 11>(J, P, tid, nthr, smem); break;
-    case 13: pass_radix<T, 13>(J, P, tid, nthr, smem); break;
-    case 17: pass_radix<T, 17>(J, P, tid, nthr, smem); break;
-    case 19: pass_radix<T, 19>(J, P, tid, nthr, smem); break;
-    case 23: pass_radix<T, 23>(J, P, tid, nthr, smem); break;
-    case 29: pass_radix<T, 29>(J, P, tid, nthr, smem); break;
-    case 31: pass_radix<T, 31>(J, P, tid, nthr, smem); break;
+    case 11: pass_radix_big<T, 11>(J, P, tid, nthr, smem); break;
+    case 13: pass_radix_big<T, 13>(J, P, tid, nthr, smem); break;
+    case 17: pass_radix_big<T, 17>(J, P, tid, nthr, smem); break;
+    case 19: pass_radix_big<T, 19>(J, P, tid, nthr, smem); break;
+    case 23: pass_radix_big<T, 23>(J, P, tid, nthr, smem); break;
+    case 29: pass_radix_big<T, 29>(J, P, tid, nthr, smem); break;
+    case 31: pass_radix_big<T, 31>(J, P, tid, nthr, smem); break;
     default: break;
   }
 }
@@ -316,8 +331,10 @@ IMP_HD void phase_elementwise(const LineJob &J, const Phase &P, uint32_t tid, ui
   const cx<T> *bk = (const cx<T> *)J.bk;
   const cx<T> *bkf = (const cx<T> *)J.bkf;
   const cx<T> *twr = (const cx<T> *)J.tw_r;
+  const bool bfast = J.swz_mask != 0;
   for (uint32_t g = tid; g < total; g += nthr) {
-    const uint32_t c = g & cmask, e = g >> J.log_c;
+    uint32_t c, e;
+    if (bfast) { c = g / n; e = g - c * n; } else { c = g & cmask; e = g >> J.log_c; }
     cx<T> *S = smem + (size_t)c * J.pitch;
     switch (P.op) {
       case OP_BLUE_PRE: {
@@ -381,7 +398,7 @@ IMP_HD cx<T> r2c_even_bin(const LineJob &J, const cx<T> *S, uint32_t k) {
 }
 
 template <typename T>
-IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e) {
+IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e, uint32_t tw_idx) {
   T *outr = (T *)J.out;
   cx<T> *outc = (cx<T> *)J.out;
   const int64_t es = J.es_out;
@@ -390,8 +407,19 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e)
   switch (J.store_mode) {
     case ST_C:
     case ST_HERM_HALF: {
-      cx<T> v = read_bin<T>(J, S, e);
-      v.x *= f; v.y *= f;
+      cx<T> v;
+      if (J.zero_pad_from && e >= J.zero_pad_from) {
+        v = mk<T>((T)0, (T)0);
+      } else {
+        v = read_bin<T>(J, S, e);
+        if (J.tw4_n) {  // four-step twiddle W_N^(e*tw_idx), conjugated for the backward transform
+          const uint32_t m = e * tw_idx;
+          const cx<T> w = cmul(IMP_LDG((const cx<T> *)J.tw4_hi + (m >> J.tw4_shift)),
+                               IMP_LDG((const cx<T> *)J.tw4_lo + (m & ((1u << J.tw4_shift) - 1))));
+          v = cmul(v, cconj_if(w, (J.flags & F_CONJ_OUT) != 0));
+        }
+        v.x *= f; v.y *= f;
+      }
       outc[off + (int64_t)e * es] = cconj_if(v, cres);
     } break;
     case ST_HERM_SYM: {
@@ -452,13 +480,14 @@ IMP_HD void phase_store(const LineJob &J, const TileCtx &tc, uint32_t tid, uint3
     const uint64_t total = (uint64_t)n << J.log_c;
     for (uint64_t g = tid; g < total; g += nthr) {
       uint32_t c = (uint32_t)g & cmask, e = (uint32_t)(g >> J.log_c);
-      if (c < tc.nlines) store_one<T>(J, smem + (size_t)c * J.pitch, offs[2 * c + 1], e);
+      if (c < tc.nlines) store_one<T>(J, smem + (size_t)c * J.pitch, offs[3 * c + 1], e, (uint32_t)offs[3 * c + 2]);
     }
   } else {
     for (uint32_t c = 0; c < tc.nlines; ++c) {
       const cx<T> *S = smem + (size_t)c * J.pitch;
-      const int64_t off = offs[2 * c + 1];
-      for (uint32_t e = tid; e < n; e += nthr) store_one<T>(J, S, off, e);
+      const int64_t off = offs[3 * c + 1];
+      const uint32_t twi = (uint32_t)offs[3 * c + 2];
+      for (uint32_t e = tid; e < n; e += nthr) store_one<T>(J, S, off, e, twi);
     }
   }
 }

@@ -14,8 +14,9 @@ namespace impulse {
 
 thread_local const char *g_last_kernel = "";
 
-template <typename T>
-__global__ void __launch_bounds__(kMaxThreads)
+// BIG = tiles above half the SM's shared memory (one CTA per SM anyway): 512 threads, 128 registers.
+template <typename T, bool BIG>
+__global__ void __launch_bounds__(BIG ? kMaxThreadsBig : kMaxThreads, BIG ? 1 : kMinCtasPerSm)
 line_fft_kernel(const __grid_constant__ LineJob J) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int64_t *offs = reinterpret_cast<int64_t *>(smem_raw);
@@ -38,16 +39,16 @@ line_fft_kernel(const __grid_constant__ LineJob J) {
 }
 
 int configure_kernels(size_t max_dyn_smem) {
-  cudaError_t e = cudaFuncSetAttribute(line_fft_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)max_dyn_smem);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(line_fft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn_smem);
-  if (e != cudaSuccess) return (int)e;
-  // without this the driver may pick a carve-out that fits one CTA only
-  e = cudaFuncSetAttribute(line_fft_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(line_fft_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return (int)e;
+  const void *ks[4] = {(const void *)line_fft_kernel<double, false>, (const void *)line_fft_kernel<double, true>,
+                       (const void *)line_fft_kernel<float, false>, (const void *)line_fft_kernel<float, true>};
+  for (const void *k : ks) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn_smem);
+    if (e != cudaSuccess) return (int)e;
+    // without this the driver may pick a carve-out that fits one CTA only
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
 }
 
 int launch_line_job(const LineJob &J, int threads, size_t smem_bytes, uint64_t n_tiles, void *stream) {
@@ -64,8 +65,14 @@ int launch_line_job(const LineJob &J, int threads, size_t smem_bytes, uint64_t n
   const unsigned grid = (unsigned)(n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   g_last_kernel = J.dtype == 1 ? "line_fft_kernel<double>" : "line_fft_kernel<float>";
-  if (J.dtype == 1) line_fft_kernel<double><<<grid, threads, smem_bytes, s>>>(J);
-  else line_fft_kernel<float><<<grid, threads, smem_bytes, s>>>(J);
+  const bool big = threads > kMaxThreads;
+  if (J.dtype == 1) {
+    if (big) line_fft_kernel<double, true><<<grid, threads, smem_bytes, s>>>(J);
+    else line_fft_kernel<double, false><<<grid, threads, smem_bytes, s>>>(J);
+  } else {
+    if (big) line_fft_kernel<float, true><<<grid, threads, smem_bytes, s>>>(J);
+    else line_fft_kernel<float, false><<<grid, threads, smem_bytes, s>>>(J);
+  }
   return (int)cudaGetLastError();
 }
 

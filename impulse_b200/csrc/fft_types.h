@@ -22,9 +22,11 @@ namespace impulse {
 
 constexpr int kMaxPhases = 40;
 constexpr int kMaxBatchDims = 3;
-constexpr int kSmemHeaderBytes = 1024;  // per-line global offsets (2 x int64 x 64 lines)
+constexpr int kSmemHeaderBytes = 2048;  // per-line header: in offset, out offset, four-step index (3 x int64 x 64 lines)
 constexpr int kMaxLinesPerCta = 64;
-constexpr int kMaxThreads = 512;
+constexpr int kMaxThreads = 256;
+constexpr int kMaxThreadsBig = 512;  // tiles that leave room for one CTA per SM only
+constexpr int kMinCtasPerSm = 3;
 constexpr uint32_t kMaxGenericRadix = 31;  // odd prime radices up to this are direct; above -> Bluestein
 
 enum PhaseOp : uint8_t {
@@ -113,6 +115,13 @@ struct LineJob {
   const void *tw_r;        // exp(-2*pi*i*k/N), k <= N/2 (even real transforms)
   const void *bk;          // exp(+i*pi*n^2/L), n < L
   const void *bkf;         // FFT_{n_fft}(wrapped bk)/n_fft at digit-reversed positions
+  // four-step (long lines split N = N1*N2 over two launches): the first launch multiplies output
+  // element k1 of the line with index n2 along batch dim tw4_dim by W_N^(k1*n2) = hi[m>>shift]*lo[m&mask]
+  const void *tw4_hi, *tw4_lo;
+  uint32_t tw4_n;          // N of the split transform; 0 = no store twiddle
+  uint32_t tw4_shift;
+  uint32_t tw4_dim;
+  uint32_t zero_pad_from;  // ST_C: elements e >= this are stored as zero (0 = off; Bluestein staging)
   double fct;
   Phase ph[kMaxPhases];
 };

@@ -153,6 +153,7 @@ PlanCache::~PlanCache() {
     for (void *p : {e->d_tw, e->d_perm, e->d_bk, e->d_bkf}) if (p) alloc_->release(p);
   }
   for (auto &kv : real_tw_) if (kv.second) alloc_->release(kv.second);
+  for (auto &kv : tw4_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
 }
 
 int PlanCache::status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err) {
@@ -202,6 +203,25 @@ int PlanCache::status_engine(uint32_t L, int dtype, const Engine1D **out, std::s
   return ST_OK;
 }
 
+int PlanCache::four_step_tables(uint32_t N, int dtype, const void **hi, const void **lo, uint32_t *shift, std::string *err) {
+  std::lock_guard<std::mutex> lk(mu_);
+  uint32_t sh = 0;
+  while ((1ull << (2 * sh)) < N) ++sh;  // B = 2^sh >= sqrt(N)
+  *shift = sh;
+  auto key = std::make_pair(N, dtype);
+  auto it = tw4_.find(key);
+  if (it != tw4_.end()) { *hi = it->second.first; *lo = it->second.second; return ST_OK; }
+  const uint32_t B = 1u << sh, nhi = (N + B - 1) / B;
+  std::vector<cld> vh(nhi), vl(B);
+  for (uint32_t j = 0; j < nhi; ++j) vh[j] = std::conj(unit_root((uint64_t)j * B, N));
+  for (uint32_t j = 0; j < B; ++j) vl[j] = std::conj(unit_root(j, N));
+  void *dh = upload_cplx(alloc_, vh, dtype), *dl = upload_cplx(alloc_, vl, dtype);
+  if (!dh || !dl) { *err = "table upload failed"; return ERR_NOMEM; }
+  tw4_[key] = std::make_pair(dh, dl);
+  *hi = dh; *lo = dl;
+  return ST_OK;
+}
+
 int PlanCache::real_twiddle(uint32_t N, int dtype, const void **out, std::string *err) {
   std::lock_guard<std::mutex> lk(mu_);
   auto key = std::make_pair(N, dtype);
@@ -247,6 +267,13 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     n_lines *= J->bdim[d];
   }
   J->n_lines = n_lines;
+  if (s.tw4_n) {
+    rc = four_step_tables(s.tw4_n, s.dtype, &J->tw4_hi, &J->tw4_lo, &J->tw4_shift, err);
+    if (rc) return rc;
+    J->tw4_n = s.tw4_n;
+    J->tw4_dim = s.tw4_dim;
+  }
+  J->zero_pad_from = s.zero_pad_from;
 
   uint32_t need = E->n_fft;  // shared-memory element slots per line
   uint32_t flags = 0;
@@ -333,24 +360,29 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   auto pitch_for = [&](uint32_t C) { return ((need + S - 1) / S) * S + (C > 1 ? 1 : 0); };
   uint32_t target = f64 ? 4096 : 8192;
   uint32_t C = pow2floor(std::max<uint64_t>(1, target / need));
-  if (in_lf || out_lf) C = std::max(C, S);
+  // strided axes: S adjacent lines give full 128-byte segments; small tiles keep many CTAs per SM in
+  // flight, which is what hides the load->compute->store serialisation of one CTA (measured: 8 lines
+  // beat 64 on the two launches of the 8192-point column split)
+  if (in_lf || out_lf) C = S;
   int envC = env_int("IMPULSE_FFT_LINES", 0);
   if (envC > 0) C = pow2floor((uint64_t)envC);
   C = std::min<uint32_t>(C, kMaxLinesPerCta);
   while (C > 1 && (size_t)C * pitch_for(C) * esz > budget) C /= 2;
   if ((size_t)C * pitch_for(C) * esz > budget) {
-    *err = "line of " + std::to_string(E->n_fft) + " points does not fit in shared memory (four-step path not built yet)";
+    *err = "line of " + std::to_string(E->n_fft) + " points does not fit in shared memory";
     return ERR_UNSUPPORTED;
   }
   C = std::min<uint32_t>(C, pow2ceil(n_lines));
   J->log_c = ilog2(C);
   J->pitch = pitch_for(C);
   J->swz_mask = (C < S) ? (S - 1) : 0;
-  int threads = (int)std::min<uint64_t>(kMaxThreads, std::max<uint64_t>(64, (((uint64_t)C * E->n_fft / 8) + 31) / 32 * 32));
+  const size_t smem_bytes = kSmemHeaderBytes + (size_t)C * J->pitch * esz;
+  const int tmax = smem_bytes > max_smem / 2 ? kMaxThreadsBig : kMaxThreads;
+  int threads = (int)std::min<uint64_t>(tmax, std::max<uint64_t>(64, (((uint64_t)C * E->n_fft / 8) + 31) / 32 * 32));
   int envT = env_int("IMPULSE_FFT_THREADS", 0);
-  if (envT > 0) threads = std::min(kMaxThreads, (envT + 31) / 32 * 32);
+  if (envT > 0) threads = std::min(tmax, (envT + 31) / 32 * 32);
   cfg->threads = threads;
-  cfg->smem_bytes = kSmemHeaderBytes + (size_t)C * J->pitch * esz;
+  cfg->smem_bytes = smem_bytes;
   cfg->n_tiles = (n_lines + C - 1) / C;
 
   // vector access for the packed-real sides (pointer alignment is re-checked at execute time)
@@ -364,7 +396,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
 
   // specialised kernels: contiguous complex rows, one batch dimension, headline lengths
   J->fast_id = FAST_NONE;
-  if (s.kind == KIND_C2C && !E->blue && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
+  if (s.kind == KIND_C2C && !E->blue && !s.tw4_n && !s.zero_pad_from && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
       !env_int("IMPULSE_FFT_NO_FAST", 0)) {
     if (f64 && N == 1024) J->fast_id = FAST2_1024_F64;
     else if (f64 && N == 512) J->fast_id = FAST2_512_F64;
@@ -399,6 +431,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   plan->desc = d;
   plan->steps.clear();
   plan->tmp_bytes = 0;
+  plan->tmp2_bytes = 0;
   const size_t nd = d.shape.size();
   // sanity_check (pocketfft_hdronly.h:446-476)
   if (nd < 1) { *err = "ndim must be >= 1"; return ERR_INVALID; }
@@ -443,36 +476,55 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   }
   if (plan->empty) return ST_OK;
 
-  // one batched line transform along `axis`
-  auto add_axis = [&](int kind, int layout, bool forward, size_t axis, uint32_t N,
-                      const std::vector<size_t> &bshape, const std::vector<ptrdiff_t> &sin, size_t esz_in,
-                      const std::vector<ptrdiff_t> &sout, size_t esz_out, int src, int dst, bool takes_fct) -> int {
-    std::vector<Dim> dims;
-    for (size_t i = 0; i < nd; ++i) {
-      if (i == axis || bshape[i] == 1) continue;
-      dims.push_back({bshape[i], sin[i] / (ptrdiff_t)esz_in, sout[i] / (ptrdiff_t)esz_out});
-    }
-    std::sort(dims.begin(), dims.end(), [](const Dim &a, const Dim &b) {
-      if (std::llabs(a.sin) != std::llabs(b.sin)) return std::llabs(a.sin) < std::llabs(b.sin);
-      return std::llabs(a.sout) < std::llabs(b.sout);
+  // ---- emit one batched line transform; `dims` are the batch dimensions (element units)
+  struct TwDim { bool on = false; uint32_t n = 0; };  // four-step: which dim indexes n2, and N
+  auto emit = [&](int kind, int layout, bool forward, uint32_t N, int64_t es_in, int64_t es_out,
+                  std::vector<Dim> dims, int tw_key /*index into dims of the n2 dim, -1 = none*/, uint32_t tw4_n,
+                  size_t esz_in, size_t esz_out, int src, int dst, int64_t src_base, int64_t dst_base,
+                  bool takes_fct) -> int {
+    std::vector<int> key(dims.size());
+    for (size_t i = 0; i < dims.size(); ++i) key[i] = (int)i;
+    std::vector<size_t> order(dims.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+      if (std::llabs(dims[a].sin) != std::llabs(dims[b].sin)) return std::llabs(dims[a].sin) < std::llabs(dims[b].sin);
+      if (std::llabs(dims[a].sout) != std::llabs(dims[b].sout)) return std::llabs(dims[a].sout) < std::llabs(dims[b].sout);
+      return a < b;
     });
-    // merge dims that are contiguous with each other on both sides
-    for (size_t i = 0; i + 1 < dims.size();) {
-      if (dims[i + 1].sin == dims[i].sin * (int64_t)dims[i].n && dims[i + 1].sout == dims[i].sout * (int64_t)dims[i].n) {
-        dims[i].n *= dims[i + 1].n;
-        dims.erase(dims.begin() + (ptrdiff_t)i + 1);
+    std::vector<Dim> sd;
+    std::vector<bool> is_tw;
+    for (size_t o : order) { sd.push_back(dims[o]); is_tw.push_back((int)o == tw_key); }
+    // merge dims that are contiguous with each other on both sides (never the four-step index dim)
+    for (size_t i = 0; i + 1 < sd.size();) {
+      if (!is_tw[i] && !is_tw[i + 1] && sd[i + 1].sin == sd[i].sin * (int64_t)sd[i].n &&
+          sd[i + 1].sout == sd[i].sout * (int64_t)sd[i].n) {
+        sd[i].n *= sd[i + 1].n;
+        sd.erase(sd.begin() + (ptrdiff_t)i + 1);
+        is_tw.erase(is_tw.begin() + (ptrdiff_t)i + 1);
       } else {
         ++i;
       }
     }
+    // the four-step index dim must be one of the three dims the kernel sees
+    if (tw_key >= 0) {
+      size_t pos = 0;
+      while (pos < sd.size() && !is_tw[pos]) ++pos;
+      if (pos >= (size_t)kMaxBatchDims) {
+        std::swap(sd[pos], sd[kMaxBatchDims - 1]);
+        is_tw[pos] = false;
+        is_tw[kMaxBatchDims - 1] = true;
+      }
+    }
     LineSpec s;
     s.kind = kind; s.dtype = d.dtype; s.layout = layout; s.forward = forward; s.N = N;
-    s.es_in = sin[axis] / (ptrdiff_t)esz_in;
-    s.es_out = sout[axis] / (ptrdiff_t)esz_out;
-    const size_t nk = std::min<size_t>(dims.size(), kMaxBatchDims);
-    for (size_t i = 0; i < nk; ++i) { s.bdim[i] = dims[i].n; s.bs_in[i] = dims[i].sin; s.bs_out[i] = dims[i].sout; }
-    // outer dims beyond three are looped on the host
-    std::vector<Dim> outer(dims.begin() + (ptrdiff_t)nk, dims.end());
+    s.es_in = es_in;
+    s.es_out = es_out;
+    const size_t nk = std::min<size_t>(sd.size(), kMaxBatchDims);
+    for (size_t i = 0; i < nk; ++i) {
+      s.bdim[i] = sd[i].n; s.bs_in[i] = sd[i].sin; s.bs_out[i] = sd[i].sout;
+      if (is_tw[i]) { s.tw4_n = tw4_n; s.tw4_dim = (uint32_t)i; }
+    }
+    std::vector<Dim> outer(sd.begin() + (ptrdiff_t)nk, sd.end());
     uint64_t nouter = 1;
     for (auto &o : outer) nouter *= o.n;
     Step proto;
@@ -485,11 +537,72 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       uint64_t r = it;
       int64_t oi = 0, oo = 0;
       for (auto &o : outer) { uint64_t idx = r % o.n; r /= o.n; oi += (int64_t)idx * o.sin; oo += (int64_t)idx * o.sout; }
-      st.src_off_bytes = oi * (int64_t)esz_in;
-      st.dst_off_bytes = oo * (int64_t)esz_out;
+      st.src_off_bytes = src_base + oi * (int64_t)esz_in;
+      st.dst_off_bytes = dst_base + oo * (int64_t)esz_out;
       plan->steps.push_back(st);
     }
     return ST_OK;
+  };
+
+  // byte span of buffer `b` relative to its base pointer (the four-step scratch mirrors the layout of
+  // the array it is fed from, so its accesses coalesce exactly like the source's)
+  auto span_lo_hi = [&](int b, ptrdiff_t *lo, ptrdiff_t *hi) {
+    if (b == BUF_IN) { *lo = plan->in_lo; *hi = plan->in_hi; }
+    else if (b == BUF_OUT) { *lo = plan->out_lo; *hi = plan->out_hi; }
+    else { *lo = 0; *hi = (ptrdiff_t)plan->tmp_bytes; }
+  };
+
+  // one batched line transform along `axis`
+  auto add_axis = [&](int kind, int layout, bool forward, size_t axis, uint32_t N,
+                      const std::vector<size_t> &bshape, const std::vector<ptrdiff_t> &sin, size_t esz_in,
+                      const std::vector<ptrdiff_t> &sout, size_t esz_out, int src, int dst, bool takes_fct) -> int {
+    std::vector<Dim> dims;
+    for (size_t i = 0; i < nd; ++i) {
+      if (i == axis || bshape[i] == 1) continue;
+      dims.push_back({bshape[i], sin[i] / (ptrdiff_t)esz_in, sout[i] / (ptrdiff_t)esz_out});
+    }
+    const int64_t es_in = sin[axis] / (ptrdiff_t)esz_in, es_out = sout[axis] / (ptrdiff_t)esz_out;
+    // ---- does the line fit one CTA with coalesced access?  If not, split N = N1*N2 (four-step).
+    bool split = false;
+    if (kind == KIND_C2C && N >= 64 && !choose_radices(N).empty()) {
+      const size_t csize = d.dtype == DT_F64 ? 16 : 8;
+      const uint32_t S = d.dtype == DT_F64 ? 8 : 16;
+      const size_t budget = max_smem - kSmemHeaderBytes;
+      const bool fits1 = (size_t)(N + S) * csize <= budget;
+      const bool fitsS = (size_t)S * (N + S + 1) * csize <= budget;
+      uint64_t fastest_in = ~0ull, fastest_out = ~0ull;
+      for (auto &dm : dims) {
+        fastest_in = std::min<uint64_t>(fastest_in, (uint64_t)std::llabs(dm.sin));
+        fastest_out = std::min<uint64_t>(fastest_out, (uint64_t)std::llabs(dm.sout));
+      }
+      const bool strided = (!dims.empty()) && (fastest_in < (uint64_t)std::llabs(es_in) || fastest_out < (uint64_t)std::llabs(es_out));
+      split = !fits1 || (strided && !fitsS) || env_int("IMPULSE_FFT_FORCE_FOURSTEP", 0);
+    }
+    if (!split)
+      return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
+
+    // N1 = largest divisor of N not above sqrt(N); both halves then run in shared memory
+    uint32_t N1 = 1;
+    for (uint32_t f = 1; (uint64_t)f * f <= N; ++f) if (N % f == 0) N1 = f;
+    const uint32_t N2 = N / N1;
+    if (N1 < 2 || N > (1u << 22)) { *err = "transform length " + std::to_string(N) + " is not supported by the two-kernel split"; return ERR_UNSUPPORTED; }
+    ptrdiff_t slo, shi;
+    span_lo_hi(src, &slo, &shi);
+    plan->tmp2_bytes = std::max<size_t>(plan->tmp2_bytes, (size_t)(shi - slo));
+    // step A: for every (line, n2): FFT over n1 of src[(n1*N2 + n2)*es_in], times W_N^(k1*n2),
+    //         written to the scratch at the SAME offsets (k1 in place of n1)
+    std::vector<Dim> da;
+    da.push_back({N2, es_in, es_in});
+    for (auto &dm : dims) da.push_back({dm.n, dm.sin, dm.sin});
+    int rc = emit(KIND_C2C, RL_HERMITIAN, forward, N1, es_in * (int64_t)N2, es_in * (int64_t)N2, da, 0, N, esz_in, esz_in,
+                  src, BUF_TMP2, 0, -(int64_t)slo, false);
+    if (rc) return rc;
+    // step B: for every (line, k1): FFT over n2 of scratch[(k1*N2 + n2)*es_in] -> dst[(k1 + N1*k2)*es_out]
+    std::vector<Dim> db;
+    db.push_back({N1, es_in * (int64_t)N2, es_out});
+    for (auto &dm : dims) db.push_back({dm.n, dm.sin, dm.sout});
+    return emit(KIND_C2C, RL_HERMITIAN, forward, N2, es_in, es_out * (int64_t)N1, db, -1, 0, esz_in, esz_out, BUF_TMP2, dst,
+                -(int64_t)slo, 0, takes_fct);
   };
 
   int rc = ST_OK;

@@ -62,9 +62,11 @@ struct LineSpec {
   uint64_t bdim[kMaxBatchDims] = {1, 1, 1};
   int64_t bs_in[kMaxBatchDims] = {0, 0, 0}, bs_out[kMaxBatchDims] = {0, 0, 0};
   int64_t es_in = 1, es_out = 1;  // element units of the respective side
+  uint32_t tw4_n = 0, tw4_dim = 0;  // four-step store twiddle (first of the two launches)
+  uint32_t zero_pad_from = 0;
 };
 
-enum BufId : int { BUF_IN = 0, BUF_OUT = 1, BUF_TMP = 2 };
+enum BufId : int { BUF_IN = 0, BUF_OUT = 1, BUF_TMP = 2, BUF_TMP2 = 3 };
 
 struct Step {
   LineJob job;
@@ -85,7 +87,8 @@ struct NdDesc {
 struct NdPlan {
   NdDesc desc;
   std::vector<Step> steps;
-  size_t tmp_bytes = 0;
+  size_t tmp_bytes = 0;   // c2r N-D intermediate (hdronly.h:3384)
+  size_t tmp2_bytes = 0;  // four-step scratch
   // byte spans touched relative to the base pointers (for host staging)
   ptrdiff_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
   bool empty = false;  // zero-size array: nothing to do
@@ -100,6 +103,7 @@ class PlanCache {
   size_t max_smem = 227 * 1024;
   int status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err);
   int real_twiddle(uint32_t N, int dtype, const void **out, std::string *err);
+  int four_step_tables(uint32_t N, int dtype, const void **hi, const void **lo, uint32_t *shift, std::string *err);
   int build_line_job(const LineSpec &s, LineJob *job, LaunchCfg *cfg, std::string *err);
   int build_nd(const NdDesc &d, NdPlan *plan, std::string *err);
 
@@ -108,6 +112,7 @@ class PlanCache {
   std::mutex mu_;
   std::map<std::pair<uint32_t, int>, std::unique_ptr<Engine1D>> engines_;
   std::map<std::pair<uint32_t, int>, void *> real_tw_;
+  std::map<std::pair<uint32_t, int>, std::pair<void *, void *>> tw4_;
 };
 
 // planner utilities exposed for tests

@@ -61,16 +61,31 @@ int emu_nd(int kind, int dtype, int layout, size_t ndim, const size_t *shape, co
   int rc = g_cache->build_nd(d, &plan, &g_err);
   if (rc) return rc;
   if (plan.empty) return 0;
-  std::vector<unsigned char> tmp(plan.tmp_bytes + 16);
+  std::vector<unsigned char> tmp(plan.tmp_bytes + 16), tmp2(plan.tmp2_bytes + 16, 0xCD);
   for (Step &st : plan.steps) {
-    const unsigned char *bufs_in[3] = {(const unsigned char *)in, (const unsigned char *)out, tmp.data()};
-    unsigned char *bufs_out[3] = {nullptr, (unsigned char *)out, tmp.data()};
+    const unsigned char *bufs_in[4] = {(const unsigned char *)in, (const unsigned char *)out, tmp.data(), tmp2.data()};
+    unsigned char *bufs_out[4] = {nullptr, (unsigned char *)out, tmp.data(), tmp2.data()};
     st.job.in = bufs_in[st.src] + st.src_off_bytes;
     st.job.out = bufs_out[st.dst] + st.dst_off_bytes;
     st.job.fct = st.takes_fct ? fct : 1.0;
     if (dtype == DT_F64) run_job<double>(st.job, st.cfg); else run_job<float>(st.job, st.cfg);
   }
   return 0;
+}
+
+// number of kernel launches the N-D plan would issue (tests: four-step split, host-looped dims)
+int emu_nd_steps(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                 const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward) {
+  if (!g_cache) g_cache = new PlanCache(&g_alloc);
+  NdDesc d;
+  d.kind = kind; d.dtype = dtype; d.layout = layout; d.forward = forward != 0;
+  d.shape.assign(shape, shape + ndim);
+  d.stride_in.assign(stride_in, stride_in + ndim);
+  d.stride_out.assign(stride_out, stride_out + ndim);
+  d.axes.assign(axes, axes + naxes);
+  NdPlan plan;
+  int rc = g_cache->build_nd(d, &plan, &g_err);
+  return rc ? rc : (int)plan.steps.size();
 }
 
 // plan introspection for tests

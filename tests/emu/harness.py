@@ -38,6 +38,8 @@ def lib():
                                 C.POINTER(C.c_ssize_t), C.POINTER(C.c_ssize_t), C.c_size_t,
                                 C.POINTER(C.c_size_t), C.c_int, C.c_void_p, C.c_void_p, C.c_double]
         _lib.emu_last_error.restype = C.c_char_p
+        _lib.emu_nd_steps.restype = C.c_int
+        _lib.emu_nd_steps.argtypes = _lib.emu_nd.argtypes[:10]
         _lib.emu_plan_info.restype = C.c_int
         _lib.emu_plan_info.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int),
                                        C.POINTER(C.c_uint32), C.c_int]
@@ -60,6 +62,17 @@ def nd(kind, a_in, a_out, shape, axes, forward=True, fct=1.0, layout="hermitian"
     if rc:
         raise EmuError(rc, L.emu_last_error().decode())
     return a_out
+
+
+def nd_steps(kind, a_in, a_out, shape, axes, forward=True, layout="hermitian"):
+    L = lib()
+    dt = 1 if a_in.dtype in (np.float64, np.complex128) else 0
+    n = len(shape)
+    rc = L.emu_nd_steps(KIND[kind], dt, LAYOUT[layout], n, (C.c_size_t * n)(*shape), (C.c_ssize_t * n)(*a_in.strides),
+                        (C.c_ssize_t * n)(*a_out.strides), len(axes), (C.c_size_t * len(axes))(*axes), int(forward))
+    if rc < 0:
+        raise EmuError(rc, L.emu_last_error().decode())
+    return rc
 
 
 def plan_info(L_, dtype=1):

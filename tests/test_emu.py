@@ -166,3 +166,42 @@ def test_errors_like_sanity_check():
         emu.nd("c2c", a, a.copy(), a.shape, [0, 0], True, 1.0)    # repeated axis
     z = np.zeros((0, 4), np.complex128)
     emu.nd("c2c", z, z.copy(), z.shape, [1], True, 1.0)            # empty: no-op (hdronly.h:3277)
+
+
+def test_four_step_split(checker, monkeypatch):
+    """Lines too long for one CTA (or strided and too long for a coalesced tile) are split N = N1*N2 over two
+    launches with a twiddle in between; forced here at small sizes, and natural at 16384 / strided 4096."""
+    rng = np.random.default_rng(12)
+    # natural: contiguous 32768-point complex128 line does not fit 227 KB
+    x = rnd(rng, (2, 32768), np.complex128)
+    assert emu.nd_steps("c2c", x, x, x.shape, [1]) == 2
+    for fwd in (True, False):
+        got = emu.nd("c2c", x, np.empty_like(x), x.shape, [1], fwd, 0.5)
+        assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.5)) <= tol(32768), fwd
+    # natural: strided axis of 4096 points (8 adjacent columns of 4096 complex128 do not fit)
+    y = rnd(rng, (4096, 12), np.complex128)
+    assert emu.nd_steps("c2c", y, y, y.shape, [0]) == 2
+    got = emu.nd("c2c", y, np.empty_like(y), y.shape, [0], True, 1.0)
+    assert oracle.rel_l2(got, checker.c2c(y, [0], True, 1.0)) <= tol(4096)
+    yi = y.copy()
+    emu.nd("c2c", yi, yi, yi.shape, [0], False, 1.0)        # in place through the scratch buffer
+    assert oracle.rel_l2(yi, checker.c2c(y, [0], False, 1.0)) <= tol(4096)
+    # forced at small sizes: every layout class
+    monkeypatch.setenv("IMPULSE_FFT_FORCE_FOURSTEP", "1")
+    for n in (64, 72, 100, 128, 243, 360, 1000, 1024):
+        z = rnd(rng, (3, n), np.complex128)
+        assert emu.nd_steps("c2c", z, z, z.shape, [1]) == 2, n
+        for fwd in (True, False):
+            got = emu.nd("c2c", z, np.empty_like(z), z.shape, [1], fwd, 1.0)
+            assert oracle.max_row_rel_l2(got, checker.c2c(z, [1], fwd, 1.0)) <= tol(n), (n, fwd)
+    a = rnd(rng, (5, 96, 7), np.complex64)[::-1]
+    got = emu.nd("c2c", a, np.empty(a.shape, np.complex64), a.shape, [1], True, 1.0)
+    assert oracle.rel_l2(got, checker.c2c(a, [1], True, 1.0)) <= tol(96, np.float32)
+    b = rnd(rng, (2, 3, 2, 64, 3), np.complex128)
+    got = emu.nd("c2c", b, np.empty_like(b), b.shape, [3, 1], True, 1.0)
+    assert oracle.rel_l2(got, checker.c2c(b, [3, 1], True, 1.0)) <= tol(64)
+    r = rnd(rng, (80, 66), np.float64)
+    spec = emu.nd("r2c", r, np.zeros((80, 34), np.complex128), r.shape, [0, 1], True, 1.0)
+    assert oracle.rel_l2(spec, checker.r2c(r, [0, 1], True, 1.0)) <= tol(80)
+    back = emu.nd("c2r", spec, np.zeros_like(r), r.shape, [0, 1], False, 1.0 / r.size)
+    assert oracle.rel_l2(back, r) <= tol(80)

@@ -329,3 +329,44 @@ def test_config1_and_3_shapes(ib, torch_mod, checker):
         num = torch_mod.linalg.vector_norm(back - x, dim=1)
         den = torch_mod.linalg.vector_norm(x, dim=1)
         assert float((num / den).max()) <= 2e-15 * np.log2(n), n
+
+
+def test_four_step_long_and_strided_lines(ib, torch_mod, checker):
+    """Lines that do not fit one CTA (contiguous 32768 points) or cannot be tiled 8 columns wide
+    (strided 4096 / 8192 points) run as two launches with a twiddle in between."""
+    rng = np.random.default_rng(12)
+    x = rnd(rng, (3, 32768), np.complex128)
+    xd = torch_mod.from_numpy(x).cuda()
+    for fwd in (True, False):
+        got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], fwd, 0.5).cpu().numpy()
+        assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.5)) <= tol(32768), fwd
+    y = rnd(rng, (4096, 40), np.complex128)
+    yd = torch_mod.from_numpy(y).cuda()
+    got = apply_nd(ib, "c2c", yd, torch_mod.empty_like(yd), [0]).cpu().numpy()
+    assert oracle.rel_l2(got, checker.c2c(y, [0])) <= tol(4096)
+    apply_nd(ib, "c2c", yd, yd, [0], False, 1.0 / 4096)   # in place
+    assert oracle.rel_l2(yd.cpu().numpy(), checker.c2c(y, [0], False, 1.0 / 4096)) <= tol(4096)
+    # fft2 (FFTDesc axes=[0,1], the path of BASELINE config 4) at 2048^2 against the oracle
+    m = rnd(rng, (2048, 2048), np.complex128)
+    md = torch_mod.from_numpy(m).cuda()
+    got = apply_nd(ib, "c2c", md, torch_mod.empty_like(md), [0, 1]).cpu().numpy()
+    assert oracle.rel_l2(got, checker.c2c(m, [0, 1], nthreads=0)) <= tol(2048)
+    f32 = rnd(rng, (4096, 24), np.complex64)
+    fd = torch_mod.from_numpy(f32).cuda()
+    got = apply_nd(ib, "c2c", fd, torch_mod.empty_like(fd), [0]).cpu().numpy()
+    assert oracle.rel_l2(got, checker.c2c(f32, [0])) <= tol(4096, np.float32)
+
+
+def test_config4_full_size_properties(ib, torch_mod):
+    """fft2 8192 x 8192 complex128 on one GPU: round trip, Parseval and a DC/impulse check."""
+    g = torch_mod.Generator(device="cuda").manual_seed(1234)
+    x = torch_mod.view_as_complex(torch_mod.rand((8192, 8192, 2), generator=g, device="cuda", dtype=torch_mod.float64) - 0.5)
+    y = torch_mod.empty_like(x)
+    apply_nd(ib, "c2c", x, y, [0, 1])
+    e_in = float((x.abs() ** 2).sum())
+    e_out = float((y.abs() ** 2).sum()) / (8192.0 * 8192.0)
+    assert abs(e_in - e_out) / e_in <= 1e-13
+    assert abs(complex(y[0, 0]) - complex(x.sum())) / abs(complex(x.sum())) <= 1e-11
+    apply_nd(ib, "c2c", y, y, [0, 1], False, 1.0 / (8192.0 * 8192.0))
+    err = float(torch_mod.linalg.vector_norm(y - x) / torch_mod.linalg.vector_norm(x))
+    assert err <= 2e-15 * 26, err
