@@ -48,7 +48,7 @@ EXPORTS = [
     "impulse_fft_r2c", "impulse_fft_c2r", "impulse_fft_cfft_rows", "impulse_fft_rfft_rows",
     "impulse_fft_plan_get_info", "impulse_fft_launch_count", "impulse_fft_last_error", "impulse_fft_version",
     "impulse_fft_last_kernel",
-    "impulse_fft_cmul", "impulse_fft_transpose",
+    "impulse_fft_cmul", "impulse_fft_transpose", "impulse_fft_copy2d",
     # include/pocketfft.h
     "make_cfft_plan", "destroy_cfft_plan", "cfft_backward", "cfft_forward", "cfft_length",
     "make_rfft_plan", "destroy_rfft_plan", "rfft_backward", "rfft_forward", "rfft_length",
@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
     L.impulse_fft_cmul.argtypes = [C.c_int, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_double, vp]
     L.impulse_fft_transpose.restype = C.c_int
     L.impulse_fft_transpose.argtypes = [C.c_int, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp]
+    L.impulse_fft_copy2d.restype = C.c_int
+    L.impulse_fft_copy2d.argtypes = [C.c_int, vp, vp] + [C.c_size_t] * 7 + [vp]
     L.make_cfft_plan.restype = vp
     L.make_cfft_plan.argtypes = [C.c_size_t]
     L.make_rfft_plan.restype = vp

@@ -444,6 +444,19 @@ int impulse_fft_transpose(int dtype, const void *in, void *out, size_t rows, siz
   return e ? cuda_fail((cudaError_t)e, "kernel launch") : 0;
 }
 
+int impulse_fft_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
+                       size_t batch, size_t bs_in, size_t bs_out, void *stream) {
+  DeviceCtx *ctx = nullptr;
+  int rc = get_ctx(&ctx);
+  if (rc) return rc;
+  if (!in || !out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
+  if (ld_in < cols || ld_out < cols) return fail(IMPULSE_FFT_ERR_STRIDE, "leading dimension smaller than the row length");
+  if (!is_device_ptr(in) || !is_device_ptr(out)) return fail(IMPULSE_FFT_ERR_INVALID, "impulse_fft_copy2d takes device pointers");
+  int e = launch_copy2d(dtype, in, out, rows, cols, ld_in, ld_out, batch, bs_in, bs_out, ctx->sm_count, stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return e ? cuda_fail((cudaError_t)e, "kernel launch") : 0;
+}
+
 // ---- the ten pocketfft symbols (include/pocketfft.h) -------------------------
 struct cfft_plan_i { size_t length; };
 struct rfft_plan_i { size_t length; };

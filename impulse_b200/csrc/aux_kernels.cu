@@ -49,6 +49,33 @@ __global__ void __launch_bounds__(256) transpose_kernel(const cx<T> *__restrict_
   }
 }
 
+// batched strided matrix copy: out[b][r][c] = in[b][r][c] with independent leading dimensions and
+// batch strides (elements).  Packs the per-peer blocks of a slab into contiguous send buffers.
+template <typename T>
+__global__ void __launch_bounds__(256) copy2d_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, size_t rows,
+                                                     size_t cols, size_t ld_in, size_t ld_out, size_t batch,
+                                                     size_t bs_in, size_t bs_out) {
+  const size_t per = rows * cols, total = per * batch;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = g / per, rem = g - b * per;
+    const size_t r = rem / cols, cc = rem - r * cols;
+    out[b * bs_out + r * ld_out + cc] = in[b * bs_in + r * ld_in + cc];
+  }
+}
+
+int launch_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
+                  size_t batch, size_t bs_in, size_t bs_out, int sm_count, void *stream) {
+  const size_t total = rows * cols * batch;
+  if (!total) return 0;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == 1) copy2d_kernel<double><<<(unsigned)blocks, 256, 0, s>>>((const cx<double> *)in, (cx<double> *)out, rows, cols, ld_in, ld_out, batch, bs_in, bs_out);
+  else copy2d_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const cx<float> *)in, (cx<float> *)out, rows, cols, ld_in, ld_out, batch, bs_in, bs_out);
+  return (int)cudaGetLastError();
+}
+
 int launch_cmul(int dtype, const void *a, const void *f, void *out, size_t n_inner, size_t n_batch, double scale,
                 int sm_count, void *stream) {
   const size_t total = n_inner * n_batch;

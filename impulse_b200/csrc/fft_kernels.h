@@ -20,4 +20,7 @@ int launch_cmul(int dtype, const void *a, const void *f, void *out, size_t n_inn
 // out[b][c][r] = in[b][r][c], complex elements, leading dimensions in elements
 int launch_transpose(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
                      size_t batch, int sm_count, void *stream);
+// out[b][r][c] = in[b][r][c] for complex matrices with independent leading dimensions / batch strides
+int launch_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
+                  size_t batch, size_t bs_in, size_t bs_out, int sm_count, void *stream);
 }  // namespace impulse

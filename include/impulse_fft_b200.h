@@ -112,6 +112,12 @@ int impulse_fft_cmul(int dtype, const void *a, const void *filter, void *out, si
 int impulse_fft_transpose(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in,
                           size_t ld_out, size_t batch, void *stream);
 
+/* Batched strided copy of complex matrices, out[b][r][c] = in[b][r][c], leading dimensions and batch
+ * strides in elements.  Packs the per-peer column blocks of a row slab into contiguous send buffers
+ * ahead of the all-to-all of the multi-GPU 2-D transform.  Device pointers. */
+int impulse_fft_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
+                       size_t batch, size_t bs_in, size_t bs_out, void *stream);
+
 /* Introspection (tests, benchmarks). */
 typedef struct {
   uint32_t n_steps;        /* kernel launches per execute                       */

@@ -1,0 +1,46 @@
+"""Worker for tests/test_gpu_dist.py: run under torch.distributed.run with one rank per GPU (NCCL)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from impulse_b200 import dist as idist  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    chk = oracle.load()
+    rng = np.random.default_rng(4321)
+    ok = True
+    for shape, restore in (((64, 96), False), ((64, 96), True), ((1024, 2048), False), ((2048, 1024), True)):
+        full = rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)
+        lo, hi = idist.shard_rows(shape[0], rank, world)
+        local_x = torch.from_numpy(full[lo:hi].copy()).cuda()
+        res = idist.fft2_slab(local_x, True, 1.0, restore=restore).cpu().numpy()
+        want = chk.c2c(full, [0, 1], True, 1.0, nthreads=0)
+        cb = shape[1] // world
+        ref = want[lo:hi] if restore else want[:, rank * cb:(rank + 1) * cb]
+        err = oracle.rel_l2(res, ref)
+        tol = 1e-12 * np.log2(max(shape))
+        print(f"rank {rank} fft2_slab {shape} restore={restore} rel_l2={err:.3e}", flush=True)
+        ok = ok and err <= tol
+        # round trip through the inverse slab transform (column slab -> needs row slab input: use restore)
+    rows = idist.fft_rows_sharded(local_x, True, 1.0).cpu().numpy()
+    err = oracle.max_row_rel_l2(rows, chk.c2c(full[lo:hi], [1], True, 1.0))
+    ok = ok and err <= 1e-12 * 11
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

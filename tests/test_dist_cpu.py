@@ -1,0 +1,94 @@
+"""Multi-process (world_size 2 and 4, gloo, CPU) tests of the distributed host logic in
+impulse_b200.dist: partitioning, per-peer packing and the all-to-all of the slab fft2.  The
+arithmetic engine injected here is the host emulation of the CUDA phases (tests/emu) — the
+product engine (CudaEngine) is exercised by the GPU tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from impulse_b200 import dist as idist
+from oracle import oracle
+
+
+class EmuEngine:
+    def c2c_axis(self, x, out, axis, forward, fct=1.0):
+        from tests.emu import harness as emu
+        emu.nd("c2c", x.numpy(), out.numpy(), tuple(x.shape), [axis], forward, fct)
+        return out
+
+    def pack_blocks(self, x, out, nblocks):
+        r, c = x.shape
+        cb = c // nblocks
+        out.copy_(x.view(r, nblocks, cb).permute(1, 0, 2))
+        return out
+
+    def unpack_blocks(self, x, out, nblocks):
+        nb, r, cb = x.shape
+        out.view(r, nb, cb).copy_(x.permute(1, 0, 2))
+        return out
+
+    def empty(self, shape, like):
+        return torch.empty(shape, dtype=like.dtype)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, shape, restore, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(99)
+        full = rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)
+        lo, hi = idist.shard_rows(shape[0], rank, world)
+        local = torch.from_numpy(full[lo:hi].copy())
+        res = idist.fft2_slab(local, True, 0.5, engine=EmuEngine(), restore=restore)
+        want = oracle.load().c2c(full, [0, 1], True, 0.5)
+        if restore:
+            err = oracle.rel_l2(res.numpy(), want[lo:hi])
+        else:
+            cb = shape[1] // world
+            err = oracle.rel_l2(res.numpy(), want[:, rank * cb:(rank + 1) * cb])
+        # batch sharding: no collective, each rank its own rows
+        rows = idist.fft_rows_sharded(local, True, 1.0, engine=EmuEngine())
+        err2 = oracle.max_row_rel_l2(rows.numpy(), oracle.load().c2c(full[lo:hi], [1], True, 1.0))
+        q.put((rank, err, err2))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,restore", [(2, (16, 24), False), (2, (16, 24), True), (4, (32, 20), False),
+                                                  (4, (8, 64), True)])
+def test_fft2_slab_gloo(world, shape, restore):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, restore, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert [g[0] for g in got] == list(range(world))
+    for _, err, err2 in got:
+        assert err <= 1e-12 * 6 and err2 <= 1e-12 * 6, (err, err2)
+
+
+def test_shard_rows_partition():
+    for n in (1, 7, 64, 65536, 1000003):
+        for w in (1, 2, 3, 4, 8):
+            parts = [idist.shard_rows(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
