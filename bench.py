@@ -42,6 +42,7 @@ WORKLOADS = {
     "c2c_8192x8192_c128": ("c2c", 8192, 8192, "f64"),
     "c2c_131072x1024_c64": ("c2c", 131072, 1024, "f32"),
     "fft2_8192x8192_c128": ("fft2", 8192, 8192, "f64"),
+    "filter2d_64x4096x4096_f32": ("filter2d", 64, 4096, "f32"),
 }
 DEFAULT_WORKLOAD = "c2c_65536x1024_c128"
 
@@ -52,6 +53,8 @@ def algorithmic_bytes(kind, rows, n, dtype):
         return rows * n * 2 * r * 2          # read + write one complex element each
     if kind == "fft2":
         return 2 * rows * n * 2 * r * 2      # two passes, each one read + one write
+    if kind == "filter2d":                   # rows = images, n = P: SURVEY 8(d) config 5 (circular, P x P)
+        return rows * (2 * r * n * n + 8 * n * (n // 2 + 1) * r)
     return rows * (n * r + (n // 2 + 1) * 2 * r)  # real side + half-spectrum side
 
 
@@ -217,7 +220,16 @@ def main():
     cdt = torch.complex128 if dtype == "f64" else torch.complex64
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     slab = kind == "fft2" and world > 1
-    if slab:
+    filt = None
+    if kind == "filter2d":
+        from impulse_b200.filter import FFTFilter2D
+        from impulse_b200 import dist as idist
+        lo, hi = idist.shard_rows(rows, rank, world) if world > 1 else (0, rows)
+        x = torch.rand((hi - lo, n, n), generator=g, device=dev, dtype=rdt)
+        ker = torch.rand((31, 31), generator=g, device=dev, dtype=rdt)
+        filt = FFTFilter2D(ker / ker.sum(), n, n)
+        y = torch.empty_like(x)
+    elif slab:
         # ONE 2-D transform split by row slabs: total work fixed ("strong"), one NCCL all-to-all per step
         from impulse_b200 import dist as idist
         lo, hi = idist.shard_rows(rows, rank, world)
@@ -233,11 +245,13 @@ def main():
         x = torch.view_as_complex(torch.rand((rows, n // 2 + 1, 2), generator=g, device=dev, dtype=rdt) - 0.5)
         y = torch.empty((rows, n), device=dev, dtype=rdt)
     fdesc = ib.FFTDesc.init(axes=[0, 1] if kind == "fft2" else [1], forward=(kind != "c2r"), scalingFactor=1.0)
-    if not slab:
+    if not slab and filt is None:
         din, dout = ib.DataDesc.init(x), ib.DataDesc.init(y)
 
     def step():
-        if slab:
+        if filt is not None:
+            filt.apply(x, out=y)
+        elif slab:
             idist.fft2_slab(x, True, 1.0)
         else:
             fdesc.apply(dout, din)
@@ -269,11 +283,12 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / steps
     bytes_per_gpu = algorithmic_bytes(kind, rows, n, dtype)
-    value = (1 if slab else world) * bytes_per_gpu / (ms_per_step * 1e-3) / 1e9
+    strong = slab or (filt is not None and world > 1)   # total work fixed, split over ranks
+    value = (1 if strong else world) * bytes_per_gpu / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e: public API with pinned HOST buffers, copies inside the timed region
     e2e = None
-    if not args.no_e2e and not slab:
+    if not args.no_e2e and not slab and filt is None:
         hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
         hy = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
         hx.copy_(x)
@@ -306,7 +321,7 @@ def main():
         line = {
             "metric": "batched fp64 FFT throughput (algorithmic GB/s)" if dtype == "f64" else "batched fp32 FFT throughput (algorithmic GB/s)",
             "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong" if slab else "weak",
+            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": args.workload, "rows_per_gpu": (rows // world) if slab else rows, "length": n, "kind": kind,
                        "placement": "out of place, device resident", "l2": "input+output per step exceed the 126 MB L2"
@@ -322,7 +337,7 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu and world == 1:
+        if not args.no_cpu and world == 1 and filt is None:
             try:
                 _, info = cpu_reference(kind, rows, n, dtype)
                 line["cpu_baseline"] = info

@@ -115,7 +115,7 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     return fail(IMPULSE_FFT_ERR_STRIDE, "data pointer is not aligned to its element size");
   if (in == out && nd.desc.kind == KIND_C2C && nd.desc.stride_in != nd.desc.stride_out)
     return fail(IMPULSE_FFT_ERR_STRIDE, "stride mismatch");  // hdronly.h:455-456
-  void *tmp = nullptr, *tmp2 = nullptr;
+  void *tmp = nullptr, *tmp2 = nullptr, *tmp3 = nullptr;
   if (nd.tmp_bytes) {
     cudaError_t e = cudaMallocAsync(&tmp, nd.tmp_bytes, stream);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(tmp)");
@@ -124,12 +124,22 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     cudaError_t e = cudaMallocAsync(&tmp2, nd.tmp2_bytes, stream);
     if (e != cudaSuccess) { if (tmp) cudaFreeAsync(tmp, stream); return cuda_fail(e, "cudaMallocAsync(tmp2)"); }
   }
+  if (nd.tmp3_bytes) {
+    cudaError_t e = cudaMallocAsync(&tmp3, nd.tmp3_bytes, stream);
+    if (e != cudaSuccess) {
+      if (tmp) cudaFreeAsync(tmp, stream);
+      if (tmp2) cudaFreeAsync(tmp2, stream);
+      return cuda_fail(e, "cudaMallocAsync(tmp3)");
+    }
+  }
   int rc = 0;
   for (const Step &st : nd.steps) {
     LineJob J = st.job;
     const unsigned char *src = st.src == BUF_IN ? (const unsigned char *)in : st.src == BUF_OUT ? (const unsigned char *)out
-                               : st.src == BUF_TMP ? (const unsigned char *)tmp : (const unsigned char *)tmp2;
-    unsigned char *dst = st.dst == BUF_OUT ? (unsigned char *)out : st.dst == BUF_TMP ? (unsigned char *)tmp : (unsigned char *)tmp2;
+                               : st.src == BUF_TMP ? (const unsigned char *)tmp
+                               : st.src == BUF_TMP2 ? (const unsigned char *)tmp2 : (const unsigned char *)tmp3;
+    unsigned char *dst = st.dst == BUF_OUT ? (unsigned char *)out : st.dst == BUF_TMP ? (unsigned char *)tmp
+                         : st.dst == BUF_TMP2 ? (unsigned char *)tmp2 : (unsigned char *)tmp3;
     J.in = src + st.src_off_bytes;
     J.out = dst + st.dst_off_bytes;
     J.fct = st.takes_fct ? fct : 1.0;
@@ -142,6 +152,7 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
   }
   if (tmp) cudaFreeAsync(tmp, stream);
   if (tmp2) cudaFreeAsync(tmp2, stream);
+  if (tmp3) cudaFreeAsync(tmp3, stream);
   return rc;
 }
 
@@ -159,7 +170,7 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
   if (nd.empty) return 0;
   const bool inplace = (in == out);
   // ---- try the chunked pipeline
-  if (nd.steps.size() == 1 && nd.tmp_bytes == 0 && nd.tmp2_bytes == 0) {
+  if (nd.steps.size() == 1 && nd.tmp_bytes == 0 && nd.tmp2_bytes == 0 && nd.tmp3_bytes == 0) {
     const Step &st = nd.steps[0];
     const LineJob &J0 = st.job;
     int od = -1;  // outermost batch dim in use
@@ -365,7 +376,7 @@ int impulse_fft_plan_get_info(impulse_fft_plan plan, impulse_fft_plan_info *info
   if (!plan || !info) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
   std::memset(info, 0, sizeof(*info));
   info->n_steps = (uint32_t)plan->nd.steps.size();
-  info->tmp_bytes = plan->nd.tmp_bytes + plan->nd.tmp2_bytes;
+  info->tmp_bytes = plan->nd.tmp_bytes + plan->nd.tmp2_bytes + plan->nd.tmp3_bytes;
   if (!plan->nd.steps.empty()) {
     const Step &s = plan->nd.steps[0];
     info->n_fft = s.job.n_fft;

@@ -158,7 +158,7 @@ IMP_HD void phase_prolog(const LineJob &J, const TileCtx &tc, uint32_t tid, int6
     uint64_t i2 = r / J.bdim[1];
     offs[3 * tid] = (int64_t)i0 * J.bs_in[0] + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
     offs[3 * tid + 1] = (int64_t)i0 * J.bs_out[0] + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
-    offs[3 * tid + 2] = (int64_t)(J.tw4_dim == 0 ? i0 : J.tw4_dim == 1 ? i1 : i2);
+    offs[3 * tid + 2] = (int64_t)(J.tw4_dim == 0 ? i0 : J.tw4_dim == 1 ? i1 : J.tw4_dim == 2 ? i2 : 0);
   }
 }
 
@@ -324,6 +324,7 @@ IMP_HD void phase_elementwise(const LineJob &J, const Phase &P, uint32_t tid, ui
     case OP_BLUE_PRE: n = J.n_fft; break;
     case OP_BLUE_MUL: n = J.n_fft; break;
     case OP_BLUE_POST: n = L; break;
+    case OP_MUL_CONJ_BK: n = L; break;
     case OP_C2R_PRE_EVEN: n = L / 2 + 1; break;
     default: return;
   }
@@ -348,6 +349,10 @@ IMP_HD void phase_elementwise(const LineJob &J, const Phase &P, uint32_t tid, ui
       case OP_BLUE_POST: {
         const uint32_t p = phys<T>(J, e);
         S[p] = cconj(cmul(S[p], IMP_LDG(bk + e)));
+      } break;
+      case OP_MUL_CONJ_BK: {
+        const uint32_t p = phys<T>(J, e);
+        S[p] = cmul(S[p], cconj(IMP_LDG(bk + e)));
       } break;
       case OP_C2R_PRE_EVEN: {
         // X[0..M] -> Z[k] = (X[k]+conj X[M-k]) + i e^{+2 pi i k/N} (X[k]-conj X[M-k])
@@ -418,6 +423,7 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e,
                                IMP_LDG((const cx<T> *)J.tw4_lo + (m & ((1u << J.tw4_shift) - 1))));
           v = cmul(v, cconj_if(w, (J.flags & F_CONJ_OUT) != 0));
         }
+        if (J.mul_tab) v = cmul(v, IMP_LDG((const cx<T> *)J.mul_tab + (tw_idx + J.mul_stride * e)));
         v.x *= f; v.y *= f;
       }
       outc[off + (int64_t)e * es] = cconj_if(v, cres);

@@ -36,6 +36,7 @@ enum PhaseOp : uint8_t {
   OP_BLUE_MUL = 4,      // s[p] = conj(s[p]*bkf[p])                              pocketfft.c:1973-1987
   OP_BLUE_POST = 5,     // s[k] = conj(s[k]*bk[k]) (k<L)                         pocketfft.c:1993-2005
   OP_C2R_PRE_EVEN = 6,  // half-spectrum X[0..M] -> packed complex Z[0..M-1]
+  OP_MUL_CONJ_BK = 7,   // s[k] = s[k]*conj(bk[k]) (k<L): last step of the multi-launch Bluestein
 };
 
 enum LoadMode : uint8_t {
@@ -122,6 +123,8 @@ struct LineJob {
   uint32_t tw4_shift;
   uint32_t tw4_dim;
   uint32_t zero_pad_from;  // ST_C: elements e >= this are stored as zero (0 = off; Bluestein staging)
+  const void *mul_tab;     // ST_C: multiply output element e by mul_tab[line_index + mul_stride*e] (null = off)
+  uint32_t mul_stride;
   double fct;
   Phase ph[kMaxPhases];
 };

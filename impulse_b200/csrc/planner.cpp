@@ -6,6 +6,7 @@
 #include <complex>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 
 namespace impulse {
 
@@ -150,7 +151,7 @@ std::vector<uint32_t> dif_positions(uint32_t n, const std::vector<uint32_t> &rad
 PlanCache::~PlanCache() {
   for (auto &kv : engines_) {
     Engine1D *e = kv.second.get();
-    for (void *p : {e->d_tw, e->d_perm, e->d_bk, e->d_bkf}) if (p) alloc_->release(p);
+    for (void *p : {e->d_tw, e->d_perm, e->d_bk, e->d_bkf, e->d_bkf_nat}) if (p) alloc_->release(p);
   }
   for (auto &kv : real_tw_) if (kv.second) alloc_->release(kv.second);
   for (auto &kv : tw4_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
@@ -194,12 +195,34 @@ int PlanCache::status_engine(uint32_t L, int dtype, const Engine1D **out, std::s
     host_fft(bw, e->radices);
     std::vector<cld> bkf(n);
     for (uint32_t k = 0; k < n; ++k) bkf[pos[k]] = bw[k];
+    e->bkf_nat_host.resize(2 * (size_t)n);
+    for (uint32_t k = 0; k < n; ++k) { e->bkf_nat_host[2 * k] = (double)bw[k].real(); e->bkf_nat_host[2 * k + 1] = (double)bw[k].imag(); }
     e->d_bk = upload_cplx(alloc_, bk, dtype);
     e->d_bkf = upload_cplx(alloc_, bkf, dtype);
     if (!e->d_bk || !e->d_bkf) { *err = "table upload failed"; return ERR_NOMEM; }
   }
   *out = e.get();
   engines_[key] = std::move(e);
+  return ST_OK;
+}
+
+int PlanCache::bluestein_natural_table(uint32_t L, int dtype, const void **out, std::string *err) {
+  const Engine1D *ce = nullptr;
+  int rc = status_engine(L, dtype, &ce, err);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(mu_);
+  Engine1D *e = engines_[std::make_pair(L, dtype)].get();
+  if (!e->blue) { *err = "not a Bluestein length"; return ERR_INVALID; }
+  if (!e->d_bkf_nat) {
+    if (dtype == DT_F64) {
+      e->d_bkf_nat = alloc_->upload(e->bkf_nat_host.data(), e->bkf_nat_host.size() * sizeof(double));
+    } else {
+      std::vector<float> f(e->bkf_nat_host.begin(), e->bkf_nat_host.end());
+      e->d_bkf_nat = alloc_->upload(f.data(), f.size() * sizeof(float));
+    }
+    if (!e->d_bkf_nat) { *err = "table upload failed"; return ERR_NOMEM; }
+  }
+  *out = e->d_bkf_nat;
   return ST_OK;
 }
 
@@ -267,15 +290,22 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     n_lines *= J->bdim[d];
   }
   J->n_lines = n_lines;
+  J->tw4_dim = s.tw4_dim;
   if (s.tw4_n) {
     rc = four_step_tables(s.tw4_n, s.dtype, &J->tw4_hi, &J->tw4_lo, &J->tw4_shift, err);
     if (rc) return rc;
     J->tw4_n = s.tw4_n;
-    J->tw4_dim = s.tw4_dim;
   }
   J->zero_pad_from = s.zero_pad_from;
+  J->mul_tab = s.mul_tab;
+  J->mul_stride = s.mul_stride;
+  if (s.blue_stage) {  // the line itself (L points) lives in shared memory; the n2-point work array is global
+    if (!E->blue) { *err = "internal: Bluestein staging on a direct length"; return ERR_INVALID; }
+    J->n_fft = L;
+    J->perm = nullptr;
+  }
 
-  uint32_t need = E->n_fft;  // shared-memory element slots per line
+  uint32_t need = J->n_fft;  // shared-memory element slots per line
   uint32_t flags = 0;
   std::vector<Phase> pre;
   switch (s.kind) {
@@ -340,7 +370,17 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     if (dit) std::reverse(ps.begin(), ps.end());
     prog.insert(prog.end(), ps.begin(), ps.end());
   };
-  if (E->blue) {
+  if (s.blue_stage == 1) {
+    Phase p{}; p.op = OP_BLUE_PRE; prog.push_back(p);
+    J->store_mode = ST_C; J->n_store = E->n_fft; J->zero_pad_from = L;
+    flags &= ~(uint32_t)(F_CONJ_OUT | F_CONJ_RESULT);
+  } else if (s.blue_stage == 2) {
+    prog.clear();
+    Phase p{}; p.op = OP_MUL_CONJ_BK; prog.push_back(p);
+    J->load_mode = LD_C; J->n_load = L;
+    flags &= ~(uint32_t)(F_CONJ_IN | F_CONJ_SEQ);
+    need = L;
+  } else if (E->blue) {
     Phase p{}; p.op = OP_BLUE_PRE; prog.push_back(p);
     add_passes(false);
     p.op = OP_BLUE_MUL; prog.push_back(p);
@@ -369,7 +409,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   C = std::min<uint32_t>(C, kMaxLinesPerCta);
   while (C > 1 && (size_t)C * pitch_for(C) * esz > budget) C /= 2;
   if ((size_t)C * pitch_for(C) * esz > budget) {
-    *err = "line of " + std::to_string(E->n_fft) + " points does not fit in shared memory";
+    *err = "line of " + std::to_string(J->n_fft) + " points does not fit in shared memory";
     return ERR_UNSUPPORTED;
   }
   C = std::min<uint32_t>(C, pow2ceil(n_lines));
@@ -378,7 +418,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   J->swz_mask = (C < S) ? (S - 1) : 0;
   const size_t smem_bytes = kSmemHeaderBytes + (size_t)C * J->pitch * esz;
   const int tmax = smem_bytes > max_smem / 2 ? kMaxThreadsBig : kMaxThreads;
-  int threads = (int)std::min<uint64_t>(tmax, std::max<uint64_t>(64, (((uint64_t)C * E->n_fft / 8) + 31) / 32 * 32));
+  int threads = (int)std::min<uint64_t>(tmax, std::max<uint64_t>(64, (((uint64_t)C * J->n_fft / 8) + 31) / 32 * 32));
   int envT = env_int("IMPULSE_FFT_THREADS", 0);
   if (envT > 0) threads = std::min(tmax, (envT + 31) / 32 * 32);
   cfg->threads = threads;
@@ -396,7 +436,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
 
   // specialised kernels: contiguous complex rows, one batch dimension, headline lengths
   J->fast_id = FAST_NONE;
-  if (s.kind == KIND_C2C && !E->blue && !s.tw4_n && !s.zero_pad_from && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
+  if (s.kind == KIND_C2C && !E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
       !env_int("IMPULSE_FFT_NO_FAST", 0)) {
     if (f64 && N == 1024) J->fast_id = FAST2_1024_F64;
     else if (f64 && N == 512) J->fast_id = FAST2_512_F64;
@@ -432,6 +472,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   plan->steps.clear();
   plan->tmp_bytes = 0;
   plan->tmp2_bytes = 0;
+  plan->tmp3_bytes = 0;
   const size_t nd = d.shape.size();
   // sanity_check (pocketfft_hdronly.h:446-476)
   if (nd < 1) { *err = "ndim must be >= 1"; return ERR_INVALID; }
@@ -479,7 +520,8 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   // ---- emit one batched line transform; `dims` are the batch dimensions (element units)
   struct TwDim { bool on = false; uint32_t n = 0; };  // four-step: which dim indexes n2, and N
   auto emit = [&](int kind, int layout, bool forward, uint32_t N, int64_t es_in, int64_t es_out,
-                  std::vector<Dim> dims, int tw_key /*index into dims of the n2 dim, -1 = none*/, uint32_t tw4_n,
+                  std::vector<Dim> dims, int tw_key /*index into dims of the line-index dim, -1 = none*/, uint32_t tw4_n,
+                  const void *mul_tab, uint32_t mul_stride, int blue_stage,
                   size_t esz_in, size_t esz_out, int src, int dst, int64_t src_base, int64_t dst_base,
                   bool takes_fct) -> int {
     std::vector<int> key(dims.size());
@@ -524,6 +566,9 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       s.bdim[i] = sd[i].n; s.bs_in[i] = sd[i].sin; s.bs_out[i] = sd[i].sout;
       if (is_tw[i]) { s.tw4_n = tw4_n; s.tw4_dim = (uint32_t)i; }
     }
+    s.mul_tab = mul_tab;
+    s.mul_stride = mul_stride;
+    s.blue_stage = blue_stage;
     std::vector<Dim> outer(sd.begin() + (ptrdiff_t)nk, sd.end());
     uint64_t nouter = 1;
     for (auto &o : outer) nouter *= o.n;
@@ -549,38 +594,36 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   auto span_lo_hi = [&](int b, ptrdiff_t *lo, ptrdiff_t *hi) {
     if (b == BUF_IN) { *lo = plan->in_lo; *hi = plan->in_hi; }
     else if (b == BUF_OUT) { *lo = plan->out_lo; *hi = plan->out_hi; }
+    else if (b == BUF_TMP3) { *lo = 0; *hi = (ptrdiff_t)plan->tmp3_bytes; }
     else { *lo = 0; *hi = (ptrdiff_t)plan->tmp_bytes; }
   };
 
-  // one batched line transform along `axis`
-  auto add_axis = [&](int kind, int layout, bool forward, size_t axis, uint32_t N,
-                      const std::vector<size_t> &bshape, const std::vector<ptrdiff_t> &sin, size_t esz_in,
-                      const std::vector<ptrdiff_t> &sout, size_t esz_out, int src, int dst, bool takes_fct) -> int {
-    std::vector<Dim> dims;
-    for (size_t i = 0; i < nd; ++i) {
-      if (i == axis || bshape[i] == 1) continue;
-      dims.push_back({bshape[i], sin[i] / (ptrdiff_t)esz_in, sout[i] / (ptrdiff_t)esz_out});
-    }
-    const int64_t es_in = sin[axis] / (ptrdiff_t)esz_in, es_out = sout[axis] / (ptrdiff_t)esz_out;
-    // ---- does the line fit one CTA with coalesced access?  If not, split N = N1*N2 (four-step).
+  const size_t csize_g = d.dtype == DT_F64 ? 16 : 8;
+  const uint32_t S_g = d.dtype == DT_F64 ? 8 : 16;
+  const size_t budget_g = max_smem - kSmemHeaderBytes;
+  auto fits_one = [&](uint64_t n) { return (size_t)(n + S_g) * csize_g <= budget_g; };
+
+  // complex line transform of length N; splits N = N1*N2 over two launches when one CTA cannot hold the
+  // line, or cannot hold S adjacent lines of a strided axis.  mul_tab (optional) multiplies output k.
+  std::function<int(bool, uint32_t, int64_t, int64_t, const std::vector<Dim> &, size_t, size_t, int, int, int64_t, int64_t,
+                    bool, const void *)>
+      emit_c2c = [&](bool forward, uint32_t N, int64_t es_in, int64_t es_out, const std::vector<Dim> &dims, size_t esz_in,
+                     size_t esz_out, int src, int dst, int64_t src_base, int64_t dst_base, bool takes_fct,
+                     const void *mul_tab) -> int {
     bool split = false;
-    if (kind == KIND_C2C && N >= 64 && !choose_radices(N).empty()) {
-      const size_t csize = d.dtype == DT_F64 ? 16 : 8;
-      const uint32_t S = d.dtype == DT_F64 ? 8 : 16;
-      const size_t budget = max_smem - kSmemHeaderBytes;
-      const bool fits1 = (size_t)(N + S) * csize <= budget;
-      const bool fitsS = (size_t)S * (N + S + 1) * csize <= budget;
+    if (N >= 64 && !choose_radices(N).empty()) {
+      const bool fitsS = (size_t)S_g * (N + S_g + 1) * csize_g <= budget_g;
       uint64_t fastest_in = ~0ull, fastest_out = ~0ull;
       for (auto &dm : dims) {
         fastest_in = std::min<uint64_t>(fastest_in, (uint64_t)std::llabs(dm.sin));
         fastest_out = std::min<uint64_t>(fastest_out, (uint64_t)std::llabs(dm.sout));
       }
       const bool strided = (!dims.empty()) && (fastest_in < (uint64_t)std::llabs(es_in) || fastest_out < (uint64_t)std::llabs(es_out));
-      split = !fits1 || (strided && !fitsS) || env_int("IMPULSE_FFT_FORCE_FOURSTEP", 0);
+      split = !fits_one(N) || (strided && !fitsS) || env_int("IMPULSE_FFT_FORCE_FOURSTEP", 0);
     }
     if (!split)
-      return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
-
+      return emit(KIND_C2C, RL_HERMITIAN, forward, N, es_in, es_out, dims, -1, 0, mul_tab, 1, 0, esz_in, esz_out, src, dst,
+                  src_base, dst_base, takes_fct);
     // N1 = largest divisor of N not above sqrt(N); both halves then run in shared memory
     uint32_t N1 = 1;
     for (uint32_t f = 1; (uint64_t)f * f <= N; ++f) if (N % f == 0) N1 = f;
@@ -594,15 +637,62 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     std::vector<Dim> da;
     da.push_back({N2, es_in, es_in});
     for (auto &dm : dims) da.push_back({dm.n, dm.sin, dm.sin});
-    int rc = emit(KIND_C2C, RL_HERMITIAN, forward, N1, es_in * (int64_t)N2, es_in * (int64_t)N2, da, 0, N, esz_in, esz_in,
-                  src, BUF_TMP2, 0, -(int64_t)slo, false);
+    int rc = emit(KIND_C2C, RL_HERMITIAN, forward, N1, es_in * (int64_t)N2, es_in * (int64_t)N2, da, 0, N, nullptr, 0, 0,
+                  esz_in, esz_in, src, BUF_TMP2, src_base, -(int64_t)slo + src_base, false);
     if (rc) return rc;
     // step B: for every (line, k1): FFT over n2 of scratch[(k1*N2 + n2)*es_in] -> dst[(k1 + N1*k2)*es_out]
     std::vector<Dim> db;
     db.push_back({N1, es_in * (int64_t)N2, es_out});
     for (auto &dm : dims) db.push_back({dm.n, dm.sin, dm.sout});
-    return emit(KIND_C2C, RL_HERMITIAN, forward, N2, es_in, es_out * (int64_t)N1, db, -1, 0, esz_in, esz_out, BUF_TMP2, dst,
-                -(int64_t)slo, 0, takes_fct);
+    return emit(KIND_C2C, RL_HERMITIAN, forward, N2, es_in, es_out * (int64_t)N1, db, mul_tab ? 0 : -1, 0, mul_tab, N1, 0,
+                esz_in, esz_out, BUF_TMP2, dst, -(int64_t)slo + src_base, dst_base, takes_fct);
+  };
+
+  // one batched line transform along `axis`
+  auto add_axis = [&](int kind, int layout, bool forward, size_t axis, uint32_t N,
+                      const std::vector<size_t> &bshape, const std::vector<ptrdiff_t> &sin, size_t esz_in,
+                      const std::vector<ptrdiff_t> &sout, size_t esz_out, int src, int dst, bool takes_fct) -> int {
+    std::vector<Dim> dims;
+    for (size_t i = 0; i < nd; ++i) {
+      if (i == axis || bshape[i] == 1) continue;
+      dims.push_back({bshape[i], sin[i] / (ptrdiff_t)esz_in, sout[i] / (ptrdiff_t)esz_out});
+    }
+    const int64_t es_in = sin[axis] / (ptrdiff_t)esz_in, es_out = sout[axis] / (ptrdiff_t)esz_out;
+    const uint32_t L = (kind != KIND_C2C && N % 2 == 0) ? N / 2 : N;  // complex length run on the device
+    const Engine1D *E = nullptr;
+    int rc = status_engine(L, d.dtype, &E, err);
+    if (rc) return rc;
+    if (E->blue && (!fits_one(E->n_fft) || env_int("IMPULSE_FFT_FORCE_BIGBLUE", 0))) {
+      // ---- multi-launch Bluestein: the L-point line fits a CTA, its n2-point work array does not.
+      //   1. load + (c2r pre-twiddle) + chirp, zero-padded to n2, into the work array [lines][n2]
+      //   2. forward FFT(n2) (two launches), output multiplied by FFT(b)/n2
+      //   3. backward FFT(n2) (two launches)
+      //   4. chirp + the transform's own store
+      if (!fits_one(L + 1)) { *err = "line of " + std::to_string(L) + " points does not fit in shared memory"; return ERR_UNSUPPORTED; }
+      const uint32_t n2 = E->n_fft;
+      const void *bkf_nat = nullptr;
+      rc = bluestein_natural_table(L, d.dtype, &bkf_nat, err);
+      if (rc) return rc;
+      uint64_t nlines = 1;
+      std::vector<Dim> d_in, d_w, d_out;  // batch dims: source->work, work->work, work->destination
+      for (auto &dm : dims) {
+        d_in.push_back({dm.n, dm.sin, (int64_t)(nlines * n2)});
+        d_w.push_back({dm.n, (int64_t)(nlines * n2), (int64_t)(nlines * n2)});
+        d_out.push_back({dm.n, (int64_t)(nlines * n2), dm.sout});
+        nlines *= dm.n;
+      }
+      plan->tmp3_bytes = std::max<size_t>(plan->tmp3_bytes, (size_t)nlines * n2 * csize_g);
+      rc = emit(kind, layout, forward, N, es_in, 1, d_in, -1, 0, nullptr, 0, 1, esz_in, csize_g, src, BUF_TMP3, 0, 0, false);
+      if (rc) return rc;
+      rc = emit_c2c(true, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, bkf_nat);
+      if (rc) return rc;
+      rc = emit_c2c(false, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, nullptr);
+      if (rc) return rc;
+      return emit(kind, layout, forward, N, 1, es_out, d_out, -1, 0, nullptr, 0, 2, csize_g, esz_out, BUF_TMP3, dst, 0, 0, takes_fct);
+    }
+    if (kind == KIND_C2C)
+      return emit_c2c(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, 0, 0, takes_fct, nullptr);
+    return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, nullptr, 0, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
   };
 
   int rc = ST_OK;

@@ -47,6 +47,8 @@ struct Engine1D {
   bool blue = false;
   std::vector<uint32_t> radices;  // DIF order
   void *d_tw = nullptr, *d_perm = nullptr, *d_bk = nullptr, *d_bkf = nullptr;
+  void *d_bkf_nat = nullptr;  // FFT(b)/n2 in natural order (multi-launch Bluestein), uploaded on demand
+  std::vector<double> bkf_nat_host;  // interleaved re,im in double; kept for the on-demand upload
 };
 
 struct LaunchCfg {
@@ -62,11 +64,14 @@ struct LineSpec {
   uint64_t bdim[kMaxBatchDims] = {1, 1, 1};
   int64_t bs_in[kMaxBatchDims] = {0, 0, 0}, bs_out[kMaxBatchDims] = {0, 0, 0};
   int64_t es_in = 1, es_out = 1;  // element units of the respective side
-  uint32_t tw4_n = 0, tw4_dim = 0;  // four-step store twiddle (first of the two launches)
+  uint32_t tw4_n = 0, tw4_dim = 3;  // four-step store twiddle (first of the two launches); dim 3 = none
   uint32_t zero_pad_from = 0;
+  const void *mul_tab = nullptr;  // ST_C: multiply by a table indexed line_index + mul_stride*e
+  uint32_t mul_stride = 0;
+  int blue_stage = 0;  // multi-launch Bluestein: 1 = load+chirp+zero-pad to scratch, 2 = scratch+chirp+store
 };
 
-enum BufId : int { BUF_IN = 0, BUF_OUT = 1, BUF_TMP = 2, BUF_TMP2 = 3 };
+enum BufId : int { BUF_IN = 0, BUF_OUT = 1, BUF_TMP = 2, BUF_TMP2 = 3, BUF_TMP3 = 4 };
 
 struct Step {
   LineJob job;
@@ -89,6 +94,7 @@ struct NdPlan {
   std::vector<Step> steps;
   size_t tmp_bytes = 0;   // c2r N-D intermediate (hdronly.h:3384)
   size_t tmp2_bytes = 0;  // four-step scratch
+  size_t tmp3_bytes = 0;  // multi-launch Bluestein work array [lines][n2]
   // byte spans touched relative to the base pointers (for host staging)
   ptrdiff_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
   bool empty = false;  // zero-size array: nothing to do
@@ -103,6 +109,7 @@ class PlanCache {
   size_t max_smem = 227 * 1024;
   int status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err);
   int real_twiddle(uint32_t N, int dtype, const void **out, std::string *err);
+  int bluestein_natural_table(uint32_t L, int dtype, const void **out, std::string *err);
   int four_step_tables(uint32_t N, int dtype, const void **hi, const void **lo, uint32_t *shift, std::string *err);
   int build_line_job(const LineSpec &s, LineJob *job, LaunchCfg *cfg, std::string *err);
   int build_nd(const NdDesc &d, NdPlan *plan, std::string *err);

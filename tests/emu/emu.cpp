@@ -61,10 +61,10 @@ int emu_nd(int kind, int dtype, int layout, size_t ndim, const size_t *shape, co
   int rc = g_cache->build_nd(d, &plan, &g_err);
   if (rc) return rc;
   if (plan.empty) return 0;
-  std::vector<unsigned char> tmp(plan.tmp_bytes + 16), tmp2(plan.tmp2_bytes + 16, 0xCD);
+  std::vector<unsigned char> tmp(plan.tmp_bytes + 16), tmp2(plan.tmp2_bytes + 16, 0xCD), tmp3(plan.tmp3_bytes + 16, 0xCD);
   for (Step &st : plan.steps) {
-    const unsigned char *bufs_in[4] = {(const unsigned char *)in, (const unsigned char *)out, tmp.data(), tmp2.data()};
-    unsigned char *bufs_out[4] = {nullptr, (unsigned char *)out, tmp.data(), tmp2.data()};
+    const unsigned char *bufs_in[5] = {(const unsigned char *)in, (const unsigned char *)out, tmp.data(), tmp2.data(), tmp3.data()};
+    unsigned char *bufs_out[5] = {nullptr, (unsigned char *)out, tmp.data(), tmp2.data(), tmp3.data()};
     st.job.in = bufs_in[st.src] + st.src_off_bytes;
     st.job.out = bufs_out[st.dst] + st.dst_off_bytes;
     st.job.fct = st.takes_fct ? fct : 1.0;

@@ -205,3 +205,47 @@ def test_four_step_split(checker, monkeypatch):
     assert oracle.rel_l2(spec, checker.r2c(r, [0, 1], True, 1.0)) <= tol(80)
     back = emu.nd("c2r", spec, np.zeros_like(r), r.shape, [0, 1], False, 1.0 / r.size)
     assert oracle.rel_l2(back, r) <= tol(80)
+
+
+def test_multi_launch_bluestein(checker, monkeypatch):
+    """Bluestein lengths whose n2 exceeds one CTA's shared memory (odd N > 7204 with a large prime
+    factor, complex primes > 7232) run as stage-in / FFT(n2) x bkf / IFFT(n2) / stage-out launches."""
+    rng = np.random.default_rng(13)
+    # natural triggers at the top of the reference's 1..8191 sweep
+    for n in (7211, 7919, 8191):
+        r = rnd(rng, (2, n), np.float64)
+        assert emu.nd_steps("r2c", r, np.zeros((2, n // 2 + 1), np.complex128), r.shape, [1]) == 6, n
+        got = emu.nd("r2c", r, np.zeros((2, n // 2 + 1), np.complex128), r.shape, [1], True, 1.0)
+        want = checker.r2c(r, [1], True, 1.0)
+        assert oracle.max_row_rel_l2(got, want) <= tol(n), n
+        back = emu.nd("c2r", want, np.zeros_like(r), r.shape, [1], False, 1.0 / n)
+        assert oracle.max_row_rel_l2(back, r) <= tol(n), n
+        d = r[:1].copy()
+        emu.nd("r2c", d, d, d.shape, [1], True, 1.0, layout="halfcomplex")
+        assert oracle.rel_l2(d, checker.rfft_rows(r[:1].copy(), True, 1.0)) <= tol(n), n
+        emu.nd("c2r", d, d, d.shape, [1], False, 1.0 / n, layout="halfcomplex")
+        assert oracle.rel_l2(d, r[:1]) <= 2e-15 * np.log2(n), n
+    x = rnd(rng, (2, 7879), np.complex128)
+    for fwd in (True, False):
+        got = emu.nd("c2c", x, np.empty_like(x), x.shape, [1], fwd, 0.5)
+        assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.5)) <= tol(7879), fwd
+    # forced on small Bluestein lengths: every kind / layout / parity, batches and strides
+    monkeypatch.setenv("IMPULSE_FFT_FORCE_BIGBLUE", "1")
+    for n in (37, 74, 97, 134, 191, 382, 1009, 2018):
+        c = rnd(rng, (3, n), np.complex128)
+        for fwd in (True, False):
+            got = emu.nd("c2c", c, np.empty_like(c), c.shape, [1], fwd, 1.0)
+            assert oracle.max_row_rel_l2(got, checker.c2c(c, [1], fwd, 1.0)) <= tol(n), (n, fwd)
+        r = rnd(rng, (3, n), np.float64)
+        for fwd in (True, False):
+            got = emu.nd("r2c", r, np.zeros((3, n // 2 + 1), np.complex128), r.shape, [1], fwd, 1.0)
+            assert oracle.max_row_rel_l2(got, checker.r2c(r, [1], fwd, 1.0)) <= tol(n), (n, fwd)
+        spec = checker.r2c(r, [1], True, 1.0)
+        for fwd in (False, True):
+            got = emu.nd("c2r", spec, np.zeros_like(r), r.shape, [1], fwd, 1.0 / n)
+            assert oracle.max_row_rel_l2(got, checker.c2r(spec, r.shape, [1], fwd, 1.0 / n)) <= tol(n), (n, fwd)
+        full = emu.nd("r2c", r, np.zeros((3, n), np.complex128), r.shape, [1], True, 1.0, layout="fullsym")
+        assert oracle.max_row_rel_l2(full, checker.c2c(r.astype(np.complex128), [1], True, 1.0)) <= tol(n), n
+    a = rnd(rng, (6, 37, 5), np.complex64)[:, :, ::-1]
+    got = emu.nd("c2c", a, np.empty(a.shape, np.complex64), a.shape, [1], True, 1.0)
+    assert oracle.rel_l2(got, checker.c2c(a, [1], True, 1.0)) <= tol(37, np.float32)

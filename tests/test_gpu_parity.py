@@ -133,8 +133,8 @@ def test_c2c_lengths(ib, torch_mod, checker, dtype):
 def test_real_roundtrip_all_lengths(ib, torch_mod, checker):
     """tests/test_fft.nim:29-109 — every length 1..8191, forward then backward(1/N) through the
     packed in-place layout recovers the input; forward parity vs the oracle on every length too.
-    Lengths whose Bluestein size exceeds one CTA's shared memory are reported unsupported (not
-    silently wrong): they must raise, and are listed in DESIGN.md as the open gap."""
+    Every length must be supported: Bluestein sizes beyond one CTA's shared memory (odd N > 7204 with
+    a large prime factor) take the multi-launch path."""
     rng = np.random.default_rng(7)
     odata = rng.uniform(-0.5, 0.5, 8192)
     odata[0] = 0.340188
@@ -156,7 +156,7 @@ def test_real_roundtrip_all_lengths(ib, torch_mod, checker):
         worst_rt = max(worst_rt, oracle.rel_l2(d.cpu().numpy(), odata[:n]) / max(1.0, np.log2(n)))
     assert worst_fw <= 1e-12, worst_fw
     assert worst_rt <= 2e-15, worst_rt
-    assert all(n > 7200 and n % 2 == 1 for n in unsupported), unsupported[:10]
+    assert not unsupported, unsupported[:10]
     print(f"unsupported lengths: {len(unsupported)}; worst forward {worst_fw:.2e}, round trip {worst_rt:.2e} (per log2 N)")
 
 
@@ -370,3 +370,33 @@ def test_config4_full_size_properties(ib, torch_mod):
     apply_nd(ib, "c2c", y, y, [0, 1], False, 1.0 / (8192.0 * 8192.0))
     err = float(torch_mod.linalg.vector_norm(y - x) / torch_mod.linalg.vector_norm(x))
     assert err <= 2e-15 * 26, err
+
+
+def test_fft_filter2d(ib, torch_mod, checker):
+    """BASELINE config 5 path (r2c -> multiply -> c2r, float32) at a reduced size, against the same
+    composition on the oracle and against a direct circular convolution."""
+    from impulse_b200.filter import FFTFilter2D
+    rng = np.random.default_rng(15)
+    for (b, h, w, kh, kw, dt, rt) in ((3, 64, 96, 5, 7, np.float32, 2e-5), (2, 40, 36, 31, 31, np.float64, 1e-12),
+                                      (2, 512, 512, 31, 31, np.float32, 2e-5)):
+        img = rng.uniform(0, 1, (b, h, w)).astype(dt)
+        ker = rng.uniform(0, 1, (kh, kw)).astype(dt)
+        ker /= ker.sum()
+        f = FFTFilter2D(torch_mod.from_numpy(ker).cuda(), h, w)
+        got = f.apply(torch_mod.from_numpy(img).cuda()).cpu().numpy()
+        pad = np.zeros((h, w), dt)
+        ii = (np.arange(kh) - kh // 2) % h
+        jj = (np.arange(kw) - kw // 2) % w
+        pad[np.ix_(ii, jj)] = ker
+        kspec = checker.r2c(pad, [0, 1], True, 1.0)
+        spec = checker.r2c(img, [1, 2], True, 1.0) * kspec[None]
+        want = checker.c2r(np.ascontiguousarray(spec), img.shape, [1, 2], False, 1.0 / (h * w))
+        assert oracle.rel_l2(got, want) <= rt * np.log2(max(h, w)), (h, w)
+        if h <= 64:  # direct circular convolution, one image
+            direct = np.zeros((h, w))
+            for i in range(kh):
+                for j in range(kw):
+                    direct += ker[i, j] * np.roll(np.roll(img[0].astype(np.float64), i - kh // 2, axis=0), j - kw // 2, axis=1)
+            assert oracle.rel_l2(got[0], direct) <= rt * 10
+        # mean preserved by a unit-sum kernel (the image_filters benchmark's sanity metric)
+        assert abs(got.mean() - img.mean()) <= 1e-4
