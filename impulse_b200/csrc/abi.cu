@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -49,11 +50,39 @@ struct CudaAlloc : TableAlloc {
   void release(void *d) override { cudaFree(d); }
 };
 
+// Staging resources for host-pointer calls, kept across calls: cudaMalloc/cudaFree and stream
+// creation cost milliseconds, comparable to the PCIe time of a whole step.
+struct StagePool {
+  std::mutex mu;
+  cudaStream_t s[2] = {nullptr, nullptr};
+  unsigned char *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
+  size_t cap_in = 0, cap_out = 0;
+  cudaError_t ensure(size_t need_in, size_t need_out) {
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+      if (!s[i]) e = cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess && need_in > cap_in) {
+      for (int i = 0; i < 2; ++i) { if (in[i]) cudaFree(in[i]); in[i] = nullptr; }
+      cap_in = 0;
+      for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&in[i], need_in);
+      if (e == cudaSuccess) cap_in = need_in;
+    }
+    if (e == cudaSuccess && need_out > cap_out) {
+      for (int i = 0; i < 2; ++i) { if (out[i]) cudaFree(out[i]); out[i] = nullptr; }
+      cap_out = 0;
+      for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&out[i], need_out);
+      if (e == cudaSuccess) cap_out = need_out;
+    }
+    return e;
+  }
+};
+
 struct DeviceCtx {
   int dev = -1;
   CudaAlloc alloc;
   std::unique_ptr<PlanCache> cache;
   int sm_count = 0;
+  StagePool stage;
 };
 
 std::mutex g_ctx_mu;
@@ -146,6 +175,8 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     const size_t r = J.dtype == 1 ? 8 : 4;
     if ((J.flags & F_VEC_IN) && ((uintptr_t)J.in % (2 * r))) J.flags &= ~F_VEC_IN;
     if ((J.flags & F_VEC_OUT) && ((uintptr_t)J.out % (2 * r))) J.flags &= ~F_VEC_OUT;
+    // the register kernels address real rows as complex pairs: fall back to the generic engine otherwise
+    if (J.fast_id >= FAST3_2048_F64 && (((uintptr_t)J.in % (2 * r)) || ((uintptr_t)J.out % (2 * r)))) J.fast_id = FAST_NONE;
     int e = launch_line_job(J, st.cfg.threads, st.cfg.smem_bytes, st.cfg.n_tiles, stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e) { rc = cuda_fail((cudaError_t)e, "kernel launch"); break; }
@@ -160,11 +191,6 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
 // Pipelined path for the common case (single-step plan whose slowest batch dimension cuts both
 // arrays into disjoint slabs): chunks flow H2D -> kernel -> D2H on alternating streams so that
 // the two PCIe directions and the kernel overlap.  Anything else: whole-span staging.
-struct Staging {
-  cudaStream_t s[2] = {nullptr, nullptr};
-  ~Staging() { for (auto &x : s) if (x) cudaStreamDestroy(x); }
-};
-
 int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
   const NdPlan &nd = p->nd;
   if (nd.empty) return 0;
@@ -186,19 +212,20 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
       if (disjoint && J0.bdim[od] >= 4 && total_bytes >= (8u << 20)) {
         uint64_t inner_lines = 1;
         for (int d = 0; d < od; ++d) inner_lines *= J0.bdim[d];
-        // ~16 MiB of traffic per chunk, at least 4 chunks
-        uint64_t per = std::max<uint64_t>(1, (16u << 20) / std::max<int64_t>(1, sin_b + sout_b));
+        // ~16 MiB of traffic per chunk (IMPULSE_FFT_STAGE_MB overrides), at least 4 chunks
+        static const uint64_t stage_bytes = [] {
+          const char *e = std::getenv("IMPULSE_FFT_STAGE_MB");
+          const long mb = e ? std::atol(e) : 16;
+          return (uint64_t)(mb > 0 ? mb : 16) << 20;
+        }();
+        uint64_t per = std::max<uint64_t>(1, stage_bytes / std::max<int64_t>(1, sin_b + sout_b));
         per = std::min<uint64_t>(per, (J0.bdim[od] + 3) / 4);
         const uint64_t nchunks = (J0.bdim[od] + per - 1) / per;
-        Staging sg;
-        unsigned char *dbuf_in[2] = {nullptr, nullptr}, *dbuf_out[2] = {nullptr, nullptr};
+        StagePool &sg = p->ctx->stage;
+        std::lock_guard<std::mutex> stage_lock(sg.mu);
         const size_t cin = (size_t)((per - 1) * sin_b + in_slab), cout = (size_t)((per - 1) * sout_b + out_slab);
-        cudaError_t e = cudaSuccess;
-        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-          e = cudaStreamCreateWithFlags(&sg.s[i], cudaStreamNonBlocking);
-          if (e == cudaSuccess) e = cudaMalloc(&dbuf_in[i], cin);
-          if (e == cudaSuccess) e = cudaMalloc(&dbuf_out[i], cout);
-        }
+        cudaError_t e = sg.ensure(cin, inplace ? 0 : cout);
+        unsigned char **dbuf_in = sg.in, **dbuf_out = sg.out;
         int rc = 0;
         if (e != cudaSuccess) rc = cuda_fail(e, "staging allocation");
         for (uint64_t c = 0; c < nchunks && !rc; ++c) {
@@ -225,11 +252,8 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
           e = cudaMemcpyAsync(hout, inplace ? dbuf_in[b] : dbuf_out[b], inplace ? bin : bout, cudaMemcpyDeviceToHost, sg.s[b]);
           if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy"); break; }
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 2; ++i)
           if (sg.s[i]) { cudaError_t se = cudaStreamSynchronize(sg.s[i]); if (se != cudaSuccess && !rc) rc = cuda_fail(se, "staging sync"); }
-          if (dbuf_in[i]) cudaFree(dbuf_in[i]);
-          if (dbuf_out[i]) cudaFree(dbuf_out[i]);
-        }
         return rc;
       }
     }

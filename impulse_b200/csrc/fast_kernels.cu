@@ -345,6 +345,218 @@ int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
 }  // namespace
 
 // fast_id encodes the specialised kernel chosen by the planner (0 = generic engine)
+
+// =================================================================================================
+// Three-pass register kernel: N = R1*R2*R3 complex points per row, T = N/E threads per row each
+// holding E points, two shared-memory exchanges, one row per CTA at a time, rows claimed dynamically.
+// (index formulas validated by tools/model_fast3.py)
+//
+//   load   x[t + T*q]                                                   coalesced LDG.128
+//   pass 1 radix R1 over j1 (regs q = m + (E/R1)*j1), twiddle tw1[k1][i1], i1 = t + T*m
+//   X1[k1*P1 + i1]            P1 = roundup(N/R1, S) + 1   -> pass-2 reads conflict-free
+//   pass 2 butterflies b2 = t + T*m2: k1 = b2 % R1, i2 = b2 / R1; radix R2 over X1[k1][i2 + R3*j2];
+//          twiddle tw2[k2][i2]
+//   X2[i2*P2 + k1 + R1*k2]    P2 = R1*R2 (aliases X1 after a barrier)
+//   pass 3 butterflies klow = t + T*m3: radix R3 over X2[j3][klow] -> X[klow + R1*R2*k3]   coalesced STG.128
+//
+// KIND: 0 = c2c; 1 = r2c (row of 2N reals viewed as N complex, Hermitian post-twiddle through shared
+// memory, N+1 bins out); 2 = c2r (N+1 bins in, pre-twiddle through shared memory, 2N reals out).
+// =================================================================================================
+enum { F3_C2C = 0, F3_R2C = 1, F3_C2R = 2 };
+
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB>
+__global__ void __launch_bounds__((R1 * R2 * R3) / E, MINB)
+fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
+             const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, const cx<T> *__restrict__ twr, T fct,
+             unsigned int *__restrict__ sched) {
+  constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
+  constexpr int P1 = ((M1 + S - 1) / S) * S + 1, P2 = R1 * R2;
+  constexpr int NB1 = E / R1, NB2 = E / R2, NB3 = E / R3;
+  static_assert(E % R1 == 0 && E % R2 == 0 && E % R3 == 0 && TT % R1 == 0 && TT % 32 == 0, "fast3 shape");
+  constexpr int BUFN = (R1 * P1 > N + 1) ? R1 * P1 : N + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
+  unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + BUFN);  // [2]
+  const int t = threadIdx.x;
+  if (t == 0) { s_row[0] = atomicAdd(&sched[0], 1u); s_row[1] = atomicAdd(&sched[0], 1u); }
+  __syncthreads();
+  const int k1 = t % R1, i2b = t / R1;  // pass-2 ownership (T % R1 == 0)
+  for (unsigned it = 0;; ++it) {
+    const uint64_t row = s_row[it & 1];
+    if (row >= nrows) break;
+    cx<T> x[E];
+    // ---------------- load (+ c2r pre-twiddle) ----------------
+    if (KIND == F3_C2R) {
+      const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
+#pragma unroll
+      for (int q = 0; q < E; ++q) buf[t + TT * q] = src[t + TT * q];
+      if (t == 0) buf[N] = src[N];
+      __syncthreads();
+      if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // claim for iteration it+2
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int n = t + TT * q;
+        cx<T> a = buf[n], b = buf[N - n];
+        if (BWD) { a.y = -a.y; b.y = -b.y; }       // c2r with forward=true conjugates its input
+        if (n == 0) { a.y = (T)0; b.y = (T)0; }    // imaginary parts of bins 0 and N are ignored
+        const cx<T> w = cconj(__ldg(twr + n));     // e^{+2 pi i n/(2N)}
+        const cx<T> s = cadd(a, cconj(b)), d = csub(a, cconj(b));
+        const cx<T> z = cadd(s, mul_pi(cmul(w, d)));
+        x[q] = cconj(z);                           // backward = conj(FFT(conj z))
+      }
+      __syncthreads();
+    } else {
+      const cx<T> *src = KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)row * rs_in)
+                                        : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        x[q] = src[t + TT * q];
+        if (KIND == F3_C2C && BWD) x[q].y = -x[q].y;
+      }
+    }
+    // ---------------- pass 1 ----------------
+#pragma unroll
+    for (int m = 0; m < NB1; ++m) {
+      cx<T> y[R1];
+#pragma unroll
+      for (int j = 0; j < R1; ++j) y[j] = x[m + NB1 * j];
+      RegFFT<T, R1>::run(y);
+      const int i1 = t + TT * m;
+#pragma unroll
+      for (int k = 1; k < R1; ++k) y[k] = cmul(y[k], __ldg(tw1 + k * M1 + i1));
+#pragma unroll
+      for (int k = 0; k < R1; ++k) buf[k * P1 + i1] = y[k];
+    }
+    __syncthreads();
+    if (KIND != F3_C2R && t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // everyone has read s_row[it&1]
+    // ---------------- pass 2 ----------------
+#pragma unroll
+    for (int m = 0; m < NB2; ++m) {
+      const int i2 = i2b + (TT / R1) * m;
+      cx<T> y[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) y[j] = buf[k1 * P1 + i2 + R3 * j];
+      RegFFT<T, R2>::run(y);
+#pragma unroll
+      for (int k = 1; k < R2; ++k) y[k] = cmul(y[k], __ldg(tw2 + k * R3 + i2));
+#pragma unroll
+      for (int k = 0; k < R2; ++k) x[m * R2 + k] = y[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < NB2; ++m) {
+      const int i2 = i2b + (TT / R1) * m;
+#pragma unroll
+      for (int k = 0; k < R2; ++k) buf[i2 * P2 + k1 + R1 * k] = x[m * R2 + k];
+    }
+    __syncthreads();
+    // ---------------- pass 3 ----------------
+#pragma unroll
+    for (int m = 0; m < NB3; ++m) {
+      const int klow = t + TT * m;
+      cx<T> y[R3];
+#pragma unroll
+      for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
+      RegFFT<T, R3>::run(y);
+#pragma unroll
+      for (int k = 0; k < R3; ++k) x[m * R3 + k] = y[k];   // X[klow + R1*R2*k]
+    }
+    // ---------------- store ----------------
+    if (KIND == F3_C2C) {
+      cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
+#pragma unroll
+      for (int m = 0; m < NB3; ++m)
+#pragma unroll
+        for (int k = 0; k < R3; ++k) {
+          cx<T> v = x[m * R3 + k];
+          v.x *= fct; v.y *= BWD ? -fct : fct;
+          dst[t + TT * m + R1 * R2 * k] = v;
+        }
+      __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
+    } else if (KIND == F3_C2R) {
+      cx<T> *dst = reinterpret_cast<cx<T> *>(reinterpret_cast<T *>(out_v) + (int64_t)row * rs_out);
+#pragma unroll
+      for (int m = 0; m < NB3; ++m)
+#pragma unroll
+        for (int k = 0; k < R3; ++k) {
+          cx<T> v = x[m * R3 + k];
+          v.x *= fct; v.y *= -fct;                 // undo the conjugation of the backward trick
+          dst[t + TT * m + R1 * R2 * k] = v;       // (x[2n], x[2n+1])
+        }
+      __syncthreads();
+    } else {  // r2c: Hermitian post-twiddle needs Z[k] and Z[N-k]
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < NB3; ++m)
+#pragma unroll
+        for (int k = 0; k < R3; ++k) buf[t + TT * m + R1 * R2 * k] = x[m * R3 + k];
+      __syncthreads();
+      cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
+      const T h = (T)0.5;
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int k = t + TT * q;
+        const cx<T> a = buf[k], b = cconj(buf[(N - k) & (N - 1)]);
+        const cx<T> Ev = mk<T>((a.x + b.x) * h, (a.y + b.y) * h), Dv = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
+        cx<T> v = cadd(Ev, cmul(__ldg(twr + k), mul_mi(Dv)));
+        v.x *= fct; v.y *= BWD ? -fct : fct;       // r2c with forward=false returns the conjugate spectrum
+        dst[k] = v;
+        if (k == 0) {                               // bin N: Re Z0 - Im Z0
+          cx<T> last = mk<T>((a.x - a.y) * fct, (T)0);
+          dst[N] = last;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // the last CTA to leave re-arms the scheduler words
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(&sched[1], 1u);
+    if (done == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
+  }
+}
+
+namespace {
+template <typename T, int R1, int R2, int R3, int E, int MINB>
+int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
+  constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
+  constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
+  constexpr int BUFN = (R1 * P1 > N + 1) ? R1 * P1 : N + 1;
+  const size_t smem = sizeof(cx<T>) * (size_t)BUFN + 16;
+  const int kind = J.store_mode == ST_R2C_EVEN ? F3_R2C : J.load_mode == LD_HERM_EVEN ? F3_C2R : F3_C2C;
+  const bool bwd = kind == F3_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == F3_R2C ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
+  typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, const cx<T> *, const cx<T> *, const cx<T> *, T, unsigned int *);
+  kern_t k = nullptr;
+  switch (kind * 2 + (bwd ? 1 : 0)) {
+    case 0: k = fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB>; break;
+    case 1: k = fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB>; break;
+    case 2: k = fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB>; break;
+    case 3: k = fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB>; break;
+    case 4: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB>; break;
+    default: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB>; break;
+  }
+  static bool configured[6] = {false, false, false, false, false, false};
+  if (!configured[kind * 2 + (bwd ? 1 : 0)]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    configured[kind * 2 + (bwd ? 1 : 0)] = true;
+  }
+  uint64_t grid = J.n_lines;
+  const uint64_t cap = (uint64_t)sm_count * MINB;
+  if (grid > cap) grid = cap;
+  unsigned int *sched = sched_slot();
+  if (!sched) return (int)cudaErrorMemoryAllocation;
+  if (J.n_lines > 0xfff00000ull) return (int)cudaErrorInvalidValue;
+  k<<<(unsigned)grid, TT, smem, s>>>(J.in, J.out, J.n_lines, J.bs_in[0], J.bs_out[0], (const cx<T> *)J.f3_tw1,
+                                      (const cx<T> *)J.f3_tw2, (const cx<T> *)J.tw_r, (T)J.fct, sched);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+
 static int fast_variant() {  // IMPULSE_FFT_FAST_VARIANT=1 selects the non-TMA kernel (A/B measurements)
   static int v = -1;
   if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST_VARIANT"); v = e ? atoi(e) : 0; }
@@ -361,6 +573,11 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST2_512_F64: g_last_kernel = "fast2_kernel<double,32,16,4,2>"; return launch_fast2<double, 32, 16, 4, 2>(J, sm_count, s);
     case FAST2_256_F64: g_last_kernel = "fast2_kernel<double,16,16,4,4>"; return launch_fast2<double, 16, 16, 4, 4>(J, sm_count, s);
     case FAST2_1024_F32: g_last_kernel = "fast2_kernel<float,32,32,4,4>"; return launch_fast2<float, 32, 32, 4, 4>(J, sm_count, s);
+    case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3>(J, sm_count, s);
+    case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2>(J, sm_count, s);
+    case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,32,16,16,E32>"; return launch_fast3<double, 32, 16, 16, 32, 1>(J, sm_count, s);
+    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4>(J, sm_count, s);
+    case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;
   }
 }

@@ -79,6 +79,11 @@ enum FastId : uint32_t {
   FAST2_512_F64 = 2,
   FAST2_256_F64 = 3,
   FAST2_1024_F32 = 4,
+  FAST3_2048_F64 = 5,
+  FAST3_4096_F64 = 6,
+  FAST3_8192_F64 = 7,
+  FAST3_2048_F32 = 8,
+  FAST3_4096_F32 = 9,
 };
 
 struct Phase {
@@ -123,6 +128,7 @@ struct LineJob {
   uint32_t tw4_shift;
   uint32_t tw4_dim;
   uint32_t zero_pad_from;  // ST_C: elements e >= this are stored as zero (0 = off; Bluestein staging)
+  const void *f3_tw1, *f3_tw2;  // twiddle tables of the three-pass register kernels ([k1][i1], [k2][i2])
   const void *mul_tab;     // ST_C: multiply output element e by mul_tab[line_index + mul_stride*e] (null = off)
   uint32_t mul_stride;
   double fct;

@@ -155,6 +155,7 @@ PlanCache::~PlanCache() {
   }
   for (auto &kv : real_tw_) if (kv.second) alloc_->release(kv.second);
   for (auto &kv : tw4_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
+  for (auto &kv : f3_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
 }
 
 int PlanCache::status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err) {
@@ -223,6 +224,26 @@ int PlanCache::bluestein_natural_table(uint32_t L, int dtype, const void **out, 
     if (!e->d_bkf_nat) { *err = "table upload failed"; return ERR_NOMEM; }
   }
   *out = e->d_bkf_nat;
+  return ST_OK;
+}
+
+// tw1[k1][i1] = W_N^(i1*k1) (i1 < N/R1), tw2[k2][i2] = W_N^(R1*i2*k2) (i2 < R3): fast3_kernel
+int PlanCache::fast3_tables(uint32_t N, uint32_t R1, uint32_t R2, uint32_t R3, int dtype, const void **tw1, const void **tw2,
+                            std::string *err) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto key = std::make_pair(((uint64_t)N << 32) | (R1 << 16) | (R2 << 8) | R3, dtype);
+  auto it = f3_.find(key);
+  if (it != f3_.end()) { *tw1 = it->second.first; *tw2 = it->second.second; return ST_OK; }
+  const uint32_t M1 = N / R1;
+  std::vector<cld> a((size_t)R1 * M1), b((size_t)R2 * R3);
+  for (uint32_t k1 = 0; k1 < R1; ++k1)
+    for (uint32_t i1 = 0; i1 < M1; ++i1) a[(size_t)k1 * M1 + i1] = std::conj(unit_root((uint64_t)i1 * k1, N));
+  for (uint32_t k2 = 0; k2 < R2; ++k2)
+    for (uint32_t i2 = 0; i2 < R3; ++i2) b[(size_t)k2 * R3 + i2] = std::conj(unit_root((uint64_t)R1 * i2 * k2, N));
+  void *da = upload_cplx(alloc_, a, dtype), *db = upload_cplx(alloc_, b, dtype);
+  if (!da || !db) { *err = "table upload failed"; return ERR_NOMEM; }
+  f3_[key] = std::make_pair(da, db);
+  *tw1 = da; *tw2 = db;
   return ST_OK;
 }
 
@@ -442,6 +463,25 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     else if (f64 && N == 512) J->fast_id = FAST2_512_F64;
     else if (f64 && N == 256) J->fast_id = FAST2_256_F64;
     else if (!f64 && N == 1024) J->fast_id = FAST2_1024_F32;
+  }
+  // three-pass register kernels: c2c of 2048/4096/8192 points, and even-N r2c/c2r (Hermitian layout)
+  // whose half-length complex transform is one of those; contiguous rows, one batch dimension
+  if (!E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
+      J->bdim[1] == 1 && J->bdim[2] == 1 && !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_FAST3", 0)) {
+    const bool c2c = s.kind == KIND_C2C;
+    const bool r2c = s.kind == KIND_R2C && even && s.layout == RL_HERMITIAN && (J->bdim[0] == 1 || s.bs_in[0] % 2 == 0);
+    const bool c2r = s.kind == KIND_C2R && even && s.layout == RL_HERMITIAN && (J->bdim[0] == 1 || s.bs_out[0] % 2 == 0);
+    if (c2c || r2c || c2r) {
+      uint32_t id = FAST_NONE, r1 = 0, r2 = 0, r3 = 0;
+      if (L == 2048) { id = f64 ? FAST3_2048_F64 : FAST3_2048_F32; r1 = 16; r2 = 16; r3 = 8; }
+      else if (L == 4096) { id = f64 ? FAST3_4096_F64 : FAST3_4096_F32; r1 = 16; r2 = 16; r3 = 16; }
+      else if (L == 8192 && f64) { id = FAST3_8192_F64; r1 = 32; r2 = 16; r3 = 16; }
+      if (id != FAST_NONE) {
+        rc = fast3_tables(L, r1, r2, r3, s.dtype, &J->f3_tw1, &J->f3_tw2, err);
+        if (rc) return rc;
+        J->fast_id = id;
+      }
+    }
   }
   return ST_OK;
 }

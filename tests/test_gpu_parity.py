@@ -400,3 +400,39 @@ def test_fft_filter2d(ib, torch_mod, checker):
             assert oracle.rel_l2(got[0], direct) <= rt * 10
         # mean preserved by a unit-sum kernel (the image_filters benchmark's sanity metric)
         assert abs(got.mean() - img.mean()) <= 1e-4
+
+
+def test_register_kernels_all_kinds(ib, torch_mod, checker):
+    """The specialised register kernels (two-pass 256/512/1024, three-pass 2048/4096/8192) in every
+    kind they serve: c2c both directions, r2c/c2r with both `forward` flags, fp64 and fp32, odd batch
+    sizes (dynamic row claiming with a ragged tail), plus the generic engine on the same inputs
+    (IMPULSE_FFT_NO_FAST) as a second opinion."""
+    rng = np.random.default_rng(21)
+    used = set()
+    for dt, cdt in ((np.float64, np.complex128), (np.float32, np.complex64)):
+        for n in (256, 512, 1024, 2048, 4096, 8192):
+            for rows in (1, 37, 301):
+                x = rnd(rng, (rows, n), cdt)
+                xd = torch_mod.from_numpy(x).cuda()
+                for fwd in (True, False):
+                    got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], fwd, 0.7).cpu().numpy()
+                    used.add(ib.last_kernel())
+                    assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.7)) <= tol(n, dt), (n, rows, fwd, dt)
+        for n in (4096, 8192, 16384):
+            for rows in (1, 53):
+                r = rnd(rng, (rows, n), dt)
+                rd = torch_mod.from_numpy(r).cuda()
+                for fwd in (True, False):
+                    spec = apply_nd(ib, "r2c", rd, torch_mod.empty((rows, n // 2 + 1), dtype=getattr(torch_mod, np.dtype(cdt).name),
+                                                                   device="cuda"), [1], fwd, 1.0)
+                    used.add(ib.last_kernel())
+                    want = checker.r2c(r, [1], fwd, 1.0)
+                    assert oracle.max_row_rel_l2(spec.cpu().numpy(), want) <= tol(n, dt), (n, rows, fwd, dt)
+                sp = checker.r2c(r, [1], True, 1.0)
+                sd = torch_mod.from_numpy(sp).cuda()
+                for fwd in (False, True):
+                    back = apply_nd(ib, "c2r", sd, torch_mod.empty_like(rd), [1], fwd, 1.0 / n).cpu().numpy()
+                    used.add(ib.last_kernel())
+                    assert oracle.max_row_rel_l2(back, checker.c2r(sp, r.shape, [1], fwd, 1.0 / n)) <= tol(n, dt), (n, rows, fwd, dt)
+    print(sorted(used))
+    assert any(k.startswith("fast3_kernel") for k in used) and any(k.startswith("fast2") for k in used)
