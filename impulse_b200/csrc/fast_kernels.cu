@@ -83,6 +83,9 @@ template <typename T, int RA, int RB> struct Composite {
 };
 template <typename T> struct RegFFT<T, 16> { static __device__ __forceinline__ void run(cx<T> (&x)[16]) { Composite<T, 4, 4>::run(x); } };
 template <typename T> struct RegFFT<T, 32> { static __device__ __forceinline__ void run(cx<T> (&x)[32]) { Composite<T, 4, 8>::run(x); } };
+template <typename T> struct RegFFT<T, 6> { static __device__ __forceinline__ void run(cx<T> (&x)[6]) { Composite<T, 2, 3>::run(x); } };
+template <typename T> struct RegFFT<T, 10> { static __device__ __forceinline__ void run(cx<T> (&x)[10]) { Composite<T, 2, 5>::run(x); } };
+template <typename T> struct RegFFT<T, 18> { static __device__ __forceinline__ void run(cx<T> (&x)[18]) { Composite<T, 2, 9>::run(x); } };
 template <typename T> struct RegFFT<T, 64> { static __device__ __forceinline__ void run(cx<T> (&x)[64]) { Composite<T, 8, 8>::run(x); } };
 
 template <typename T, int R1, int R2, int WARPS, int MINB, bool BWD>
@@ -364,26 +367,52 @@ int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
 // =================================================================================================
 enum { F3_C2C = 0, F3_R2C = 1, F3_C2R = 2 };
 
+__device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB>
 __global__ void __launch_bounds__((R1 * R2 * R3) / E, MINB)
 fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
              const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, const cx<T> *__restrict__ twr, T fct,
              unsigned int *__restrict__ sched) {
+  // pass-1 twiddles W_N^(t*k1) as a product A[k1>>2]*B[k1&3] of six per-thread values held in registers
+  // for the whole kernel (R1 = 16): 15 global table loads per row become 9 multiplies
+  constexpr bool TW1_REGS = (R1 == 16) && (E / R1 == 1);
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1, P2 = R1 * R2;
   constexpr int NB1 = E / R1, NB2 = E / R2, NB3 = E / R3;
-  static_assert(E % R1 == 0 && E % R2 == 0 && E % R3 == 0 && TT % R1 == 0 && TT % 32 == 0, "fast3 shape");
+  static_assert(E % R1 == 0 && E % R2 == 0 && E % R3 == 0 && TT % R1 == 0, "fast3 shape");
   constexpr int BUFN = (R1 * P1 > N + 1) ? R1 * P1 : N + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
-  unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + BUFN);  // [2]
+  unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + BUFN);  // [2] (+2 pad)
+  cx<T> *s_tw2 = reinterpret_cast<cx<T> *>(s_row + 4);                 // [R2][R3]
   const int t = threadIdx.x;
   if (t == 0) { s_row[0] = atomicAdd(&sched[0], 1u); s_row[1] = atomicAdd(&sched[0], 1u); }
+  for (int idx = t; idx < R2 * R3; idx += TT) s_tw2[idx] = tw2[idx];
+  cx<T> twA[3], twB[3];
+  if (TW1_REGS) {
+#pragma unroll
+    for (int a = 1; a < 4; ++a) { twA[a - 1] = tw1[(4 * a) * M1 + t]; twB[a - 1] = tw1[a * M1 + t]; }
+  }
   __syncthreads();
+  constexpr uint32_t ROW_BYTES_IN = (KIND == F3_C2R ? (N + 1) : N) * sizeof(cx<T>);
   const int k1 = t % R1, i2b = t / R1;  // pass-2 ownership (T % R1 == 0)
   for (unsigned it = 0;; ++it) {
     const uint64_t row = s_row[it & 1];
     if (row >= nrows) break;
+    if (t == 0) {  // pull the next claimed row into L2 while this one is transformed
+      const uint64_t nxt = s_row[(it + 1) & 1];
+      if (nxt < nrows) {
+        const char *p = KIND == F3_R2C ? reinterpret_cast<const char *>(reinterpret_cast<const T *>(in_v) + (int64_t)nxt * rs_in)
+                                       : reinterpret_cast<const char *>(reinterpret_cast<const cx<T> *>(in_v) + (int64_t)nxt * rs_in);
+        // the bulk prefetch wants 16-byte aligned address and size (float c2r rows are only 8-byte aligned)
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15;
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(p) + ROW_BYTES_IN) & ~(uintptr_t)15;
+        if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void *>(lo), (uint32_t)(hi - lo));
+      }
+    }
     cx<T> x[E];
     // ---------------- load (+ c2r pre-twiddle) ----------------
     if (KIND == F3_C2R) {
@@ -422,8 +451,18 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
       for (int j = 0; j < R1; ++j) y[j] = x[m + NB1 * j];
       RegFFT<T, R1>::run(y);
       const int i1 = t + TT * m;
+      if (TW1_REGS) {
 #pragma unroll
-      for (int k = 1; k < R1; ++k) y[k] = cmul(y[k], __ldg(tw1 + k * M1 + i1));
+        for (int k = 1; k < R1; ++k) {
+          const int a = k >> 2, b = k & 3;
+          if (a == 0) y[k] = cmul(y[k], twB[b - 1]);
+          else if (b == 0) y[k] = cmul(y[k], twA[a - 1]);
+          else y[k] = cmul(y[k], cmul(twA[a - 1], twB[b - 1]));
+        }
+      } else {
+#pragma unroll
+        for (int k = 1; k < R1; ++k) y[k] = cmul(y[k], __ldg(tw1 + k * M1 + i1));
+      }
 #pragma unroll
       for (int k = 0; k < R1; ++k) buf[k * P1 + i1] = y[k];
     }
@@ -438,7 +477,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
       for (int j = 0; j < R2; ++j) y[j] = buf[k1 * P1 + i2 + R3 * j];
       RegFFT<T, R2>::run(y);
 #pragma unroll
-      for (int k = 1; k < R2; ++k) y[k] = cmul(y[k], __ldg(tw2 + k * R3 + i2));
+      for (int k = 1; k < R2; ++k) y[k] = cmul(y[k], s_tw2[k * R3 + i2]);
 #pragma unroll
       for (int k = 0; k < R2; ++k) x[m * R2 + k] = y[k];
     }
@@ -496,7 +535,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
 #pragma unroll
       for (int q = 0; q < E; ++q) {
         const int k = t + TT * q;
-        const cx<T> a = buf[k], b = cconj(buf[(N - k) & (N - 1)]);
+        const cx<T> a = buf[k], b = cconj(buf[k == 0 ? 0 : N - k]);
         const cx<T> Ev = mk<T>((a.x + b.x) * h, (a.y + b.y) * h), Dv = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
         cx<T> v = cadd(Ev, cmul(__ldg(twr + k), mul_mi(Dv)));
         v.x *= fct; v.y *= BWD ? -fct : fct;       // r2c with forward=false returns the conjugate spectrum
@@ -524,7 +563,7 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
   constexpr int BUFN = (R1 * P1 > N + 1) ? R1 * P1 : N + 1;
-  const size_t smem = sizeof(cx<T>) * (size_t)BUFN + 16;
+  const size_t smem = sizeof(cx<T>) * ((size_t)BUFN + (size_t)R2 * R3) + 16;
   const int kind = J.store_mode == ST_R2C_EVEN ? F3_R2C : J.load_mode == LD_HERM_EVEN ? F3_C2R : F3_C2C;
   const bool bwd = kind == F3_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == F3_R2C ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
   typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, const cx<T> *, const cx<T> *, const cx<T> *, T, unsigned int *);
@@ -576,6 +615,9 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3>(J, sm_count, s);
     case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2>(J, sm_count, s);
     case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,32,16,16,E32>"; return launch_fast3<double, 32, 16, 16, 32, 1>(J, sm_count, s);
+    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8>(J, sm_count, s);
+    case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4>(J, sm_count, s);
+    case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5>(J, sm_count, s);
     case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4>(J, sm_count, s);
     case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;

@@ -84,6 +84,9 @@ enum FastId : uint32_t {
   FAST3_8192_F64 = 7,
   FAST3_2048_F32 = 8,
   FAST3_4096_F32 = 9,
+  FAST3_500_F64 = 10,
+  FAST3_1944_F64 = 11,
+  FAST3_1000_F64 = 12,
 };
 
 struct Phase {

@@ -410,7 +410,7 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
     rng = np.random.default_rng(21)
     used = set()
     for dt, cdt in ((np.float64, np.complex128), (np.float32, np.complex64)):
-        for n in (256, 512, 1024, 2048, 4096, 8192):
+        for n in (256, 500, 512, 1000, 1024, 1944, 2048, 4096, 8192):
             for rows in (1, 37, 301):
                 x = rnd(rng, (rows, n), cdt)
                 xd = torch_mod.from_numpy(x).cuda()
@@ -418,7 +418,7 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
                     got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], fwd, 0.7).cpu().numpy()
                     used.add(ib.last_kernel())
                     assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.7)) <= tol(n, dt), (n, rows, fwd, dt)
-        for n in (4096, 8192, 16384):
+        for n in (1000, 3888, 4096, 8192, 16384):
             for rows in (1, 53):
                 r = rnd(rng, (rows, n), dt)
                 rd = torch_mod.from_numpy(r).cuda()
