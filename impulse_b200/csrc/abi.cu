@@ -212,11 +212,11 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
       if (disjoint && J0.bdim[od] >= 4 && total_bytes >= (8u << 20)) {
         uint64_t inner_lines = 1;
         for (int d = 0; d < od; ++d) inner_lines *= J0.bdim[d];
-        // ~16 MiB of traffic per chunk (IMPULSE_FFT_STAGE_MB overrides), at least 4 chunks
+        // ~64 MiB of traffic per chunk (IMPULSE_FFT_STAGE_MB overrides; measured 8:30.6 16:26.0 32:23.9 64:23.2 128:23.1 ms), at least 4 chunks
         static const uint64_t stage_bytes = [] {
           const char *e = std::getenv("IMPULSE_FFT_STAGE_MB");
-          const long mb = e ? std::atol(e) : 16;
-          return (uint64_t)(mb > 0 ? mb : 16) << 20;
+          const long mb = e ? std::atol(e) : 64;
+          return (uint64_t)(mb > 0 ? mb : 64) << 20;
         }();
         uint64_t per = std::max<uint64_t>(1, stage_bytes / std::max<int64_t>(1, sin_b + sout_b));
         per = std::min<uint64_t>(per, (J0.bdim[od] + 3) / 4);
