@@ -596,6 +596,94 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
 }
 }  // namespace
 
+
+// =================================================================================================
+// Column kernel: two-pass register FFT over LPC adjacent STRIDED lines (element n of line l at
+// base + n*es + l).  Thread u = line + LPC*i, so for every register index the lanes of a warp read /
+// write LPC*16 B contiguous runs (128 B for LPC = 8 complex128 / 16 complex64).  The exchange buffer is
+// laid out [k1][i][line] (line fastest): conflict-free both ways without padding.  Serves the strided
+// axes of N-D transforms and both launches of the four-step split (optional W_N^(k*n2) store twiddle).
+// One group of LPC lines per CTA: the hardware block scheduler balances the SMs.
+// =================================================================================================
+template <typename T, int R1, int R2, int LPC, bool BWD>
+__global__ void __launch_bounds__(LPC * R2)
+colfast2_kernel(const __grid_constant__ LineJob J) {
+  constexpr int N = R1 * R2, NB2 = R1 / R2;
+  static_assert(R1 % R2 == 0, "column two-pass shape");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *S = reinterpret_cast<cx<T> *>(smem_raw);
+  const int u = threadIdx.x, line = u % LPC, i = u / LPC;
+  // group -> batch indices (bdim[0] is the adjacent-lines dimension; its last group may be ragged)
+  const uint64_t g0n = (J.bdim[0] + LPC - 1) / LPC;
+  const uint64_t i0 = ((uint64_t)blockIdx.x % g0n) * LPC, r = (uint64_t)blockIdx.x / g0n, i1 = r % J.bdim[1], i2 = r / J.bdim[1];
+  const bool valid = i0 + line < J.bdim[0];
+  const int64_t off_in = (int64_t)i0 + line + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
+  const int64_t off_out = (int64_t)i0 + line + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
+  const uint32_t twi = J.tw4_dim == 0 ? (uint32_t)i0 + line : J.tw4_dim == 1 ? (uint32_t)i1 : J.tw4_dim == 2 ? (uint32_t)i2 : 0u;
+  const cx<T> *in = reinterpret_cast<const cx<T> *>(J.in) + off_in;
+  cx<T> *out = reinterpret_cast<cx<T> *>(J.out) + off_out;
+  const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);   // W_N^m
+  cx<T> x[R1];
+#pragma unroll
+  for (int j = 0; j < R1; ++j) {
+    x[j] = valid ? in[(int64_t)(i + R2 * j) * J.es_in] : mk<T>((T)0, (T)0);
+    if (BWD) x[j].y = -x[j].y;
+  }
+  RegFFT<T, R1>::run(x);
+#pragma unroll
+  for (int k = 1; k < R1; ++k) x[k] = cmul(x[k], __ldg(tw + i * k));
+#pragma unroll
+  for (int k = 0; k < R1; ++k) S[(k * R2 + i) * LPC + line] = x[k];
+  __syncthreads();
+  const T f = (T)J.fct;
+#pragma unroll
+  for (int m = 0; m < NB2; ++m) {
+    const int k1 = i + R2 * m;
+    cx<T> y[R2];
+#pragma unroll
+    for (int j = 0; j < R2; ++j) y[j] = S[(k1 * R2 + j) * LPC + line];
+    RegFFT<T, R2>::run(y);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) {
+      const int k = k1 + R1 * k2;
+      cx<T> v = y[k2];
+      if (J.tw4_n) {  // first launch of the split: W_N^(k*n2); the conjugation below turns it into its inverse
+        const uint32_t mm = (uint32_t)k * twi;
+        const cx<T> w = cmul(__ldg(reinterpret_cast<const cx<T> *>(J.tw4_hi) + (mm >> J.tw4_shift)),
+                             __ldg(reinterpret_cast<const cx<T> *>(J.tw4_lo) + (mm & ((1u << J.tw4_shift) - 1))));
+        v = cmul(v, w);
+      }
+      v.x *= f;
+      v.y *= BWD ? -f : f;
+      if (valid) out[(int64_t)k * J.es_out] = v;
+    }
+  }
+}
+
+namespace {
+template <typename T, int R1, int R2, int LPC>
+int launch_colfast2(const LineJob &J, cudaStream_t s) {
+  const size_t smem = sizeof(cx<T>) * (size_t)R1 * R2 * LPC;
+  const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
+  auto kf = colfast2_kernel<T, R1, R2, LPC, false>;
+  auto kb = colfast2_kernel<T, R1, R2, LPC, true>;
+  static bool configured = false;
+  if (!configured) {
+    for (auto k : {kf, kb}) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return (int)e;
+    }
+    configured = true;
+  }
+  const uint64_t groups = ((J.bdim[0] + LPC - 1) / LPC) * J.bdim[1] * J.bdim[2];
+  if (groups == 0 || groups > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+  (bwd ? kb : kf)<<<(unsigned)groups, LPC * R2, smem, s>>>(J);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+
 static int fast_variant() {  // IMPULSE_FFT_FAST_VARIANT=1 selects the non-TMA kernel (A/B measurements)
   static int v = -1;
   if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST_VARIANT"); v = e ? atoi(e) : 0; }
@@ -615,6 +703,16 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3>(J, sm_count, s);
     case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2>(J, sm_count, s);
     case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,32,16,16,E32>"; return launch_fast3<double, 32, 16, 16, 32, 1>(J, sm_count, s);
+    case COL2_32_F64: g_last_kernel = "colfast2_kernel<double,8,4,8>"; return launch_colfast2<double, 8, 4, 8>(J, s);
+    case COL2_512_F64: g_last_kernel = "colfast2_kernel<double,32,16,8>"; return launch_colfast2<double, 32, 16, 8>(J, s);
+    case COL2_32_F32: g_last_kernel = "colfast2_kernel<float,8,4,16>"; return launch_colfast2<float, 8, 4, 16>(J, s);
+    case COL2_512_F32: g_last_kernel = "colfast2_kernel<float,32,16,16>"; return launch_colfast2<float, 32, 16, 16>(J, s);
+    case COL2_64_F64: g_last_kernel = "colfast2_kernel<double,8,8,8>"; return launch_colfast2<double, 8, 8, 8>(J, s);
+    case COL2_128_F64: g_last_kernel = "colfast2_kernel<double,16,8,8>"; return launch_colfast2<double, 16, 8, 8>(J, s);
+    case COL2_256_F64: g_last_kernel = "colfast2_kernel<double,16,16,8>"; return launch_colfast2<double, 16, 16, 8>(J, s);
+    case COL2_64_F32: g_last_kernel = "colfast2_kernel<float,8,8,16>"; return launch_colfast2<float, 8, 8, 16>(J, s);
+    case COL2_128_F32: g_last_kernel = "colfast2_kernel<float,16,8,16>"; return launch_colfast2<float, 16, 8, 16>(J, s);
+    case COL2_256_F32: g_last_kernel = "colfast2_kernel<float,16,16,16>"; return launch_colfast2<float, 16, 16, 16>(J, s);
     case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8>(J, sm_count, s);
     case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4>(J, sm_count, s);
     case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5>(J, sm_count, s);

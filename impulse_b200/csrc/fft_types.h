@@ -87,6 +87,16 @@ enum FastId : uint32_t {
   FAST3_500_F64 = 10,
   FAST3_1944_F64 = 11,
   FAST3_1000_F64 = 12,
+  COL2_64_F64 = 13,
+  COL2_128_F64 = 14,
+  COL2_256_F64 = 15,
+  COL2_64_F32 = 16,
+  COL2_128_F32 = 17,
+  COL2_256_F32 = 18,
+  COL2_32_F64 = 19,
+  COL2_512_F64 = 20,
+  COL2_32_F32 = 21,
+  COL2_512_F32 = 22,
 };
 
 struct Phase {

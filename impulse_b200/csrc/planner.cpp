@@ -464,6 +464,21 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     else if (f64 && N == 256) J->fast_id = FAST2_256_F64;
     else if (!f64 && N == 1024) J->fast_id = FAST2_1024_F32;
   }
+  // column kernels: complex sub-transforms of 64/128/256 points over adjacent strided lines (both sides
+  // lines-fastest with unit line stride, whole groups of S lines) — the strided axes of N-D transforms and
+  // the two launches of the four-step split
+  if (s.kind == KIND_C2C && !E->blue && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && in_lf && out_lf &&
+      s.bs_in[0] == 1 && s.bs_out[0] == 1 && J->bdim[0] >= S &&
+      (N == 32 || N == 64 || N == 128 || N == 256 || N == 512) &&
+      !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_COLFAST", 0)) {
+    switch (N) {
+      case 32: J->fast_id = f64 ? COL2_32_F64 : COL2_32_F32; break;
+      case 64: J->fast_id = f64 ? COL2_64_F64 : COL2_64_F32; break;
+      case 128: J->fast_id = f64 ? COL2_128_F64 : COL2_128_F32; break;
+      case 256: J->fast_id = f64 ? COL2_256_F64 : COL2_256_F32; break;
+      default: J->fast_id = f64 ? COL2_512_F64 : COL2_512_F32; break;
+    }
+  }
   // three-pass register kernels: c2c of 2048/4096/8192 points, and even-N r2c/c2r (Hermitian layout)
   // whose half-length complex transform is one of those; contiguous rows, one batch dimension
   if (!E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&

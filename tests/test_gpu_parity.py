@@ -436,3 +436,25 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
                     assert oracle.max_row_rel_l2(back, checker.c2r(sp, r.shape, [1], fwd, 1.0 / n)) <= tol(n, dt), (n, rows, fwd, dt)
     print(sorted(used))
     assert any(k.startswith("fast3_kernel") for k in used) and any(k.startswith("fast2") for k in used)
+
+
+def test_column_kernels(ib, torch_mod, checker):
+    """Strided-axis register kernels (colfast2) directly (axis 0 of 32..512 points over >= 8/16 adjacent
+    columns, both directions, fp64/fp32) and inside the four-step split (1024..16384-point columns)."""
+    rng = np.random.default_rng(31)
+    used = set()
+    for dt, cdt, cols in ((np.float64, np.complex128, 24), (np.float32, np.complex64, 48), (np.float64, np.complex128, 29),
+                          (np.float32, np.complex64, 2049)):
+        for n in ((32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384) if cols < 100 else (64, 4096)):
+            a = rnd(rng, (n, cols), cdt)
+            ad = torch_mod.from_numpy(a).cuda()
+            for fwd in (True, False):
+                got = apply_nd(ib, "c2c", ad, torch_mod.empty_like(ad), [0], fwd, 0.5).cpu().numpy()
+                used.add(ib.last_kernel())
+                assert oracle.rel_l2(got, checker.c2c(a, [0], fwd, 0.5)) <= tol(n, dt), (n, fwd, dt)
+        b = rnd(rng, (3, 128, 5, cols), cdt)       # two more batch dims around the strided axis
+        bd = torch_mod.from_numpy(b).cuda()
+        got = apply_nd(ib, "c2c", bd, torch_mod.empty_like(bd), [1], True, 1.0).cpu().numpy()
+        assert oracle.rel_l2(got, checker.c2c(b, [1], True, 1.0)) <= tol(128, dt)
+    print(sorted(used))
+    assert any(k.startswith("colfast2") for k in used)
