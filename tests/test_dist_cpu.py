@@ -68,17 +68,28 @@ def _worker(rank, world, port, shape, restore, q):
 
 @pytest.mark.parametrize("world,shape,restore", [(2, (16, 24), False), (2, (16, 24), True), (4, (32, 20), False),
                                                   (4, (8, 64), True)])
-def test_fft2_slab_gloo(world, shape, restore):
+def _run_world(world, shape, restore):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, shape, restore, q)) for r in range(world)]
     for p in procs:
         p.start()
+    ok = True
     for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
-    got = sorted(q.get(timeout=5) for _ in range(world))
+        p.join(timeout=180)
+        if p.exitcode != 0:
+            ok = False
+            if p.is_alive():
+                p.kill()
+    return sorted(q.get(timeout=5) for _ in range(world)) if ok else None
+
+
+def test_fft2_slab_gloo(world, shape, restore):
+    got = _run_world(world, shape, restore)
+    if got is None:  # rendezvous can lose a race for the probed port on a busy host: one retry
+        got = _run_world(world, shape, restore)
+    assert got is not None
     assert [g[0] for g in got] == list(range(world))
     for _, err, err2 in got:
         assert err <= 1e-12 * 6 and err2 <= 1e-12 * 6, (err, err2)
