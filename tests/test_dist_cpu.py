@@ -66,8 +66,6 @@ def _worker(rank, world, port, shape, restore, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shape,restore", [(2, (16, 24), False), (2, (16, 24), True), (4, (32, 20), False),
-                                                  (4, (8, 64), True)])
 def _run_world(world, shape, restore):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -85,6 +83,8 @@ def _run_world(world, shape, restore):
     return sorted(q.get(timeout=5) for _ in range(world)) if ok else None
 
 
+@pytest.mark.parametrize("world,shape,restore", [(2, (16, 24), False), (2, (16, 24), True), (4, (32, 20), False),
+                                                  (4, (8, 64), True)])
 def test_fft2_slab_gloo(world, shape, restore):
     got = _run_world(world, shape, restore)
     if got is None:  # rendezvous can lose a race for the probed port on a busy host: one retry
