@@ -24,6 +24,20 @@
 
 namespace impulse {
 
+namespace {
+constexpr int kMaxDevices = 64;
+inline int cur_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+// function attributes (dynamic shared memory size, carve-out) are per device: remember where they were set
+struct PerDeviceFlag {
+  bool done[kMaxDevices] = {};
+  bool &here() { return done[cur_dev()]; }
+};
+}  // namespace
+
 // v * exp(-2*pi*i*M/R) with the trivial roots folded at compile time
 template <typename T, int R, int M> __device__ __forceinline__ cx<T> mul_root(cx<T> v) {
   constexpr int m = ((M % R) + R) % R;
@@ -154,7 +168,8 @@ int launch_fast2(const LineJob &J, int sm_count, cudaStream_t s) {
   const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
   auto kf = fast2_kernel<T, R1, R2, WARPS, MINB, false>;
   auto kb = fast2_kernel<T, R1, R2, WARPS, MINB, true>;
-  static bool configured = false;  // per process; attributes are per function (all devices of the process are B200)
+  static PerDeviceFlag flag;
+  bool &configured = flag.here();
   if (!configured) {
     for (auto k : {kf, kb}) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -308,10 +323,11 @@ namespace {
 // scheduler slots: zero-initialised device words, one pair per in-flight launch (ring)
 constexpr int kSchedSlots = 1024;
 unsigned int *sched_slot() {
-  static unsigned int *base = nullptr;
+  static unsigned int *bases[kMaxDevices] = {};
   static unsigned next = 0;
+  unsigned int *&base = bases[cur_dev()];
   if (!base) {
-    if (cudaMalloc(&base, sizeof(unsigned int) * 2 * kSchedSlots) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&base, sizeof(unsigned int) * 2 * kSchedSlots) != cudaSuccess) { base = nullptr; return nullptr; }
     cudaMemset(base, 0, sizeof(unsigned int) * 2 * kSchedSlots);
   }
   const unsigned s = __atomic_fetch_add(&next, 1u, __ATOMIC_RELAXED) % kSchedSlots;
@@ -325,7 +341,8 @@ int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
   const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
   auto kf = fast2p_kernel<T, R1, R2, WARPS, false>;
   auto kb = fast2p_kernel<T, R1, R2, WARPS, true>;
-  static bool configured = false;
+  static PerDeviceFlag flag;
+  bool &configured = flag.here();
   if (!configured) {
     for (auto k : {kf, kb}) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -576,13 +593,14 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
     case 4: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB>; break;
     default: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB>; break;
   }
-  static bool configured[6] = {false, false, false, false, false, false};
-  if (!configured[kind * 2 + (bwd ? 1 : 0)]) {
+  static PerDeviceFlag flags[6];
+  bool &configured_here = flags[kind * 2 + (bwd ? 1 : 0)].here();
+  if (!configured_here) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
-    configured[kind * 2 + (bwd ? 1 : 0)] = true;
+    configured_here = true;
   }
   uint64_t grid = J.n_lines;
   const uint64_t cap = (uint64_t)sm_count * MINB;
@@ -667,7 +685,8 @@ int launch_colfast2(const LineJob &J, cudaStream_t s) {
   const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
   auto kf = colfast2_kernel<T, R1, R2, LPC, false>;
   auto kb = colfast2_kernel<T, R1, R2, LPC, true>;
-  static bool configured = false;
+  static PerDeviceFlag flag;
+  bool &configured = flag.here();
   if (!configured) {
     for (auto k : {kf, kb}) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -54,12 +54,11 @@ int configure_kernels(size_t max_dyn_smem) {
 int launch_line_job(const LineJob &J, int threads, size_t smem_bytes, uint64_t n_tiles, void *stream) {
   if (n_tiles == 0) return 0;
   if (J.fast_id != FAST_NONE) {
-    static int sm_count = 0;
-    if (!sm_count) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
+    static int sm_counts[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &sm_count = sm_counts[(dev >= 0 && dev < 64) ? dev : 0];
+    if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     return launch_fast_job(J, sm_count, stream);
   }
   const unsigned grid = (unsigned)(n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull);

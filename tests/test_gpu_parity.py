@@ -458,3 +458,32 @@ def test_column_kernels(ib, torch_mod, checker):
         assert oracle.rel_l2(got, checker.c2c(b, [1], True, 1.0)) <= tol(128, dt)
     print(sorted(used))
     assert any(k.startswith("colfast2") for k in used)
+
+
+def test_host_staging_pipeline(ib, torch_mod, checker):
+    """Host arrays large enough to take the chunked H2D -> kernel -> D2H pipeline must give exactly what
+    the device-resident call gives (same kernels, same arithmetic), in and out of place, for the
+    register kernels and the generic engine; plus parity of sampled rows against the oracle."""
+    rng = np.random.default_rng(41)
+    x = rnd(rng, (6000, 1024), np.complex128)                       # 94 MiB each way: fast2p, several chunks
+    want_dev = ib.fft(torch_mod.from_numpy(x).cuda()).cpu().numpy()
+    got = ib.fft(x)
+    assert np.array_equal(got, want_dev)
+    assert oracle.max_row_rel_l2(got[::997], checker.c2c(x[::997], [1])) <= tol(1024)
+    y = x.copy()
+    ib.fft_inplace(y)
+    assert np.array_equal(y, want_dev)
+    r = rnd(rng, (3000, 4096), np.float64)                          # r2c through fast3 2048, out of place
+    spec = np.empty((3000, 2049), np.complex128)
+    apply_nd(ib, "r2c", r, spec, [1])
+    sd = torch_mod.empty((3000, 2049), dtype=torch_mod.complex128, device="cuda")
+    apply_nd(ib, "r2c", torch_mod.from_numpy(r).cuda(), sd, [1])
+    assert np.array_equal(spec, sd.cpu().numpy())
+    p = rnd(rng, (5000, 1000), np.float64)                          # packed in-place layout of the C API, generic engine
+    q = ib.rfft_packed(p)
+    assert oracle.max_row_rel_l2(q[::499], checker.rfft_rows(p[::499].copy(), True, 1.0)) <= tol(1000)
+    assert oracle.max_row_rel_l2(ib.rfft_packed(q, forward=False), p) <= 2e-15 * 10
+    v = rnd(rng, (4000, 600), np.complex128)[:, ::2]                # strided view: gaps in the input rows
+    out = np.empty((4000, 300), np.complex128)
+    apply_nd(ib, "c2c", v, out, [1])
+    assert oracle.max_row_rel_l2(out[::333], checker.c2c(np.ascontiguousarray(v[::333]), [1])) <= tol(300)
