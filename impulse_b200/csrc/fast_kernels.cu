@@ -56,6 +56,14 @@ template <typename T, int R, int M> __device__ __forceinline__ cx<T> mul_root(cx
   }
 }
 
+// v * exp(-2*pi*i*m/R) for an m that is a compile-time constant after unrolling
+template <typename T, int R, int M = 0> struct RootSel {
+  static __device__ __forceinline__ cx<T> run(cx<T> v, int m) { return m == M ? mul_root<T, R, M>(v) : RootSel<T, R, M + 1>::run(v, m); }
+};
+template <typename T, int R> struct RootSel<T, R, R> {
+  static __device__ __forceinline__ cx<T> run(cx<T> v, int) { return v; }
+};
+
 // forward DFT of R points held in registers, natural order in and out
 template <typename T, int R> struct RegFFT {
   static __device__ __forceinline__ void run(cx<T> (&x)[R]) { Bfly<T, R>::run(x); }
@@ -97,6 +105,7 @@ template <typename T, int RA, int RB> struct Composite {
 };
 template <typename T> struct RegFFT<T, 16> { static __device__ __forceinline__ void run(cx<T> (&x)[16]) { Composite<T, 4, 4>::run(x); } };
 template <typename T> struct RegFFT<T, 32> { static __device__ __forceinline__ void run(cx<T> (&x)[32]) { Composite<T, 4, 8>::run(x); } };
+template <typename T> struct RegFFT<T, 9> { static __device__ __forceinline__ void run(cx<T> (&x)[9]) { Composite<T, 3, 3>::run(x); } };
 template <typename T> struct RegFFT<T, 6> { static __device__ __forceinline__ void run(cx<T> (&x)[6]) { Composite<T, 2, 3>::run(x); } };
 template <typename T> struct RegFFT<T, 10> { static __device__ __forceinline__ void run(cx<T> (&x)[10]) { Composite<T, 2, 5>::run(x); } };
 template <typename T> struct RegFFT<T, 18> { static __device__ __forceinline__ void run(cx<T> (&x)[18]) { Composite<T, 2, 9>::run(x); } };
@@ -395,7 +404,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
              unsigned int *__restrict__ sched) {
   // pass-1 twiddles W_N^(t*k1) as a product A[k1>>2]*B[k1&3] of six per-thread values held in registers
   // for the whole kernel (R1 = 16): 15 global table loads per row become 9 multiplies
-  constexpr bool TW1_REGS = (R1 == 16) && (E / R1 == 1);
+  constexpr bool TW1_REGS = (R1 == 16);  // with E/R1 > 1 the extra factor W_E^(m*k1) is a compile-time root
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1, P2 = R1 * R2;
   constexpr int NB1 = E / R1, NB2 = E / R2, NB3 = E / R3;
@@ -475,6 +484,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
           if (a == 0) y[k] = cmul(y[k], twB[b - 1]);
           else if (b == 0) y[k] = cmul(y[k], twA[a - 1]);
           else y[k] = cmul(y[k], cmul(twA[a - 1], twB[b - 1]));
+          if (NB1 > 1 && m > 0) y[k] = RootSel<T, E>::run(y[k], (m * k) % E);
         }
       } else {
 #pragma unroll
@@ -623,6 +633,8 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
 // axes of N-D transforms and both launches of the four-step split (optional W_N^(k*n2) store twiddle).
 // One group of LPC lines per CTA: the hardware block scheduler balances the SMs.
 // =================================================================================================
+constexpr uint64_t kColPrefetchDistance = 148 * 12;  // groups ahead (about one resident wave)
+
 template <typename T, int R1, int R2, int LPC, bool BWD>
 __global__ void __launch_bounds__(LPC * R2)
 colfast2_kernel(const __grid_constant__ LineJob J) {
@@ -641,6 +653,18 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   const cx<T> *in = reinterpret_cast<const cx<T> *>(J.in) + off_in;
   cx<T> *out = reinterpret_cast<cx<T> *>(J.out) + off_out;
   const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);   // W_N^m
+  // CTAs are short-lived and cannot double-buffer: instead each one pulls the input of the group that
+  // will be scheduled a few waves later into L2 (one lane per 128-byte run issues the prefetch)
+  if (line == 0) {
+    const uint64_t pg = (uint64_t)blockIdx.x + kColPrefetchDistance;
+    if (pg < (uint64_t)gridDim.x) {
+      const uint64_t p0 = (pg % g0n) * LPC, pr = pg / g0n, p1 = pr % J.bdim[1], p2 = pr / J.bdim[1];
+      const cx<T> *pin = reinterpret_cast<const cx<T> *>(J.in) + (int64_t)p0 + (int64_t)p1 * J.bs_in[1] + (int64_t)p2 * J.bs_in[2];
+#pragma unroll
+      for (int j = 0; j < R1; ++j)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pin + (int64_t)(i + R2 * j) * J.es_in));
+    }
+  }
   cx<T> x[R1];
 #pragma unroll
   for (int j = 0; j < R1; ++j) {
@@ -721,7 +745,7 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST2_1024_F32: g_last_kernel = "fast2_kernel<float,32,32,4,4>"; return launch_fast2<float, 32, 32, 4, 4>(J, sm_count, s);
     case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3>(J, sm_count, s);
     case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2>(J, sm_count, s);
-    case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,32,16,16,E32>"; return launch_fast3<double, 32, 16, 16, 32, 1>(J, sm_count, s);
+    case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1>(J, sm_count, s);
     case COL2_32_F64: g_last_kernel = "colfast2_kernel<double,8,4,8>"; return launch_colfast2<double, 8, 4, 8>(J, s);
     case COL2_512_F64: g_last_kernel = "colfast2_kernel<double,32,16,8>"; return launch_colfast2<double, 32, 16, 8>(J, s);
     case COL2_32_F32: g_last_kernel = "colfast2_kernel<float,8,4,16>"; return launch_colfast2<float, 8, 4, 16>(J, s);

@@ -490,7 +490,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       uint32_t id = FAST_NONE, r1 = 0, r2 = 0, r3 = 0;
       if (L == 2048) { id = f64 ? FAST3_2048_F64 : FAST3_2048_F32; r1 = 16; r2 = 16; r3 = 8; }
       else if (L == 4096) { id = f64 ? FAST3_4096_F64 : FAST3_4096_F32; r1 = 16; r2 = 16; r3 = 16; }
-      else if (L == 8192 && f64) { id = FAST3_8192_F64; r1 = 32; r2 = 16; r3 = 16; }
+      else if (L == 8192 && f64) { id = FAST3_8192_F64; r1 = 16; r2 = 16; r3 = 32; }
       else if (L == 500 && f64) { id = FAST3_500_F64; r1 = 5; r2 = 10; r3 = 10; }
       else if (L == 1944 && f64) { id = FAST3_1944_F64; r1 = 6; r2 = 18; r3 = 18; }
       else if (L == 1000 && f64) { id = FAST3_1000_F64; r1 = 10; r2 = 10; r3 = 10; }

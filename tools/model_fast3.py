@@ -53,7 +53,7 @@ def model(N, R1, R2, R3, E, x, check_conflicts=True):
     return out, conflicts
 
 rng = np.random.default_rng(0)
-for (N, R1, R2, R3, E) in ((4096, 16, 16, 16, 16), (2048, 8, 16, 16, 16), (2048, 16, 16, 8, 16), (8192, 32, 16, 16, 32),
+for (N, R1, R2, R3, E) in ((4096, 16, 16, 16, 16), (2048, 8, 16, 16, 16), (2048, 16, 16, 8, 16), (8192, 32, 16, 16, 32), (8192, 16, 16, 32, 32),
                            (512, 8, 8, 8, 8), (1000, 10, 10, 10, 10), (500, 5, 10, 10, 10)):
     x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
     try:
