@@ -97,6 +97,9 @@ enum FastId : uint32_t {
   COL2_512_F64 = 20,
   COL2_32_F32 = 21,
   COL2_512_F32 = 22,
+  FASTBLUE_2048_F64 = 23,
+  FASTBLUE_4096_F64 = 24,
+  FASTBLUE_8192_F64 = 25,
 };
 
 struct Phase {
@@ -142,6 +145,8 @@ struct LineJob {
   uint32_t tw4_dim;
   uint32_t zero_pad_from;  // ST_C: elements e >= this are stored as zero (0 = off; Bluestein staging)
   const void *f3_tw1, *f3_tw2;  // twiddle tables of the three-pass register kernels ([k1][i1], [k2][i2])
+  const void *fb_bf, *fb_corr;  // fused Bluestein (fastblue_kernel): FFT(b)/M natural order, alias corrections
+  uint32_t fb_d;                // its deficiency d = max(0, 2L-1-M)
   const void *mul_tab;     // ST_C: multiply output element e by mul_tab[line_index + mul_stride*e] (null = off)
   uint32_t mul_stride;
   double fct;

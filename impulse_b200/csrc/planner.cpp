@@ -156,6 +156,7 @@ PlanCache::~PlanCache() {
   for (auto &kv : real_tw_) if (kv.second) alloc_->release(kv.second);
   for (auto &kv : tw4_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
   for (auto &kv : f3_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
+  for (auto &kv : fb_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
 }
 
 int PlanCache::status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err) {
@@ -224,6 +225,41 @@ int PlanCache::bluestein_natural_table(uint32_t L, int dtype, const void **out, 
     if (!e->d_bkf_nat) { *err = "table upload failed"; return ERR_NOMEM; }
   }
   *out = e->d_bkf_nat;
+  return ST_OK;
+}
+
+// Fused Bluestein with a power-of-two work length M that may fall short of 2L-1 by d points:
+// bf = FFT_M(wrapped chirp, positive lags kept)/M in natural order; corr[k][j] = b(n-k) - b(M-n+k) with
+// n = L-d+j, the products lost to aliasing (outputs k < d only).  See fastblue_kernel.
+int PlanCache::fastblue_tables(uint32_t L, uint32_t M, int dtype, const void **bf, const void **corr, uint32_t *dd, std::string *err) {
+  const uint32_t need = 2 * L - 1;
+  const uint32_t d = need > M ? need - M : 0;
+  *dd = d;
+  if (d > 16 || L > M) { *err = "work length too short for the fused Bluestein"; return ERR_UNSUPPORTED; }
+  std::lock_guard<std::mutex> lk(mu_);
+  auto key = std::make_pair(((uint64_t)L << 32) | M, dtype);
+  auto it = fb_.find(key);
+  if (it != fb_.end()) { *bf = it->second.first; *corr = it->second.second; return ST_OK; }
+  std::vector<cld> b(L), bw(M, cld(0, 0));
+  uint64_t coeff = 0;
+  for (uint32_t m = 0; m < L; ++m) {
+    if (m > 0) { coeff += 2 * (uint64_t)m - 1; if (coeff >= 2 * (uint64_t)L) coeff -= 2 * (uint64_t)L; }
+    b[m] = unit_root(coeff, 2 * (uint64_t)L);
+  }
+  const ld xn = 1.0L / (ld)M;
+  for (uint32_t m = 1; m < L; ++m) bw[M - m] = b[m] * xn;   // negative lags first ...
+  for (uint32_t m = 0; m < L; ++m) bw[m] = b[m] * xn;       // ... positive lags win the aliased residues
+  host_fft(bw, choose_radices(M));
+  std::vector<cld> cr(16 * 16, cld(0, 0));
+  for (uint32_t k = 0; k < d; ++k)
+    for (uint32_t j = k; j < d; ++j) {
+      const uint32_t n = L - d + j;              // n >= L-d+k
+      cr[k * 16 + j] = b[n - k] - b[M - n + k];  // true lag n-k vs the positive lag stored at residue M-(n-k)
+    }
+  void *dbf = upload_cplx(alloc_, bw, dtype), *dcr = upload_cplx(alloc_, cr, dtype);
+  if (!dbf || !dcr) { *err = "table upload failed"; return ERR_NOMEM; }
+  fb_[key] = std::make_pair(dbf, dcr);
+  *bf = dbf; *corr = dcr;
   return ST_OK;
 }
 
@@ -477,6 +513,24 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       case 128: J->fast_id = f64 ? COL2_128_F64 : COL2_128_F32; break;
       case 256: J->fast_id = f64 ? COL2_256_F64 : COL2_256_F32; break;
       default: J->fast_id = f64 ? COL2_512_F64 : COL2_512_F32; break;
+    }
+  }
+  // fused Bluestein on the register core: complex Bluestein lengths up to 4104 points, and odd real
+  // lengths in that range with two rows packed per complex line (Hermitian layout); contiguous rows
+  if (E->blue && f64 && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
+      J->bdim[1] == 1 && J->bdim[2] == 1 && !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_FASTBLUE", 0)) {
+    const bool okc = s.kind == KIND_C2C;
+    const bool okr = s.kind != KIND_C2C && !even && s.layout == RL_HERMITIAN;
+    uint32_t M = 0, r1 = 16, r2 = 16, r3 = 0, id = FAST_NONE;
+    if (2 * L - 1 <= 2048 + 8 && L > 256) { M = 2048; r3 = 8; id = FASTBLUE_2048_F64; }
+    else if (2 * L - 1 <= 4096 + 8 && L > 256) { M = 4096; r3 = 16; id = FASTBLUE_4096_F64; }
+    else if (2 * L - 1 <= 8192 + 8 && L > 256) { M = 8192; r3 = 32; id = FASTBLUE_8192_F64; }
+    if ((okc || okr) && id != FAST_NONE) {
+      rc = fast3_tables(M, r1, r2, r3, s.dtype, &J->f3_tw1, &J->f3_tw2, err);
+      if (rc) return rc;
+      rc = fastblue_tables(L, M, s.dtype, &J->fb_bf, &J->fb_corr, &J->fb_d, err);
+      if (rc) return rc;
+      J->fast_id = id;
     }
   }
   // three-pass register kernels: c2c of 2048/4096/8192 points, and even-N r2c/c2r (Hermitian layout)

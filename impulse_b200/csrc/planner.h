@@ -110,6 +110,7 @@ class PlanCache {
   int status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err);
   int real_twiddle(uint32_t N, int dtype, const void **out, std::string *err);
   int bluestein_natural_table(uint32_t L, int dtype, const void **out, std::string *err);
+  int fastblue_tables(uint32_t L, uint32_t M, int dtype, const void **bf, const void **corr, uint32_t *d, std::string *err);
   int fast3_tables(uint32_t N, uint32_t R1, uint32_t R2, uint32_t R3, int dtype, const void **tw1, const void **tw2, std::string *err);
   int four_step_tables(uint32_t N, int dtype, const void **hi, const void **lo, uint32_t *shift, std::string *err);
   int build_line_job(const LineSpec &s, LineJob *job, LaunchCfg *cfg, std::string *err);
@@ -122,6 +123,7 @@ class PlanCache {
   std::map<std::pair<uint32_t, int>, void *> real_tw_;
   std::map<std::pair<uint32_t, int>, std::pair<void *, void *>> tw4_;
   std::map<std::pair<uint64_t, int>, std::pair<void *, void *>> f3_;
+  std::map<std::pair<uint64_t, int>, std::pair<void *, void *>> fb_;
 };
 
 // planner utilities exposed for tests

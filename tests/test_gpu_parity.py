@@ -487,3 +487,41 @@ def test_host_staging_pipeline(ib, torch_mod, checker):
     out = np.empty((4000, 300), np.complex128)
     apply_nd(ib, "c2c", v, out, [1])
     assert oracle.max_row_rel_l2(out[::333], checker.c2c(np.ascontiguousarray(v[::333]), [1])) <= tol(300)
+
+
+def test_fused_bluestein(ib, torch_mod, checker):
+    """Fused register Bluestein (fastblue): complex prime lengths across the three work sizes, including
+    work lengths SHORTER than 2L-1 (alias corrections: 1031->2048 is too short by 13 and goes to 4096,
+    2051->4096 by 5, 4099->8192 by 5, 4100 even -> generic), and odd real lengths with two rows packed per
+    complex line (odd and even row counts, both `forward` flags)."""
+    rng = np.random.default_rng(51)
+    used = set()
+    for n in (257, 521, 1021, 1031, 2039, 2051, 2053, 3001, 4093, 4099, 4101):
+        for rows in (1, 2, 7, 64):
+            x = rnd(rng, (rows, n), np.complex128)
+            xd = torch_mod.from_numpy(x).cuda()
+            for fwd in (True, False):
+                got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], fwd, 0.9).cpu().numpy()
+                used.add(ib.last_kernel())
+                assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.9)) <= tol(n), (n, rows, fwd)
+    for n in (263, 1019, 2043, 4099):   # 2043 = 3^2 * 227
+        for rows in (1, 2, 5, 32):
+            r = rnd(rng, (rows, n), np.float64)
+            rd = torch_mod.from_numpy(r).cuda()
+            for fwd in (True, False):
+                spec = apply_nd(ib, "r2c", rd, torch_mod.empty((rows, n // 2 + 1), dtype=torch_mod.complex128, device="cuda"),
+                                [1], fwd, 1.0)
+                used.add(ib.last_kernel())
+                assert oracle.max_row_rel_l2(spec.cpu().numpy(), checker.r2c(r, [1], fwd, 1.0)) <= tol(n), (n, rows, fwd)
+            sp = checker.r2c(r, [1], True, 1.0)
+            sd = torch_mod.from_numpy(sp).cuda()
+            for fwd in (False, True):
+                back = apply_nd(ib, "c2r", sd, torch_mod.empty_like(rd), [1], fwd, 1.0 / n).cpu().numpy()
+                used.add(ib.last_kernel())
+                assert oracle.max_row_rel_l2(back, checker.c2r(sp, r.shape, [1], fwd, 1.0 / n)) <= tol(n), (n, rows, fwd)
+            rt = apply_nd(ib, "c2r", apply_nd(ib, "r2c", rd, torch_mod.empty((rows, n // 2 + 1), dtype=torch_mod.complex128,
+                                                                            device="cuda"), [1]),
+                          torch_mod.empty_like(rd), [1], False, 1.0 / n).cpu().numpy()
+            assert oracle.max_row_rel_l2(rt, r) <= 2e-15 * np.log2(n), (n, rows)
+    print(sorted(used))
+    assert any(k.startswith("fastblue") for k in used)
