@@ -139,8 +139,9 @@ namespace {
 size_t side_align(const NdDesc &d, bool input) {
   const size_t r = d.dtype == DT_F64 ? 8 : 4;
   bool real_side;
-  if (input) real_side = d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX);
-  else real_side = d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX);
+  const bool r2r = d.kind == KIND_DCT || d.kind == KIND_DST;
+  if (input) real_side = r2r || d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX);
+  else real_side = r2r || d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX);
   return real_side ? r : 2 * r;
 }
 
@@ -150,7 +151,8 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
   if (nd.empty) return 0;
   if (((uintptr_t)in % p->in_esz) || ((uintptr_t)out % p->out_esz))
     return fail(IMPULSE_FFT_ERR_STRIDE, "data pointer is not aligned to its element size");
-  if (in == out && nd.desc.kind == KIND_C2C && nd.desc.stride_in != nd.desc.stride_out)
+  if (in == out && (nd.desc.kind == KIND_C2C || nd.desc.kind == KIND_DCT || nd.desc.kind == KIND_DST) &&
+      nd.desc.stride_in != nd.desc.stride_out)
     return fail(IMPULSE_FFT_ERR_STRIDE, "stride mismatch");  // hdronly.h:455-456
   void *tmp = nullptr, *tmp2 = nullptr, *tmp3 = nullptr;
   if (nd.tmp_bytes) {
@@ -324,7 +326,7 @@ int create_plan(impulse_fft_plan *out, const NdDesc &d) {
 
 // one-shot plan cache (the role of get_plan, hdronly.h:2655-2706)
 struct OneShotKey {
-  int dev, kind, dtype, layout, forward;
+  int dev, kind, dtype, layout, forward;  // for DCT/DST `layout` carries the type and `forward` the ortho flag
   std::vector<size_t> shape, axes;
   std::vector<ptrdiff_t> sin, sout;
   bool operator<(const OneShotKey &o) const {
@@ -340,8 +342,10 @@ int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, 
              const ptrdiff_t *sout, size_t naxes, const size_t *axes, int forward, const void *in, void *out,
              double fct, void *stream) {
   NdDesc d;
-  int rc = make_desc(&d, kind, dtype, layout, forward, ndim, shape, sin, sout, naxes, axes);
+  const bool r2r = kind == KIND_DCT || kind == KIND_DST;
+  int rc = make_desc(&d, kind, dtype, r2r ? RL_HERMITIAN : layout, r2r ? 1 : forward, ndim, shape, sin, sout, naxes, axes);
   if (rc) return rc;
+  if (r2r) { d.r2r_type = layout; d.ortho = forward != 0; }
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }
   OneShotKey key{dev, kind, dtype, layout, forward != 0, d.shape, d.axes, d.stride_in, d.stride_out};
@@ -442,6 +446,19 @@ int impulse_fft_c2r(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t
                     const void *data_in, void *data_out, double fct, size_t, void *stream) {
   return one_shot(KIND_C2R, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, forward,
                   data_in, data_out, fct, stream);
+}
+
+int impulse_fft_dct(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int type, const void *data_in,
+                    void *data_out, double fct, int ortho, size_t, void *stream) {
+  if (type < 1 || type > 4) return fail(IMPULSE_FFT_ERR_INVALID, "invalid DCT type");  // hdronly.h:3288
+  return one_shot(KIND_DCT, dtype, type, ndim, shape, stride_in, stride_out, naxes, axes, ortho != 0, data_in, data_out, fct, stream);
+}
+int impulse_fft_dst(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int type, const void *data_in,
+                    void *data_out, double fct, int ortho, size_t, void *stream) {
+  if (type < 1 || type > 4) return fail(IMPULSE_FFT_ERR_INVALID, "invalid DST type");  // hdronly.h:3305
+  return one_shot(KIND_DST, dtype, type, ndim, shape, stride_in, stride_out, naxes, axes, ortho != 0, data_in, data_out, fct, stream);
 }
 
 int impulse_fft_cfft_rows(double *data, size_t nrows, size_t length, int forward, double fct, void *stream) {

@@ -215,6 +215,45 @@ IMP_HD void load_one(const LineJob &J, cx<T> *S /*line base*/, int64_t off, uint
       S[phys<T>(J, e)] = v;
       if (e > 0) S[phys<T>(J, J.n_real - e)] = cconj(v);
     } break;
+    case LD_X_ZPAD: {
+      const uint32_t N = J.n_real;
+      S[phys<T>(J, e)] = e < N ? mk<T>(inr[off + (int64_t)e * es], (T)0) : mk<T>((T)0, (T)0);
+    } break;
+    case LD_X_TW: {
+      const uint32_t N = J.n_real;
+      cx<T> v = mk<T>((T)0, (T)0);
+      if (e < N) {
+        const T f = (T)(e == 0 ? J.x_f0 : J.x_f);
+        const cx<T> w = IMP_LDG((const cx<T> *)J.x_tw + 2 * e);
+        const T xv = inr[off + (int64_t)e * es] * f;
+        v = mk<T>(xv * w.x, xv * w.y);
+      }
+      S[phys<T>(J, e)] = v;
+    } break;
+    case LD_X_TW_SHIFT: {
+      const uint32_t N = J.n_real;
+      cx<T> v = mk<T>((T)0, (T)0);
+      if (e >= 1 && e <= N) {
+        const T f = (T)(e == N ? J.x_fl : J.x_f) * (T)(e == 1 ? J.x_f0 : 1.0);
+        const cx<T> w = IMP_LDG((const cx<T> *)J.x_tw + 2 * e);
+        const T xv = inr[off + (int64_t)(e - 1) * es] * f;
+        v = mk<T>(xv * w.x, xv * w.y);
+      }
+      S[phys<T>(J, e)] = v;
+    } break;
+    case LD_X_SYM: {
+      const uint32_t N = J.n_real, M = J.n_seq;
+      const uint32_t j = e < N ? e : M - e;
+      const T f = (T)((j == 0 || j == N - 1) ? J.x_f0 : 1.0);
+      S[phys<T>(J, e)] = mk<T>(inr[off + (int64_t)j * es] * f, (T)0);
+    } break;
+    case LD_X_ASYM: {
+      const uint32_t N = J.n_real, M = J.n_seq;
+      T xv = (T)0;
+      if (e >= 1 && e <= N) xv = inr[off + (int64_t)(e - 1) * es];
+      else if (e > N + 1) xv = -inr[off + (int64_t)(M - e - 1) * es];
+      S[phys<T>(J, e)] = mk<T>(xv, (T)0);
+    } break;
     default: break;
   }
 }
@@ -466,6 +505,14 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e,
       if (e == 0) outr[off] = v.x;
       else if (e == J.n_seq) outr[off + (int64_t)(J.n_real - 1) * es] = v.x;
       else { outr[off + (2 * (int64_t)e - 1) * es] = v.x; outr[off + (2 * (int64_t)e) * es] = v.y; }
+    } break;
+    case ST_X: {
+      cx<T> v = read_bin<T>(J, S, e + J.x_shift);
+      if (J.x_wadd != 0xffffffffu) v = cmul(v, IMP_LDG((const cx<T> *)J.x_tw + (2 * e + J.x_wadd)));
+      T y = (J.x_im ? -v.y : v.x) * (T)J.x_s * f;
+      if (e == 0) y *= (T)J.x_s0;
+      if (e == J.n_real - 1) y *= (T)J.x_sn;
+      outr[off + (int64_t)e * es] = y;
     } break;
     case ST_HC_FULL: {
       cx<T> v = read_bin<T>(J, S, e);

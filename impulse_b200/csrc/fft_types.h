@@ -47,6 +47,12 @@ enum LoadMode : uint8_t {
   LD_HERM_FULL = 4,  // c2r odd N: X[0..(N-1)/2] Hermitian-extended to N complex
   LD_HC_EVEN = 5,    // FFTPACK halfcomplex reals -> X[0..N/2]   (pocketfft.nim:228-238)
   LD_HC_FULL = 6,    // FFTPACK halfcomplex reals -> Hermitian-extended N complex
+  // real-to-real transforms (DCT/DST I-IV, pocketfft_hdronly.h:2424-2648) embedded in a complex FFT of M points
+  LD_X_ZPAD = 7,     // u[n] = x[n] (n<N), 0 above                          DCT-II, DST-II   (M = 2N)
+  LD_X_TW = 8,       // u[n] = f_n x[n] W_4N^n (n<N), 0 above               DCT-III, DCT-IV, DST-IV
+  LD_X_TW_SHIFT = 9, // u[m] = f_m x[m-1] W_4N^m (1<=m<=N), 0 elsewhere     DST-III
+  LD_X_SYM = 10,     // even extension, M = 2(N-1)                          DCT-I
+  LD_X_ASYM = 11,    // odd extension,  M = 2(N+1)                          DST-I
 };
 
 enum StoreMode : uint8_t {
@@ -59,6 +65,7 @@ enum StoreMode : uint8_t {
   ST_HC_FULL = 6,    // odd-N r2c written as FFTPACK halfcomplex reals
   ST_R2C_EVEN_SYM = 7,   // even-N r2c, all N bins (Hermitian half + conjugate mirror): fused `symmetrize`
   ST_HERM_SYM = 8,       // odd-N r2c, all N bins                                   (pocketfft.nim:160-171)
+  ST_X = 9,              // real-to-real: y[k] = s * (Re | -Im)(W_8N^(mul*k+add) * F[k+shift])
 };
 
 enum JobFlags : uint32_t {
@@ -147,6 +154,12 @@ struct LineJob {
   const void *f3_tw1, *f3_tw2;  // twiddle tables of the three-pass register kernels ([k1][i1], [k2][i2])
   const void *fb_bf, *fb_corr;  // fused Bluestein (fastblue_kernel): FFT(b)/M natural order, alias corrections
   uint32_t fb_d;                // its deficiency d = max(0, 2L-1-M)
+  // real-to-real (DCT/DST): W_8N^m table (m < 2N+2), load factors (first / other / last input element),
+  // store recipe
+  const void *x_tw;
+  double x_f0, x_f, x_fl, x_s, x_s0, x_sn;
+  uint32_t x_shift, x_wadd;   // F index offset; twiddle index 2k + x_wadd (x_wadd = 0xffffffff: no twiddle)
+  uint32_t x_im;              // 0: real part, 1: minus imaginary part
   const void *mul_tab;     // ST_C: multiply output element e by mul_tab[line_index + mul_stride*e] (null = off)
   uint32_t mul_stride;
   double fct;

@@ -154,6 +154,7 @@ PlanCache::~PlanCache() {
     for (void *p : {e->d_tw, e->d_perm, e->d_bk, e->d_bkf, e->d_bkf_nat}) if (p) alloc_->release(p);
   }
   for (auto &kv : real_tw_) if (kv.second) alloc_->release(kv.second);
+  for (auto &kv : r2r_tw_) if (kv.second) alloc_->release(kv.second);
   for (auto &kv : tw4_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
   for (auto &kv : f3_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
   for (auto &kv : fb_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
@@ -302,6 +303,21 @@ int PlanCache::four_step_tables(uint32_t N, int dtype, const void **hi, const vo
   return ST_OK;
 }
 
+// W_8N^m = exp(-2*pi*i*m/(8N)), m < 2N+2: W_4N^n = tab[2n], W_8N^(2k+1) = tab[2k+1]  (DCT/DST II-IV)
+int PlanCache::r2r_twiddle(uint32_t N, int dtype, const void **out, std::string *err) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto key = std::make_pair(N, dtype);
+  auto it = r2r_tw_.find(key);
+  if (it != r2r_tw_.end()) { *out = it->second; return ST_OK; }
+  std::vector<cld> w(2 * (size_t)N + 2);
+  for (uint32_t m = 0; m < 2 * N + 2; ++m) w[m] = std::conj(unit_root(m, 8 * (uint64_t)N));
+  void *d = upload_cplx(alloc_, w, dtype);
+  if (!d) { *err = "table upload failed"; return ERR_NOMEM; }
+  r2r_tw_[key] = d;
+  *out = d;
+  return ST_OK;
+}
+
 int PlanCache::real_twiddle(uint32_t N, int dtype, const void **out, std::string *err) {
   std::lock_guard<std::mutex> lk(mu_);
   auto key = std::make_pair(N, dtype);
@@ -322,8 +338,15 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   if (N == 0) { *err = "zero-length transform"; return ERR_INVALID; }
   const bool f64 = s.dtype == DT_F64;
   const bool even = (N % 2) == 0;
+  const bool r2r = s.kind == KIND_DCT || s.kind == KIND_DST;
   uint32_t L = N;
-  if (s.kind != KIND_C2C && even) L = N / 2;
+  if (r2r) {  // complex embedding length M (see LD_X_* in fft_types.h)
+    if (s.r2r_type < 1 || s.r2r_type > 4) { *err = s.kind == KIND_DCT ? "invalid DCT type" : "invalid DST type"; return ERR_INVALID; }
+    if (s.r2r_type == 1 && s.kind == KIND_DCT && N < 2) { *err = "DCT-I needs at least two points"; return ERR_INVALID; }
+    L = s.r2r_type == 1 ? (s.kind == KIND_DCT ? 2 * (N - 1) : 2 * (N + 1)) : 2 * N;
+  } else if (s.kind != KIND_C2C && even) {
+    L = N / 2;
+  }
   const Engine1D *E = nullptr;
   int rc = status_engine(L, s.dtype, &E, err);
   if (rc) return rc;
@@ -399,6 +422,33 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       }
       if (s.layout == RL_FULLSYM) { *err = "FULLSYM layout is an r2c output layout"; return ERR_INVALID; }
       break;
+    case KIND_DCT:
+    case KIND_DST: {
+      const bool cosine = s.kind == KIND_DCT;
+      const double r2 = 1.4142135623730950488016887242097, ir2 = 0.70710678118654752440084436210485;
+      J->n_load = L; J->n_store = N; J->store_mode = ST_X;
+      J->x_f0 = J->x_f = J->x_fl = J->x_s = J->x_s0 = J->x_sn = 1.0;
+      J->x_shift = 0; J->x_wadd = 0xffffffffu; J->x_im = cosine ? 0 : 1;
+      if (s.r2r_type != 1) { rc = r2r_twiddle(N, s.dtype, &J->x_tw, err); if (rc) return rc; }
+      switch (s.r2r_type) {
+        case 1:
+          J->load_mode = cosine ? LD_X_SYM : LD_X_ASYM;
+          if (cosine) { if (s.ortho) { J->x_f0 = r2; J->x_s0 = J->x_sn = ir2; } }
+          else J->x_shift = 1;
+          break;
+        case 2:
+          J->load_mode = LD_X_ZPAD; J->x_s = 2.0; J->x_wadd = cosine ? 0 : 2; J->x_shift = cosine ? 0 : 1;
+          if (s.ortho) J->x_s0 = ir2;
+          break;
+        case 3:
+          J->load_mode = cosine ? LD_X_TW : LD_X_TW_SHIFT; J->x_f = 2.0; J->x_fl = 1.0;
+          J->x_f0 = s.ortho ? r2 : 1.0;
+          break;
+        default:
+          J->load_mode = LD_X_TW; J->x_s = 2.0; J->x_wadd = 1;
+          break;
+      }
+    } break;
     default: *err = "bad transform kind"; return ERR_INVALID;
   }
 
@@ -520,7 +570,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   if (E->blue && f64 && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
       J->bdim[1] == 1 && J->bdim[2] == 1 && !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_FASTBLUE", 0)) {
     const bool okc = s.kind == KIND_C2C;
-    const bool okr = s.kind != KIND_C2C && !even && s.layout == RL_HERMITIAN;
+    const bool okr = (s.kind == KIND_R2C || s.kind == KIND_C2R) && !even && s.layout == RL_HERMITIAN;
     uint32_t M = 0, r1 = 16, r2 = 16, r3 = 0, id = FAST_NONE;
     if (2 * L - 1 <= 2048 + 8 && L > 256) { M = 2048; r3 = 8; id = FASTBLUE_2048_F64; }
     else if (2 * L - 1 <= 4096 + 8 && L > 256) { M = 4096; r3 = 16; id = FASTBLUE_4096_F64; }
@@ -606,12 +656,13 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   const size_t rsz = d.dtype == DT_F64 ? 8 : 4, csz = 2 * rsz;
   const size_t last = d.axes.back();
   std::vector<size_t> cshape = d.shape;  // shape of the complex (half-spectrum) array for real transforms
-  if (d.kind != KIND_C2C) {
+  if (d.kind == KIND_R2C || d.kind == KIND_C2R) {
     if (d.layout == RL_HERMITIAN) cshape[last] = d.shape[last] / 2 + 1;
     else if (d.layout == RL_FULLSYM) cshape[last] = d.shape[last];
   }
-  const size_t in_esz = (d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX)) ? rsz : csz;
-  const size_t out_esz = (d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX)) ? rsz : csz;
+  const bool nd_r2r = d.kind == KIND_DCT || d.kind == KIND_DST;
+  const size_t in_esz = (nd_r2r || d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX)) ? rsz : csz;
+  const size_t out_esz = (nd_r2r || d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX)) ? rsz : csz;
   const std::vector<size_t> &in_shape = (d.kind == KIND_C2R && d.layout == RL_HERMITIAN) ? cshape : d.shape;
   const std::vector<size_t> &out_shape = (d.kind == KIND_R2C && d.layout != RL_HALFCOMPLEX) ? cshape : d.shape;
   for (size_t i = 0; i < nd; ++i) {
@@ -681,6 +732,8 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     s.mul_tab = mul_tab;
     s.mul_stride = mul_stride;
     s.blue_stage = blue_stage;
+    s.r2r_type = d.r2r_type;
+    s.ortho = d.ortho;
     std::vector<Dim> outer(sd.begin() + (ptrdiff_t)nk, sd.end());
     uint64_t nouter = 1;
     for (auto &o : outer) nouter *= o.n;
@@ -770,6 +823,8 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       dims.push_back({bshape[i], sin[i] / (ptrdiff_t)esz_in, sout[i] / (ptrdiff_t)esz_out});
     }
     const int64_t es_in = sin[axis] / (ptrdiff_t)esz_in, es_out = sout[axis] / (ptrdiff_t)esz_out;
+    if (kind == KIND_DCT || kind == KIND_DST)
+      return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, nullptr, 0, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
     const uint32_t L = (kind != KIND_C2C && N % 2 == 0) ? N / 2 : N;  // complex length run on the device
     const Engine1D *E = nullptr;
     int rc = status_engine(L, d.dtype, &E, err);
@@ -815,6 +870,13 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       rc = add_axis(KIND_C2C, RL_HERMITIAN, d.forward, d.axes[i], (uint32_t)d.shape[d.axes[i]], d.shape,
                     first ? d.stride_in : d.stride_out, csz, d.stride_out, csz,
                     first ? BUF_IN : BUF_OUT, BUF_OUT, first);
+    }
+  } else if (nd_r2r) {
+    // general_nd with ExecDcst (hdronly.h:3105-3121): every axis is the same 1-D transform, fct once
+    for (size_t i = 0; i < d.axes.size() && !rc; ++i) {
+      const bool first = i == 0;
+      rc = add_axis(d.kind, RL_HERMITIAN, true, d.axes[i], (uint32_t)d.shape[d.axes[i]], d.shape,
+                    first ? d.stride_in : d.stride_out, rsz, d.stride_out, rsz, first ? BUF_IN : BUF_OUT, BUF_OUT, first);
     }
   } else if (d.kind == KIND_R2C) {
     // r2c on axes.back(), then c2c in place over the rest on the reduced shape (hdronly.h:3334-3349)

@@ -27,7 +27,7 @@ struct TableAlloc {
   virtual void release(void *dev) = 0;
 };
 
-enum Kind : int { KIND_C2C = 0, KIND_R2C = 1, KIND_C2R = 2 };
+enum Kind : int { KIND_C2C = 0, KIND_R2C = 1, KIND_C2R = 2, KIND_DCT = 3, KIND_DST = 4 };
 enum DType : int { DT_F32 = 0, DT_F64 = 1 };
 enum RealLayout : int { RL_HERMITIAN = 0, RL_HALFCOMPLEX = 1, RL_FULLSYM = 2 };
 
@@ -68,6 +68,8 @@ struct LineSpec {
   uint32_t zero_pad_from = 0;
   const void *mul_tab = nullptr;  // ST_C: multiply by a table indexed line_index + mul_stride*e
   uint32_t mul_stride = 0;
+  int r2r_type = 2;    // DCT/DST type 1..4 (pocketfft_hdronly.h:3284-3318)
+  bool ortho = false;
   int blue_stage = 0;  // multi-launch Bluestein: 1 = load+chirp+zero-pad to scratch, 2 = scratch+chirp+store
 };
 
@@ -87,6 +89,8 @@ struct NdDesc {
   std::vector<size_t> shape;            // c2c: array shape; r2c/c2r: shape of the REAL array
   std::vector<ptrdiff_t> stride_in, stride_out;  // bytes
   std::vector<size_t> axes;
+  int r2r_type = 2;  // DCT/DST only
+  bool ortho = false;
 };
 
 struct NdPlan {
@@ -110,6 +114,7 @@ class PlanCache {
   int status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err);
   int real_twiddle(uint32_t N, int dtype, const void **out, std::string *err);
   int bluestein_natural_table(uint32_t L, int dtype, const void **out, std::string *err);
+  int r2r_twiddle(uint32_t N, int dtype, const void **out, std::string *err);
   int fastblue_tables(uint32_t L, uint32_t M, int dtype, const void **bf, const void **corr, uint32_t *d, std::string *err);
   int fast3_tables(uint32_t N, uint32_t R1, uint32_t R2, uint32_t R3, int dtype, const void **tw1, const void **tw2, std::string *err);
   int four_step_tables(uint32_t N, int dtype, const void **hi, const void **lo, uint32_t *shift, std::string *err);
@@ -121,6 +126,7 @@ class PlanCache {
   std::mutex mu_;
   std::map<std::pair<uint32_t, int>, std::unique_ptr<Engine1D>> engines_;
   std::map<std::pair<uint32_t, int>, void *> real_tw_;
+  std::map<std::pair<uint32_t, int>, void *> r2r_tw_;
   std::map<std::pair<uint32_t, int>, std::pair<void *, void *>> tw4_;
   std::map<std::pair<uint64_t, int>, std::pair<void *, void *>> f3_;
   std::map<std::pair<uint64_t, int>, std::pair<void *, void *>> fb_;

@@ -68,7 +68,48 @@ class FFTDesc:
         apply(self, descOut, descIn)
 
 
-def apply(fft: FFTDesc, descOut: DataDesc, descIn: DataDesc) -> None:
+@dataclass
+class DCTDesc:
+    """Descriptor of a discrete cosine transform (cpp_pocketfft/pocketfft.nim:151-156, 217-233).
+    `sine=True` selects the DST family (pocketfft::dst, imported at pocketfft.nim:120-132 but not
+    reachable through the reference's DCTDesc)."""
+    axes: list = field(default_factory=list)
+    dctType: int = 2
+    scalingFactor: float = 1.0
+    nthreads: int = 1
+    ortho: bool = False
+    sine: bool = False
+
+    @classmethod
+    def init(cls, axes: Sequence[int], dctType: int = 2, ortho: bool = False, scalingFactor: float = 1.0,
+             nthreads: int = 1, sine: bool = False) -> "DCTDesc":
+        if not 1 <= int(dctType) <= 4:
+            raise ValueError("dctType must be in 1..4")  # range[1'i32..4'i32] in the Nim type
+        return cls([int(a) for a in axes], int(dctType), float(scalingFactor), int(nthreads), bool(ortho), bool(sine))
+
+    def apply(self, descOut: DataDesc, descIn: DataDesc) -> None:
+        """pocketfft.nim:279-295."""
+        L = _lib.lib()
+        if descIn.complex or descOut.complex:
+            raise TypeError("DCT/DST are real-to-real transforms")
+        if descIn.dtype != descOut.dtype:
+            raise TypeError("input and output precision differ")
+        nd, na = len(descIn.shape), len(self.axes)
+        if len(descIn.stride) != nd or len(descOut.stride) != nd:
+            raise _lib.FFTError(-2, "stride dimension mismatch")
+        if nd > _lib.MAX_DIMS or na > _lib.MAX_DIMS or any(a < 0 for a in self.axes):
+            raise _lib.FFTError(-1, "bad axis number")
+        fn = L.impulse_fft_dst if self.sine else L.impulse_fft_dct
+        rc = fn(descIn.dtype, nd, (C.c_size_t * nd)(*descIn.shape), (C.c_ssize_t * nd)(*descIn.stride),
+                (C.c_ssize_t * nd)(*descOut.stride), na, (C.c_size_t * na)(*self.axes), self.dctType,
+                B.ptr(descIn.buf), B.ptr(descOut.buf), float(self.scalingFactor), int(self.ortho), int(self.nthreads),
+                B.stream_of(descIn.buf, descOut.buf))
+        _lib.check(rc)
+
+
+def apply(fft, descOut: DataDesc, descIn: DataDesc) -> None:
+    if isinstance(fft, DCTDesc):
+        return fft.apply(descOut, descIn)
     L = _lib.lib()
     if descIn.dtype != descOut.dtype:
         raise TypeError("input and output precision differ")

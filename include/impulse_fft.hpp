@@ -220,4 +220,29 @@ template <typename T> struct FFTDesc {
   }
 };
 
+
+// DCTDesc (NX:151-156, 217-233) and its apply (NX:279-295); `sine` selects pocketfft::dst
+template <typename T> struct DCTDesc {
+  std::vector<std::size_t> axes;
+  int dctType = 2;  // 1..4
+  T scalingFactor = 1;
+  unsigned nthreads = 1;
+  bool ortho = false;
+  bool sine = false;
+  static DCTDesc init(const std::vector<std::size_t> &axes, int dctType = 2, bool ortho = false, T scalingFactor = 1,
+                      unsigned nthreads = 1, bool sine = false) {
+    if (dctType < 1 || dctType > 4) throw std::invalid_argument("dctType must be in 1..4");
+    DCTDesc d;
+    d.axes = axes; d.dctType = dctType; d.ortho = ortho; d.scalingFactor = scalingFactor; d.nthreads = nthreads; d.sine = sine;
+    return d;
+  }
+  void apply(DataDesc<T> &descOut, const DataDesc<T> &descIn, void *stream = nullptr) const {
+    constexpr int dtype = std::is_same<T, float>::value ? IMPULSE_FFT_F32 : IMPULSE_FFT_F64;
+    auto fn = sine ? impulse_fft_dst : impulse_fft_dct;
+    const int rc = fn(dtype, descIn.shape.size(), descIn.shape.data(), descIn.stride.data(), descOut.stride.data(), axes.size(),
+                      axes.data(), dctType, descIn.buf, descOut.buf, double(scalingFactor), ortho, nthreads, stream);
+    if (rc != 0) throw std::runtime_error(std::string("impulse_fft_b200: ") + impulse_fft_last_error());
+  }
+};
+
 }  // namespace impulse

@@ -95,6 +95,17 @@ int impulse_fft_c2r(int dtype, size_t ndim, const size_t *shape_out, const ptrdi
                     const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
                     const void *data_in, void *data_out, double fct, size_t nthreads, void *stream);
 
+/* Discrete cosine / sine transforms of type 1..4 over `axes`, real to real, with the argument list of
+ * pocketfft::dct / pocketfft::dst (pocketfft_hdronly.h:3284-3318; FFTW's REDFT/RODFT definitions;
+ * `ortho` as documented at README_pocketfft.md:220-241).  Called by DCTDesc.apply
+ * (impulse/fft/cpp_pocketfft/pocketfft.nim:279-295).  in == out allowed with equal strides. */
+int impulse_fft_dct(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int type, const void *data_in,
+                    void *data_out, double fct, int ortho, size_t nthreads, void *stream);
+int impulse_fft_dst(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int type, const void *data_in,
+                    void *data_out, double fct, int ortho, size_t nthreads, void *stream);
+
 /* Batched forms of the C backend's in-place row transforms: `nrows` contiguous rows of
  * `length` complex (cfft) or real (rfft, FFTPACK halfcomplex) doubles, device or host memory.
  * This is what a caller looping fft() over rows should call instead. */

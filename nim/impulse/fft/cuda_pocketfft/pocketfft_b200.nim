@@ -51,6 +51,13 @@ proc impulse_fft_c2r(dtype: cint; ndim: csize_t; shape: ptr csize_t; strideIn, s
                      naxes: csize_t; axes: ptr csize_t; forward: cint; dataIn, dataOut: pointer;
                      fct: cdouble; nthreads: csize_t; stream: pointer): cint {.importc, dynlib: libName, cdecl.}
 
+proc impulse_fft_dct(dtype: cint; ndim: csize_t; shape: ptr csize_t; strideIn, strideOut: ptr int;
+                     naxes: csize_t; axes: ptr csize_t; dctType: cint; dataIn, dataOut: pointer;
+                     fct: cdouble; ortho: cint; nthreads: csize_t; stream: pointer): cint {.importc, dynlib: libName, cdecl.}
+proc impulse_fft_dst(dtype: cint; ndim: csize_t; shape: ptr csize_t; strideIn, strideOut: ptr int;
+                     naxes: csize_t; axes: ptr csize_t; dstType: cint; dataIn, dataOut: pointer;
+                     fct: cdouble; ortho: cint; nthreads: csize_t; stream: pointer): cint {.importc, dynlib: libName, cdecl.}
+
 type
   DataDesc*[T] = object
     ## Descriptor of the data used in or out of the FFT (cpp_pocketfft/pocketfft.nim:137-142)
@@ -122,3 +129,29 @@ proc apply*[In, Out](fft: FFTDesc, descOut: var DataDesc[Out], descIn: DataDesc[
                           descIn.buf, descOut.buf, cdouble(fft.scalingFactor), csize_t(fft.nthreads), nil)
   else:
     {.error: "Not implemented".}
+
+type
+  DCTDesc*[T] = object
+    ## cpp_pocketfft/pocketfft.nim:151-156
+    axes*: seq[csize_t]
+    dctType*: range[1'i32..4'i32]
+    scalingFactor*: T
+    nthreads*: uint
+    ortho*: bool
+
+func init*[T](_: type DCTDesc[T], axes: varargs[int], dctType: range[1'i32..4'i32] = 2'i32, ortho = false,
+              scalingFactor: T = 1, nthreads = 1): DCTDesc[T] =
+  ## cpp_pocketfft/pocketfft.nim:217-233
+  for a in axes: result.axes.add csize_t(a)
+  result.dctType = dctType
+  result.ortho = ortho
+  result.scalingFactor = scalingFactor
+  result.nthreads = uint nthreads
+
+proc apply*[T](dct: DCTDesc[T], descOut: var DataDesc[T], descIn: DataDesc[T]) =
+  ## cpp_pocketfft/pocketfft.nim:279-295
+  var axes = dct.axes
+  var shape = descIn.shape
+  check impulse_fft_dct(dtypeCode(T), csize_t shape.len, shape[0].addr, descIn.stride[0].unsafeAddr,
+                        descOut.stride[0].addr, csize_t axes.len, axes[0].addr, cint(dct.dctType),
+                        descIn.buf, descOut.buf, cdouble(dct.scalingFactor), cint(dct.ortho), csize_t(dct.nthreads), nil)

@@ -72,6 +72,10 @@ class Ref:
             f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_double, C.c_int, C.c_int]
         L.ref_last_error.restype = C.c_char_p
         L.ref_hardware_threads.restype = C.c_uint
+        if hasattr(L, "ref_r2r"):
+            L.ref_r2r.restype = C.c_int
+            L.ref_r2r.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, _size_p, _ssize_p, _ssize_p, C.c_size_t,
+                                  _size_p, C.c_void_p, C.c_void_p, C.c_double, C.c_size_t]
         # the ten C symbols (c_pocketfft/pocketfft.h:18-32)
         L.make_cfft_plan.restype = C.c_void_p
         L.make_cfft_plan.argtypes = [C.c_size_t]
@@ -136,6 +140,18 @@ class Ref:
         if out is None:
             out = np.empty(real_shape, dtype=np.float32 if a.dtype == np.complex64 else np.float64)
         return self._nd(self.lib.ref_c2r, a, out, real_shape, axes, forward, fct, nthreads)
+
+    def r2r(self, cosine, type_, a, axes, fct=1.0, ortho=False, out=None, nthreads=1):
+        """pocketfft::dct (cosine=True) / dst of type 1..4."""
+        out = np.empty_like(a) if out is None else out
+        nd = a.ndim
+        rc = self.lib.ref_r2r(int(cosine), type_, int(ortho), 1 if a.dtype == np.float64 else 0, nd,
+                              _arr(list(a.shape), C.c_size_t), _arr(list(a.strides), C.c_ssize_t),
+                              _arr(list(out.strides), C.c_ssize_t), len(axes), _arr(list(axes), C.c_size_t),
+                              a.ctypes.data, out.ctypes.data, float(fct), nthreads)
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return out
 
 
 class Port:
@@ -274,6 +290,51 @@ class Port:
             out[...] = res
             return out
         return np.ascontiguousarray(res)
+
+
+def r2r_direct(cosine, type_, x, fct=1.0, ortho=False):
+    """O(N^2) restatement of the DCT/DST definitions pocketfft implements (FFTW's REDFT/RODFT kinds,
+    README_pocketfft.md:220-241 for `ortho`), along the last axis.  Checker of last resort for small N and
+    the thing the compiled reference's conventions are pinned against in tests/test_oracle.py."""
+    x = np.array(x, dtype=np.float64, copy=True)
+    n = x.shape[-1]
+    j = np.arange(n)[:, None]
+    k = np.arange(n)[None, :]
+    r2 = np.sqrt(2.0)
+    if ortho and type_ == 1 and cosine:
+        x[..., 0] *= r2
+        x[..., -1] *= r2
+    if ortho and type_ == 3:
+        x[..., 0] *= r2
+    if cosine:
+        if type_ == 1:
+            m = 2 * np.cos(np.pi * j * k / (n - 1))
+            m[0, :] = 1.0
+            m[n - 1, :] = (-1.0) ** np.arange(n)
+        elif type_ == 2:
+            m = 2 * np.cos(np.pi * (j + 0.5) * k / n)
+        elif type_ == 3:
+            m = 2 * np.cos(np.pi * j * (k + 0.5) / n)
+            m[0, :] = 1.0
+        else:
+            m = 2 * np.cos(np.pi * (j + 0.5) * (k + 0.5) / n)
+    else:
+        if type_ == 1:
+            m = 2 * np.sin(np.pi * (j + 1) * (k + 1) / (n + 1))
+        elif type_ == 2:
+            m = 2 * np.sin(np.pi * (j + 0.5) * (k + 1) / n)
+        elif type_ == 3:
+            m = 2 * np.sin(np.pi * (j + 1) * (k + 0.5) / n)
+            m[n - 1, :] = (-1.0) ** np.arange(n)
+        else:
+            m = 2 * np.sin(np.pi * (j + 0.5) * (k + 0.5) / n)
+    y = (x @ m) * fct
+    if ortho and type_ == 1 and cosine:
+        y[..., 0] /= r2
+        y[..., -1] /= r2
+    if ortho and type_ == 2:
+        y[..., 0] /= r2
+    return y
 
 
 def load(prefer_ref: bool = True):

@@ -106,6 +106,24 @@ int ref_c2r(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride
   });
 }
 
+// DCT (cosine != 0) / DST types 1..4 (pocketfft_hdronly.h:3284-3318)
+int ref_r2r(int cosine, int type, int ortho, int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+            const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, const void *in, void *out, double fct,
+            size_t nthreads) {
+  return guarded([&] {
+    auto sh = mk_shape(shape, ndim);
+    auto si = mk_stride(stride_in, ndim), so = mk_stride(stride_out, ndim);
+    auto ax = mk_shape(axes, naxes);
+    if (dtype == 1) {
+      if (cosine) pocketfft::dct<double>(sh, si, so, ax, type, (const double *)in, (double *)out, fct, ortho != 0, nthreads);
+      else pocketfft::dst<double>(sh, si, so, ax, type, (const double *)in, (double *)out, fct, ortho != 0, nthreads);
+    } else {
+      if (cosine) pocketfft::dct<float>(sh, si, so, ax, type, (const float *)in, (float *)out, (float)fct, ortho != 0, nthreads);
+      else pocketfft::dst<float>(sh, si, so, ax, type, (const float *)in, (float *)out, (float)fct, ortho != 0, nthreads);
+    }
+  });
+}
+
 // Row drivers over the reference C engine: `nrows` contiguous rows transformed in
 // place, one plan shared by `nthreads` threads.  plan_per_row != 0 reproduces what
 // the Nim wrapper does (a fresh plan per call, c_pocketfft/pocketfft.nim:285,300).

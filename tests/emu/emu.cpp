@@ -47,11 +47,29 @@ extern "C" {
 const char *emu_last_error() { return g_err.c_str(); }
 
 // mirrors impulse_fft_nd() of the product ABI, on host memory
+static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                       const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
+                       void *out, double fct, int r2r_type, int ortho);
+
 int emu_nd(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
            const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
            void *out, double fct) {
+  return emu_nd_impl(kind, dtype, layout, ndim, shape, stride_in, stride_out, naxes, axes, forward, in, out, fct, 2, 0);
+}
+
+// DCT (cosine != 0) / DST of type 1..4, mirrors impulse_fft_dct / impulse_fft_dst
+int emu_r2r(int cosine, int type, int ortho, int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+            const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, const void *in, void *out, double fct) {
+  return emu_nd_impl(cosine ? KIND_DCT : KIND_DST, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, 1,
+                     in, out, fct, type, ortho);
+}
+
+static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                       const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
+                       void *out, double fct, int r2r_type, int ortho) {
   if (!g_cache) g_cache = new PlanCache(&g_alloc);
   NdDesc d;
+  d.r2r_type = r2r_type; d.ortho = ortho != 0;
   d.kind = kind; d.dtype = dtype; d.layout = layout; d.forward = forward != 0;
   d.shape.assign(shape, shape + ndim);
   d.stride_in.assign(stride_in, stride_in + ndim);

@@ -64,6 +64,23 @@ def nd(kind, a_in, a_out, shape, axes, forward=True, fct=1.0, layout="hermitian"
     return a_out
 
 
+def r2r(cosine, type_, a_in, a_out, axes, fct=1.0, ortho=False):
+    L = lib()
+    if not hasattr(L, "_r2r_bound"):
+        L.emu_r2r.restype = C.c_int
+        L.emu_r2r.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_ssize_t),
+                              C.POINTER(C.c_ssize_t), C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_double]
+        L._r2r_bound = True
+    dt = 1 if a_in.dtype == np.float64 else 0
+    n = a_in.ndim
+    rc = L.emu_r2r(int(cosine), type_, int(ortho), dt, n, (C.c_size_t * n)(*a_in.shape), (C.c_ssize_t * n)(*a_in.strides),
+                   (C.c_ssize_t * n)(*a_out.strides), len(axes), (C.c_size_t * len(axes))(*axes), a_in.ctypes.data,
+                   a_out.ctypes.data, fct)
+    if rc:
+        raise EmuError(rc, L.emu_last_error().decode())
+    return a_out
+
+
 def nd_steps(kind, a_in, a_out, shape, axes, forward=True, layout="hermitian"):
     L = lib()
     dt = 1 if a_in.dtype in (np.float64, np.complex128) else 0

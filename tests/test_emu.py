@@ -249,3 +249,43 @@ def test_multi_launch_bluestein(checker, monkeypatch):
     a = rnd(rng, (6, 37, 5), np.complex64)[:, :, ::-1]
     got = emu.nd("c2c", a, np.empty(a.shape, np.complex64), a.shape, [1], True, 1.0)
     assert oracle.rel_l2(got, checker.c2c(a, [1], True, 1.0)) <= tol(37, np.float32)
+
+
+def test_dct_dst_all_types(checker):
+    """DCTDesc path: DCT/DST I-IV, ortho, fp64/fp32, N-D and strided, through the
+    emulated engine against the compiled reference (or the O(N^2) definitions when it is absent)."""
+    rng = np.random.default_rng(18)
+
+    def want(cosine, t, x, axes, fct, ortho):
+        if hasattr(checker, "r2r"):
+            return checker.r2r(cosine, t, x, axes, fct, ortho)
+        y = x.astype(np.float64)
+        for i, ax in enumerate(axes):
+            y = np.moveaxis(oracle.r2r_direct(cosine, t, np.moveaxis(y, ax, -1), fct if i == 0 else 1.0, ortho), -1, ax)
+        return y
+
+    for dt, rt in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        for n in (2, 3, 5, 8, 16, 37, 100, 128, 1000):
+            x = rnd(rng, (3, n), dt)
+            for cosine in (True, False):
+                for t in (1, 2, 3, 4):
+                    for ortho in (False, True):
+                        got = emu.r2r(cosine, t, x, np.empty_like(x), [1], 0.5, ortho)
+                        assert oracle.max_row_rel_l2(got, want(cosine, t, x, [1], 0.5, ortho)) <= rt * max(1, np.log2(n)), \
+                            (n, cosine, t, ortho, dt)
+    a = rnd(rng, (6, 10, 7), np.float64)
+    for axes in ([0, 1, 2], [2, 0], [1]):
+        got = emu.r2r(True, 2, a, np.empty_like(a), axes, 1.0, True)
+        assert oracle.rel_l2(got, want(True, 2, a, axes, 1.0, True)) <= 1e-12 * 4
+    v = rnd(rng, (8, 24), np.float64)[:, ::2]
+    got = emu.r2r(False, 3, v, np.empty(v.shape), [0, 1], 1.0, False)
+    assert oracle.rel_l2(got, want(False, 3, np.ascontiguousarray(v), [0, 1], 1.0, False)) <= 1e-12 * 4
+    b = a.copy()
+    emu.r2r(True, 4, b, b, [1], 1.0, False)  # in place
+    assert oracle.rel_l2(b, want(True, 4, a, [1], 1.0, False)) <= 1e-12 * 4
+    # DCT-II then DCT-III with 1/(2N) is the identity (orthogonality of the pair)
+    x = rnd(rng, (4, 60), np.float64)
+    y = emu.r2r(True, 3, emu.r2r(True, 2, x, np.empty_like(x), [1]), np.empty_like(x), [1], 1.0 / 120)
+    assert oracle.max_row_rel_l2(y, x) <= 1e-14
+    with pytest.raises(emu.EmuError):
+        emu.r2r(True, 1, np.zeros((2, 1)), np.zeros((2, 1)), [1])   # DCT-I of one point (pocketfft throws too)

@@ -197,3 +197,20 @@ def test_length_one_scaling_quirk(port, ref):
         assert e.cfft_rows(c.copy(), True, 0.37)[0, 0] == 2.0 + 1.0j
         assert e.rfft_rows(np.array([[3.0]]), True, 0.37)[0, 0] == 3.0
         assert np.allclose(e.c2c(c, [1], True, 0.5), c * 0.5)
+
+
+def test_dct_dst_conventions(ref):
+    """pocketfft::dct / dst (pocketfft_hdronly.h:3284-3318) against the O(N^2) definitions
+    (FFTW REDFT/RODFT kinds) incl. the `ortho` rules of README_pocketfft.md:220-241, and the one
+    value the reference prints: DCT-II of [4,3,5,10] (cpp_pocketfft/pocketfft.nim:322-339)."""
+    rng = np.random.default_rng(17)
+    for n in (2, 3, 4, 5, 8, 9, 16, 31, 64):
+        x = rng.uniform(-0.5, 0.5, (2, n))
+        for cosine in (True, False):
+            for t in (1, 2, 3, 4):
+                for ortho in (False, True):
+                    a = ref.r2r(cosine, t, x, [1], 0.7, ortho)
+                    assert oracle.rel_l2(oracle.r2r_direct(cosine, t, x, 0.7, ortho), a) <= 1e-13, (n, cosine, t, ortho)
+    d = ref.r2r(True, 2, np.array([[4.0, 3.0, 5.0, 10.0]]), [1], 1.0, False)[0]
+    np.testing.assert_allclose(d, oracle.r2r_direct(True, 2, np.array([4.0, 3.0, 5.0, 10.0])), rtol=1e-14)
+    assert abs(d[0] - 44.0) < 1e-13   # 2 * sum(x)
