@@ -1,0 +1,68 @@
+"""Small cases of every kernel family for compute-sanitizer (memcheck / racecheck) runs:
+    compute-sanitizer --tool memcheck python tests/sanitizer_cases.py
+Not collected by pytest (no test_ prefix); exits non-zero on a parity failure."""
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, __file__.rsplit("/tests/", 1)[0])
+import impulse_b200 as ib  # noqa: E402
+from impulse_b200.filter import FFTFilter2D  # noqa: E402
+
+
+def run(kind, x, out, axes, fwd=True, fct=1.0):
+    ib.FFTDesc.init(axes=axes, forward=fwd, scalingFactor=fct).apply(ib.DataDesc.init(out), ib.DataDesc.init(x))
+    return out
+
+
+def main():
+    rng = np.random.default_rng(0)
+    ok = True
+
+    def c(shape, dt=np.complex128):
+        return torch.from_numpy((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dt)).cuda()
+
+    def r(shape, dt=np.float64):
+        return torch.from_numpy(rng.standard_normal(shape).astype(dt)).cuda()
+
+    # generic engine (mixed radix, Bluestein, r2c/c2r odd+even, packed), fast2/fast2p, fast3, colfast2, fastblue, four-step, DCT
+    for n in (1, 6, 30, 97, 1000, 256, 512, 1024, 2048, 4096, 8192, 4099, 500, 1944):
+        for rows in (1, 5):
+            x = c((rows, n))
+            y = run("c2c", x, torch.empty_like(x), [1])
+            back = run("c2c", y, torch.empty_like(x), [1], False, 1.0 / n)
+            ok &= bool(torch.allclose(back, x, atol=1e-9))
+            ref = torch.fft.fft(x, dim=1)   # second opinion only; parity proper is in tests/
+            ok &= bool(torch.allclose(y, ref, rtol=1e-9, atol=1e-9 * n))
+    for n in (5, 8, 1000, 3888, 4096, 4099, 16384):
+        x = r((3, n))
+        s = run("r2c", x, torch.empty((3, n // 2 + 1), dtype=torch.complex128, device="cuda"), [1])
+        ok &= bool(torch.allclose(s, torch.fft.rfft(x, dim=1), rtol=1e-9, atol=1e-9 * n))
+        b = run("c2r", s, torch.empty_like(x), [1], False, 1.0 / n)
+        ok &= bool(torch.allclose(b, x, atol=1e-9))
+        p = ib.rfft_packed(x)
+        ok &= bool(torch.allclose(ib.rfft_packed(p, forward=False), x, atol=1e-9))
+    for shape, axes in (((64, 24), [0]), ((4096, 16), [0]), ((300, 520), [0, 1]), ((3, 40, 36), [1, 2])):
+        x = c(shape)
+        y = run("c2c", x, torch.empty_like(x), axes)
+        ok &= bool(torch.allclose(y, torch.fft.fftn(x, dim=axes), rtol=1e-9, atol=1e-8 * max(shape)))
+    x = c((2, 32768))
+    ok &= bool(torch.allclose(run("c2c", x, torch.empty_like(x), [1]), torch.fft.fft(x, dim=1), rtol=1e-9, atol=1e-6))
+    x32 = c((7, 1024), np.complex64)
+    ok &= bool(torch.allclose(run("c2c", x32, torch.empty_like(x32), [1]), torch.fft.fft(x32, dim=1), rtol=1e-4, atol=1e-2))
+    img = torch.rand((2, 64, 96), device="cuda", dtype=torch.float32)
+    ker = torch.rand((5, 5), device="cuda", dtype=torch.float32)
+    FFTFilter2D(ker / ker.sum(), 64, 96).apply(img)
+    d = r((4, 100))
+    o = torch.empty_like(d)
+    ib.DCTDesc.init(axes=[1], dctType=2).apply(ib.DataDesc.init(o), ib.DataDesc.init(d))
+    h = np.random.default_rng(1).standard_normal((600, 1024)) + 0j     # host staging path
+    ok &= bool(np.allclose(ib.fft(h), np.fft.fft(h, axis=1), rtol=1e-9, atol=1e-8))
+    torch.cuda.synchronize()
+    print("sanitizer cases:", "ok" if ok else "PARITY FAILURE", "last kernel", ib.last_kernel())
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
