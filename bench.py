@@ -235,6 +235,9 @@ def main():
         lo, hi = idist.shard_rows(rows, rank, world)
         x = torch.view_as_complex(torch.rand((hi - lo, n, 2), generator=g, device=dev, dtype=rdt) - 0.5)
         y = None
+        # default: exchange fused into the column kernels over peer memory; IMPULSE_FFT_SLAB=nccl selects
+        # the pack + NCCL all-to-all variant
+        slab_op = None if os.environ.get("IMPULSE_FFT_SLAB", "p2p") == "nccl" else idist.SlabFFT2P2P(hi - lo, n, cdt)
     elif kind in ("c2c", "fft2"):
         x = torch.view_as_complex(torch.rand((rows, n, 2), generator=g, device=dev, dtype=rdt) - 0.5)
         y = torch.empty_like(x)
@@ -252,7 +255,10 @@ def main():
         if filt is not None:
             filt.apply(x, out=y)
         elif slab:
-            idist.fft2_slab(x, True, 1.0)
+            if slab_op is not None:
+                slab_op(x, True, 1.0)
+            else:
+                idist.fft2_slab(x, True, 1.0)
         else:
             fdesc.apply(dout, din)
 
@@ -326,7 +332,8 @@ def main():
             "config": {"workload": args.workload, "rows_per_gpu": (rows // world) if slab else rows, "length": n, "kind": kind,
                        "placement": "out of place, device resident", "l2": "input+output per step exceed the 126 MB L2"
                        if bytes_per_gpu > 2 * 126e6 else "working set fits L2: reported as is, see DESIGN.md",
-                       "parallelism": (f"row-slab x{world}, one NCCL all-to-all per transform, result left in column slabs" if slab
+                       "parallelism": (f"row-slab x{world}, " + ("column kernels load peers' row slabs over NVLink (CUDA IPC), one 1-element all-reduce as barrier"
+                                                                if slab_op is not None else "pack + NCCL all-to-all") + ", result left in column slabs" if slab
                                        else f"batch-shard x{world}, no collective"),
                        "elements_per_s": round((1 if slab else world) * rows * n / (ms_per_step * 1e-3), 1),
                        "frac_of_8TBps_nominal": round(value / world / 8000.0, 4)},

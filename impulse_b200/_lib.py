@@ -48,7 +48,8 @@ EXPORTS = [
     "impulse_fft_r2c", "impulse_fft_c2r", "impulse_fft_dct", "impulse_fft_dst", "impulse_fft_cfft_rows", "impulse_fft_rfft_rows",
     "impulse_fft_plan_get_info", "impulse_fft_launch_count", "impulse_fft_last_error", "impulse_fft_version",
     "impulse_fft_last_kernel",
-    "impulse_fft_cmul", "impulse_fft_transpose", "impulse_fft_copy2d",
+    "impulse_fft_cmul", "impulse_fft_transpose", "impulse_fft_copy2d", "impulse_fft_cols_from_parts", "impulse_fft_enable_peer_access", "impulse_fft_ipc_alloc", "impulse_fft_ipc_free",
+    "impulse_fft_ipc_open", "impulse_fft_ipc_close",
     # include/pocketfft.h
     "make_cfft_plan", "destroy_cfft_plan", "cfft_backward", "cfft_forward", "cfft_length",
     "make_rfft_plan", "destroy_rfft_plan", "rfft_backward", "rfft_forward", "rfft_length",
@@ -96,6 +97,18 @@ def lib() -> C.CDLL:
     L.impulse_fft_transpose.argtypes = [C.c_int, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     L.impulse_fft_copy2d.restype = C.c_int
     L.impulse_fft_copy2d.argtypes = [C.c_int, vp, vp] + [C.c_size_t] * 7 + [vp]
+    L.impulse_fft_ipc_alloc.restype = C.c_int
+    L.impulse_fft_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
+    L.impulse_fft_ipc_open.restype = C.c_int
+    L.impulse_fft_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    for n in ("impulse_fft_ipc_free", "impulse_fft_ipc_close"):
+        getattr(L, n).restype = C.c_int
+        getattr(L, n).argtypes = [vp]
+    L.impulse_fft_enable_peer_access.restype = C.c_int
+    L.impulse_fft_enable_peer_access.argtypes = [C.c_int]
+    L.impulse_fft_cols_from_parts.restype = C.c_int
+    L.impulse_fft_cols_from_parts.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp,
+                                              C.c_size_t, C.c_int, C.c_double, vp]
     L.make_cfft_plan.restype = vp
     L.make_cfft_plan.argtypes = [C.c_size_t]
     L.make_rfft_plan.restype = vp

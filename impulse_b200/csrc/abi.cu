@@ -402,6 +402,11 @@ int impulse_fft_execute(impulse_fft_plan plan, const void *in, void *out, double
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
   if (dev != plan->ctx->dev) return fail(IMPULSE_FFT_ERR_INVALID, "plan was created on another device");
+  {  // in-place is defined for c2c / r2r with equal strides and for the packed real layout only
+    const NdDesc &d = plan->nd.desc;     // (README_pocketfft.md:133-135)
+    if (in == out && (d.kind == KIND_R2C || d.kind == KIND_C2R) && d.layout != RL_HALFCOMPLEX)
+      return fail(IMPULSE_FFT_ERR_INVALID, "in-place r2c/c2r is only defined for the FFTPACK halfcomplex layout");
+  }
   const bool din = is_device_ptr(in), dout = is_device_ptr(out);
   if (din != dout) return fail(IMPULSE_FFT_ERR_INVALID, "input and output must both be device or both be host memory");
   if (din) return run_device(plan, in, out, fct, static_cast<cudaStream_t>(stream));
@@ -515,6 +520,82 @@ int impulse_fft_copy2d(int dtype, const void *in, void *out, size_t rows, size_t
   int e = launch_copy2d(dtype, in, out, rows, cols, ld_in, ld_out, batch, bs_in, bs_out, ctx->sm_count, stream);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return e ? cuda_fail((cudaError_t)e, "kernel launch") : 0;
+}
+
+int impulse_fft_ipc_alloc(size_t bytes, void **ptr, void *handle64) {
+  if (!ptr || !handle64 || !bytes) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  std::memcpy(handle64, &h, 64);
+  return 0;
+}
+int impulse_fft_ipc_free(void *ptr) {
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cudaFree");
+}
+int impulse_fft_ipc_open(const void *handle64, void **ptr) {
+  if (!ptr || !handle64) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cudaIpcOpenMemHandle");
+}
+int impulse_fft_ipc_close(void *ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cudaIpcCloseMemHandle");
+}
+
+int impulse_fft_enable_peer_access(int peer_device) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (peer_device == dev) return 0;
+  int can = 0;
+  e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceCanAccessPeer");
+  if (!can) return fail(IMPULSE_FFT_ERR_UNSUPPORTED, "no peer access between these devices");
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cudaDeviceEnablePeerAccess");
+}
+
+int impulse_fft_cols_from_parts(int dtype, size_t nparts, const void *const *parts, size_t rows_per_part, size_t ld_part,
+                                size_t col0, size_t ncols, void *out, size_t ld_out, int forward, double fct, void *stream) {
+  if (!parts || !out || nparts < 1 || nparts > 8 || !rows_per_part || !ncols)
+    return fail(IMPULSE_FFT_ERR_INVALID, "bad argument (1 <= nparts <= 8)");
+  if (ld_part < col0 + ncols || ld_out < ncols) return fail(IMPULSE_FFT_ERR_STRIDE, "leading dimension too small");
+  const size_t csz = dtype == DT_F64 ? 16 : 8;
+  const size_t R = nparts * rows_per_part;
+  // plan the column transform of a virtual [R, ncols] array whose rows are ld_part apart, then point the
+  // launches that read the input at the parts
+  NdDesc d;
+  d.kind = KIND_C2C; d.dtype = dtype; d.layout = RL_HERMITIAN; d.forward = forward != 0;
+  d.shape = {R, ncols};
+  d.stride_in = {(ptrdiff_t)(ld_part * csz), (ptrdiff_t)csz};
+  d.stride_out = {(ptrdiff_t)(ld_out * csz), (ptrdiff_t)csz};
+  d.axes = {0};
+  impulse_fft_plan raw = nullptr;
+  int rc = create_plan(&raw, d);
+  if (rc) return rc;
+  std::unique_ptr<impulse_fft_plan_s> plan(raw);
+  for (Step &st : plan->nd.steps) {
+    if (st.src != BUF_IN) continue;
+    LineJob &J = st.job;
+    if (J.load_mode != LD_C || J.es_in <= 0 || (rows_per_part * ld_part) % (size_t)J.es_in)
+      return fail(IMPULSE_FFT_ERR_UNSUPPORTED, "rows per part must be a multiple of the column split");
+    J.seg_len = (uint32_t)((rows_per_part * ld_part) / (size_t)J.es_in);
+    if (J.fast_id != FAST_NONE && !(J.fast_id >= COL2_64_F64 && J.fast_id <= COL2_512_F32)) J.fast_id = FAST_NONE;
+    for (size_t q = 0; q < nparts; ++q) {
+      if (!parts[q] || ((uintptr_t)parts[q] % csz)) return fail(IMPULSE_FFT_ERR_STRIDE, "part pointer null or misaligned");
+      J.seg_base[q] = (const unsigned char *)parts[q] + col0 * csz;
+    }
+  }
+  // the first part stands in for `in` (only its alignment is looked at; every load goes through seg_base)
+  return run_device(plan.get(), (const unsigned char *)parts[0] + col0 * csz, out, fct, static_cast<cudaStream_t>(stream));
 }
 
 // ---- the ten pocketfft symbols (include/pocketfft.h) -------------------------

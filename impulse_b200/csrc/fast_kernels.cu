@@ -655,7 +655,7 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);   // W_N^m
   // CTAs are short-lived and cannot double-buffer: instead each one pulls the input of the group that
   // will be scheduled a few waves later into L2 (one lane per 128-byte run issues the prefetch)
-  if (line == 0) {
+  if (line == 0 && !J.seg_len) {
     const uint64_t pg = (uint64_t)blockIdx.x + kColPrefetchDistance;
     if (pg < (uint64_t)gridDim.x) {
       const uint64_t p0 = (pg % g0n) * LPC, pr = pg / g0n, p1 = pr % J.bdim[1], p2 = pr / J.bdim[1];
@@ -668,7 +668,13 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   cx<T> x[R1];
 #pragma unroll
   for (int j = 0; j < R1; ++j) {
-    x[j] = valid ? in[(int64_t)(i + R2 * j) * J.es_in] : mk<T>((T)0, (T)0);
+    const uint32_t n = (uint32_t)(i + R2 * j);
+    if (J.seg_len) {  // the line is spread over several allocations (peer slabs): segment n / seg_len
+      const uint32_t sg = n / J.seg_len, w = n - sg * J.seg_len;
+      x[j] = valid ? (reinterpret_cast<const cx<T> *>(J.seg_base[sg]) + off_in)[(int64_t)w * J.es_in] : mk<T>((T)0, (T)0);
+    } else {
+      x[j] = valid ? in[(int64_t)n * J.es_in] : mk<T>((T)0, (T)0);
+    }
     if (BWD) x[j].y = -x[j].y;
   }
   RegFFT<T, R1>::run(x);

@@ -173,7 +173,13 @@ IMP_HD void load_one(const LineJob &J, cx<T> *S /*line base*/, int64_t off, uint
   const int64_t es = J.es_in;
   switch (J.load_mode) {
     case LD_C: {
-      cx<T> v = inc[off + (int64_t)e * es];
+      cx<T> v;
+      if (J.seg_len) {
+        const uint32_t sg = e / J.seg_len, w = e - sg * J.seg_len;
+        v = ((const cx<T> *)J.seg_base[sg])[off + (int64_t)w * es];
+      } else {
+        v = inc[off + (int64_t)e * es];
+      }
       S[phys<T>(J, e)] = cconj_if(v, cin != cseq);
     } break;
     case LD_R_PAIRS: {

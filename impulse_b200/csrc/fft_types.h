@@ -160,6 +160,10 @@ struct LineJob {
   double x_f0, x_f, x_fl, x_s, x_s0, x_sn;
   uint32_t x_shift, x_wadd;   // F index offset; twiddle index 2k + x_wadd (x_wadd = 0xffffffff: no twiddle)
   uint32_t x_im;              // 0: real part, 1: minus imaginary part
+  // segmented input (LD_C): element e of a line is read from seg_base[e / seg_len] at (e % seg_len)*es_in —
+  // the line is distributed over several allocations (peer GPUs' row slabs in the multi-GPU 2-D transform)
+  uint32_t seg_len;            // 0 = off
+  const void *seg_base[8];
   const void *mul_tab;     // ST_C: multiply output element e by mul_tab[line_index + mul_stride*e] (null = off)
   uint32_t mul_stride;
   double fct;

@@ -103,3 +103,97 @@ def fft2_slab(x_local, forward: bool = True, fct: float = 1.0, group=None, engin
     back = engine.empty((world, rl, cb), x_local)
     dist.all_to_all_single(back.view(-1), cols.view(-1), group=group)
     return engine.unpack_blocks(back, engine.empty((rl, c), x_local), world)
+
+
+class SlabFFT2P2P:
+    """Slab-decomposed 2-D complex transform with the exchange FUSED into the column pass: every rank
+    publishes its row-FFT output through CUDA IPC, and the column kernels of each rank load their column
+    block straight out of the peers' memory over NVLink/NVSwitch (``impulse_fft_cols_from_parts``).  No
+    pack, no all-to-all staging buffer; the only collective left is a one-element all-reduce used as a
+    stream-ordered barrier ("all row slabs are complete").
+
+    Two row buffers alternate between calls, so one barrier per transform suffices: a rank overwrites the
+    buffer its peers read two calls ago, and every peer has passed the barrier of the previous call since.
+
+    The shared buffers are allocated and mapped by the library itself (``impulse_fft_ipc_*``): the peers'
+    memory has to be mapped into THIS device's address space for kernels to load from it, which the IPC
+    tensors of torch.multiprocessing (opened on the owner's device) do not give.  ``torch.distributed``
+    carries the 64-byte handles and the barrier.
+    """
+
+    def __init__(self, rows_local: int, cols: int, dtype, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if cols % self.world:
+            raise ValueError(f"columns ({cols}) must be divisible by the number of ranks ({self.world})")
+        if self.world > 8:
+            raise ValueError("at most 8 ranks (one NVSwitch box)")
+        self.rl, self.c, self.cb = int(rows_local), int(cols), int(cols) // self.world
+        self.dtype = dtype
+        self.esz = 16 if dtype == torch.complex128 else 8
+        self.code = _lib.F64 if dtype == torch.complex128 else _lib.F32
+        L = self.L = _lib.lib()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf_bytes = self.rl * self.c * self.esz
+        self.base = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _lib.check(L.impulse_fft_ipc_alloc(2 * self.buf_bytes, C.byref(self.base), handle))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(handle), group=group)
+        self.peer_base = []   # rank q's two buffers as mapped into this device's address space
+        self._opened = []
+        for q in range(self.world):
+            if q == self.rank:
+                self.peer_base.append(self.base.value)
+            else:
+                p = C.c_void_p()
+                hb = (C.c_ubyte * 64).from_buffer_copy(gathered[q])
+                _lib.check(L.impulse_fft_ipc_open(hb, C.byref(p)))
+                self._opened.append(p)
+                self.peer_base.append(p.value)
+        self.flag = torch.zeros(1, device=dev)
+        self.step = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+        if self.base is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)      # nobody is still reading
+        for p in self._opened:
+            self.L.impulse_fft_ipc_close(p)
+        self._opened = []
+        dist.barrier(group=self.group)      # every mapping is gone before the owner frees
+        self.L.impulse_fft_ipc_free(self.base)
+        self.base = None
+
+    def __call__(self, x_local, forward: bool = True, fct: float = 1.0, out=None):
+        import torch
+        import torch.distributed as dist
+        L = self.L
+        k = self.step & 1
+        self.step += 1
+        stream = C.c_void_p(torch.cuda.current_stream(x_local.device).cuda_stream)
+        # 1. row FFTs of the local slab straight into the published buffer
+        shape = (C.c_size_t * 2)(self.rl, self.c)
+        sin = (C.c_ssize_t * 2)(x_local.stride(0) * self.esz, x_local.stride(1) * self.esz)
+        sout = (C.c_ssize_t * 2)(self.c * self.esz, self.esz)
+        axes = (C.c_size_t * 1)(1)
+        rows_ptr = self.base.value + k * self.buf_bytes
+        _lib.check(L.impulse_fft_c2c(self.code, 2, shape, sin, sout, 1, axes, int(forward), x_local.data_ptr(), rows_ptr,
+                                     float(fct), 0, stream))
+        # 2. stream-ordered barrier: completes once every rank's rows are written
+        dist.all_reduce(self.flag, group=self.group)
+        # 3. column transforms, loading the column block from all row slabs (local + peers over NVLink)
+        if out is None:
+            out = torch.empty((self.world * self.rl, self.cb), dtype=self.dtype, device=x_local.device)
+        parts = (C.c_void_p * self.world)(*[self.peer_base[q] + k * self.buf_bytes for q in range(self.world)])
+        _lib.check(L.impulse_fft_cols_from_parts(self.code, self.world, parts, self.rl, self.c, self.rank * self.cb, self.cb,
+                                                 out.data_ptr(), self.cb, int(forward), 1.0, stream))
+        return out

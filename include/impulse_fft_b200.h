@@ -129,6 +129,29 @@ int impulse_fft_transpose(int dtype, const void *in, void *out, size_t rows, siz
 int impulse_fft_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
                        size_t batch, size_t bs_in, size_t bs_out, void *stream);
 
+/* Column pass of a 2-D complex transform whose ROWS are distributed over `nparts` allocations of
+ * `rows_per_part` rows each (leading dimension `ld_part` elements) — typically the row slabs of the other
+ * GPUs of the box, mapped through CUDA IPC: out[k][c] = fct * sum_r part[r / rpp][(r % rpp)*ld_part + col0 + c]
+ * * exp(-+2 pi i r k / R), R = nparts*rows_per_part, c < ncols, written with leading dimension ld_out.
+ * The kernel loads straight from the peers' memory over NVLink (no pack, no all-to-all staging): the
+ * exchange is fused into the load phase of the transform.  nparts <= 8.  Device pointers. */
+int impulse_fft_cols_from_parts(int dtype, size_t nparts, const void *const *parts, size_t rows_per_part, size_t ld_part,
+                                size_t col0, size_t ncols, void *out, size_t ld_out, int forward, double fct, void *stream);
+
+/* Device buffers that other PROCESSES of the same box can map (CUDA IPC), for the row slabs of the
+ * multi-GPU 2-D transform.  alloc: cudaMalloc + cudaIpcGetMemHandle (handle = 64 opaque bytes to send to the
+ * peers).  open: maps a peer's buffer into the CURRENT device's address space with peer access enabled
+ * (cudaIpcOpenMemHandle, lazy peer access) so that kernels of this device can load from it over NVLink. */
+int impulse_fft_ipc_alloc(size_t bytes, void **ptr, void *handle64);
+int impulse_fft_ipc_free(void *ptr);
+int impulse_fft_ipc_open(const void *handle64, void **ptr);
+int impulse_fft_ipc_close(void *ptr);
+
+/* Let kernels of the CURRENT device dereference memory that lives on `peer_device` (cudaDeviceEnablePeerAccess;
+ * "already enabled" is not an error).  Needed once per peer before impulse_fft_cols_from_parts is given
+ * pointers into other GPUs' memory. */
+int impulse_fft_enable_peer_access(int peer_device);
+
 /* Introspection (tests, benchmarks). */
 typedef struct {
   uint32_t n_steps;        /* kernel launches per execute                       */

@@ -289,6 +289,9 @@ def test_errors(ib):
     apply_nd(ib, "c2c", z, z.copy(), [1])  # empty array: no-op (hdronly.h:3277)
     with pytest.raises(TypeError):
         apply_nd(ib, "r2r", np.zeros(4), np.zeros(4), [0])
+    with pytest.raises(ib.FFTError):  # r2c in place (Hermitian layout): rows would overlap their neighbours' output
+        buf = np.zeros((4, 10))
+        ib.FFTDesc.init(axes=[1], forward=True).apply(ib.DataDesc.init(buf.view(np.complex128)), ib.DataDesc.init(buf[:, :8]))
     with pytest.raises(ib.FFTError):  # in place with different strides (hdronly.h:455)
         m = np.zeros((4, 4), np.complex128)
         ib.FFTDesc.init(axes=[0], forward=True).apply(ib.DataDesc.init(m.T), ib.DataDesc.init(m))
@@ -562,3 +565,23 @@ def test_dct_dst(ib, torch_mod, checker):
         ib.DCTDesc.init(axes=[0], dctType=5)
     with pytest.raises(ib.FFTError):
         ib.DCTDesc.init(axes=[0], dctType=1).apply(ib.DataDesc.init(np.zeros(1)), ib.DataDesc.init(np.zeros(1)))
+
+
+def test_cols_from_parts_single_gpu(ib, torch_mod, checker):
+    """impulse_fft_cols_from_parts with the parts in separate allocations of ONE GPU: the segmented-load
+    logic of the fused multi-GPU column pass, isolated from CUDA IPC (tests/test_gpu_dist.py covers that)."""
+    import ctypes as C
+    from impulse_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(71)
+    for (nparts, rpp, cols, col0, ncols) in ((2, 32, 96, 48, 48), (2, 32, 96, 0, 48), (4, 256, 64, 16, 24), (8, 1024, 40, 8, 32),
+                                             (2, 4096, 24, 0, 24), (1, 64, 16, 0, 16)):
+        full = rnd(rng, (nparts * rpp, cols), np.complex128)
+        parts = [torch_mod.from_numpy(full[q * rpp:(q + 1) * rpp].copy()).cuda() for q in range(nparts)]
+        out = torch_mod.empty((nparts * rpp, ncols), dtype=torch_mod.complex128, device="cuda")
+        ptrs = (C.c_void_p * nparts)(*[p.data_ptr() for p in parts])
+        for fwd in (True, False):
+            _lib.check(L.impulse_fft_cols_from_parts(_lib.F64, nparts, ptrs, rpp, cols, col0, ncols, out.data_ptr(), ncols,
+                                                     int(fwd), 0.5, None))
+            want = checker.c2c(np.ascontiguousarray(full[:, col0:col0 + ncols]), [0], fwd, 0.5)
+            assert oracle.rel_l2(out.cpu().numpy(), want) <= tol(nparts * rpp), (nparts, rpp, cols, col0, ncols, fwd)
