@@ -585,3 +585,31 @@ def test_cols_from_parts_single_gpu(ib, torch_mod, checker):
                                                      int(fwd), 0.5, None))
             want = checker.c2c(np.ascontiguousarray(full[:, col0:col0 + ncols]), [0], fwd, 0.5)
             assert oracle.rel_l2(out.cpu().numpy(), want) <= tol(nparts * rpp), (nparts, rpp, cols, col0, ncols, fwd)
+
+
+def test_config5_full_image_size_properties(ib, torch_mod):
+    """BASELINE config 5 at the full 4096 x 4096 float32 image size (batch reduced to 4): identity kernel
+    returns the image (2-D r2c -> c2r round trip), a 31x31 kernel matches the direct sum at sampled
+    pixels, and the transform is linear."""
+    from impulse_b200.filter import FFTFilter2D
+    g = torch_mod.Generator(device="cuda").manual_seed(77)
+    img = torch_mod.rand((4, 4096, 4096), generator=g, device="cuda", dtype=torch_mod.float32)
+    delta = torch_mod.zeros((31, 31), device="cuda", dtype=torch_mod.float32)
+    delta[15, 15] = 1.0
+    same = FFTFilter2D(delta, 4096, 4096).apply(img)
+    err = float(torch_mod.linalg.vector_norm(same - img) / torch_mod.linalg.vector_norm(img))
+    assert err <= 1e-5 * 12, err
+    ker = torch_mod.rand((31, 31), generator=g, device="cuda", dtype=torch_mod.float32)
+    ker /= ker.sum()
+    f = FFTFilter2D(ker, 4096, 4096)
+    out = f.apply(img)
+    kn = ker.cpu().numpy().astype(np.float64)
+    im0 = img[1].cpu().numpy().astype(np.float64)
+    for (r, c) in ((0, 0), (15, 4000), (2048, 2048), (4095, 4095), (100, 7)):
+        rr = (r - (np.arange(31) - 15)) % 4096      # circular: out[r,c] = sum k[i,j] * img[r-(i-15), c-(j-15)]
+        cc = (c - (np.arange(31) - 15)) % 4096
+        direct = float((kn * im0[np.ix_(rr, cc)]).sum())
+        assert abs(float(out[1, r, c]) - direct) <= 2e-5, (r, c)
+    lin = f.apply(2.0 * img[:2] + img[2:4])
+    ref = 2.0 * out[:2] + out[2:4]
+    assert float(torch_mod.linalg.vector_norm(lin - ref) / torch_mod.linalg.vector_norm(ref)) <= 1e-5
