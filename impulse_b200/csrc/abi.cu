@@ -146,7 +146,7 @@ size_t side_align(const NdDesc &d, bool input) {
 }
 
 // run all steps with device pointers on `stream`
-int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaStream_t stream) {
+int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaStream_t stream, const void *umul = nullptr) {
   const NdPlan &nd = p->nd;
   if (nd.empty) return 0;
   if (((uintptr_t)in % p->in_esz) || ((uintptr_t)out % p->out_esz))
@@ -182,6 +182,12 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     J.in = src + st.src_off_bytes;
     J.out = dst + st.dst_off_bytes;
     J.fct = st.takes_fct ? fct : 1.0;
+    if (st.takes_umul) {
+      if (!umul) { rc = fail(IMPULSE_FFT_ERR_INVALID, "this plan needs a multiplier array"); break; }
+      J.umul = umul;
+    } else {
+      J.umul_mod = 0;
+    }
     const size_t r = J.dtype == 1 ? 8 : 4;
     if ((J.flags & F_VEC_IN) && ((uintptr_t)J.in % (2 * r))) J.flags &= ~F_VEC_IN;
     if ((J.flags & F_VEC_OUT) && ((uintptr_t)J.out % (2 * r))) J.flags &= ~F_VEC_OUT;
@@ -451,6 +457,27 @@ int impulse_fft_c2r(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t
                     const void *data_in, void *data_out, double fct, size_t, void *stream) {
   return one_shot(KIND_C2R, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, forward,
                   data_in, data_out, fct, stream);
+}
+
+int impulse_fft_c2c_mul(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                        const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *data_in,
+                        void *data_out, double fct, const void *mul, size_t mul_elems, void *stream) {
+  if (!mul || !mul_elems) return fail(IMPULSE_FFT_ERR_INVALID, "null multiplier");
+  NdDesc d;
+  int rc = make_desc(&d, KIND_C2C, dtype, RL_HERMITIAN, forward, ndim, shape, stride_in, stride_out, naxes, axes);
+  if (rc) return rc;
+  d.umul_mod = mul_elems;
+  for (size_t i = 0; i < ndim; ++i)
+    if (stride_out[i] <= 0) return fail(IMPULSE_FFT_ERR_STRIDE, "the output of a fused multiply needs positive strides");
+  if (!data_in || !data_out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
+  if (!is_device_ptr(data_in) || !is_device_ptr(data_out) || !is_device_ptr(mul))
+    return fail(IMPULSE_FFT_ERR_INVALID, "impulse_fft_c2c_mul takes device pointers");
+  impulse_fft_plan raw = nullptr;
+  rc = create_plan(&raw, d);
+  if (rc) return rc;
+  std::unique_ptr<impulse_fft_plan_s> plan(raw);
+  if (!plan->nd.out_dense) return fail(IMPULSE_FFT_ERR_STRIDE, "the output of a fused multiply must be dense");
+  return run_device(plan.get(), data_in, data_out, fct, static_cast<cudaStream_t>(stream), mul);
 }
 
 int impulse_fft_dct(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,

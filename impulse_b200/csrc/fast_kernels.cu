@@ -684,6 +684,7 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   for (int k = 0; k < R1; ++k) S[(k * R2 + i) * LPC + line] = x[k];
   __syncthreads();
   const T f = (T)J.fct;
+  const uint64_t umul_off = J.umul_mod ? (uint64_t)off_out % J.umul_mod : 0;
 #pragma unroll
   for (int m = 0; m < NB2; ++m) {
     const int k1 = i + R2 * m;
@@ -703,6 +704,11 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
       }
       v.x *= f;
       v.y *= BWD ? -f : f;
+      if (J.umul_mod && valid) {  // fused pointwise multiply (e.g. the filter spectrum of an FFT convolution)
+        uint64_t o = umul_off + (uint64_t)((int64_t)k * J.es_out);
+        if (o >= J.umul_mod) o %= J.umul_mod;   // one line usually spans at most one period: rarely taken
+        v = cmul(v, __ldg(reinterpret_cast<const cx<T> *>(J.umul) + o));
+      }
       if (valid) out[(int64_t)k * J.es_out] = v;
     }
   }

@@ -469,6 +469,11 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e,
           v = cmul(v, cconj_if(w, (J.flags & F_CONJ_OUT) != 0));
         }
         if (J.mul_tab) v = cmul(v, IMP_LDG((const cx<T> *)J.mul_tab + (tw_idx + J.mul_stride * e)));
+        if (J.umul_mod) {
+          uint64_t o = (uint64_t)(off + (int64_t)e * es);
+          if (o >= J.umul_mod) o %= J.umul_mod;
+          v = cmul(v, IMP_LDG((const cx<T> *)J.umul + o));
+        }
         v.x *= f; v.y *= f;
       }
       outc[off + (int64_t)e * es] = cconj_if(v, cres);

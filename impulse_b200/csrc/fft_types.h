@@ -164,6 +164,10 @@ struct LineJob {
   // the line is distributed over several allocations (peer GPUs' row slabs in the multi-GPU 2-D transform)
   uint32_t seg_len;            // 0 = off
   const void *seg_base[8];
+  // caller-supplied multiplier fused into the store (FFT -> pointwise multiply): output element at element
+  // offset o of the output array is multiplied by umul[o % umul_mod]  (umul_mod = 0: off)
+  const void *umul;
+  uint64_t umul_mod;
   const void *mul_tab;     // ST_C: multiply output element e by mul_tab[line_index + mul_stride*e] (null = off)
   uint32_t mul_stride;
   double fct;

@@ -379,6 +379,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   J->zero_pad_from = s.zero_pad_from;
   J->mul_tab = s.mul_tab;
   J->mul_stride = s.mul_stride;
+  J->umul_mod = s.umul_mod;
   if (s.blue_stage) {  // the line itself (L points) lives in shared memory; the n2-point work array is global
     if (!E->blue) { *err = "internal: Bluestein staging on a direct length"; return ERR_INVALID; }
     J->n_fft = L;
@@ -543,7 +544,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
 
   // specialised kernels: contiguous complex rows, one batch dimension, headline lengths
   J->fast_id = FAST_NONE;
-  if (s.kind == KIND_C2C && !E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
+  if (s.kind == KIND_C2C && !E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
       !env_int("IMPULSE_FFT_NO_FAST", 0)) {
     if (f64 && N == 1024) J->fast_id = FAST2_1024_F64;
     else if (f64 && N == 512) J->fast_id = FAST2_512_F64;
@@ -567,7 +568,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   }
   // fused Bluestein on the register core: complex Bluestein lengths up to 4104 points, and odd real
   // lengths in that range with two rows packed per complex line (Hermitian layout); contiguous rows
-  if (E->blue && f64 && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
+  if (E->blue && f64 && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
       J->bdim[1] == 1 && J->bdim[2] == 1 && !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_FASTBLUE", 0)) {
     const bool okc = s.kind == KIND_C2C;
     const bool okr = (s.kind == KIND_R2C || s.kind == KIND_C2R) && !even && s.layout == RL_HERMITIAN;
@@ -585,7 +586,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   }
   // three-pass register kernels: c2c of 2048/4096/8192 points, and even-N r2c/c2r (Hermitian layout)
   // whose half-length complex transform is one of those; contiguous rows, one batch dimension
-  if (!E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
+  if (!E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
       J->bdim[1] == 1 && J->bdim[2] == 1 && !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_FAST3", 0)) {
     const bool c2c = s.kind == KIND_C2C;
     const bool r2c = s.kind == KIND_R2C && even && s.layout == RL_HERMITIAN && (J->bdim[0] == 1 || s.bs_in[0] % 2 == 0);
@@ -648,6 +649,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     }
   }
   if (d.dtype != DT_F32 && d.dtype != DT_F64) { *err = "bad dtype"; return ERR_INVALID; }
+  if (d.umul_mod && d.kind != KIND_C2C) { *err = "fused multiply is a c2c option"; return ERR_INVALID; }
   if (d.layout != RL_HERMITIAN && d.axes.size() != 1) { *err = "packed/symmetric real layouts are 1-axis only"; return ERR_INVALID; }
   size_t total = 1;
   for (size_t s : d.shape) total *= s;
@@ -686,7 +688,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
                   std::vector<Dim> dims, int tw_key /*index into dims of the line-index dim, -1 = none*/, uint32_t tw4_n,
                   const void *mul_tab, uint32_t mul_stride, int blue_stage,
                   size_t esz_in, size_t esz_out, int src, int dst, int64_t src_base, int64_t dst_base,
-                  bool takes_fct) -> int {
+                  bool takes_fct, uint64_t umul_mod = 0) -> int {
     std::vector<int> key(dims.size());
     for (size_t i = 0; i < dims.size(); ++i) key[i] = (int)i;
     std::vector<size_t> order(dims.size());
@@ -731,6 +733,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     }
     s.mul_tab = mul_tab;
     s.mul_stride = mul_stride;
+    s.umul_mod = umul_mod;
     s.blue_stage = blue_stage;
     s.r2r_type = d.r2r_type;
     s.ortho = d.ortho;
@@ -741,6 +744,8 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     int rc = build_line_job(s, &proto.job, &proto.cfg, err);
     if (rc) return rc;
     proto.takes_fct = takes_fct;
+    proto.takes_umul = umul_mod != 0;
+    if (umul_mod && nouter > 1) { *err = "fused multiply supports at most three batch dimensions"; return ERR_UNSUPPORTED; }
     proto.src = src; proto.dst = dst;
     for (uint64_t it = 0; it < nouter; ++it) {
       Step st = proto;
@@ -771,10 +776,10 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   // complex line transform of length N; splits N = N1*N2 over two launches when one CTA cannot hold the
   // line, or cannot hold S adjacent lines of a strided axis.  mul_tab (optional) multiplies output k.
   std::function<int(bool, uint32_t, int64_t, int64_t, const std::vector<Dim> &, size_t, size_t, int, int, int64_t, int64_t,
-                    bool, const void *)>
+                    bool, const void *, uint64_t)>
       emit_c2c = [&](bool forward, uint32_t N, int64_t es_in, int64_t es_out, const std::vector<Dim> &dims, size_t esz_in,
                      size_t esz_out, int src, int dst, int64_t src_base, int64_t dst_base, bool takes_fct,
-                     const void *mul_tab) -> int {
+                     const void *mul_tab, uint64_t umul_mod) -> int {
     bool split = false;
     if (N >= 64 && !choose_radices(N).empty()) {
       const bool fitsS = (size_t)S_g * (N + S_g + 1) * csize_g <= budget_g;
@@ -788,7 +793,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     }
     if (!split)
       return emit(KIND_C2C, RL_HERMITIAN, forward, N, es_in, es_out, dims, -1, 0, mul_tab, 1, 0, esz_in, esz_out, src, dst,
-                  src_base, dst_base, takes_fct);
+                  src_base, dst_base, takes_fct, umul_mod);
     // N1 = largest divisor of N not above sqrt(N); both halves then run in shared memory
     uint32_t N1 = 1;
     for (uint32_t f = 1; (uint64_t)f * f <= N; ++f) if (N % f == 0) N1 = f;
@@ -810,13 +815,14 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     db.push_back({N1, es_in * (int64_t)N2, es_out});
     for (auto &dm : dims) db.push_back({dm.n, dm.sin, dm.sout});
     return emit(KIND_C2C, RL_HERMITIAN, forward, N2, es_in, es_out * (int64_t)N1, db, mul_tab ? 0 : -1, 0, mul_tab, N1, 0,
-                esz_in, esz_out, BUF_TMP2, dst, -(int64_t)slo + src_base, dst_base, takes_fct);
+                esz_in, esz_out, BUF_TMP2, dst, -(int64_t)slo + src_base, dst_base, takes_fct, umul_mod);
   };
 
   // one batched line transform along `axis`
   auto add_axis = [&](int kind, int layout, bool forward, size_t axis, uint32_t N,
                       const std::vector<size_t> &bshape, const std::vector<ptrdiff_t> &sin, size_t esz_in,
-                      const std::vector<ptrdiff_t> &sout, size_t esz_out, int src, int dst, bool takes_fct) -> int {
+                      const std::vector<ptrdiff_t> &sout, size_t esz_out, int src, int dst, bool takes_fct,
+                      uint64_t umul_mod = 0) -> int {
     std::vector<Dim> dims;
     for (size_t i = 0; i < nd; ++i) {
       if (i == axis || bshape[i] == 1) continue;
@@ -829,6 +835,10 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     const Engine1D *E = nullptr;
     int rc = status_engine(L, d.dtype, &E, err);
     if (rc) return rc;
+    if (umul_mod && (kind != KIND_C2C || (E->blue && !fits_one(E->n_fft)))) {
+      *err = "fused multiply is available for single- and split-launch complex transforms";
+      return ERR_UNSUPPORTED;
+    }
     if (E->blue && (!fits_one(E->n_fft) || env_int("IMPULSE_FFT_FORCE_BIGBLUE", 0))) {
       // ---- multi-launch Bluestein: the L-point line fits a CTA, its n2-point work array does not.
       //   1. load + (c2r pre-twiddle) + chirp, zero-padded to n2, into the work array [lines][n2]
@@ -851,14 +861,14 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       plan->tmp3_bytes = std::max<size_t>(plan->tmp3_bytes, (size_t)nlines * n2 * csize_g);
       rc = emit(kind, layout, forward, N, es_in, 1, d_in, -1, 0, nullptr, 0, 1, esz_in, csize_g, src, BUF_TMP3, 0, 0, false);
       if (rc) return rc;
-      rc = emit_c2c(true, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, bkf_nat);
+      rc = emit_c2c(true, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, bkf_nat, 0);
       if (rc) return rc;
-      rc = emit_c2c(false, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, nullptr);
+      rc = emit_c2c(false, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, nullptr, 0);
       if (rc) return rc;
       return emit(kind, layout, forward, N, 1, es_out, d_out, -1, 0, nullptr, 0, 2, csize_g, esz_out, BUF_TMP3, dst, 0, 0, takes_fct);
     }
     if (kind == KIND_C2C)
-      return emit_c2c(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, 0, 0, takes_fct, nullptr);
+      return emit_c2c(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, 0, 0, takes_fct, nullptr, umul_mod);
     return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, nullptr, 0, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
   };
 
@@ -867,9 +877,10 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     // general_nd: first axis in -> out with fct, remaining axes in place on out (hdronly.h:3018-3048)
     for (size_t i = 0; i < d.axes.size() && !rc; ++i) {
       const bool first = i == 0;
+      const bool lastax = i + 1 == d.axes.size();
       rc = add_axis(KIND_C2C, RL_HERMITIAN, d.forward, d.axes[i], (uint32_t)d.shape[d.axes[i]], d.shape,
                     first ? d.stride_in : d.stride_out, csz, d.stride_out, csz,
-                    first ? BUF_IN : BUF_OUT, BUF_OUT, first);
+                    first ? BUF_IN : BUF_OUT, BUF_OUT, first, lastax ? d.umul_mod : 0);
     }
   } else if (nd_r2r) {
     // general_nd with ExecDcst (hdronly.h:3105-3121): every axis is the same 1-D transform, fct once

@@ -70,6 +70,7 @@ struct LineSpec {
   uint32_t mul_stride = 0;
   int r2r_type = 2;    // DCT/DST type 1..4 (pocketfft_hdronly.h:3284-3318)
   bool ortho = false;
+  uint64_t umul_mod = 0;  // caller-supplied multiplier fused into the store (pointer set at execute time)
   int blue_stage = 0;  // multi-launch Bluestein: 1 = load+chirp+zero-pad to scratch, 2 = scratch+chirp+store
 };
 
@@ -80,6 +81,7 @@ struct Step {
   LaunchCfg cfg;
   int src = BUF_IN, dst = BUF_OUT;
   int64_t src_off_bytes = 0, dst_off_bytes = 0;  // host-looped outer dims
+  bool takes_umul = false;  // this step multiplies its output by the caller's array (impulse_fft_c2c_mul)
   bool takes_fct = false;  // the scaling factor is applied once, in these steps (hdronly.h:3048)
 };
 
@@ -91,6 +93,7 @@ struct NdDesc {
   std::vector<size_t> axes;
   int r2r_type = 2;  // DCT/DST only
   bool ortho = false;
+  uint64_t umul_mod = 0;  // c2c only: multiply the result by umul[offset % umul_mod]
 };
 
 struct NdPlan {

@@ -95,6 +95,14 @@ int impulse_fft_c2r(int dtype, size_t ndim, const size_t *shape_out, const ptrdi
                     const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
                     const void *data_in, void *data_out, double fct, size_t nthreads, void *stream);
 
+/* impulse_fft_c2c with a pointwise multiply fused into the store of the last pass: the output element at
+ * element offset o of the (dense) output array is multiplied by mul[o % mul_elems] — mul_elems = the
+ * size of one image broadcasts one filter spectrum over a batch.  This is the FFT -> multiply half of an
+ * FFT convolution without the extra pass over the spectrum.  Device pointers. */
+int impulse_fft_c2c_mul(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                        const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *data_in,
+                        void *data_out, double fct, const void *mul, size_t mul_elems, void *stream);
+
 /* Discrete cosine / sine transforms of type 1..4 over `axes`, real to real, with the argument list of
  * pocketfft::dct / pocketfft::dst (pocketfft_hdronly.h:3284-3318; FFTW's REDFT/RODFT definitions;
  * `ortho` as documented at README_pocketfft.md:220-241).  Called by DCTDesc.apply

@@ -49,12 +49,20 @@ const char *emu_last_error() { return g_err.c_str(); }
 // mirrors impulse_fft_nd() of the product ABI, on host memory
 static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
                        const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
-                       void *out, double fct, int r2r_type, int ortho);
+                       void *out, double fct, int r2r_type, int ortho, const void *umul = nullptr, size_t umul_mod = 0);
 
 int emu_nd(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
            const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
            void *out, double fct) {
   return emu_nd_impl(kind, dtype, layout, ndim, shape, stride_in, stride_out, naxes, axes, forward, in, out, fct, 2, 0);
+}
+
+// mirrors impulse_fft_c2c_mul: complex transform with a pointwise multiply fused into the last store
+int emu_c2c_mul(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in, const ptrdiff_t *stride_out,
+                size_t naxes, const size_t *axes, int forward, const void *in, void *out, double fct, const void *mul,
+                size_t mul_elems) {
+  return emu_nd_impl(KIND_C2C, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, forward, in, out, fct,
+                     2, 0, mul, mul_elems);
 }
 
 // DCT (cosine != 0) / DST of type 1..4, mirrors impulse_fft_dct / impulse_fft_dst
@@ -66,10 +74,11 @@ int emu_r2r(int cosine, int type, int ortho, int dtype, size_t ndim, const size_
 
 static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
                        const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
-                       void *out, double fct, int r2r_type, int ortho) {
+                       void *out, double fct, int r2r_type, int ortho, const void *umul, size_t umul_mod) {
   if (!g_cache) g_cache = new PlanCache(&g_alloc);
   NdDesc d;
   d.r2r_type = r2r_type; d.ortho = ortho != 0;
+  d.umul_mod = umul_mod;
   d.kind = kind; d.dtype = dtype; d.layout = layout; d.forward = forward != 0;
   d.shape.assign(shape, shape + ndim);
   d.stride_in.assign(stride_in, stride_in + ndim);
@@ -86,6 +95,7 @@ static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_
     st.job.in = bufs_in[st.src] + st.src_off_bytes;
     st.job.out = bufs_out[st.dst] + st.dst_off_bytes;
     st.job.fct = st.takes_fct ? fct : 1.0;
+    if (st.takes_umul) st.job.umul = umul; else st.job.umul_mod = 0;
     if (dtype == DT_F64) run_job<double>(st.job, st.cfg); else run_job<float>(st.job, st.cfg);
   }
   return 0;

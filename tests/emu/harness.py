@@ -64,6 +64,23 @@ def nd(kind, a_in, a_out, shape, axes, forward=True, fct=1.0, layout="hermitian"
     return a_out
 
 
+def c2c_mul(a_in, a_out, axes, mul, forward=True, fct=1.0):
+    """Mirror of impulse_fft_c2c_mul: a_out = c2c(a_in) * mul[flat offset % mul.size]."""
+    L = lib()
+    L.emu_c2c_mul.restype = C.c_int
+    L.emu_c2c_mul.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_ssize_t), C.POINTER(C.c_ssize_t),
+                              C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                              C.c_size_t]
+    dt = 1 if a_in.dtype == np.complex128 else 0
+    n = a_in.ndim
+    rc = L.emu_c2c_mul(dt, n, (C.c_size_t * n)(*a_in.shape), (C.c_ssize_t * n)(*a_in.strides),
+                       (C.c_ssize_t * n)(*a_out.strides), len(axes), (C.c_size_t * len(axes))(*axes), int(forward),
+                       a_in.ctypes.data, a_out.ctypes.data, fct, mul.ctypes.data, mul.size)
+    if rc:
+        raise EmuError(rc, L.emu_last_error().decode())
+    return a_out
+
+
 def r2r(cosine, type_, a_in, a_out, axes, fct=1.0, ortho=False):
     L = lib()
     if not hasattr(L, "_r2r_bound"):

@@ -289,3 +289,22 @@ def test_dct_dst_all_types(checker):
     assert oracle.max_row_rel_l2(y, x) <= 1e-14
     with pytest.raises(emu.EmuError):
         emu.r2r(True, 1, np.zeros((2, 1)), np.zeros((2, 1)), [1])   # DCT-I of one point (pocketfft throws too)
+
+
+@pytest.mark.parametrize("shape,axes,period", [
+    ((6, 64), [1], 64),          # one row of multipliers broadcast over the batch
+    ((3, 40, 24), [1], 40 * 24),  # strided axis, one image of multipliers
+    ((3, 40, 24), [1, 2], 40 * 24),
+    ((2, 4099), [1], 2 * 4099),  # Bluestein line, no broadcast
+    ((5, 16384), [1], 16384),    # split into two launches: the multiply rides on the second
+])
+@pytest.mark.parametrize("forward", [True, False])
+def test_c2c_fused_multiply(shape, axes, period, forward):
+    """impulse_fft_c2c_mul: out = c2c(in) * mul[offset % period]; checked against numpy."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    m = rng.standard_normal(period) + 1j * rng.standard_normal(period)
+    want = (np.fft.fftn(x, axes=axes) if forward else np.fft.ifftn(x, axes=axes, norm="forward"))
+    want = (want.reshape(-1, period) * m).reshape(shape)
+    got = emu.c2c_mul(x, np.empty_like(x), axes, m, forward=forward)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13

@@ -613,3 +613,44 @@ def test_config5_full_image_size_properties(ib, torch_mod):
     lin = f.apply(2.0 * img[:2] + img[2:4])
     ref = 2.0 * out[:2] + out[2:4]
     assert float(torch_mod.linalg.vector_norm(lin - ref) / torch_mod.linalg.vector_norm(ref)) <= 1e-5
+
+
+def test_c2c_fused_multiply(ib, torch_mod, checker):
+    """impulse_fft_c2c_mul: out = c2c(in) * mul[offset % period], through every kernel that can carry it
+    (generic line kernel, strided register kernel, both launches of the split), in place and out of place."""
+    import ctypes as C
+    from impulse_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(81)
+    used = set()
+    cases = [((6, 64), [1], 64, np.complex128), ((3, 40, 24), [1], 960, np.complex128), ((3, 40, 24), [1, 2], 960, np.complex64),
+             ((2, 4099), [1], 2 * 4099, np.complex128), ((5, 16384), [1], 16384, np.complex128),
+             ((3, 256, 100), [1], 25600, np.complex64), ((2, 4096, 2049), [1], 4096 * 2049, np.complex64),
+             ((4, 1024, 24), [1], 1024 * 24 * 2, np.complex128)]
+    for shape, axes, period, cdt in cases:
+        x = rnd(rng, shape, cdt)
+        m = rnd(rng, (period,), cdt)
+        xd, md = torch_mod.from_numpy(x).cuda(), torch_mod.from_numpy(m).cuda()
+        code = _lib.F64 if cdt == np.complex128 else _lib.F32
+        n = len(shape)
+        st = (C.c_ssize_t * n)(*x.strides)
+        for fwd in (True, False):
+            want = (checker.c2c(x, axes, fwd, 0.5).reshape(-1, period) * m).reshape(shape)
+            for inplace in (False, True):
+                src = xd.clone()
+                dst = src if inplace else torch_mod.empty_like(src)
+                _lib.check(L.impulse_fft_c2c_mul(code, n, (C.c_size_t * n)(*shape), st, st, len(axes),
+                                                 (C.c_size_t * len(axes))(*axes), int(fwd), src.data_ptr(), dst.data_ptr(), 0.5,
+                                                 md.data_ptr(), period, None))
+                used.add(ib.last_kernel())
+                big = max(shape[a] for a in axes)
+                assert oracle.rel_l2(dst.cpu().numpy(), want) <= 2 * tol(big, np.float64 if cdt == np.complex128 else np.float32), \
+                    (shape, axes, fwd, inplace)
+    print(sorted(used))
+    assert any(k.startswith("colfast2") for k in used) and any(k.startswith("line_fft") for k in used)
+    # a real transform cannot take a multiplier; host pointers are refused
+    x = np.zeros((4, 8), np.complex128)
+    st = (C.c_ssize_t * 2)(*x.strides)
+    rc = L.impulse_fft_c2c_mul(_lib.F64, 2, (C.c_size_t * 2)(4, 8), st, st, 1, (C.c_size_t * 1)(1), 1, x.ctypes.data,
+                               x.ctypes.data, 1.0, x.ctypes.data, 8, None)
+    assert rc == -1  # IMPULSE_FFT_ERR_INVALID
