@@ -6,10 +6,11 @@ Python host layer over the C ABI (libimpulse_fft_b200.so).  Two API mirrors:
 plus the multi-GPU drivers in impulse_b200.dist.
 """
 from ._lib import FFTError, last_kernel, launch_count  # noqa: F401
-from .desc import DataDesc, DCTDesc, FFTDesc, apply  # noqa: F401
+from .desc import (DataDesc, DCTDesc, FFTDesc, apply, r2r_fftpack, r2r_genuine_hartley,  # noqa: F401
+                   r2r_separable_hartley)
 from .fft import (fft, fft_inplace, ifft, initNormalize, isOdd, nkBackward, nkCustom, nkForward,  # noqa: F401
                   nkOrtho, rfft, rfft_packed, symmetrize, symmTargetSize, unpackFFT)
 
 __all__ = ["fft", "ifft", "rfft", "rfft_packed", "fft_inplace", "unpackFFT", "symmetrize", "symmTargetSize",
            "initNormalize", "isOdd", "nkBackward", "nkOrtho", "nkForward", "nkCustom",
-           "DataDesc", "FFTDesc", "DCTDesc", "apply", "FFTError", "launch_count", "last_kernel"]
+           "DataDesc", "FFTDesc", "DCTDesc", "apply", "r2r_fftpack", "r2r_separable_hartley", "r2r_genuine_hartley", "FFTError", "launch_count", "last_kernel"]

@@ -45,7 +45,8 @@ class PlanInfo(C.Structure):
 EXPORTS = [
     # include/impulse_fft_b200.h
     "impulse_fft_plan_create", "impulse_fft_plan_destroy", "impulse_fft_execute", "impulse_fft_c2c",
-    "impulse_fft_r2c", "impulse_fft_c2r", "impulse_fft_dct", "impulse_fft_dst", "impulse_fft_c2c_mul", "impulse_fft_cfft_rows", "impulse_fft_rfft_rows",
+    "impulse_fft_r2c", "impulse_fft_c2r", "impulse_fft_dct", "impulse_fft_dst", "impulse_fft_c2c_mul",
+    "impulse_fft_r2r_fftpack", "impulse_fft_r2r_separable_hartley", "impulse_fft_r2r_genuine_hartley", "impulse_fft_cfft_rows", "impulse_fft_rfft_rows",
     "impulse_fft_plan_get_info", "impulse_fft_launch_count", "impulse_fft_last_error", "impulse_fft_version",
     "impulse_fft_last_kernel",
     "impulse_fft_cmul", "impulse_fft_transpose", "impulse_fft_copy2d", "impulse_fft_cols_from_parts", "impulse_fft_enable_peer_access", "impulse_fft_ipc_alloc", "impulse_fft_ipc_free",
@@ -79,6 +80,13 @@ def lib() -> C.CDLL:
         f.argtypes = [C.c_int, C.c_size_t, sp, ssp, ssp, C.c_size_t, sp, C.c_int, vp, vp, C.c_double, C.c_size_t, vp]
     L.impulse_fft_c2c_mul.restype = C.c_int
     L.impulse_fft_c2c_mul.argtypes = [C.c_int, C.c_size_t, sp, ssp, ssp, C.c_size_t, sp, C.c_int, vp, vp, C.c_double, vp, C.c_size_t, vp]
+    L.impulse_fft_r2r_fftpack.restype = C.c_int
+    L.impulse_fft_r2r_fftpack.argtypes = [C.c_int, C.c_size_t, sp, ssp, ssp, C.c_size_t, sp, C.c_int, C.c_int, vp, vp, C.c_double,
+                                          C.c_size_t, vp]
+    for n in ("impulse_fft_r2r_separable_hartley", "impulse_fft_r2r_genuine_hartley"):
+        f = getattr(L, n)
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, C.c_size_t, sp, ssp, ssp, C.c_size_t, sp, vp, vp, C.c_double, C.c_size_t, vp]
     for n in ("impulse_fft_dct", "impulse_fft_dst"):
         f = getattr(L, n)
         f.restype = C.c_int

@@ -139,7 +139,7 @@ namespace {
 size_t side_align(const NdDesc &d, bool input) {
   const size_t r = d.dtype == DT_F64 ? 8 : 4;
   bool real_side;
-  const bool r2r = d.kind == KIND_DCT || d.kind == KIND_DST;
+  const bool r2r = d.kind >= KIND_DCT;  // DCT, DST, FFTPACK, Hartley: real on both sides
   if (input) real_side = r2r || d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX);
   else real_side = r2r || d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX);
   return real_side ? r : 2 * r;
@@ -151,7 +151,7 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
   if (nd.empty) return 0;
   if (((uintptr_t)in % p->in_esz) || ((uintptr_t)out % p->out_esz))
     return fail(IMPULSE_FFT_ERR_STRIDE, "data pointer is not aligned to its element size");
-  if (in == out && (nd.desc.kind == KIND_C2C || nd.desc.kind == KIND_DCT || nd.desc.kind == KIND_DST) &&
+  if (in == out && (nd.desc.kind == KIND_C2C || nd.desc.kind >= KIND_DCT) &&
       nd.desc.stride_in != nd.desc.stride_out)
     return fail(IMPULSE_FFT_ERR_STRIDE, "stride mismatch");  // hdronly.h:455-456
   void *tmp = nullptr, *tmp2 = nullptr, *tmp3 = nullptr;
@@ -179,6 +179,15 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
                                : st.src == BUF_TMP2 ? (const unsigned char *)tmp2 : (const unsigned char *)tmp3;
     unsigned char *dst = st.dst == BUF_OUT ? (unsigned char *)out : st.dst == BUF_TMP ? (unsigned char *)tmp
                          : st.dst == BUF_TMP2 ? (unsigned char *)tmp2 : (unsigned char *)tmp3;
+    if (st.combine) {
+      CombineJob cj = st.cj;
+      cj.in = src + st.src_off_bytes;
+      cj.out = dst + st.dst_off_bytes;
+      int e = launch_hartley_combine(cj, p->ctx->sm_count, stream);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (e) { rc = cuda_fail((cudaError_t)e, "kernel launch"); break; }
+      continue;
+    }
     J.in = src + st.src_off_bytes;
     J.out = dst + st.dst_off_bytes;
     J.fct = st.takes_fct ? fct : 1.0;
@@ -348,10 +357,13 @@ int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, 
              const ptrdiff_t *sout, size_t naxes, const size_t *axes, int forward, const void *in, void *out,
              double fct, void *stream) {
   NdDesc d;
-  const bool r2r = kind == KIND_DCT || kind == KIND_DST;
-  int rc = make_desc(&d, kind, dtype, r2r ? RL_HERMITIAN : layout, r2r ? 1 : forward, ndim, shape, sin, sout, naxes, axes);
+  // real-to-real kinds carry their own options in the `layout` / `forward` slots of this helper
+  const bool r2r = kind == KIND_DCT || kind == KIND_DST, fpk = kind == KIND_FFTPACK, hart = kind >= KIND_HARTLEY_SEP;
+  int rc = make_desc(&d, kind, dtype, (r2r || fpk || hart) ? RL_HERMITIAN : layout, (r2r || hart) ? 1 : forward, ndim, shape,
+                     sin, sout, naxes, axes);
   if (rc) return rc;
   if (r2r) { d.r2r_type = layout; d.ortho = forward != 0; }
+  if (fpk) d.real2hermitian = layout != 0;
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }
   OneShotKey key{dev, kind, dtype, layout, forward != 0, d.shape, d.axes, d.stride_in, d.stride_out};
@@ -491,6 +503,24 @@ int impulse_fft_dst(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t
                     void *data_out, double fct, int ortho, size_t, void *stream) {
   if (type < 1 || type > 4) return fail(IMPULSE_FFT_ERR_INVALID, "invalid DST type");  // hdronly.h:3305
   return one_shot(KIND_DST, dtype, type, ndim, shape, stride_in, stride_out, naxes, axes, ortho != 0, data_in, data_out, fct, stream);
+}
+
+// pocketfft::r2r_fftpack / r2r_separable_hartley / r2r_genuine_hartley (pocketfft_hdronly.h:3392-3445)
+int impulse_fft_r2r_fftpack(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                            const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int real2hermitian, int forward,
+                            const void *data_in, void *data_out, double fct, size_t, void *stream) {
+  return one_shot(KIND_FFTPACK, dtype, real2hermitian != 0, ndim, shape, stride_in, stride_out, naxes, axes, forward != 0,
+                  data_in, data_out, fct, stream);
+}
+int impulse_fft_r2r_separable_hartley(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                                      const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, const void *data_in,
+                                      void *data_out, double fct, size_t, void *stream) {
+  return one_shot(KIND_HARTLEY_SEP, dtype, 0, ndim, shape, stride_in, stride_out, naxes, axes, 1, data_in, data_out, fct, stream);
+}
+int impulse_fft_r2r_genuine_hartley(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, const void *data_in,
+                                    void *data_out, double fct, size_t, void *stream) {
+  return one_shot(KIND_HARTLEY_GEN, dtype, 0, ndim, shape, stride_in, stride_out, naxes, axes, 1, data_in, data_out, fct, stream);
 }
 
 int impulse_fft_cfft_rows(double *data, size_t nrows, size_t length, int forward, double fct, void *stream) {

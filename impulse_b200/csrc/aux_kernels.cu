@@ -102,4 +102,21 @@ int launch_transpose(int dtype, const void *in, void *out, size_t rows, size_t c
   return (int)cudaGetLastError();
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) hartley_combine_kernel(const __grid_constant__ CombineJob C) {
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < C.total; g += (uint64_t)gridDim.x * blockDim.x)
+    hartley_combine_one<T>(C, g);
+}
+
+int launch_hartley_combine(const CombineJob &job, int sm_count, void *stream) {
+  if (job.total == 0) return 0;
+  const uint64_t want = (job.total + 255) / 256, cap = (uint64_t)sm_count * 16;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (job.dtype == 1) hartley_combine_kernel<double><<<grid, 256, 0, s>>>(job);
+  else hartley_combine_kernel<float><<<grid, 256, 0, s>>>(job);
+  g_last_kernel = "hartley_combine_kernel";
+  return (int)cudaGetLastError();
+}
+
 }  // namespace impulse

@@ -190,10 +190,13 @@ IMP_HD void load_one(const LineJob &J, cx<T> *S /*line base*/, int64_t off, uint
         v.x = inr[off + (2 * (int64_t)e) * es];
         v.y = inr[off + (2 * (int64_t)e + 1) * es];
       }
+      if ((J.flags & F_NEG_EVEN_IN) && e > 0) v.x = -v.x;
       S[phys<T>(J, e)] = v;
     } break;
     case LD_R_ZEROIM: {
-      S[phys<T>(J, e)] = mk<T>(inr[off + (int64_t)e * es], (T)0);
+      T xv = inr[off + (int64_t)e * es];
+      if ((J.flags & F_NEG_EVEN_IN) && e > 0 && !(e & 1)) xv = -xv;
+      S[phys<T>(J, e)] = mk<T>(xv, (T)0);
     } break;
     case LD_HERM_EVEN: {
       cx<T> v = inc[off + (int64_t)e * es];
@@ -500,6 +503,7 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e,
     case ST_R_PAIRS: {
       cx<T> v = read_bin<T>(J, S, e);
       v.x *= f; v.y *= f;
+      if ((J.flags & F_NEG_EVEN_OUT) && e > 0) v.x = -v.x;
       if (J.flags & F_VEC_OUT) {
         *(cx<T> *)(outr + off + 2 * (int64_t)e) = v;
       } else {
@@ -508,7 +512,20 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e,
       }
     } break;
     case ST_R_REALPART: {
-      outr[off + (int64_t)e * es] = read_bin<T>(J, S, e).x * f;
+      T y = read_bin<T>(J, S, e).x * f;
+      if ((J.flags & F_NEG_EVEN_OUT) && e > 0 && !(e & 1)) y = -y;
+      outr[off + (int64_t)e * es] = y;
+    } break;
+    case ST_HARTLEY_EVEN:
+    case ST_HARTLEY_FULL: {
+      cx<T> v = J.store_mode == ST_HARTLEY_EVEN ? r2c_even_bin<T>(J, S, e) : read_bin<T>(J, S, e);
+      v.x *= f; v.y *= f;
+      if (e == 0 || 2 * e == J.n_real) {
+        outr[off + (int64_t)e * es] = v.x;
+      } else {
+        outr[off + (int64_t)e * es] = v.x + v.y;
+        outr[off + (int64_t)(J.n_real - e) * es] = v.x - v.y;
+      }
     } break;
     case ST_HC_EVEN: {
       cx<T> v = r2c_even_bin<T>(J, S, e);
@@ -561,6 +578,28 @@ template <typename T>
 IMP_HD void phase_mid(const LineJob &J, const Phase &P, uint32_t tid, uint32_t nthr, cx<T> *smem) {
   if (P.op == OP_PASS_DIF || P.op == OP_PASS_DIT) phase_pass<T>(J, P, tid, nthr, smem);
   else phase_elementwise<T>(J, P, tid, nthr, smem);
+}
+
+// Genuine Hartley fold of element `idx` of the half spectrum (see CombineJob).  Elements whose mirror image
+// lies inside the half spectrum as well (index 0 or N/2 along the halved axis) write only themselves: the
+// mirror is written by its own element, so no output is written twice.
+template <typename T>
+IMP_HD void hartley_combine_one(const CombineJob &C, uint64_t idx) {
+  const cx<T> v = ((const cx<T> *)C.in)[idx];
+  int64_t off = 0, roff = 0;
+  uint32_t kh = 0;
+  uint64_t r = idx;
+  for (int d = C.ndim - 1; d >= 0; --d) {
+    const uint32_t k = (uint32_t)(r % C.hshape[d]);
+    r /= C.hshape[d];
+    const uint32_t rk = C.rev[d] ? (k == 0 ? 0 : C.full[d] - k) : k;
+    off += (int64_t)k * C.so[d];
+    roff += (int64_t)rk * C.so[d];
+    if ((uint32_t)d == C.half_axis) kh = k;
+  }
+  T *out = (T *)C.out;
+  out[off] = v.x + v.y;
+  if (kh != 0 && 2 * kh != C.full[C.half_axis]) out[roff] = v.x - v.y;
 }
 
 }  // namespace impulse

@@ -66,6 +66,8 @@ enum StoreMode : uint8_t {
   ST_R2C_EVEN_SYM = 7,   // even-N r2c, all N bins (Hermitian half + conjugate mirror): fused `symmetrize`
   ST_HERM_SYM = 8,       // odd-N r2c, all N bins                                   (pocketfft.nim:160-171)
   ST_X = 9,              // real-to-real: y[k] = s * (Re | -Im)(W_8N^(mul*k+add) * F[k+shift])
+  ST_HARTLEY_EVEN = 10,  // even-N real line -> y[k] = Re X[k] + Im X[k], y[N-k] = Re X[k] - Im X[k]
+  ST_HARTLEY_FULL = 11,  // odd-N, same combination                       (pocketfft_hdronly.h:3066-3095)
 };
 
 enum JobFlags : uint32_t {
@@ -77,6 +79,8 @@ enum JobFlags : uint32_t {
   F_OUT_LINES_FAST = 1u << 5,  // global writes: same
   F_VEC_IN = 1u << 6,       // LD_R_PAIRS may use one 2-element vector load
   F_VEC_OUT = 1u << 7,      // ST_R_PAIRS may use one 2-element vector store
+  F_NEG_EVEN_IN = 1u << 8,  // negate real input elements 2, 4, 6, ... (ExecR2R, pocketfft_hdronly.h:3134-3136)
+  F_NEG_EVEN_OUT = 1u << 9, // negate real output elements 2, 4, 6, ...       (pocketfft_hdronly.h:3138-3140)
 };
 
 // specialised register-resident kernels (fast_kernels.cu); 0 = generic phase interpreter
@@ -172,6 +176,23 @@ struct LineJob {
   uint32_t mul_stride;
   double fct;
   Phase ph[kMaxPhases];
+};
+
+// Genuine (non-separable) Hartley transform, last step (pocketfft_hdronly.h:3432-3444): the contiguous
+// half spectrum F of an N-D r2c is folded into the real output, out[k] = Re F[k] + Im F[k] and
+// out[-k mod shape] = Re F[k] - Im F[k].  One element of F per thread.
+constexpr int kMaxCombineDims = 8;
+struct CombineJob {
+  const void *in;   // complex, C-contiguous, shape hshape
+  void *out;        // real, strides so (elements)
+  int dtype;        // 0 = f32, 1 = f64
+  int ndim;
+  uint32_t half_axis;                 // the axis whose extent is halved in F (axes.back())
+  uint32_t hshape[kMaxCombineDims];   // iteration space
+  uint32_t full[kMaxCombineDims];     // output shape
+  uint8_t rev[kMaxCombineDims];       // transformed axes: the mirrored element has index (full - k) % full
+  int64_t so[kMaxCombineDims];
+  uint64_t total;
 };
 
 // shared-memory position of logical index a within a line

@@ -388,6 +388,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
 
   uint32_t need = J->n_fft;  // shared-memory element slots per line
   uint32_t flags = 0;
+  const bool hc = s.layout == RL_HALFCOMPLEX || s.layout == RL_HALFCOMPLEX_NEG;
   std::vector<Phase> pre;
   switch (s.kind) {
     case KIND_C2C:
@@ -398,30 +399,32 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     case KIND_R2C:
       if (even) {
         J->load_mode = LD_R_PAIRS; J->n_load = L; J->n_store = L + 1;
-        J->store_mode = s.layout == RL_HALFCOMPLEX ? ST_HC_EVEN : s.layout == RL_FULLSYM ? ST_R2C_EVEN_SYM : ST_R2C_EVEN;
+        J->store_mode = hc ? ST_HC_EVEN : s.layout == RL_FULLSYM ? ST_R2C_EVEN_SYM : s.layout == RL_HARTLEY ? ST_HARTLEY_EVEN : ST_R2C_EVEN;
         rc = real_twiddle(N, s.dtype, &J->tw_r, err);
         if (rc) return rc;
       } else {
         J->load_mode = LD_R_ZEROIM; J->n_load = N; J->n_store = (N + 1) / 2;
-        J->store_mode = s.layout == RL_HALFCOMPLEX ? ST_HC_FULL : s.layout == RL_FULLSYM ? ST_HERM_SYM : ST_HERM_HALF;
+        J->store_mode = hc ? ST_HC_FULL : s.layout == RL_FULLSYM ? ST_HERM_SYM : s.layout == RL_HARTLEY ? ST_HARTLEY_FULL : ST_HERM_HALF;
       }
       if (!s.forward) flags |= F_CONJ_RESULT;
+      if (s.layout == RL_HALFCOMPLEX_NEG) flags |= F_NEG_EVEN_IN;
       break;
     case KIND_C2R:
       flags |= F_CONJ_SEQ | F_CONJ_OUT;
       if (s.forward) flags |= F_CONJ_IN;
       if (even) {
-        J->load_mode = s.layout == RL_HALFCOMPLEX ? LD_HC_EVEN : LD_HERM_EVEN;
+        J->load_mode = hc ? LD_HC_EVEN : LD_HERM_EVEN;
         J->n_load = L + 1; J->n_store = L; J->store_mode = ST_R_PAIRS;
         need = std::max(need, L + 1);
         rc = real_twiddle(N, s.dtype, &J->tw_r, err);
         if (rc) return rc;
         Phase p{}; p.op = OP_C2R_PRE_EVEN; pre.push_back(p);
       } else {
-        J->load_mode = s.layout == RL_HALFCOMPLEX ? LD_HC_FULL : LD_HERM_FULL;
+        J->load_mode = hc ? LD_HC_FULL : LD_HERM_FULL;
         J->n_load = (N + 1) / 2; J->n_store = N; J->store_mode = ST_R_REALPART;
       }
-      if (s.layout == RL_FULLSYM) { *err = "FULLSYM layout is an r2c output layout"; return ERR_INVALID; }
+      if (s.layout == RL_FULLSYM || s.layout == RL_HARTLEY) { *err = "FULLSYM / Hartley are r2c output layouts"; return ERR_INVALID; }
+      if (s.layout == RL_HALFCOMPLEX_NEG) flags |= F_NEG_EVEN_OUT;
       break;
     case KIND_DCT:
     case KIND_DST: {
@@ -662,7 +665,8 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     if (d.layout == RL_HERMITIAN) cshape[last] = d.shape[last] / 2 + 1;
     else if (d.layout == RL_FULLSYM) cshape[last] = d.shape[last];
   }
-  const bool nd_r2r = d.kind == KIND_DCT || d.kind == KIND_DST;
+  const bool nd_r2r = d.kind == KIND_DCT || d.kind == KIND_DST || d.kind == KIND_FFTPACK || d.kind == KIND_HARTLEY_SEP ||
+                      d.kind == KIND_HARTLEY_GEN;
   const size_t in_esz = (nd_r2r || d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX)) ? rsz : csz;
   const size_t out_esz = (nd_r2r || d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX)) ? rsz : csz;
   const std::vector<size_t> &in_shape = (d.kind == KIND_C2R && d.layout == RL_HERMITIAN) ? cshape : d.shape;
@@ -721,6 +725,12 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
         is_tw[pos] = false;
         is_tw[kMaxBatchDims - 1] = true;
       }
+    }
+    // fused multiply: walk the dim along which the multiplier repeats (the image index of a filter bank)
+    // BEFORE the other outer dim, so that a block of multipliers is reused from L2 by every image in turn
+    if (umul_mod && sd.size() == 3 && sd[2].sout % (int64_t)umul_mod == 0 && sd[1].sout % (int64_t)umul_mod != 0) {
+      std::swap(sd[1], sd[2]);
+      const bool t = is_tw[1]; is_tw[1] = is_tw[2]; is_tw[2] = t;
     }
     LineSpec s;
     s.kind = kind; s.dtype = d.dtype; s.layout = layout; s.forward = forward; s.N = N;
@@ -881,6 +891,55 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       rc = add_axis(KIND_C2C, RL_HERMITIAN, d.forward, d.axes[i], (uint32_t)d.shape[d.axes[i]], d.shape,
                     first ? d.stride_in : d.stride_out, csz, d.stride_out, csz,
                     first ? BUF_IN : BUF_OUT, BUF_OUT, first, lastax ? d.umul_mod : 0);
+    }
+  } else if (d.kind == KIND_FFTPACK) {
+    // general_nd with ExecR2R (hdronly.h:3123-3143, 3392-3403): every axis in the given order.  The vendored
+    // engine passes `forward` (not `real2hermitian`) to the 1-D plan, so the direction of the real transform
+    // follows `forward`, and the mixed combinations only add the sign flips of elements 2,4,6,... —
+    // reproduced here as the reference computes it.
+    const int kind1 = d.forward ? KIND_R2C : KIND_C2R;
+    const int lay = (d.real2hermitian != d.forward) ? RL_HALFCOMPLEX_NEG : RL_HALFCOMPLEX;
+    for (size_t i = 0; i < d.axes.size() && !rc; ++i) {
+      const bool first = i == 0;
+      rc = add_axis(kind1, lay, d.forward, d.axes[i], (uint32_t)d.shape[d.axes[i]], d.shape,
+                    first ? d.stride_in : d.stride_out, rsz, d.stride_out, rsz, first ? BUF_IN : BUF_OUT, BUF_OUT, first);
+    }
+  } else if (d.kind == KIND_HARTLEY_SEP || (d.kind == KIND_HARTLEY_GEN && d.axes.size() == 1)) {
+    // general_nd with ExecHartley (hdronly.h:3097-3103): forward real transform, then Re + Im / Re - Im
+    for (size_t i = 0; i < d.axes.size() && !rc; ++i) {
+      const bool first = i == 0;
+      rc = add_axis(KIND_R2C, RL_HARTLEY, true, d.axes[i], (uint32_t)d.shape[d.axes[i]], d.shape,
+                    first ? d.stride_in : d.stride_out, rsz, d.stride_out, rsz, first ? BUF_IN : BUF_OUT, BUF_OUT, first);
+    }
+  } else if (d.kind == KIND_HARTLEY_GEN) {
+    // r2c over all axes into a contiguous temporary, then the fold (hdronly.h:3423-3444)
+    if (nd > (size_t)kMaxCombineDims) { *err = "too many dimensions"; return ERR_INVALID; }
+    std::vector<size_t> hs = d.shape;
+    hs[last] = d.shape[last] / 2 + 1;
+    std::vector<ptrdiff_t> st(nd);
+    st[nd - 1] = (ptrdiff_t)csz;
+    for (size_t i = nd - 1; i-- > 0;) st[i] = st[i + 1] * (ptrdiff_t)hs[i + 1];
+    size_t nval = 1;
+    for (size_t s : hs) nval *= s;
+    plan->tmp_bytes = nval * csz;
+    rc = add_axis(KIND_R2C, RL_HERMITIAN, true, last, (uint32_t)d.shape[last], d.shape, d.stride_in, rsz, st, csz, BUF_IN,
+                  BUF_TMP, true);
+    for (size_t i = 0; i + 1 < d.axes.size() && !rc; ++i)
+      rc = add_axis(KIND_C2C, RL_HERMITIAN, true, d.axes[i], (uint32_t)hs[d.axes[i]], hs, st, csz, st, csz, BUF_TMP, BUF_TMP,
+                    false);
+    if (!rc) {
+      Step fold;
+      fold.combine = true;
+      fold.src = BUF_TMP; fold.dst = BUF_OUT;
+      CombineJob &C = fold.cj;
+      C.in = nullptr; C.out = nullptr;
+      C.dtype = d.dtype; C.ndim = (int)nd; C.half_axis = (uint32_t)last; C.total = nval;
+      for (size_t i = 0; i < nd; ++i) {
+        C.hshape[i] = (uint32_t)hs[i]; C.full[i] = (uint32_t)d.shape[i]; C.rev[i] = 0;
+        C.so[i] = d.stride_out[i] / (ptrdiff_t)rsz;
+      }
+      for (size_t ax : d.axes) C.rev[ax] = 1;
+      plan->steps.push_back(fold);
     }
   } else if (nd_r2r) {
     // general_nd with ExecDcst (hdronly.h:3105-3121): every axis is the same 1-D transform, fct once

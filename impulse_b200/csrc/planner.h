@@ -27,9 +27,19 @@ struct TableAlloc {
   virtual void release(void *dev) = 0;
 };
 
-enum Kind : int { KIND_C2C = 0, KIND_R2C = 1, KIND_C2R = 2, KIND_DCT = 3, KIND_DST = 4 };
+enum Kind : int {
+  KIND_C2C = 0, KIND_R2C = 1, KIND_C2R = 2, KIND_DCT = 3, KIND_DST = 4,
+  KIND_FFTPACK = 5,       // r2r_fftpack: halfcomplex real transform on every axis (pocketfft_hdronly.h:3392-3403)
+  KIND_HARTLEY_SEP = 6,   // r2r_separable_hartley                               (pocketfft_hdronly.h:3405-3415)
+  KIND_HARTLEY_GEN = 7,   // r2r_genuine_hartley                                 (pocketfft_hdronly.h:3417-3445)
+};
 enum DType : int { DT_F32 = 0, DT_F64 = 1 };
-enum RealLayout : int { RL_HERMITIAN = 0, RL_HALFCOMPLEX = 1, RL_FULLSYM = 2 };
+enum RealLayout : int {
+  RL_HERMITIAN = 0, RL_HALFCOMPLEX = 1, RL_FULLSYM = 2,
+  // internal (not part of the ABI): halfcomplex with elements 2,4,6,... of the REAL side negated, and the
+  // Hartley combination of an r2c result
+  RL_HALFCOMPLEX_NEG = 3, RL_HARTLEY = 4,
+};
 
 enum Status : int {
   ST_OK = 0,
@@ -81,6 +91,8 @@ struct Step {
   LaunchCfg cfg;
   int src = BUF_IN, dst = BUF_OUT;
   int64_t src_off_bytes = 0, dst_off_bytes = 0;  // host-looped outer dims
+  bool combine = false;     // not a line job: the genuine-Hartley fold `cj` (src/dst as usual)
+  CombineJob cj{};
   bool takes_umul = false;  // this step multiplies its output by the caller's array (impulse_fft_c2c_mul)
   bool takes_fct = false;  // the scaling factor is applied once, in these steps (hdronly.h:3048)
 };
@@ -93,6 +105,7 @@ struct NdDesc {
   std::vector<size_t> axes;
   int r2r_type = 2;  // DCT/DST only
   bool ortho = false;
+  bool real2hermitian = true;  // KIND_FFTPACK only
   uint64_t umul_mod = 0;  // c2c only: multiply the result by umul[offset % umul_mod]
 };
 

@@ -107,6 +107,41 @@ class DCTDesc:
         _lib.check(rc)
 
 
+def _r2r_real(fn_name, descOut: DataDesc, descIn: DataDesc, axes, fct, nthreads, extra=()):
+    L = _lib.lib()
+    if descIn.complex or descOut.complex:
+        raise TypeError("real-to-real transform")
+    if descIn.dtype != descOut.dtype:
+        raise TypeError("input and output precision differ")
+    nd, na = len(descIn.shape), len(axes)
+    if len(descIn.stride) != nd or len(descOut.stride) != nd:
+        raise _lib.FFTError(-2, "stride dimension mismatch")
+    if nd > _lib.MAX_DIMS or na > _lib.MAX_DIMS or any(int(a) < 0 for a in axes):
+        raise _lib.FFTError(-1, "bad axis number")
+    rc = getattr(L, fn_name)(descIn.dtype, nd, (C.c_size_t * nd)(*descIn.shape), (C.c_ssize_t * nd)(*descIn.stride),
+                             (C.c_ssize_t * nd)(*descOut.stride), na, (C.c_size_t * na)(*[int(a) for a in axes]), *extra,
+                             B.ptr(descIn.buf), B.ptr(descOut.buf), float(fct), int(nthreads),
+                             B.stream_of(descIn.buf, descOut.buf))
+    _lib.check(rc)
+
+
+def r2r_fftpack(descOut: DataDesc, descIn: DataDesc, axes, real2hermitian: bool, forward: bool, fct: float = 1.0,
+                nthreads: int = 1) -> None:
+    """`r2r_fftpack` (cpp_pocketfft/pocketfft.nim:71-82 -> pocketfft_hdronly.h:3392-3403): FFTPACK halfcomplex
+    real transform along every listed axis, in the given order."""
+    _r2r_real("impulse_fft_r2r_fftpack", descOut, descIn, axes, fct, nthreads, (int(bool(real2hermitian)), int(bool(forward))))
+
+
+def r2r_separable_hartley(descOut: DataDesc, descIn: DataDesc, axes, fct: float = 1.0, nthreads: int = 1) -> None:
+    """`r2r_separable_hartley` (pocketfft.nim:84-94 -> pocketfft_hdronly.h:3405-3415)."""
+    _r2r_real("impulse_fft_r2r_separable_hartley", descOut, descIn, axes, fct, nthreads)
+
+
+def r2r_genuine_hartley(descOut: DataDesc, descIn: DataDesc, axes, fct: float = 1.0, nthreads: int = 1) -> None:
+    """`r2r_genuine_hartley` (pocketfft.nim:96-106 -> pocketfft_hdronly.h:3417-3445)."""
+    _r2r_real("impulse_fft_r2r_genuine_hartley", descOut, descIn, axes, fct, nthreads)
+
+
 def apply(fft, descOut: DataDesc, descIn: DataDesc) -> None:
     if isinstance(fft, DCTDesc):
         return fft.apply(descOut, descIn)

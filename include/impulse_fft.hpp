@@ -245,4 +245,25 @@ template <typename T> struct DCTDesc {
   }
 };
 
+// r2r_fftpack / r2r_separable_hartley / r2r_genuine_hartley (NX:71-106): the reference imports them but
+// no descriptor reaches them; free functions over DataDesc here
+template <typename T>
+void r2r_fftpack(DataDesc<T> &descOut, const DataDesc<T> &descIn, const std::vector<std::size_t> &axes, bool real2hermitian,
+                 bool forward, T fct = 1, unsigned nthreads = 1, void *stream = nullptr) {
+  constexpr int dtype = std::is_same<T, float>::value ? IMPULSE_FFT_F32 : IMPULSE_FFT_F64;
+  const int rc = impulse_fft_r2r_fftpack(dtype, descIn.shape.size(), descIn.shape.data(), descIn.stride.data(),
+                                         descOut.stride.data(), axes.size(), axes.data(), real2hermitian, forward, descIn.buf,
+                                         descOut.buf, double(fct), nthreads, stream);
+  if (rc != 0) throw std::runtime_error(std::string("impulse_fft_b200: ") + impulse_fft_last_error());
+}
+template <typename T>
+void r2r_hartley(DataDesc<T> &descOut, const DataDesc<T> &descIn, const std::vector<std::size_t> &axes, bool genuine, T fct = 1,
+                 unsigned nthreads = 1, void *stream = nullptr) {
+  constexpr int dtype = std::is_same<T, float>::value ? IMPULSE_FFT_F32 : IMPULSE_FFT_F64;
+  auto fn = genuine ? impulse_fft_r2r_genuine_hartley : impulse_fft_r2r_separable_hartley;
+  const int rc = fn(dtype, descIn.shape.size(), descIn.shape.data(), descIn.stride.data(), descOut.stride.data(), axes.size(),
+                    axes.data(), descIn.buf, descOut.buf, double(fct), nthreads, stream);
+  if (rc != 0) throw std::runtime_error(std::string("impulse_fft_b200: ") + impulse_fft_last_error());
+}
+
 }  // namespace impulse

@@ -95,6 +95,24 @@ int impulse_fft_c2r(int dtype, size_t ndim, const size_t *shape_out, const ptrdi
                     const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward,
                     const void *data_in, void *data_out, double fct, size_t nthreads, void *stream);
 
+/* FFTPACK halfcomplex real transforms on every listed axis, and the two Hartley transforms: the
+ * flattened argument lists of pocketfft::r2r_fftpack / r2r_separable_hartley / r2r_genuine_hartley
+ * (pocketfft_hdronly.h:3392-3445; imported at impulse/fft/cpp_pocketfft/pocketfft.nim:71-106).  All arrays
+ * are real with the same shape; strides in bytes.  Hartley sign convention as the reference: out[k] =
+ * Re F[k] + Im F[k] with F the FORWARD transform.  r2r_fftpack follows the vendored engine exactly: the
+ * direction of the real transform is chosen by `forward` (true: real -> halfcomplex, false: halfcomplex ->
+ * real); when real2hermitian != forward, elements 2, 4, 6, ... along the axis change sign (on the output
+ * for real2hermitian, on the input otherwise), as pocketfft_hdronly.h:3134-3140 computes it. */
+int impulse_fft_r2r_fftpack(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                            const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int real2hermitian, int forward,
+                            const void *data_in, void *data_out, double fct, size_t nthreads, void *stream);
+int impulse_fft_r2r_separable_hartley(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                                      const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, const void *data_in,
+                                      void *data_out, double fct, size_t nthreads, void *stream);
+int impulse_fft_r2r_genuine_hartley(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                                    const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, const void *data_in,
+                                    void *data_out, double fct, size_t nthreads, void *stream);
+
 /* impulse_fft_c2c with a pointwise multiply fused into the store of the last pass: the output element at
  * element offset o of the (dense) output array is multiplied by mul[o % mul_elems] — mul_elems = the
  * size of one image broadcasts one filter spectrum over a batch.  This is the FFT -> multiply half of an

@@ -72,6 +72,10 @@ class Ref:
             f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_double, C.c_int, C.c_int]
         L.ref_last_error.restype = C.c_char_p
         L.ref_hardware_threads.restype = C.c_uint
+        if hasattr(L, "ref_r2r_real"):
+            L.ref_r2r_real.restype = C.c_int
+            L.ref_r2r_real.argtypes = [C.c_int, C.c_int, C.c_size_t, _size_p, _ssize_p, _ssize_p, C.c_size_t, _size_p, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_size_t]
         if hasattr(L, "ref_r2r"):
             L.ref_r2r.restype = C.c_int
             L.ref_r2r.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, _size_p, _ssize_p, _ssize_p, C.c_size_t,
@@ -149,6 +153,20 @@ class Ref:
                               _arr(list(a.shape), C.c_size_t), _arr(list(a.strides), C.c_ssize_t),
                               _arr(list(out.strides), C.c_ssize_t), len(axes), _arr(list(axes), C.c_size_t),
                               a.ctypes.data, out.ctypes.data, float(fct), nthreads)
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return out
+
+
+    def r2r_real(self, which, a, axes, real2hermitian=True, forward=True, fct=1.0, out=None, nthreads=1):
+        """pocketfft::r2r_fftpack ('fftpack') / r2r_separable_hartley / r2r_genuine_hartley."""
+        w = {"fftpack": 0, "separable_hartley": 1, "genuine_hartley": 2}[which]
+        out = np.empty_like(a) if out is None else out
+        nd = a.ndim
+        rc = self.lib.ref_r2r_real(w, 1 if a.dtype == np.float64 else 0, nd, _arr(list(a.shape), C.c_size_t),
+                                   _arr(list(a.strides), C.c_ssize_t), _arr(list(out.strides), C.c_ssize_t), len(axes),
+                                   _arr(list(axes), C.c_size_t), int(real2hermitian), int(forward), a.ctypes.data,
+                                   out.ctypes.data, float(fct), nthreads)
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return out
@@ -365,3 +383,62 @@ def max_row_rel_l2(a, b) -> float:
     den = np.sum(np.abs(b) ** 2, axis=1)
     den = np.where(den == 0, 1.0, den)
     return float(np.sqrt(np.max(num / den)))
+
+
+# ---- numpy restatements of the real-to-real FFTPACK / Hartley entry points -------------------------
+def _halfcomplex_pack(spec, n):
+    """N/2+1 complex bins (last axis) -> FFTPACK halfcomplex reals [R0, R1, I1, ..., (R_{N/2})]."""
+    out = np.empty(spec.shape[:-1] + (n,), dtype=np.float64)
+    out[..., 0] = spec[..., 0].real
+    m = (n - 1) // 2
+    out[..., 1:2 * m + 1:2] = spec[..., 1:m + 1].real
+    out[..., 2:2 * m + 2:2] = spec[..., 1:m + 1].imag
+    if n % 2 == 0:
+        out[..., n - 1] = spec[..., n // 2].real
+    return out
+
+
+def _halfcomplex_unpack(x):
+    n = x.shape[-1]
+    spec = np.zeros(x.shape[:-1] + (n // 2 + 1,), dtype=np.complex128)
+    spec[..., 0] = x[..., 0]
+    m = (n - 1) // 2
+    spec[..., 1:m + 1] = x[..., 1:2 * m + 1:2] + 1j * x[..., 2:2 * m + 2:2]
+    if n % 2 == 0:
+        spec[..., n // 2] = x[..., n - 1]
+    return spec
+
+
+def fftpack_numpy(a, axes, real2hermitian=True, forward=True, fct=1.0):
+    """r2r_fftpack as the VENDORED header computes it (ExecR2R, pocketfft_hdronly.h:3123-3143): the 1-D plan
+    is executed with r2hc = `forward`; (not real2hermitian) and forward negates elements 2,4,.. of the
+    input, real2hermitian and (not forward) negates them on the output.  Axes in the given order, fct once."""
+    x = np.array(a, dtype=np.float64, copy=True)
+    for i, ax in enumerate(axes):
+        x = np.moveaxis(x, ax, -1).copy()
+        n = x.shape[-1]
+        if (not real2hermitian) and forward:
+            x[..., 2::2] *= -1.0
+        if forward:
+            x = _halfcomplex_pack(np.fft.rfft(x, axis=-1), n)
+        else:
+            x = np.fft.irfft(_halfcomplex_unpack(x), n=n, axis=-1) * n
+        if real2hermitian and not forward:
+            x[..., 2::2] *= -1.0
+        if i == 0:
+            x = x * fct
+        x = np.moveaxis(x, -1, ax)
+    return np.ascontiguousarray(x)
+
+
+def hartley_numpy(a, axes, genuine=False, fct=1.0):
+    """r2r_separable_hartley / r2r_genuine_hartley (pocketfft_hdronly.h:3066-3103, 3405-3445): Re + Im of
+    the forward transform, per axis (separable) or of the N-D transform (genuine)."""
+    x = np.array(a, dtype=np.float64, copy=True)
+    if genuine:
+        f = np.fft.fftn(x, axes=axes)
+        return (f.real + f.imag) * fct
+    for ax in axes:
+        f = np.fft.fft(x, axis=ax)
+        x = f.real + f.imag
+    return x * fct

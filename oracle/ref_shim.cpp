@@ -124,6 +124,28 @@ int ref_r2r(int cosine, int type, int ortho, int dtype, size_t ndim, const size_
   });
 }
 
+// r2r_fftpack (which = 0), r2r_separable_hartley (1), r2r_genuine_hartley (2)  (pocketfft_hdronly.h:3392-3445)
+int ref_r2r_real(int which, int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                 const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int real2hermitian, int forward,
+                 const void *in, void *out, double fct, size_t nthreads) {
+  return guarded([&] {
+    auto sh = mk_shape(shape, ndim);
+    auto si = mk_stride(stride_in, ndim), so = mk_stride(stride_out, ndim);
+    auto ax = mk_shape(axes, naxes);
+    if (dtype == 1) {
+      const double *i = (const double *)in; double *o = (double *)out;
+      if (which == 0) pocketfft::r2r_fftpack<double>(sh, si, so, ax, real2hermitian != 0, forward != 0, i, o, fct, nthreads);
+      else if (which == 1) pocketfft::r2r_separable_hartley<double>(sh, si, so, ax, i, o, fct, nthreads);
+      else pocketfft::r2r_genuine_hartley<double>(sh, si, so, ax, i, o, fct, nthreads);
+    } else {
+      const float *i = (const float *)in; float *o = (float *)out;
+      if (which == 0) pocketfft::r2r_fftpack<float>(sh, si, so, ax, real2hermitian != 0, forward != 0, i, o, (float)fct, nthreads);
+      else if (which == 1) pocketfft::r2r_separable_hartley<float>(sh, si, so, ax, i, o, (float)fct, nthreads);
+      else pocketfft::r2r_genuine_hartley<float>(sh, si, so, ax, i, o, (float)fct, nthreads);
+    }
+  });
+}
+
 // Row drivers over the reference C engine: `nrows` contiguous rows transformed in
 // place, one plan shared by `nthreads` threads.  plan_per_row != 0 reproduces what
 // the Nim wrapper does (a fresh plan per call, c_pocketfft/pocketfft.nim:285,300).

@@ -49,7 +49,8 @@ const char *emu_last_error() { return g_err.c_str(); }
 // mirrors impulse_fft_nd() of the product ABI, on host memory
 static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
                        const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
-                       void *out, double fct, int r2r_type, int ortho, const void *umul = nullptr, size_t umul_mod = 0);
+                       void *out, double fct, int r2r_type, int ortho, const void *umul = nullptr, size_t umul_mod = 0,
+                       int real2hermitian = 1);
 
 int emu_nd(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
            const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
@@ -65,6 +66,14 @@ int emu_c2c_mul(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *st
                      2, 0, mul, mul_elems);
 }
 
+// mirrors impulse_fft_r2r_fftpack (which = 0), _separable_hartley (1), _genuine_hartley (2)
+int emu_r2r_real(int which, int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in, const ptrdiff_t *stride_out,
+                 size_t naxes, const size_t *axes, int real2hermitian, int forward, const void *in, void *out, double fct) {
+  const int kind = which == 0 ? KIND_FFTPACK : which == 1 ? KIND_HARTLEY_SEP : KIND_HARTLEY_GEN;
+  return emu_nd_impl(kind, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, which == 0 ? forward : 1, in,
+                     out, fct, 2, 0, nullptr, 0, real2hermitian);
+}
+
 // DCT (cosine != 0) / DST of type 1..4, mirrors impulse_fft_dct / impulse_fft_dst
 int emu_r2r(int cosine, int type, int ortho, int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
             const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, const void *in, void *out, double fct) {
@@ -74,11 +83,13 @@ int emu_r2r(int cosine, int type, int ortho, int dtype, size_t ndim, const size_
 
 static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
                        const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
-                       void *out, double fct, int r2r_type, int ortho, const void *umul, size_t umul_mod) {
+                       void *out, double fct, int r2r_type, int ortho, const void *umul, size_t umul_mod,
+                       int real2hermitian) {
   if (!g_cache) g_cache = new PlanCache(&g_alloc);
   NdDesc d;
   d.r2r_type = r2r_type; d.ortho = ortho != 0;
   d.umul_mod = umul_mod;
+  d.real2hermitian = real2hermitian != 0;
   d.kind = kind; d.dtype = dtype; d.layout = layout; d.forward = forward != 0;
   d.shape.assign(shape, shape + ndim);
   d.stride_in.assign(stride_in, stride_in + ndim);
@@ -92,6 +103,15 @@ static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_
   for (Step &st : plan.steps) {
     const unsigned char *bufs_in[5] = {(const unsigned char *)in, (const unsigned char *)out, tmp.data(), tmp2.data(), tmp3.data()};
     unsigned char *bufs_out[5] = {nullptr, (unsigned char *)out, tmp.data(), tmp2.data(), tmp3.data()};
+    if (st.combine) {
+      CombineJob cj = st.cj;
+      cj.in = bufs_in[st.src] + st.src_off_bytes;
+      cj.out = bufs_out[st.dst] + st.dst_off_bytes;
+      for (uint64_t g = 0; g < cj.total; ++g) {
+        if (dtype == DT_F64) hartley_combine_one<double>(cj, g); else hartley_combine_one<float>(cj, g);
+      }
+      continue;
+    }
     st.job.in = bufs_in[st.src] + st.src_off_bytes;
     st.job.out = bufs_out[st.dst] + st.dst_off_bytes;
     st.job.fct = st.takes_fct ? fct : 1.0;

@@ -81,6 +81,23 @@ def c2c_mul(a_in, a_out, axes, mul, forward=True, fct=1.0):
     return a_out
 
 
+def r2r_real(which, a_in, a_out, axes, real2hermitian=True, forward=True, fct=1.0):
+    """which: 'fftpack' | 'separable_hartley' | 'genuine_hartley' (mirrors the impulse_fft_r2r_* entry points)."""
+    L = lib()
+    L.emu_r2r_real.restype = C.c_int
+    L.emu_r2r_real.argtypes = [C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_ssize_t), C.POINTER(C.c_ssize_t),
+                               C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
+    w = {"fftpack": 0, "separable_hartley": 1, "genuine_hartley": 2}[which]
+    dt = 1 if a_in.dtype == np.float64 else 0
+    n = a_in.ndim
+    rc = L.emu_r2r_real(w, dt, n, (C.c_size_t * n)(*a_in.shape), (C.c_ssize_t * n)(*a_in.strides),
+                        (C.c_ssize_t * n)(*a_out.strides), len(axes), (C.c_size_t * len(axes))(*axes), int(real2hermitian),
+                        int(forward), a_in.ctypes.data, a_out.ctypes.data, fct)
+    if rc:
+        raise EmuError(rc, L.emu_last_error().decode())
+    return a_out
+
+
 def r2r(cosine, type_, a_in, a_out, axes, fct=1.0, ortho=False):
     L = lib()
     if not hasattr(L, "_r2r_bound"):

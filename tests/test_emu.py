@@ -308,3 +308,41 @@ def test_c2c_fused_multiply(shape, axes, period, forward):
     want = (want.reshape(-1, period) * m).reshape(shape)
     got = emu.c2c_mul(x, np.empty_like(x), axes, m, forward=forward)
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+
+
+R2R_REAL_CASES = [((7,), [0]), ((8,), [0]), ((1,), [0]), ((2,), [0]), ((3, 10), [1]), ((6, 9), [0, 1]), ((4, 5, 6), [2, 0]),
+                  ((2, 191), [1]), ((3, 1000), [1]), ((2, 4099), [1]), ((40, 24), [0]), ((12, 16, 10), [0, 1, 2])]
+
+
+@pytest.mark.parametrize("shape,axes", R2R_REAL_CASES)
+def test_r2r_fftpack(shape, axes):
+    """impulse_fft_r2r_fftpack against the (reference-pinned) restatement, all four flag combinations."""
+    rng = np.random.default_rng(23)
+    a = rng.standard_normal(shape)
+    for r2h in (True, False):
+        for fwd in (True, False):
+            want = oracle.fftpack_numpy(a, axes, r2h, fwd, 0.25)
+            got = emu.r2r_real("fftpack", a, np.empty_like(a), axes, r2h, fwd, 0.25)
+            assert oracle.rel_l2(got, want) < 2e-14, (r2h, fwd)
+    b = a.copy()                                    # in place
+    emu.r2r_real("fftpack", b, b, axes, True, True, 1.0)
+    assert oracle.rel_l2(b, oracle.fftpack_numpy(a, axes, True, True, 1.0)) < 2e-14
+
+
+@pytest.mark.parametrize("shape,axes", R2R_REAL_CASES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_hartley(shape, axes, dtype):
+    rng = np.random.default_rng(29)
+    a = rng.standard_normal(shape).astype(dtype)
+    tol = 2e-14 if dtype == np.float64 else 2e-5
+    for which, genuine in (("separable_hartley", False), ("genuine_hartley", True)):
+        want = oracle.hartley_numpy(a, axes, genuine, 0.5)
+        got = emu.r2r_real(which, a, np.empty_like(a), axes, fct=0.5)
+        assert oracle.rel_l2(got.astype(np.float64), want) < tol, which
+    # strided output, non-contiguous input
+    big = rng.standard_normal(tuple(2 * s for s in shape)).astype(dtype)
+    view = big[tuple(slice(None, None, 2) for _ in shape)]
+    out = np.zeros_like(big)
+    oview = out[tuple(slice(None, None, 2) for _ in shape)]
+    emu.r2r_real("genuine_hartley", view, oview, axes)
+    assert oracle.rel_l2(oview.astype(np.float64), oracle.hartley_numpy(view, axes, True)) < tol

@@ -654,3 +654,42 @@ def test_c2c_fused_multiply(ib, torch_mod, checker):
     rc = L.impulse_fft_c2c_mul(_lib.F64, 2, (C.c_size_t * 2)(4, 8), st, st, 1, (C.c_size_t * 1)(1), 1, x.ctypes.data,
                                x.ctypes.data, 1.0, x.ctypes.data, 8, None)
     assert rc == -1  # IMPULSE_FFT_ERR_INVALID
+
+
+def test_fftpack_and_hartley(ib, torch_mod, ref):
+    """impulse_fft_r2r_fftpack / _separable_hartley / _genuine_hartley against the compiled reference
+    (pocketfft_hdronly.h:3392-3445): 1-D and N-D, both precisions, all four fftpack flag combinations,
+    Bluestein lengths, in place, host buffers."""
+    rng = np.random.default_rng(91)
+    cases = [((7,), [0]), ((8,), [0]), ((1,), [0]), ((3, 10), [1]), ((6, 9), [0, 1]), ((4, 5, 6), [2, 0]), ((2, 191), [1]),
+             ((64, 1000), [1]), ((16, 4099), [1]), ((512, 24), [0]), ((12, 16, 10), [0, 1, 2]), ((8, 4096), [1]),
+             ((256, 256), [0, 1])]
+    for dt in (np.float64, np.float32):
+        for shape, axes in cases:
+            a = rng.standard_normal(shape).astype(dt)
+            ad = torch_mod.from_numpy(a).cuda()
+            big = max(shape[x] for x in axes)
+            t = tol(max(big, 2), dt) * len(axes)
+            for r2h in (True, False):
+                for fwd in (True, False):
+                    out = torch_mod.empty_like(ad)
+                    ib.r2r_fftpack(ib.DataDesc.init(out), ib.DataDesc.init(ad), axes, r2h, fwd, 0.25)
+                    want = ref.r2r_real("fftpack", a, axes, r2h, fwd, 0.25)
+                    assert oracle.rel_l2(out.cpu().numpy(), want) <= t, (shape, axes, r2h, fwd, dt)
+            for name, fn in (("separable_hartley", ib.r2r_separable_hartley), ("genuine_hartley", ib.r2r_genuine_hartley)):
+                out = torch_mod.empty_like(ad)
+                fn(ib.DataDesc.init(out), ib.DataDesc.init(ad), axes, 0.5)
+                want = ref.r2r_real(name, a, axes, fct=0.5)
+                assert oracle.rel_l2(out.cpu().numpy(), want) <= t, (shape, axes, name, dt)
+            inpl = ad.clone()                                       # in place
+            ib.r2r_separable_hartley(ib.DataDesc.init(inpl), ib.DataDesc.init(inpl), axes)
+            assert oracle.rel_l2(inpl.cpu().numpy(), ref.r2r_real("separable_hartley", a, axes)) <= t
+            host = np.empty_like(a)                                 # host buffers are staged
+            ib.r2r_genuine_hartley(ib.DataDesc.init(host), ib.DataDesc.init(a), axes)
+            assert oracle.rel_l2(host, ref.r2r_real("genuine_hartley", a, axes)) <= t
+    # Hartley is an involution up to 1/N (size-independent property at a full-size image)
+    img = torch_mod.rand((2048, 2048), device="cuda", dtype=torch_mod.float64)
+    h1, h2 = torch_mod.empty_like(img), torch_mod.empty_like(img)
+    ib.r2r_genuine_hartley(ib.DataDesc.init(h1), ib.DataDesc.init(img), [0, 1])
+    ib.r2r_genuine_hartley(ib.DataDesc.init(h2), ib.DataDesc.init(h1), [0, 1], 1.0 / (2048 * 2048))
+    assert float(torch_mod.linalg.vector_norm(h2 - img) / torch_mod.linalg.vector_norm(img)) <= 1e-13

@@ -214,3 +214,25 @@ def test_dct_dst_conventions(ref):
     d = ref.r2r(True, 2, np.array([[4.0, 3.0, 5.0, 10.0]]), [1], 1.0, False)[0]
     np.testing.assert_allclose(d, oracle.r2r_direct(True, 2, np.array([4.0, 3.0, 5.0, 10.0])), rtol=1e-14)
     assert abs(d[0] - 44.0) < 1e-13   # 2 * sum(x)
+
+
+def test_fftpack_and_hartley_conventions(ref):
+    """Pin the numpy restatements of r2r_fftpack / r2r_separable_hartley / r2r_genuine_hartley against the
+    compiled reference (pocketfft_hdronly.h:3392-3445), including the mixed real2hermitian/forward cases
+    that the vendored header computes in its own way."""
+    rng = np.random.default_rng(17)
+    for shape, axes in (((7,), [0]), ((8,), [0]), ((3, 10), [1]), ((6, 9), [0, 1]), ((4, 5, 6), [2, 0]), ((2, 191), [1])):
+        a = rng.standard_normal(shape)
+        for r2h in (True, False):
+            for fwd in (True, False):
+                got = oracle.fftpack_numpy(a, axes, r2h, fwd, 0.5)
+                want = ref.r2r_real("fftpack", a, axes, r2h, fwd, 0.5)
+                assert oracle.rel_l2(got, want) < 1e-14, (shape, axes, r2h, fwd)
+        for which, genuine in (("separable_hartley", False), ("genuine_hartley", True)):
+            got = oracle.hartley_numpy(a, axes, genuine, 2.0)
+            want = ref.r2r_real(which, a, axes, fct=2.0)
+            assert oracle.rel_l2(got, want) < 1e-14, (shape, axes, which)
+    # a Hartley transform is its own inverse up to 1/N
+    a = rng.standard_normal((5, 12))
+    back = ref.r2r_real("genuine_hartley", ref.r2r_real("genuine_hartley", a, [0, 1]), [0, 1], fct=1.0 / 60)
+    assert oracle.rel_l2(back, a) < 1e-14
