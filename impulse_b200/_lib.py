@@ -45,7 +45,7 @@ class PlanInfo(C.Structure):
 EXPORTS = [
     # include/impulse_fft_b200.h
     "impulse_fft_plan_create", "impulse_fft_plan_destroy", "impulse_fft_execute", "impulse_fft_c2c",
-    "impulse_fft_r2c", "impulse_fft_c2r", "impulse_fft_dct", "impulse_fft_dst", "impulse_fft_c2c_mul",
+    "impulse_fft_r2c", "impulse_fft_c2r", "impulse_fft_dct", "impulse_fft_dst", "impulse_fft_c2c_mul", "impulse_fft_convolve_axis",
     "impulse_fft_r2r_fftpack", "impulse_fft_r2r_separable_hartley", "impulse_fft_r2r_genuine_hartley", "impulse_fft_cfft_rows", "impulse_fft_rfft_rows",
     "impulse_fft_plan_get_info", "impulse_fft_launch_count", "impulse_fft_last_error", "impulse_fft_version",
     "impulse_fft_last_kernel",
@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
         f.argtypes = [C.c_int, C.c_size_t, sp, ssp, ssp, C.c_size_t, sp, C.c_int, vp, vp, C.c_double, C.c_size_t, vp]
     L.impulse_fft_c2c_mul.restype = C.c_int
     L.impulse_fft_c2c_mul.argtypes = [C.c_int, C.c_size_t, sp, ssp, ssp, C.c_size_t, sp, C.c_int, vp, vp, C.c_double, vp, C.c_size_t, vp]
+    L.impulse_fft_convolve_axis.restype = C.c_int
+    L.impulse_fft_convolve_axis.argtypes = [C.c_int, C.c_size_t, sp, ssp, ssp, C.c_size_t, vp, vp, C.c_double, vp, C.c_size_t, vp]
     L.impulse_fft_r2r_fftpack.restype = C.c_int
     L.impulse_fft_r2r_fftpack.argtypes = [C.c_int, C.c_size_t, sp, ssp, ssp, C.c_size_t, sp, C.c_int, C.c_int, vp, vp, C.c_double,
                                           C.c_size_t, vp]

@@ -139,7 +139,7 @@ namespace {
 size_t side_align(const NdDesc &d, bool input) {
   const size_t r = d.dtype == DT_F64 ? 8 : 4;
   bool real_side;
-  const bool r2r = d.kind >= KIND_DCT;  // DCT, DST, FFTPACK, Hartley: real on both sides
+  const bool r2r = d.kind >= KIND_DCT && d.kind <= KIND_HARTLEY_GEN;  // DCT, DST, FFTPACK, Hartley: real on both sides
   if (input) real_side = r2r || d.kind == KIND_R2C || (d.kind == KIND_C2R && d.layout == RL_HALFCOMPLEX);
   else real_side = r2r || d.kind == KIND_C2R || (d.kind == KIND_R2C && d.layout == RL_HALFCOMPLEX);
   return real_side ? r : 2 * r;
@@ -151,7 +151,7 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
   if (nd.empty) return 0;
   if (((uintptr_t)in % p->in_esz) || ((uintptr_t)out % p->out_esz))
     return fail(IMPULSE_FFT_ERR_STRIDE, "data pointer is not aligned to its element size");
-  if (in == out && (nd.desc.kind == KIND_C2C || nd.desc.kind >= KIND_DCT) &&
+  if (in == out && (nd.desc.kind == KIND_C2C || (nd.desc.kind >= KIND_DCT && nd.desc.kind <= KIND_HARTLEY_GEN)) &&
       nd.desc.stride_in != nd.desc.stride_out)
     return fail(IMPULSE_FFT_ERR_STRIDE, "stride mismatch");  // hdronly.h:455-456
   void *tmp = nullptr, *tmp2 = nullptr, *tmp3 = nullptr;
@@ -344,9 +344,10 @@ struct OneShotKey {
   int dev, kind, dtype, layout, forward;  // for DCT/DST `layout` carries the type and `forward` the ortho flag
   std::vector<size_t> shape, axes;
   std::vector<ptrdiff_t> sin, sout;
+  uint64_t umul_mod = 0;
   bool operator<(const OneShotKey &o) const {
-    return std::tie(dev, kind, dtype, layout, forward, shape, axes, sin, sout) <
-           std::tie(o.dev, o.kind, o.dtype, o.layout, o.forward, o.shape, o.axes, o.sin, o.sout);
+    return std::tie(dev, kind, dtype, layout, forward, shape, axes, sin, sout, umul_mod) <
+           std::tie(o.dev, o.kind, o.dtype, o.layout, o.forward, o.shape, o.axes, o.sin, o.sout, o.umul_mod);
   }
 };
 std::mutex g_os_mu;
@@ -355,18 +356,20 @@ constexpr size_t kOneShotCap = 64;
 
 int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *sin,
              const ptrdiff_t *sout, size_t naxes, const size_t *axes, int forward, const void *in, void *out,
-             double fct, void *stream) {
+             double fct, void *stream, const void *umul = nullptr, uint64_t umul_mod = 0) {
   NdDesc d;
   // real-to-real kinds carry their own options in the `layout` / `forward` slots of this helper
-  const bool r2r = kind == KIND_DCT || kind == KIND_DST, fpk = kind == KIND_FFTPACK, hart = kind >= KIND_HARTLEY_SEP;
+  const bool r2r = kind == KIND_DCT || kind == KIND_DST, fpk = kind == KIND_FFTPACK,
+             hart = kind == KIND_HARTLEY_SEP || kind == KIND_HARTLEY_GEN;
   int rc = make_desc(&d, kind, dtype, (r2r || fpk || hart) ? RL_HERMITIAN : layout, (r2r || hart) ? 1 : forward, ndim, shape,
                      sin, sout, naxes, axes);
   if (rc) return rc;
   if (r2r) { d.r2r_type = layout; d.ortho = forward != 0; }
   if (fpk) d.real2hermitian = layout != 0;
+  d.umul_mod = umul_mod;
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }
-  OneShotKey key{dev, kind, dtype, layout, forward != 0, d.shape, d.axes, d.stride_in, d.stride_out};
+  OneShotKey key{dev, kind, dtype, layout, forward != 0, d.shape, d.axes, d.stride_in, d.stride_out, umul_mod};
   std::shared_ptr<impulse_fft_plan_s> plan;
   {
     std::lock_guard<std::mutex> lk(g_os_mu);
@@ -381,6 +384,13 @@ int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, 
     std::lock_guard<std::mutex> lk(g_os_mu);
     if (g_os.size() >= kOneShotCap) g_os.clear();  // plans are cheap to rebuild: tables stay cached per device
     g_os[key] = plan;
+  }
+  if (umul_mod) {  // fused-multiply plans: device pointers, dense output
+    if (!in || !out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
+    if (!is_device_ptr(in) || !is_device_ptr(out) || !is_device_ptr(umul))
+      return fail(IMPULSE_FFT_ERR_INVALID, "transforms with a fused multiply take device pointers");
+    if (!plan->nd.out_dense) return fail(IMPULSE_FFT_ERR_STRIDE, "the output of a fused multiply must be dense");
+    return run_device(plan.get(), in, out, fct, static_cast<cudaStream_t>(stream), umul);
   }
   return impulse_fft_execute(plan.get(), in, out, fct, stream);
 }
@@ -475,21 +485,23 @@ int impulse_fft_c2c_mul(int dtype, size_t ndim, const size_t *shape, const ptrdi
                         const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *data_in,
                         void *data_out, double fct, const void *mul, size_t mul_elems, void *stream) {
   if (!mul || !mul_elems) return fail(IMPULSE_FFT_ERR_INVALID, "null multiplier");
-  NdDesc d;
-  int rc = make_desc(&d, KIND_C2C, dtype, RL_HERMITIAN, forward, ndim, shape, stride_in, stride_out, naxes, axes);
-  if (rc) return rc;
-  d.umul_mod = mul_elems;
-  for (size_t i = 0; i < ndim; ++i)
+  if (!stride_out) return fail(IMPULSE_FFT_ERR_INVALID, "null descriptor array");
+  for (size_t i = 0; i < ndim && i < IMPULSE_FFT_MAX_DIMS; ++i)
     if (stride_out[i] <= 0) return fail(IMPULSE_FFT_ERR_STRIDE, "the output of a fused multiply needs positive strides");
-  if (!data_in || !data_out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
-  if (!is_device_ptr(data_in) || !is_device_ptr(data_out) || !is_device_ptr(mul))
-    return fail(IMPULSE_FFT_ERR_INVALID, "impulse_fft_c2c_mul takes device pointers");
-  impulse_fft_plan raw = nullptr;
-  rc = create_plan(&raw, d);
-  if (rc) return rc;
-  std::unique_ptr<impulse_fft_plan_s> plan(raw);
-  if (!plan->nd.out_dense) return fail(IMPULSE_FFT_ERR_STRIDE, "the output of a fused multiply must be dense");
-  return run_device(plan.get(), data_in, data_out, fct, static_cast<cudaStream_t>(stream), mul);
+  return one_shot(KIND_C2C, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, naxes, axes, forward, data_in, data_out, fct,
+                  stream, mul, mul_elems);
+}
+
+int impulse_fft_convolve_axis(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                              const ptrdiff_t *stride_out, size_t axis, const void *data_in, void *data_out, double fct,
+                              const void *mul, size_t mul_elems, void *stream) {
+  if (!mul || !mul_elems) return fail(IMPULSE_FFT_ERR_INVALID, "null multiplier");
+  if (!stride_out) return fail(IMPULSE_FFT_ERR_INVALID, "null descriptor array");
+  for (size_t i = 0; i < ndim && i < IMPULSE_FFT_MAX_DIMS; ++i)
+    if (stride_out[i] <= 0) return fail(IMPULSE_FFT_ERR_STRIDE, "the output of a fused multiply needs positive strides");
+  const size_t axes[1] = {axis};
+  return one_shot(KIND_CONV_AXIS, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, 1, axes, 1, data_in, data_out, fct,
+                  stream, mul, mul_elems);
 }
 
 int impulse_fft_dct(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,

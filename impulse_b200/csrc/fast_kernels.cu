@@ -741,6 +741,122 @@ int launch_colfast2(const LineJob &J, cudaStream_t s) {
 
 
 // =================================================================================================
+// Convolution along a strided axis, middle pass.  A length-N = N1*N2 convolution is
+//     IFFT_N( FFT_N(x) .* m ).
+// With the forward transform split as n = n1*N2 + n2 -> k = k1 + N1*k2 and the inverse split the
+// other way round (n = n1'*N1 + n2' -> k' = k1' + N2*k2'), bin k of the spectrum is element
+// (n1' = k2, n2' = k1) of the inverse's input: the N2 outputs of the forward transform's second pass
+// for one k1 ARE the inputs of one line of the inverse's first pass.  So per line (k1 fixed):
+//     N2-point forward FFT -> * m[k1 + N1*k2] -> N2-point inverse FFT -> * conj(W_N^(k1'*k1))
+// never leaves the SM, and the spectrum is neither written nor re-read: three passes over the data
+// instead of five (FFT pass A, this kernel, inverse pass B).  Layout and thread mapping as
+// colfast2_kernel; the multiplier is indexed by the element offset this kernel writes to.
+// =================================================================================================
+template <typename T, int R1, int R2, int LPC>
+__global__ void __launch_bounds__(LPC * R2)
+colconv2_kernel(const __grid_constant__ LineJob J) {
+  constexpr int N = R1 * R2, NB2 = R1 / R2;
+  static_assert(R1 % R2 == 0, "column two-pass shape");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *S0 = reinterpret_cast<cx<T> *>(smem_raw), *S1 = S0 + N * LPC;
+  const int u = threadIdx.x, line = u % LPC, i = u / LPC;
+  const uint64_t g0n = (J.bdim[0] + LPC - 1) / LPC;
+  const uint64_t i0 = ((uint64_t)blockIdx.x % g0n) * LPC, r = (uint64_t)blockIdx.x / g0n, i1 = r % J.bdim[1], i2 = r / J.bdim[1];
+  const bool valid = i0 + line < J.bdim[0];
+  const int64_t off_in = (int64_t)i0 + line + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
+  const int64_t off_out = (int64_t)i0 + line + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
+  const uint32_t twi = J.tw4_dim == 0 ? (uint32_t)i0 + line : J.tw4_dim == 1 ? (uint32_t)i1 : (uint32_t)i2;
+  const cx<T> *in = reinterpret_cast<const cx<T> *>(J.in) + off_in;
+  cx<T> *out = reinterpret_cast<cx<T> *>(J.out) + off_out;
+  const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);
+  const cx<T> *um = reinterpret_cast<const cx<T> *>(J.umul);
+  const uint64_t umul_off = (uint64_t)off_out % J.umul_mod;
+  cx<T> x[R1];
+#pragma unroll
+  for (int j = 0; j < R1; ++j) x[j] = valid ? in[(int64_t)(i + R2 * j) * J.es_in] : mk<T>((T)0, (T)0);
+  // ---- forward N-point FFT
+  RegFFT<T, R1>::run(x);
+#pragma unroll
+  for (int k = 1; k < R1; ++k) x[k] = cmul(x[k], __ldg(tw + i * k));
+#pragma unroll
+  for (int k = 0; k < R1; ++k) S0[(k * R2 + i) * LPC + line] = x[k];
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < NB2; ++m) {
+    const int k1 = i + R2 * m;
+    cx<T> y[R2];
+#pragma unroll
+    for (int j = 0; j < R2; ++j) y[j] = S0[(k1 * R2 + j) * LPC + line];
+    RegFFT<T, R2>::run(y);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) {
+      const int k = k1 + R1 * k2;
+      cx<T> v = y[k2];
+      if (valid) {
+        uint64_t o = umul_off + (uint64_t)((int64_t)k * J.es_out);
+        if (o >= J.umul_mod) o %= J.umul_mod;
+        v = cmul(v, __ldg(um + o));
+      }
+      v.y = -v.y;  // inverse = conj(FFT(conj(.)))
+      S1[k * LPC + line] = v;
+    }
+  }
+  __syncthreads();
+  // ---- inverse N-point FFT of the products
+#pragma unroll
+  for (int j = 0; j < R1; ++j) x[j] = S1[(i + R2 * j) * LPC + line];
+  RegFFT<T, R1>::run(x);
+#pragma unroll
+  for (int k = 1; k < R1; ++k) x[k] = cmul(x[k], __ldg(tw + i * k));
+#pragma unroll
+  for (int k = 0; k < R1; ++k) S0[(k * R2 + i) * LPC + line] = x[k];   // S0 is free: everyone passed the second barrier
+  __syncthreads();
+  const T f = (T)J.fct;
+#pragma unroll
+  for (int m = 0; m < NB2; ++m) {
+    const int k1 = i + R2 * m;
+    cx<T> y[R2];
+#pragma unroll
+    for (int j = 0; j < R2; ++j) y[j] = S0[(k1 * R2 + j) * LPC + line];
+    RegFFT<T, R2>::run(y);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) {
+      const int k = k1 + R1 * k2;
+      const uint32_t mm = (uint32_t)k * twi;   // four-step twiddle of the inverse's first pass (conjugated below)
+      const cx<T> w = cmul(__ldg(reinterpret_cast<const cx<T> *>(J.tw4_hi) + (mm >> J.tw4_shift)),
+                           __ldg(reinterpret_cast<const cx<T> *>(J.tw4_lo) + (mm & ((1u << J.tw4_shift) - 1))));
+      cx<T> v = cmul(y[k2], w);
+      v.x *= f;
+      v.y *= -f;
+      if (valid) out[(int64_t)k * J.es_out] = v;
+    }
+  }
+}
+
+namespace {
+template <typename T, int R1, int R2, int LPC>
+int launch_colconv2(const LineJob &J, cudaStream_t s) {
+  const size_t smem = 2 * sizeof(cx<T>) * (size_t)R1 * R2 * LPC;
+  auto k = colconv2_kernel<T, R1, R2, LPC>;
+  static PerDeviceFlag flag;
+  bool &configured = flag.here();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  if (!J.umul || !J.umul_mod || !J.tw4_n) return (int)cudaErrorInvalidValue;
+  const uint64_t groups = ((J.bdim[0] + LPC - 1) / LPC) * J.bdim[1] * J.bdim[2];
+  if (groups == 0 || groups > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+  k<<<(unsigned)groups, LPC * R2, smem, s>>>(J);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+
+
+// =================================================================================================
 // Fused Bluestein on the three-pass register core: chirp -> FFT(M) -> x FFT(b)/M -> inverse FFT(M)
 // -> chirp, the M-point work array never leaves the SM (registers + one shared buffer).
 //
@@ -1037,6 +1153,12 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FASTBLUE_2048_F64: g_last_kernel = "fastblue_kernel<double,16,16,8,E16>"; return launch_fastblue<double, 16, 16, 8, 16>(J, sm_count, s);
     case FASTBLUE_4096_F64: g_last_kernel = "fastblue_kernel<double,16,16,16,E16>"; return launch_fastblue<double, 16, 16, 16, 16>(J, sm_count, s);
     case FASTBLUE_8192_F64: g_last_kernel = "fastblue_kernel<double,16,16,32,E32>"; return launch_fastblue<double, 16, 16, 32, 32>(J, sm_count, s);
+    case COLCONV_32_F64: g_last_kernel = "colconv2_kernel<double,8,4,8>"; return launch_colconv2<double, 8, 4, 8>(J, s);
+    case COLCONV_64_F64: g_last_kernel = "colconv2_kernel<double,8,8,8>"; return launch_colconv2<double, 8, 8, 8>(J, s);
+    case COLCONV_128_F64: g_last_kernel = "colconv2_kernel<double,16,8,8>"; return launch_colconv2<double, 16, 8, 8>(J, s);
+    case COLCONV_32_F32: g_last_kernel = "colconv2_kernel<float,8,4,16>"; return launch_colconv2<float, 8, 4, 16>(J, s);
+    case COLCONV_64_F32: g_last_kernel = "colconv2_kernel<float,8,8,16>"; return launch_colconv2<float, 8, 8, 16>(J, s);
+    case COLCONV_128_F32: g_last_kernel = "colconv2_kernel<float,16,8,16>"; return launch_colconv2<float, 16, 8, 16>(J, s);
     case COL2_32_F64: g_last_kernel = "colfast2_kernel<double,8,4,8>"; return launch_colfast2<double, 8, 4, 8>(J, s);
     case COL2_512_F64: g_last_kernel = "colfast2_kernel<double,32,16,8>"; return launch_colfast2<double, 32, 16, 8>(J, s);
     case COL2_32_F32: g_last_kernel = "colfast2_kernel<float,8,4,16>"; return launch_colfast2<float, 8, 4, 16>(J, s);

@@ -111,6 +111,12 @@ enum FastId : uint32_t {
   FASTBLUE_2048_F64 = 23,
   FASTBLUE_4096_F64 = 24,
   FASTBLUE_8192_F64 = 25,
+  COLCONV_32_F64 = 26,   // fused middle pass of a convolution along a strided axis (colconv2_kernel)
+  COLCONV_64_F64 = 27,
+  COLCONV_128_F64 = 28,
+  COLCONV_32_F32 = 29,
+  COLCONV_64_F32 = 30,
+  COLCONV_128_F32 = 31,
 };
 
 struct Phase {

@@ -568,6 +568,18 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       case 256: J->fast_id = f64 ? COL2_256_F64 : COL2_256_F32; break;
       default: J->fast_id = f64 ? COL2_512_F64 : COL2_512_F32; break;
     }
+    if (s.conv_mid) {
+      J->fast_id = FAST_NONE;
+      if (s.tw4_n && s.umul_mod && J->tw4_dim < 3) {
+        if (N == 32) J->fast_id = f64 ? COLCONV_32_F64 : COLCONV_32_F32;
+        else if (N == 64) J->fast_id = f64 ? COLCONV_64_F64 : COLCONV_64_F32;
+        else if (N == 128) J->fast_id = f64 ? COLCONV_128_F64 : COLCONV_128_F32;
+      }
+    }
+  }
+  if (s.conv_mid && (J->fast_id < COLCONV_32_F64 || J->fast_id > COLCONV_128_F32)) {
+    *err = "no fused convolution kernel for this shape";
+    return ERR_UNSUPPORTED;
   }
   // fused Bluestein on the register core: complex Bluestein lengths up to 4104 points, and odd real
   // lengths in that range with two rows packed per complex line (Hermitian layout); contiguous rows
@@ -652,7 +664,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     }
   }
   if (d.dtype != DT_F32 && d.dtype != DT_F64) { *err = "bad dtype"; return ERR_INVALID; }
-  if (d.umul_mod && d.kind != KIND_C2C) { *err = "fused multiply is a c2c option"; return ERR_INVALID; }
+  if (d.umul_mod && d.kind != KIND_C2C && d.kind != KIND_CONV_AXIS) { *err = "fused multiply is a c2c option"; return ERR_INVALID; }
   if (d.layout != RL_HERMITIAN && d.axes.size() != 1) { *err = "packed/symmetric real layouts are 1-axis only"; return ERR_INVALID; }
   size_t total = 1;
   for (size_t s : d.shape) total *= s;
@@ -692,7 +704,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
                   std::vector<Dim> dims, int tw_key /*index into dims of the line-index dim, -1 = none*/, uint32_t tw4_n,
                   const void *mul_tab, uint32_t mul_stride, int blue_stage,
                   size_t esz_in, size_t esz_out, int src, int dst, int64_t src_base, int64_t dst_base,
-                  bool takes_fct, uint64_t umul_mod = 0) -> int {
+                  bool takes_fct, uint64_t umul_mod = 0, bool conv_mid = false) -> int {
     std::vector<int> key(dims.size());
     for (size_t i = 0; i < dims.size(); ++i) key[i] = (int)i;
     std::vector<size_t> order(dims.size());
@@ -744,6 +756,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     s.mul_tab = mul_tab;
     s.mul_stride = mul_stride;
     s.umul_mod = umul_mod;
+    s.conv_mid = conv_mid;
     s.blue_stage = blue_stage;
     s.r2r_type = d.r2r_type;
     s.ortho = d.ortho;
@@ -891,6 +904,47 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       rc = add_axis(KIND_C2C, RL_HERMITIAN, d.forward, d.axes[i], (uint32_t)d.shape[d.axes[i]], d.shape,
                     first ? d.stride_in : d.stride_out, csz, d.stride_out, csz,
                     first ? BUF_IN : BUF_OUT, BUF_OUT, first, lastax ? d.umul_mod : 0);
+    }
+  } else if (d.kind == KIND_CONV_AXIS) {
+    // out = fct * IFFT_axis(FFT_axis(in) .* m[offset % umul_mod]) over one axis of a complex array
+    if (d.axes.size() != 1 || !d.umul_mod) { *err = "axis convolution takes one axis and a multiplier"; return ERR_INVALID; }
+    const size_t ax = d.axes[0];
+    const uint32_t N = (uint32_t)d.shape[ax];
+    std::vector<Dim> dims;
+    for (size_t i = 0; i < nd; ++i)
+      if (i != ax && d.shape[i] != 1) dims.push_back({d.shape[i], d.stride_in[i] / (ptrdiff_t)csz, d.stride_out[i] / (ptrdiff_t)csz});
+    const int64_t es = d.stride_out[ax] / (ptrdiff_t)csz;
+    bool fused = false;
+    uint32_t N1 = 1;
+    for (uint32_t f = 1; (uint64_t)f * f <= N; ++f) if (N % f == 0) N1 = f;
+    const uint32_t N2 = N / N1;
+    if (allow_conv_fusion && d.stride_in == d.stride_out && plan->out_dense && plan->out_lo == 0 && es > 1 && N1 >= 32 &&
+        !env_int("IMPULSE_FFT_NO_CONV_FUSION", 0)) {
+      // three passes through two scratch arrays that mirror the array's own layout (see colconv2_kernel)
+      const size_t n0 = plan->steps.size();
+      const size_t span = (size_t)(plan->out_hi - plan->out_lo);
+      plan->tmp2_bytes = std::max(plan->tmp2_bytes, span);
+      plan->tmp3_bytes = std::max(plan->tmp3_bytes, span);
+      std::vector<Dim> da, dm, db;
+      da.push_back({N2, es, es});                                   // A: FFT over n1 for every n2, times W_N^(k1*n2)
+      dm.push_back({N1, es * (int64_t)N2, es});                     // middle: line k1 <- row block k1, -> rows k1' * N1 + k1
+      db.push_back({N2, es * (int64_t)N1, es});                     // B': FFT over n2' for every k1'
+      for (auto &x : dims) { da.push_back({x.n, x.sout, x.sout}); dm.push_back({x.n, x.sout, x.sout}); db.push_back({x.n, x.sout, x.sout}); }
+      rc = emit(KIND_C2C, RL_HERMITIAN, true, N1, es * (int64_t)N2, es * (int64_t)N2, da, 0, N, nullptr, 0, 0, csz, csz, BUF_IN,
+                BUF_TMP2, 0, 0, false);
+      if (!rc) rc = emit(KIND_C2C, RL_HERMITIAN, true, N2, es, es * (int64_t)N1, dm, 0, N, nullptr, 0, 0, csz, csz, BUF_TMP2,
+                         BUF_TMP3, 0, 0, false, d.umul_mod, true);
+      if (!rc) rc = emit(KIND_C2C, RL_HERMITIAN, false, N1, es, es * (int64_t)N2, db, -1, 0, nullptr, 0, 0, csz, csz, BUF_TMP3,
+                         BUF_OUT, 0, 0, true);
+      fused = !rc && plan->steps.size() == n0 + 3;
+      if (fused)   // every pass must have landed on a register kernel, otherwise the plain sequence is the better plan
+        for (size_t i = n0; i < plan->steps.size(); ++i) fused = fused && plan->steps[i].job.fast_id != FAST_NONE;
+      if (!fused) { plan->steps.resize(n0); rc = ST_OK; err->clear(); }
+    }
+    if (!fused) {
+      rc = add_axis(KIND_C2C, RL_HERMITIAN, true, ax, N, d.shape, d.stride_in, csz, d.stride_out, csz, BUF_IN, BUF_OUT, false,
+                    d.umul_mod);
+      if (!rc) rc = add_axis(KIND_C2C, RL_HERMITIAN, false, ax, N, d.shape, d.stride_out, csz, d.stride_out, csz, BUF_OUT, BUF_OUT, true);
     }
   } else if (d.kind == KIND_FFTPACK) {
     // general_nd with ExecR2R (hdronly.h:3123-3143, 3392-3403): every axis in the given order.  The vendored

@@ -32,6 +32,7 @@ enum Kind : int {
   KIND_FFTPACK = 5,       // r2r_fftpack: halfcomplex real transform on every axis (pocketfft_hdronly.h:3392-3403)
   KIND_HARTLEY_SEP = 6,   // r2r_separable_hartley                               (pocketfft_hdronly.h:3405-3415)
   KIND_HARTLEY_GEN = 7,   // r2r_genuine_hartley                                 (pocketfft_hdronly.h:3417-3445)
+  KIND_CONV_AXIS = 8,     // complex: IFFT_axis(FFT_axis(x) .* m), one axis (impulse_fft_convolve_axis)
 };
 enum DType : int { DT_F32 = 0, DT_F64 = 1 };
 enum RealLayout : int {
@@ -81,6 +82,7 @@ struct LineSpec {
   int r2r_type = 2;    // DCT/DST type 1..4 (pocketfft_hdronly.h:3284-3318)
   bool ortho = false;
   uint64_t umul_mod = 0;  // caller-supplied multiplier fused into the store (pointer set at execute time)
+  bool conv_mid = false;  // fused middle pass of an axis convolution (colconv2_kernel); needs tw4_n and umul_mod
   int blue_stage = 0;  // multi-launch Bluestein: 1 = load+chirp+zero-pad to scratch, 2 = scratch+chirp+store
 };
 
@@ -127,6 +129,8 @@ class PlanCache {
   ~PlanCache();
   // max shared memory per CTA the engine may use (bytes), set by the backend
   size_t max_smem = 227 * 1024;
+  // the fused convolution pass exists as a register kernel only; the host emulator turns it off
+  bool allow_conv_fusion = true;
   int status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err);
   int real_twiddle(uint32_t N, int dtype, const void **out, std::string *err);
   int bluestein_natural_table(uint32_t L, int dtype, const void **out, std::string *err);

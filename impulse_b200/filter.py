@@ -53,15 +53,15 @@ class FFTFilter2D:
         spec = self._spec_buf
         if out is None:
             out = torch.empty_like(images)
-        # rows: real -> half spectrum; columns: complex transform with the filter multiply fused into its store
+        # rows: real -> half spectrum; columns: FFT -> x filter spectrum -> inverse FFT as one axis convolution
+        # (three passes, the 2-D spectrum is never materialised); rows: half spectrum -> real
         FFTDesc.init(axes=[2], forward=True).apply(DataDesc.init(spec), DataDesc.init(images))
         stream = C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)
         esz = spec.element_size()
         shape = (C.c_size_t * 3)(b, self.h, wc)
         st = (C.c_ssize_t * 3)(self.h * wc * esz, wc * esz, esz)
-        axes = (C.c_size_t * 1)(1)
-        _lib.check(_lib.lib().impulse_fft_c2c_mul(self.code, 3, shape, st, st, 1, axes, 1, spec.data_ptr(), spec.data_ptr(), 1.0,
-                                                  self.spectrum.data_ptr(), self.h * wc, stream))
-        FFTDesc.init(axes=[1, 2], forward=False, scalingFactor=1.0 / (self.h * self.w)).apply(
+        _lib.check(_lib.lib().impulse_fft_convolve_axis(self.code, 3, shape, st, st, 1, spec.data_ptr(), spec.data_ptr(), 1.0,
+                                                        self.spectrum.data_ptr(), self.h * wc, stream))
+        FFTDesc.init(axes=[2], forward=False, scalingFactor=1.0 / (self.h * self.w)).apply(
             DataDesc.init(out), DataDesc.init(spec))
         return out

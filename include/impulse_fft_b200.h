@@ -121,6 +121,15 @@ int impulse_fft_c2c_mul(int dtype, size_t ndim, const size_t *shape, const ptrdi
                         const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *data_in,
                         void *data_out, double fct, const void *mul, size_t mul_elems, void *stream);
 
+/* Convolution along ONE axis of a complex array in the frequency domain:
+ *   out = fct * IFFT_axis( FFT_axis(in) .* mul[o % mul_elems] ),   o = element offset in the output layout.
+ * With equal, dense in/out layouts and a strided axis whose length splits into register-kernel factors
+ * (1024 ... 16384) this runs as three passes with the spectrum never written to memory; otherwise it is
+ * impulse_fft_c2c_mul followed by the inverse transform.  Device pointers; in place allowed. */
+int impulse_fft_convolve_axis(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                              const ptrdiff_t *stride_out, size_t axis, const void *data_in, void *data_out, double fct,
+                              const void *mul, size_t mul_elems, void *stream);
+
 /* Discrete cosine / sine transforms of type 1..4 over `axes`, real to real, with the argument list of
  * pocketfft::dct / pocketfft::dst (pocketfft_hdronly.h:3284-3318; FFTW's REDFT/RODFT definitions;
  * `ortho` as documented at README_pocketfft.md:220-241).  Called by DCTDesc.apply

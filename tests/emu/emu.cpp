@@ -42,6 +42,12 @@ template <typename T> void run_job(const LineJob &J, const LaunchCfg &cfg) {
 }
 }  // namespace
 
+static void ensure_cache() {
+  if (g_cache) return;
+  g_cache = new PlanCache(&g_alloc);
+  g_cache->allow_conv_fusion = false;  // the fused convolution pass exists as a register kernel only
+}
+
 extern "C" {
 
 const char *emu_last_error() { return g_err.c_str(); }
@@ -66,6 +72,14 @@ int emu_c2c_mul(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *st
                      2, 0, mul, mul_elems);
 }
 
+// mirrors impulse_fft_convolve_axis (the plain FFT -> multiply -> inverse FFT plan; the fused kernel is GPU-only)
+int emu_convolve_axis(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in, const ptrdiff_t *stride_out,
+                      size_t axis, const void *in, void *out, double fct, const void *mul, size_t mul_elems) {
+  const size_t axes[1] = {axis};
+  return emu_nd_impl(KIND_CONV_AXIS, dtype, RL_HERMITIAN, ndim, shape, stride_in, stride_out, 1, axes, 1, in, out, fct, 2, 0, mul,
+                     mul_elems);
+}
+
 // mirrors impulse_fft_r2r_fftpack (which = 0), _separable_hartley (1), _genuine_hartley (2)
 int emu_r2r_real(int which, int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in, const ptrdiff_t *stride_out,
                  size_t naxes, const size_t *axes, int real2hermitian, int forward, const void *in, void *out, double fct) {
@@ -85,7 +99,7 @@ static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_
                        const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *in,
                        void *out, double fct, int r2r_type, int ortho, const void *umul, size_t umul_mod,
                        int real2hermitian) {
-  if (!g_cache) g_cache = new PlanCache(&g_alloc);
+  ensure_cache();
   NdDesc d;
   d.r2r_type = r2r_type; d.ortho = ortho != 0;
   d.umul_mod = umul_mod;
@@ -124,7 +138,7 @@ static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_
 // number of kernel launches the N-D plan would issue (tests: four-step split, host-looped dims)
 int emu_nd_steps(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
                  const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward) {
-  if (!g_cache) g_cache = new PlanCache(&g_alloc);
+  ensure_cache();
   NdDesc d;
   d.kind = kind; d.dtype = dtype; d.layout = layout; d.forward = forward != 0;
   d.shape.assign(shape, shape + ndim);
@@ -138,7 +152,7 @@ int emu_nd_steps(int kind, int dtype, int layout, size_t ndim, const size_t *sha
 
 // plan introspection for tests
 int emu_plan_info(uint32_t L, int dtype, uint32_t *n_fft, int *blue, uint32_t *radices, int max_r) {
-  if (!g_cache) g_cache = new PlanCache(&g_alloc);
+  ensure_cache();
   const Engine1D *e = nullptr;
   int rc = g_cache->status_engine(L, dtype, &e, &g_err);
   if (rc) return rc;

@@ -81,6 +81,21 @@ def c2c_mul(a_in, a_out, axes, mul, forward=True, fct=1.0):
     return a_out
 
 
+def convolve_axis(a_in, a_out, axis, mul, fct=1.0):
+    L = lib()
+    L.emu_convolve_axis.restype = C.c_int
+    L.emu_convolve_axis.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_ssize_t), C.POINTER(C.c_ssize_t),
+                                    C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_size_t]
+    dt = 1 if a_in.dtype == np.complex128 else 0
+    n = a_in.ndim
+    rc = L.emu_convolve_axis(dt, n, (C.c_size_t * n)(*a_in.shape), (C.c_ssize_t * n)(*a_in.strides),
+                             (C.c_ssize_t * n)(*a_out.strides), axis, a_in.ctypes.data, a_out.ctypes.data, fct, mul.ctypes.data,
+                             mul.size)
+    if rc:
+        raise EmuError(rc, L.emu_last_error().decode())
+    return a_out
+
+
 def r2r_real(which, a_in, a_out, axes, real2hermitian=True, forward=True, fct=1.0):
     """which: 'fftpack' | 'separable_hartley' | 'genuine_hartley' (mirrors the impulse_fft_r2r_* entry points)."""
     L = lib()

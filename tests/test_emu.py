@@ -346,3 +346,19 @@ def test_hartley(shape, axes, dtype):
     oview = out[tuple(slice(None, None, 2) for _ in shape)]
     emu.r2r_real("genuine_hartley", view, oview, axes)
     assert oracle.rel_l2(oview.astype(np.float64), oracle.hartley_numpy(view, axes, True)) < tol
+
+
+@pytest.mark.parametrize("shape,axis", [((4, 64), 1), ((3, 40, 24), 1), ((2, 1024, 12), 1), ((5, 4099), 1), ((3, 16384), 1)])
+def test_convolve_axis(shape, axis):
+    """impulse_fft_convolve_axis (plain plan): IFFT(FFT(x) * m) along one axis, m broadcast over the batch."""
+    rng = np.random.default_rng(37)
+    x = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    period = int(np.prod(shape[1:]))
+    m = rng.standard_normal(period) + 1j * rng.standard_normal(period)
+    n = shape[axis]
+    want = np.fft.ifft(np.fft.fft(x, axis=axis) * m.reshape(shape[1:]), axis=axis)
+    got = emu.convolve_axis(x, np.empty_like(x), axis, m, fct=1.0 / n)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+    y = x.copy()
+    emu.convolve_axis(y, y, axis, m, fct=1.0 / n)   # in place
+    assert np.linalg.norm(y - want) / np.linalg.norm(want) < 1e-13

@@ -693,3 +693,46 @@ def test_fftpack_and_hartley(ib, torch_mod, ref):
     ib.r2r_genuine_hartley(ib.DataDesc.init(h1), ib.DataDesc.init(img), [0, 1])
     ib.r2r_genuine_hartley(ib.DataDesc.init(h2), ib.DataDesc.init(h1), [0, 1], 1.0 / (2048 * 2048))
     assert float(torch_mod.linalg.vector_norm(h2 - img) / torch_mod.linalg.vector_norm(img)) <= 1e-13
+
+
+def test_convolve_axis(ib, torch_mod, checker):
+    """impulse_fft_convolve_axis: IFFT_axis(FFT_axis(x) * m) — the fused three-pass plan (colconv2 kernel) on
+    strided axes of 1024..16384 points, ragged column counts, both precisions, in place and out of place;
+    and the plain two-transform plan everywhere else.  Checked against the oracle's transforms."""
+    import ctypes as C
+    from impulse_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(97)
+    used = set()
+    cases = [((2, 1024, 24), np.complex128), ((2, 2048, 40), np.complex64), ((3, 4096, 29), np.complex64),
+             ((2, 4096, 16), np.complex128), ((1, 8192, 16), np.complex64), ((2, 16384, 8), np.complex128),
+             ((4, 64), np.complex128), ((3, 40, 24), np.complex64), ((2, 4099, 8), np.complex128), ((2, 4096), np.complex128)]
+    for shape, cdt in cases:
+        axis = 1
+        x = rnd(rng, shape, cdt)
+        period = int(np.prod(shape[1:]))
+        m = rnd(rng, (period,), cdt)
+        n = shape[axis]
+        spec = checker.c2c(x, [axis], True, 1.0) * m.reshape(shape[1:])
+        want = checker.c2c(spec.astype(cdt), [axis], False, 1.0 / n)
+        xd, md = torch_mod.from_numpy(x).cuda(), torch_mod.from_numpy(m).cuda()
+        code = _lib.F64 if cdt == np.complex128 else _lib.F32
+        nd = len(shape)
+        st = (C.c_ssize_t * nd)(*x.strides)
+        for inplace in (False, True):
+            src = xd.clone()
+            dst = src if inplace else torch_mod.empty_like(src)
+            _lib.check(L.impulse_fft_convolve_axis(code, nd, (C.c_size_t * nd)(*shape), st, st, axis, src.data_ptr(),
+                                                   dst.data_ptr(), 1.0 / n, md.data_ptr(), period, None))
+            used.add(ib.last_kernel())
+            assert oracle.rel_l2(dst.cpu().numpy(), want) <= 3 * tol(n, np.float64 if cdt == np.complex128 else np.float32), \
+                (shape, cdt, inplace)
+    print(sorted(used))
+    # the fused path ends on a column register kernel; count its launches: 3 per call
+    before = ib.launch_count()
+    x = torch_mod.zeros((2, 4096, 32), dtype=torch_mod.complex64, device="cuda")
+    m = torch_mod.ones(4096 * 32, dtype=torch_mod.complex64, device="cuda")
+    st = (C.c_ssize_t * 3)(4096 * 32 * 8, 32 * 8, 8)
+    _lib.check(L.impulse_fft_convolve_axis(_lib.F32, 3, (C.c_size_t * 3)(2, 4096, 32), st, st, 1, x.data_ptr(), x.data_ptr(), 1.0,
+                                           m.data_ptr(), 4096 * 32, None))
+    assert ib.launch_count() - before == 3
