@@ -625,6 +625,13 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
 }  // namespace
 
 
+// W_N^m from the two-level four-step table of the job (m < N)
+template <typename T>
+__device__ __forceinline__ cx<T> four_step_w(const LineJob &J, uint32_t m) {
+  return cmul(__ldg(reinterpret_cast<const cx<T> *>(J.tw4_hi) + (m >> J.tw4_shift)),
+              __ldg(reinterpret_cast<const cx<T> *>(J.tw4_lo) + (m & ((1u << J.tw4_shift) - 1))));
+}
+
 // =================================================================================================
 // Column kernel: two-pass register FFT over LPC adjacent STRIDED lines (element n of line l at
 // base + n*es + l).  Thread u = line + LPC*i, so for every register index the lanes of a warp read /
@@ -633,9 +640,51 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
 // axes of N-D transforms and both launches of the four-step split (optional W_N^(k*n2) store twiddle).
 // One group of LPC lines per CTA: the hardware block scheduler balances the SMs.
 // =================================================================================================
-constexpr uint64_t kColPrefetchDistance = 148 * 12;  // groups ahead (about one resident wave)
+// Column kernels: CTA -> (group of adjacent lines, second and third batch index).  Launched as a 3-D grid
+// whenever the two outer extents fit (no divisions at all); a 1-D grid decodes with 32-bit divisions.
+struct ColGroup { uint32_t g0, i1, i2; };
+__device__ __forceinline__ ColGroup col_group(const LineJob &J, uint32_t g0n) {
+  ColGroup g;
+  if (gridDim.y > 1 || gridDim.z > 1 || (J.bdim[1] == 1 && J.bdim[2] == 1)) {
+    g.g0 = blockIdx.x; g.i1 = blockIdx.y; g.i2 = blockIdx.z;
+  } else {
+    const uint32_t b = blockIdx.x, r = b / g0n, d1 = (uint32_t)J.bdim[1];
+    g.g0 = b - r * g0n; g.i2 = r / d1; g.i1 = r - g.i2 * d1;
+  }
+  return g;
+}
+// Short-lived CTAs cannot double-buffer; instead one lane per 128-byte run asks L2 for the input of the
+// group `rows_ahead` rows further along the second batch index (about one resident wave of CTAs ahead).
+__device__ __forceinline__ void col_prefetch(const LineJob &J, const ColGroup &cg, uint32_t lpc, int i, int r1, int r2) {
+  const uint32_t g0n = (uint32_t)((J.bdim[0] + lpc - 1) / lpc);
+  const uint32_t rows_ahead = (1776u + g0n - 1) / g0n;
+  uint32_t p1 = cg.i1 + rows_ahead, p2 = cg.i2;
+  if (p1 >= (uint32_t)J.bdim[1]) { p1 -= (uint32_t)J.bdim[1]; ++p2; }
+  if (p1 >= (uint32_t)J.bdim[1] || p2 >= (uint32_t)J.bdim[2]) return;
+  const char *pin = reinterpret_cast<const char *>(J.in) +
+                    ((int64_t)(cg.g0 * lpc) + (int64_t)p1 * J.bs_in[1] + (int64_t)p2 * J.bs_in[2]) * (J.dtype == 1 ? 16 : 8);
+  const int64_t step = J.es_in * (J.dtype == 1 ? 16 : 8);
+  for (int j = 0; j < r1; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pin + (int64_t)(i + r2 * j) * step));
+}
+// Measured on the 64 x 4096 x 4096 filter (fp32: 128-thread CTAs) the prefetch is worth 12-25% per column
+// pass; on the 8192 x 8192 complex128 transform (64-thread CTAs, twice as many resident) it costs 7%.
+// IMPULSE_FFT_COL_PREFETCH=0/1 forces it off/on for A/B runs.
+static inline bool col_prefetch_enabled(bool f32) {
+  static const int mode = [] { const char *e = getenv("IMPULSE_FFT_COL_PREFETCH"); return e ? atoi(e) : -1; }();
+  return mode < 0 ? f32 : mode != 0;
+}
+// grid for the column kernels (see col_group); returns false if the job cannot be launched
+static inline bool col_grid(const LineJob &J, int lpc, dim3 *grid) {
+  const uint64_t g0n = (J.bdim[0] + lpc - 1) / lpc, groups = g0n * J.bdim[1] * J.bdim[2];
+  if (groups == 0 || groups > 0x7fffffffull) return false;
+  static const int force1d = [] { const char *e = getenv("IMPULSE_FFT_COL_GRID1D"); return e ? atoi(e) : 0; }();
+  if (!force1d && J.bdim[1] <= 65535 && J.bdim[2] <= 65535) *grid = dim3((unsigned)g0n, (unsigned)J.bdim[1], (unsigned)J.bdim[2]);
+  else *grid = dim3((unsigned)groups, 1, 1);
+  return true;
+}
 
-template <typename T, int R1, int R2, int LPC, bool BWD>
+
+template <typename T, int R1, int R2, int LPC, bool BWD, bool PF>
 __global__ void __launch_bounds__(LPC * R2)
 colfast2_kernel(const __grid_constant__ LineJob J) {
   constexpr int N = R1 * R2, NB2 = R1 / R2;
@@ -644,27 +693,16 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   cx<T> *S = reinterpret_cast<cx<T> *>(smem_raw);
   const int u = threadIdx.x, line = u % LPC, i = u / LPC;
   // group -> batch indices (bdim[0] is the adjacent-lines dimension; its last group may be ragged)
-  const uint64_t g0n = (J.bdim[0] + LPC - 1) / LPC;
-  const uint64_t i0 = ((uint64_t)blockIdx.x % g0n) * LPC, r = (uint64_t)blockIdx.x / g0n, i1 = r % J.bdim[1], i2 = r / J.bdim[1];
-  const bool valid = i0 + line < J.bdim[0];
-  const int64_t off_in = (int64_t)i0 + line + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
-  const int64_t off_out = (int64_t)i0 + line + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
-  const uint32_t twi = J.tw4_dim == 0 ? (uint32_t)i0 + line : J.tw4_dim == 1 ? (uint32_t)i1 : J.tw4_dim == 2 ? (uint32_t)i2 : 0u;
+  const ColGroup cg = col_group(J, (uint32_t)((J.bdim[0] + LPC - 1) / LPC));
+  const uint32_t i0 = cg.g0 * LPC, i1 = cg.i1, i2 = cg.i2;
+  const bool valid = i0 + line < (uint32_t)J.bdim[0];
+  const int64_t off_in = (int64_t)(i0 + line) + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
+  const int64_t off_out = (int64_t)(i0 + line) + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
+  const uint32_t twi = J.tw4_dim == 0 ? i0 + line : J.tw4_dim == 1 ? i1 : J.tw4_dim == 2 ? i2 : 0u;
   const cx<T> *in = reinterpret_cast<const cx<T> *>(J.in) + off_in;
   cx<T> *out = reinterpret_cast<cx<T> *>(J.out) + off_out;
   const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);   // W_N^m
-  // CTAs are short-lived and cannot double-buffer: instead each one pulls the input of the group that
-  // will be scheduled a few waves later into L2 (one lane per 128-byte run issues the prefetch)
-  if (line == 0 && !J.seg_len) {
-    const uint64_t pg = (uint64_t)blockIdx.x + kColPrefetchDistance;
-    if (pg < (uint64_t)gridDim.x) {
-      const uint64_t p0 = (pg % g0n) * LPC, pr = pg / g0n, p1 = pr % J.bdim[1], p2 = pr / J.bdim[1];
-      const cx<T> *pin = reinterpret_cast<const cx<T> *>(J.in) + (int64_t)p0 + (int64_t)p1 * J.bs_in[1] + (int64_t)p2 * J.bs_in[2];
-#pragma unroll
-      for (int j = 0; j < R1; ++j)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pin + (int64_t)(i + R2 * j) * J.es_in));
-    }
-  }
+  if (PF && line == 0 && !J.seg_len) col_prefetch(J, cg, LPC, i, R1, R2);
   cx<T> x[R1];
 #pragma unroll
   for (int j = 0; j < R1; ++j) {
@@ -685,6 +723,10 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   __syncthreads();
   const T f = (T)J.fct;
   const uint64_t umul_off = J.umul_mod ? (uint64_t)off_out % J.umul_mod : 0;
+  // first launch of the split: output k is multiplied by W_N^(k*n2) (n2 = twi).  k = k1 + R1*k2 walks in
+  // steps of R1, so one table lookup per k1 plus the step W_N^(R1*n2) replace a lookup per element.
+  cx<T> wstep = mk<T>((T)1, (T)0);
+  if (J.tw4_n) wstep = four_step_w<T>(J, (uint32_t)R1 * twi);
 #pragma unroll
   for (int m = 0; m < NB2; ++m) {
     const int k1 = i + R2 * m;
@@ -692,15 +734,15 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
 #pragma unroll
     for (int j = 0; j < R2; ++j) y[j] = S[(k1 * R2 + j) * LPC + line];
     RegFFT<T, R2>::run(y);
+    cx<T> w = mk<T>((T)1, (T)0);
+    if (J.tw4_n) w = four_step_w<T>(J, (uint32_t)k1 * twi);
 #pragma unroll
     for (int k2 = 0; k2 < R2; ++k2) {
       const int k = k1 + R1 * k2;
       cx<T> v = y[k2];
-      if (J.tw4_n) {  // first launch of the split: W_N^(k*n2); the conjugation below turns it into its inverse
-        const uint32_t mm = (uint32_t)k * twi;
-        const cx<T> w = cmul(__ldg(reinterpret_cast<const cx<T> *>(J.tw4_hi) + (mm >> J.tw4_shift)),
-                             __ldg(reinterpret_cast<const cx<T> *>(J.tw4_lo) + (mm & ((1u << J.tw4_shift) - 1))));
+      if (J.tw4_n) {  // the conjugation below turns the twiddle into its inverse for the backward transform
         v = cmul(v, w);
+        w = cmul(w, wstep);
       }
       v.x *= f;
       v.y *= BWD ? -f : f;
@@ -719,8 +761,9 @@ template <typename T, int R1, int R2, int LPC>
 int launch_colfast2(const LineJob &J, cudaStream_t s) {
   const size_t smem = sizeof(cx<T>) * (size_t)R1 * R2 * LPC;
   const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
-  auto kf = colfast2_kernel<T, R1, R2, LPC, false>;
-  auto kb = colfast2_kernel<T, R1, R2, LPC, true>;
+  const bool pf = col_prefetch_enabled(sizeof(T) == 4);
+  auto kf = pf ? colfast2_kernel<T, R1, R2, LPC, false, true> : colfast2_kernel<T, R1, R2, LPC, false, false>;
+  auto kb = pf ? colfast2_kernel<T, R1, R2, LPC, true, true> : colfast2_kernel<T, R1, R2, LPC, true, false>;
   static PerDeviceFlag flag;
   bool &configured = flag.here();
   if (!configured) {
@@ -732,9 +775,9 @@ int launch_colfast2(const LineJob &J, cudaStream_t s) {
     }
     configured = true;
   }
-  const uint64_t groups = ((J.bdim[0] + LPC - 1) / LPC) * J.bdim[1] * J.bdim[2];
-  if (groups == 0 || groups > 0x7fffffffull) return (int)cudaErrorInvalidValue;
-  (bwd ? kb : kf)<<<(unsigned)groups, LPC * R2, smem, s>>>(J);
+  dim3 grid;
+  if (!col_grid(J, LPC, &grid)) return (int)cudaErrorInvalidValue;
+  (bwd ? kb : kf)<<<grid, LPC * R2, smem, s>>>(J);
   return (int)cudaGetLastError();
 }
 }  // namespace
@@ -752,7 +795,7 @@ int launch_colfast2(const LineJob &J, cudaStream_t s) {
 // instead of five (FFT pass A, this kernel, inverse pass B).  Layout and thread mapping as
 // colfast2_kernel; the multiplier is indexed by the element offset this kernel writes to.
 // =================================================================================================
-template <typename T, int R1, int R2, int LPC>
+template <typename T, int R1, int R2, int LPC, bool PF>
 __global__ void __launch_bounds__(LPC * R2)
 colconv2_kernel(const __grid_constant__ LineJob J) {
   constexpr int N = R1 * R2, NB2 = R1 / R2;
@@ -760,20 +803,33 @@ colconv2_kernel(const __grid_constant__ LineJob J) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *S0 = reinterpret_cast<cx<T> *>(smem_raw), *S1 = S0 + N * LPC;
   const int u = threadIdx.x, line = u % LPC, i = u / LPC;
-  const uint64_t g0n = (J.bdim[0] + LPC - 1) / LPC;
-  const uint64_t i0 = ((uint64_t)blockIdx.x % g0n) * LPC, r = (uint64_t)blockIdx.x / g0n, i1 = r % J.bdim[1], i2 = r / J.bdim[1];
-  const bool valid = i0 + line < J.bdim[0];
-  const int64_t off_in = (int64_t)i0 + line + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
-  const int64_t off_out = (int64_t)i0 + line + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
-  const uint32_t twi = J.tw4_dim == 0 ? (uint32_t)i0 + line : J.tw4_dim == 1 ? (uint32_t)i1 : (uint32_t)i2;
+  const ColGroup cg = col_group(J, (uint32_t)((J.bdim[0] + LPC - 1) / LPC));
+  const uint32_t i0 = cg.g0 * LPC, i1 = cg.i1, i2 = cg.i2;
+  const bool valid = i0 + line < (uint32_t)J.bdim[0];
+  const int64_t off_in = (int64_t)(i0 + line) + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
+  const int64_t off_out = (int64_t)(i0 + line) + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
+  const uint32_t twi = J.tw4_dim == 0 ? i0 + line : J.tw4_dim == 1 ? i1 : i2;
   const cx<T> *in = reinterpret_cast<const cx<T> *>(J.in) + off_in;
   cx<T> *out = reinterpret_cast<cx<T> *>(J.out) + off_out;
   const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);
   const cx<T> *um = reinterpret_cast<const cx<T> *>(J.umul);
   const uint64_t umul_off = (uint64_t)off_out % J.umul_mod;
+  if (PF && line == 0) col_prefetch(J, cg, LPC, i, R1, R2);
   cx<T> x[R1];
 #pragma unroll
   for (int j = 0; j < R1; ++j) x[j] = valid ? in[(int64_t)(i + R2 * j) * J.es_in] : mk<T>((T)0, (T)0);
+  // the multipliers this thread will need after the forward transform: requested now, so that their
+  // (L2) latency overlaps the data loads instead of sitting between the two transforms
+  cx<T> mreg[R1];
+#pragma unroll
+  for (int m = 0; m < NB2; ++m)
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) {
+      const int k = i + R2 * m + R1 * k2;
+      uint64_t o = umul_off + (uint64_t)((int64_t)k * J.es_out);
+      if (o >= J.umul_mod) o %= J.umul_mod;
+      mreg[m * R2 + k2] = valid ? __ldg(um + o) : mk<T>((T)0, (T)0);
+    }
   // ---- forward N-point FFT
   RegFFT<T, R1>::run(x);
 #pragma unroll
@@ -791,12 +847,7 @@ colconv2_kernel(const __grid_constant__ LineJob J) {
 #pragma unroll
     for (int k2 = 0; k2 < R2; ++k2) {
       const int k = k1 + R1 * k2;
-      cx<T> v = y[k2];
-      if (valid) {
-        uint64_t o = umul_off + (uint64_t)((int64_t)k * J.es_out);
-        if (o >= J.umul_mod) o %= J.umul_mod;
-        v = cmul(v, __ldg(um + o));
-      }
+      cx<T> v = cmul(y[k2], mreg[m * R2 + k2]);
       v.y = -v.y;  // inverse = conj(FFT(conj(.)))
       S1[k * LPC + line] = v;
     }
@@ -812,20 +863,20 @@ colconv2_kernel(const __grid_constant__ LineJob J) {
   for (int k = 0; k < R1; ++k) S0[(k * R2 + i) * LPC + line] = x[k];   // S0 is free: everyone passed the second barrier
   __syncthreads();
   const T f = (T)J.fct;
-#pragma unroll
+  const cx<T> wstep = four_step_w<T>(J, (uint32_t)R1 * twi);   // four-step twiddle of the inverse's first pass,
+#pragma unroll                                                 // stepped along k = k1 + R1*k2 (conjugated below)
   for (int m = 0; m < NB2; ++m) {
     const int k1 = i + R2 * m;
     cx<T> y[R2];
 #pragma unroll
     for (int j = 0; j < R2; ++j) y[j] = S0[(k1 * R2 + j) * LPC + line];
     RegFFT<T, R2>::run(y);
+    cx<T> w = four_step_w<T>(J, (uint32_t)k1 * twi);
 #pragma unroll
     for (int k2 = 0; k2 < R2; ++k2) {
       const int k = k1 + R1 * k2;
-      const uint32_t mm = (uint32_t)k * twi;   // four-step twiddle of the inverse's first pass (conjugated below)
-      const cx<T> w = cmul(__ldg(reinterpret_cast<const cx<T> *>(J.tw4_hi) + (mm >> J.tw4_shift)),
-                           __ldg(reinterpret_cast<const cx<T> *>(J.tw4_lo) + (mm & ((1u << J.tw4_shift) - 1))));
       cx<T> v = cmul(y[k2], w);
+      w = cmul(w, wstep);
       v.x *= f;
       v.y *= -f;
       if (valid) out[(int64_t)k * J.es_out] = v;
@@ -837,7 +888,7 @@ namespace {
 template <typename T, int R1, int R2, int LPC>
 int launch_colconv2(const LineJob &J, cudaStream_t s) {
   const size_t smem = 2 * sizeof(cx<T>) * (size_t)R1 * R2 * LPC;
-  auto k = colconv2_kernel<T, R1, R2, LPC>;
+  auto k = col_prefetch_enabled(sizeof(T) == 4) ? colconv2_kernel<T, R1, R2, LPC, true> : colconv2_kernel<T, R1, R2, LPC, false>;
   static PerDeviceFlag flag;
   bool &configured = flag.here();
   if (!configured) {
@@ -848,9 +899,9 @@ int launch_colconv2(const LineJob &J, cudaStream_t s) {
     configured = true;
   }
   if (!J.umul || !J.umul_mod || !J.tw4_n) return (int)cudaErrorInvalidValue;
-  const uint64_t groups = ((J.bdim[0] + LPC - 1) / LPC) * J.bdim[1] * J.bdim[2];
-  if (groups == 0 || groups > 0x7fffffffull) return (int)cudaErrorInvalidValue;
-  k<<<(unsigned)groups, LPC * R2, smem, s>>>(J);
+  dim3 grid;
+  if (!col_grid(J, LPC, &grid)) return (int)cudaErrorInvalidValue;
+  k<<<grid, LPC * R2, smem, s>>>(J);
   return (int)cudaGetLastError();
 }
 }  // namespace
