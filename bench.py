@@ -43,7 +43,9 @@ WORKLOADS = {
     "c2c_131072x1024_c64": ("c2c", 131072, 1024, "f32"),
     "fft2_8192x8192_c128": ("fft2", 8192, 8192, "f64"),
     "filter2d_64x4096x4096_f32": ("filter2d", 64, 4096, "f32"),
+    "fftconvolve_4096x16384_k257_f64": ("fftconv", 4096, 16384, "f64"),   # rows (*) 257-tap FIR, full
 }
+FIR_TAPS = 257
 DEFAULT_WORKLOAD = "c2c_65536x1024_c128"
 
 
@@ -53,6 +55,8 @@ def algorithmic_bytes(kind, rows, n, dtype):
         return rows * n * 2 * r * 2          # read + write one complex element each
     if kind == "fft2":
         return 2 * rows * n * 2 * r * 2      # two passes, each one read + one write
+    if kind == "fftconv":                    # signal read once, full convolution written once
+        return rows * (n + n + FIR_TAPS - 1) * r
     if kind == "filter2d":                   # rows = images, n = P: SURVEY 8(d) config 5 (circular, P x P)
         return rows * (2 * r * n * n + 8 * n * (n // 2 + 1) * r)
     return rows * (n * r + (n // 2 + 1) * 2 * r)  # real side + half-spectrum side
@@ -221,7 +225,14 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     slab = kind == "fft2" and world > 1
     filt = None
-    if kind == "filter2d":
+    conv = None
+    if kind == "fftconv":
+        from impulse_b200 import signal as isig
+        x = torch.rand((rows, n), generator=g, device=dev, dtype=rdt) - 0.5
+        taps = torch.rand((FIR_TAPS,), generator=g, device=dev, dtype=rdt) - 0.5
+        y = None
+        conv = lambda: isig.fftconvolve(x, taps, "full")  # noqa: E731
+    elif kind == "filter2d":
         from impulse_b200.filter import FFTFilter2D
         from impulse_b200 import dist as idist
         lo, hi = idist.shard_rows(rows, rank, world) if world > 1 else (0, rows)
@@ -248,11 +259,13 @@ def main():
         x = torch.view_as_complex(torch.rand((rows, n // 2 + 1, 2), generator=g, device=dev, dtype=rdt) - 0.5)
         y = torch.empty((rows, n), device=dev, dtype=rdt)
     fdesc = ib.FFTDesc.init(axes=[0, 1] if kind == "fft2" else [1], forward=(kind != "c2r"), scalingFactor=1.0)
-    if not slab and filt is None:
+    if not slab and filt is None and conv is None:
         din, dout = ib.DataDesc.init(x), ib.DataDesc.init(y)
 
     def step():
-        if filt is not None:
+        if conv is not None:
+            conv()
+        elif filt is not None:
             filt.apply(x, out=y)
         elif slab:
             if slab_op is not None:
@@ -294,7 +307,7 @@ def main():
 
     # ---- e2e: public API with pinned HOST buffers, copies inside the timed region
     e2e = None
-    if not args.no_e2e and not slab and filt is None:
+    if not args.no_e2e and not slab and filt is None and conv is None:
         hx = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
         hy = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
         hx.copy_(x)
@@ -322,7 +335,9 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         # dominant (only) kernel of the step: one launch per step on this stream
-        k_ms = e0.elapsed_time(e1) / max(1, launches)
+        # (multi-launch steps — fft2, filter2d, fftconvolve: the step's algorithmic bytes over the whole step)
+        per_step = max(1, round(launches / steps))
+        k_ms = e0.elapsed_time(e1) / steps if per_step > 1 else e0.elapsed_time(e1) / max(1, launches)
         achieved = bytes_per_gpu / (k_ms * 1e-3) / 1e9
         line = {
             "metric": "batched fp64 FFT throughput (algorithmic GB/s)" if dtype == "f64" else "batched fp32 FFT throughput (algorithmic GB/s)",
@@ -339,12 +354,13 @@ def main():
                        "frac_of_8TBps_nominal": round(value / world / 8000.0, 4)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": committed_traffic(args.workload),
-                         "peak_source": peak_src, "kernel": ib.last_kernel(), "algorithmic_bytes_per_launch": bytes_per_gpu},
+                         "peak_source": peak_src, "kernel": ib.last_kernel() + (f" (last of {per_step} launches per step)" if per_step > 1 else ""),
+                         "algorithmic_bytes_per_launch": bytes_per_gpu},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu and world == 1 and filt is None:
+        if not args.no_cpu and world == 1 and filt is None and conv is None:
             try:
                 _, info = cpu_reference(kind, rows, n, dtype)
                 line["cpu_baseline"] = info
