@@ -174,46 +174,74 @@ def next_fast_len(n: int, even: bool = False) -> int:
     return best
 
 
+# transform lengths served by the register kernels (fast_kernels.cu): real rows run as a half-length complex
+# transform, so the real lengths are twice the complex ones
+_FAST_REAL = {"f64": (4096, 8192, 16384), "f32": (4096, 8192)}
+_FAST_CPLX = {"f64": (1024, 2048, 4096, 8192), "f32": (1024, 2048, 4096)}
+_ONE_SHOT_MAX = 16384      # longest single-launch transform worth using when no register kernel fits
+
+
+def plan_blocks(n: int, m: int, real: bool, prec: str):
+    """Overlap-save blocking of an n-sample row convolved with m taps: returns (P, V, nb) — nb blocks of P
+    samples advancing by V = P - (m - 1), each yielding V valid outputs.  Picks the transform length that
+    moves the least data, counting lengths without a register kernel 2.5x."""
+    out_len = n + m - 1
+    best = None
+    fast = (_FAST_REAL if real else _FAST_CPLX)[prec]
+    one = next_fast_len(out_len + m - 1, even=real)       # a single block: V = P - (m-1) >= out_len
+    cands = [(one, 1.0 if one in fast else 2.5)] if one <= _ONE_SHOT_MAX else []
+    cands += [(p, 1.0) for p in fast]
+    for p, penalty in cands:
+        v = p - (m - 1)
+        if v < 1:
+            continue
+        nb = -(-out_len // v)
+        cost = nb * p * penalty
+        if best is None or cost < best[0]:
+            best = (cost, p, v, nb)
+    if best is None:
+        raise _lib.FFTError(-3, f"a filter of {m} taps needs a transform longer than this engine runs in one launch")
+    return best[1], best[2], best[3]
+
+
 class CudaConvEngine:
     """Full linear convolution of the rows of `x` ([B, n], CUDA tensor) with one filter `h` ([m]) through
-    libimpulse_fft_b200: zero-pad to a fast length P >= n+m-1, transform, multiply, transform back."""
+    libimpulse_fft_b200, by overlap-save: the padded rows are viewed as overlapping blocks of P samples (a
+    strided view, nothing is gathered), each block is transformed, multiplied by the filter's spectrum and
+    transformed back (three launches for the whole batch), and the valid V = P - (m-1) samples of every
+    block are the output.  Short rows are the one-block case."""
 
     def full(self, x, h):
         import torch
         from .desc import DataDesc, FFTDesc
         L = _lib.lib()
         b, n = x.shape
+        real = not x.is_complex()
+        true_len = n + h.shape[0] - 1
+        if real and h.shape[0] % 2 == 0:       # an odd tap count keeps the block stride even (paired real loads)
+            h = torch.cat([h, torch.zeros(1, dtype=h.dtype, device=h.device)])
         m = h.shape[0]
-        out_len = n + m - 1
-        p = next_fast_len(out_len, even=not x.is_complex())
+        prec = "f64" if x.dtype in (torch.float64, torch.complex128) else "f32"
+        code = _lib.F64 if prec == "f64" else _lib.F32
+        p, v, nb = plan_blocks(n, m, real, prec)
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        if x.is_complex():
-            xp = torch.zeros((b, p), dtype=x.dtype, device=x.device)
-            xp[:, :n] = x
-            hp = torch.zeros((p,), dtype=x.dtype, device=x.device)
-            hp[:m] = h
-            hf = torch.empty_like(hp)
-            FFTDesc.init(axes=[0], forward=True).apply(DataDesc.init(hf), DataDesc.init(hp))
-            esz = xp.element_size()
-            code = _lib.F64 if x.dtype == torch.complex128 else _lib.F32
-            st = (C.c_ssize_t * 2)(p * esz, esz)
-            _lib.check(L.impulse_fft_convolve_axis(code, 2, (C.c_size_t * 2)(b, p), st, st, 1, xp.data_ptr(), xp.data_ptr(),
-                                                   1.0 / p, hf.data_ptr(), p, stream))
-            return xp[:, :out_len]
-        cdt = torch.complex128 if x.dtype == torch.float64 else torch.complex64
-        code = _lib.F64 if x.dtype == torch.float64 else _lib.F32
-        xp = torch.zeros((b, p), dtype=x.dtype, device=x.device)
-        xp[:, :n] = x
+        # rows laid end to end, each as [m-1 zeros | signal | zeros up to nb*v]; the zeros that the last block of
+        # a row reads past its end are the leading zeros of the next row (one more run closes the buffer)
+        flat = torch.zeros(b * nb * v + (m - 1) + p, dtype=x.dtype, device=x.device)
+        flat[:b * nb * v].view(b, nb * v)[:, m - 1:m - 1 + n] = x
+        blocks = flat.as_strided((b * nb, p), (v, 1))
+        cdt = x.dtype if not real else (torch.complex128 if prec == "f64" else torch.complex64)
+        pc = p // 2 + 1 if real else p
         hp = torch.zeros((p,), dtype=x.dtype, device=x.device)
         hp[:m] = h
-        pc = p // 2 + 1
         hf = torch.empty((pc,), dtype=cdt, device=x.device)
         FFTDesc.init(axes=[0], forward=True).apply(DataDesc.init(hf), DataDesc.init(hp))
-        spec = torch.empty((b, pc), dtype=cdt, device=x.device)
-        FFTDesc.init(axes=[1], forward=True).apply(DataDesc.init(spec), DataDesc.init(xp))
-        _lib.check(L.impulse_fft_cmul(code, spec.data_ptr(), hf.data_ptr(), spec.data_ptr(), pc, b, 1.0, stream))
-        FFTDesc.init(axes=[1], forward=False, scalingFactor=1.0 / p).apply(DataDesc.init(xp), DataDesc.init(spec))
-        return xp[:, :out_len]
+        spec = torch.empty((b * nb, pc), dtype=cdt, device=x.device)
+        FFTDesc.init(axes=[1], forward=True).apply(DataDesc.init(spec), DataDesc.init(blocks))
+        _lib.check(L.impulse_fft_cmul(code, spec.data_ptr(), hf.data_ptr(), spec.data_ptr(), pc, b * nb, 1.0, stream))
+        res = torch.empty((b * nb, p), dtype=x.dtype, device=x.device)
+        FFTDesc.init(axes=[1], forward=False, scalingFactor=1.0 / p).apply(DataDesc.init(res), DataDesc.init(spec))
+        return res[:, m - 1:].reshape(b, nb * v)[:, :true_len]
 
 
 def _to_device(a, engine=None):
