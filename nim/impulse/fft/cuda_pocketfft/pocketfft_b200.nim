@@ -57,6 +57,15 @@ proc impulse_fft_dct(dtype: cint; ndim: csize_t; shape: ptr csize_t; strideIn, s
 proc impulse_fft_dst(dtype: cint; ndim: csize_t; shape: ptr csize_t; strideIn, strideOut: ptr int;
                      naxes: csize_t; axes: ptr csize_t; dstType: cint; dataIn, dataOut: pointer;
                      fct: cdouble; ortho: cint; nthreads: csize_t; stream: pointer): cint {.importc, dynlib: libName, cdecl.}
+proc impulse_fft_r2r_fftpack(dtype: cint; ndim: csize_t; shape: ptr csize_t; strideIn, strideOut: ptr int;
+                             naxes: csize_t; axes: ptr csize_t; real2hermitian, forward: cint; dataIn, dataOut: pointer;
+                             fct: cdouble; nthreads: csize_t; stream: pointer): cint {.importc, dynlib: libName, cdecl.}
+proc impulse_fft_r2r_separable_hartley(dtype: cint; ndim: csize_t; shape: ptr csize_t; strideIn, strideOut: ptr int;
+                                       naxes: csize_t; axes: ptr csize_t; dataIn, dataOut: pointer;
+                                       fct: cdouble; nthreads: csize_t; stream: pointer): cint {.importc, dynlib: libName, cdecl.}
+proc impulse_fft_r2r_genuine_hartley(dtype: cint; ndim: csize_t; shape: ptr csize_t; strideIn, strideOut: ptr int;
+                                     naxes: csize_t; axes: ptr csize_t; dataIn, dataOut: pointer;
+                                     fct: cdouble; nthreads: csize_t; stream: pointer): cint {.importc, dynlib: libName, cdecl.}
 
 type
   DataDesc*[T] = object
@@ -155,3 +164,27 @@ proc apply*[T](dct: DCTDesc[T], descOut: var DataDesc[T], descIn: DataDesc[T]) =
   check impulse_fft_dct(dtypeCode(T), csize_t shape.len, shape[0].addr, descIn.stride[0].unsafeAddr,
                         descOut.stride[0].addr, csize_t axes.len, axes[0].addr, cint(dct.dctType),
                         descIn.buf, descOut.buf, cdouble(dct.scalingFactor), cint(dct.ortho), csize_t(dct.nthreads), nil)
+
+proc r2r_fftpack*[T](descOut: var DataDesc[T], descIn: DataDesc[T], axes: varargs[int],
+                     real2hermitian, forward: bool, fct: T = 1) =
+  ## cpp_pocketfft/pocketfft.nim:71-82 (imported there, reachable here)
+  var ax = newSeq[csize_t](axes.len)
+  for i, a in axes: ax[i] = csize_t a
+  var shape = descIn.shape
+  check impulse_fft_r2r_fftpack(dtypeCode(T), csize_t shape.len, shape[0].addr, descIn.stride[0].unsafeAddr,
+                                descOut.stride[0].addr, csize_t ax.len, ax[0].addr, cint(real2hermitian), cint(forward),
+                                descIn.buf, descOut.buf, cdouble(fct), 1, nil)
+
+proc r2r_hartley*[T](descOut: var DataDesc[T], descIn: DataDesc[T], axes: varargs[int], genuine = false, fct: T = 1) =
+  ## cpp_pocketfft/pocketfft.nim:84-106 (the reference's import of the separable variant has a stray `forward`)
+  var ax = newSeq[csize_t](axes.len)
+  for i, a in axes: ax[i] = csize_t a
+  var shape = descIn.shape
+  if genuine:
+    check impulse_fft_r2r_genuine_hartley(dtypeCode(T), csize_t shape.len, shape[0].addr, descIn.stride[0].unsafeAddr,
+                                          descOut.stride[0].addr, csize_t ax.len, ax[0].addr, descIn.buf, descOut.buf,
+                                          cdouble(fct), 1, nil)
+  else:
+    check impulse_fft_r2r_separable_hartley(dtypeCode(T), csize_t shape.len, shape[0].addr, descIn.stride[0].unsafeAddr,
+                                            descOut.stride[0].addr, csize_t ax.len, ax[0].addr, descIn.buf, descOut.buf,
+                                            cdouble(fct), 1, nil)
