@@ -154,20 +154,27 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
   if (in == out && (nd.desc.kind == KIND_C2C || (nd.desc.kind >= KIND_DCT && nd.desc.kind <= KIND_HARTLEY_GEN)) &&
       nd.desc.stride_in != nd.desc.stride_out)
     return fail(IMPULSE_FFT_ERR_STRIDE, "stride mismatch");  // hdronly.h:455-456
-  void *tmp = nullptr, *tmp2 = nullptr, *tmp3 = nullptr;
+  if ((nd.cplx_view_in && ((uintptr_t)in % (2 * p->in_esz))) || (nd.cplx_view_out && ((uintptr_t)out % (2 * p->out_esz))))
+    return fail(IMPULSE_FFT_ERR_STRIDE, "long real lines are processed as complex pairs: the real array must be aligned to 2 elements");
+  void *tmp = nullptr, *tmp2 = nullptr, *tmp3 = nullptr, *tmp4 = nullptr;
+  if (nd.tmp4_bytes) {
+    cudaError_t e = cudaMallocAsync(&tmp4, nd.tmp4_bytes, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(tmp4)");
+  }
   if (nd.tmp_bytes) {
     cudaError_t e = cudaMallocAsync(&tmp, nd.tmp_bytes, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(tmp)");
+    if (e != cudaSuccess) { if (tmp4) cudaFreeAsync(tmp4, stream); return cuda_fail(e, "cudaMallocAsync(tmp)"); }
   }
   if (nd.tmp2_bytes) {
     cudaError_t e = cudaMallocAsync(&tmp2, nd.tmp2_bytes, stream);
-    if (e != cudaSuccess) { if (tmp) cudaFreeAsync(tmp, stream); return cuda_fail(e, "cudaMallocAsync(tmp2)"); }
+    if (e != cudaSuccess) { if (tmp) cudaFreeAsync(tmp, stream); if (tmp4) cudaFreeAsync(tmp4, stream); return cuda_fail(e, "cudaMallocAsync(tmp2)"); }
   }
   if (nd.tmp3_bytes) {
     cudaError_t e = cudaMallocAsync(&tmp3, nd.tmp3_bytes, stream);
     if (e != cudaSuccess) {
       if (tmp) cudaFreeAsync(tmp, stream);
       if (tmp2) cudaFreeAsync(tmp2, stream);
+      if (tmp4) cudaFreeAsync(tmp4, stream);
       return cuda_fail(e, "cudaMallocAsync(tmp3)");
     }
   }
@@ -176,9 +183,21 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     LineJob J = st.job;
     const unsigned char *src = st.src == BUF_IN ? (const unsigned char *)in : st.src == BUF_OUT ? (const unsigned char *)out
                                : st.src == BUF_TMP ? (const unsigned char *)tmp
-                               : st.src == BUF_TMP2 ? (const unsigned char *)tmp2 : (const unsigned char *)tmp3;
+                               : st.src == BUF_TMP2 ? (const unsigned char *)tmp2
+                               : st.src == BUF_TMP3 ? (const unsigned char *)tmp3 : (const unsigned char *)tmp4;
     unsigned char *dst = st.dst == BUF_OUT ? (unsigned char *)out : st.dst == BUF_TMP ? (unsigned char *)tmp
-                         : st.dst == BUF_TMP2 ? (unsigned char *)tmp2 : (unsigned char *)tmp3;
+                         : st.dst == BUF_TMP2 ? (unsigned char *)tmp2
+                         : st.dst == BUF_TMP3 ? (unsigned char *)tmp3 : (unsigned char *)tmp4;
+    if (st.aux) {
+      AuxJob aj = st.aj;
+      aj.in = src + st.src_off_bytes;
+      aj.out = dst + st.dst_off_bytes;
+      aj.fct = st.takes_fct ? fct : 1.0;
+      int e = launch_aux(aj, p->ctx->sm_count, stream);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (e) { rc = cuda_fail((cudaError_t)e, "kernel launch"); break; }
+      continue;
+    }
     if (st.combine) {
       CombineJob cj = st.cj;
       cj.in = src + st.src_off_bytes;
@@ -209,6 +228,7 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
   if (tmp) cudaFreeAsync(tmp, stream);
   if (tmp2) cudaFreeAsync(tmp2, stream);
   if (tmp3) cudaFreeAsync(tmp3, stream);
+  if (tmp4) cudaFreeAsync(tmp4, stream);
   return rc;
 }
 
@@ -221,7 +241,8 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
   if (nd.empty) return 0;
   const bool inplace = (in == out);
   // ---- try the chunked pipeline
-  if (nd.steps.size() == 1 && nd.tmp_bytes == 0 && nd.tmp2_bytes == 0 && nd.tmp3_bytes == 0) {
+  if (nd.steps.size() == 1 && !nd.steps[0].aux && !nd.steps[0].combine && nd.tmp_bytes == 0 && nd.tmp2_bytes == 0 &&
+      nd.tmp3_bytes == 0 && nd.tmp4_bytes == 0) {
     const Step &st = nd.steps[0];
     const LineJob &J0 = st.job;
     int od = -1;  // outermost batch dim in use
@@ -445,7 +466,7 @@ int impulse_fft_plan_get_info(impulse_fft_plan plan, impulse_fft_plan_info *info
   if (!plan || !info) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
   std::memset(info, 0, sizeof(*info));
   info->n_steps = (uint32_t)plan->nd.steps.size();
-  info->tmp_bytes = plan->nd.tmp_bytes + plan->nd.tmp2_bytes + plan->nd.tmp3_bytes;
+  info->tmp_bytes = plan->nd.tmp_bytes + plan->nd.tmp2_bytes + plan->nd.tmp3_bytes + plan->nd.tmp4_bytes;
   if (!plan->nd.steps.empty()) {
     const Step &s = plan->nd.steps[0];
     info->n_fft = s.job.n_fft;

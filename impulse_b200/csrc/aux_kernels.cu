@@ -119,4 +119,21 @@ int launch_hartley_combine(const CombineJob &job, int sm_count, void *stream) {
   return (int)cudaGetLastError();
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) aux_kernel(const __grid_constant__ AuxJob A) {
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.total; g += (uint64_t)gridDim.x * blockDim.x)
+    aux_one<T>(A, g);
+}
+
+int launch_aux(const AuxJob &job, int sm_count, void *stream) {
+  if (job.total == 0) return 0;
+  const uint64_t want = (job.total + 255) / 256, cap = (uint64_t)sm_count * 16;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (job.dtype == 1) aux_kernel<double><<<grid, 256, 0, s>>>(job);
+  else aux_kernel<float><<<grid, 256, 0, s>>>(job);
+  g_last_kernel = "aux_kernel";
+  return (int)cudaGetLastError();
+}
+
 }  // namespace impulse

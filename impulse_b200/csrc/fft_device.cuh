@@ -602,4 +602,129 @@ IMP_HD void hartley_combine_one(const CombineJob &C, uint64_t idx) {
   if (kh != 0 && 2 * kh != C.full[C.half_axis]) out[roff] = v.x - v.y;
 }
 
+// ---------------------------------------------------------------------------
+// AuxJob: one element of the iteration space (see fft_types.h)
+// ---------------------------------------------------------------------------
+// store spectrum bin k of a length-N real transform in the user layout (RealLayout values of planner.h:
+// 0 Hermitian complex, 1 FFTPACK halfcomplex reals, 2 full symmetric complex, 4 Hartley reals)
+template <typename T>
+IMP_HD void aux_store_bin(const AuxJob &A, int64_t off, int64_t es, uint32_t k, cx<T> v) {
+  const T f = (T)A.fct;
+  v.x *= f; v.y *= f;
+  if (A.flags & F_CONJ_RESULT) v.y = -v.y;
+  const uint32_t N = A.N;
+  cx<T> *oc = (cx<T> *)A.out;
+  T *orl = (T *)A.out;
+  switch (A.layout) {
+    case 1:
+      if (k == 0) orl[off] = v.x;
+      else if (2 * k == N) orl[off + (int64_t)(N - 1) * es] = v.x;
+      else { orl[off + (2 * (int64_t)k - 1) * es] = v.x; orl[off + (2 * (int64_t)k) * es] = v.y; }
+      break;
+    case 2:
+      oc[off + (int64_t)k * es] = v;
+      if (k > 0 && 2 * k != N) oc[off + (int64_t)(N - k) * es] = cconj(v);
+      break;
+    case 4:
+      if (k == 0 || 2 * k == N) orl[off + (int64_t)k * es] = v.x;
+      else { orl[off + (int64_t)k * es] = v.x + v.y; orl[off + (int64_t)(N - k) * es] = v.x - v.y; }
+      break;
+    default:
+      oc[off + (int64_t)k * es] = v;
+      break;
+  }
+}
+
+// load spectrum bin k (0 <= k <= N/2) of a Hermitian input in the user layout (0 Hermitian, 1 halfcomplex)
+template <typename T>
+IMP_HD cx<T> aux_load_bin(const AuxJob &A, int64_t off, int64_t es, uint32_t k) {
+  const uint32_t N = A.N;
+  cx<T> v;
+  if (A.layout == 1) {
+    const T *ir = (const T *)A.in;
+    if (k == 0) v = mk<T>(ir[off], (T)0);
+    else if (2 * k == N) v = mk<T>(ir[off + (int64_t)(N - 1) * es], (T)0);
+    else v = mk<T>(ir[off + (2 * (int64_t)k - 1) * es], ir[off + (2 * (int64_t)k) * es]);
+  } else {
+    v = ((const cx<T> *)A.in)[off + (int64_t)k * es];
+    if (k == 0 || 2 * k == N) v.y = (T)0;   // pocketfft ignores these imaginary parts
+  }
+  if (A.flags & F_CONJ_IN) v.y = -v.y;
+  return v;
+}
+
+template <typename T>
+IMP_HD void aux_one(const AuxJob &A, uint64_t idx) {
+  // decode: last dimension = position along the transform axis
+  const int ax = A.ndim - 1;
+  const uint32_t e = (uint32_t)(idx % A.shape[ax]);
+  uint64_t r = idx / A.shape[ax];
+  int64_t ou = 0, ow = 0;
+  for (int d = ax - 1; d >= 0; --d) {
+    const uint32_t i = (uint32_t)(r % A.shape[d]);
+    r /= A.shape[d];
+    ou += (int64_t)i * A.s_user[d];
+    ow += (int64_t)i * A.s_work[d];
+  }
+  const int64_t eu = A.s_user[ax], ew = A.s_work[ax];
+  const uint32_t N = A.N, M = A.M;
+  const cx<T> *tab = (const cx<T> *)A.tab;
+  switch (A.mode) {
+    case AUX_R2C_POST_EVEN: {   // e = k in 0..M
+      const cx<T> *Z = (const cx<T> *)A.in + ow;
+      const cx<T> a = Z[(int64_t)(e == M ? 0 : e) * ew], b = cconj(Z[(int64_t)(e == 0 ? 0 : M - e) * ew]);
+      const T h = (T)0.5;
+      const cx<T> E = mk<T>((a.x + b.x) * h, (a.y + b.y) * h), D = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
+      aux_store_bin<T>(A, ou, eu, e, cadd(E, cmul(IMP_LDG(tab + e), mul_mi(D))));
+    } break;
+    case AUX_C2R_PRE_EVEN: {    // e = k in 0..M/2: writes Z[k] and Z[M-k]
+      cx<T> *Z = (cx<T> *)A.out + ow;
+      const uint32_t k = e, km = M - k;
+      const cx<T> a = aux_load_bin<T>(A, ou, eu, k), b = aux_load_bin<T>(A, ou, eu, km);
+      const cx<T> w = cconj(IMP_LDG(tab + k));   // e^{+2 pi i k/N}
+      {
+        const cx<T> s = cadd(a, cconj(b)), d = csub(a, cconj(b));
+        Z[(int64_t)(k == M ? 0 : k) * ew] = cadd(s, mul_pi(cmul(w, d)));
+      }
+      if (k != 0 && k != km) {
+        const cx<T> s = cadd(b, cconj(a)), d = csub(b, cconj(a));
+        const cx<T> wm = mk<T>(-w.x, w.y);
+        Z[(int64_t)km * ew] = cadd(s, mul_pi(cmul(wm, d)));
+      }
+    } break;
+    case AUX_R2C_PRE_ODD:
+      ((cx<T> *)A.out)[ow + (int64_t)e * ew] = mk<T>(((const T *)A.in)[ou + (int64_t)e * eu], (T)0);
+      break;
+    case AUX_R2C_POST_ODD:
+      aux_store_bin<T>(A, ou, eu, e, ((const cx<T> *)A.in)[ow + (int64_t)e * ew]);
+      break;
+    case AUX_C2R_PRE_ODD: {     // e = k in 0..(N-1)/2
+      const cx<T> v = aux_load_bin<T>(A, ou, eu, e);
+      cx<T> *Z = (cx<T> *)A.out + ow;
+      Z[(int64_t)e * ew] = v;
+      if (e > 0) Z[(int64_t)(N - e) * ew] = cconj(v);
+    } break;
+    case AUX_C2R_POST_ODD:
+      ((T *)A.out)[ou + (int64_t)e * eu] = ((const cx<T> *)A.in)[ow + (int64_t)e * ew].x * (T)A.fct;
+      break;
+    case AUX_BLUE_PRE: {        // e = n in 0..n2
+      cx<T> v = mk<T>((T)0, (T)0);
+      if (e < N) {
+        v = ((const cx<T> *)A.in)[ou + (int64_t)e * eu];
+        if (A.flags & F_CONJ_IN) v.y = -v.y;
+        v = cmul(v, cconj(IMP_LDG(tab + e)));
+      }
+      ((cx<T> *)A.out)[ow + (int64_t)e * ew] = v;
+    } break;
+    case AUX_BLUE_POST: {       // e = k in 0..L
+      cx<T> v = cmul(((const cx<T> *)A.in)[ow + (int64_t)e * ew], cconj(IMP_LDG(tab + e)));
+      const T f = (T)A.fct;
+      v.x *= f; v.y *= f;
+      if (A.flags & F_CONJ_RESULT) v.y = -v.y;
+      ((cx<T> *)A.out)[ou + (int64_t)e * eu] = v;
+    } break;
+    default: break;
+  }
+}
+
 }  // namespace impulse

@@ -23,6 +23,8 @@ int launch_transpose(int dtype, const void *in, void *out, size_t rows, size_t c
 // out[b][r][c] = in[b][r][c] for complex matrices with independent leading dimensions / batch strides
 int launch_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
                   size_t batch, size_t bs_in, size_t bs_out, int sm_count, void *stream);
+// elementwise conversion / chirp pass around a long transform (AuxJob)
+int launch_aux(const AuxJob &job, int sm_count, void *stream);
 // genuine Hartley fold of a contiguous half spectrum into the real output (CombineJob)
 int launch_hartley_combine(const CombineJob &job, int sm_count, void *stream);
 }  // namespace impulse

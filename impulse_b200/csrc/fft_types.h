@@ -184,6 +184,36 @@ struct LineJob {
   Phase ph[kMaxPhases];
 };
 
+// Elementwise passes around a complex transform whose line does not fit in one CTA's shared memory: the
+// real <-> complex conversions of long real transforms and the chirp multiplications of long Bluestein
+// transforms.  One thread per element of an N-D iteration space; `work` is the complex work array, `user`
+// the caller-side array (real or complex elements depending on the mode / layout).
+enum AuxMode : int {
+  AUX_R2C_POST_EVEN = 1,  // work Z[0..M) (M = N/2 point FFT of the packed line) -> bins 0..M in the output layout
+  AUX_C2R_PRE_EVEN = 2,   // half spectrum -> Z[0..M) whose backward FFT is the packed real line
+  AUX_R2C_PRE_ODD = 3,    // real line -> complex line with zero imaginary part
+  AUX_R2C_POST_ODD = 4,   // bins 0..(N-1)/2 of the N-point FFT -> output layout
+  AUX_C2R_PRE_ODD = 5,    // half spectrum -> Hermitian-extended N-point line
+  AUX_C2R_POST_ODD = 6,   // real parts
+  AUX_BLUE_PRE = 7,       // w[n] = x[n] * conj(b[n]) (n < L), 0 (L <= n < n2)      pocketfft.c:1954-1968
+  AUX_BLUE_POST = 8,      // y[k] = w[k] * conj(b[k]) * fct (k < L)                 pocketfft.c:1993-2005
+};
+constexpr int kMaxAuxDims = 8;
+struct AuxJob {
+  int mode, dtype, layout, ndim;   // layout: RealLayout of the user side (real modes)
+  uint32_t flags;                  // F_CONJ_IN (c2r forward / backward Bluestein input), F_CONJ_RESULT
+  uint32_t N;                      // real length (real modes) or L (Bluestein modes)
+  uint32_t M;                      // length of the complex work line
+  uint32_t shape[kMaxAuxDims];     // iteration space; the LAST dimension runs along the transform axis
+  int64_t s_user[kMaxAuxDims];     // strides in elements of the respective side
+  int64_t s_work[kMaxAuxDims];
+  const void *in;
+  void *out;
+  const void *tab;                 // real modes: W_N^k (k <= N/2); Bluestein: b[n]
+  double fct;
+  uint64_t total;
+};
+
 // Genuine (non-separable) Hartley transform, last step (pocketfft_hdronly.h:3432-3444): the contiguous
 // half spectrum F of an N-D r2c is folded into the real output, out[k] = Re F[k] + Im F[k] and
 // out[-k mod shape] = Re F[k] - Im F[k].  One element of F per thread.

@@ -788,6 +788,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     if (b == BUF_IN) { *lo = plan->in_lo; *hi = plan->in_hi; }
     else if (b == BUF_OUT) { *lo = plan->out_lo; *hi = plan->out_hi; }
     else if (b == BUF_TMP3) { *lo = 0; *hi = (ptrdiff_t)plan->tmp3_bytes; }
+    else if (b == BUF_TMP4) { *lo = 0; *hi = (ptrdiff_t)plan->tmp4_bytes; }
     else { *lo = 0; *hi = (ptrdiff_t)plan->tmp_bytes; }
   };
 
@@ -841,6 +842,77 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
                 esz_in, esz_out, BUF_TMP2, dst, -(int64_t)slo + src_base, dst_base, takes_fct, umul_mod);
   };
 
+  // elementwise pass around a long transform (AuxJob); `dims` = batch dims with user/work strides, the
+  // transform axis is appended as the last dimension
+  auto emit_aux = [&](int mode, int layout, uint32_t flags, uint32_t N, uint32_t M, uint32_t extent,
+                      const std::vector<Dim> &dims /*sin = user side, sout = work side*/, int64_t es_user, int64_t es_work,
+                      const void *tab, int src, int dst, bool takes_fct) -> int {
+    if (dims.size() + 1 > (size_t)kMaxAuxDims) { *err = "too many dimensions"; return ERR_INVALID; }
+    Step st;
+    st.aux = true;
+    st.src = src; st.dst = dst; st.takes_fct = takes_fct;
+    AuxJob &A = st.aj;
+    A.mode = mode; A.dtype = d.dtype; A.layout = layout; A.flags = flags; A.N = N; A.M = M;
+    A.in = nullptr; A.out = nullptr; A.tab = tab; A.fct = 1.0;
+    A.ndim = (int)dims.size() + 1;
+    A.total = extent;
+    for (size_t i = 0; i < dims.size(); ++i) {
+      A.shape[i] = (uint32_t)dims[i].n; A.s_user[i] = dims[i].sin; A.s_work[i] = dims[i].sout;
+      A.total *= dims[i].n;
+    }
+    A.shape[dims.size()] = extent; A.s_user[dims.size()] = es_user; A.s_work[dims.size()] = es_work;
+    plan->steps.push_back(st);
+    return ST_OK;
+  };
+
+  // complex line transform of any supported length: direct / split (emit_c2c), or Bluestein with the
+  // n2-point work array in global memory when it does not fit a CTA
+  std::function<int(bool, uint32_t, int64_t, int64_t, const std::vector<Dim> &, size_t, size_t, int, int, bool, uint64_t)>
+      c2c_line = [&](bool forward, uint32_t N, int64_t es_in, int64_t es_out, const std::vector<Dim> &dims, size_t esz_in,
+                     size_t esz_out, int src, int dst, bool takes_fct, uint64_t umul_mod) -> int {
+    const Engine1D *E = nullptr;
+    int rc = status_engine(N, d.dtype, &E, err);
+    if (rc) return rc;
+    if (!(E->blue && (!fits_one(E->n_fft) || env_int("IMPULSE_FFT_FORCE_BIGBLUE", 0))))
+      return emit_c2c(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, 0, 0, takes_fct, nullptr, umul_mod);
+    if (umul_mod) { *err = "fused multiply is available for single- and split-launch complex transforms"; return ERR_UNSUPPORTED; }
+    // ---- multi-launch Bluestein:
+    //   1. chirp, zero-padded to n2, into the work array [lines][n2]
+    //   2. forward FFT(n2) (two launches), output multiplied by FFT(b)/n2
+    //   3. backward FFT(n2) (two launches)
+    //   4. chirp + store
+    const uint32_t n2 = E->n_fft;
+    const void *bkf_nat = nullptr;
+    rc = bluestein_natural_table(N, d.dtype, &bkf_nat, err);
+    if (rc) return rc;
+    uint64_t nlines = 1;
+    std::vector<Dim> d_in, d_w, d_out;  // batch dims: source->work, work->work, work->destination
+    for (auto &dm : dims) {
+      d_in.push_back({dm.n, dm.sin, (int64_t)(nlines * n2)});
+      d_w.push_back({dm.n, (int64_t)(nlines * n2), (int64_t)(nlines * n2)});
+      d_out.push_back({dm.n, dm.sout, (int64_t)(nlines * n2)});   // (user, work) for emit_aux; swapped for emit below
+      nlines *= dm.n;
+    }
+    plan->tmp3_bytes = std::max<size_t>(plan->tmp3_bytes, (size_t)nlines * n2 * csize_g);
+    const bool line_fits = fits_one((uint64_t)N + 1) && !env_int("IMPULSE_FFT_FORCE_AUXBLUE", 0);
+    if (line_fits) {   // stage in/out through the line kernel (strided sides stay coalesced)
+      rc = emit(KIND_C2C, RL_HERMITIAN, forward, N, es_in, 1, d_in, -1, 0, nullptr, 0, 1, esz_in, csize_g, src, BUF_TMP3, 0, 0, false);
+    } else {           // the line itself is too long for a CTA: elementwise chirp passes
+      rc = emit_aux(AUX_BLUE_PRE, 0, forward ? 0u : (uint32_t)F_CONJ_IN, N, n2, n2, d_in, es_in, 1, E->d_bk, src, BUF_TMP3, false);
+    }
+    if (rc) return rc;
+    rc = emit_c2c(true, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, bkf_nat, 0);
+    if (rc) return rc;
+    rc = emit_c2c(false, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, nullptr, 0);
+    if (rc) return rc;
+    if (line_fits) {
+      std::vector<Dim> d_o;
+      for (auto &x : d_out) d_o.push_back({x.n, x.sout, x.sin});
+      return emit(KIND_C2C, RL_HERMITIAN, forward, N, 1, es_out, d_o, -1, 0, nullptr, 0, 2, csize_g, esz_out, BUF_TMP3, dst, 0, 0, takes_fct);
+    }
+    return emit_aux(AUX_BLUE_POST, 0, forward ? 0u : (uint32_t)F_CONJ_RESULT, N, n2, N, d_out, es_out, 1, E->d_bk, BUF_TMP3, dst, takes_fct);
+  };
+
   // one batched line transform along `axis`
   auto add_axis = [&](int kind, int layout, bool forward, size_t axis, uint32_t N,
                       const std::vector<size_t> &bshape, const std::vector<ptrdiff_t> &sin, size_t esz_in,
@@ -854,45 +926,94 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     const int64_t es_in = sin[axis] / (ptrdiff_t)esz_in, es_out = sout[axis] / (ptrdiff_t)esz_out;
     if (kind == KIND_DCT || kind == KIND_DST)
       return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, nullptr, 0, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
-    const uint32_t L = (kind != KIND_C2C && N % 2 == 0) ? N / 2 : N;  // complex length run on the device
+    if (kind == KIND_C2C) return c2c_line(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, takes_fct, umul_mod);
+    if (umul_mod) { *err = "fused multiply is a c2c option"; return ERR_INVALID; }
+    const bool even = N % 2 == 0;
+    const uint32_t L = even ? N / 2 : N;  // complex length run on the device
     const Engine1D *E = nullptr;
     int rc = status_engine(L, d.dtype, &E, err);
     if (rc) return rc;
-    if (umul_mod && (kind != KIND_C2C || (E->blue && !fits_one(E->n_fft)))) {
-      *err = "fused multiply is available for single- and split-launch complex transforms";
-      return ERR_UNSUPPORTED;
-    }
-    if (E->blue && (!fits_one(E->n_fft) || env_int("IMPULSE_FFT_FORCE_BIGBLUE", 0))) {
-      // ---- multi-launch Bluestein: the L-point line fits a CTA, its n2-point work array does not.
-      //   1. load + (c2r pre-twiddle) + chirp, zero-padded to n2, into the work array [lines][n2]
-      //   2. forward FFT(n2) (two launches), output multiplied by FFT(b)/n2
-      //   3. backward FFT(n2) (two launches)
-      //   4. chirp + the transform's own store
-      if (!fits_one(L + 1)) { *err = "line of " + std::to_string(L) + " points does not fit in shared memory"; return ERR_UNSUPPORTED; }
-      const uint32_t n2 = E->n_fft;
-      const void *bkf_nat = nullptr;
-      rc = bluestein_natural_table(L, d.dtype, &bkf_nat, err);
-      if (rc) return rc;
-      uint64_t nlines = 1;
-      std::vector<Dim> d_in, d_w, d_out;  // batch dims: source->work, work->work, work->destination
-      for (auto &dm : dims) {
-        d_in.push_back({dm.n, dm.sin, (int64_t)(nlines * n2)});
-        d_w.push_back({dm.n, (int64_t)(nlines * n2), (int64_t)(nlines * n2)});
-        d_out.push_back({dm.n, (int64_t)(nlines * n2), dm.sout});
-        nlines *= dm.n;
+    const bool big = !fits_one((uint64_t)L + 1) || env_int("IMPULSE_FFT_FORCE_BIGREAL", 0);
+    if (!big) {
+      if (E->blue && (!fits_one(E->n_fft) || env_int("IMPULSE_FFT_FORCE_BIGBLUE", 0))) {
+        // multi-launch Bluestein around a real line that fits a CTA: stage in (load + pre-twiddle + chirp),
+        // two FFT(n2) in global memory, stage out (chirp + the transform's own store)
+        const uint32_t n2 = E->n_fft;
+        const void *bkf_nat = nullptr;
+        rc = bluestein_natural_table(L, d.dtype, &bkf_nat, err);
+        if (rc) return rc;
+        uint64_t nlines = 1;
+        std::vector<Dim> d_in, d_w, d_out;
+        for (auto &dm : dims) {
+          d_in.push_back({dm.n, dm.sin, (int64_t)(nlines * n2)});
+          d_w.push_back({dm.n, (int64_t)(nlines * n2), (int64_t)(nlines * n2)});
+          d_out.push_back({dm.n, (int64_t)(nlines * n2), dm.sout});
+          nlines *= dm.n;
+        }
+        plan->tmp3_bytes = std::max<size_t>(plan->tmp3_bytes, (size_t)nlines * n2 * csize_g);
+        rc = emit(kind, layout, forward, N, es_in, 1, d_in, -1, 0, nullptr, 0, 1, esz_in, csize_g, src, BUF_TMP3, 0, 0, false);
+        if (rc) return rc;
+        rc = emit_c2c(true, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, bkf_nat, 0);
+        if (rc) return rc;
+        rc = emit_c2c(false, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, nullptr, 0);
+        if (rc) return rc;
+        return emit(kind, layout, forward, N, 1, es_out, d_out, -1, 0, nullptr, 0, 2, csize_g, esz_out, BUF_TMP3, dst, 0, 0, takes_fct);
       }
-      plan->tmp3_bytes = std::max<size_t>(plan->tmp3_bytes, (size_t)nlines * n2 * csize_g);
-      rc = emit(kind, layout, forward, N, es_in, 1, d_in, -1, 0, nullptr, 0, 1, esz_in, csize_g, src, BUF_TMP3, 0, 0, false);
-      if (rc) return rc;
-      rc = emit_c2c(true, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, bkf_nat, 0);
-      if (rc) return rc;
-      rc = emit_c2c(false, n2, 1, 1, d_w, csize_g, csize_g, BUF_TMP3, BUF_TMP3, 0, 0, false, nullptr, 0);
-      if (rc) return rc;
-      return emit(kind, layout, forward, N, 1, es_out, d_out, -1, 0, nullptr, 0, 2, csize_g, esz_out, BUF_TMP3, dst, 0, 0, takes_fct);
+      return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, nullptr, 0, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
     }
-    if (kind == KIND_C2C)
-      return emit_c2c(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, 0, 0, takes_fct, nullptr, umul_mod);
-    return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, nullptr, 0, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
+    // ---- long real lines: the complex transform runs through c2c_line on a work array [lines][L] (or, for
+    // even N, directly on the packed view of the real side), with elementwise conversion passes around it
+    if (layout == RL_HALFCOMPLEX_NEG) { *err = "r2r_fftpack with real2hermitian != forward is limited to lines that fit one CTA"; return ERR_UNSUPPORTED; }
+    const bool r2c = kind == KIND_R2C;
+    const void *twr = nullptr;
+    if (even) { rc = real_twiddle(N, d.dtype, &twr, err); if (rc) return rc; }
+    uint64_t nlines = 1;
+    std::vector<Dim> d_uw, d_ww, d_view_in, d_view_out;   // (user, work), (work, work), packed complex views of the real side
+    bool view_ok = true;
+    for (auto &dm : dims) {
+      d_uw.push_back({dm.n, r2c ? dm.sout : dm.sin, (int64_t)(nlines * L)});
+      d_ww.push_back({dm.n, (int64_t)(nlines * L), (int64_t)(nlines * L)});
+      if ((r2c ? dm.sin : dm.sout) % 2) view_ok = false;
+      d_view_in.push_back({dm.n, dm.sin / 2, (int64_t)(nlines * L)});
+      d_view_out.push_back({dm.n, (int64_t)(nlines * L), dm.sout / 2});
+      nlines *= dm.n;
+    }
+    plan->tmp4_bytes = std::max<size_t>(plan->tmp4_bytes, (size_t)nlines * L * csize_g);
+    if (even) {
+      if ((r2c ? es_in : es_out) != 1 || !view_ok) {
+        *err = "real lines of more than " + std::to_string(2 * (budget_g / csize_g - S_g - 1)) +
+               " points must be contiguous with even row strides";
+        return ERR_UNSUPPORTED;
+      }
+      if (r2c) {
+        plan->cplx_view_in = true;
+        rc = c2c_line(true, L, 1, 1, d_view_in, csize_g, csize_g, src, BUF_TMP4, false, 0);
+        if (rc) return rc;
+        return emit_aux(AUX_R2C_POST_EVEN, layout, forward ? 0u : (uint32_t)F_CONJ_RESULT, N, L, L + 1, d_uw, es_out, 1, twr,
+                        BUF_TMP4, dst, takes_fct);
+      }
+      plan->cplx_view_out = true;
+      rc = emit_aux(AUX_C2R_PRE_EVEN, layout, forward ? (uint32_t)F_CONJ_IN : 0u, N, L, L / 2 + 1, d_uw, es_in, 1, twr, src,
+                    BUF_TMP4, false);
+      if (rc) return rc;
+      return c2c_line(false, L, 1, 1, d_view_out, csize_g, csize_g, BUF_TMP4, dst, takes_fct, 0);
+    }
+    if (r2c) {
+      rc = emit_aux(AUX_R2C_PRE_ODD, layout, 0, N, L, N, [&] { std::vector<Dim> v; uint64_t nl = 1; for (auto &dm : dims) { v.push_back({dm.n, dm.sin, (int64_t)(nl * L)}); nl *= dm.n; } return v; }(),
+                    es_in, 1, nullptr, src, BUF_TMP4, false);
+      if (rc) return rc;
+      rc = c2c_line(true, L, 1, 1, d_ww, csize_g, csize_g, BUF_TMP4, BUF_TMP4, false, 0);
+      if (rc) return rc;
+      return emit_aux(AUX_R2C_POST_ODD, layout, forward ? 0u : (uint32_t)F_CONJ_RESULT, N, L, (N + 1) / 2, d_uw, es_out, 1, nullptr,
+                      BUF_TMP4, dst, takes_fct);
+    }
+    rc = emit_aux(AUX_C2R_PRE_ODD, layout, forward ? (uint32_t)F_CONJ_IN : 0u, N, L, (N + 1) / 2, d_uw, es_in, 1, nullptr, src,
+                  BUF_TMP4, false);
+    if (rc) return rc;
+    rc = c2c_line(false, L, 1, 1, d_ww, csize_g, csize_g, BUF_TMP4, BUF_TMP4, false, 0);
+    if (rc) return rc;
+    return emit_aux(AUX_C2R_POST_ODD, layout, 0, N, L, N, [&] { std::vector<Dim> v; uint64_t nl = 1; for (auto &dm : dims) { v.push_back({dm.n, dm.sout, (int64_t)(nl * L)}); nl *= dm.n; } return v; }(),
+                    es_out, 1, nullptr, BUF_TMP4, dst, takes_fct);
   };
 
   int rc = ST_OK;

@@ -86,13 +86,15 @@ struct LineSpec {
   int blue_stage = 0;  // multi-launch Bluestein: 1 = load+chirp+zero-pad to scratch, 2 = scratch+chirp+store
 };
 
-enum BufId : int { BUF_IN = 0, BUF_OUT = 1, BUF_TMP = 2, BUF_TMP2 = 3, BUF_TMP3 = 4 };
+enum BufId : int { BUF_IN = 0, BUF_OUT = 1, BUF_TMP = 2, BUF_TMP2 = 3, BUF_TMP3 = 4, BUF_TMP4 = 5 };
 
 struct Step {
   LineJob job;
   LaunchCfg cfg;
   int src = BUF_IN, dst = BUF_OUT;
   int64_t src_off_bytes = 0, dst_off_bytes = 0;  // host-looped outer dims
+  bool aux = false;         // not a line job: the elementwise pass `aj` (long real / long Bluestein transforms)
+  AuxJob aj{};
   bool combine = false;     // not a line job: the genuine-Hartley fold `cj` (src/dst as usual)
   CombineJob cj{};
   bool takes_umul = false;  // this step multiplies its output by the caller's array (impulse_fft_c2c_mul)
@@ -117,6 +119,10 @@ struct NdPlan {
   size_t tmp_bytes = 0;   // c2r N-D intermediate (hdronly.h:3384)
   size_t tmp2_bytes = 0;  // four-step scratch
   size_t tmp3_bytes = 0;  // multi-launch Bluestein work array [lines][n2]
+  size_t tmp4_bytes = 0;  // long real transforms: complex work array [lines][L]
+  // long even real transforms address the real side as packed complex pairs: the base pointer must be
+  // aligned to a complex element
+  bool cplx_view_in = false, cplx_view_out = false;
   // byte spans touched relative to the base pointers (for host staging)
   ptrdiff_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
   bool empty = false;  // zero-size array: nothing to do

@@ -113,10 +113,21 @@ static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_
   int rc = g_cache->build_nd(d, &plan, &g_err);
   if (rc) return rc;
   if (plan.empty) return 0;
-  std::vector<unsigned char> tmp(plan.tmp_bytes + 16), tmp2(plan.tmp2_bytes + 16, 0xCD), tmp3(plan.tmp3_bytes + 16, 0xCD);
+  std::vector<unsigned char> tmp(plan.tmp_bytes + 16), tmp2(plan.tmp2_bytes + 16, 0xCD), tmp3(plan.tmp3_bytes + 16, 0xCD),
+      tmp4(plan.tmp4_bytes + 16, 0xCD);
   for (Step &st : plan.steps) {
-    const unsigned char *bufs_in[5] = {(const unsigned char *)in, (const unsigned char *)out, tmp.data(), tmp2.data(), tmp3.data()};
-    unsigned char *bufs_out[5] = {nullptr, (unsigned char *)out, tmp.data(), tmp2.data(), tmp3.data()};
+    const unsigned char *bufs_in[6] = {(const unsigned char *)in, (const unsigned char *)out, tmp.data(), tmp2.data(), tmp3.data(), tmp4.data()};
+    unsigned char *bufs_out[6] = {nullptr, (unsigned char *)out, tmp.data(), tmp2.data(), tmp3.data(), tmp4.data()};
+    if (st.aux) {
+      AuxJob aj = st.aj;
+      aj.in = bufs_in[st.src] + st.src_off_bytes;
+      aj.out = bufs_out[st.dst] + st.dst_off_bytes;
+      aj.fct = st.takes_fct ? fct : 1.0;
+      for (uint64_t g = 0; g < aj.total; ++g) {
+        if (dtype == DT_F64) aux_one<double>(aj, g); else aux_one<float>(aj, g);
+      }
+      continue;
+    }
     if (st.combine) {
       CombineJob cj = st.cj;
       cj.in = bufs_in[st.src] + st.src_off_bytes;

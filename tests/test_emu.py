@@ -362,3 +362,72 @@ def test_convolve_axis(shape, axis):
     y = x.copy()
     emu.convolve_axis(y, y, axis, m, fct=1.0 / n)   # in place
     assert np.linalg.norm(y - want) / np.linalg.norm(want) < 1e-13
+
+
+def _real_roundtrip_case(n, rows, dtype, layout="hermitian"):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((rows, n)).astype(dtype)
+    cdt = np.complex128 if dtype == np.float64 else np.complex64
+    tol = 1e-12 * np.log2(max(n, 2)) if dtype == np.float64 else 1e-5 * np.log2(max(n, 2))
+    want = np.fft.rfft(x.astype(np.float64), axis=1)
+    if layout == "hermitian":
+        spec = emu.nd("r2c", x, np.empty((rows, n // 2 + 1), cdt), [rows, n], [1], True, 0.5)
+        assert oracle.rel_l2(spec, 0.5 * want) < tol, (n, "r2c")
+        back = emu.nd("c2r", spec, np.empty_like(x), [rows, n], [1], False, 2.0 / n)
+        assert oracle.rel_l2(back, x) < tol, (n, "c2r")
+        conj = emu.nd("r2c", x, np.empty((rows, n // 2 + 1), cdt), [rows, n], [1], False, 1.0)
+        assert oracle.rel_l2(conj, np.conj(want)) < tol, (n, "r2c backward")
+    else:
+        packed = emu.nd("r2c", x, np.empty_like(x), [rows, n], [1], True, 1.0, layout="halfcomplex")
+        assert oracle.rel_l2(packed, oracle._halfcomplex_pack(want, n)) < tol, (n, "packed")
+        back = emu.nd("c2r", packed, np.empty_like(x), [rows, n], [1], False, 1.0 / n, layout="halfcomplex")
+        assert oracle.rel_l2(back, x) < tol, (n, "unpacked")
+
+
+@pytest.mark.parametrize("n", [32768, 65536, 30000, 28930, 29999, 40001])
+def test_long_real_lines(n):
+    """Real transforms whose complex line does not fit one CTA (N/2 > 14464, odd N > 14464): complex
+    transform on a work array (split / Bluestein) with elementwise conversion passes around it."""
+    _real_roundtrip_case(n, 2, np.float64)
+    if n in (32768, 29999):
+        _real_roundtrip_case(n, 2, np.float64, "halfcomplex")
+        _real_roundtrip_case(n, 1, np.float32)
+
+
+@pytest.mark.parametrize("n", [6, 7, 64, 100, 191, 1000, 4099])
+def test_long_real_path_forced_on_short_lines(n, monkeypatch):
+    """The same plan shape forced on short lines, where every layout can be compared cheaply."""
+    monkeypatch.setenv("IMPULSE_FFT_FORCE_BIGREAL", "1")
+    _real_roundtrip_case(n, 3, np.float64)
+    _real_roundtrip_case(n, 3, np.float64, "halfcomplex")
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, 3, n))
+    full = emu.nd("r2c", x, np.empty((2, 3, n), np.complex128), [2, 3, n], [2], True, 1.0, layout="fullsym")
+    assert oracle.rel_l2(full, np.fft.fft(x, axis=2)) < 1e-12
+    hart = emu.r2r_real("separable_hartley", x, np.empty_like(x), [2])
+    assert oracle.rel_l2(hart, oracle.hartley_numpy(x, [2])) < 1e-12
+    y = rng.standard_normal((n, 4))                       # strided axis: only the even-N view needs contiguity
+    if n % 2:
+        spec = emu.nd("r2c", y, np.empty((n // 2 + 1, 4), np.complex128), [n, 4], [0], True, 1.0)
+        assert oracle.rel_l2(spec, np.fft.rfft(y, axis=0)) < 1e-12
+    else:
+        with pytest.raises(emu.EmuError):
+            emu.nd("r2c", y, np.empty((n // 2 + 1, 4), np.complex128), [n, 4], [0], True, 1.0)
+
+
+@pytest.mark.parametrize("n", [89, 191, 4099, 100003, 20011])
+def test_long_bluestein_lines(n, monkeypatch):
+    """Complex Bluestein lengths whose LINE does not fit one CTA (elementwise chirp passes), and the same plan
+    forced on short prime lengths."""
+    if n < 20000:
+        monkeypatch.setenv("IMPULSE_FFT_FORCE_BIGBLUE", "1")
+        monkeypatch.setenv("IMPULSE_FFT_FORCE_AUXBLUE", "1")
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+    tol = 1e-12 * np.log2(n)
+    for fwd in (True, False):
+        got = emu.nd("c2c", x, np.empty_like(x), [2, n], [1], fwd, 0.5)
+        want = 0.5 * (np.fft.fft(x, axis=1) if fwd else np.fft.ifft(x, axis=1) * n)
+        assert oracle.rel_l2(got, want) < tol, (n, fwd)
+    if n == 20011:                                        # odd real line on top of it
+        _real_roundtrip_case(n, 1, np.float64)

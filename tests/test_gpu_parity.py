@@ -736,3 +736,42 @@ def test_convolve_axis(ib, torch_mod, checker):
     _lib.check(L.impulse_fft_convolve_axis(_lib.F32, 3, (C.c_size_t * 3)(2, 4096, 32), st, st, 1, x.data_ptr(), x.data_ptr(), 1.0,
                                            m.data_ptr(), 4096 * 32, None))
     assert ib.launch_count() - before == 3
+
+
+def test_long_lines(ib, torch_mod, checker):
+    """Lines beyond one CTA's shared memory: real transforms with N/2 > 14464 or odd N > 14464 (complex
+    transform on a work array + elementwise conversion passes), complex Bluestein lengths whose line does
+    not fit (elementwise chirp passes), through the high-level API (in-place packed, rfft) and DataDesc."""
+    rng = np.random.default_rng(101)
+    for n in (32768, 65536, 30000, 29999, 40001, 131072, 1 << 20):
+        rows = 2 if n < (1 << 20) else 1
+        x = rng.uniform(-0.5, 0.5, (rows, n))
+        xd = torch_mod.from_numpy(x).cuda()
+        spec = torch_mod.empty((rows, n // 2 + 1), dtype=torch_mod.complex128, device="cuda")
+        apply_nd(ib, "r2c", xd, spec, [1], True, 1.0)
+        want = checker.r2c(x, [1], True, 1.0)
+        assert oracle.max_row_rel_l2(spec.cpu().numpy(), want) <= tol(n), n
+        back = torch_mod.empty_like(xd)
+        apply_nd(ib, "c2r", spec, back, [1], False, 1.0 / n)
+        assert oracle.max_row_rel_l2(back.cpu().numpy(), x) <= 2e-15 * np.log2(n), n
+        d = xd[0].clone()                               # FFTPACK packing, in place (the C-backend API)
+        ib.fft_inplace(d, forward=True)
+        wantp = checker.rfft_rows(x[:1].copy(), True, 1.0)[0]
+        assert oracle.rel_l2(d.cpu().numpy(), wantp) <= tol(n), n
+        ib.fft_inplace(d, forward=False)
+        assert oracle.rel_l2(d.cpu().numpy(), x[0]) <= 2e-15 * np.log2(n), n
+    xs = rng.uniform(-0.5, 0.5, (3, 32768)).astype(np.float32)          # float32, host buffers
+    out = np.empty((3, 16385), np.complex64)
+    apply_nd(ib, "r2c", xs, out, [1], True, 1.0)
+    assert oracle.max_row_rel_l2(out, checker.r2c(xs, [1], True, 1.0)) <= tol(32768, np.float32)
+    for n in (100003, 20011, 65537):                                     # complex primes
+        z = rnd(rng, (2, n), np.complex128)
+        zd = torch_mod.from_numpy(z).cuda()
+        for fwd in (True, False):
+            got = apply_nd(ib, "c2c", zd, torch_mod.empty_like(zd), [1], fwd, 0.5).cpu().numpy()
+            assert oracle.max_row_rel_l2(got, checker.c2c(z, [1], fwd, 0.5)) <= tol(n), (n, fwd)
+    # 2-D real transform whose last axis is long
+    img = rng.uniform(-0.5, 0.5, (6, 40000))
+    got = apply_nd(ib, "r2c", torch_mod.from_numpy(img).cuda(), torch_mod.empty((6, 20001), dtype=torch_mod.complex128,
+                                                                                  device="cuda"), [0, 1], True, 1.0)
+    assert oracle.rel_l2(got.cpu().numpy(), checker.r2c(img, [0, 1], True, 1.0)) <= tol(40000)
