@@ -822,7 +822,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     uint32_t N1 = 1;
     for (uint32_t f = 1; (uint64_t)f * f <= N; ++f) if (N % f == 0) N1 = f;
     const uint32_t N2 = N / N1;
-    if (N1 < 2 || N > (1u << 22)) { *err = "transform length " + std::to_string(N) + " is not supported by the two-kernel split"; return ERR_UNSUPPORTED; }
+    if (N1 < 2 || !fits_one(N2) || N > (1u << 28)) { *err = "transform length " + std::to_string(N) + " is not supported by the two-kernel split"; return ERR_UNSUPPORTED; }
     ptrdiff_t slo, shi;
     span_lo_hi(src, &slo, &shi);
     plan->tmp2_bytes = std::max<size_t>(plan->tmp2_bytes, (size_t)(shi - slo));
@@ -870,11 +870,13 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   std::function<int(bool, uint32_t, int64_t, int64_t, const std::vector<Dim> &, size_t, size_t, int, int, bool, uint64_t)>
       c2c_line = [&](bool forward, uint32_t N, int64_t es_in, int64_t es_out, const std::vector<Dim> &dims, size_t esz_in,
                      size_t esz_out, int src, int dst, bool takes_fct, uint64_t umul_mod) -> int {
+    // (no tables are built here for lengths that factor: a split length never runs as ONE engine)
+    const bool blue = N > 1 && choose_radices(N).empty();
+    if (!(blue && (!fits_one(bluestein_size(N)) || env_int("IMPULSE_FFT_FORCE_BIGBLUE", 0))))
+      return emit_c2c(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, 0, 0, takes_fct, nullptr, umul_mod);
     const Engine1D *E = nullptr;
     int rc = status_engine(N, d.dtype, &E, err);
     if (rc) return rc;
-    if (!(E->blue && (!fits_one(E->n_fft) || env_int("IMPULSE_FFT_FORCE_BIGBLUE", 0))))
-      return emit_c2c(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, 0, 0, takes_fct, nullptr, umul_mod);
     if (umul_mod) { *err = "fused multiply is available for single- and split-launch complex transforms"; return ERR_UNSUPPORTED; }
     // ---- multi-launch Bluestein:
     //   1. chirp, zero-padded to n2, into the work array [lines][n2]
@@ -930,11 +932,12 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     if (umul_mod) { *err = "fused multiply is a c2c option"; return ERR_INVALID; }
     const bool even = N % 2 == 0;
     const uint32_t L = even ? N / 2 : N;  // complex length run on the device
-    const Engine1D *E = nullptr;
-    int rc = status_engine(L, d.dtype, &E, err);
-    if (rc) return rc;
+    int rc = ST_OK;
     const bool big = !fits_one((uint64_t)L + 1) || env_int("IMPULSE_FFT_FORCE_BIGREAL", 0);
     if (!big) {
+      const Engine1D *E = nullptr;
+      rc = status_engine(L, d.dtype, &E, err);
+      if (rc) return rc;
       if (E->blue && (!fits_one(E->n_fft) || env_int("IMPULSE_FFT_FORCE_BIGBLUE", 0))) {
         // multi-launch Bluestein around a real line that fits a CTA: stage in (load + pre-twiddle + chirp),
         // two FFT(n2) in global memory, stage out (chirp + the transform's own store)

@@ -431,3 +431,12 @@ def test_long_bluestein_lines(n, monkeypatch):
         assert oracle.rel_l2(got, want) < tol, (n, fwd)
     if n == 20011:                                        # odd real line on top of it
         _real_roundtrip_case(n, 1, np.float64)
+
+
+def test_split_beyond_four_million_points():
+    """The two-launch split has no table of the whole length: 2^23 points (sub-transforms 2048 x 4096)."""
+    n = 1 << 23
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).reshape(1, n)
+    got = emu.nd("c2c", x, np.empty_like(x), [1, n], [1], True, 1.0)
+    assert oracle.rel_l2(got, np.fft.fft(x, axis=1)) < 1e-14
