@@ -41,6 +41,8 @@ WORKLOADS = {
     "c2c_16384x4096_c128": ("c2c", 16384, 4096, "f64"),
     "c2c_8192x8192_c128": ("c2c", 8192, 8192, "f64"),
     "c2c_131072x1024_c64": ("c2c", 131072, 1024, "f32"),
+    "c2c_131072x512_c128": ("c2c", 131072, 512, "f64"),
+    "c2c_262144x256_c128": ("c2c", 262144, 256, "f64"),
     "fft2_8192x8192_c128": ("fft2", 8192, 8192, "f64"),
     "filter2d_64x4096x4096_f32": ("filter2d", 64, 4096, "f32"),
     "fftconvolve_4096x16384_k257_f64": ("fftconv", 4096, 16384, "f64"),   # rows (*) 257-tap FIR, full
