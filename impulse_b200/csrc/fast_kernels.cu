@@ -585,7 +585,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
 }
 
 namespace {
-template <typename T, int R1, int R2, int R3, int E, int MINB>
+template <typename T, int R1, int R2, int R3, int E, int MINB, bool REAL_ONLY = false>
 int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
@@ -595,9 +595,10 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   const bool bwd = kind == F3_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == F3_R2C ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
   typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, const cx<T> *, const cx<T> *, const cx<T> *, T, unsigned int *);
   kern_t k = nullptr;
+  if (REAL_ONLY && kind == F3_C2C) return (int)cudaErrorInvalidValue;   // complex rows of this length use the two-pass kernels
   switch (kind * 2 + (bwd ? 1 : 0)) {
-    case 0: k = fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB>; break;
-    case 1: k = fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB>; break;
+    case 0: k = fast3_kernel<T, R1, R2, R3, E, REAL_ONLY ? F3_R2C : F3_C2C, false, MINB>; break;
+    case 1: k = fast3_kernel<T, R1, R2, R3, E, REAL_ONLY ? F3_R2C : F3_C2C, true, MINB>; break;
     case 2: k = fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB>; break;
     case 3: k = fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB>; break;
     case 4: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB>; break;
@@ -684,7 +685,7 @@ static inline bool col_grid(const LineJob &J, int lpc, dim3 *grid) {
 }
 
 
-template <typename T, int R1, int R2, int LPC, bool BWD, bool PF>
+template <typename T, int R1, int R2, int LPC, bool BWD, bool PF, bool INROWS>
 __global__ void __launch_bounds__(LPC * R2)
 colfast2_kernel(const __grid_constant__ LineJob J) {
   constexpr int N = R1 * R2, NB2 = R1 / R2;
@@ -696,14 +697,36 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   const ColGroup cg = col_group(J, (uint32_t)((J.bdim[0] + LPC - 1) / LPC));
   const uint32_t i0 = cg.g0 * LPC, i1 = cg.i1, i2 = cg.i2;
   const bool valid = i0 + line < (uint32_t)J.bdim[0];
-  const int64_t off_in = (int64_t)(i0 + line) + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
+  const int64_t off_in = (INROWS ? (int64_t)(i0 + line) * J.bs_in[0] : (int64_t)(i0 + line)) + (int64_t)i1 * J.bs_in[1] +
+                         (int64_t)i2 * J.bs_in[2];
   const int64_t off_out = (int64_t)(i0 + line) + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
   const uint32_t twi = J.tw4_dim == 0 ? i0 + line : J.tw4_dim == 1 ? i1 : J.tw4_dim == 2 ? i2 : 0u;
   const cx<T> *in = reinterpret_cast<const cx<T> *>(J.in) + off_in;
   cx<T> *out = reinterpret_cast<cx<T> *>(J.out) + off_out;
   const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);   // W_N^m
-  if (PF && line == 0 && !J.seg_len) col_prefetch(J, cg, LPC, i, R1, R2);
+  if (PF && !INROWS && line == 0 && !J.seg_len) col_prefetch(J, cg, LPC, i, R1, R2);
   cx<T> x[R1];
+  if (INROWS) {
+    // every line is a CONTIGUOUS row (second launch of the split on contiguous data: rows in, transposed out).
+    // The group's rows are copied to shared memory with consecutive threads on consecutive elements and read
+    // back in the compute layout; rows are padded by one element so that both sides are conflict-free.
+    cx<T> *stage = S;   // shares the exchange buffer: one more barrier, half the shared memory
+    const cx<T> *g0 = reinterpret_cast<const cx<T> *>(J.in) + (int64_t)i0 * J.bs_in[0] + (int64_t)i1 * J.bs_in[1] +
+                      (int64_t)i2 * J.bs_in[2];
+    const uint32_t nl = min((uint32_t)LPC, (uint32_t)J.bdim[0] - i0);
+#pragma unroll
+    for (int q = 0; q < R1; ++q) {
+      const uint32_t f = (uint32_t)u + (uint32_t)(LPC * R2) * q, l = f / N, n = f % N;
+      if (l < nl) stage[l * (N + 1) + n] = g0[(int64_t)l * J.bs_in[0] + n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < R1; ++j) {
+      x[j] = valid ? stage[line * (N + 1) + i + R2 * j] : mk<T>((T)0, (T)0);
+      if (BWD) x[j].y = -x[j].y;
+    }
+    __syncthreads();
+  } else
 #pragma unroll
   for (int j = 0; j < R1; ++j) {
     const uint32_t n = (uint32_t)(i + R2 * j);
@@ -759,13 +782,17 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
 namespace {
 template <typename T, int R1, int R2, int LPC>
 int launch_colfast2(const LineJob &J, cudaStream_t s) {
-  const size_t smem = sizeof(cx<T>) * (size_t)R1 * R2 * LPC;
+  const bool rows_in = J.col_in_rows != 0;
+  const size_t smem = sizeof(cx<T>) * (rows_in ? (size_t)LPC * (R1 * R2 + 1) : (size_t)R1 * R2 * LPC);
   const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
-  const bool pf = col_prefetch_enabled(sizeof(T) == 4);
-  auto kf = pf ? colfast2_kernel<T, R1, R2, LPC, false, true> : colfast2_kernel<T, R1, R2, LPC, false, false>;
-  auto kb = pf ? colfast2_kernel<T, R1, R2, LPC, true, true> : colfast2_kernel<T, R1, R2, LPC, true, false>;
-  static PerDeviceFlag flag;
-  bool &configured = flag.here();
+  const bool pf = !rows_in && sizeof(T) == 4 && col_prefetch_enabled(true);   // fp64: measured slower with it
+  typedef void (*kern_t)(const LineJob);
+  kern_t kf, kb;
+  if (rows_in) { kf = colfast2_kernel<T, R1, R2, LPC, false, false, true>; kb = colfast2_kernel<T, R1, R2, LPC, true, false, true>; }
+  else if (pf) { kf = colfast2_kernel<T, R1, R2, LPC, false, sizeof(T) == 4, false>; kb = colfast2_kernel<T, R1, R2, LPC, true, sizeof(T) == 4, false>; }
+  else { kf = colfast2_kernel<T, R1, R2, LPC, false, false, false>; kb = colfast2_kernel<T, R1, R2, LPC, true, false, false>; }
+  static PerDeviceFlag flags[3];
+  bool &configured = flags[rows_in ? 2 : pf ? 1 : 0].here();
   if (!configured) {
     for (auto k : {kf, kb}) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1208,6 +1235,31 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
       // four 4-warp CTAs per SM — complex64 rows are instruction-issue bound, not latency bound
       g_last_kernel = "fast2_kernel<float,32,32,4,4>";
       return launch_fast2<float, 32, 32, 4, 4>(J, sm_count, s);
+    case FAST2_16_F64:   // short rows: plain loads beat the bulk copies (5.2-5.4 against 2.0-3.1 TB/s measured)
+      g_last_kernel = "fast2_kernel<double,4,4,8,4>";
+      return launch_fast2<double, 4, 4, 8, 4>(J, sm_count, s);
+    case FAST2_32_F64:   // short rows: plain loads beat the bulk copies (5.2-5.4 against 2.0-3.1 TB/s measured)
+      g_last_kernel = "fast2_kernel<double,8,4,8,4>";
+      return launch_fast2<double, 8, 4, 8, 4>(J, sm_count, s);
+    case FAST2_64_F64:   // short rows: plain loads beat the bulk copies (5.2-5.4 against 2.0-3.1 TB/s measured)
+      g_last_kernel = "fast2_kernel<double,8,8,8,4>";
+      return launch_fast2<double, 8, 8, 8, 4>(J, sm_count, s);
+    case FAST2_128_F64:
+      if (fast_variant() == 0) { g_last_kernel = "fast2p_kernel<double,16,8,10>"; return launch_fast2p<double, 16, 8, 10>(J, sm_count, s); }
+      g_last_kernel = "fast2_kernel<double,16,8,8,4>";
+      return launch_fast2<double, 16, 8, 8, 4>(J, sm_count, s);
+    case FAST2_16_F32: g_last_kernel = "fast2_kernel<float,4,4,8,6>"; return launch_fast2<float, 4, 4, 8, 6>(J, sm_count, s);
+    case FAST2_32_F32: g_last_kernel = "fast2_kernel<float,8,4,8,6>"; return launch_fast2<float, 8, 4, 8, 6>(J, sm_count, s);
+    case FAST2_64_F32: g_last_kernel = "fast2_kernel<float,8,8,8,6>"; return launch_fast2<float, 8, 8, 8, 6>(J, sm_count, s);
+    case FAST2_128_F32: g_last_kernel = "fast2_kernel<float,16,8,8,4>"; return launch_fast2<float, 16, 8, 8, 4>(J, sm_count, s);
+    case FAST2_256_F32: g_last_kernel = "fast2_kernel<float,16,16,8,4>"; return launch_fast2<float, 16, 16, 8, 4>(J, sm_count, s);
+    case FAST2_512_F32: g_last_kernel = "fast2_kernel<float,32,16,4,4>"; return launch_fast2<float, 32, 16, 4, 4>(J, sm_count, s);
+    case FAST3R_256_F64: g_last_kernel = "fast3_kernel<double,8,8,4,E8>"; return launch_fast3<double, 8, 8, 4, 8, 16, true>(J, sm_count, s);
+    case FAST3R_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E8>"; return launch_fast3<double, 8, 8, 8, 8, 8, true>(J, sm_count, s);
+    case FAST3R_1024_F64: g_last_kernel = "fast3_kernel<double,16,8,8,E16>"; return launch_fast3<double, 16, 8, 8, 16, 8, true>(J, sm_count, s);
+    case FAST3R_256_F32: g_last_kernel = "fast3_kernel<float,8,8,4,E8>"; return launch_fast3<float, 8, 8, 4, 8, 16, true>(J, sm_count, s);
+    case FAST3R_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E8>"; return launch_fast3<float, 8, 8, 8, 8, 12, true>(J, sm_count, s);
+    case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, true>(J, sm_count, s);
     case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3>(J, sm_count, s);
     case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2>(J, sm_count, s);
     case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1>(J, sm_count, s);
@@ -1233,6 +1285,7 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8>(J, sm_count, s);
     case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4>(J, sm_count, s);
     case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5>(J, sm_count, s);
+    case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2>(J, sm_count, s);
     case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4>(J, sm_count, s);
     case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;

@@ -117,6 +117,23 @@ enum FastId : uint32_t {
   COLCONV_32_F32 = 29,
   COLCONV_64_F32 = 30,
   COLCONV_128_F32 = 31,
+  FAST2_16_F64 = 32,     // short contiguous rows, several rows per warp (fast2p_kernel / fast2_kernel)
+  FAST2_32_F64 = 33,
+  FAST2_64_F64 = 34,
+  FAST2_128_F64 = 35,
+  FAST2_16_F32 = 36,
+  FAST2_32_F32 = 37,
+  FAST2_64_F32 = 38,
+  FAST2_128_F32 = 39,
+  FAST2_256_F32 = 40,
+  FAST2_512_F32 = 41,
+  FAST3R_256_F64 = 42,   // three-pass kernels instantiated for real rows only (r2c / c2r of 512, 1024, 2048 points)
+  FAST3R_512_F64 = 43,
+  FAST3R_1024_F64 = 44,
+  FAST3R_256_F32 = 45,
+  FAST3R_512_F32 = 46,
+  FAST3R_1024_F32 = 47,
+  FAST3_8192_F32 = 48,
 };
 
 struct Phase {
@@ -178,6 +195,7 @@ struct LineJob {
   // offset o of the output array is multiplied by umul[o % umul_mod]  (umul_mod = 0: off)
   const void *umul;
   uint64_t umul_mod;
+  uint32_t col_in_rows;    // column kernels: every line is a contiguous row on the input side (staged through smem)
   const void *mul_tab;     // ST_C: multiply output element e by mul_tab[line_index + mul_stride*e] (null = off)
   uint32_t mul_stride;
   double fct;

@@ -549,16 +549,26 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   J->fast_id = FAST_NONE;
   if (s.kind == KIND_C2C && !E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
       !env_int("IMPULSE_FFT_NO_FAST", 0)) {
-    if (f64 && N == 1024) J->fast_id = FAST2_1024_F64;
-    else if (f64 && N == 512) J->fast_id = FAST2_512_F64;
-    else if (f64 && N == 256) J->fast_id = FAST2_256_F64;
-    else if (!f64 && N == 1024) J->fast_id = FAST2_1024_F32;
+    switch (N) {
+      case 16: J->fast_id = f64 ? FAST2_16_F64 : FAST2_16_F32; break;
+      case 32: J->fast_id = f64 ? FAST2_32_F64 : FAST2_32_F32; break;
+      case 64: J->fast_id = f64 ? FAST2_64_F64 : FAST2_64_F32; break;
+      case 128: J->fast_id = f64 ? FAST2_128_F64 : FAST2_128_F32; break;
+      case 256: J->fast_id = f64 ? FAST2_256_F64 : FAST2_256_F32; break;
+      case 512: J->fast_id = f64 ? FAST2_512_F64 : FAST2_512_F32; break;
+      case 1024: J->fast_id = f64 ? FAST2_1024_F64 : FAST2_1024_F32; break;
+      default: break;
+    }
   }
   // column kernels: complex sub-transforms of 64/128/256 points over adjacent strided lines (both sides
   // lines-fastest with unit line stride, whole groups of S lines) — the strided axes of N-D transforms and
   // the two launches of the four-step split
-  if (s.kind == KIND_C2C && !E->blue && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && in_lf && out_lf &&
-      s.bs_in[0] == 1 && s.bs_out[0] == 1 && J->bdim[0] >= S &&
+  // (also: contiguous rows in, lines-fastest out — the second launch of the split on contiguous data)
+  const bool rows_in = !in_lf && s.es_in == 1 && J->bdim[0] > 1 && s.bs_in[0] >= (int64_t)N && !s.tw4_n && !s.umul_mod &&
+                       !env_int("IMPULSE_FFT_NO_COLROWS", 0);
+  J->col_in_rows = 0;
+  if (s.kind == KIND_C2C && !E->blue && !s.zero_pad_from && !s.mul_tab && !s.blue_stage && (in_lf || rows_in) && out_lf &&
+      (rows_in || s.bs_in[0] == 1) && s.bs_out[0] == 1 && J->bdim[0] >= S &&
       (N == 32 || N == 64 || N == 128 || N == 256 || N == 512) &&
       !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_COLFAST", 0)) {
     switch (N) {
@@ -568,6 +578,7 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       case 256: J->fast_id = f64 ? COL2_256_F64 : COL2_256_F32; break;
       default: J->fast_id = f64 ? COL2_512_F64 : COL2_512_F32; break;
     }
+    J->col_in_rows = (rows_in && !in_lf) ? 1u : 0u;
     if (s.conv_mid) {
       J->fast_id = FAST_NONE;
       if (s.tw4_n && s.umul_mod && J->tw4_dim < 3) {
@@ -610,10 +621,13 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       uint32_t id = FAST_NONE, r1 = 0, r2 = 0, r3 = 0;
       if (L == 2048) { id = f64 ? FAST3_2048_F64 : FAST3_2048_F32; r1 = 16; r2 = 16; r3 = 8; }
       else if (L == 4096) { id = f64 ? FAST3_4096_F64 : FAST3_4096_F32; r1 = 16; r2 = 16; r3 = 16; }
-      else if (L == 8192 && f64) { id = FAST3_8192_F64; r1 = 16; r2 = 16; r3 = 32; }
+      else if (L == 8192) { id = f64 ? FAST3_8192_F64 : FAST3_8192_F32; r1 = 16; r2 = 16; r3 = 32; }
       else if (L == 500 && f64) { id = FAST3_500_F64; r1 = 5; r2 = 10; r3 = 10; }
       else if (L == 1944 && f64) { id = FAST3_1944_F64; r1 = 6; r2 = 18; r3 = 18; }
       else if (L == 1000 && f64) { id = FAST3_1000_F64; r1 = 10; r2 = 10; r3 = 10; }
+      else if (!c2c && L == 256) { id = f64 ? FAST3R_256_F64 : FAST3R_256_F32; r1 = 8; r2 = 8; r3 = 4; }
+      else if (!c2c && L == 512) { id = f64 ? FAST3R_512_F64 : FAST3R_512_F32; r1 = 8; r2 = 8; r3 = 8; }
+      else if (!c2c && L == 1024) { id = f64 ? FAST3R_1024_F64 : FAST3R_1024_F32; r1 = 16; r2 = 8; r3 = 8; }
       if (id != FAST_NONE) {
         rc = fast3_tables(L, r1, r2, r3, s.dtype, &J->f3_tw1, &J->f3_tw2, err);
         if (rc) return rc;
@@ -814,6 +828,11 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       }
       const bool strided = (!dims.empty()) && (fastest_in < (uint64_t)std::llabs(es_in) || fastest_out < (uint64_t)std::llabs(es_out));
       split = !fits_one(N) || (strided && !fitsS) || env_int("IMPULSE_FFT_FORCE_FOURSTEP", 0);
+      // fp32 lines of 16384 points (and strided ones of 8192) fit one CTA but have no register kernel: two
+      // column-kernel launches (128 x 128, 64 x 128) measure 2-3x faster than the generic single launch
+      if (!split && d.dtype == DT_F32 && (N == 16384 || (N == 8192 && strided)) && !env_int("IMPULSE_FFT_NO_FAST", 0) &&
+          !env_int("IMPULSE_FFT_NO_COLFAST", 0))
+        split = true;
     }
     if (!split)
       return emit(KIND_C2C, RL_HERMITIAN, forward, N, es_in, es_out, dims, -1, 0, mul_tab, 1, 0, esz_in, esz_out, src, dst,

@@ -406,23 +406,23 @@ def test_fft_filter2d(ib, torch_mod, checker):
 
 
 def test_register_kernels_all_kinds(ib, torch_mod, checker):
-    """The specialised register kernels (two-pass 256/512/1024, three-pass 2048/4096/8192) in every
+    """The specialised register kernels (two-pass 16...1024, three-pass 2048/4096/8192) in every
     kind they serve: c2c both directions, r2c/c2r with both `forward` flags, fp64 and fp32, odd batch
     sizes (dynamic row claiming with a ragged tail), plus the generic engine on the same inputs
     (IMPULSE_FFT_NO_FAST) as a second opinion."""
     rng = np.random.default_rng(21)
     used = set()
     for dt, cdt in ((np.float64, np.complex128), (np.float32, np.complex64)):
-        for n in (256, 500, 512, 1000, 1024, 1944, 2048, 4096, 8192):
-            for rows in (1, 37, 301):
+        for n in (16, 32, 64, 128, 256, 500, 512, 1000, 1024, 1944, 2048, 4096, 8192):
+            for rows in (1, 37, 301) + ((5000,) if n <= 128 else ()):
                 x = rnd(rng, (rows, n), cdt)
                 xd = torch_mod.from_numpy(x).cuda()
                 for fwd in (True, False):
                     got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], fwd, 0.7).cpu().numpy()
                     used.add(ib.last_kernel())
                     assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.7)) <= tol(n, dt), (n, rows, fwd, dt)
-        for n in (1000, 3888, 4096, 8192, 16384):
-            for rows in (1, 53):
+        for n in (512, 1024, 2048, 1000, 3888, 4096, 8192, 16384):
+            for rows in (1, 53) + ((1001,) if n <= 2048 else ()):
                 r = rnd(rng, (rows, n), dt)
                 rd = torch_mod.from_numpy(r).cuda()
                 for fwd in (True, False):
