@@ -27,7 +27,7 @@ def main():
         return torch.from_numpy(rng.standard_normal(shape).astype(dt)).cuda()
 
     # generic engine (mixed radix, Bluestein, r2c/c2r odd+even, packed), fast2/fast2p, fast3, colfast2, fastblue, four-step, DCT
-    for n in (1, 6, 30, 97, 1000, 256, 512, 1024, 2048, 4096, 8192, 4099, 500, 1944):
+    for n in (1, 6, 16, 30, 32, 64, 97, 128, 1000, 256, 512, 1024, 2048, 4096, 8192, 4099, 500, 1944):
         for rows in (1, 5):
             x = c((rows, n))
             y = run("c2c", x, torch.empty_like(x), [1])
@@ -35,7 +35,7 @@ def main():
             ok &= bool(torch.allclose(back, x, atol=1e-9))
             ref = torch.fft.fft(x, dim=1)   # second opinion only; parity proper is in tests/
             ok &= bool(torch.allclose(y, ref, rtol=1e-9, atol=1e-9 * n))
-    for n in (5, 8, 1000, 3888, 4096, 4099, 16384):
+    for n in (5, 8, 512, 1000, 1024, 2048, 3888, 4096, 4099, 16384, 32768, 29999):
         x = r((3, n))
         s = run("r2c", x, torch.empty((3, n // 2 + 1), dtype=torch.complex128, device="cuda"), [1])
         ok &= bool(torch.allclose(s, torch.fft.rfft(x, dim=1), rtol=1e-9, atol=1e-9 * n))
@@ -49,8 +49,34 @@ def main():
         ok &= bool(torch.allclose(y, torch.fft.fftn(x, dim=axes), rtol=1e-9, atol=1e-8 * max(shape)))
     x = c((2, 32768))
     ok &= bool(torch.allclose(run("c2c", x, torch.empty_like(x), [1]), torch.fft.fft(x, dim=1), rtol=1e-9, atol=1e-6))
-    x32 = c((7, 1024), np.complex64)
-    ok &= bool(torch.allclose(run("c2c", x32, torch.empty_like(x32), [1]), torch.fft.fft(x32, dim=1), rtol=1e-4, atol=1e-2))
+    for n in (16, 64, 256, 512, 1024, 8192, 16384):                   # fp32 row kernels and the fp32 split
+        x32 = c((7, n), np.complex64)
+        ok &= bool(torch.allclose(run("c2c", x32, torch.empty_like(x32), [1]), torch.fft.fft(x32, dim=1), rtol=1e-4, atol=2e-2))
+    r32 = r((5, 2048), np.float32)                                    # real rows on the three-pass kernels, fp32
+    ok &= bool(torch.allclose(run("r2c", r32, torch.empty((5, 1025), dtype=torch.complex64, device="cuda"), [1]),
+                              torch.fft.rfft(r32, dim=1), rtol=1e-4, atol=2e-2))
+    x = c((2, 20011))                                                  # long Bluestein line: elementwise chirp passes
+    ok &= bool(torch.allclose(run("c2c", x, torch.empty_like(x), [1]), torch.fft.fft(x, dim=1), rtol=1e-9, atol=1e-6))
+    # fused multiply, axis convolution (fused middle pass), Hartley fold, FFTPACK
+    import ctypes as C
+    from impulse_b200 import _lib
+    L = _lib.lib()
+    z = c((2, 4096, 24), np.complex64)
+    m = c((4096 * 24,), np.complex64)
+    want = torch.fft.ifft(torch.fft.fft(z, dim=1) * m.view(4096, 24), dim=1)
+    st = (C.c_ssize_t * 3)(4096 * 24 * 8, 24 * 8, 8)
+    _lib.check(L.impulse_fft_convolve_axis(_lib.F32, 3, (C.c_size_t * 3)(2, 4096, 24), st, st, 1, z.data_ptr(), z.data_ptr(),
+                                           1.0 / 4096, m.data_ptr(), 4096 * 24, None))
+    ok &= bool(torch.allclose(z, want, rtol=1e-3, atol=1e-3))
+    hsrc = r((6, 10, 12))
+    hout = torch.empty_like(hsrc)
+    ib.r2r_genuine_hartley(ib.DataDesc.init(hout), ib.DataDesc.init(hsrc), [0, 2])
+    f = torch.fft.fftn(hsrc, dim=[0, 2])
+    ok &= bool(torch.allclose(hout, f.real + f.imag, atol=1e-9))
+    ib.r2r_fftpack(ib.DataDesc.init(hout), ib.DataDesc.init(hsrc), [1, 2], True, True)
+    from impulse_b200 import signal as isig
+    sig = isig.fftconvolve(r((3, 5000)), r((65,)))
+    ok &= sig.shape == (3, 5064)
     img = torch.rand((2, 64, 96), device="cuda", dtype=torch.float32)
     ker = torch.rand((5, 5), device="cuda", dtype=torch.float32)
     FFTFilter2D(ker / ker.sum(), 64, 96).apply(img)
