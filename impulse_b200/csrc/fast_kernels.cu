@@ -199,6 +199,133 @@ int launch_fast2(const LineJob &J, int sm_count, cudaStream_t s) {
 }  // namespace
 
 
+// Short REAL rows: r2c / c2r of N = 2M points with M = R1*R2 in 16...128, several rows per warp.  The packed
+// row (x[2m], x[2m+1]) is an M-point complex line for the two-pass scheme of fast2_kernel; the Hermitian
+// post-twiddle (r2c) / pre-twiddle (c2r) pairs bin k with bin M-k through the group's shared buffer.
+constexpr int F2R_R2C = 1, F2R_C2R = 2;
+template <typename T, int R1, int R2, int WARPS, int MINB, int KIND, bool BWD>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+fast2r_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
+              const cx<T> *__restrict__ twN, const cx<T> *__restrict__ twr, T fct) {
+  constexpr int M = R1 * R2, TPR = R2, GPW = 32 / TPR, NB2 = R1 / R2, PITCH = R2 + 1, BUF = R1 * PITCH;
+  static_assert(R2 <= 32 && 32 % R2 == 0 && R1 % R2 == 0 && BUF >= M + 1, "two-pass shape");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *tw = reinterpret_cast<cx<T> *>(smem_raw);
+  cx<T> *xbuf = tw + M;
+  for (int idx = threadIdx.x; idx < M; idx += WARPS * 32) {
+    const int k1 = idx / R2, i = idx % R2;
+    tw[idx] = twN[k1 * i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / TPR, i = lane % TPR;
+  cx<T> *S = xbuf + (size_t)(warp * GPW + g) * BUF;
+  constexpr uint64_t RPC = (uint64_t)WARPS * GPW;
+  for (uint64_t wrow = (uint64_t)blockIdx.x * RPC + (uint64_t)warp * GPW; wrow < nrows; wrow += (uint64_t)gridDim.x * RPC) {
+    const uint64_t row = wrow + g;
+    const bool active = row < nrows;
+    cx<T> x[R1];
+    if (KIND == F2R_R2C) {
+      const cx<T> *src = reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)row * rs_in) + i;
+#pragma unroll
+      for (int j = 0; j < R1; ++j) x[j] = active ? src[j * R2] : mk<T>((T)0, (T)0);
+    } else {
+      const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
+      for (int n = i; n <= M; n += TPR) S[n] = active ? src[n] : mk<T>((T)0, (T)0);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < R1; ++j) {
+        const int n = i + R2 * j;
+        cx<T> a = S[n], b = S[M - n];
+        if (BWD) { a.y = -a.y; b.y = -b.y; }       // c2r with forward=true conjugates its input
+        if (n == 0) { a.y = (T)0; b.y = (T)0; }    // imaginary parts of bins 0 and M are ignored
+        const cx<T> w = cconj(__ldg(twr + n));
+        const cx<T> s = cadd(a, cconj(b)), d = csub(a, cconj(b));
+        x[j] = cconj(cadd(s, mul_pi(cmul(w, d))));  // backward = conj(FFT(conj z))
+      }
+      __syncwarp();
+    }
+    RegFFT<T, R1>::run(x);
+#pragma unroll
+    for (int k1 = 1; k1 < R1; ++k1) x[k1] = cmul(x[k1], tw[k1 * R2 + i]);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) S[k1 * PITCH + i] = x[k1];
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < NB2; ++m) {
+      const int k1 = i + R2 * m;
+      cx<T> y[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) y[j] = S[k1 * PITCH + j];
+      RegFFT<T, R2>::run(y);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) x[m * R2 + k2] = y[k2];   // bin k1 + R1*k2
+    }
+    __syncwarp();
+    if (KIND == F2R_C2R) {
+      cx<T> *dst = reinterpret_cast<cx<T> *>(reinterpret_cast<T *>(out_v) + (int64_t)row * rs_out);
+      if (active) {
+#pragma unroll
+        for (int m = 0; m < NB2; ++m)
+#pragma unroll
+          for (int k2 = 0; k2 < R2; ++k2) {
+            cx<T> v = x[m * R2 + k2];
+            v.x *= fct; v.y *= -fct;                  // undo the conjugation of the backward trick
+            dst[i + R2 * m + R1 * k2] = v;            // (x[2n], x[2n+1])
+          }
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < NB2; ++m)
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) S[i + R2 * m + R1 * k2] = x[m * R2 + k2];
+      __syncwarp();
+      cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
+      const T h = (T)0.5;
+      if (active) {
+        for (int n = i; n <= M; n += TPR) {
+          const cx<T> a = S[n == M ? 0 : n], b = cconj(S[n == 0 ? 0 : M - n]);
+          const cx<T> Ev = mk<T>((a.x + b.x) * h, (a.y + b.y) * h), Dv = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
+          cx<T> v = cadd(Ev, cmul(__ldg(twr + n), mul_mi(Dv)));
+          v.x *= fct; v.y *= BWD ? -fct : fct;       // r2c with forward=false returns the conjugate spectrum
+          dst[n] = v;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+namespace {
+template <typename T, int R1, int R2, int WARPS, int MINB>
+int launch_fast2r(const LineJob &J, int sm_count, cudaStream_t s) {
+  constexpr int M = R1 * R2, GPW = 32 / R2;
+  const size_t smem = sizeof(cx<T>) * ((size_t)M + (size_t)WARPS * GPW * R1 * (R2 + 1));
+  const int kind = J.store_mode == ST_R2C_EVEN ? F2R_R2C : F2R_C2R;
+  const bool bwd = kind == F2R_R2C ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
+  typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, const cx<T> *, const cx<T> *, T);
+  kern_t k = kind == F2R_R2C ? (bwd ? (kern_t)fast2r_kernel<T, R1, R2, WARPS, MINB, F2R_R2C, true> : (kern_t)fast2r_kernel<T, R1, R2, WARPS, MINB, F2R_R2C, false>)
+                             : (bwd ? (kern_t)fast2r_kernel<T, R1, R2, WARPS, MINB, F2R_C2R, true> : (kern_t)fast2r_kernel<T, R1, R2, WARPS, MINB, F2R_C2R, false>);
+  static PerDeviceFlag flags[4];
+  bool &configured = flags[(kind == F2R_R2C ? 0 : 2) + (bwd ? 1 : 0)].here();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const uint64_t rpc = (uint64_t)WARPS * GPW;
+  uint64_t grid = (J.n_lines + rpc - 1) / rpc;
+  const uint64_t cap = (uint64_t)sm_count * MINB;
+  if (grid > cap) grid = cap;
+  k<<<(unsigned)grid, WARPS * 32, smem, s>>>(J.in, J.out, J.n_lines, J.bs_in[0], J.bs_out[0], (const cx<T> *)J.tw,
+                                             (const cx<T> *)J.tw_r, (T)J.fct);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+
+
 // ---- TMA helpers (1-D bulk copy global -> shared, completion on an mbarrier) ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -1254,6 +1381,14 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST2_128_F32: g_last_kernel = "fast2_kernel<float,16,8,8,4>"; return launch_fast2<float, 16, 8, 8, 4>(J, sm_count, s);
     case FAST2_256_F32: g_last_kernel = "fast2_kernel<float,16,16,8,4>"; return launch_fast2<float, 16, 16, 8, 4>(J, sm_count, s);
     case FAST2_512_F32: g_last_kernel = "fast2_kernel<float,32,16,4,4>"; return launch_fast2<float, 32, 16, 4, 4>(J, sm_count, s);
+    case FAST2R_16_F64: g_last_kernel = "fast2r_kernel<double,4,4>"; return launch_fast2r<double, 4, 4, 8, 4>(J, sm_count, s);
+    case FAST2R_32_F64: g_last_kernel = "fast2r_kernel<double,8,4>"; return launch_fast2r<double, 8, 4, 8, 4>(J, sm_count, s);
+    case FAST2R_64_F64: g_last_kernel = "fast2r_kernel<double,8,8>"; return launch_fast2r<double, 8, 8, 8, 4>(J, sm_count, s);
+    case FAST2R_128_F64: g_last_kernel = "fast2r_kernel<double,16,8>"; return launch_fast2r<double, 16, 8, 8, 3>(J, sm_count, s);
+    case FAST2R_16_F32: g_last_kernel = "fast2r_kernel<float,4,4>"; return launch_fast2r<float, 4, 4, 8, 6>(J, sm_count, s);
+    case FAST2R_32_F32: g_last_kernel = "fast2r_kernel<float,8,4>"; return launch_fast2r<float, 8, 4, 8, 6>(J, sm_count, s);
+    case FAST2R_64_F32: g_last_kernel = "fast2r_kernel<float,8,8>"; return launch_fast2r<float, 8, 8, 8, 6>(J, sm_count, s);
+    case FAST2R_128_F32: g_last_kernel = "fast2r_kernel<float,16,8>"; return launch_fast2r<float, 16, 8, 8, 4>(J, sm_count, s);
     case FAST3R_256_F64: g_last_kernel = "fast3_kernel<double,8,8,4,E8>"; return launch_fast3<double, 8, 8, 4, 8, 16, true>(J, sm_count, s);
     case FAST3R_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E8>"; return launch_fast3<double, 8, 8, 8, 8, 8, true>(J, sm_count, s);
     case FAST3R_1024_F64: g_last_kernel = "fast3_kernel<double,16,8,8,E16>"; return launch_fast3<double, 16, 8, 8, 16, 8, true>(J, sm_count, s);

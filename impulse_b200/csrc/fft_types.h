@@ -134,6 +134,14 @@ enum FastId : uint32_t {
   FAST3R_512_F32 = 46,
   FAST3R_1024_F32 = 47,
   FAST3_8192_F32 = 48,
+  FAST2R_16_F64 = 49,    // short real rows (r2c / c2r of 32 ... 256 points), several rows per warp (fast2r_kernel)
+  FAST2R_32_F64 = 50,
+  FAST2R_64_F64 = 51,
+  FAST2R_128_F64 = 52,
+  FAST2R_16_F32 = 53,
+  FAST2R_32_F32 = 54,
+  FAST2R_64_F32 = 55,
+  FAST2R_128_F32 = 56,
 };
 
 struct Phase {

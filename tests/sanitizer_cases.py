@@ -35,7 +35,7 @@ def main():
             ok &= bool(torch.allclose(back, x, atol=1e-9))
             ref = torch.fft.fft(x, dim=1)   # second opinion only; parity proper is in tests/
             ok &= bool(torch.allclose(y, ref, rtol=1e-9, atol=1e-9 * n))
-    for n in (5, 8, 512, 1000, 1024, 2048, 3888, 4096, 4099, 16384, 32768, 29999):
+    for n in (5, 8, 32, 64, 128, 256, 512, 1000, 1024, 2048, 3888, 4096, 4099, 16384, 32768, 29999):
         x = r((3, n))
         s = run("r2c", x, torch.empty((3, n // 2 + 1), dtype=torch.complex128, device="cuda"), [1])
         ok &= bool(torch.allclose(s, torch.fft.rfft(x, dim=1), rtol=1e-9, atol=1e-9 * n))

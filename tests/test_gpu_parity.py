@@ -421,7 +421,7 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
                     got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], fwd, 0.7).cpu().numpy()
                     used.add(ib.last_kernel())
                     assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.7)) <= tol(n, dt), (n, rows, fwd, dt)
-        for n in (512, 1024, 2048, 1000, 3888, 4096, 8192, 16384):
+        for n in (32, 64, 128, 256, 512, 1024, 2048, 1000, 3888, 4096, 8192, 16384):
             for rows in (1, 53) + ((1001,) if n <= 2048 else ()):
                 r = rnd(rng, (rows, n), dt)
                 rd = torch_mod.from_numpy(r).cuda()
