@@ -6,6 +6,7 @@
 // All HBM traffic is one coalesced read and one coalesced write per element; everything in
 // between lives in shared memory (up to 227 KB per CTA on B200).
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include "fft_device.cuh"
 #include "fft_kernels.h"
@@ -65,6 +66,29 @@ int launch_line_job(const LineJob &J, int threads, size_t smem_bytes, uint64_t n
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   g_last_kernel = J.dtype == 1 ? "line_fft_kernel<double>" : "line_fft_kernel<float>";
   const bool big = threads > kMaxThreads;
+  {
+    // The radix passes read their twiddles through L1.  With the carve-out pinned at "all shared memory" L1
+    // shrinks to its minimum and every twiddle becomes an L2 round trip (ncu: long-scoreboard stalls dominate);
+    // ask only for the shared memory the resident CTAs need and leave the rest to L1.
+    static const int mode = [] { const char *e = getenv("IMPULSE_FFT_CARVEOUT"); return e ? atoi(e) : 0; }();  // 0 = adaptive, else percent
+    const size_t per_cta = smem_bytes + 1024;
+    size_t ctas = big ? 1 : (size_t)kMinCtasPerSm;
+    while (ctas > 1 && ctas * per_cta > 227 * 1024) --ctas;
+    int pct = mode > 0 ? mode : (int)((ctas * per_cta * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    static int last_pct[64][4] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int kidx = (J.dtype == 1 ? 0 : 2) + (big ? 1 : 0);
+    int &lp = last_pct[(dev >= 0 && dev < 64) ? dev : 0][kidx];
+    if (lp != pct + 1) {
+      const void *k = J.dtype == 1 ? (big ? (const void *)line_fft_kernel<double, true> : (const void *)line_fft_kernel<double, false>)
+                                   : (big ? (const void *)line_fft_kernel<float, true> : (const void *)line_fft_kernel<float, false>);
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      if (e != cudaSuccess) return (int)e;
+      lp = pct + 1;
+    }
+  }
   if (J.dtype == 1) {
     if (big) line_fft_kernel<double, true><<<grid, threads, smem_bytes, s>>>(J);
     else line_fft_kernel<double, false><<<grid, threads, smem_bytes, s>>>(J);
