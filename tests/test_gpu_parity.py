@@ -775,3 +775,93 @@ def test_long_lines(ib, torch_mod, checker):
     got = apply_nd(ib, "r2c", torch_mod.from_numpy(img).cuda(), torch_mod.empty((6, 20001), dtype=torch_mod.complex128,
                                                                                   device="cuda"), [0, 1], True, 1.0)
     assert oracle.rel_l2(got.cpu().numpy(), checker.r2c(img, [0, 1], True, 1.0)) <= tol(40000)
+
+
+def test_randomized_shapes_strides_against_reference(ib, torch_mod, ref):
+    """300 seeded random cases against the compiled reference: kind (c2c/r2c/c2r/dct/dst/hartley/fftpack),
+    precision, 1-4 dimensions, any subset and order of axes, lengths drawn to hit every kernel family
+    (short rows, register sizes, composite, prime, long), non-contiguous views on both sides (steps, offsets,
+    permuted dimensions) and misaligned bases — the kernel SELECTION logic is what this exercises."""
+    rng = np.random.default_rng(20261017)
+    pool = [1, 2, 3, 4, 5, 7, 8, 12, 16, 17, 30, 32, 33, 64, 97, 100, 128, 191, 243, 255, 256, 257, 500, 512, 625, 1000, 1024,
+            1025, 2000, 2048, 4096, 4099, 8192, 16384, 20000]
+    kinds_seen, kernels = set(), set()
+    for case in range(300):
+        kind = ["c2c", "c2c", "r2c", "r2c", "c2r", "c2r", "dct", "dst", "hartley_s", "hartley_g", "fftpack"][rng.integers(0, 11)]
+        f64 = bool(rng.integers(0, 2))
+        rdt, cdt = (np.float64, np.complex128) if f64 else (np.float32, np.complex64)
+        nd = int(rng.integers(1, 5))
+        budget = 1 << 19
+        shape = []
+        for _ in range(nd):
+            cand = [p for p in pool if p <= max(1, budget)]
+            n = int(cand[rng.integers(0, len(cand))])
+            shape.append(n)
+            budget //= n
+        rng.shuffle(shape)
+        shape = tuple(int(s) for s in shape)
+        naxes = int(rng.integers(1, nd + 1))
+        axes = [int(a) for a in rng.permutation(nd)[:naxes]]
+        if kind in ("dct", "dst") and any(shape[a] > 4000 for a in axes):
+            kind = "c2c"
+        if kind in ("dct", "dst", "hartley_s", "hartley_g", "fftpack"):
+            axes = axes[:2]
+        fwd = bool(rng.integers(0, 2))
+        fct = float(rng.choice([1.0, 0.5, 1.0 / 3.0]))
+
+        def view_of(shp, dtype):
+            """A device tensor of logical shape `shp` that is a strided view into a larger allocation."""
+            steps = [int(rng.choice([1, 1, 1, 2])) for _ in shp]
+            offs = [int(rng.integers(0, 2)) for _ in shp]
+            big = tuple(o + s * (n - 1) + 1 + int(rng.integers(0, 2)) for o, s, n in zip(offs, steps, shp))
+            base = torch_mod.zeros(big, dtype=dtype, device="cuda")
+            sl = tuple(slice(o, o + s * (n - 1) + 1, s) for o, s, n in zip(offs, steps, shp))
+            return base[sl]
+
+        tdt = {np.float64: torch_mod.float64, np.float32: torch_mod.float32, np.complex128: torch_mod.complex128,
+               np.complex64: torch_mod.complex64}
+        last = axes[-1]
+        cshape = tuple(s // 2 + 1 if i == last else s for i, s in enumerate(shape))
+        if kind == "c2c":
+            a = rnd(rng, shape, cdt)
+            want = ref.c2c(a, axes, fwd, fct)
+            src, dst = view_of(shape, tdt[cdt]), view_of(shape, tdt[cdt])
+        elif kind == "r2c":
+            a = rnd(rng, shape, rdt)
+            want = ref.r2c(a, axes, fwd, fct)
+            src, dst = view_of(shape, tdt[rdt]), view_of(cshape, tdt[cdt])
+        elif kind == "c2r":
+            a = rnd(rng, cshape, cdt)
+            want = ref.c2r(a, shape, axes, fwd, fct)
+            src, dst = view_of(cshape, tdt[cdt]), view_of(shape, tdt[rdt])
+        else:
+            a = rnd(rng, shape, rdt)
+            src, dst = view_of(shape, tdt[rdt]), view_of(shape, tdt[rdt])
+        src.copy_(torch_mod.from_numpy(a).cuda())
+        din, dout = ib.DataDesc.init(src), ib.DataDesc.init(dst)
+        typ = int(rng.integers(1, 5))
+        if kind in ("c2c", "r2c", "c2r"):
+            ib.FFTDesc.init(axes=axes, forward=fwd, scalingFactor=fct).apply(dout, din)
+        elif kind in ("dct", "dst"):
+            ortho = bool(rng.integers(0, 2))
+            if typ == 1 and any(shape[x] < 2 for x in axes):
+                continue
+            want = ref.r2r(kind == "dct", typ, a, axes, fct, ortho)
+            ib.DCTDesc.init(axes=axes, dctType=typ, ortho=ortho, scalingFactor=fct, sine=(kind == "dst")).apply(dout, din)
+        elif kind == "fftpack":
+            r2h = bool(rng.integers(0, 2))
+            want = ref.r2r_real("fftpack", a, axes, r2h, fwd, fct)
+            ib.r2r_fftpack(dout, din, axes, r2h, fwd, fct)
+        else:
+            name = "separable_hartley" if kind == "hartley_s" else "genuine_hartley"
+            want = ref.r2r_real(name, a, axes, fct=fct)
+            (ib.r2r_separable_hartley if kind == "hartley_s" else ib.r2r_genuine_hartley)(dout, din, axes, fct)
+        kinds_seen.add(kind)
+        kernels.add(ib.last_kernel().split("<")[0])
+        got = dst.cpu().numpy()
+        big = max(shape[x] for x in axes)
+        bound = (1e-12 if f64 else 1e-5) * max(1.0, np.log2(big)) * len(axes) * (4 if kind in ("dct", "dst") else 1)
+        err = oracle.rel_l2(got, want)
+        assert err <= bound, (case, kind, f64, shape, axes, fwd, typ, err, ib.last_kernel())
+    print(sorted(kinds_seen), sorted(kernels))
+    assert len(kinds_seen) == 8 and len(kernels) >= 6
