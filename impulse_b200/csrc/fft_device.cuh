@@ -657,14 +657,26 @@ template <typename T>
 IMP_HD void aux_one(const AuxJob &A, uint64_t idx) {
   // decode: last dimension = position along the transform axis
   const int ax = A.ndim - 1;
-  const uint32_t e = (uint32_t)(idx % A.shape[ax]);
-  uint64_t r = idx / A.shape[ax];
+  uint32_t e;
   int64_t ou = 0, ow = 0;
-  for (int d = ax - 1; d >= 0; --d) {
-    const uint32_t i = (uint32_t)(r % A.shape[d]);
-    r /= A.shape[d];
-    ou += (int64_t)i * A.s_user[d];
-    ow += (int64_t)i * A.s_work[d];
+  if (A.total <= 0xffffffffull) {   // the usual case: 32-bit index arithmetic
+    uint32_t r = (uint32_t)idx / A.shape[ax];
+    e = (uint32_t)idx - r * A.shape[ax];
+    for (int d = ax - 1; d >= 0; --d) {
+      const uint32_t q = r / A.shape[d], i = r - q * A.shape[d];
+      r = q;
+      ou += (int64_t)i * A.s_user[d];
+      ow += (int64_t)i * A.s_work[d];
+    }
+  } else {
+    e = (uint32_t)(idx % A.shape[ax]);
+    uint64_t r = idx / A.shape[ax];
+    for (int d = ax - 1; d >= 0; --d) {
+      const uint32_t i = (uint32_t)(r % A.shape[d]);
+      r /= A.shape[d];
+      ou += (int64_t)i * A.s_user[d];
+      ow += (int64_t)i * A.s_work[d];
+    }
   }
   const int64_t eu = A.s_user[ax], ew = A.s_work[ax];
   const uint32_t N = A.N, M = A.M;

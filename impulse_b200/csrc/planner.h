@@ -160,7 +160,8 @@ class PlanCache {
 
 // planner utilities exposed for tests
 std::vector<uint32_t> choose_radices(uint32_t L);      // empty when a prime factor > kMaxGenericRadix
-uint32_t bluestein_size(uint32_t L);                    // smallest 7-smooth n2 >= 2L-1
+// smallest 7-smooth n2 >= 2L-1; a power of two instead when that does not fit one CTA (`one_cta_limit` points)
+uint32_t bluestein_size(uint32_t L, uint64_t one_cta_limit = ~0ull);
 std::vector<uint32_t> dif_positions(uint32_t n, const std::vector<uint32_t> &radices);  // pos_of_k
 
 }  // namespace impulse
