@@ -11,4 +11,5 @@ for wl in r2c_1024x4096_f64 r2c_16384x1000_f64 c2r_16384x1000_f64 r2c_16384x3888
   timeout 120 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu --workload $wl 2>/dev/null | \
     python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$wl', d['value'], d['ms_per_step'], d['roofline']['kernel'])" >> gpurun_out/sweep.txt
 done
+timeout 300 python tools/size_sweep.py > gpurun_out/size_sweep.txt 2>&1
 tail -3 gpurun_out/smoke.log; tail -8 gpurun_out/tests.log; cat gpurun_out/bench_default.json; cat gpurun_out/sweep.txt
