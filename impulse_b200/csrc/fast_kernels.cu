@@ -906,10 +906,114 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   }
 }
 
+// Software-pipelined variant for complex128 (plain strided lines, optional four-step twiddle): a CTA walks G
+// consecutive groups along the adjacent-lines dimension and requests the NEXT group's elements into a second
+// register set before it transforms the current one, so the global-load latency that dominates the 64-thread
+// complex128 CTAs (ncu: long-scoreboard 9-16 per issue) overlaps the arithmetic instead of preceding it.
+template <typename T, int R1, int R2, int LPC, bool BWD>
+__global__ void __launch_bounds__(LPC * R2)
+colpipe2_kernel(const __grid_constant__ LineJob J, const uint32_t G) {
+  constexpr int N = R1 * R2, NB2 = R1 / R2;
+  static_assert(R1 % R2 == 0, "column two-pass shape");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *S = reinterpret_cast<cx<T> *>(smem_raw);
+  const int u = threadIdx.x, line = u % LPC, i = u / LPC;
+  const uint32_t g0n = (uint32_t)((J.bdim[0] + LPC - 1) / LPC), chunks = (g0n + G - 1) / G;
+  const ColGroup cg = col_group(J, chunks);
+  const uint32_t i1 = cg.i1, i2 = cg.i2, gA = cg.g0 * G;
+  const int64_t base_in = (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
+  const int64_t base_out = (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
+  const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);
+  const T f = (T)J.fct;
+  auto load = [&](uint32_t grp, cx<T> (&x)[R1]) {
+    const uint32_t l0 = grp * LPC + line;
+    const bool ok = grp < g0n && l0 < (uint32_t)J.bdim[0];
+    const cx<T> *in = reinterpret_cast<const cx<T> *>(J.in) + base_in + l0;
+#pragma unroll
+    for (int j = 0; j < R1; ++j) x[j] = ok ? in[(int64_t)(i + R2 * j) * J.es_in] : mk<T>((T)0, (T)0);
+  };
+  cx<T> x[R1], xn[R1];
+  load(gA, x);
+  for (uint32_t g = 0; g < G; ++g) {
+    const uint32_t grp = gA + g;
+    if (grp >= g0n) break;
+    if (g + 1 < G) load(grp + 1, xn);
+    const uint32_t l0 = grp * LPC + line;
+    const bool valid = l0 < (uint32_t)J.bdim[0];
+    const uint32_t twi = J.tw4_dim == 0 ? l0 : J.tw4_dim == 1 ? i1 : J.tw4_dim == 2 ? i2 : 0u;
+    cx<T> *out = reinterpret_cast<cx<T> *>(J.out) + base_out + l0;
+    if (BWD) {
+#pragma unroll
+      for (int j = 0; j < R1; ++j) x[j].y = -x[j].y;
+    }
+    RegFFT<T, R1>::run(x);
+#pragma unroll
+    for (int k = 1; k < R1; ++k) x[k] = cmul(x[k], __ldg(tw + i * k));
+#pragma unroll
+    for (int k = 0; k < R1; ++k) S[(k * R2 + i) * LPC + line] = x[k];
+    __syncthreads();
+    cx<T> wstep = mk<T>((T)1, (T)0);
+    if (J.tw4_n) wstep = four_step_w<T>(J, (uint32_t)R1 * twi);
+#pragma unroll
+    for (int m = 0; m < NB2; ++m) {
+      const int k1 = i + R2 * m;
+      cx<T> y[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) y[j] = S[(k1 * R2 + j) * LPC + line];
+      RegFFT<T, R2>::run(y);
+      cx<T> w = mk<T>((T)1, (T)0);
+      if (J.tw4_n) w = four_step_w<T>(J, (uint32_t)k1 * twi);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) {
+        cx<T> v = y[k2];
+        if (J.tw4_n) { v = cmul(v, w); w = cmul(w, wstep); }
+        v.x *= f;
+        v.y *= BWD ? -f : f;
+        if (valid) out[(int64_t)(k1 + R1 * k2) * J.es_out] = v;
+      }
+    }
+    __syncthreads();   // the exchange buffer is reused by the next group
+#pragma unroll
+    for (int j = 0; j < R1; ++j) x[j] = xn[j];
+  }
+}
+
+static inline uint32_t col_pipe_groups() {  // IMPULSE_FFT_COL_PIPE=G (0 or 1 turns the pipelined variant off)
+  static const int g = [] { const char *e = getenv("IMPULSE_FFT_COL_PIPE"); return e ? atoi(e) : 2; }();
+  return g > 1 ? (uint32_t)g : 0u;
+}
+
 namespace {
 template <typename T, int R1, int R2, int LPC>
 int launch_colfast2(const LineJob &J, cudaStream_t s) {
   const bool rows_in = J.col_in_rows != 0;
+  // (64- and 128-point sub-transforms only: at 256 points the second register set costs more occupancy than
+  // the overlap returns — measured 1.80 -> 1.64 TB/s on 65536-point rows)
+  if (sizeof(T) == 8 && R1 * R2 <= 128 && !rows_in && !J.seg_len && !J.umul_mod && col_pipe_groups() && J.bdim[0] >= 2 * LPC) {
+    const uint32_t G = col_pipe_groups();
+    const size_t smem_p = sizeof(cx<T>) * (size_t)R1 * R2 * LPC;
+    const bool bwd_p = (J.flags & F_CONJ_SEQ) != 0;
+    auto kpf = colpipe2_kernel<T, (R1 <= 16 ? R1 : 16), R2, LPC, false>;
+    auto kpb = colpipe2_kernel<T, (R1 <= 16 ? R1 : 16), R2, LPC, true>;
+    static PerDeviceFlag pflag;
+    bool &pconf = pflag.here();
+    if (!pconf) {
+      for (auto k : {kpf, kpb}) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+      }
+      pconf = true;
+    }
+    const uint64_t g0n = (J.bdim[0] + LPC - 1) / LPC, chunks = (g0n + G - 1) / G, groups = chunks * J.bdim[1] * J.bdim[2];
+    if (groups == 0 || groups > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    dim3 grid = (J.bdim[1] <= 65535 && J.bdim[2] <= 65535) ? dim3((unsigned)chunks, (unsigned)J.bdim[1], (unsigned)J.bdim[2])
+                                                           : dim3((unsigned)groups, 1, 1);
+    g_last_kernel = "colpipe2_kernel";
+    (bwd_p ? kpb : kpf)<<<grid, LPC * R2, smem_p, s>>>(J, G);
+    return (int)cudaGetLastError();
+  }
   const size_t smem = sizeof(cx<T>) * (rows_in ? (size_t)LPC * (R1 * R2 + 1) : (size_t)R1 * R2 * LPC);
   const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
   const bool pf = !rows_in && sizeof(T) == 4 && col_prefetch_enabled(true);   // fp64: measured slower with it
@@ -1342,6 +1446,15 @@ static int fast_variant() {  // IMPULSE_FFT_FAST_VARIANT=1 selects the non-TMA k
   return v;
 }
 
+// 16 adjacent complex128 lines per CTA (256-byte runs) for the 64- and 128-point column kernels: measured
+// 1.51 -> 1.43 ms on the 8192 x 8192 transform, 1.36 ms together with the pipelined variant.
+// IMPULSE_FFT_COL_LPC16=0 restores 8 lines for A/B runs.
+static int col_lpc16() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("IMPULSE_FFT_COL_LPC16"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (J.fast_id) {
@@ -1411,8 +1524,12 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case COL2_512_F64: g_last_kernel = "colfast2_kernel<double,32,16,8>"; return launch_colfast2<double, 32, 16, 8>(J, s);
     case COL2_32_F32: g_last_kernel = "colfast2_kernel<float,8,4,16>"; return launch_colfast2<float, 8, 4, 16>(J, s);
     case COL2_512_F32: g_last_kernel = "colfast2_kernel<float,32,16,16>"; return launch_colfast2<float, 32, 16, 16>(J, s);
-    case COL2_64_F64: g_last_kernel = "colfast2_kernel<double,8,8,8>"; return launch_colfast2<double, 8, 8, 8>(J, s);
-    case COL2_128_F64: g_last_kernel = "colfast2_kernel<double,16,8,8>"; return launch_colfast2<double, 16, 8, 8>(J, s);
+    case COL2_64_F64:
+      if (col_lpc16() && J.bdim[0] >= 64) { g_last_kernel = "colfast2_kernel<double,8,8,16>"; return launch_colfast2<double, 8, 8, 16>(J, s); }
+      g_last_kernel = "colfast2_kernel<double,8,8,8>"; return launch_colfast2<double, 8, 8, 8>(J, s);
+    case COL2_128_F64:
+      if (col_lpc16() && J.bdim[0] >= 64) { g_last_kernel = "colfast2_kernel<double,16,8,16>"; return launch_colfast2<double, 16, 8, 16>(J, s); }
+      g_last_kernel = "colfast2_kernel<double,16,8,8>"; return launch_colfast2<double, 16, 8, 8>(J, s);
     case COL2_256_F64: g_last_kernel = "colfast2_kernel<double,16,16,8>"; return launch_colfast2<double, 16, 16, 8>(J, s);
     case COL2_64_F32: g_last_kernel = "colfast2_kernel<float,8,8,16>"; return launch_colfast2<float, 8, 8, 16>(J, s);
     case COL2_128_F32: g_last_kernel = "colfast2_kernel<float,16,8,16>"; return launch_colfast2<float, 16, 8, 16>(J, s);
