@@ -552,6 +552,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
   __syncthreads();
   constexpr uint32_t ROW_BYTES_IN = (KIND == F3_C2R ? (N + 1) : N) * sizeof(cx<T>);
   const int k1 = t % R1, i2b = t / R1;  // pass-2 ownership (T % R1 == 0)
+  const cx<T> wt = KIND == F3_C2C ? mk<T>((T)1, (T)0) : __ldg(twr + t);   // real kinds: W_2N^t, this thread's twiddle factor
   for (unsigned it = 0;; ++it) {
     const uint64_t row = s_row[it & 1];
     if (row >= nrows) break;
@@ -581,7 +582,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
         cx<T> a = buf[n], b = buf[N - n];
         if (BWD) { a.y = -a.y; b.y = -b.y; }       // c2r with forward=true conjugates its input
         if (n == 0) { a.y = (T)0; b.y = (T)0; }    // imaginary parts of bins 0 and N are ignored
-        const cx<T> w = cconj(__ldg(twr + n));     // e^{+2 pi i n/(2N)}
+        const cx<T> w = cconj(q == 0 ? wt : cmul(wt, __ldg(twr + TT * q)));   // e^{+2 pi i n/(2N)}, n = t + TT*q
         const cx<T> s = cadd(a, cconj(b)), d = csub(a, cconj(b));
         const cx<T> z = cadd(s, mul_pi(cmul(w, d)));
         x[q] = cconj(z);                           // backward = conj(FFT(conj z))
@@ -691,7 +692,10 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
         const int k = t + TT * q;
         const cx<T> a = buf[k], b = cconj(buf[k == 0 ? 0 : N - k]);
         const cx<T> Ev = mk<T>((a.x + b.x) * h, (a.y + b.y) * h), Dv = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
-        cx<T> v = cadd(Ev, cmul(__ldg(twr + k), mul_mi(Dv)));
+        // W_2N^k = W^t * W^(TT*q): one per-thread factor and one warp-uniform factor (both L1-resident)
+        // instead of a 16-byte table entry per output streamed from L2
+        const cx<T> wk = q == 0 ? wt : cmul(wt, __ldg(twr + TT * q));
+        cx<T> v = cadd(Ev, cmul(wk, mul_mi(Dv)));
         v.x *= fct; v.y *= BWD ? -fct : fct;       // r2c with forward=false returns the conjugate spectrum
         dst[k] = v;
         if (k == 0) {                               // bin N: Re Z0 - Im Z0
