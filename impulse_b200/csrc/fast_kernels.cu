@@ -457,7 +457,7 @@ fast2p_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nr
 
 namespace {
 // scheduler slots: zero-initialised device words, one pair per in-flight launch (ring)
-constexpr int kSchedSlots = 1024;
+constexpr int kSchedSlots = 65536;  // a slot is reused after this many launches: far more than can be queued across streams
 unsigned int *sched_slot() {
   static unsigned int *bases[kMaxDevices] = {};
   static unsigned next = 0;
