@@ -55,6 +55,10 @@ def main():
     r32 = r((5, 2048), np.float32)                                    # real rows on the three-pass kernels, fp32
     ok &= bool(torch.allclose(run("r2c", r32, torch.empty((5, 1025), dtype=torch.complex64, device="cuda"), [1]),
                               torch.fft.rfft(r32, dim=1), rtol=1e-4, atol=2e-2))
+    x = c((1, 1 << 19))                                                # peeled three-pass split, pipelined column kernel
+    ok &= bool(torch.allclose(run("c2c", x, torch.empty_like(x), [1]), torch.fft.fft(x, dim=1), rtol=1e-9, atol=1e-5))
+    x = c((8192, 160))                                                 # strided 8192-point columns: 64 x 128, 16 lines per CTA
+    ok &= bool(torch.allclose(run("c2c", x, torch.empty_like(x), [0]), torch.fft.fft(x, dim=0), rtol=1e-9, atol=1e-6))
     x = c((2, 20011))                                                  # long Bluestein line: elementwise chirp passes
     ok &= bool(torch.allclose(run("c2c", x, torch.empty_like(x), [1]), torch.fft.fft(x, dim=1), rtol=1e-9, atol=1e-6))
     # fused multiply, axis convolution (fused middle pass), Hartley fold, FFTPACK
