@@ -848,6 +848,11 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       split = !fits_one(N) || (strided && !fitsS) || env_int("IMPULSE_FFT_FORCE_FOURSTEP", 0);
       // fp32 lines of 16384 points (and strided ones of 8192) fit one CTA but have no register kernel: two
       // column-kernel launches (128 x 128, 64 x 128) measure 2-3x faster than the generic single launch
+      // strided power-of-two lines of 1024 points and more that would run as ONE generic launch with a single
+      // CTA per SM (8 / 16 adjacent lines fill the shared memory): 32 x 32 ... column-kernel launches instead
+      if (!split && strided && (N & (N - 1)) == 0 && N >= 1024 && !env_int("IMPULSE_FFT_NO_FAST", 0) &&
+          !env_int("IMPULSE_FFT_NO_COLFAST", 0))
+        split = true;
       if (!split && d.dtype == DT_F32 && (N == 16384 || (N == 8192 && strided)) && !env_int("IMPULSE_FFT_NO_FAST", 0) &&
           !env_int("IMPULSE_FFT_NO_COLFAST", 0))
         split = true;
