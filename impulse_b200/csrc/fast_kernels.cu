@@ -19,6 +19,7 @@
 
 #include <cstdlib>
 
+#include "fast3_device.cuh"
 #include "fft_device.cuh"
 #include "fft_kernels.h"
 
@@ -38,78 +39,6 @@ struct PerDeviceFlag {
 };
 }  // namespace
 
-// v * exp(-2*pi*i*M/R) with the trivial roots folded at compile time
-template <typename T, int R, int M> __device__ __forceinline__ cx<T> mul_root(cx<T> v) {
-  constexpr int m = ((M % R) + R) % R;
-  constexpr T h = (T)0.7071067811865475244008444;
-  if constexpr (m == 0) return v;
-  else if constexpr (4 * m == R) return mul_mi(v);
-  else if constexpr (2 * m == R) return mk<T>(-v.x, -v.y);
-  else if constexpr (4 * m == 3 * R) return mul_pi(v);
-  else if constexpr (8 * m == R) return mk<T>((v.x + v.y) * h, (v.y - v.x) * h);
-  else if constexpr (8 * m == 3 * R) return mk<T>((v.y - v.x) * h, -(v.x + v.y) * h);
-  else if constexpr (8 * m == 5 * R) return mk<T>(-(v.x + v.y) * h, (v.x - v.y) * h);
-  else if constexpr (8 * m == 7 * R) return mk<T>((v.x - v.y) * h, (v.x + v.y) * h);
-  else {
-    constexpr T c = (T)Trig<R>::c(m), s = (T)Trig<R>::s(m);
-    return mk<T>(v.x * c + v.y * s, v.y * c - v.x * s);
-  }
-}
-
-// v * exp(-2*pi*i*m/R) for an m that is a compile-time constant after unrolling
-template <typename T, int R, int M = 0> struct RootSel {
-  static __device__ __forceinline__ cx<T> run(cx<T> v, int m) { return m == M ? mul_root<T, R, M>(v) : RootSel<T, R, M + 1>::run(v, m); }
-};
-template <typename T, int R> struct RootSel<T, R, R> {
-  static __device__ __forceinline__ cx<T> run(cx<T> v, int) { return v; }
-};
-
-// forward DFT of R points held in registers, natural order in and out
-template <typename T, int R> struct RegFFT {
-  static __device__ __forceinline__ void run(cx<T> (&x)[R]) { Bfly<T, R>::run(x); }
-};
-
-template <typename T, int RA, int RB> struct Composite {
-  static constexpr int R = RA * RB;
-  template <int J, int S> static __device__ __forceinline__ void tw_row(cx<T> (&x)[R], const cx<T> (&y)[RA]) {
-    if constexpr (S < RA) {
-      x[J + RB * S] = mul_root<T, R, J * S>(y[S]);
-      tw_row<J, S + 1>(x, y);
-    }
-  }
-  template <int J> static __device__ __forceinline__ void stage_a(cx<T> (&x)[R]) {
-    if constexpr (J < RB) {
-      cx<T> y[RA];
-#pragma unroll
-      for (int q = 0; q < RA; ++q) y[q] = x[J + RB * q];
-      RegFFT<T, RA>::run(y);
-      tw_row<J, 0>(x, y);
-      stage_a<J + 1>(x);
-    }
-  }
-  static __device__ __forceinline__ void run(cx<T> (&x)[R]) {
-    stage_a<0>(x);
-    cx<T> out[R];
-#pragma unroll
-    for (int s = 0; s < RA; ++s) {
-      cx<T> z[RB];
-#pragma unroll
-      for (int j = 0; j < RB; ++j) z[j] = x[j + RB * s];
-      RegFFT<T, RB>::run(z);
-#pragma unroll
-      for (int r = 0; r < RB; ++r) out[s + RA * r] = z[r];
-    }
-#pragma unroll
-    for (int k = 0; k < R; ++k) x[k] = out[k];
-  }
-};
-template <typename T> struct RegFFT<T, 16> { static __device__ __forceinline__ void run(cx<T> (&x)[16]) { Composite<T, 4, 4>::run(x); } };
-template <typename T> struct RegFFT<T, 32> { static __device__ __forceinline__ void run(cx<T> (&x)[32]) { Composite<T, 4, 8>::run(x); } };
-template <typename T> struct RegFFT<T, 9> { static __device__ __forceinline__ void run(cx<T> (&x)[9]) { Composite<T, 3, 3>::run(x); } };
-template <typename T> struct RegFFT<T, 6> { static __device__ __forceinline__ void run(cx<T> (&x)[6]) { Composite<T, 2, 3>::run(x); } };
-template <typename T> struct RegFFT<T, 10> { static __device__ __forceinline__ void run(cx<T> (&x)[10]) { Composite<T, 2, 5>::run(x); } };
-template <typename T> struct RegFFT<T, 18> { static __device__ __forceinline__ void run(cx<T> (&x)[18]) { Composite<T, 2, 9>::run(x); } };
-template <typename T> struct RegFFT<T, 64> { static __device__ __forceinline__ void run(cx<T> (&x)[64]) { Composite<T, 8, 8>::run(x); } };
 
 template <typename T, int R1, int R2, int WARPS, int MINB, bool BWD>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
@@ -502,221 +431,16 @@ int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
 
 // fast_id encodes the specialised kernel chosen by the planner (0 = generic engine)
 
-// =================================================================================================
-// Three-pass register kernel: N = R1*R2*R3 complex points per row, T = N/E threads per row each
-// holding E points, two shared-memory exchanges, one row per CTA at a time, rows claimed dynamically.
-// (index formulas validated by tools/model_fast3.py)
-//
-//   load   x[t + T*q]                                                   coalesced LDG.128
-//   pass 1 radix R1 over j1 (regs q = m + (E/R1)*j1), twiddle tw1[k1][i1], i1 = t + T*m
-//   X1[k1*P1 + i1]            P1 = roundup(N/R1, S) + 1   -> pass-2 reads conflict-free
-//   pass 2 butterflies b2 = t + T*m2: k1 = b2 % R1, i2 = b2 / R1; radix R2 over X1[k1][i2 + R3*j2];
-//          twiddle tw2[k2][i2]
-//   X2[i2*P2 + k1 + R1*k2]    P2 = R1*R2 (aliases X1 after a barrier)
-//   pass 3 butterflies klow = t + T*m3: radix R3 over X2[j3][klow] -> X[klow + R1*R2*k3]   coalesced STG.128
-//
-// KIND: 0 = c2c; 1 = r2c (row of 2N reals viewed as N complex, Hermitian post-twiddle through shared
-// memory, N+1 bins out); 2 = c2r (N+1 bins in, pre-twiddle through shared memory, 2N reals out).
-// =================================================================================================
-enum { F3_C2C = 0, F3_R2C = 1, F3_C2R = 2 };
-
-__device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
-
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB>
-__global__ void __launch_bounds__((R1 * R2 * R3) / E, MINB)
-fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
-             const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, const cx<T> *__restrict__ twr, T fct,
-             unsigned int *__restrict__ sched) {
-  // pass-1 twiddles W_N^(t*k1) as a product A[k1>>2]*B[k1&3] of six per-thread values held in registers
-  // for the whole kernel (R1 = 16): 15 global table loads per row become 9 multiplies
-  constexpr bool TW1_REGS = (R1 == 16);  // with E/R1 > 1 the extra factor W_E^(m*k1) is a compile-time root
-  constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
-  constexpr int P1 = ((M1 + S - 1) / S) * S + 1, P2 = R1 * R2;
-  constexpr int NB1 = E / R1, NB2 = E / R2, NB3 = E / R3;
-  static_assert(E % R1 == 0 && E % R2 == 0 && E % R3 == 0 && TT % R1 == 0, "fast3 shape");
-  constexpr int BUFN = (R1 * P1 > N + 1) ? R1 * P1 : N + 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
-  unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + BUFN);  // [2] (+2 pad)
-  cx<T> *s_tw2 = reinterpret_cast<cx<T> *>(s_row + 4);                 // [R2][R3]
-  const int t = threadIdx.x;
-  if (t == 0) { s_row[0] = atomicAdd(&sched[0], 1u); s_row[1] = atomicAdd(&sched[0], 1u); }
-  for (int idx = t; idx < R2 * R3; idx += TT) s_tw2[idx] = tw2[idx];
-  cx<T> twA[3], twB[3];
-  if (TW1_REGS) {
-#pragma unroll
-    for (int a = 1; a < 4; ++a) { twA[a - 1] = tw1[(4 * a) * M1 + t]; twB[a - 1] = tw1[a * M1 + t]; }
-  }
-  __syncthreads();
-  constexpr uint32_t ROW_BYTES_IN = (KIND == F3_C2R ? (N + 1) : N) * sizeof(cx<T>);
-  const int k1 = t % R1, i2b = t / R1;  // pass-2 ownership (T % R1 == 0)
-  const cx<T> wt = KIND == F3_C2C ? mk<T>((T)1, (T)0) : __ldg(twr + t);   // real kinds: W_2N^t, this thread's twiddle factor
-  for (unsigned it = 0;; ++it) {
-    const uint64_t row = s_row[it & 1];
-    if (row >= nrows) break;
-    if (t == 0) {  // pull the next claimed row into L2 while this one is transformed
-      const uint64_t nxt = s_row[(it + 1) & 1];
-      if (nxt < nrows) {
-        const char *p = KIND == F3_R2C ? reinterpret_cast<const char *>(reinterpret_cast<const T *>(in_v) + (int64_t)nxt * rs_in)
-                                       : reinterpret_cast<const char *>(reinterpret_cast<const cx<T> *>(in_v) + (int64_t)nxt * rs_in);
-        // the bulk prefetch wants 16-byte aligned address and size (float c2r rows are only 8-byte aligned)
-        const uintptr_t lo = (reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15;
-        const uintptr_t hi = (reinterpret_cast<uintptr_t>(p) + ROW_BYTES_IN) & ~(uintptr_t)15;
-        if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void *>(lo), (uint32_t)(hi - lo));
-      }
-    }
-    cx<T> x[E];
-    // ---------------- load (+ c2r pre-twiddle) ----------------
-    if (KIND == F3_C2R) {
-      const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
-#pragma unroll
-      for (int q = 0; q < E; ++q) buf[t + TT * q] = src[t + TT * q];
-      if (t == 0) buf[N] = src[N];
-      __syncthreads();
-      if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // claim for iteration it+2
-#pragma unroll
-      for (int q = 0; q < E; ++q) {
-        const int n = t + TT * q;
-        cx<T> a = buf[n], b = buf[N - n];
-        if (BWD) { a.y = -a.y; b.y = -b.y; }       // c2r with forward=true conjugates its input
-        if (n == 0) { a.y = (T)0; b.y = (T)0; }    // imaginary parts of bins 0 and N are ignored
-        const cx<T> w = cconj(q == 0 ? wt : cmul(wt, __ldg(twr + TT * q)));   // e^{+2 pi i n/(2N)}, n = t + TT*q
-        const cx<T> s = cadd(a, cconj(b)), d = csub(a, cconj(b));
-        const cx<T> z = cadd(s, mul_pi(cmul(w, d)));
-        x[q] = cconj(z);                           // backward = conj(FFT(conj z))
-      }
-      __syncthreads();
-    } else {
-      const cx<T> *src = KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)row * rs_in)
-                                        : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
-#pragma unroll
-      for (int q = 0; q < E; ++q) {
-        x[q] = src[t + TT * q];
-        if (KIND == F3_C2C && BWD) x[q].y = -x[q].y;
-      }
-    }
-    // ---------------- pass 1 ----------------
-#pragma unroll
-    for (int m = 0; m < NB1; ++m) {
-      cx<T> y[R1];
-#pragma unroll
-      for (int j = 0; j < R1; ++j) y[j] = x[m + NB1 * j];
-      RegFFT<T, R1>::run(y);
-      const int i1 = t + TT * m;
-      if (TW1_REGS) {
-#pragma unroll
-        for (int k = 1; k < R1; ++k) {
-          const int a = k >> 2, b = k & 3;
-          if (a == 0) y[k] = cmul(y[k], twB[b - 1]);
-          else if (b == 0) y[k] = cmul(y[k], twA[a - 1]);
-          else y[k] = cmul(y[k], cmul(twA[a - 1], twB[b - 1]));
-          if (NB1 > 1 && m > 0) y[k] = RootSel<T, E>::run(y[k], (m * k) % E);
-        }
-      } else {
-#pragma unroll
-        for (int k = 1; k < R1; ++k) y[k] = cmul(y[k], __ldg(tw1 + k * M1 + i1));
-      }
-#pragma unroll
-      for (int k = 0; k < R1; ++k) buf[k * P1 + i1] = y[k];
-    }
-    __syncthreads();
-    if (KIND != F3_C2R && t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // everyone has read s_row[it&1]
-    // ---------------- pass 2 ----------------
-#pragma unroll
-    for (int m = 0; m < NB2; ++m) {
-      const int i2 = i2b + (TT / R1) * m;
-      cx<T> y[R2];
-#pragma unroll
-      for (int j = 0; j < R2; ++j) y[j] = buf[k1 * P1 + i2 + R3 * j];
-      RegFFT<T, R2>::run(y);
-#pragma unroll
-      for (int k = 1; k < R2; ++k) y[k] = cmul(y[k], s_tw2[k * R3 + i2]);
-#pragma unroll
-      for (int k = 0; k < R2; ++k) x[m * R2 + k] = y[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < NB2; ++m) {
-      const int i2 = i2b + (TT / R1) * m;
-#pragma unroll
-      for (int k = 0; k < R2; ++k) buf[i2 * P2 + k1 + R1 * k] = x[m * R2 + k];
-    }
-    __syncthreads();
-    // ---------------- pass 3 ----------------
-#pragma unroll
-    for (int m = 0; m < NB3; ++m) {
-      const int klow = t + TT * m;
-      cx<T> y[R3];
-#pragma unroll
-      for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
-      RegFFT<T, R3>::run(y);
-#pragma unroll
-      for (int k = 0; k < R3; ++k) x[m * R3 + k] = y[k];   // X[klow + R1*R2*k]
-    }
-    // ---------------- store ----------------
-    if (KIND == F3_C2C) {
-      cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
-#pragma unroll
-      for (int m = 0; m < NB3; ++m)
-#pragma unroll
-        for (int k = 0; k < R3; ++k) {
-          cx<T> v = x[m * R3 + k];
-          v.x *= fct; v.y *= BWD ? -fct : fct;
-          dst[t + TT * m + R1 * R2 * k] = v;
-        }
-      __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
-    } else if (KIND == F3_C2R) {
-      cx<T> *dst = reinterpret_cast<cx<T> *>(reinterpret_cast<T *>(out_v) + (int64_t)row * rs_out);
-#pragma unroll
-      for (int m = 0; m < NB3; ++m)
-#pragma unroll
-        for (int k = 0; k < R3; ++k) {
-          cx<T> v = x[m * R3 + k];
-          v.x *= fct; v.y *= -fct;                 // undo the conjugation of the backward trick
-          dst[t + TT * m + R1 * R2 * k] = v;       // (x[2n], x[2n+1])
-        }
-      __syncthreads();
-    } else {  // r2c: Hermitian post-twiddle needs Z[k] and Z[N-k]
-      __syncthreads();
-#pragma unroll
-      for (int m = 0; m < NB3; ++m)
-#pragma unroll
-        for (int k = 0; k < R3; ++k) buf[t + TT * m + R1 * R2 * k] = x[m * R3 + k];
-      __syncthreads();
-      cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
-      const T h = (T)0.5;
-#pragma unroll
-      for (int q = 0; q < E; ++q) {
-        const int k = t + TT * q;
-        const cx<T> a = buf[k], b = cconj(buf[k == 0 ? 0 : N - k]);
-        const cx<T> Ev = mk<T>((a.x + b.x) * h, (a.y + b.y) * h), Dv = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
-        // W_2N^k = W^t * W^(TT*q): one per-thread factor and one warp-uniform factor (both L1-resident)
-        // instead of a 16-byte table entry per output streamed from L2
-        const cx<T> wk = q == 0 ? wt : cmul(wt, __ldg(twr + TT * q));
-        cx<T> v = cadd(Ev, cmul(wk, mul_mi(Dv)));
-        v.x *= fct; v.y *= BWD ? -fct : fct;       // r2c with forward=false returns the conjugate spectrum
-        dst[k] = v;
-        if (k == 0) {                               // bin N: Re Z0 - Im Z0
-          cx<T> last = mk<T>((a.x - a.y) * fct, (T)0);
-          dst[N] = last;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  // the last CTA to leave re-arms the scheduler words
-  __syncthreads();
-  if (t == 0) {
-    __threadfence();
-    const unsigned done = atomicAdd(&sched[1], 1u);
-    if (done == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
-  }
-}
-
 namespace {
-template <typename T, int R1, int R2, int R3, int E, int MINB, bool REAL_ONLY = false>
+// IMPULSE_FFT_R2C_PAIR=0 restores the post-twiddle through shared memory (A/B runs)
+inline bool r2c_pair_enabled() {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_R2C_PAIR"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
+
+// PAIRMODE: 0 = r2c post-twiddle through shared memory; 1 = in pass 3 (pair units) unless switched off;
+// 2 = the shape exists for the pair variant only (r2c rows)
+template <typename T, int R1, int R2, int R3, int E, int MINB, bool REAL_ONLY = false, int PAIRMODE = 0>
 int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
@@ -735,8 +459,16 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
     case 4: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB>; break;
     default: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB>; break;
   }
-  static PerDeviceFlag flags[6];
-  bool &configured_here = flags[kind * 2 + (bwd ? 1 : 0)].here();
+  bool pair = false;
+  if constexpr (PAIRMODE != 0) {
+    if (kind == F3_R2C && (PAIRMODE == 2 || r2c_pair_enabled())) {
+      pair = true;
+      k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB, true>;
+    }
+    if (PAIRMODE == 2 && kind != F3_R2C) return (int)cudaErrorInvalidValue;
+  }
+  static PerDeviceFlag flags[8];
+  bool &configured_here = flags[pair ? 6 + (bwd ? 1 : 0) : kind * 2 + (bwd ? 1 : 0)].here();
   if (!configured_here) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -1506,13 +1238,13 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST2R_32_F32: g_last_kernel = "fast2r_kernel<float,8,4>"; return launch_fast2r<float, 8, 4, 8, 6>(J, sm_count, s);
     case FAST2R_64_F32: g_last_kernel = "fast2r_kernel<float,8,8>"; return launch_fast2r<float, 8, 8, 8, 6>(J, sm_count, s);
     case FAST2R_128_F32: g_last_kernel = "fast2r_kernel<float,16,8>"; return launch_fast2r<float, 16, 8, 8, 4>(J, sm_count, s);
-    case FAST3R_256_F64: g_last_kernel = "fast3_kernel<double,8,8,4,E8>"; return launch_fast3<double, 8, 8, 4, 8, 16, true>(J, sm_count, s);
+    case FAST3R_256_F64: g_last_kernel = "fast3_kernel<double,8,8,4,E8>"; return launch_fast3<double, 8, 8, 4, 8, 16, true, 1>(J, sm_count, s);
     case FAST3R_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E8>"; return launch_fast3<double, 8, 8, 8, 8, 8, true>(J, sm_count, s);
-    case FAST3R_1024_F64: g_last_kernel = "fast3_kernel<double,16,8,8,E16>"; return launch_fast3<double, 16, 8, 8, 16, 8, true>(J, sm_count, s);
-    case FAST3R_256_F32: g_last_kernel = "fast3_kernel<float,8,8,4,E8>"; return launch_fast3<float, 8, 8, 4, 8, 16, true>(J, sm_count, s);
+    case FAST3R_1024_F64: g_last_kernel = "fast3_kernel<double,16,8,8,E16>"; return launch_fast3<double, 16, 8, 8, 16, 8, true, 1>(J, sm_count, s);
+    case FAST3R_256_F32: g_last_kernel = "fast3_kernel<float,8,8,4,E8>"; return launch_fast3<float, 8, 8, 4, 8, 16, true, 1>(J, sm_count, s);
     case FAST3R_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E8>"; return launch_fast3<float, 8, 8, 8, 8, 12, true>(J, sm_count, s);
-    case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, true>(J, sm_count, s);
-    case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3>(J, sm_count, s);
+    case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, true, 1>(J, sm_count, s);
+    case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, false, 1>(J, sm_count, s);
     case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2>(J, sm_count, s);
     case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1>(J, sm_count, s);
     case FASTBLUE_2048_F64: g_last_kernel = "fastblue_kernel<double,16,16,8,E16>"; return launch_fastblue<double, 16, 16, 8, 16>(J, sm_count, s);
@@ -1541,8 +1273,10 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8>(J, sm_count, s);
     case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4>(J, sm_count, s);
     case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5>(J, sm_count, s);
+    case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10,pair>"; return launch_fast3<double, 10, 10, 5, 10, 8, true, 2>(J, sm_count, s);
+    case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18,pair>"; return launch_fast3<double, 18, 18, 6, 18, 4, true, 2>(J, sm_count, s);
     case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2>(J, sm_count, s);
-    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4>(J, sm_count, s);
+    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, false, 1>(J, sm_count, s);
     case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;
   }

@@ -142,6 +142,8 @@ enum FastId : uint32_t {
   FAST2R_32_F32 = 54,
   FAST2R_64_F32 = 55,
   FAST2R_128_F32 = 56,
+  FAST3R_500_F64 = 57,   // r2c-only shapes whose pass 3 pairs bin k with bin N-k in registers (10*10*5, 18*18*6)
+  FAST3R_1944_F64 = 58,
 };
 
 struct Phase {

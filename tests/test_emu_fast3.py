@@ -1,0 +1,73 @@
+"""CPU-only check of fast3_kernel's index algebra through the thread-per-thread host emulation
+(tests/emu/emu_fast3.cpp): the SAME kernel body the GPU runs, compiled with g++.  The paths that were already
+parity-green on the B200 (c2c, r2c/c2r through shared memory) pin the emulation itself; the in-register pair
+post-twiddle (PAIR) is then checked the same way.  Semantics: pocketfft r2c/c2r with `forward`
+(pocketfft_hdronly.h:3125-3250) restated with numpy."""
+import numpy as np
+import pytest
+
+from tests.emu import harness_fast3 as f3
+
+SHAPES_PAIR = [(16, 16, 8, 16), (16, 8, 8, 16), (8, 8, 4, 8), (10, 10, 5, 10), (18, 18, 6, 18)]
+SHAPES_OLD = [(8, 8, 8, 8), (5, 10, 10, 10), (6, 18, 18, 18), (16, 16, 16, 16)]
+
+
+def rel(a, b):
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+def ref_r2c(x, forward, fct):
+    X = np.fft.rfft(x.astype(np.float64), axis=1)
+    return (X if forward else np.conj(X)) * fct
+
+
+def ref_c2r(X, n, forward, fct):
+    X = X.astype(np.complex128).copy()
+    if forward:
+        X = np.conj(X)
+    return np.fft.irfft(X, n=n, axis=1) * n * fct
+
+
+@pytest.mark.parametrize("shape", SHAPES_PAIR + SHAPES_OLD)
+def test_emulation_matches_known_good_paths(shape):
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(n)
+    x = rng.random((3, 2 * n)) - 0.5
+    assert rel(f3.run(shape, "r2c", x, True, 0.5), ref_r2c(x, True, 0.5)) < 2e-15 * np.log2(n) * 4
+    X = ref_r2c(x, True, 1.0)
+    X[:, 0] += 0.25j   # the imaginary parts of bins 0 and N must be ignored
+    assert rel(f3.run(shape, "c2r", X, False, 1.0 / (2 * n)), x) < 2e-15 * np.log2(n) * 4
+    if shape in ((16, 16, 8, 16), (16, 16, 16, 16), (5, 10, 10, 10)):
+        z = rng.random((2, n)) - 0.5 + 1j * (rng.random((2, n)) - 0.5)
+        assert rel(f3.run(shape, "c2c", z, True, 2.0), np.fft.fft(z, axis=1) * 2.0) < 2e-15 * np.log2(n) * 4
+        assert rel(f3.run(shape, "c2c", z, False, 1.0), np.fft.ifft(z, axis=1) * n) < 2e-15 * np.log2(n) * 4
+
+
+@pytest.mark.parametrize("shape", SHAPES_PAIR)
+@pytest.mark.parametrize("forward", [True, False])
+def test_pair_post_twiddle_f64(shape, forward):
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(7 * n + forward)
+    x = rng.random((5, 2 * n)) - 0.5     # 5 rows over 2 CTAs: exercises the dynamic row claims
+    got = f3.run(shape, "r2c", x, forward, 0.75, pair=True, ctas=2)
+    assert not np.isnan(got.view(np.float64)).any()      # every bin 0..N written
+    want = ref_r2c(x, forward, 0.75)
+    assert rel(got, want) < 2e-15 * np.log2(n) * 4
+    for r in range(x.shape[0]):
+        assert rel(got[r], want[r]) < 2e-15 * np.log2(n) * 4
+    # same numbers as the shared-memory post-twiddle to rounding
+    old = f3.run(shape, "r2c", x, forward, 0.75, pair=False, ctas=1)
+    assert rel(got, old) < 1e-15
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 8, 16), (16, 8, 8, 16), (8, 8, 4, 8)])
+def test_pair_post_twiddle_f32(shape):
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(n + 1)
+    x = (rng.random((3, 2 * n)) - 0.5).astype(np.float32)
+    got = f3.run(shape, "r2c", x, True, 1.0, pair=True)
+    assert got.dtype == np.complex64 and not np.isnan(got.view(np.float32)).any()
+    assert rel(got.astype(np.complex128), ref_r2c(x, True, 1.0)) < 1e-6 * np.log2(n)

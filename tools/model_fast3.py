@@ -61,3 +61,56 @@ for (N, R1, R2, R3, E) in ((4096, 16, 16, 16, 16), (2048, 8, 16, 16, 16), (2048,
         print(N, (R1, R2, R3), E, "T=", N // E, "err", np.abs(out - np.fft.fft(x)).max(), "pass2-read conflicts", conf)
     except AssertionError as e:
         print(N, (R1, R2, R3), E, "constraint violated")
+
+
+def model_r2c_pair(N, R1, R2, R3, E, xr):
+    """r2c of 2N reals with the Hermitian post-twiddle done INSIDE pass 3: a thread runs the pass-3 butterflies
+    klow = u and P2 - u, whose outputs are each other's mirrors (bin k = u + P2*k3 <-> N - k = (P2-u) + P2*(R3-1-k3)),
+    so Z[k] and Z[N-k] meet in registers.  Unit 0 = butterflies 0 and P2/2 (each mirrors into itself)."""
+    T = N // E
+    P2 = R1 * R2
+    assert P2 % 2 == 0
+    z = xr[0::2] + 1j * xr[1::2]
+    Z, _ = model(N, R1, R2, R3, E, z, check_conflicts=False)     # Z[klow + P2*k3] is what butterfly klow leaves in y[k3]
+    out = np.full(N + 1, np.nan, complex)
+    units = P2 // 2
+    NU = -(-units // T)                                           # units per thread (last sweep may be ragged)
+    w2n = lambda k: np.exp(-1j * np.pi * k / N)
+    owner = {}
+    for t in range(T):
+        for mu in range(NU):
+            u = t + T * mu
+            if u >= units:
+                continue
+            if u == 0:
+                ya = np.array([Z[0 + P2 * k3] for k3 in range(R3)]); yb = np.array([Z[P2 // 2 + P2 * k3] for k3 in range(R3)])
+                out[0] = ya[0].real + ya[0].imag; out[N] = ya[0].real - ya[0].imag
+                for k3 in range(1, R3 // 2 + 1):
+                    a, c = ya[k3], ya[R3 - k3]; k = P2 * k3
+                    s, d = a + np.conj(c), a - np.conj(c)
+                    Q = 0.5j * w2n(k) * d
+                    out[k] = 0.5 * s - Q; out[N - k] = np.conj(0.5 * s + Q)
+                for k3 in range((R3 + 1) // 2):
+                    a, c = yb[k3], yb[R3 - 1 - k3]; k = P2 // 2 + P2 * k3
+                    s, d = a + np.conj(c), a - np.conj(c)
+                    Q = 0.5j * w2n(k) * d
+                    out[k] = 0.5 * s - Q; out[N - k] = np.conj(0.5 * s + Q)
+                continue
+            ka, kb = u, P2 - u
+            ya = np.array([Z[ka + P2 * k3] for k3 in range(R3)]); yb = np.array([Z[kb + P2 * k3] for k3 in range(R3)])
+            wt = w2n(u)                                           # per-thread factor, twr[u]
+            for k3 in range(R3):
+                a, c = ya[k3], yb[R3 - 1 - k3]; k = ka + P2 * k3
+                root = np.exp(-2j * np.pi * k3 / (2 * R3))        # compile-time root W_{2 R3}^{k3}
+                s, d = a + np.conj(c), a - np.conj(c)
+                Q = 0.5j * (wt * root) * d
+                assert k not in owner and (N - k) not in owner
+                owner[k] = owner[N - k] = t
+                out[k] = 0.5 * s - Q; out[N - k] = np.conj(0.5 * s + Q)
+    return out
+
+
+for (N, R1, R2, R3, E) in ((2048, 16, 16, 8, 16), (1024, 16, 8, 8, 16), (256, 8, 8, 4, 8), (500, 10, 10, 5, 10), (1944, 18, 18, 6, 18), (1000, 10, 10, 10, 10), (4096, 16, 16, 16, 16)):
+    xr = rng.standard_normal(2 * N)
+    out = model_r2c_pair(N, R1, R2, R3, E, xr)
+    print("r2c pair", 2 * N, (R1, R2, R3), E, "err", np.abs(out - np.fft.rfft(xr)).max())
