@@ -150,61 +150,129 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
       }
     }
     cx<T> x[E];
-    // ---------------- load (+ c2r pre-twiddle) ----------------
-    if (KIND == F3_C2R) {
+    if constexpr (KIND == F3_C2R && PAIR) {
+      // ---------------- load + c2r pre-twiddle in registers + pass 1 ----------------
+      // Pass-1 butterfly i1 consumes z[i1 + M1*j]; the mirror of that point, N - n = (M1 - i1) + M1*(R1-1-j),
+      // feeds butterfly M1 - i1.  A thread that owns BOTH butterflies of a unit {u, M1 - u} loads X[n] and X[N-n]
+      // straight from global memory (ascending / descending runs across the lanes, both coalesced) and forms
+      //   z[n] = conj(s + p),  z[N-n] = s - p,   s = X[n] + conj X[N-n],  p = i conj(W_2N^n) (X[n] - conj X[N-n]),
+      // with W_2N^n = W_2N^u * W_(2 R1)^j (per-thread factor x compile-time root): no staging buffer, no barrier.
+      // Unit 0 = butterflies 0 and M1/2, which mirror into themselves.  (backward = conj(FFT(conj z)).)
+      static_assert(M1 % 2 == 0, "pair units need an even N/R1");
+      constexpr int UNITS = M1 / 2, NU = (UNITS + TT - 1) / TT;
       const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
-#pragma unroll
-      for (int q = 0; q < E; ++q) buf[t + TT * q] = src[t + TT * q];
-      if (t == 0) buf[N] = src[N];
-      __syncthreads();
-      if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // claim for iteration it+2
-#pragma unroll
-      for (int q = 0; q < E; ++q) {
-        const int n = t + TT * q;
-        cx<T> a = buf[n], b = buf[N - n];
-        if (BWD) { a.y = -a.y; b.y = -b.y; }       // c2r with forward=true conjugates its input
-        if (n == 0) { a.y = (T)0; b.y = (T)0; }    // imaginary parts of bins 0 and N are ignored
-        const cx<T> w = cconj(q == 0 ? wt : cmul(wt, __ldg(twr + TT * q)));   // e^{+2 pi i n/(2N)}, n = t + TT*q
-        const cx<T> s = cadd(a, cconj(b)), d = csub(a, cconj(b));
-        const cx<T> z = cadd(s, mul_pi(cmul(w, d)));
-        x[q] = cconj(z);                           // backward = conj(FFT(conj z))
-      }
-      __syncthreads();
-    } else {
-      const cx<T> *src = KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)row * rs_in)
-                                        : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
-#pragma unroll
-      for (int q = 0; q < E; ++q) {
-        x[q] = src[t + TT * q];
-        if (KIND == F3_C2C && BWD) x[q].y = -x[q].y;
-      }
-    }
-    // ---------------- pass 1 ----------------
-#pragma unroll
-    for (int m = 0; m < NB1; ++m) {
-      cx<T> y[R1];
-#pragma unroll
-      for (int j = 0; j < R1; ++j) y[j] = x[m + NB1 * j];
-      RegFFT<T, R1>::run(y);
-      const int i1 = t + TT * m;
-      if (TW1_REGS) {
-#pragma unroll
-        for (int k = 1; k < R1; ++k) {
-          const int a = k >> 2, b = k & 3;
-          if (a == 0) y[k] = cmul(y[k], twB[b - 1]);
-          else if (b == 0) y[k] = cmul(y[k], twA[a - 1]);
-          else y[k] = cmul(y[k], cmul(twA[a - 1], twB[b - 1]));
-          if (NB1 > 1 && m > 0) y[k] = RootSel<T, E>::run(y[k], (m * k) % E);
-        }
-      } else {
+      auto pass1 = [&](cx<T> (&y)[R1], const int i1) {
+        RegFFT<T, R1>::run(y);
 #pragma unroll
         for (int k = 1; k < R1; ++k) y[k] = cmul(y[k], __ldg(tw1 + k * M1 + i1));
-      }
 #pragma unroll
-      for (int k = 0; k < R1; ++k) buf[k * P1 + i1] = y[k];
+        for (int k = 0; k < R1; ++k) buf[k * P1 + i1] = y[k];
+      };
+#pragma unroll
+      for (int mu = 0; mu < NU; ++mu) {
+        const int u = t + TT * mu;
+        if (UNITS % TT != 0 && u >= UNITS) continue;
+        const int ka = u, kb = u == 0 ? M1 / 2 : M1 - u;
+        cx<T> A[R1], B[R1], xa[R1], xb[R1];
+#pragma unroll
+        for (int j = 0; j < R1; ++j) { A[j] = src[ka + M1 * j]; B[j] = src[kb + M1 * j]; }
+        if (BWD) {                                  // c2r with forward=true conjugates its input
+#pragma unroll
+          for (int j = 0; j < R1; ++j) { A[j].y = -A[j].y; B[j].y = -B[j].y; }
+        }
+        if (u != 0) {
+          const cx<T> wu = mu == 0 ? wt : __ldg(twr + u);
+          const cx<T> cwi = mk<T>(wu.y, wu.x);      // i * conj(W_2N^u)
+#pragma unroll
+          for (int j = 0; j < R1; ++j) {
+            const cx<T> a = A[j], b = B[R1 - 1 - j];
+            const cx<T> s = mk<T>(a.x + b.x, a.y - b.y), d = mk<T>(a.x - b.x, a.y + b.y);
+            const cx<T> pp = RootSel<T, 2 * R1>::run(cmul(cwi, d), (2 * R1 - j) % (2 * R1));   // * conj(W_(2 R1)^j)
+            xa[j] = mk<T>(s.x + pp.x, -(s.y + pp.y));
+            xb[R1 - 1 - j] = mk<T>(s.x - pp.x, s.y - pp.y);
+          }
+        } else {
+          {                                         // n = 0 pairs with bin N; their imaginary parts are ignored
+            const T a0 = A[0].x, bn = src[N].x;
+            xa[0] = mk<T>(a0 + bn, -(a0 - bn));
+          }
+#pragma unroll
+          for (int j = 1; j <= R1 / 2; ++j) {       // butterfly 0: n = M1*j <-> M1*(R1-j)
+            const cx<T> a = A[j], b = A[R1 - j], w = __ldg(twr + M1 * j);
+            const cx<T> s = mk<T>(a.x + b.x, a.y - b.y), d = mk<T>(a.x - b.x, a.y + b.y);
+            const cx<T> pp = cmul(mk<T>(w.y, w.x), d);
+            xa[j] = mk<T>(s.x + pp.x, -(s.y + pp.y));
+            xa[R1 - j] = mk<T>(s.x - pp.x, s.y - pp.y);
+          }
+#pragma unroll
+          for (int j = 0; j < (R1 + 1) / 2; ++j) {  // butterfly M1/2: n = M1/2 + M1*j <-> M1/2 + M1*(R1-1-j)
+            const cx<T> a = B[j], b = B[R1 - 1 - j], w = __ldg(twr + M1 / 2 + M1 * j);
+            const cx<T> s = mk<T>(a.x + b.x, a.y - b.y), d = mk<T>(a.x - b.x, a.y + b.y);
+            const cx<T> pp = cmul(mk<T>(w.y, w.x), d);
+            xb[j] = mk<T>(s.x + pp.x, -(s.y + pp.y));
+            xb[R1 - 1 - j] = mk<T>(s.x - pp.x, s.y - pp.y);
+          }
+        }
+        pass1(xa, ka);
+        pass1(xb, kb);
+      }
+    } else {
+      // ---------------- load (+ c2r pre-twiddle) ----------------
+      if (KIND == F3_C2R) {
+        const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
+#pragma unroll
+        for (int q = 0; q < E; ++q) buf[t + TT * q] = src[t + TT * q];
+        if (t == 0) buf[N] = src[N];
+        __syncthreads();
+        if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // claim for iteration it+2
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int n = t + TT * q;
+          cx<T> a = buf[n], b = buf[N - n];
+          if (BWD) { a.y = -a.y; b.y = -b.y; }       // c2r with forward=true conjugates its input
+          if (n == 0) { a.y = (T)0; b.y = (T)0; }    // imaginary parts of bins 0 and N are ignored
+          const cx<T> w = cconj(q == 0 ? wt : cmul(wt, __ldg(twr + TT * q)));   // e^{+2 pi i n/(2N)}, n = t + TT*q
+          const cx<T> s = cadd(a, cconj(b)), d = csub(a, cconj(b));
+          const cx<T> z = cadd(s, mul_pi(cmul(w, d)));
+          x[q] = cconj(z);                           // backward = conj(FFT(conj z))
+        }
+        __syncthreads();
+      } else {
+        const cx<T> *src = KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)row * rs_in)
+                                          : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          x[q] = src[t + TT * q];
+          if (KIND == F3_C2C && BWD) x[q].y = -x[q].y;
+        }
+      }
+      // ---------------- pass 1 ----------------
+#pragma unroll
+      for (int m = 0; m < NB1; ++m) {
+        cx<T> y[R1];
+#pragma unroll
+        for (int j = 0; j < R1; ++j) y[j] = x[m + NB1 * j];
+        RegFFT<T, R1>::run(y);
+        const int i1 = t + TT * m;
+        if (TW1_REGS) {
+#pragma unroll
+          for (int k = 1; k < R1; ++k) {
+            const int a = k >> 2, b = k & 3;
+            if (a == 0) y[k] = cmul(y[k], twB[b - 1]);
+            else if (b == 0) y[k] = cmul(y[k], twA[a - 1]);
+            else y[k] = cmul(y[k], cmul(twA[a - 1], twB[b - 1]));
+            if (NB1 > 1 && m > 0) y[k] = RootSel<T, E>::run(y[k], (m * k) % E);
+          }
+        } else {
+#pragma unroll
+          for (int k = 1; k < R1; ++k) y[k] = cmul(y[k], __ldg(tw1 + k * M1 + i1));
+        }
+#pragma unroll
+        for (int k = 0; k < R1; ++k) buf[k * P1 + i1] = y[k];
+      }
     }
     __syncthreads();
-    if (KIND != F3_C2R && t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // everyone has read s_row[it&1]
+    if ((KIND != F3_C2R || PAIR) && t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // everyone has read s_row[it&1]
     // ---------------- pass 2 ----------------
 #pragma unroll
     for (int m = 0; m < NB2; ++m) {
@@ -286,68 +354,68 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
         }
       }
       __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
-      continue;
-    }
-    // ---------------- pass 3 ----------------
+    } else {
+      // ---------------- pass 3 ----------------
 #pragma unroll
-    for (int m = 0; m < NB3; ++m) {
-      const int klow = t + TT * m;
-      cx<T> y[R3];
+      for (int m = 0; m < NB3; ++m) {
+        const int klow = t + TT * m;
+        cx<T> y[R3];
 #pragma unroll
-      for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
-      RegFFT<T, R3>::run(y);
+        for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
+        RegFFT<T, R3>::run(y);
 #pragma unroll
-      for (int k = 0; k < R3; ++k) x[m * R3 + k] = y[k];   // X[klow + R1*R2*k]
-    }
-    // ---------------- store ----------------
-    if (KIND == F3_C2C) {
-      cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
-#pragma unroll
-      for (int m = 0; m < NB3; ++m)
-#pragma unroll
-        for (int k = 0; k < R3; ++k) {
-          cx<T> v = x[m * R3 + k];
-          v.x *= fct; v.y *= BWD ? -fct : fct;
-          dst[t + TT * m + R1 * R2 * k] = v;
-        }
-      __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
-    } else if (KIND == F3_C2R) {
-      cx<T> *dst = reinterpret_cast<cx<T> *>(reinterpret_cast<T *>(out_v) + (int64_t)row * rs_out);
-#pragma unroll
-      for (int m = 0; m < NB3; ++m)
-#pragma unroll
-        for (int k = 0; k < R3; ++k) {
-          cx<T> v = x[m * R3 + k];
-          v.x *= fct; v.y *= -fct;                 // undo the conjugation of the backward trick
-          dst[t + TT * m + R1 * R2 * k] = v;       // (x[2n], x[2n+1])
-        }
-      __syncthreads();
-    } else {  // r2c: Hermitian post-twiddle needs Z[k] and Z[N-k]
-      __syncthreads();
-#pragma unroll
-      for (int m = 0; m < NB3; ++m)
-#pragma unroll
-        for (int k = 0; k < R3; ++k) buf[t + TT * m + R1 * R2 * k] = x[m * R3 + k];
-      __syncthreads();
-      cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
-      const T h = (T)0.5;
-#pragma unroll
-      for (int q = 0; q < E; ++q) {
-        const int k = t + TT * q;
-        const cx<T> a = buf[k], b = cconj(buf[k == 0 ? 0 : N - k]);
-        const cx<T> Ev = mk<T>((a.x + b.x) * h, (a.y + b.y) * h), Dv = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
-        // W_2N^k = W^t * W^(TT*q): one per-thread factor and one warp-uniform factor (both L1-resident)
-        // instead of a 16-byte table entry per output streamed from L2
-        const cx<T> wk = q == 0 ? wt : cmul(wt, __ldg(twr + TT * q));
-        cx<T> v = cadd(Ev, cmul(wk, mul_mi(Dv)));
-        v.x *= fct; v.y *= BWD ? -fct : fct;       // r2c with forward=false returns the conjugate spectrum
-        dst[k] = v;
-        if (k == 0) {                               // bin N: Re Z0 - Im Z0
-          cx<T> last = mk<T>((a.x - a.y) * fct, (T)0);
-          dst[N] = last;
-        }
+        for (int k = 0; k < R3; ++k) x[m * R3 + k] = y[k];   // X[klow + R1*R2*k]
       }
-      __syncthreads();
+      // ---------------- store ----------------
+      if (KIND == F3_C2C) {
+        cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
+#pragma unroll
+        for (int m = 0; m < NB3; ++m)
+#pragma unroll
+          for (int k = 0; k < R3; ++k) {
+            cx<T> v = x[m * R3 + k];
+            v.x *= fct; v.y *= BWD ? -fct : fct;
+            dst[t + TT * m + R1 * R2 * k] = v;
+          }
+        __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
+      } else if (KIND == F3_C2R) {
+        cx<T> *dst = reinterpret_cast<cx<T> *>(reinterpret_cast<T *>(out_v) + (int64_t)row * rs_out);
+#pragma unroll
+        for (int m = 0; m < NB3; ++m)
+#pragma unroll
+          for (int k = 0; k < R3; ++k) {
+            cx<T> v = x[m * R3 + k];
+            v.x *= fct; v.y *= -fct;                 // undo the conjugation of the backward trick
+            dst[t + TT * m + R1 * R2 * k] = v;       // (x[2n], x[2n+1])
+          }
+        __syncthreads();
+      } else {  // r2c: Hermitian post-twiddle needs Z[k] and Z[N-k]
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < NB3; ++m)
+#pragma unroll
+          for (int k = 0; k < R3; ++k) buf[t + TT * m + R1 * R2 * k] = x[m * R3 + k];
+        __syncthreads();
+        cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
+        const T h = (T)0.5;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int k = t + TT * q;
+          const cx<T> a = buf[k], b = cconj(buf[k == 0 ? 0 : N - k]);
+          const cx<T> Ev = mk<T>((a.x + b.x) * h, (a.y + b.y) * h), Dv = mk<T>((a.x - b.x) * h, (a.y - b.y) * h);
+          // W_2N^k = W^t * W^(TT*q): one per-thread factor and one warp-uniform factor (both L1-resident)
+          // instead of a 16-byte table entry per output streamed from L2
+          const cx<T> wk = q == 0 ? wt : cmul(wt, __ldg(twr + TT * q));
+          cx<T> v = cadd(Ev, cmul(wk, mul_mi(Dv)));
+          v.x *= fct; v.y *= BWD ? -fct : fct;       // r2c with forward=false returns the conjugate spectrum
+          dst[k] = v;
+          if (k == 0) {                               // bin N: Re Z0 - Im Z0
+            cx<T> last = mk<T>((a.x - a.y) * fct, (T)0);
+            dst[N] = last;
+          }
+        }
+        __syncthreads();
+      }
     }
   }
   // the last CTA to leave re-arms the scheduler words

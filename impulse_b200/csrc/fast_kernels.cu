@@ -17,6 +17,7 @@
 // from long double on the host.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "fast3_device.cuh"
@@ -432,15 +433,20 @@ int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
 // fast_id encodes the specialised kernel chosen by the planner (0 = generic engine)
 
 namespace {
-// IMPULSE_FFT_R2C_PAIR=0 restores the post-twiddle through shared memory (A/B runs)
+// IMPULSE_FFT_R2C_PAIR=0 / IMPULSE_FFT_C2R_PAIR=0 restore the post- / pre-twiddle through shared memory (A/B runs)
 inline bool r2c_pair_enabled() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_R2C_PAIR"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
+inline bool c2r_pair_enabled() {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_C2R_PAIR"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
 
-// PAIRMODE: 0 = r2c post-twiddle through shared memory; 1 = in pass 3 (pair units) unless switched off;
-// 2 = the shape exists for the pair variant only (r2c rows)
-template <typename T, int R1, int R2, int R3, int E, int MINB, bool REAL_ONLY = false, int PAIRMODE = 0>
+// KINDS: which kinds the shape is instantiated for (1 = c2c, 2 = r2c, 4 = c2r).
+// PAIRS: 1 = r2c post-twiddle in pass 3 (pair units) unless switched off, 2 = r2c always paired (the shape exists
+//        for that variant only); 4 / 8 = the same for the c2r pre-twiddle in pass 1.
+template <typename T, int R1, int R2, int R3, int E, int MINB, int KINDS = 7, int PAIRS = 0>
 int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
@@ -450,25 +456,42 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   const bool bwd = kind == F3_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == F3_R2C ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
   typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, const cx<T> *, const cx<T> *, const cx<T> *, T, unsigned int *);
   kern_t k = nullptr;
-  if (REAL_ONLY && kind == F3_C2C) return (int)cudaErrorInvalidValue;   // complex rows of this length use the two-pass kernels
-  switch (kind * 2 + (bwd ? 1 : 0)) {
-    case 0: k = fast3_kernel<T, R1, R2, R3, E, REAL_ONLY ? F3_R2C : F3_C2C, false, MINB>; break;
-    case 1: k = fast3_kernel<T, R1, R2, R3, E, REAL_ONLY ? F3_R2C : F3_C2C, true, MINB>; break;
-    case 2: k = fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB>; break;
-    case 3: k = fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB>; break;
-    case 4: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB>; break;
-    default: k = fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB>; break;
-  }
   bool pair = false;
-  if constexpr (PAIRMODE != 0) {
-    if (kind == F3_R2C && (PAIRMODE == 2 || r2c_pair_enabled())) {
-      pair = true;
-      k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB, true>;
+  if (kind == F3_C2C) {
+    if constexpr ((KINDS & 1) != 0) k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB>;
+  } else if (kind == F3_R2C) {
+    if constexpr ((KINDS & 2) != 0) {
+      if constexpr ((PAIRS & 3) != 0) {
+        if ((PAIRS & 2) != 0 || r2c_pair_enabled()) {
+          pair = true;
+          k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB, true>;
+        }
+      }
+      if constexpr ((PAIRS & 2) == 0) {
+        if (!pair) k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB>;
+      }
     }
-    if (PAIRMODE == 2 && kind != F3_R2C) return (int)cudaErrorInvalidValue;
+  } else {
+    if constexpr ((KINDS & 4) != 0) {
+      if constexpr ((PAIRS & 12) != 0) {
+        if ((PAIRS & 8) != 0 || c2r_pair_enabled()) {
+          pair = true;
+          k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB, true>;
+        }
+      }
+      if constexpr ((PAIRS & 8) == 0) {
+        if (!pair) k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB>;
+      }
+    }
   }
-  static PerDeviceFlag flags[8];
-  bool &configured_here = flags[pair ? 6 + (bwd ? 1 : 0) : kind * 2 + (bwd ? 1 : 0)].here();
+  if (!k) return (int)cudaErrorInvalidValue;   // the planner never selects a shape for a kind it is not built for
+  if (pair) {  // reported by impulse_fft_last_kernel()
+    static thread_local char name[96];
+    snprintf(name, sizeof(name), "%s+pair", g_last_kernel);
+    g_last_kernel = name;
+  }
+  static PerDeviceFlag flags[12];
+  bool &configured_here = flags[(pair ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
   if (!configured_here) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -1238,15 +1261,15 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST2R_32_F32: g_last_kernel = "fast2r_kernel<float,8,4>"; return launch_fast2r<float, 8, 4, 8, 6>(J, sm_count, s);
     case FAST2R_64_F32: g_last_kernel = "fast2r_kernel<float,8,8>"; return launch_fast2r<float, 8, 8, 8, 6>(J, sm_count, s);
     case FAST2R_128_F32: g_last_kernel = "fast2r_kernel<float,16,8>"; return launch_fast2r<float, 16, 8, 8, 4>(J, sm_count, s);
-    case FAST3R_256_F64: g_last_kernel = "fast3_kernel<double,8,8,4,E8>"; return launch_fast3<double, 8, 8, 4, 8, 16, true, 1>(J, sm_count, s);
-    case FAST3R_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E8>"; return launch_fast3<double, 8, 8, 8, 8, 8, true>(J, sm_count, s);
-    case FAST3R_1024_F64: g_last_kernel = "fast3_kernel<double,16,8,8,E16>"; return launch_fast3<double, 16, 8, 8, 16, 8, true, 1>(J, sm_count, s);
-    case FAST3R_256_F32: g_last_kernel = "fast3_kernel<float,8,8,4,E8>"; return launch_fast3<float, 8, 8, 4, 8, 16, true, 1>(J, sm_count, s);
-    case FAST3R_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E8>"; return launch_fast3<float, 8, 8, 8, 8, 12, true>(J, sm_count, s);
-    case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, true, 1>(J, sm_count, s);
-    case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, false, 1>(J, sm_count, s);
-    case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2>(J, sm_count, s);
-    case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1>(J, sm_count, s);
+    case FAST3R_256_F64: g_last_kernel = "fast3_kernel<double,8,8,4,E8>"; return launch_fast3<double, 8, 8, 4, 8, 16, 6, 1>(J, sm_count, s);
+    case FAST3R_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E8>"; return launch_fast3<double, 8, 8, 8, 8, 8, 6, 0>(J, sm_count, s);
+    case FAST3R_1024_F64: g_last_kernel = "fast3_kernel<double,16,8,8,E16>"; return launch_fast3<double, 16, 8, 8, 16, 8, 6, 1>(J, sm_count, s);
+    case FAST3R_256_F32: g_last_kernel = "fast3_kernel<float,8,8,4,E8>"; return launch_fast3<float, 8, 8, 4, 8, 16, 6, 1>(J, sm_count, s);
+    case FAST3R_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E8>"; return launch_fast3<float, 8, 8, 8, 8, 12, 6, 0>(J, sm_count, s);
+    case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, 6, 1>(J, sm_count, s);
+    case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1>(J, sm_count, s);
+    case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2, 7, 0>(J, sm_count, s);
+    case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1, 7, 0>(J, sm_count, s);
     case FASTBLUE_2048_F64: g_last_kernel = "fastblue_kernel<double,16,16,8,E16>"; return launch_fastblue<double, 16, 16, 8, 16>(J, sm_count, s);
     case FASTBLUE_4096_F64: g_last_kernel = "fastblue_kernel<double,16,16,16,E16>"; return launch_fastblue<double, 16, 16, 16, 16>(J, sm_count, s);
     case FASTBLUE_8192_F64: g_last_kernel = "fastblue_kernel<double,16,16,32,E32>"; return launch_fastblue<double, 16, 16, 32, 32>(J, sm_count, s);
@@ -1270,14 +1293,18 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case COL2_64_F32: g_last_kernel = "colfast2_kernel<float,8,8,16>"; return launch_colfast2<float, 8, 8, 16>(J, s);
     case COL2_128_F32: g_last_kernel = "colfast2_kernel<float,16,8,16>"; return launch_colfast2<float, 16, 8, 16>(J, s);
     case COL2_256_F32: g_last_kernel = "colfast2_kernel<float,16,16,16>"; return launch_colfast2<float, 16, 16, 16>(J, s);
-    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8>(J, sm_count, s);
-    case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4>(J, sm_count, s);
-    case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5>(J, sm_count, s);
-    case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10,pair>"; return launch_fast3<double, 10, 10, 5, 10, 8, true, 2>(J, sm_count, s);
-    case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18,pair>"; return launch_fast3<double, 18, 18, 6, 18, 4, true, 2>(J, sm_count, s);
-    case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2>(J, sm_count, s);
-    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, false, 1>(J, sm_count, s);
-    case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3>(J, sm_count, s);
+    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8, 7, 4>(J, sm_count, s);
+    case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4, 7, 4>(J, sm_count, s);
+    case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5, 7, 0>(J, sm_count, s);
+    case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10>"; return launch_fast3<double, 10, 10, 5, 10, 8, 2, 2>(J, sm_count, s);
+    case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18>"; return launch_fast3<double, 18, 18, 6, 18, 4, 2, 2>(J, sm_count, s);
+    case FAST3C_2048_F64: g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8>(J, sm_count, s);
+    case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s);
+    case FAST3C_1024_F64: g_last_kernel = "fast3_kernel<double,8,8,16,E16>"; return launch_fast3<double, 8, 8, 16, 16, 8, 4, 8>(J, sm_count, s);
+    case FAST3C_1024_F32: g_last_kernel = "fast3_kernel<float,8,8,16,E16>"; return launch_fast3<float, 8, 8, 16, 16, 12, 4, 8>(J, sm_count, s);
+    case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2, 7, 0>(J, sm_count, s);
+    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, 7, 1>(J, sm_count, s);
+    case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3, 7, 0>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;
   }
 }

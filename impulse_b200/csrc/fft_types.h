@@ -144,6 +144,10 @@ enum FastId : uint32_t {
   FAST2R_128_F32 = 56,
   FAST3R_500_F64 = 57,   // r2c-only shapes whose pass 3 pairs bin k with bin N-k in registers (10*10*5, 18*18*6)
   FAST3R_1944_F64 = 58,
+  FAST3C_2048_F64 = 59,  // c2r-only shapes whose pass 1 pairs point n with point N-n in registers (8*16*16, 8*8*16)
+  FAST3C_2048_F32 = 60,
+  FAST3C_1024_F64 = 61,
+  FAST3C_1024_F32 = 62,
 };
 
 struct Phase {

@@ -626,7 +626,11 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     const bool c2r = s.kind == KIND_C2R && even && s.layout == RL_HERMITIAN && (J->bdim[0] == 1 || s.bs_out[0] % 2 == 0);
     if (c2c || r2c || c2r) {
       uint32_t id = FAST_NONE, r1 = 0, r2 = 0, r3 = 0;
-      if (L == 2048) { id = f64 ? FAST3_2048_F64 : FAST3_2048_F32; r1 = 16; r2 = 16; r3 = 8; }
+      // c2r of 4096 / 2048 points: shapes with a SHORT first radix, whose pass 1 pairs point n with point N-n in
+      // registers (fast3_kernel, PAIR); IMPULSE_FFT_C2R_PAIR=0 restores the shapes shared with c2c / r2c
+      if (L == 2048 && c2r && env_int("IMPULSE_FFT_C2R_PAIR", 1)) { id = f64 ? FAST3C_2048_F64 : FAST3C_2048_F32; r1 = 8; r2 = 16; r3 = 16; }
+      else if (L == 1024 && c2r && env_int("IMPULSE_FFT_C2R_PAIR", 1)) { id = f64 ? FAST3C_1024_F64 : FAST3C_1024_F32; r1 = 8; r2 = 8; r3 = 16; }
+      else if (L == 2048) { id = f64 ? FAST3_2048_F64 : FAST3_2048_F32; r1 = 16; r2 = 16; r3 = 8; }
       else if (L == 4096) { id = f64 ? FAST3_4096_F64 : FAST3_4096_F32; r1 = 16; r2 = 16; r3 = 16; }
       else if (L == 8192) { id = f64 ? FAST3_8192_F64 : FAST3_8192_F32; r1 = 16; r2 = 16; r3 = 32; }
       // r2c of 1000 / 3888 points: shapes with a SHORT last radix, whose pass 3 pairs bin k with bin N-k in

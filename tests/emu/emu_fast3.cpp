@@ -85,6 +85,9 @@ int dispatch(int kind, int bwd, int pair, const void *in, void *out, uint64_t nr
     }
     bwd ? GO(F3_R2C, true, false) : GO(F3_R2C, false, false);
   } else if (kind == F3_C2R) {
+    if constexpr ((R2 * R3) % 2 == 0) {
+      if (pair) { bwd ? GO(F3_C2R, true, true) : GO(F3_C2R, false, true); return 0; }
+    }
     bwd ? GO(F3_C2R, true, false) : GO(F3_C2R, false, false);
   } else {
     bwd ? GO(F3_C2C, true, false) : GO(F3_C2C, false, false);
@@ -112,6 +115,10 @@ int emu_fast3(int shape, int dtype, int kind, int bwd, int pair, const void *in,
   SHAPE(5, 10, 10, 10)
   SHAPE(6, 18, 18, 18)
   SHAPE(16, 16, 16, 16)
+  SHAPE(8, 16, 16, 16)
+  SHAPE(8, 8, 16, 16)
+  SHAPE(8, 8, 8, 16)
+  SHAPE(4, 8, 8, 8)
 #undef SHAPE
   return -1;
 }

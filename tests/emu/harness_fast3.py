@@ -47,17 +47,27 @@ def run(shape, kind, x, forward=True, fct=1.0, pair=False, ctas=2):
     rows = x.shape[0]
     if kind == "c2c":
         assert x.shape[1] == n
-        out = np.full((rows, n), np.nan, cdt)
+        oshape, odt = (rows, n), cdt
     elif kind == "r2c":
         assert x.shape[1] == 2 * n
-        out = np.full((rows, n + 1), np.nan, cdt)
+        oshape, odt = (rows, n + 1), cdt
     else:
         assert x.shape[1] == n + 1
-        out = np.full((rows, 2 * n), np.nan, rdt)
+        oshape, odt = (rows, 2 * n), rdt
+    # guard zones around the output and the input: an out-of-bounds store / a stray load shows up as a changed canary
+    # / a NaN in the result
+    pad = 64
+    flat = np.full(oshape[0] * oshape[1] + 2 * pad, np.nan, odt)
+    out = flat[pad:-pad].reshape(oshape)
+    xin = np.full(x.size + 2 * pad, np.nan, x.dtype)
+    xin[pad:-pad] = x.ravel()
+    x = xin[pad:-pad].reshape(x.shape)
     # the kernel's BWD flag: c2c / r2c = backward transform; c2r = "conjugate the input" = forward=True (F_CONJ_IN)
     bwd = (1 if forward else 0) if kind == "c2r" else (0 if forward else 1)
     rc = lib().emu_fast3(r1 * 1000000 + r2 * 10000 + r3 * 100 + e, 1 if f64 else 0, KIND[kind], bwd,
                          1 if pair else 0, x.ctypes.data, out.ctypes.data, rows, x.shape[1], out.shape[1], fct, ctas)
     if rc:
         raise RuntimeError(f"emu_fast3 rc={rc}")
-    return out
+    if not (np.isnan(flat[:pad]).all() and np.isnan(flat[-pad:]).all()):
+        raise AssertionError("store outside the output rows")
+    return out.copy()

@@ -71,3 +71,37 @@ def test_pair_post_twiddle_f32(shape):
     got = f3.run(shape, "r2c", x, True, 1.0, pair=True)
     assert got.dtype == np.complex64 and not np.isnan(got.view(np.float32)).any()
     assert rel(got.astype(np.complex128), ref_r2c(x, True, 1.0)) < 1e-6 * np.log2(n)
+
+
+SHAPES_C2R_PAIR = [(5, 10, 10, 10), (6, 18, 18, 18), (8, 16, 16, 16), (8, 8, 16, 16), (8, 8, 8, 16), (4, 8, 8, 8)]
+
+
+@pytest.mark.parametrize("shape", SHAPES_C2R_PAIR)
+@pytest.mark.parametrize("forward", [False, True])
+def test_pair_pre_twiddle_f64(shape, forward):
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(11 * n + forward)
+    X = rng.random((5, n + 1)) - 0.5 + 1j * (rng.random((5, n + 1)) - 0.5)   # bins 0 and N carry junk imaginary parts
+    got = f3.run(shape, "c2r", X, forward, 0.5 / n, pair=True, ctas=2)
+    assert not np.isnan(got).any()
+    Xc = X.copy()
+    Xc[:, 0] = Xc[:, 0].real
+    Xc[:, n] = Xc[:, n].real
+    want = ref_c2r(Xc, 2 * n, forward, 0.5 / n)
+    for r in range(X.shape[0]):
+        assert rel(got[r], want[r]) < 2e-15 * np.log2(n) * 4
+    old = f3.run(shape, "c2r", X, forward, 0.5 / n, pair=False, ctas=1)
+    assert rel(got, old) < 1e-15
+
+
+@pytest.mark.parametrize("shape", [(8, 16, 16, 16), (8, 8, 16, 16), (4, 8, 8, 8)])
+def test_pair_pre_twiddle_f32(shape):
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(n + 2)
+    x = rng.random((3, 2 * n)) - 0.5
+    X = np.fft.rfft(x, axis=1).astype(np.complex64)
+    got = f3.run(shape, "c2r", X, False, 0.5 / n, pair=True)
+    assert got.dtype == np.float32 and not np.isnan(got).any()
+    assert rel(got.astype(np.float64), x) < 1e-6 * np.log2(n)

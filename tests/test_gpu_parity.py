@@ -437,8 +437,18 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
                     back = apply_nd(ib, "c2r", sd, torch_mod.empty_like(rd), [1], fwd, 1.0 / n).cpu().numpy()
                     used.add(ib.last_kernel())
                     assert oracle.max_row_rel_l2(back, checker.c2r(sp, r.shape, [1], fwd, 1.0 / n)) <= tol(n, dt), (n, rows, fwd, dt)
+                # pocketfft's c2r never reads the imaginary parts of bins 0 and N/2 (pocketfft_hdronly.h:3196-3210)
+                sj = sp.copy()
+                sj[:, 0] += 0.375j
+                sj[:, -1] -= 0.25j
+                back = apply_nd(ib, "c2r", torch_mod.from_numpy(sj).cuda(), torch_mod.empty_like(rd), [1], False, 1.0 / n).cpu().numpy()
+                assert oracle.max_row_rel_l2(back, checker.c2r(sp, r.shape, [1], False, 1.0 / n)) <= tol(n, dt), (n, rows, "junk imag", dt)
     print(sorted(used))
     assert any(k.startswith("fast3_kernel") for k in used) and any(k.startswith("fast2") for k in used)
+    # the in-register pair variants (r2c post-twiddle in pass 3, c2r pre-twiddle in pass 1) are the default
+    if os.environ.get("IMPULSE_FFT_R2C_PAIR", "1") != "0" and os.environ.get("IMPULSE_FFT_C2R_PAIR", "1") != "0":
+        pair = sorted(k for k in used if k.endswith("+pair"))
+        assert any("10,10,5" in k for k in pair) and any("18,18,6" in k for k in pair) and any("8,16,16" in k for k in pair), pair
 
 
 def test_column_kernels(ib, torch_mod, checker):

@@ -13,7 +13,10 @@ if kind == "c2c":
 else:
     x = torch.rand((rows, n), device="cuda", dtype=rdt) - 0.5
     y = torch.empty((rows, n // 2 + 1), device="cuda", dtype=cdt)
-f = ib.FFTDesc.init(axes=[1], forward=True)
+f = ib.FFTDesc.init(axes=[1], forward=kind != "c2r")
+if kind == "c2r":   # spectrum of x in, real rows out
+    ib.FFTDesc.init(axes=[1], forward=True).apply(ib.DataDesc.init(y), ib.DataDesc.init(x))
+    x, y = y, x
 for _ in range(3):
     f.apply(ib.DataDesc.init(y), ib.DataDesc.init(x))
 torch.cuda.synchronize()

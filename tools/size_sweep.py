@@ -1,5 +1,6 @@
 """Throughput of batched 1-D transforms over a range of lengths (device resident, out of place):
-which kernel serves each length and how far it is from the copy roofline.  Usage: python tools/size_sweep.py"""
+which kernel serves each length and how far it is from the copy roofline.
+Usage: python tools/size_sweep.py [--kinds c2c,r2c,c2r] [--dtypes f64,f32] [--lengths 512,1000,...]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -22,8 +23,11 @@ def run(kind, dt, n):
         x = torch.rand((rows, n), device="cuda", dtype=rdt) - 0.5
         y = torch.empty((rows, n // 2 + 1), device="cuda", dtype=cdt)
         nbytes = x.numel() * x.element_size() + y.numel() * y.element_size()
-    f = ib.FFTDesc.init(axes=[1], forward=True)
+    f = ib.FFTDesc.init(axes=[1], forward=kind != "c2r")
     din, dout = ib.DataDesc.init(x), ib.DataDesc.init(y)
+    if kind == "c2r":   # half spectrum in, real rows out (the spectrum of x, so the values are representative)
+        ib.FFTDesc.init(axes=[1], forward=True).apply(dout, din)
+        din, dout = dout, din
     for _ in range(3):
         f.apply(dout, din)
     torch.cuda.synchronize()
@@ -40,8 +44,15 @@ def run(kind, dt, n):
 
 
 if __name__ == "__main__":
-    for kind, dt in (("c2c", "f64"), ("c2c", "f32"), ("r2c", "f64"), ("r2c", "f32")):
-        for n in LENGTHS:
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kinds", default="c2c,r2c")
+    ap.add_argument("--dtypes", default="f64,f32")
+    ap.add_argument("--lengths", default="")
+    a = ap.parse_args()
+    lengths = [int(v) for v in a.lengths.split(",")] if a.lengths else LENGTHS
+    for kind, dt in [(k, d) for k in a.kinds.split(",") for d in a.dtypes.split(",")]:
+        for n in lengths:
             try:
                 gbs, ms, nl, k = run(kind, dt, n)
                 print(f"{kind} {dt} n={n:8d} {gbs:8.0f} GB/s {ms:8.3f} ms launches={nl} {k}", flush=True)
