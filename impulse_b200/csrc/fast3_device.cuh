@@ -106,7 +106,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t byte
 #endif
 }
 
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB, bool PAIR = false>
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB, bool PAIR = false, bool PF = false>
 __global__ void __launch_bounds__((R1 * R2 * R3) / E, MINB)
 fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
              const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, const cx<T> *__restrict__ twr, T fct,
@@ -135,6 +135,37 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
   constexpr uint32_t ROW_BYTES_IN = (KIND == F3_C2R ? (N + 1) : N) * sizeof(cx<T>);
   const int k1 = t % R1, i2b = t / R1;  // pass-2 ownership (T % R1 == 0)
   const cx<T> wt = KIND == F3_C2C ? mk<T>((T)1, (T)0) : __ldg(twr + t);   // real kinds: W_2N^t, this thread's twiddle factor
+  // PF: the NEXT claimed row is requested into registers right after the second exchange, when the row in flight
+  // no longer needs them, so that its global-load latency hides behind pass 3 and the stores.
+  static_assert(!PF || KIND == F3_C2C || PAIR, "register prefetch needs the direct-load variants");
+  constexpr bool C2R_PAIR = KIND == F3_C2R && PAIR;
+  constexpr int UNITS1 = M1 / 2, NU1 = C2R_PAIR ? (UNITS1 + TT - 1) / TT : 1, RP = C2R_PAIR ? R1 : 1;
+  cx<T> x[E];
+  cx<T> pA[NU1][RP], pB[NU1][RP];   // c2r pair units: X[u + M1*j] and X[M1 - u + M1*j]
+  T pN = (T)0;                      //                 Re X[N] (unit 0)
+  auto load_row = [&](const uint64_t r) {
+    if constexpr (C2R_PAIR) {
+      const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)r * rs_in;
+#pragma unroll
+      for (int mu = 0; mu < NU1; ++mu) {
+        const int u = t + TT * mu;
+        if (UNITS1 % TT != 0 && u >= UNITS1) continue;
+        const int ka = u, kb = u == 0 ? M1 / 2 : M1 - u;
+#pragma unroll
+        for (int j = 0; j < R1; ++j) { pA[mu][j] = src[ka + M1 * j]; pB[mu][j] = src[kb + M1 * j]; }
+        if (u == 0) pN = src[N].x;
+      }
+    } else if constexpr (KIND != F3_C2R) {
+      const cx<T> *src = KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)r * rs_in)
+                                        : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)r * rs_in;
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        x[q] = src[t + TT * q];
+        if (KIND == F3_C2C && BWD) x[q].y = -x[q].y;
+      }
+    }
+  };
+  bool loaded = false;
   for (unsigned it = 0;; ++it) {
     const uint64_t row = s_row[it & 1];
     if (row >= nrows) break;
@@ -149,7 +180,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
         if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void *>(lo), (uint32_t)(hi - lo));
       }
     }
-    cx<T> x[E];
+    if (!(PF && loaded)) load_row(row);
     if constexpr (KIND == F3_C2R && PAIR) {
       // ---------------- load + c2r pre-twiddle in registers + pass 1 ----------------
       // Pass-1 butterfly i1 consumes z[i1 + M1*j]; the mirror of that point, N - n = (M1 - i1) + M1*(R1-1-j),
@@ -159,8 +190,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
       // with W_2N^n = W_2N^u * W_(2 R1)^j (per-thread factor x compile-time root): no staging buffer, no barrier.
       // Unit 0 = butterflies 0 and M1/2, which mirror into themselves.  (backward = conj(FFT(conj z)).)
       static_assert(M1 % 2 == 0, "pair units need an even N/R1");
-      constexpr int UNITS = M1 / 2, NU = (UNITS + TT - 1) / TT;
-      const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
+      constexpr int UNITS = UNITS1, NU = NU1;
       auto pass1 = [&](cx<T> (&y)[R1], const int i1) {
         RegFFT<T, R1>::run(y);
 #pragma unroll
@@ -175,7 +205,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
         const int ka = u, kb = u == 0 ? M1 / 2 : M1 - u;
         cx<T> A[R1], B[R1], xa[R1], xb[R1];
 #pragma unroll
-        for (int j = 0; j < R1; ++j) { A[j] = src[ka + M1 * j]; B[j] = src[kb + M1 * j]; }
+        for (int j = 0; j < R1; ++j) { A[j] = pA[mu][j]; B[j] = pB[mu][j]; }
         if (BWD) {                                  // c2r with forward=true conjugates its input
 #pragma unroll
           for (int j = 0; j < R1; ++j) { A[j].y = -A[j].y; B[j].y = -B[j].y; }
@@ -193,7 +223,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
           }
         } else {
           {                                         // n = 0 pairs with bin N; their imaginary parts are ignored
-            const T a0 = A[0].x, bn = src[N].x;
+            const T a0 = A[0].x, bn = pN;
             xa[0] = mk<T>(a0 + bn, -(a0 - bn));
           }
 #pragma unroll
@@ -237,14 +267,6 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
           x[q] = cconj(z);                           // backward = conj(FFT(conj z))
         }
         __syncthreads();
-      } else {
-        const cx<T> *src = KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)row * rs_in)
-                                          : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
-#pragma unroll
-        for (int q = 0; q < E; ++q) {
-          x[q] = src[t + TT * q];
-          if (KIND == F3_C2C && BWD) x[q].y = -x[q].y;
-        }
       }
       // ---------------- pass 1 ----------------
 #pragma unroll
@@ -294,6 +316,11 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
       for (int k = 0; k < R2; ++k) buf[i2 * P2 + k1 + R1 * k] = x[m * R2 + k];
     }
     __syncthreads();
+    if constexpr (PF) {   // x[] (pA/pB) are free from here on: request the next claimed row
+      const uint64_t nxt = s_row[(it + 1) & 1];
+      loaded = nxt < nrows;
+      if (loaded) load_row(nxt);
+    }
     if constexpr (KIND == F3_R2C && PAIR) {
       // ---------------- pass 3 with the Hermitian post-twiddle in registers ----------------
       // Butterfly klow leaves Z[klow + P2*k3] in y[k3]; the mirror of that bin, N - k = (P2 - klow) + P2*(R3-1-k3),
@@ -355,41 +382,34 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
       }
       __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
     } else {
-      // ---------------- pass 3 ----------------
+      // ---------------- pass 3 (+ store for c2c / c2r: straight from the butterfly's registers) ----------------
+      if constexpr (KIND != F3_R2C) {
+        // c2c: X[klow + R1*R2*k];  c2r: (x[2n], x[2n+1]) with the conjugation of the backward trick undone
+        cx<T> *dst = KIND == F3_C2C ? reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out
+                                    : reinterpret_cast<cx<T> *>(reinterpret_cast<T *>(out_v) + (int64_t)row * rs_out);
+        const T fy = (KIND == F3_C2R || BWD) ? -fct : fct;
 #pragma unroll
-      for (int m = 0; m < NB3; ++m) {
-        const int klow = t + TT * m;
-        cx<T> y[R3];
+        for (int m = 0; m < NB3; ++m) {
+          const int klow = t + TT * m;
+          cx<T> y[R3];
 #pragma unroll
-        for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
-        RegFFT<T, R3>::run(y);
+          for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
+          RegFFT<T, R3>::run(y);
 #pragma unroll
-        for (int k = 0; k < R3; ++k) x[m * R3 + k] = y[k];   // X[klow + R1*R2*k]
-      }
-      // ---------------- store ----------------
-      if (KIND == F3_C2C) {
-        cx<T> *dst = reinterpret_cast<cx<T> *>(out_v) + (int64_t)row * rs_out;
-#pragma unroll
-        for (int m = 0; m < NB3; ++m)
-#pragma unroll
-          for (int k = 0; k < R3; ++k) {
-            cx<T> v = x[m * R3 + k];
-            v.x *= fct; v.y *= BWD ? -fct : fct;
-            dst[t + TT * m + R1 * R2 * k] = v;
-          }
+          for (int k = 0; k < R3; ++k) dst[klow + R1 * R2 * k] = mk<T>(y[k].x * fct, y[k].y * fy);
+        }
         __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
-      } else if (KIND == F3_C2R) {
-        cx<T> *dst = reinterpret_cast<cx<T> *>(reinterpret_cast<T *>(out_v) + (int64_t)row * rs_out);
-#pragma unroll
-        for (int m = 0; m < NB3; ++m)
-#pragma unroll
-          for (int k = 0; k < R3; ++k) {
-            cx<T> v = x[m * R3 + k];
-            v.x *= fct; v.y *= -fct;                 // undo the conjugation of the backward trick
-            dst[t + TT * m + R1 * R2 * k] = v;       // (x[2n], x[2n+1])
-          }
-        __syncthreads();
       } else {  // r2c: Hermitian post-twiddle needs Z[k] and Z[N-k]
+#pragma unroll
+        for (int m = 0; m < NB3; ++m) {
+          const int klow = t + TT * m;
+          cx<T> y[R3];
+#pragma unroll
+          for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
+          RegFFT<T, R3>::run(y);
+#pragma unroll
+          for (int k = 0; k < R3; ++k) x[m * R3 + k] = y[k];   // Z[klow + R1*R2*k]
+        }
         __syncthreads();
 #pragma unroll
         for (int m = 0; m < NB3; ++m)

@@ -148,6 +148,11 @@ enum FastId : uint32_t {
   FAST3C_2048_F32 = 60,
   FAST3C_1024_F64 = 61,
   FAST3C_1024_F32 = 62,
+  FAST3_500_F32 = 63,    // float32 instances of the 500 / 1000 / 1944-point shapes
+  FAST3_1944_F32 = 64,
+  FAST3_1000_F32 = 65,
+  FAST3R_500_F32 = 66,
+  FAST3R_1944_F32 = 67,
 };
 
 struct Phase {

@@ -635,11 +635,11 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       else if (L == 8192) { id = f64 ? FAST3_8192_F64 : FAST3_8192_F32; r1 = 16; r2 = 16; r3 = 32; }
       // r2c of 1000 / 3888 points: shapes with a SHORT last radix, whose pass 3 pairs bin k with bin N-k in
       // registers (fast3_kernel, PAIR); IMPULSE_FFT_R2C_PAIR=0 restores the shapes shared with c2c / c2r
-      else if (L == 500 && f64 && r2c && env_int("IMPULSE_FFT_R2C_PAIR", 1)) { id = FAST3R_500_F64; r1 = 10; r2 = 10; r3 = 5; }
-      else if (L == 1944 && f64 && r2c && env_int("IMPULSE_FFT_R2C_PAIR", 1)) { id = FAST3R_1944_F64; r1 = 18; r2 = 18; r3 = 6; }
-      else if (L == 500 && f64) { id = FAST3_500_F64; r1 = 5; r2 = 10; r3 = 10; }
-      else if (L == 1944 && f64) { id = FAST3_1944_F64; r1 = 6; r2 = 18; r3 = 18; }
-      else if (L == 1000 && f64) { id = FAST3_1000_F64; r1 = 10; r2 = 10; r3 = 10; }
+      else if (L == 500 && r2c && env_int("IMPULSE_FFT_R2C_PAIR", 1)) { id = f64 ? FAST3R_500_F64 : FAST3R_500_F32; r1 = 10; r2 = 10; r3 = 5; }
+      else if (L == 1944 && r2c && env_int("IMPULSE_FFT_R2C_PAIR", 1)) { id = f64 ? FAST3R_1944_F64 : FAST3R_1944_F32; r1 = 18; r2 = 18; r3 = 6; }
+      else if (L == 500) { id = f64 ? FAST3_500_F64 : FAST3_500_F32; r1 = 5; r2 = 10; r3 = 10; }
+      else if (L == 1944) { id = f64 ? FAST3_1944_F64 : FAST3_1944_F32; r1 = 6; r2 = 18; r3 = 18; }
+      else if (L == 1000) { id = f64 ? FAST3_1000_F64 : FAST3_1000_F32; r1 = 10; r2 = 10; r3 = 10; }
       else if (!c2c && (L == 16 || L == 32 || L == 64 || L == 128) && J->tw_r) {
         // short real rows: two-pass warp kernel (fast2r_kernel), tables = the engine's own W_L^m and W_N^k
         J->fast_id = (L == 16 ? FAST2R_16_F64 : L == 32 ? FAST2R_32_F64 : L == 64 ? FAST2R_64_F64 : FAST2R_128_F64) + (f64 ? 0 : 4);

@@ -49,7 +49,7 @@ template <typename T> std::vector<cx<T>> conv(const std::vector<cld> &v) {
   return r;
 }
 
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool PAIR>
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool PAIR, bool PF = false>
 void run(const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1;
   std::vector<cld> a((size_t)R1 * M1), b((size_t)R2 * R3), r((size_t)N + 1);
@@ -69,7 +69,7 @@ void run(const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_ou
     for (int t = 0; t < TT; ++t)
       th.emplace_back([&, t] {
         threadIdx.x = (unsigned)t;
-        fast3_kernel<T, R1, R2, R3, E, KIND, BWD, 1, PAIR>(in, out, nrows, rs_in, rs_out, tw1.data(), tw2.data(), twr.data(), (T)fct, sched);
+        fast3_kernel<T, R1, R2, R3, E, KIND, BWD, 1, PAIR, PF>(in, out, nrows, rs_in, rs_out, tw1.data(), tw2.data(), twr.data(), (T)fct, sched);
       });
     for (auto &x : th) x.join();
   }
@@ -77,21 +77,28 @@ void run(const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_ou
 }
 
 template <typename T, int R1, int R2, int R3, int E>
-int dispatch(int kind, int bwd, int pair, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
-#define GO(K, B, P) run<T, R1, R2, R3, E, K, B, P>(in, out, nrows, rs_in, rs_out, fct, ctas)
+int dispatch(int kind, int bwd, int flags, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
+  const bool pair = (flags & 1) != 0, pf = (flags & 2) != 0;   // flags: 1 = pair units, 2 = register prefetch of the next row
+#define GO(K, B, P, F) run<T, R1, R2, R3, E, K, B, P, F>(in, out, nrows, rs_in, rs_out, fct, ctas)
+#define GO2(K, P, F) (bwd ? GO(K, true, P, F) : GO(K, false, P, F))
   if (kind == F3_R2C) {
-    if constexpr ((R1 * R2) % 2 == 0) {
-      if (pair) { bwd ? GO(F3_R2C, true, true) : GO(F3_R2C, false, true); return 0; }
+    if (pair) {
+      if constexpr ((R1 * R2) % 2 == 0) { if (pf) GO2(F3_R2C, true, true); else GO2(F3_R2C, true, false); return 0; }
+      return -2;
     }
-    bwd ? GO(F3_R2C, true, false) : GO(F3_R2C, false, false);
+    if (pf) return -2;
+    GO2(F3_R2C, false, false);
   } else if (kind == F3_C2R) {
-    if constexpr ((R2 * R3) % 2 == 0) {
-      if (pair) { bwd ? GO(F3_C2R, true, true) : GO(F3_C2R, false, true); return 0; }
+    if (pair) {
+      if constexpr ((R2 * R3) % 2 == 0) { if (pf) GO2(F3_C2R, true, true); else GO2(F3_C2R, true, false); return 0; }
+      return -2;
     }
-    bwd ? GO(F3_C2R, true, false) : GO(F3_C2R, false, false);
+    if (pf) return -2;
+    GO2(F3_C2R, false, false);
   } else {
-    bwd ? GO(F3_C2C, true, false) : GO(F3_C2C, false, false);
+    if (pf) GO2(F3_C2C, false, true); else GO2(F3_C2C, false, false);
   }
+#undef GO2
 #undef GO
   return 0;
 }
@@ -100,12 +107,12 @@ int dispatch(int kind, int bwd, int pair, const void *in, void *out, uint64_t nr
 extern "C" {
 // shape = R1*1000000 + R2*10000 + R3*100 + E; dtype 1 = f64, 0 = f32; kind 0 c2c / 1 r2c / 2 c2r; row strides in
 // elements of the row's own type (reals for the real side), as LineJob::bs_in/bs_out
-int emu_fast3(int shape, int dtype, int kind, int bwd, int pair, const void *in, void *out, uint64_t nrows, int64_t rs_in,
+int emu_fast3(int shape, int dtype, int kind, int bwd, int flags, const void *in, void *out, uint64_t nrows, int64_t rs_in,
               int64_t rs_out, double fct, unsigned ctas) {
 #define SHAPE(A, B, C, D)                                                                                                   \
   if (shape == A * 1000000 + B * 10000 + C * 100 + D)                                                                       \
-    return dtype ? dispatch<double, A, B, C, D>(kind, bwd, pair, in, out, nrows, rs_in, rs_out, fct, ctas)                  \
-                 : dispatch<float, A, B, C, D>(kind, bwd, pair, in, out, nrows, rs_in, rs_out, fct, ctas);
+    return dtype ? dispatch<double, A, B, C, D>(kind, bwd, flags, in, out, nrows, rs_in, rs_out, fct, ctas)                  \
+                 : dispatch<float, A, B, C, D>(kind, bwd, flags, in, out, nrows, rs_in, rs_out, fct, ctas);
   SHAPE(16, 16, 8, 16)
   SHAPE(16, 8, 8, 16)
   SHAPE(8, 8, 4, 8)
@@ -119,6 +126,7 @@ int emu_fast3(int shape, int dtype, int kind, int bwd, int pair, const void *in,
   SHAPE(8, 8, 16, 16)
   SHAPE(8, 8, 8, 16)
   SHAPE(4, 8, 8, 8)
+  SHAPE(10, 10, 10, 10)
 #undef SHAPE
   return -1;
 }

@@ -9,7 +9,7 @@ import pytest
 from tests.emu import harness_fast3 as f3
 
 SHAPES_PAIR = [(16, 16, 8, 16), (16, 8, 8, 16), (8, 8, 4, 8), (10, 10, 5, 10), (18, 18, 6, 18)]
-SHAPES_OLD = [(8, 8, 8, 8), (5, 10, 10, 10), (6, 18, 18, 18), (16, 16, 16, 16)]
+SHAPES_OLD = [(8, 8, 8, 8), (5, 10, 10, 10), (6, 18, 18, 18), (16, 16, 16, 16), (10, 10, 10, 10)]
 
 
 def rel(a, b):
@@ -105,3 +105,47 @@ def test_pair_pre_twiddle_f32(shape):
     got = f3.run(shape, "c2r", X, False, 0.5 / n, pair=True)
     assert got.dtype == np.float32 and not np.isnan(got).any()
     assert rel(got.astype(np.float64), x) < 1e-6 * np.log2(n)
+
+
+@pytest.mark.parametrize("shape,kind", [((16, 16, 8, 16), "r2c"), ((18, 18, 6, 18), "r2c"), ((10, 10, 5, 10), "r2c"),
+                                        ((8, 16, 16, 16), "c2r"), ((6, 18, 18, 18), "c2r"), ((5, 10, 10, 10), "c2r"),
+                                        ((16, 16, 16, 16), "c2c"), ((16, 16, 8, 16), "c2c"), ((10, 10, 10, 10), "c2c")])
+@pytest.mark.parametrize("forward", [True, False])
+def test_register_prefetch_of_next_row(shape, kind, forward):
+    """PF variant: the next claimed row is loaded into registers during pass 3.  7 rows over 2 CTAs, so that every
+    CTA runs several rows back to back (first row loaded at the top, later rows prefetched, last one without a successor)."""
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(3 * n + forward)
+    if kind == "r2c":
+        x = rng.random((7, 2 * n)) - 0.5
+        want = ref_r2c(x, forward, 1.25)
+    elif kind == "c2r":
+        x = rng.random((7, n + 1)) - 0.5 + 1j * (rng.random((7, n + 1)) - 0.5)
+        xc = x.copy()
+        xc[:, 0] = xc[:, 0].real
+        xc[:, n] = xc[:, n].real
+        want = ref_c2r(xc, 2 * n, forward, 1.25)
+    else:
+        x = rng.random((7, n)) - 0.5 + 1j * (rng.random((7, n)) - 0.5)
+        want = (np.fft.fft(x, axis=1) if forward else np.fft.ifft(x, axis=1) * n) * 1.25
+    got = f3.run(shape, kind, x, forward, 1.25, pair=kind != "c2c", ctas=2, prefetch=True)
+    for r in range(7):
+        assert rel(got[r], want[r]) < 2e-15 * np.log2(n) * 4, r
+
+
+@pytest.mark.parametrize("shape", [(5, 10, 10, 10), (10, 10, 5, 10), (18, 18, 6, 18), (6, 18, 18, 18), (10, 10, 10, 10)])
+def test_non_power_of_two_shapes_f32(shape):
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(n + 5)
+    x = (rng.random((3, 2 * n)) - 0.5).astype(np.float32)
+    pr = (r1 * r2) % 2 == 0 and e // r3 >= 2
+    got = f3.run(shape, "r2c", x, True, 1.0, pair=pr)
+    assert rel(got.astype(np.complex128), ref_r2c(x, True, 1.0)) < 1e-6 * np.log2(n)
+    X = np.fft.rfft(x.astype(np.float64), axis=1).astype(np.complex64)
+    pc = (r2 * r3) % 2 == 0 and e // r1 >= 2
+    back = f3.run(shape, "c2r", X, False, 0.5 / n, pair=pc)
+    assert rel(back.astype(np.float64), x.astype(np.float64)) < 1e-6 * np.log2(n)
+    z = (rng.random((2, n)) - 0.5 + 1j * (rng.random((2, n)) - 0.5)).astype(np.complex64)
+    assert rel(f3.run(shape, "c2c", z, True, 1.0).astype(np.complex128), np.fft.fft(z.astype(np.complex128), axis=1)) < 1e-6 * np.log2(n)
