@@ -137,25 +137,12 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
   const cx<T> wt = KIND == F3_C2C ? mk<T>((T)1, (T)0) : __ldg(twr + t);   // real kinds: W_2N^t, this thread's twiddle factor
   // PF: the NEXT claimed row is requested into registers right after the second exchange, when the row in flight
   // no longer needs them, so that its global-load latency hides behind pass 3 and the stores.
-  static_assert(!PF || KIND == F3_C2C || PAIR, "register prefetch needs the direct-load variants");
-  constexpr bool C2R_PAIR = KIND == F3_C2R && PAIR;
-  constexpr int UNITS1 = M1 / 2, NU1 = C2R_PAIR ? (UNITS1 + TT - 1) / TT : 1, RP = C2R_PAIR ? R1 : 1;
+  // (c2c and paired r2c only: for the paired c2r, whose loads sit inside the pass-1 units, hoisting them measured
+  // 2-13 % SLOWER on the B200 — more live registers, spills on the 18-point shapes.)
+  static_assert(!PF || KIND == F3_C2C || (KIND == F3_R2C && PAIR), "register prefetch needs the direct-load variants");
   cx<T> x[E];
-  cx<T> pA[NU1][RP], pB[NU1][RP];   // c2r pair units: X[u + M1*j] and X[M1 - u + M1*j]
-  T pN = (T)0;                      //                 Re X[N] (unit 0)
   auto load_row = [&](const uint64_t r) {
-    if constexpr (C2R_PAIR) {
-      const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)r * rs_in;
-#pragma unroll
-      for (int mu = 0; mu < NU1; ++mu) {
-        const int u = t + TT * mu;
-        if (UNITS1 % TT != 0 && u >= UNITS1) continue;
-        const int ka = u, kb = u == 0 ? M1 / 2 : M1 - u;
-#pragma unroll
-        for (int j = 0; j < R1; ++j) { pA[mu][j] = src[ka + M1 * j]; pB[mu][j] = src[kb + M1 * j]; }
-        if (u == 0) pN = src[N].x;
-      }
-    } else if constexpr (KIND != F3_C2R) {
+    if constexpr (KIND != F3_C2R) {
       const cx<T> *src = KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)r * rs_in)
                                         : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)r * rs_in;
 #pragma unroll
@@ -180,7 +167,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
         if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void *>(lo), (uint32_t)(hi - lo));
       }
     }
-    if (!(PF && loaded)) load_row(row);
+    if (!(PF && loaded)) load_row(row);   // (no-op for c2r, which loads below)
     if constexpr (KIND == F3_C2R && PAIR) {
       // ---------------- load + c2r pre-twiddle in registers + pass 1 ----------------
       // Pass-1 butterfly i1 consumes z[i1 + M1*j]; the mirror of that point, N - n = (M1 - i1) + M1*(R1-1-j),
@@ -190,7 +177,8 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
       // with W_2N^n = W_2N^u * W_(2 R1)^j (per-thread factor x compile-time root): no staging buffer, no barrier.
       // Unit 0 = butterflies 0 and M1/2, which mirror into themselves.  (backward = conj(FFT(conj z)).)
       static_assert(M1 % 2 == 0, "pair units need an even N/R1");
-      constexpr int UNITS = UNITS1, NU = NU1;
+      constexpr int UNITS = M1 / 2, NU = (UNITS + TT - 1) / TT;
+      const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
       auto pass1 = [&](cx<T> (&y)[R1], const int i1) {
         RegFFT<T, R1>::run(y);
 #pragma unroll
@@ -205,7 +193,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
         const int ka = u, kb = u == 0 ? M1 / 2 : M1 - u;
         cx<T> A[R1], B[R1], xa[R1], xb[R1];
 #pragma unroll
-        for (int j = 0; j < R1; ++j) { A[j] = pA[mu][j]; B[j] = pB[mu][j]; }
+        for (int j = 0; j < R1; ++j) { A[j] = src[ka + M1 * j]; B[j] = src[kb + M1 * j]; }
         if (BWD) {                                  // c2r with forward=true conjugates its input
 #pragma unroll
           for (int j = 0; j < R1; ++j) { A[j].y = -A[j].y; B[j].y = -B[j].y; }
@@ -223,7 +211,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
           }
         } else {
           {                                         // n = 0 pairs with bin N; their imaginary parts are ignored
-            const T a0 = A[0].x, bn = pN;
+            const T a0 = A[0].x, bn = src[N].x;
             xa[0] = mk<T>(a0 + bn, -(a0 - bn));
           }
 #pragma unroll

@@ -438,10 +438,13 @@ inline bool r2c_pair_enabled() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_R2C_PAIR"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
-// IMPULSE_FFT_F3_PF=1: request the next claimed row into registers during pass 3 (PF variants, selected shapes)
-inline bool f3_prefetch_enabled() {
-  static const int v = [] { const char *e = getenv("IMPULSE_FFT_F3_PF"); return e ? atoi(e) : 0; }();
-  return v != 0;
+// Register prefetch of the next claimed row during pass 3 (PF variants).  Measured on the B200: +7 % for c2c rows of
+// 2048 points (5.74 -> 6.14 TB/s), within +-2 % for the paired r2c shapes, slower wherever the extra live
+// registers spill (c2c 4096: 5.24 -> 4.71).  So it is on by default only where the launcher says so (PFDEF);
+// IMPULSE_FFT_F3_PF=0 / 1 forces it off / on for every instantiated variant (A/B runs).
+inline bool f3_prefetch_enabled(bool dflt) {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_F3_PF"); return e ? atoi(e) : -1; }();
+  return v < 0 ? dflt : v != 0;
 }
 inline bool c2r_pair_enabled() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_C2R_PAIR"); return e ? atoi(e) : 1; }();
@@ -452,7 +455,8 @@ inline bool c2r_pair_enabled() {
 // PAIRS: 1 = r2c post-twiddle in pass 3 (pair units) unless switched off, 2 = r2c always paired (the shape exists
 //        for that variant only); 4 / 8 = the same for the c2r pre-twiddle in pass 1.
 // PFK:   kinds for which the register-prefetch variant is instantiated (same bits as KINDS; real kinds: pair only)
-template <typename T, int R1, int R2, int R3, int E, int MINB, int KINDS = 7, int PAIRS = 0, int PFK = 0>
+// PFDEF: kinds for which it is the default
+template <typename T, int R1, int R2, int R3, int E, int MINB, int KINDS = 7, int PAIRS = 0, int PFK = 0, int PFDEF = 0>
 int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
@@ -466,7 +470,7 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   if (kind == F3_C2C) {
     if constexpr ((KINDS & 1) != 0) k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB>;
     if constexpr ((KINDS & 1) != 0 && (PFK & 1) != 0) {
-      if (f3_prefetch_enabled()) {
+      if (f3_prefetch_enabled((PFDEF & 1) != 0)) {
         pf = true;
         k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB, false, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB, false, true>;
       }
@@ -478,7 +482,7 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
           pair = true;
           k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB, true>;
           if constexpr ((PFK & 2) != 0) {
-            if (f3_prefetch_enabled()) {
+            if (f3_prefetch_enabled((PFDEF & 2) != 0)) {
               pf = true;
               k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB, true, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB, true, true>;
             }
@@ -495,12 +499,6 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
         if ((PAIRS & 8) != 0 || c2r_pair_enabled()) {
           pair = true;
           k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB, true>;
-          if constexpr ((PFK & 4) != 0) {
-            if (f3_prefetch_enabled()) {
-              pf = true;
-              k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB, true, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB, true, true>;
-            }
-          }
         }
       }
       if constexpr ((PAIRS & 8) == 0) {
@@ -1291,8 +1289,8 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3R_256_F32: g_last_kernel = "fast3_kernel<float,8,8,4,E8>"; return launch_fast3<float, 8, 8, 4, 8, 16, 6, 1>(J, sm_count, s);
     case FAST3R_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E8>"; return launch_fast3<float, 8, 8, 8, 8, 12, 6, 0>(J, sm_count, s);
     case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, 6, 1>(J, sm_count, s);
-    case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3>(J, sm_count, s);
-    case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2, 7, 0, 1>(J, sm_count, s);
+    case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3, 1>(J, sm_count, s);
+    case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2, 7, 0>(J, sm_count, s);
     case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1, 7, 0>(J, sm_count, s);
     case FASTBLUE_2048_F64: g_last_kernel = "fastblue_kernel<double,16,16,8,E16>"; return launch_fastblue<double, 16, 16, 8, 16>(J, sm_count, s);
     case FASTBLUE_4096_F64: g_last_kernel = "fastblue_kernel<double,16,16,16,E16>"; return launch_fastblue<double, 16, 16, 16, 16>(J, sm_count, s);
@@ -1317,13 +1315,13 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case COL2_64_F32: g_last_kernel = "colfast2_kernel<float,8,8,16>"; return launch_colfast2<float, 8, 8, 16>(J, s);
     case COL2_128_F32: g_last_kernel = "colfast2_kernel<float,16,8,16>"; return launch_colfast2<float, 16, 8, 16>(J, s);
     case COL2_256_F32: g_last_kernel = "colfast2_kernel<float,16,16,16>"; return launch_colfast2<float, 16, 16, 16>(J, s);
-    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8, 7, 4, 4>(J, sm_count, s);
-    case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4, 7, 4, 4>(J, sm_count, s);
+    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8, 7, 4>(J, sm_count, s);
+    case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4, 7, 4>(J, sm_count, s);
     case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5, 7, 0>(J, sm_count, s);
     case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10>"; return launch_fast3<double, 10, 10, 5, 10, 8, 2, 2, 2>(J, sm_count, s);
-    case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18>"; return launch_fast3<double, 18, 18, 6, 18, 4, 2, 2, 2>(J, sm_count, s);
-    case FAST3C_2048_F64: g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8, 4>(J, sm_count, s);
-    case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8, 4>(J, sm_count, s);
+    case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18>"; return launch_fast3<double, 18, 18, 6, 18, 4, 2, 2>(J, sm_count, s);
+    case FAST3C_2048_F64: g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8>(J, sm_count, s);
+    case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s);
     case FAST3C_1024_F64: g_last_kernel = "fast3_kernel<double,8,8,16,E16>"; return launch_fast3<double, 8, 8, 16, 16, 8, 4, 8>(J, sm_count, s);
     case FAST3C_1024_F32: g_last_kernel = "fast3_kernel<float,8,8,16,E16>"; return launch_fast3<float, 8, 8, 16, 16, 12, 4, 8>(J, sm_count, s);
     case FAST3_500_F32: g_last_kernel = "fast3_kernel<float,5,10,10,E10>"; return launch_fast3<float, 5, 10, 10, 10, 16, 7, 4>(J, sm_count, s);

@@ -90,7 +90,8 @@ int dispatch(int kind, int bwd, int flags, const void *in, void *out, uint64_t n
     GO2(F3_R2C, false, false);
   } else if (kind == F3_C2R) {
     if (pair) {
-      if constexpr ((R2 * R3) % 2 == 0) { if (pf) GO2(F3_C2R, true, true); else GO2(F3_C2R, true, false); return 0; }
+      if (pf) return -2;   // (no register prefetch for c2r)
+      if constexpr ((R2 * R3) % 2 == 0) { GO2(F3_C2R, true, false); return 0; }
       return -2;
     }
     if (pf) return -2;

@@ -108,7 +108,6 @@ def test_pair_pre_twiddle_f32(shape):
 
 
 @pytest.mark.parametrize("shape,kind", [((16, 16, 8, 16), "r2c"), ((18, 18, 6, 18), "r2c"), ((10, 10, 5, 10), "r2c"),
-                                        ((8, 16, 16, 16), "c2r"), ((6, 18, 18, 18), "c2r"), ((5, 10, 10, 10), "c2r"),
                                         ((16, 16, 16, 16), "c2c"), ((16, 16, 8, 16), "c2c"), ((10, 10, 10, 10), "c2c")])
 @pytest.mark.parametrize("forward", [True, False])
 def test_register_prefetch_of_next_row(shape, kind, forward):
