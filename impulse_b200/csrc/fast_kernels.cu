@@ -1030,7 +1030,9 @@ struct Fft3 {
 enum { BL_C2C = 0, BL_R2C_PAIR = 1, BL_C2R_PAIR = 2 };
 constexpr int kBlueMaxDef = 16;  // largest supported deficiency d
 
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD>
+// BKS: the chirp table b_k (L entries, used before the first and after the second transform of every unit) is
+// copied to shared memory once per CTA instead of being streamed from L2 twice per unit.
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool BKS = false>
 __global__ void __launch_bounds__((R1 * R2 * R3) / E, 1)
 fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
                 uint32_t L, uint32_t d, const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2,
@@ -1043,7 +1045,10 @@ fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_
   unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + F::BUFN);
   cx<T> *s_tw2 = reinterpret_cast<cx<T> *>(s_row + 4);
   cx<T> *s_tail = s_tw2 + R2 * R3;  // a[n], n >= L-d
+  cx<T> *s_bk = s_tail + kBlueMaxDef;
   const int t = threadIdx.x;
+  if (BKS) for (uint32_t idx = t; idx < L; idx += TT) s_bk[idx] = bk[idx];
+  const cx<T> *bkp = BKS ? s_bk : bk;
   const uint64_t nunits = KIND == BL_C2C ? nrows : (nrows + 1) / 2;
   if (t == 0) { s_row[0] = atomicAdd(&sched[0], 1u); s_row[1] = atomicAdd(&sched[0], 1u); }
   for (int idx = t; idx < R2 * R3; idx += TT) s_tw2[idx] = tw2[idx];
@@ -1085,7 +1090,7 @@ fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_
           if (n > h) { xa.y = -xa.y; xb.y = -xb.y; }
           z = mk<T>(xa.x - xb.y, -(xa.y + xb.x));     // conj(xa + i*xb)
         }
-        z = cmul(z, cconj(__ldg(bk + n)));
+        z = cmul(z, cconj(BKS ? bkp[n] : __ldg(bk + n)));
         if (n + d >= L) s_tail[n - (L - d)] = z;
       }
       x[q] = z;
@@ -1122,7 +1127,7 @@ fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_
       if (k < d) {
         for (uint32_t j = k; j < d; ++j) v = cadd(v, cmul(s_tail[j], __ldg(corr + k * kBlueMaxDef + j)));
       }
-      x[q] = k < L ? cmul(v, cconj(__ldg(bk + k))) : mk<T>((T)0, (T)0);
+      x[q] = k < L ? cmul(v, cconj(BKS ? bkp[k] : __ldg(bk + k))) : mk<T>((T)0, (T)0);
     }
     // ---- store
     if (KIND == BL_C2C) {
@@ -1178,10 +1183,16 @@ fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_
 }
 
 namespace {
+// IMPULSE_FFT_BLUE_BK_SMEM=1: chirp table in shared memory (8192-point work length only: one CTA per SM either way)
+inline bool blue_bk_smem() {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_BK_SMEM"); return e ? atoi(e) : 0; }();
+  return v != 0;
+}
 template <typename T, int R1, int R2, int R3, int E>
 int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
   using F = Fft3<T, R1, R2, R3, E>;
-  const size_t smem = sizeof(cx<T>) * ((size_t)F::BUFN + (size_t)R2 * R3 + kBlueMaxDef) + 16;
+  const bool bks = (R1 * R2 * R3 == 8192) && blue_bk_smem();
+  const size_t smem = sizeof(cx<T>) * ((size_t)F::BUFN + (size_t)R2 * R3 + kBlueMaxDef + (bks ? (size_t)J.n_seq : 0)) + 16;
   const int kind = J.store_mode == ST_HERM_HALF ? BL_R2C_PAIR : J.load_mode == LD_HERM_FULL ? BL_C2R_PAIR : BL_C2C;
   const bool bwd = kind == BL_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == BL_R2C_PAIR ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
   typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, uint32_t, uint32_t, const cx<T> *, const cx<T> *,
@@ -1195,10 +1206,26 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
     case 4: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, false>; break;
     default: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, true>; break;
   }
-  static PerDeviceFlag flags[6];
-  bool &configured_here = flags[kind * 2 + (bwd ? 1 : 0)].here();
+  if constexpr (R1 * R2 * R3 == 8192) {
+    if (bks) {
+      switch (kind * 2 + (bwd ? 1 : 0)) {
+        case 0: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, false, true>; break;
+        case 1: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, true, true>; break;
+        case 2: k = fastblue_kernel<T, R1, R2, R3, E, BL_R2C_PAIR, false, true>; break;
+        case 3: k = fastblue_kernel<T, R1, R2, R3, E, BL_R2C_PAIR, true, true>; break;
+        case 4: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, false, true>; break;
+        default: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, true, true>; break;
+      }
+      g_last_kernel = "fastblue_kernel<double,16,16,32,E32>+bk_smem";
+    }
+  }
+  // the dynamic shared-memory size depends on L when the chirp table is resident: always raise the limit to the maximum
+  const size_t smem_max = bks ? (size_t)227 * 1024 : smem;
+  if (smem > smem_max) return (int)cudaErrorInvalidValue;
+  static PerDeviceFlag flags[12];
+  bool &configured_here = flags[(bks ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
   if (!configured_here) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
