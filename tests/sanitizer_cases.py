@@ -16,7 +16,33 @@ def run(kind, x, out, axes, fwd=True, fct=1.0):
     return out
 
 
+def new_kernels_only():
+    """`--new`: only the kernel variants added last (paired real rows, register prefetch, chirp table in shared
+    memory), so that a memcheck / racecheck pass fits in a couple of minutes."""
+    rng = np.random.default_rng(0)
+    ok = True
+    for dt, cdt, tol in ((np.float64, torch.complex128, 1e-9), (np.float32, torch.complex64, 2e-4)):
+        for n in (512, 1000, 2048, 3888, 4096):
+            x = torch.from_numpy(rng.standard_normal((9, n)).astype(dt)).cuda()
+            s = run("r2c", x, torch.empty((9, n // 2 + 1), dtype=cdt, device="cuda"), [1])
+            ok &= bool(torch.allclose(s, torch.fft.rfft(x, dim=1), rtol=tol, atol=tol * n))
+            ok &= bool(torch.allclose(run("c2r", s, torch.empty_like(x), [1], False, 1.0 / n), x, atol=tol * 10))
+    z = torch.from_numpy(rng.standard_normal((11, 2048)) + 1j * rng.standard_normal((11, 2048))).cuda()
+    ok &= bool(torch.allclose(run("c2c", z, torch.empty_like(z), [1]), torch.fft.fft(z, dim=1), rtol=1e-9, atol=1e-8))
+    x = torch.from_numpy(rng.standard_normal((5, 4099))).cuda()
+    s = run("r2c", x, torch.empty((5, 2050), dtype=torch.complex128, device="cuda"), [1])
+    ok &= bool(torch.allclose(s, torch.fft.rfft(x, dim=1), rtol=1e-9, atol=1e-8))
+    ok &= bool(torch.allclose(run("c2r", s, torch.empty_like(x), [1], False, 1.0 / 4099), x, atol=1e-9))
+    z = torch.from_numpy(rng.standard_normal((3, 4099)) + 1j * rng.standard_normal((3, 4099))).cuda()
+    ok &= bool(torch.allclose(run("c2c", z, torch.empty_like(z), [1]), torch.fft.fft(z, dim=1), rtol=1e-9, atol=1e-8))
+    torch.cuda.synchronize()
+    print("sanitizer cases (new kernels):", "ok" if ok else "PARITY FAILURE", "last kernel", ib.last_kernel())
+    sys.exit(0 if ok else 1)
+
+
 def main():
+    if "--new" in sys.argv:
+        new_kernels_only()
     rng = np.random.default_rng(0)
     ok = True
 
@@ -55,6 +81,11 @@ def main():
     r32 = r((5, 2048), np.float32)                                    # real rows on the three-pass kernels, fp32
     ok &= bool(torch.allclose(run("r2c", r32, torch.empty((5, 1025), dtype=torch.complex64, device="cuda"), [1]),
                               torch.fft.rfft(r32, dim=1), rtol=1e-4, atol=2e-2))
+    for n in (1000, 3888, 4096):                                      # paired real kernels (r2c in pass 3, c2r in pass 1), fp32
+        r32 = r((7, n), np.float32)
+        s32 = run("r2c", r32, torch.empty((7, n // 2 + 1), dtype=torch.complex64, device="cuda"), [1])
+        ok &= bool(torch.allclose(s32, torch.fft.rfft(r32, dim=1), rtol=1e-4, atol=2e-2))
+        ok &= bool(torch.allclose(run("c2r", s32, torch.empty_like(r32), [1], False, 1.0 / n), r32, atol=1e-4))
     x = c((1, 1 << 19))                                                # peeled three-pass split, pipelined column kernel
     ok &= bool(torch.allclose(run("c2c", x, torch.empty_like(x), [1]), torch.fft.fft(x, dim=1), rtol=1e-9, atol=1e-5))
     x = c((8192, 160))                                                 # strided 8192-point columns: 64 x 128, 16 lines per CTA
