@@ -1249,6 +1249,13 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
 }
 }  // namespace
 
+// IMPULSE_FFT_F3_MINB4=1: 2048-point fp64 shapes at four CTAs per SM (128 registers) instead of three (A/B runs)
+static int f3_minb4() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("IMPULSE_FFT_F3_MINB4"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 static int fast_variant() {  // IMPULSE_FFT_FAST_VARIANT=1 selects the non-TMA kernel (A/B measurements)
   static int v = -1;
   if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST_VARIANT"); v = e ? atoi(e) : 0; }
@@ -1317,7 +1324,9 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3R_256_F32: g_last_kernel = "fast3_kernel<float,8,8,4,E8>"; return launch_fast3<float, 8, 8, 4, 8, 16, 6, 1>(J, sm_count, s);
     case FAST3R_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E8>"; return launch_fast3<float, 8, 8, 8, 8, 12, 6, 0>(J, sm_count, s);
     case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, 6, 1>(J, sm_count, s);
-    case FAST3_2048_F64: g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3, 1>(J, sm_count, s);
+    case FAST3_2048_F64:
+      if (f3_minb4()) { g_last_kernel = "fast3_kernel<double,16,16,8,E16,minb4>"; return launch_fast3<double, 16, 16, 8, 16, 4, 7, 1, 3, 1>(J, sm_count, s); }
+      g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3, 1>(J, sm_count, s);
     case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2, 7, 0>(J, sm_count, s);
     case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1, 7, 0>(J, sm_count, s);
     case FASTBLUE_2048_F64: g_last_kernel = "fastblue_kernel<double,16,16,8,E16>"; return launch_fastblue<double, 16, 16, 8, 16>(J, sm_count, s);
@@ -1348,7 +1357,9 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5, 7, 0>(J, sm_count, s);
     case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10>"; return launch_fast3<double, 10, 10, 5, 10, 8, 2, 2, 2>(J, sm_count, s);
     case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18>"; return launch_fast3<double, 18, 18, 6, 18, 4, 2, 2>(J, sm_count, s);
-    case FAST3C_2048_F64: g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8>(J, sm_count, s);
+    case FAST3C_2048_F64:
+      if (f3_minb4()) { g_last_kernel = "fast3_kernel<double,8,16,16,E16,minb4>"; return launch_fast3<double, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s); }
+      g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8>(J, sm_count, s);
     case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s);
     case FAST3C_1024_F64: g_last_kernel = "fast3_kernel<double,8,8,16,E16>"; return launch_fast3<double, 8, 8, 16, 16, 8, 4, 8>(J, sm_count, s);
     case FAST3C_1024_F32: g_last_kernel = "fast3_kernel<float,8,8,16,E16>"; return launch_fast3<float, 8, 8, 16, 16, 12, 4, 8>(J, sm_count, s);
@@ -1357,6 +1368,8 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3_1000_F32: g_last_kernel = "fast3_kernel<float,10,10,10,E10>"; return launch_fast3<float, 10, 10, 10, 10, 8, 7, 0>(J, sm_count, s);
     case FAST3R_500_F32: g_last_kernel = "fast3_kernel<float,10,10,5,E10>"; return launch_fast3<float, 10, 10, 5, 10, 16, 2, 2>(J, sm_count, s);
     case FAST3R_1944_F32: g_last_kernel = "fast3_kernel<float,18,18,6,E18>"; return launch_fast3<float, 18, 18, 6, 18, 6, 2, 2>(J, sm_count, s);
+    case FAST3P_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E16>"; return launch_fast3<double, 8, 8, 8, 16, 16, 6, 10>(J, sm_count, s);
+    case FAST3P_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E16>"; return launch_fast3<float, 8, 8, 8, 16, 24, 6, 10>(J, sm_count, s);
     case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2, 7, 0>(J, sm_count, s);
     case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, 7, 1, 3>(J, sm_count, s);
     case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3, 7, 0>(J, sm_count, s);

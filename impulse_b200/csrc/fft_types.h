@@ -153,6 +153,8 @@ enum FastId : uint32_t {
   FAST3_1000_F32 = 65,
   FAST3R_500_F32 = 66,
   FAST3R_1944_F32 = 67,
+  FAST3P_512_F64 = 68,   // 8*8*8 with 16 points per thread: r2c AND c2r of 1024 points paired in registers
+  FAST3P_512_F32 = 69,
 };
 
 struct Phase {

@@ -8,7 +8,7 @@ import pytest
 
 from tests.emu import harness_fast3 as f3
 
-SHAPES_PAIR = [(16, 16, 8, 16), (16, 8, 8, 16), (8, 8, 4, 8), (10, 10, 5, 10), (18, 18, 6, 18)]
+SHAPES_PAIR = [(16, 16, 8, 16), (16, 8, 8, 16), (8, 8, 4, 8), (10, 10, 5, 10), (18, 18, 6, 18), (8, 8, 8, 16)]
 SHAPES_OLD = [(8, 8, 8, 8), (5, 10, 10, 10), (6, 18, 18, 18), (16, 16, 16, 16), (10, 10, 10, 10)]
 
 
