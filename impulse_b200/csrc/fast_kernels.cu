@@ -967,8 +967,13 @@ struct Fft3 {
   static_assert(E % R1 == 0 && E % R2 == 0 && E % R3 == 0 && TT % R1 == 0, "fast3 shape");
   // forward FFT of the N points x[q] <-> n = t + TT*q; result in the same layout (k = t + TT*q).
   // `buf` must be free on entry; on return other threads may still be reading it.
+  // MUL: the result is multiplied by mul[k] and conjugated (the middle of a Bluestein convolution); half of each
+  // pass-3 butterfly's multipliers are requested BEFORE the butterfly runs, so that their L2 latency hides behind it
+  // (the registers of x[] are free at that point; all of them would not fit beside the butterfly).
+  template <bool MUL = false>
   static __device__ __forceinline__ void run(cx<T> (&x)[E], cx<T> *buf, const cx<T> *__restrict__ tw1,
-                                             const cx<T> *s_tw2, const cx<T> (&twA)[3], const cx<T> (&twB)[3], int t) {
+                                             const cx<T> *s_tw2, const cx<T> (&twA)[3], const cx<T> (&twB)[3], int t,
+                                             const cx<T> *__restrict__ mul = nullptr) {
     const int k1 = t % R1, i2b = t / R1;
 #pragma unroll
     for (int m = 0; m < NB1; ++m) {
@@ -1020,9 +1025,23 @@ struct Fft3 {
       cx<T> y[R3];
 #pragma unroll
       for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
-      RegFFT<T, R3>::run(y);
+      constexpr int PRE = MUL ? (R3 + 1) / 2 : 1;
+      cx<T> w[PRE];
+      if constexpr (MUL) {
 #pragma unroll
-      for (int k = 0; k < R3; ++k) x[m + NB3 * k] = y[k];   // X[t + TT*(m + NB3*k)]  (R1*R2 = TT*NB3)
+        for (int k = 0; k < PRE; ++k) w[k] = __ldg(mul + t + TT * (m + NB3 * k));
+      }
+      RegFFT<T, R3>::run(y);
+      if constexpr (MUL) {
+#pragma unroll
+        for (int k = 0; k < R3; ++k) {
+          const cx<T> v = cmul(y[k], k < PRE ? w[k < PRE ? k : 0] : __ldg(mul + t + TT * (m + NB3 * k)));
+          x[m + NB3 * k] = mk<T>(v.x, -v.y);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R3; ++k) x[m + NB3 * k] = y[k];   // X[t + TT*(m + NB3*k)]  (R1*R2 = TT*NB3)
+      }
     }
   }
 };
@@ -1032,7 +1051,8 @@ constexpr int kBlueMaxDef = 16;  // largest supported deficiency d
 
 // BKS: the chirp table b_k (L entries, used before the first and after the second transform of every unit) is
 // copied to shared memory once per CTA instead of being streamed from L2 twice per unit.
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool BKS = false>
+// BFE: FFT(b)/M is multiplied in inside the first transform's last pass, half of it requested ahead of the butterfly.
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool BKS = false, bool BFE = false>
 __global__ void __launch_bounds__((R1 * R2 * R3) / E, 1)
 fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
                 uint32_t L, uint32_t d, const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2,
@@ -1109,13 +1129,18 @@ fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_
         }
       }
     }
-    F::run(x, buf, tw1, s_tw2, twA, twB, t);
-    if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // every thread read s_row[it&1] before the core's barriers
-    // ---- multiply by FFT(b)/M, conjugate for the inverse transform
+    if constexpr (BFE) {
+      F::template run<true>(x, buf, tw1, s_tw2, twA, twB, t, bf);
+      if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);
+    } else {
+      F::run(x, buf, tw1, s_tw2, twA, twB, t);
+      if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // every thread read s_row[it&1] before the core's barriers
+      // ---- multiply by FFT(b)/M, conjugate for the inverse transform
 #pragma unroll
-    for (int q = 0; q < E; ++q) {
-      const cx<T> v = cmul(x[q], __ldg(bf + t + TT * q));
-      x[q] = mk<T>(v.x, -v.y);
+      for (int q = 0; q < E; ++q) {
+        const cx<T> v = cmul(x[q], __ldg(bf + t + TT * q));
+        x[q] = mk<T>(v.x, -v.y);
+      }
     }
     __syncthreads();  // pass-3 reads of the first transform are done
     F::run(x, buf, tw1, s_tw2, twA, twB, t);
@@ -1189,10 +1214,16 @@ inline bool blue_bk_smem() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_BK_SMEM"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
+// IMPULSE_FFT_BLUE_BF_EARLY=1: multiply by FFT(b)/M inside the first transform's last pass (A/B)
+inline bool blue_bf_early() {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_BF_EARLY"); return e ? atoi(e) : 0; }();
+  return v != 0;
+}
 template <typename T, int R1, int R2, int R3, int E>
 int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
   using F = Fft3<T, R1, R2, R3, E>;
   const bool bks = (R1 * R2 * R3 == 8192) && blue_bk_smem();
+  const bool bfe = bks && blue_bf_early();
   const size_t smem = sizeof(cx<T>) * ((size_t)F::BUFN + (size_t)R2 * R3 + kBlueMaxDef + (bks ? (size_t)J.n_seq : 0)) + 16;
   const int kind = J.store_mode == ST_HERM_HALF ? BL_R2C_PAIR : J.load_mode == LD_HERM_FULL ? BL_C2R_PAIR : BL_C2C;
   const bool bwd = kind == BL_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == BL_R2C_PAIR ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
@@ -1218,13 +1249,24 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
         default: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, true, true>; break;
       }
       g_last_kernel = "fastblue_kernel<double,16,16,32,E32>+bk_smem";
+      if (bfe) {
+        switch (kind * 2 + (bwd ? 1 : 0)) {
+          case 0: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, false, true, true>; break;
+          case 1: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, true, true, true>; break;
+          case 2: k = fastblue_kernel<T, R1, R2, R3, E, BL_R2C_PAIR, false, true, true>; break;
+          case 3: k = fastblue_kernel<T, R1, R2, R3, E, BL_R2C_PAIR, true, true, true>; break;
+          case 4: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, false, true, true>; break;
+          default: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, true, true, true>; break;
+        }
+        g_last_kernel = "fastblue_kernel<double,16,16,32,E32>+bk_smem+bf_early";
+      }
     }
   }
   // the dynamic shared-memory size depends on L when the chirp table is resident: always raise the limit to the maximum
   const size_t smem_max = bks ? (size_t)227 * 1024 : smem;
   if (smem > smem_max) return (int)cudaErrorInvalidValue;
-  static PerDeviceFlag flags[12];
-  bool &configured_here = flags[(bks ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
+  static PerDeviceFlag flags[18];
+  bool &configured_here = flags[(bfe ? 12 : bks ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
   if (!configured_here) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return (int)e;
