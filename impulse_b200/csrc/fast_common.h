@@ -1,0 +1,25 @@
+// Host-side helpers shared by the register-kernel translation units (fast_kernels.cu, fast3_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fft_types.h"
+
+namespace impulse {
+
+constexpr int kMaxDevices = 64;
+inline int cur_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+// function attributes (dynamic shared memory size, carve-out) are per device: remember where they were set
+struct PerDeviceFlag {
+  bool done[kMaxDevices] = {};
+  bool &here() { return done[cur_dev()]; }
+};
+// a zero-initialised pair of device words {next row, CTAs done} for one launch with dynamic row claims (fast_kernels.cu)
+unsigned int *sched_slot();
+// the three-pass register kernels (fast3_kernels.cu); returns cudaError_t, cudaErrorInvalidValue for other ids
+int launch_fast3_job(const LineJob &job, int sm_count, void *stream);
+
+}  // namespace impulse

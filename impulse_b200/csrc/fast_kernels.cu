@@ -21,24 +21,12 @@
 #include <cstdlib>
 
 #include "fast3_device.cuh"
+#include "fast_common.h"
 #include "fft_device.cuh"
 #include "fft_kernels.h"
 
 namespace impulse {
 
-namespace {
-constexpr int kMaxDevices = 64;
-inline int cur_dev() {
-  int d = 0;
-  cudaGetDevice(&d);
-  return (d >= 0 && d < kMaxDevices) ? d : 0;
-}
-// function attributes (dynamic shared memory size, carve-out) are per device: remember where they were set
-struct PerDeviceFlag {
-  bool done[kMaxDevices] = {};
-  bool &here() { return done[cur_dev()]; }
-};
-}  // namespace
 
 
 template <typename T, int R1, int R2, int WARPS, int MINB, bool BWD>
@@ -385,10 +373,9 @@ fast2p_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nr
   }
 }
 
-namespace {
-// scheduler slots: zero-initialised device words, one pair per in-flight launch (ring)
-constexpr int kSchedSlots = 65536;  // a slot is reused after this many launches: far more than can be queued across streams
+// scheduler slots: zero-initialised device words, one pair per in-flight launch (ring); shared with fast3_kernels.cu
 unsigned int *sched_slot() {
+  constexpr int kSchedSlots = 65536;  // a slot is reused after this many launches: far more than can be queued across streams
   static unsigned int *bases[kMaxDevices] = {};
   static unsigned next = 0;
   unsigned int *&base = bases[cur_dev()];
@@ -400,6 +387,7 @@ unsigned int *sched_slot() {
   return base + 2 * s;
 }
 
+namespace {
 template <typename T, int R1, int R2, int WARPS>
 int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2, GPW = 32 / R2, BUF = R1 * (R2 + 1);
@@ -432,106 +420,6 @@ int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
 
 // fast_id encodes the specialised kernel chosen by the planner (0 = generic engine)
 
-namespace {
-// IMPULSE_FFT_R2C_PAIR=0 / IMPULSE_FFT_C2R_PAIR=0 restore the post- / pre-twiddle through shared memory (A/B runs)
-inline bool r2c_pair_enabled() {
-  static const int v = [] { const char *e = getenv("IMPULSE_FFT_R2C_PAIR"); return e ? atoi(e) : 1; }();
-  return v != 0;
-}
-// Register prefetch of the next claimed row during pass 3 (PF variants).  Measured on the B200: +7 % for c2c rows of
-// 2048 points (5.74 -> 6.14 TB/s), within +-2 % for the paired r2c shapes, slower wherever the extra live
-// registers spill (c2c 4096: 5.24 -> 4.71).  So it is on by default only where the launcher says so (PFDEF);
-// IMPULSE_FFT_F3_PF=0 / 1 forces it off / on for every instantiated variant (A/B runs).
-inline bool f3_prefetch_enabled(bool dflt) {
-  static const int v = [] { const char *e = getenv("IMPULSE_FFT_F3_PF"); return e ? atoi(e) : -1; }();
-  return v < 0 ? dflt : v != 0;
-}
-inline bool c2r_pair_enabled() {
-  static const int v = [] { const char *e = getenv("IMPULSE_FFT_C2R_PAIR"); return e ? atoi(e) : 1; }();
-  return v != 0;
-}
-
-// KINDS: which kinds the shape is instantiated for (1 = c2c, 2 = r2c, 4 = c2r).
-// PAIRS: 1 = r2c post-twiddle in pass 3 (pair units) unless switched off, 2 = r2c always paired (the shape exists
-//        for that variant only); 4 / 8 = the same for the c2r pre-twiddle in pass 1.
-// PFK:   kinds for which the register-prefetch variant is instantiated (same bits as KINDS; real kinds: pair only)
-// PFDEF: kinds for which it is the default
-template <typename T, int R1, int R2, int R3, int E, int MINB, int KINDS = 7, int PAIRS = 0, int PFK = 0, int PFDEF = 0>
-int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
-  constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
-  constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
-  constexpr int BUFN = (R1 * P1 > N + 1) ? R1 * P1 : N + 1;
-  const size_t smem = sizeof(cx<T>) * ((size_t)BUFN + (size_t)R2 * R3) + 16;
-  const int kind = J.store_mode == ST_R2C_EVEN ? F3_R2C : J.load_mode == LD_HERM_EVEN ? F3_C2R : F3_C2C;
-  const bool bwd = kind == F3_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == F3_R2C ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
-  typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, const cx<T> *, const cx<T> *, const cx<T> *, T, unsigned int *);
-  kern_t k = nullptr;
-  bool pair = false, pf = false;
-  if (kind == F3_C2C) {
-    if constexpr ((KINDS & 1) != 0) k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB>;
-    if constexpr ((KINDS & 1) != 0 && (PFK & 1) != 0) {
-      if (f3_prefetch_enabled((PFDEF & 1) != 0)) {
-        pf = true;
-        k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB, false, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB, false, true>;
-      }
-    }
-  } else if (kind == F3_R2C) {
-    if constexpr ((KINDS & 2) != 0) {
-      if constexpr ((PAIRS & 3) != 0) {
-        if ((PAIRS & 2) != 0 || r2c_pair_enabled()) {
-          pair = true;
-          k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB, true>;
-          if constexpr ((PFK & 2) != 0) {
-            if (f3_prefetch_enabled((PFDEF & 2) != 0)) {
-              pf = true;
-              k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB, true, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB, true, true>;
-            }
-          }
-        }
-      }
-      if constexpr ((PAIRS & 2) == 0) {
-        if (!pair) k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB>;
-      }
-    }
-  } else {
-    if constexpr ((KINDS & 4) != 0) {
-      if constexpr ((PAIRS & 12) != 0) {
-        if ((PAIRS & 8) != 0 || c2r_pair_enabled()) {
-          pair = true;
-          k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB, true>;
-        }
-      }
-      if constexpr ((PAIRS & 8) == 0) {
-        if (!pair) k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB>;
-      }
-    }
-  }
-  if (!k) return (int)cudaErrorInvalidValue;   // the planner never selects a shape for a kind it is not built for
-  if (pair || pf) {  // reported by impulse_fft_last_kernel()
-    static thread_local char name[96];
-    snprintf(name, sizeof(name), "%s%s%s", g_last_kernel, pair ? "+pair" : "", pf ? "+pf" : "");
-    g_last_kernel = name;
-  }
-  static PerDeviceFlag flags[24];
-  bool &configured_here = flags[(pf ? 12 : 0) + (pair ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
-  if (!configured_here) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return (int)e;
-    configured_here = true;
-  }
-  uint64_t grid = J.n_lines;
-  const uint64_t cap = (uint64_t)sm_count * MINB;
-  if (grid > cap) grid = cap;
-  unsigned int *sched = sched_slot();
-  if (!sched) return (int)cudaErrorMemoryAllocation;
-  if (J.n_lines > 0xfff00000ull) return (int)cudaErrorInvalidValue;
-  k<<<(unsigned)grid, TT, smem, s>>>(J.in, J.out, J.n_lines, J.bs_in[0], J.bs_out[0], (const cx<T> *)J.f3_tw1,
-                                      (const cx<T> *)J.f3_tw2, (const cx<T> *)J.tw_r, (T)J.fct, sched);
-  return (int)cudaGetLastError();
-}
-}  // namespace
 
 
 // W_N^m from the two-level four-step table of the job (m < N)
@@ -1292,13 +1180,6 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
 }
 }  // namespace
 
-// IMPULSE_FFT_F3_MINB4=1: 2048-point fp64 shapes at four CTAs per SM (128 registers) instead of three (A/B runs)
-static int f3_minb4() {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("IMPULSE_FFT_F3_MINB4"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
 static int fast_variant() {  // IMPULSE_FFT_FAST_VARIANT=1 selects the non-TMA kernel (A/B measurements)
   static int v = -1;
   if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST_VARIANT"); v = e ? atoi(e) : 0; }
@@ -1361,17 +1242,6 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST2R_32_F32: g_last_kernel = "fast2r_kernel<float,8,4>"; return launch_fast2r<float, 8, 4, 8, 6>(J, sm_count, s);
     case FAST2R_64_F32: g_last_kernel = "fast2r_kernel<float,8,8>"; return launch_fast2r<float, 8, 8, 8, 6>(J, sm_count, s);
     case FAST2R_128_F32: g_last_kernel = "fast2r_kernel<float,16,8>"; return launch_fast2r<float, 16, 8, 8, 4>(J, sm_count, s);
-    case FAST3R_256_F64: g_last_kernel = "fast3_kernel<double,8,8,4,E8>"; return launch_fast3<double, 8, 8, 4, 8, 16, 6, 1>(J, sm_count, s);
-    case FAST3R_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E8>"; return launch_fast3<double, 8, 8, 8, 8, 8, 6, 0>(J, sm_count, s);
-    case FAST3R_1024_F64: g_last_kernel = "fast3_kernel<double,16,8,8,E16>"; return launch_fast3<double, 16, 8, 8, 16, 8, 6, 1>(J, sm_count, s);
-    case FAST3R_256_F32: g_last_kernel = "fast3_kernel<float,8,8,4,E8>"; return launch_fast3<float, 8, 8, 4, 8, 16, 6, 1>(J, sm_count, s);
-    case FAST3R_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E8>"; return launch_fast3<float, 8, 8, 8, 8, 12, 6, 0>(J, sm_count, s);
-    case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, 6, 1>(J, sm_count, s);
-    case FAST3_2048_F64:
-      if (f3_minb4()) { g_last_kernel = "fast3_kernel<double,16,16,8,E16,minb4>"; return launch_fast3<double, 16, 16, 8, 16, 4, 7, 1, 3, 1>(J, sm_count, s); }
-      g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3, 1>(J, sm_count, s);
-    case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2, 7, 0>(J, sm_count, s);
-    case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1, 7, 0>(J, sm_count, s);
     case FASTBLUE_2048_F64: g_last_kernel = "fastblue_kernel<double,16,16,8,E16>"; return launch_fastblue<double, 16, 16, 8, 16>(J, sm_count, s);
     case FASTBLUE_4096_F64: g_last_kernel = "fastblue_kernel<double,16,16,16,E16>"; return launch_fastblue<double, 16, 16, 16, 16>(J, sm_count, s);
     case FASTBLUE_8192_F64: g_last_kernel = "fastblue_kernel<double,16,16,32,E32>"; return launch_fastblue<double, 16, 16, 32, 32>(J, sm_count, s);
@@ -1395,28 +1265,7 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case COL2_64_F32: g_last_kernel = "colfast2_kernel<float,8,8,16>"; return launch_colfast2<float, 8, 8, 16>(J, s);
     case COL2_128_F32: g_last_kernel = "colfast2_kernel<float,16,8,16>"; return launch_colfast2<float, 16, 8, 16>(J, s);
     case COL2_256_F32: g_last_kernel = "colfast2_kernel<float,16,16,16>"; return launch_colfast2<float, 16, 16, 16>(J, s);
-    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8, 7, 4>(J, sm_count, s);
-    case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4, 7, 4>(J, sm_count, s);
-    case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5, 7, 0>(J, sm_count, s);
-    case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10>"; return launch_fast3<double, 10, 10, 5, 10, 8, 2, 2, 2>(J, sm_count, s);
-    case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18>"; return launch_fast3<double, 18, 18, 6, 18, 4, 2, 2>(J, sm_count, s);
-    case FAST3C_2048_F64:
-      if (f3_minb4()) { g_last_kernel = "fast3_kernel<double,8,16,16,E16,minb4>"; return launch_fast3<double, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s); }
-      g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8>(J, sm_count, s);
-    case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s);
-    case FAST3C_1024_F64: g_last_kernel = "fast3_kernel<double,8,8,16,E16>"; return launch_fast3<double, 8, 8, 16, 16, 8, 4, 8>(J, sm_count, s);
-    case FAST3C_1024_F32: g_last_kernel = "fast3_kernel<float,8,8,16,E16>"; return launch_fast3<float, 8, 8, 16, 16, 12, 4, 8>(J, sm_count, s);
-    case FAST3_500_F32: g_last_kernel = "fast3_kernel<float,5,10,10,E10>"; return launch_fast3<float, 5, 10, 10, 10, 16, 7, 4>(J, sm_count, s);
-    case FAST3_1944_F32: g_last_kernel = "fast3_kernel<float,6,18,18,E18>"; return launch_fast3<float, 6, 18, 18, 18, 6, 7, 4>(J, sm_count, s);
-    case FAST3_1000_F32: g_last_kernel = "fast3_kernel<float,10,10,10,E10>"; return launch_fast3<float, 10, 10, 10, 10, 8, 7, 0>(J, sm_count, s);
-    case FAST3R_500_F32: g_last_kernel = "fast3_kernel<float,10,10,5,E10>"; return launch_fast3<float, 10, 10, 5, 10, 16, 2, 2>(J, sm_count, s);
-    case FAST3R_1944_F32: g_last_kernel = "fast3_kernel<float,18,18,6,E18>"; return launch_fast3<float, 18, 18, 6, 18, 6, 2, 2>(J, sm_count, s);
-    case FAST3P_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E16>"; return launch_fast3<double, 8, 8, 8, 16, 16, 6, 10>(J, sm_count, s);
-    case FAST3P_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E16>"; return launch_fast3<float, 8, 8, 8, 16, 24, 6, 10>(J, sm_count, s);
-    case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2, 7, 0>(J, sm_count, s);
-    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, 7, 1, 3>(J, sm_count, s);
-    case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3, 7, 0>(J, sm_count, s);
-    default: return (int)cudaErrorInvalidValue;
+    default: return launch_fast3_job(J, sm_count, stream);   // three-pass register kernels: fast3_kernels.cu
   }
 }
 
