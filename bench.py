@@ -173,6 +173,35 @@ def cpu_reference(kind, rows, n, dtype, budget_s=12.0):
     return gbs, info
 
 
+def accuracy_report(ib, torch, kind, x, y, n, dtype):
+    """max over (sampled) rows of the rel-L2 error against the oracle with its pass bound, and the
+    forward->backward round trip over ALL rows on the device.  x = the step's input, y = its output (already
+    computed by the timed steps).  The oracle is the checker here, never the thing measured."""
+    from oracle import oracle
+    chk = oracle.load()
+    rows = x.shape[0]
+    sel = sorted({0, 1, rows // 3, rows // 2, rows - 1})
+    xs, ys = x[sel].cpu().numpy().copy(), y[sel].cpu().numpy()
+    if kind == "c2c":
+        want = chk.c2c(xs, [1], True, 1.0)
+    elif kind == "r2c":
+        want = chk.r2c(xs, [1], True, 1.0)
+    elif kind == "c2r":
+        want = chk.c2r(xs, ys.shape, [1], False, 1.0)
+    else:
+        return {"unavailable": f"not reported for {kind}"}
+    bound = (1e-12 if dtype == "f64" else 1e-5) * max(1.0, float(np.log2(max(n, 2))))
+    err = float(oracle.max_row_rel_l2(ys, want))
+    out = {"max_rel_l2_vs_oracle": err, "bound": bound, "rows_checked": len(sel), "oracle": chk.kind, "pass": bool(err <= bound)}
+    if kind in ("c2c", "r2c"):   # round trip: backward transform of the output with 1/N, against the input
+        back = torch.empty_like(x)
+        ib.FFTDesc.init(axes=[1], forward=False, scalingFactor=1.0 / n).apply(ib.DataDesc.init(back), ib.DataDesc.init(y))
+        num = torch.linalg.vector_norm(back - x, dim=1)
+        den = torch.linalg.vector_norm(x, dim=1)
+        out["round_trip_max_rel_l2"] = float((num / den).max())
+    return out
+
+
 def run_reference(args, kind, rows, n, dtype, rank, world):
     if rank != 0:
         return
@@ -368,6 +397,10 @@ def main():
                 line["cpu_baseline"] = info
             except Exception as ex:  # the oracle is optional for the measurement itself
                 line["cpu_baseline"] = {"unavailable": str(ex)}
+            try:
+                line["accuracy"] = accuracy_report(ib, torch, kind, x, y, n, dtype)
+            except Exception as ex:  # noqa: BLE001 — a reporting extra never costs the bench line
+                line["accuracy"] = {"unavailable": str(ex)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
