@@ -106,7 +106,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t byte
 #endif
 }
 
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB, bool PAIR = false, bool PF = false>
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB, bool PAIR = false, bool PF = false, bool DB = false>
 __global__ void __launch_bounds__((R1 * R2 * R3) / E, MINB)
 fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
              const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, const cx<T> *__restrict__ twr, T fct,
@@ -120,8 +120,14 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
   static_assert(E % R1 == 0 && E % R2 == 0 && E % R3 == 0 && TT % R1 == 0, "fast3 shape");
   constexpr int BUFN = (R1 * P1 > N + 1) ? R1 * P1 : N + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // DB: a second exchange buffer.  Pass-2 results (X2) no longer overwrite what pass 2 is still reading (X1), and the
+  // next row's pass 1 no longer overwrites what pass 3 is still reading, so two of the four barriers per row go:
+  // what remains is "X1 complete" and "X2 complete".  (Direct-load variants only: the shared-memory Hermitian
+  // twiddles use the buffer a third time.)
+  static_assert(!DB || KIND == F3_C2C || PAIR, "the second exchange buffer needs the direct-load variants");
   cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
-  unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + BUFN);  // [2] (+2 pad)
+  cx<T> *buf2 = DB ? buf + BUFN : buf;
+  unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + (DB ? 2 : 1) * BUFN);  // [2] (+2 pad)
   cx<T> *s_tw2 = reinterpret_cast<cx<T> *>(s_row + 4);                 // [R2][R3]
   const int t = threadIdx.x;
   if (t == 0) { s_row[0] = atomicAdd(&sched[0], 1u); s_row[1] = atomicAdd(&sched[0], 1u); }
@@ -296,12 +302,12 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
 #pragma unroll
       for (int k = 0; k < R2; ++k) x[m * R2 + k] = y[k];
     }
-    __syncthreads();
+    if (!DB) __syncthreads();   // X2 aliases X1: every pass-2 read first
 #pragma unroll
     for (int m = 0; m < NB2; ++m) {
       const int i2 = i2b + (TT / R1) * m;
 #pragma unroll
-      for (int k = 0; k < R2; ++k) buf[i2 * P2 + k1 + R1 * k] = x[m * R2 + k];
+      for (int k = 0; k < R2; ++k) buf2[i2 * P2 + k1 + R1 * k] = x[m * R2 + k];
     }
     __syncthreads();
     if constexpr (PF) {   // x[] (pA/pB) are free from here on: request the next claimed row
@@ -336,7 +342,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
         const int ka = u, kb = u == 0 ? P2 / 2 : P2 - u;
         cx<T> ya[R3], yb[R3];
 #pragma unroll
-        for (int j = 0; j < R3; ++j) { ya[j] = buf[j * P2 + ka]; yb[j] = buf[j * P2 + kb]; }
+        for (int j = 0; j < R3; ++j) { ya[j] = buf2[j * P2 + ka]; yb[j] = buf2[j * P2 + kb]; }
         RegFFT<T, R3>::run(ya);
         RegFFT<T, R3>::run(yb);
         if (u != 0) {
@@ -368,7 +374,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
           }
         }
       }
-      __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
+      if (!DB) __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
     } else {
       // ---------------- pass 3 (+ store for c2c / c2r: straight from the butterfly's registers) ----------------
       if constexpr (KIND != F3_R2C) {
@@ -381,12 +387,12 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
           const int klow = t + TT * m;
           cx<T> y[R3];
 #pragma unroll
-          for (int j = 0; j < R3; ++j) y[j] = buf[j * P2 + klow];
+          for (int j = 0; j < R3; ++j) y[j] = buf2[j * P2 + klow];
           RegFFT<T, R3>::run(y);
 #pragma unroll
           for (int k = 0; k < R3; ++k) dst[klow + R1 * R2 * k] = mk<T>(y[k].x * fct, y[k].y * fy);
         }
-        __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
+        if (!DB) __syncthreads();  // pass-3 reads done before the next row's pass-1 writes
       } else {  // r2c: Hermitian post-twiddle needs Z[k] and Z[N-k]
 #pragma unroll
         for (int m = 0; m < NB3; ++m) {

@@ -27,6 +27,12 @@ inline bool f3_prefetch_enabled(bool dflt) {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_F3_PF"); return e ? atoi(e) : -1; }();
   return v < 0 ? dflt : v != 0;
 }
+// IMPULSE_FFT_F3_DB=1: second exchange buffer (two barriers per row instead of four) where instantiated.  Not yet
+// measured on the B200 (validated under the thread-level emulation only), hence off by default.
+inline bool f3_double_buffer() {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_F3_DB"); return e ? atoi(e) : 0; }();
+  return v != 0;
+}
 inline bool c2r_pair_enabled() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_C2R_PAIR"); return e ? atoi(e) : 1; }();
   return v != 0;
@@ -37,12 +43,13 @@ inline bool c2r_pair_enabled() {
 //        for that variant only); 4 / 8 = the same for the c2r pre-twiddle in pass 1.
 // PFK:   kinds for which the register-prefetch variant is instantiated (same bits as KINDS; real kinds: pair only)
 // PFDEF: kinds for which it is the default
-template <typename T, int R1, int R2, int R3, int E, int MINB, int KINDS = 7, int PAIRS = 0, int PFK = 0, int PFDEF = 0>
+// DBK:   kinds for which the second-exchange-buffer variant is instantiated (real kinds: pair only)
+template <typename T, int R1, int R2, int R3, int E, int MINB, int KINDS = 7, int PAIRS = 0, int PFK = 0, int PFDEF = 0, int DBK = 0>
 int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
   constexpr int BUFN = (R1 * P1 > N + 1) ? R1 * P1 : N + 1;
-  const size_t smem = sizeof(cx<T>) * ((size_t)BUFN + (size_t)R2 * R3) + 16;
+  size_t smem = sizeof(cx<T>) * ((size_t)BUFN + (size_t)R2 * R3) + 16;
   const int kind = J.store_mode == ST_R2C_EVEN ? F3_R2C : J.load_mode == LD_HERM_EVEN ? F3_C2R : F3_C2C;
   const bool bwd = kind == F3_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == F3_R2C ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
   typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, const cx<T> *, const cx<T> *, const cx<T> *, T, unsigned int *);
@@ -87,14 +94,29 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
       }
     }
   }
+  bool db = false;
+  if constexpr (DBK != 0) {
+    if (f3_double_buffer()) {
+      if constexpr ((DBK & 1) != 0 && (KINDS & 1) != 0) {
+        if (kind == F3_C2C) { db = true; k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB, false, false, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB, false, false, true>; }
+      }
+      if constexpr ((DBK & 2) != 0 && (KINDS & 2) != 0 && (PAIRS & 3) != 0) {
+        if (kind == F3_R2C && pair) { db = true; k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, true, MINB, true, false, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_R2C, false, MINB, true, false, true>; }
+      }
+      if constexpr ((DBK & 4) != 0 && (KINDS & 4) != 0 && (PAIRS & 12) != 0) {
+        if (kind == F3_C2R && pair) { db = true; k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, true, MINB, true, false, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2R, false, MINB, true, false, true>; }
+      }
+      if (db) { pf = false; smem += sizeof(cx<T>) * (size_t)BUFN; }
+    }
+  }
   if (!k) return (int)cudaErrorInvalidValue;   // the planner never selects a shape for a kind it is not built for
-  if (pair || pf) {  // reported by impulse_fft_last_kernel()
+  if (pair || pf || db) {  // reported by impulse_fft_last_kernel()
     static thread_local char name[96];
-    snprintf(name, sizeof(name), "%s%s%s", g_last_kernel, pair ? "+pair" : "", pf ? "+pf" : "");
+    snprintf(name, sizeof(name), "%s%s%s%s", g_last_kernel, pair ? "+pair" : "", pf ? "+pf" : "", db ? "+db" : "");
     g_last_kernel = name;
   }
-  static PerDeviceFlag flags[24];
-  bool &configured_here = flags[(pf ? 12 : 0) + (pair ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
+  static PerDeviceFlag flags[30];
+  bool &configured_here = flags[db ? 24 + kind * 2 + (bwd ? 1 : 0) : (pf ? 12 : 0) + (pair ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
   if (!configured_here) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -132,18 +154,18 @@ int launch_fast3_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, 6, 1>(J, sm_count, s);
     case FAST3_2048_F64:
       if (f3_minb4()) { g_last_kernel = "fast3_kernel<double,16,16,8,E16,minb4>"; return launch_fast3<double, 16, 16, 8, 16, 4, 7, 1, 3, 1>(J, sm_count, s); }
-      g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3, 1>(J, sm_count, s);
+      g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3, 1, 3>(J, sm_count, s);
     case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2, 7, 0>(J, sm_count, s);
     case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1, 7, 0>(J, sm_count, s);
-    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8, 7, 4>(J, sm_count, s);
-    case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4, 7, 4>(J, sm_count, s);
+    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8, 7, 4, 0, 0, 4>(J, sm_count, s);
+    case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4, 7, 4, 0, 0, 4>(J, sm_count, s);
     case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5, 7, 0>(J, sm_count, s);
-    case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10>"; return launch_fast3<double, 10, 10, 5, 10, 8, 2, 2, 2>(J, sm_count, s);
-    case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18>"; return launch_fast3<double, 18, 18, 6, 18, 4, 2, 2>(J, sm_count, s);
+    case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10>"; return launch_fast3<double, 10, 10, 5, 10, 8, 2, 2, 2, 0, 2>(J, sm_count, s);
+    case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18>"; return launch_fast3<double, 18, 18, 6, 18, 4, 2, 2, 0, 0, 2>(J, sm_count, s);
     case FAST3C_2048_F64:
       if (f3_minb4()) { g_last_kernel = "fast3_kernel<double,8,16,16,E16,minb4>"; return launch_fast3<double, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s); }
-      g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8>(J, sm_count, s);
-    case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s);
+      g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8, 0, 0, 4>(J, sm_count, s);
+    case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8, 0, 0, 4>(J, sm_count, s);
     case FAST3C_1024_F64: g_last_kernel = "fast3_kernel<double,8,8,16,E16>"; return launch_fast3<double, 8, 8, 16, 16, 8, 4, 8>(J, sm_count, s);
     case FAST3C_1024_F32: g_last_kernel = "fast3_kernel<float,8,8,16,E16>"; return launch_fast3<float, 8, 8, 16, 16, 12, 4, 8>(J, sm_count, s);
     case FAST3_500_F32: g_last_kernel = "fast3_kernel<float,5,10,10,E10>"; return launch_fast3<float, 5, 10, 10, 10, 16, 7, 4>(J, sm_count, s);
@@ -154,7 +176,7 @@ int launch_fast3_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3P_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E16>"; return launch_fast3<double, 8, 8, 8, 16, 16, 6, 10>(J, sm_count, s);
     case FAST3P_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E16>"; return launch_fast3<float, 8, 8, 8, 16, 24, 6, 10>(J, sm_count, s);
     case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2, 7, 0>(J, sm_count, s);
-    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, 7, 1, 3>(J, sm_count, s);
+    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, 7, 1, 3, 0, 3>(J, sm_count, s);
     case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3, 7, 0>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;
   }

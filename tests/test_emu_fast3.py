@@ -148,3 +148,26 @@ def test_non_power_of_two_shapes_f32(shape):
     assert rel(back.astype(np.float64), x.astype(np.float64)) < 1e-6 * np.log2(n)
     z = (rng.random((2, n)) - 0.5 + 1j * (rng.random((2, n)) - 0.5)).astype(np.complex64)
     assert rel(f3.run(shape, "c2c", z, True, 1.0).astype(np.complex128), np.fft.fft(z.astype(np.complex128), axis=1)) < 1e-6 * np.log2(n)
+
+
+@pytest.mark.parametrize("shape,kind", [((16, 16, 8, 16), "r2c"), ((18, 18, 6, 18), "r2c"), ((10, 10, 5, 10), "r2c"),
+                                        ((8, 16, 16, 16), "c2r"), ((6, 18, 18, 18), "c2r"), ((5, 10, 10, 10), "c2r"),
+                                        ((16, 16, 8, 16), "c2c")])
+def test_second_exchange_buffer(shape, kind):
+    """DB variant (two barriers per row): 9 rows over 2 CTAs, repeated, since a missing barrier shows up as a race."""
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(5 * n)
+    for rep in range(3):
+        if kind == "r2c":
+            x = rng.random((9, 2 * n)) - 0.5
+            want = ref_r2c(x, True, 1.0)
+        elif kind == "c2r":
+            x = np.fft.rfft(rng.random((9, 2 * n)) - 0.5, axis=1)
+            want = ref_c2r(x, 2 * n, False, 1.0)
+        else:
+            x = rng.random((9, n)) - 0.5 + 1j * (rng.random((9, n)) - 0.5)
+            want = np.fft.fft(x, axis=1)
+        got = f3.run(shape, kind, x, True if kind != "c2r" else False, 1.0, pair=kind != "c2c", ctas=2, double_buffer=True)
+        for r in range(9):
+            assert rel(got[r], want[r]) < 2e-15 * np.log2(n) * 4, (rep, r)
