@@ -848,6 +848,12 @@ inline bool blue_bf_early() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_BF_EARLY"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
+// IMPULSE_FFT_BLUE_FOUR=1: the 8192-point work array on the four-pass core (512 threads x 16 points, 16 warps per SM).
+// Validated under the thread-level emulation only, not yet measured on the B200: off by default.
+inline bool blue_four_pass() {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_FOUR"); return e ? atoi(e) : 0; }();
+  return v != 0;
+}
 template <typename T, int R1, int R2, int R3, int E>
 int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
   using F = Fft3<T, R1, R2, R3, E>;
@@ -859,6 +865,7 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
   typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, uint32_t, uint32_t, const cx<T> *, const cx<T> *,
                          const cx<T> *, const cx<T> *, const cx<T> *, T, unsigned int *);
   kern_t k = nullptr;
+  bool four = false;
   switch (kind * 2 + (bwd ? 1 : 0)) {
     case 0: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, false>; break;
     case 1: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, true>; break;
@@ -889,13 +896,38 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
         }
         g_last_kernel = "fastblue_kernel<double,16,16,32,E32>+bk_smem+bf_early";
       }
+      if (blue_four_pass()) {
+        four = true;
+        if (bfe) {
+          switch (kind * 2 + (bwd ? 1 : 0)) {
+            case 0: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2C, false, true, true, true>; break;
+            case 1: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2C, true, true, true, true>; break;
+            case 2: k = fastblue_kernel<T, 16, 16, 32, 16, BL_R2C_PAIR, false, true, true, true>; break;
+            case 3: k = fastblue_kernel<T, 16, 16, 32, 16, BL_R2C_PAIR, true, true, true, true>; break;
+            case 4: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2R_PAIR, false, true, true, true>; break;
+            default: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2R_PAIR, true, true, true, true>; break;
+          }
+          g_last_kernel = "fastblue_kernel<double,16,16,16,2,E16>+bk_smem+bf_early";
+        } else {
+          switch (kind * 2 + (bwd ? 1 : 0)) {
+            case 0: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2C, false, true, false, true>; break;
+            case 1: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2C, true, true, false, true>; break;
+            case 2: k = fastblue_kernel<T, 16, 16, 32, 16, BL_R2C_PAIR, false, true, false, true>; break;
+            case 3: k = fastblue_kernel<T, 16, 16, 32, 16, BL_R2C_PAIR, true, true, false, true>; break;
+            case 4: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2R_PAIR, false, true, false, true>; break;
+            default: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2R_PAIR, true, true, false, true>; break;
+          }
+          g_last_kernel = "fastblue_kernel<double,16,16,16,2,E16>+bk_smem";
+        }
+      }
     }
   }
+  const int threads = four ? Fft4_8192<T>::TT : F::TT;
   // the dynamic shared-memory size depends on L when the chirp table is resident: always raise the limit to the maximum
   const size_t smem_max = bks ? (size_t)227 * 1024 : smem;
   if (smem > smem_max) return (int)cudaErrorInvalidValue;
-  static PerDeviceFlag flags[18];
-  bool &configured_here = flags[(bfe ? 12 : bks ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
+  static PerDeviceFlag flags[30];
+  bool &configured_here = flags[(four ? 18 + (bfe ? 6 : 0) : bfe ? 12 : bks ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
   if (!configured_here) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return (int)e;
@@ -905,7 +937,7 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
   }
   const uint64_t units = kind == BL_C2C ? J.n_lines : (J.n_lines + 1) / 2;
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, F::TT, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem);
   if (per_sm < 1) per_sm = 1;
   uint64_t grid = units;
   const uint64_t cap = (uint64_t)sm_count * per_sm;
@@ -913,7 +945,7 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
   unsigned int *sched = sched_slot();
   if (!sched) return (int)cudaErrorMemoryAllocation;
   if (J.n_lines > 0xfff00000ull) return (int)cudaErrorInvalidValue;
-  k<<<(unsigned)grid, F::TT, smem, s>>>(J.in, J.out, J.n_lines, J.bs_in[0], J.bs_out[0], J.n_seq, J.fb_d, (const cx<T> *)J.f3_tw1,
+  k<<<(unsigned)grid, threads, smem, s>>>(J.in, J.out, J.n_lines, J.bs_in[0], J.bs_out[0], J.n_seq, J.fb_d, (const cx<T> *)J.f3_tw1,
                                          (const cx<T> *)J.f3_tw2, (const cx<T> *)J.bk, (const cx<T> *)J.fb_bf,
                                          (const cx<T> *)J.fb_corr, (T)J.fct, sched);
   return (int)cudaGetLastError();

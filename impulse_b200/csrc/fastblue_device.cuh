@@ -106,19 +106,99 @@ struct Fft3 {
   }
 };
 
+// Four-pass variant of the in-CTA transform for the 8192-point work length: 512 threads x 16 points (16 warps per SM
+// where Fft3<16,16,32,E32> has 8 — the fused Bluestein kernel is bound by load and shared-memory latency, not by
+// arithmetic), radices 16 * 16 * 16 * 2, three exchanges through the one shared buffer.  Same contract as Fft3::run:
+// x[q] <-> n = t + 512*q in, k = t + 512*q out; `buf` free on entry, possibly still being read on return.
+//   pass 1  butterfly i1 = t:                      x[i1 + 512*j]           -> X1[k1*513 + i1]       * W_N^(i1*k1)
+//   pass 2  (k1, i2) = (t % 16, t / 16):           X1[k1][i2 + 32*j]       -> X2[i2*256 + k1+16*k2] * W_N^(16*i2*k2)
+//   pass 3  (klow2, i3) = (t % 256, t / 256):      X2[(i3 + 2*j)][klow2]   -> X3[i3*4096 + klow2+256*k3] * W_32^(i3*k3)
+//   pass 4  klow3 = t + 512*m (m < 8), radix 2:    X3[0|1][klow3]          -> k = klow3 + 4096*k4 = t + 512*(m + 8*k4)
+// Tables: the ones of the 16*16*32 three-pass shape (tw1[16][512], tw2[16][32]).  Every shared-memory access has
+// consecutive threads on consecutive elements (pass-2 reads: stride 513 = 1 mod 8) — conflict-free.
+template <typename T>
+struct Fft4_8192 {
+  static constexpr int N = 8192, E = 16, TT = 512, M1 = 512, P1 = 513, BUFN = 16 * P1;
+  static constexpr bool TW1_REGS = true;
+  template <bool MUL = false>
+  static __device__ __forceinline__ void run(cx<T> (&x)[16], cx<T> *buf, const cx<T> *__restrict__ /*tw1*/,
+                                             const cx<T> *s_tw2, const cx<T> (&twA)[3], const cx<T> (&twB)[3], int t,
+                                             const cx<T> *__restrict__ mul = nullptr) {
+    // ---- pass 1
+    RegFFT<T, 16>::run(x);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      const int a = k >> 2, b = k & 3;
+      if (a == 0) x[k] = cmul(x[k], twB[b - 1]);
+      else if (b == 0) x[k] = cmul(x[k], twA[a - 1]);
+      else x[k] = cmul(x[k], cmul(twA[a - 1], twB[b - 1]));
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) buf[k * P1 + t] = x[k];
+    __syncthreads();
+    // ---- pass 2
+    const int k1 = t % 16, i2 = t / 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = buf[k1 * P1 + i2 + 32 * j];
+    RegFFT<T, 16>::run(x);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) x[k] = cmul(x[k], s_tw2[k * 32 + i2]);
+    __syncthreads();   // X2 aliases X1
+#pragma unroll
+    for (int k = 0; k < 16; ++k) buf[i2 * 256 + k1 + 16 * k] = x[k];
+    __syncthreads();
+    // ---- pass 3
+    const int klow2 = t % 256, i3 = t / 256;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = buf[(i3 + 2 * j) * 256 + klow2];
+    RegFFT<T, 16>::run(x);
+    if (i3) {
+#pragma unroll
+      for (int k = 1; k < 16; ++k) x[k] = RootSel<T, 32>::run(x[k], k);
+    }
+    __syncthreads();   // X3 aliases X2
+#pragma unroll
+    for (int k = 0; k < 16; ++k) buf[i3 * 4096 + klow2 + 256 * k] = x[k];
+    // the row registers are free here: with MUL, all 16 multipliers are requested before the barrier and the radix-2 pass
+    cx<T> w[MUL ? 16 : 1];
+    if constexpr (MUL) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) w[q] = __ldg(mul + t + TT * q);
+    }
+    __syncthreads();
+    // ---- pass 4
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const cx<T> a = buf[t + TT * m], b = buf[4096 + t + TT * m];
+      cx<T> s0 = cadd(a, b), s1 = csub(a, b);
+      if constexpr (MUL) {
+        s0 = cmul(s0, w[m]); s1 = cmul(s1, w[MUL ? m + 8 : 0]);
+        s0.y = -s0.y; s1.y = -s1.y;
+      }
+      x[m] = s0;
+      x[m + 8] = s1;
+    }
+  }
+};
+
+template <typename T, int R1, int R2, int R3, int E, bool FOUR> struct FastBlueCore { using type = Fft3<T, R1, R2, R3, E>; };
+template <typename T, int R1, int R2, int R3, int E> struct FastBlueCore<T, R1, R2, R3, E, true> { using type = Fft4_8192<T>; };
+
 enum { BL_C2C = 0, BL_R2C_PAIR = 1, BL_C2R_PAIR = 2 };
 constexpr int kBlueMaxDef = 16;  // largest supported deficiency d
 
 // BKS: the chirp table b_k (L entries, used before the first and after the second transform of every unit) is
 // copied to shared memory once per CTA instead of being streamed from L2 twice per unit.
 // BFE: FFT(b)/M is multiplied in inside the first transform's last pass, half of it requested ahead of the butterfly.
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool BKS = false, bool BFE = false>
+// FOUR: the 8192-point work array on Fft4_8192 (instantiate with R1,R2,R3 = 16,16,32 and E = 16: 512 threads).
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool BKS = false, bool BFE = false, bool FOUR = false>
 __global__ void __launch_bounds__((R1 * R2 * R3) / E, 1)
 fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
                 uint32_t L, uint32_t d, const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2,
                 const cx<T> *__restrict__ bk, const cx<T> *__restrict__ bf, const cx<T> *__restrict__ corr, T fct,
                 unsigned int *__restrict__ sched) {
-  using F = Fft3<T, R1, R2, R3, E>;
+  using F = typename FastBlueCore<T, R1, R2, R3, E, FOUR>::type;
+  static_assert(F::TT * E == R1 * R2 * R3, "core / launch shape mismatch");
   constexpr int TT = F::TT, M1 = F::M1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);

@@ -44,7 +44,7 @@ struct HostAlloc : TableAlloc {
 HostAlloc g_alloc;
 PlanCache *g_cache = nullptr;
 
-template <int R3, int E, int KIND, bool BWD, bool BKS, bool BFE>
+template <int R3, int E, int KIND, bool BWD, bool BKS, bool BFE, bool FOUR = false>
 int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
   constexpr int M = 16 * 16 * R3, TT = M / E;
   if (!g_cache) g_cache = new PlanCache(&g_alloc);
@@ -65,7 +65,7 @@ int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, in
     for (int t = 0; t < TT; ++t)
       th.emplace_back([&, t] {
         threadIdx.x = (unsigned)t;
-        fastblue_kernel<double, 16, 16, R3, E, KIND, BWD, BKS, BFE>(in, out, nrows, rs_in, rs_out, L, d, (const cx<double> *)tw1, (const cx<double> *)tw2,
+        fastblue_kernel<double, 16, 16, R3, E, KIND, BWD, BKS, BFE, FOUR>(in, out, nrows, rs_in, rs_out, L, d, (const cx<double> *)tw1, (const cx<double> *)tw2,
                                                                     (const cx<double> *)eng->d_bk, (const cx<double> *)bf,
                                                                     (const cx<double> *)corr, fct, sched);
       });
@@ -75,9 +75,9 @@ int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, in
   return 0;
 }
 
-template <int R3, int E, bool BKS, bool BFE>
+template <int R3, int E, bool BKS, bool BFE, bool FOUR = false>
 int by_kind(int kind, int bwd, uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
-#define GO(K) (bwd ? run<R3, E, K, true, BKS, BFE>(L, in, out, nrows, rs_in, rs_out, fct, ctas) : run<R3, E, K, false, BKS, BFE>(L, in, out, nrows, rs_in, rs_out, fct, ctas))
+#define GO(K) (bwd ? run<R3, E, K, true, BKS, BFE, FOUR>(L, in, out, nrows, rs_in, rs_out, fct, ctas) : run<R3, E, K, false, BKS, BFE, FOUR>(L, in, out, nrows, rs_in, rs_out, fct, ctas))
   if (kind == BL_C2C) return GO(BL_C2C);
   if (kind == BL_R2C_PAIR) return GO(BL_R2C_PAIR);
   return GO(BL_C2R_PAIR);
@@ -87,7 +87,7 @@ int by_kind(int kind, int bwd, uint32_t L, const void *in, void *out, uint64_t n
 
 extern "C" {
 // kind: 0 c2c, 1 r2c (row pairs), 2 c2r (row pairs); flags: 1 = chirp table in shared memory, 2 = multipliers inside the
-// first transform's last pass; row strides in elements of the row's own type (LineJob::bs_in / bs_out)
+// first transform's last pass, 4 = four-pass core (512 threads); row strides in elements of the row's own type (LineJob::bs_in / bs_out)
 int emu_fastblue(int kind, int bwd, int flags, uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out,
                  double fct, unsigned ctas) {
   const uint32_t need = 2 * L - 1;
@@ -95,6 +95,10 @@ int emu_fastblue(int kind, int bwd, int flags, uint32_t L, const void *in, void 
   if (need <= 2048 + 8) return by_kind<8, 16, false, false>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
   if (need <= 4096 + 8) return by_kind<16, 16, false, false>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
   if (need > 8192 + 8) return -1;
+  if (flags & 4) {   // four-pass core: 512 threads x 16 points
+    if (bfe) return by_kind<32, 16, true, true, true>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
+    return by_kind<32, 16, true, false, true>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
+  }
   if (bks && bfe) return by_kind<32, 32, true, true>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
   if (bks) return by_kind<32, 32, true, false>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
   return by_kind<32, 32, false, false>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);

@@ -38,7 +38,7 @@ def lib():
     return _lib
 
 
-def run(kind, x, length, forward=True, fct=1.0, bk_smem=False, bf_early=False, ctas=2):
+def run(kind, x, length, forward=True, fct=1.0, bk_smem=False, bf_early=False, ctas=2, four_pass=False):
     """x = [rows, L] complex (c2c), [rows, L] real (r2c) or [rows, L//2+1] complex (c2r); float64 only.
     `forward` has the reference's meaning (pocketfft_hdronly.h:3125-3250)."""
     x = np.ascontiguousarray(x)
@@ -52,7 +52,7 @@ def run(kind, x, length, forward=True, fct=1.0, bk_smem=False, bf_early=False, c
     pad = 64
     flat = np.full(oshape[0] * oshape[1] + 2 * pad, np.nan, odt)
     out = flat[pad:-pad].reshape(oshape)
-    rc = lib().emu_fastblue(KIND[kind], 1 if bwd else 0, (1 if bk_smem else 0) | (2 if bf_early else 0), length, x.ctypes.data,
+    rc = lib().emu_fastblue(KIND[kind], 1 if bwd else 0, (1 if bk_smem else 0) | (2 if bf_early else 0) | (4 if four_pass else 0), length, x.ctypes.data,
                             out.ctypes.data, rows, x.shape[1], out.shape[1], fct, ctas)
     if rc:
         raise RuntimeError(f"emu_fastblue rc={rc}")

@@ -11,7 +11,8 @@ def rel(a, b):
     return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
 
 
-VARIANTS = [dict(), dict(bk_smem=True), dict(bk_smem=True, bf_early=True)]
+VARIANTS = [dict(), dict(bk_smem=True), dict(bk_smem=True, bf_early=True),
+            dict(bk_smem=True, four_pass=True), dict(bk_smem=True, bf_early=True, four_pass=True)]
 
 
 @pytest.mark.parametrize("var", VARIANTS)
