@@ -952,6 +952,38 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
 }
 }  // namespace
 
+// IMPULSE_FFT_FAST4=1: c2c rows of 8192 points (fp64) on the four-pass 512-thread core instead of the three-pass
+// 256-thread kernel.  Validated under the thread-level emulation only, not yet measured: off by default.
+static int fast4_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST4"); v = e ? atoi(e) : 0; }
+  return v;
+}
+static int launch_fast4_8192(const LineJob &J, int sm_count, cudaStream_t s) {
+  using F = Fft4_8192<double>;
+  const size_t smem = sizeof(cx<double>) * ((size_t)F::BUFN + 16 * 32) + 16;
+  const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
+  auto k = bwd ? fast4_8192_kernel<double, true> : fast4_8192_kernel<double, false>;
+  static PerDeviceFlag flags[2];
+  bool &configured = flags[bwd ? 1 : 0].here();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  uint64_t grid = J.n_lines;
+  if (grid > (uint64_t)sm_count) grid = (uint64_t)sm_count;
+  unsigned int *sched = sched_slot();
+  if (!sched) return (int)cudaErrorMemoryAllocation;
+  if (J.n_lines > 0xfff00000ull) return (int)cudaErrorInvalidValue;
+  g_last_kernel = "fast4_8192_kernel<double>";
+  k<<<(unsigned)grid, F::TT, smem, s>>>((const cx<double> *)J.in, (cx<double> *)J.out, J.n_lines, J.bs_in[0], J.bs_out[0],
+                                        (const cx<double> *)J.f3_tw1, (const cx<double> *)J.f3_tw2, J.fct, sched);
+  return (int)cudaGetLastError();
+}
+
 static int fast_variant() {  // IMPULSE_FFT_FAST_VARIANT=1 selects the non-TMA kernel (A/B measurements)
   static int v = -1;
   if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST_VARIANT"); v = e ? atoi(e) : 0; }
@@ -969,6 +1001,8 @@ static int col_lpc16() {
 
 int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (J.fast_id == FAST3_8192_F64 && J.store_mode != ST_R2C_EVEN && J.load_mode != LD_HERM_EVEN && fast4_enabled())
+    return launch_fast4_8192(J, sm_count, s);
   switch (J.fast_id) {
     case FAST2_1024_F64:
       if (fast_variant() == 0) { g_last_kernel = "fast2p_kernel<double,32,32,6>"; return launch_fast2p<double, 32, 32, 6>(J, sm_count, s); }

@@ -181,6 +181,55 @@ struct Fft4_8192 {
   }
 };
 
+// c2c rows of 8192 points on the four-pass core: 512 threads x 16 points, one row per CTA at a time, rows claimed
+// dynamically, the next claimed row pulled into L2 while this one is transformed (as fast3_kernel).
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(512, 1)
+fast4_8192_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nrows, int64_t rs_in, int64_t rs_out,
+                  const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, T fct, unsigned int *__restrict__ sched) {
+  using F = Fft4_8192<T>;
+  constexpr int TT = F::TT, M1 = F::M1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
+  unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + F::BUFN);
+  cx<T> *s_tw2 = reinterpret_cast<cx<T> *>(s_row + 4);   // [16][32]
+  const int t = threadIdx.x;
+  if (t == 0) { s_row[0] = atomicAdd(&sched[0], 1u); s_row[1] = atomicAdd(&sched[0], 1u); }
+  for (int idx = t; idx < 16 * 32; idx += TT) s_tw2[idx] = tw2[idx];
+  cx<T> twA[3], twB[3];
+#pragma unroll
+  for (int a = 1; a < 4; ++a) { twA[a - 1] = tw1[(4 * a) * M1 + t]; twB[a - 1] = tw1[a * M1 + t]; }
+  __syncthreads();
+  for (unsigned it = 0;; ++it) {
+    const uint64_t row = s_row[it & 1];
+    if (row >= nrows) break;
+    if (t == 0) {
+      const uint64_t nxt = s_row[(it + 1) & 1];
+      if (nxt < nrows) prefetch_l2_bulk(in + (int64_t)nxt * rs_in, (uint32_t)(F::N * sizeof(cx<T>)));
+    }
+    cx<T> x[16];
+    const cx<T> *src = in + (int64_t)row * rs_in;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      x[q] = src[t + TT * q];
+      if (BWD) x[q].y = -x[q].y;
+    }
+    F::run(x, buf, tw1, s_tw2, twA, twB, t);   // its first barrier comes after every thread has read s_row[it & 1]
+    if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);
+    cx<T> *dst = out + (int64_t)row * rs_out;
+    const T fy = BWD ? -fct : fct;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) dst[t + TT * q] = mk<T>(x[q].x * fct, x[q].y * fy);
+    __syncthreads();   // pass-4 reads done before the next row's pass-1 writes
+  }
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(&sched[1], 1u);
+    if (done == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
+  }
+}
+
 template <typename T, int R1, int R2, int R3, int E, bool FOUR> struct FastBlueCore { using type = Fft3<T, R1, R2, R3, E>; };
 template <typename T, int R1, int R2, int R3, int E> struct FastBlueCore<T, R1, R2, R3, E, true> { using type = Fft4_8192<T>; };
 

@@ -85,7 +85,38 @@ int by_kind(int kind, int bwd, uint32_t L, const void *in, void *out, uint64_t n
 }
 }  // namespace
 
+namespace {
+template <bool BWD>
+int run_fast4(const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
+  if (!g_cache) g_cache = new PlanCache(&g_alloc);
+  std::string err;
+  const void *tw1 = nullptr, *tw2 = nullptr;
+  if (g_cache->fast3_tables(8192, 16, 16, 32, DT_F64, &tw1, &tw2, &err)) return -3;
+  unsigned sched[2] = {0u, 0u};
+  gridDim.x = ctas;
+  pthread_barrier_init(&g_bar, nullptr, 512);
+  for (unsigned c = 0; c < ctas; ++c) {
+    blockIdx.x = c;
+    std::memset(smem_raw, 0xCD, sizeof(smem_raw));
+    std::vector<std::thread> th;
+    for (int t = 0; t < 512; ++t)
+      th.emplace_back([&, t] {
+        threadIdx.x = (unsigned)t;
+        fast4_8192_kernel<double, BWD>((const cx<double> *)in, (cx<double> *)out, nrows, rs_in, rs_out, (const cx<double> *)tw1,
+                                       (const cx<double> *)tw2, fct, sched);
+      });
+    for (auto &x : th) x.join();
+  }
+  pthread_barrier_destroy(&g_bar);
+  return 0;
+}
+}  // namespace
+
 extern "C" {
+// c2c rows of 8192 points on the four-pass core (fast4_8192_kernel)
+int emu_fast4_8192(int bwd, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
+  return bwd ? run_fast4<true>(in, out, nrows, rs_in, rs_out, fct, ctas) : run_fast4<false>(in, out, nrows, rs_in, rs_out, fct, ctas);
+}
 // kind: 0 c2c, 1 r2c (row pairs), 2 c2r (row pairs); flags: 1 = chirp table in shared memory, 2 = multipliers inside the
 // first transform's last pass, 4 = four-pass core (512 threads); row strides in elements of the row's own type (LineJob::bs_in / bs_out)
 int emu_fastblue(int kind, int bwd, int flags, uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out,

@@ -35,7 +35,24 @@ def lib():
         _lib.emu_fastblue.restype = C.c_int
         _lib.emu_fastblue.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64,
                                       C.c_int64, C.c_double, C.c_uint]
+        _lib.emu_fast4_8192.restype = C.c_int
+        _lib.emu_fast4_8192.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_uint]
     return _lib
+
+
+def run_fast4(x, forward=True, fct=1.0, ctas=2):
+    """c2c rows of 8192 complex128 points through fast4_8192_kernel."""
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    assert x.shape[1] == 8192
+    pad = 64
+    flat = np.full(x.size + 2 * pad, np.nan, np.complex128)
+    out = flat[pad:-pad].reshape(x.shape)
+    rc = lib().emu_fast4_8192(0 if forward else 1, x.ctypes.data, out.ctypes.data, x.shape[0], 8192, 8192, fct, ctas)
+    if rc:
+        raise RuntimeError(f"emu_fast4_8192 rc={rc}")
+    if not (np.isnan(flat[:pad]).all() and np.isnan(flat[-pad:]).all()):
+        raise AssertionError("store outside the output rows")
+    return out.copy()
 
 
 def run(kind, x, length, forward=True, fct=1.0, bk_smem=False, bf_early=False, ctas=2, four_pass=False):

@@ -48,3 +48,10 @@ def test_shorter_work_lengths():
         assert rel(fb.run("r2c", x, L, True, 1.0), np.fft.rfft(x, axis=1)) < 1e-14
         z = rng.random((2, L)) - 0.5 + 1j * (rng.random((2, L)) - 0.5)
         assert rel(fb.run("c2c", z, L, True, 1.0), np.fft.fft(z, axis=1)) < 1e-14
+
+
+def test_c2c_8192_on_the_four_pass_core():
+    rng = np.random.default_rng(4)
+    z = rng.random((5, 8192)) - 0.5 + 1j * (rng.random((5, 8192)) - 0.5)   # 5 rows over 2 CTAs
+    assert rel(fb.run_fast4(z, True, 0.7), np.fft.fft(z, axis=1) * 0.7) < 2e-15 * 13
+    assert rel(fb.run_fast4(z, False, 1.0 / 8192), np.fft.ifft(z, axis=1)) < 2e-15 * 13

@@ -1,6 +1,7 @@
 #!/bin/bash
 # A/B of the variants prepared at the end of round 1 (env-gated, emulation-validated, not yet measured):
 #   IMPULSE_FFT_F3_DB=1      second exchange buffer in the three-pass kernels (two barriers per row instead of four)
+#   IMPULSE_FFT_FAST4=1      c2c rows of 8192 points on the four-pass 512-thread core (config 4's row pass)
 #   IMPULSE_FFT_BLUE_FOUR=1  fused Bluestein on the four-pass core (512 threads x 16 points: 16 warps per SM instead of 8)
 # Parity under the flag first, then throughput on the config 1 / 3 / 5 workloads and a length sweep.
 #   gpurun --timeout 400 -- 'bash tools/ab_round2.sh'
@@ -18,5 +19,12 @@ for mode in 0 1; do
   for wl in r2c_16384x4099_f64 c2r_16384x4099_f64; do
     IMPULSE_FFT_BLUE_FOUR=$mode timeout 120 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu --workload $wl 2>/dev/null | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('four=$mode', '$wl', d['value'], d['ms_per_step'], d['roofline']['kernel'])" | tee -a gpurun_out/ab_blue4.txt
+  done
+done
+IMPULSE_FFT_FAST4=1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "register_kernels or config4 or nd_and_strided" 2>&1 | tail -n 3
+for mode in 0 1; do
+  for wl in c2c_8192x8192_c128 fft2_8192x8192_c128; do
+    IMPULSE_FFT_FAST4=$mode timeout 120 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu --workload $wl 2>/dev/null | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('fast4=$mode', '$wl', d['value'], d['ms_per_step'], d['roofline']['kernel'])" | tee -a gpurun_out/ab_fast4.txt
   done
 done
