@@ -141,6 +141,20 @@ def nd_steps(kind, a_in, a_out, shape, axes, forward=True, layout="hermitian"):
     return rc
 
 
+def nd_fast_ids(kind, a_in, a_out, shape, axes, forward=True, layout="hermitian"):
+    """FastId of every step the planner emits (0 = generic engine, 0xffffffff = elementwise / fold pass)."""
+    L = lib()
+    L.emu_nd_fast_ids.restype = C.c_int
+    dt = 1 if a_in.dtype in (np.float64, np.complex128) else 0
+    n = len(shape)
+    ids = (C.c_uint32 * 16)()
+    rc = L.emu_nd_fast_ids(KIND[kind], dt, LAYOUT[layout], C.c_size_t(n), (C.c_size_t * n)(*shape), (C.c_ssize_t * n)(*a_in.strides),
+                           (C.c_ssize_t * n)(*a_out.strides), C.c_size_t(len(axes)), (C.c_size_t * len(axes))(*axes), int(forward), ids, 16)
+    if rc < 0:
+        raise EmuError(rc, L.emu_last_error().decode())
+    return list(ids[:rc])
+
+
 def plan_info(L_, dtype=1):
     L = lib()
     n_fft = C.c_uint32()

@@ -1,0 +1,70 @@
+"""CPU-only: which specialised kernel the planner selects for the BASELINE configs (and what the A/B switches change).
+A silent fall back to the generic engine would keep every parity test green while costing 3-6x in throughput; this
+pins the selection.  Ids are FastId of impulse_b200/csrc/fft_types.h."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.emu import harness as emu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fast_ids():
+    src = open(os.path.join(ROOT, "impulse_b200", "csrc", "fft_types.h")).read()
+    body = src[src.index("enum FastId"):]
+    body = body[:body.index("};")]
+    return {m.group(1): int(m.group(2)) for m in re.finditer(r"(\w+)\s*=\s*(\d+)", body)}
+
+
+ID = fast_ids()
+
+
+def ids_1d(kind, n, rows, dt=np.float64):
+    cdt = np.complex128 if dt == np.float64 else np.complex64
+    if kind == "c2c":
+        a = b = np.empty((rows, n), cdt)
+    elif kind == "r2c":
+        a, b = np.empty((rows, n), dt), np.empty((rows, n // 2 + 1), cdt)
+    else:
+        a, b = np.empty((rows, n // 2 + 1), cdt), np.empty((rows, n), dt)
+    shape = (rows, n)
+    return emu.nd_fast_ids(kind, a, b, shape, [1], kind != "c2r")
+
+
+def test_baseline_configs_run_on_register_kernels():
+    assert ids_1d("c2c", 1024, 64) == [ID["FAST2_1024_F64"]]                       # config 2
+    assert ids_1d("r2c", 4096, 64) == [ID["FAST3_2048_F64"]]                       # config 1
+    assert ids_1d("r2c", 1000, 64) == [ID["FAST3R_500_F64"]]                       # config 3a
+    assert ids_1d("c2r", 1000, 64) == [ID["FAST3_500_F64"]]
+    assert ids_1d("r2c", 3888, 64) == [ID["FAST3R_1944_F64"]]                      # config 3b
+    assert ids_1d("c2r", 3888, 64) == [ID["FAST3_1944_F64"]]
+    assert ids_1d("r2c", 4099, 64) == [ID["FASTBLUE_8192_F64"]]                    # config 3c
+    assert ids_1d("c2r", 4099, 64) == [ID["FASTBLUE_8192_F64"]]
+    assert ids_1d("c2r", 4096, 64) == [ID["FAST3C_2048_F64"]]
+    assert ids_1d("r2c", 4096, 64, np.float32) == [ID["FAST3_2048_F32"]]           # config 5 rows
+    assert ids_1d("c2r", 4096, 64, np.float32) == [ID["FAST3C_2048_F32"]]
+    assert ids_1d("r2c", 1024, 64) == [ID["FAST3P_512_F64"]] and ids_1d("c2r", 1024, 64) == [ID["FAST3P_512_F64"]]
+    # config 4: fft2 8192 x 8192 = the two launches of the column split (axis 0 first, as general_nd), then the row kernel
+    a = np.empty((8192, 8192), np.complex128)
+    assert emu.nd_fast_ids("c2c", a, a, a.shape, [0, 1], True) == [ID["COL2_64_F64"], ID["COL2_128_F64"], ID["FAST3_8192_F64"]]
+
+
+def test_switches_restore_the_previous_shapes(monkeypatch):
+    monkeypatch.setenv("IMPULSE_FFT_R2C_PAIR", "0")
+    monkeypatch.setenv("IMPULSE_FFT_C2R_PAIR", "0")
+    monkeypatch.setenv("IMPULSE_FFT_F3_512P", "0")
+    assert ids_1d("r2c", 1000, 64) == [ID["FAST3_500_F64"]]
+    assert ids_1d("r2c", 3888, 64) == [ID["FAST3_1944_F64"]]
+    assert ids_1d("c2r", 4096, 64) == [ID["FAST3_2048_F64"]]
+    assert ids_1d("c2r", 2048, 64) == [ID["FAST3R_1024_F64"]]
+    assert ids_1d("r2c", 1024, 64) == [ID["FAST3R_512_F64"]]
+    monkeypatch.setenv("IMPULSE_FFT_NO_FAST", "1")
+    assert ids_1d("c2c", 1024, 64) == [0] and ids_1d("r2c", 1000, 64) == [0]
+
+
+@pytest.mark.parametrize("n", [1536, 3000, 5000, 10000])
+def test_lengths_without_a_register_kernel_use_the_generic_engine(n):
+    assert ids_1d("c2c", n, 16) == [0]
