@@ -23,6 +23,8 @@ struct HostAlloc : TableAlloc {
 HostAlloc g_alloc;
 PlanCache *g_cache = nullptr;
 std::string g_err;
+int g_col_jobs = 0;    // jobs that ran on the column-kernel emulation since the last emu_set_fast_cols()
+int g_fast_cols = 0;   // > 0: run column-kernel jobs on the thread-level emulation (emu_col.cpp); value = pipeline groups + 1
 
 template <typename T> void run_job(const LineJob &J, const LaunchCfg &cfg) {
   std::vector<unsigned char> raw(cfg.smem_bytes + 64, 0xCD);  // poison: catches reads of unwritten slots
@@ -42,15 +44,23 @@ template <typename T> void run_job(const LineJob &J, const LaunchCfg &cfg) {
 }
 }  // namespace
 
+// emu_col.cpp: 0 = ran on an emulated column kernel, 1 = not a column-kernel job, < 0 = error
+int emu_run_col_job(const LineJob &J, unsigned pipe_groups);
+
 static void ensure_cache() {
-  if (g_cache) return;
-  g_cache = new PlanCache(&g_alloc);
-  g_cache->allow_conv_fusion = false;  // the fused convolution pass exists as a register kernel only
+  if (!g_cache) g_cache = new PlanCache(&g_alloc);
+  // the fused convolution pass exists as a register kernel only: plan it only when those kernels are emulated
+  g_cache->allow_conv_fusion = g_fast_cols > 0;
 }
 
 extern "C" {
 
 const char *emu_last_error() { return g_err.c_str(); }
+
+// 0: every job on the generic engine's phase emulation (default); g >= 1: column-kernel jobs on the thread-level
+// emulation of colfast2 / colpipe2 / colconv2, with g - 1 pipeline groups for colpipe2 (the product's default is 2)
+void emu_set_fast_cols(int g) { g_fast_cols = g; g_col_jobs = 0; }
+int emu_col_job_count() { return g_col_jobs; }
 
 // mirrors impulse_fft_nd() of the product ABI, on host memory
 static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
@@ -141,6 +151,11 @@ static int emu_nd_impl(int kind, int dtype, int layout, size_t ndim, const size_
     st.job.out = bufs_out[st.dst] + st.dst_off_bytes;
     st.job.fct = st.takes_fct ? fct : 1.0;
     if (st.takes_umul) st.job.umul = umul; else st.job.umul_mod = 0;
+    if (g_fast_cols > 0) {
+      const int cr = emu_run_col_job(st.job, (unsigned)(g_fast_cols - 1));
+      if (cr < 0) { g_err = "column-kernel emulation failed"; return -100 + cr; }
+      if (cr == 0) { ++g_col_jobs; continue; }
+    }
     if (dtype == DT_F64) run_job<double>(st.job, st.cfg); else run_job<float>(st.job, st.cfg);
   }
   return 0;

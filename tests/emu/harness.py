@@ -8,9 +8,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(HERE, "libimpulse_fft_emu.so")
-SRC = [os.path.join(HERE, "emu.cpp"), os.path.join(ROOT, "impulse_b200", "csrc", "planner.cpp")]
+SRC = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "emu_col.cpp"), os.path.join(ROOT, "impulse_b200", "csrc", "planner.cpp")]
 DEPS = SRC + [os.path.join(ROOT, "impulse_b200", "csrc", f) for f in
-              ("fft_device.cuh", "fft_types.h", "planner.h", "trig_tables.h")]
+              ("fft_device.cuh", "fft_types.h", "planner.h", "trig_tables.h", "col_device.cuh", "fast3_device.cuh")]
 
 KIND = {"c2c": 0, "r2c": 1, "c2r": 2}
 LAYOUT = {"hermitian": 0, "halfcomplex": 1, "fullsym": 2}
@@ -19,7 +19,7 @@ LAYOUT = {"hermitian": 0, "halfcomplex": 1, "fullsym": 2}
 def build():
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in DEPS):
         return
-    cmd = ["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", SO] + SRC
+    cmd = ["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-pthread", "-o", SO] + SRC
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode:
         raise RuntimeError(out.stderr)
@@ -153,6 +153,19 @@ def nd_fast_ids(kind, a_in, a_out, shape, axes, forward=True, layout="hermitian"
     if rc < 0:
         raise EmuError(rc, L.emu_last_error().decode())
     return list(ids[:rc])
+
+
+def set_fast_cols(pipe_groups=None):
+    """None: every job on the generic engine's phase emulation.  An integer g >= 0: column-kernel jobs (strided axes,
+    the four-step split, the fused convolution pass) on the thread-level emulation, colpipe2 with g groups per CTA
+    (0 or 1 = the plain colfast2 kernel; the product default is 2)."""
+    L = lib()
+    L.emu_set_fast_cols(0 if pipe_groups is None else int(pipe_groups) + 1)
+
+
+def col_job_count():
+    """Jobs that ran on the thread-level column-kernel emulation since the last set_fast_cols()."""
+    return int(lib().emu_col_job_count())
 
 
 def plan_info(L_, dtype=1):

@@ -1,0 +1,68 @@
+"""CPU-only check of the column register kernels (colfast2 / colpipe2 / colconv2) through their thread-level host
+emulation (tests/emu/emu_col.cpp), driven by the jobs the product's planner builds: strided axes of N-D transforms,
+both launches of the four-step split, the fused convolution middle pass.  All of these are parity-green on the B200;
+the emulation exists so that the next change to these kernels can be checked before GPU time is spent."""
+import numpy as np
+import pytest
+
+from tests.emu import harness as emu
+
+COL_IDS = set(range(13, 23))         # COL2_* (fft_types.h)
+CONV_IDS = set(range(26, 32))        # COLCONV_*
+
+
+def rel(a, b):
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+@pytest.fixture(autouse=True)
+def _fast_cols_off_afterwards():
+    yield
+    emu.set_fast_cols(None)
+
+
+def rnd(rng, shape, dt):
+    return ((rng.random(shape) - 0.5) + 1j * (rng.random(shape) - 0.5)).astype(dt)
+
+
+@pytest.mark.parametrize("groups", [2, 0])          # 2 = colpipe2 where it applies (product default), 0 = plain colfast2
+@pytest.mark.parametrize("dt,shape,axis", [(np.complex128, (128, 64), 0), (np.complex128, (64, 40), 0), (np.complex64, (256, 48), 0),
+                                            (np.complex128, (3, 64, 32), 1), (np.complex64, (2, 32, 16), 1), (np.complex128, (512, 8), 0)])
+def test_strided_axis(groups, dt, shape, axis):
+    rng = np.random.default_rng(sum(shape))
+    x = rnd(rng, shape, dt)
+    ids = emu.nd_fast_ids("c2c", x, x, shape, [axis], True)
+    assert len(ids) == 1 and ids[0] in COL_IDS, ids
+    emu.set_fast_cols(groups)
+    tol = 2e-15 * 12 if dt == np.complex128 else 2e-6
+    for fwd in (True, False):
+        got = emu.nd("c2c", x, np.empty_like(x), shape, [axis], fwd, 0.5)
+        want = (np.fft.fft(x.astype(np.complex128), axis=axis) if fwd else np.fft.ifft(x.astype(np.complex128), axis=axis) * shape[axis]) * 0.5
+        assert rel(got, want) < tol, (fwd, rel(got, want))
+    assert emu.col_job_count() == 2
+
+
+@pytest.mark.parametrize("dt", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n,rows", [(16384, 1), (16384, 3), (32768, 2)])
+def test_four_step_split_on_the_column_kernels(dt, n, rows):
+    rng = np.random.default_rng(n + rows)
+    x = rnd(rng, (rows, n), dt)
+    ids = emu.nd_fast_ids("c2c", x, x, x.shape, [1], True)
+    assert len(ids) == 2 and all(i in COL_IDS for i in ids), ids      # A: adjacent lines + W_N^(k n2), B: rows in, lines out
+    emu.set_fast_cols(2)
+    got = emu.nd("c2c", x, np.empty_like(x), x.shape, [1], True, 1.0)
+    assert rel(got, np.fft.fft(x.astype(np.complex128), axis=1)) < (2e-15 * 16 if dt == np.complex128 else 3e-6)
+    assert emu.col_job_count() == 2
+
+
+@pytest.mark.parametrize("dt", [np.complex128, np.complex64])
+def test_fused_convolution_middle_pass(dt):
+    rng = np.random.default_rng(9)
+    shape = (2, 1024, 16)                       # axis of 1024 = 32 x 32: pass A, colconv2, pass B
+    x = rnd(rng, shape, dt)
+    m = rnd(rng, (1024, 16), dt)
+    want = np.fft.ifft(np.fft.fft(x.astype(np.complex128), axis=1) * m.astype(np.complex128), axis=1)
+    emu.set_fast_cols(2)
+    got = emu.convolve_axis(x, np.empty_like(x), 1, m.reshape(-1), 1.0 / 1024)
+    assert rel(got, want) < (1e-13 if dt == np.complex128 else 5e-6)
+    assert emu.col_job_count() == 3             # pass A, the fused middle pass, pass B
