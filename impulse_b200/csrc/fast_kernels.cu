@@ -577,7 +577,7 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
         case 4: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, false, true>; break;
         default: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, true, true>; break;
       }
-      g_last_kernel = "fastblue_kernel<double,16,16,32,E32>+bk_smem";
+      g_last_kernel = sizeof(T) == 8 ? "fastblue_kernel<double,16,16,32,E32>+bk_smem" : "fastblue_kernel<float,16,16,32,E32>+bk_smem";
       if (bfe) {
         switch (kind * 2 + (bwd ? 1 : 0)) {
           case 0: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, false, true, true>; break;
@@ -587,8 +587,9 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
           case 4: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, false, true, true>; break;
           default: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2R_PAIR, true, true, true>; break;
         }
-        g_last_kernel = "fastblue_kernel<double,16,16,32,E32>+bk_smem+bf_early";
+        g_last_kernel = sizeof(T) == 8 ? "fastblue_kernel<double,16,16,32,E32>+bk_smem+bf_early" : "fastblue_kernel<float,16,16,32,E32>+bk_smem+bf_early";
       }
+      if constexpr (sizeof(T) == 8) {
       if (blue_four_pass()) {
         four = true;
         if (bfe) {
@@ -613,9 +614,10 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
           g_last_kernel = "fastblue_kernel<double,16,16,16,2,E16>+bk_smem";
         }
       }
+      }
     }
   }
-  const int threads = four ? Fft4_8192<T>::TT : F::TT;
+  const int threads = four ? 512 : F::TT;
   // the dynamic shared-memory size depends on L when the chirp table is resident: always raise the limit to the maximum
   const size_t smem_max = bks ? (size_t)227 * 1024 : smem;
   if (smem > smem_max) return (int)cudaErrorInvalidValue;
@@ -744,6 +746,9 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FASTBLUE_2048_F64: g_last_kernel = "fastblue_kernel<double,16,16,8,E16>"; return launch_fastblue<double, 16, 16, 8, 16>(J, sm_count, s);
     case FASTBLUE_4096_F64: g_last_kernel = "fastblue_kernel<double,16,16,16,E16>"; return launch_fastblue<double, 16, 16, 16, 16>(J, sm_count, s);
     case FASTBLUE_8192_F64: g_last_kernel = "fastblue_kernel<double,16,16,32,E32>"; return launch_fastblue<double, 16, 16, 32, 32>(J, sm_count, s);
+    case FASTBLUE_2048_F32: g_last_kernel = "fastblue_kernel<float,16,16,8,E16>"; return launch_fastblue<float, 16, 16, 8, 16>(J, sm_count, s);
+    case FASTBLUE_4096_F32: g_last_kernel = "fastblue_kernel<float,16,16,16,E16>"; return launch_fastblue<float, 16, 16, 16, 16>(J, sm_count, s);
+    case FASTBLUE_8192_F32: g_last_kernel = "fastblue_kernel<float,16,16,32,E32>"; return launch_fastblue<float, 16, 16, 32, 32>(J, sm_count, s);
     case COLCONV_32_F64: g_last_kernel = "colconv2_kernel<double,8,4,8>"; return launch_colconv2<double, 8, 4, 8>(J, s);
     case COLCONV_64_F64: g_last_kernel = "colconv2_kernel<double,8,8,8>"; return launch_colconv2<double, 8, 8, 8>(J, s);
     case COLCONV_128_F64: g_last_kernel = "colconv2_kernel<double,16,8,8>"; return launch_colconv2<double, 16, 8, 8>(J, s);

@@ -155,6 +155,9 @@ enum FastId : uint32_t {
   FAST3R_1944_F32 = 67,
   FAST3P_512_F64 = 68,   // 8*8*8 with 16 points per thread: r2c AND c2r of 1024 points paired in registers
   FAST3P_512_F32 = 69,
+  FASTBLUE_2048_F32 = 70,  // fused Bluestein in float32 (selected with IMPULSE_FFT_BLUE_F32=1 until measured)
+  FASTBLUE_4096_F32 = 71,
+  FASTBLUE_8192_F32 = 72,
 };
 
 struct Phase {

@@ -601,14 +601,15 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   }
   // fused Bluestein on the register core: complex Bluestein lengths up to 4104 points, and odd real
   // lengths in that range with two rows packed per complex line (Hermitian layout); contiguous rows
-  if (E->blue && f64 && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
+  // (float32: written and emulation-validated, not yet measured on the B200 — IMPULSE_FFT_BLUE_F32=1 selects it)
+  if (E->blue && (f64 || env_int("IMPULSE_FFT_BLUE_F32", 0)) && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
       J->bdim[1] == 1 && J->bdim[2] == 1 && !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_FASTBLUE", 0)) {
     const bool okc = s.kind == KIND_C2C;
     const bool okr = (s.kind == KIND_R2C || s.kind == KIND_C2R) && !even && s.layout == RL_HERMITIAN;
     uint32_t M = 0, r1 = 16, r2 = 16, r3 = 0, id = FAST_NONE;
-    if (2 * L - 1 <= 2048 + 8 && L > 256) { M = 2048; r3 = 8; id = FASTBLUE_2048_F64; }
-    else if (2 * L - 1 <= 4096 + 8 && L > 256) { M = 4096; r3 = 16; id = FASTBLUE_4096_F64; }
-    else if (2 * L - 1 <= 8192 + 8 && L > 256) { M = 8192; r3 = 32; id = FASTBLUE_8192_F64; }
+    if (2 * L - 1 <= 2048 + 8 && L > 256) { M = 2048; r3 = 8; id = f64 ? FASTBLUE_2048_F64 : FASTBLUE_2048_F32; }
+    else if (2 * L - 1 <= 4096 + 8 && L > 256) { M = 4096; r3 = 16; id = f64 ? FASTBLUE_4096_F64 : FASTBLUE_4096_F32; }
+    else if (2 * L - 1 <= 8192 + 8 && L > 256) { M = 8192; r3 = 32; id = f64 ? FASTBLUE_8192_F64 : FASTBLUE_8192_F32; }
     if ((okc || okr) && id != FAST_NONE) {
       rc = fast3_tables(M, r1, r2, r3, s.dtype, &J->f3_tw1, &J->f3_tw2, err);
       if (rc) return rc;

@@ -44,7 +44,7 @@ struct HostAlloc : TableAlloc {
 HostAlloc g_alloc;
 PlanCache *g_cache = nullptr;
 
-template <int R3, int E, int KIND, bool BWD, bool BKS, bool BFE, bool FOUR = false>
+template <typename T, int R3, int E, int KIND, bool BWD, bool BKS, bool BFE, bool FOUR = false>
 int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
   constexpr int M = 16 * 16 * R3, TT = M / E;
   if (!g_cache) g_cache = new PlanCache(&g_alloc);
@@ -52,9 +52,10 @@ int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, in
   const void *tw1 = nullptr, *tw2 = nullptr, *bf = nullptr, *corr = nullptr;
   uint32_t d = 0;
   const Engine1D *eng = nullptr;
-  if (g_cache->fast3_tables(M, 16, 16, R3, DT_F64, &tw1, &tw2, &err)) return -3;
-  if (g_cache->fastblue_tables(L, M, DT_F64, &bf, &corr, &d, &err)) return -4;
-  if (g_cache->status_engine(L, DT_F64, &eng, &err) || !eng->d_bk) return -5;
+  constexpr int DT = sizeof(T) == 8 ? DT_F64 : DT_F32;
+  if (g_cache->fast3_tables(M, 16, 16, R3, DT, &tw1, &tw2, &err)) return -3;
+  if (g_cache->fastblue_tables(L, M, DT, &bf, &corr, &d, &err)) return -4;
+  if (g_cache->status_engine(L, DT, &eng, &err) || !eng->d_bk) return -5;
   unsigned sched[2] = {0u, 0u};
   gridDim.x = ctas;
   pthread_barrier_init(&g_bar, nullptr, TT);
@@ -65,9 +66,8 @@ int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, in
     for (int t = 0; t < TT; ++t)
       th.emplace_back([&, t] {
         threadIdx.x = (unsigned)t;
-        fastblue_kernel<double, 16, 16, R3, E, KIND, BWD, BKS, BFE, FOUR>(in, out, nrows, rs_in, rs_out, L, d, (const cx<double> *)tw1, (const cx<double> *)tw2,
-                                                                    (const cx<double> *)eng->d_bk, (const cx<double> *)bf,
-                                                                    (const cx<double> *)corr, fct, sched);
+        fastblue_kernel<T, 16, 16, R3, E, KIND, BWD, BKS, BFE, FOUR>(in, out, nrows, rs_in, rs_out, L, d, (const cx<T> *)tw1, (const cx<T> *)tw2,
+                                                                     (const cx<T> *)eng->d_bk, (const cx<T> *)bf, (const cx<T> *)corr, (T)fct, sched);
       });
     for (auto &x : th) x.join();
   }
@@ -75,9 +75,9 @@ int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, in
   return 0;
 }
 
-template <int R3, int E, bool BKS, bool BFE, bool FOUR = false>
+template <typename T, int R3, int E, bool BKS, bool BFE, bool FOUR = false>
 int by_kind(int kind, int bwd, uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
-#define GO(K) (bwd ? run<R3, E, K, true, BKS, BFE, FOUR>(L, in, out, nrows, rs_in, rs_out, fct, ctas) : run<R3, E, K, false, BKS, BFE, FOUR>(L, in, out, nrows, rs_in, rs_out, fct, ctas))
+#define GO(K) (bwd ? run<T, R3, E, K, true, BKS, BFE, FOUR>(L, in, out, nrows, rs_in, rs_out, fct, ctas) : run<T, R3, E, K, false, BKS, BFE, FOUR>(L, in, out, nrows, rs_in, rs_out, fct, ctas))
   if (kind == BL_C2C) return GO(BL_C2C);
   if (kind == BL_R2C_PAIR) return GO(BL_R2C_PAIR);
   return GO(BL_C2R_PAIR);
@@ -118,20 +118,29 @@ int emu_fast4_8192(int bwd, const void *in, void *out, uint64_t nrows, int64_t r
   return bwd ? run_fast4<true>(in, out, nrows, rs_in, rs_out, fct, ctas) : run_fast4<false>(in, out, nrows, rs_in, rs_out, fct, ctas);
 }
 // kind: 0 c2c, 1 r2c (row pairs), 2 c2r (row pairs); flags: 1 = chirp table in shared memory, 2 = multipliers inside the
-// first transform's last pass, 4 = four-pass core (512 threads); row strides in elements of the row's own type (LineJob::bs_in / bs_out)
+// first transform's last pass, 4 = four-pass core (512 threads), 8 = float32; row strides in elements of the row's own type (LineJob::bs_in / bs_out)
 int emu_fastblue(int kind, int bwd, int flags, uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out,
                  double fct, unsigned ctas) {
   const uint32_t need = 2 * L - 1;
-  const bool bks = flags & 1, bfe = flags & 2;
-  if (need <= 2048 + 8) return by_kind<8, 16, false, false>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
-  if (need <= 4096 + 8) return by_kind<16, 16, false, false>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
+  const bool bks = flags & 1, bfe = flags & 2, f32 = flags & 8;
+#define ARGS kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas
+  if (f32) {   // float32: the variants the launcher would pick (chirp table in shared memory + early multipliers at 8192)
+    if (need <= 2048 + 8) return by_kind<float, 8, 16, false, false>(ARGS);
+    if (need <= 4096 + 8) return by_kind<float, 16, 16, false, false>(ARGS);
+    if (need > 8192 + 8) return -1;
+    if (bks && bfe) return by_kind<float, 32, 32, true, true>(ARGS);
+    return by_kind<float, 32, 32, false, false>(ARGS);
+  }
+  if (need <= 2048 + 8) return by_kind<double, 8, 16, false, false>(ARGS);
+  if (need <= 4096 + 8) return by_kind<double, 16, 16, false, false>(ARGS);
   if (need > 8192 + 8) return -1;
   if (flags & 4) {   // four-pass core: 512 threads x 16 points
-    if (bfe) return by_kind<32, 16, true, true, true>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
-    return by_kind<32, 16, true, false, true>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
+    if (bfe) return by_kind<double, 32, 16, true, true, true>(ARGS);
+    return by_kind<double, 32, 16, true, false, true>(ARGS);
   }
-  if (bks && bfe) return by_kind<32, 32, true, true>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
-  if (bks) return by_kind<32, 32, true, false>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
-  return by_kind<32, 32, false, false>(kind, bwd, L, in, out, nrows, rs_in, rs_out, fct, ctas);
+  if (bks && bfe) return by_kind<double, 32, 32, true, true>(ARGS);
+  if (bks) return by_kind<double, 32, 32, true, false>(ARGS);
+  return by_kind<double, 32, 32, false, false>(ARGS);
+#undef ARGS
 }
 }

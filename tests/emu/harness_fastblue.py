@@ -56,20 +56,22 @@ def run_fast4(x, forward=True, fct=1.0, ctas=2):
 
 
 def run(kind, x, length, forward=True, fct=1.0, bk_smem=False, bf_early=False, ctas=2, four_pass=False):
-    """x = [rows, L] complex (c2c), [rows, L] real (r2c) or [rows, L//2+1] complex (c2r); float64 only.
+    """x = [rows, L] complex (c2c), [rows, L] real (r2c) or [rows, L//2+1] complex (c2r); float64 or float32.
     `forward` has the reference's meaning (pocketfft_hdronly.h:3125-3250)."""
     x = np.ascontiguousarray(x)
     rows = x.shape[0]
+    f32 = x.dtype in (np.float32, np.complex64)
+    cdt, rdt = (np.complex64, np.float32) if f32 else (np.complex128, np.float64)
     if kind == "c2c":
-        oshape, odt, bwd = (rows, length), np.complex128, not forward
+        oshape, odt, bwd = (rows, length), cdt, not forward
     elif kind == "r2c":
-        oshape, odt, bwd = (rows, length // 2 + 1), np.complex128, not forward
+        oshape, odt, bwd = (rows, length // 2 + 1), cdt, not forward
     else:
-        oshape, odt, bwd = (rows, length), np.float64, forward      # c2r: BWD = "conjugate the input" = forward=True
+        oshape, odt, bwd = (rows, length), rdt, forward      # c2r: BWD = "conjugate the input" = forward=True
     pad = 64
     flat = np.full(oshape[0] * oshape[1] + 2 * pad, np.nan, odt)
     out = flat[pad:-pad].reshape(oshape)
-    rc = lib().emu_fastblue(KIND[kind], 1 if bwd else 0, (1 if bk_smem else 0) | (2 if bf_early else 0) | (4 if four_pass else 0), length, x.ctypes.data,
+    rc = lib().emu_fastblue(KIND[kind], 1 if bwd else 0, (1 if bk_smem else 0) | (2 if bf_early else 0) | (4 if four_pass else 0) | (8 if f32 else 0), length, x.ctypes.data,
                             out.ctypes.data, rows, x.shape[1], out.shape[1], fct, ctas)
     if rc:
         raise RuntimeError(f"emu_fastblue rc={rc}")

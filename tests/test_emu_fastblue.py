@@ -55,3 +55,17 @@ def test_c2c_8192_on_the_four_pass_core():
     z = rng.random((5, 8192)) - 0.5 + 1j * (rng.random((5, 8192)) - 0.5)   # 5 rows over 2 CTAs
     assert rel(fb.run_fast4(z, True, 0.7), np.fft.fft(z, axis=1) * 0.7) < 2e-15 * 13
     assert rel(fb.run_fast4(z, False, 1.0 / 8192), np.fft.ifft(z, axis=1)) < 2e-15 * 13
+
+
+def test_float32():
+    rng = np.random.default_rng(6)
+    for L, var in ((4099, dict(bk_smem=True, bf_early=True)), (4099, dict()), (2051, dict()), (1021, dict())):
+        x = (rng.random((5, L)) - 0.5).astype(np.float32)
+        got = fb.run("r2c", x, L, True, 1.0, **var)
+        assert got.dtype == np.complex64
+        want = np.fft.rfft(x.astype(np.float64), axis=1)
+        assert rel(got.astype(np.complex128), want) < 1e-5 * np.log2(L) / 10
+        back = fb.run("c2r", want.astype(np.complex64), L, False, 1.0 / L, **var)
+        assert rel(back.astype(np.float64), x.astype(np.float64)) < 1e-5 * np.log2(L) / 10
+        z = ((rng.random((3, L)) - 0.5) + 1j * (rng.random((3, L)) - 0.5)).astype(np.complex64)
+        assert rel(fb.run("c2c", z, L, True, 1.0, **var).astype(np.complex128), np.fft.fft(z.astype(np.complex128), axis=1)) < 1e-5 * np.log2(L) / 10

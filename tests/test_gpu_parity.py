@@ -536,8 +536,27 @@ def test_fused_bluestein(ib, torch_mod, checker):
                                                                             device="cuda"), [1]),
                           torch_mod.empty_like(rd), [1], False, 1.0 / n).cpu().numpy()
             assert oracle.max_row_rel_l2(rt, r) <= 2e-15 * np.log2(n), (n, rows)
-    print(sorted(used))
+    # float32: the fused kernel when IMPULSE_FFT_BLUE_F32=1 selects it, the generic engine otherwise — same tolerance
+    used32 = set()
+    for n in (1021, 2051, 4099):
+        for rows in (1, 5, 32):
+            x = rnd(rng, (rows, n), np.complex64)
+            xd = torch_mod.from_numpy(x).cuda()
+            got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], True, 1.0).cpu().numpy()
+            used32.add(ib.last_kernel())
+            assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], True, 1.0)) <= tol(n, np.float32), (n, rows)
+            r = rnd(rng, (rows, n), np.float32)
+            rd = torch_mod.from_numpy(r).cuda()
+            spec = apply_nd(ib, "r2c", rd, torch_mod.empty((rows, n // 2 + 1), dtype=torch_mod.complex64, device="cuda"), [1], True, 1.0)
+            used32.add(ib.last_kernel())
+            want = checker.r2c(r, [1], True, 1.0)
+            assert oracle.max_row_rel_l2(spec.cpu().numpy(), want) <= tol(n, np.float32), (n, rows)
+            back = apply_nd(ib, "c2r", torch_mod.from_numpy(want).cuda(), torch_mod.empty_like(rd), [1], False, 1.0 / n).cpu().numpy()
+            assert oracle.max_row_rel_l2(back, r) <= tol(n, np.float32), (n, rows)
+    print(sorted(used), sorted(used32))
     assert any(k.startswith("fastblue") for k in used)
+    if os.environ.get("IMPULSE_FFT_BLUE_F32", "0") == "1":
+        assert any(k.startswith("fastblue_kernel<float") for k in used32), used32
 
 
 def test_dct_dst(ib, torch_mod, checker):

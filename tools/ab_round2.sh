@@ -2,6 +2,7 @@
 # A/B of the variants prepared at the end of round 1 (env-gated, emulation-validated, not yet measured):
 #   IMPULSE_FFT_F3_DB=1      second exchange buffer in the three-pass kernels (two barriers per row instead of four)
 #   IMPULSE_FFT_FAST4=1      c2c rows of 8192 points on the four-pass 512-thread core (config 4's row pass)
+#   IMPULSE_FFT_BLUE_F32=1   fused Bluestein in float32 (today: generic engine, 3 % of the roofline at 4099)
 #   IMPULSE_FFT_BLUE_FOUR=1  fused Bluestein on the four-pass core (512 threads x 16 points: 16 warps per SM instead of 8)
 # Parity under the flag first, then throughput on the config 1 / 3 / 5 workloads and a length sweep.
 #   gpurun --timeout 400 -- 'bash tools/ab_round2.sh'
@@ -27,4 +28,8 @@ for mode in 0 1; do
     IMPULSE_FFT_FAST4=$mode timeout 120 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu --workload $wl 2>/dev/null | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('fast4=$mode', '$wl', d['value'], d['ms_per_step'], d['roofline']['kernel'])" | tee -a gpurun_out/ab_fast4.txt
   done
+done
+IMPULSE_FFT_BLUE_F32=1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "fused_bluestein or randomized" 2>&1 | tail -n 3
+for mode in 0 1; do
+  IMPULSE_FFT_BLUE_F32=$mode timeout 120 python tools/size_sweep.py --kinds c2c,r2c,c2r --dtypes f32 --lengths 1021,2051,4099 2>&1 | sed "s/^/blue_f32=$mode /" | tee -a gpurun_out/ab_blue_f32.txt
 done
