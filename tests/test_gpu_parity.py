@@ -536,9 +536,10 @@ def test_fused_bluestein(ib, torch_mod, checker):
                                                                             device="cuda"), [1]),
                           torch_mod.empty_like(rd), [1], False, 1.0 / n).cpu().numpy()
             assert oracle.max_row_rel_l2(rt, r) <= 2e-15 * np.log2(n), (n, rows)
-    # float32: the fused kernel when IMPULSE_FFT_BLUE_F32=1 selects it, the generic engine otherwise — same tolerance
+    # float32 instances of the fused kernel: selected (and checked here) with IMPULSE_FFT_BLUE_F32=1 until they are
+    # measured and become the default
     used32 = set()
-    for n in (1021, 2051, 4099):
+    for n in ((1021, 2051, 4099) if os.environ.get("IMPULSE_FFT_BLUE_F32", "0") == "1" else ()):
         for rows in (1, 5, 32):
             x = rnd(rng, (rows, n), np.complex64)
             xd = torch_mod.from_numpy(x).cuda()
