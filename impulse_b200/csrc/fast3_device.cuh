@@ -78,6 +78,8 @@ template <typename T> struct RegFFT<T, 9> { static __device__ __forceinline__ vo
 template <typename T> struct RegFFT<T, 6> { static __device__ __forceinline__ void run(cx<T> (&x)[6]) { Composite<T, 2, 3>::run(x); } };
 template <typename T> struct RegFFT<T, 10> { static __device__ __forceinline__ void run(cx<T> (&x)[10]) { Composite<T, 2, 5>::run(x); } };
 template <typename T> struct RegFFT<T, 18> { static __device__ __forceinline__ void run(cx<T> (&x)[18]) { Composite<T, 2, 9>::run(x); } };
+template <typename T> struct RegFFT<T, 20> { static __device__ __forceinline__ void run(cx<T> (&x)[20]) { Composite<T, 4, 5>::run(x); } };
+template <typename T> struct RegFFT<T, 24> { static __device__ __forceinline__ void run(cx<T> (&x)[24]) { Composite<T, 3, 8>::run(x); } };
 template <typename T> struct RegFFT<T, 64> { static __device__ __forceinline__ void run(cx<T> (&x)[64]) { Composite<T, 8, 8>::run(x); } };
 
 // =================================================================================================

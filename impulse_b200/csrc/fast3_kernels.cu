@@ -178,6 +178,9 @@ int launch_fast3_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2, 7, 0>(J, sm_count, s);
     case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, 7, 1, 3, 0, 3>(J, sm_count, s);
     case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3, 7, 0>(J, sm_count, s);
+    case FAST3_1536_F64: g_last_kernel = "fast3_kernel<double,8,24,8,E24>"; return launch_fast3<double, 8, 24, 8, 24, 4, 7, 5>(J, sm_count, s);
+    case FAST3_2000_F64: g_last_kernel = "fast3_kernel<double,10,20,10,E20>"; return launch_fast3<double, 10, 20, 10, 20, 3, 7, 5>(J, sm_count, s);
+    case FAST3_4000_F64: g_last_kernel = "fast3_kernel<double,10,20,20,E20>"; return launch_fast3<double, 10, 20, 20, 20, 2, 7, 4>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;
   }
 }

@@ -139,6 +139,9 @@ int emu_fast3(int shape, int dtype, int kind, int bwd, int flags, const void *in
   SHAPE(8, 8, 8, 16)
   SHAPE(4, 8, 8, 8)
   SHAPE(10, 10, 10, 10)
+  SHAPE(8, 24, 8, 24)
+  SHAPE(10, 20, 10, 20)
+  SHAPE(10, 20, 20, 20)
 #undef SHAPE
   return -1;
 }

@@ -171,3 +171,19 @@ def test_second_exchange_buffer(shape, kind):
         got = f3.run(shape, kind, x, True if kind != "c2r" else False, 1.0, pair=kind != "c2c", ctas=2, double_buffer=True)
         for r in range(9):
             assert rel(got[r], want[r]) < 2e-15 * np.log2(n) * 4, (rep, r)
+
+
+@pytest.mark.parametrize("shape", [(8, 24, 8, 24), (10, 20, 10, 20), (10, 20, 20, 20)])
+def test_more_mixed_radix_shapes(shape):
+    """1536 = 8*24*8, 2000 = 10*20*10, 4000 = 10*20*20 (and the real rows of twice those lengths)."""
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(n + 9)
+    z = rng.random((3, n)) - 0.5 + 1j * (rng.random((3, n)) - 0.5)
+    assert rel(f3.run(shape, "c2c", z, True, 1.0), np.fft.fft(z, axis=1)) < 2e-15 * np.log2(n) * 4
+    assert rel(f3.run(shape, "c2c", z, False, 1.0 / n), np.fft.ifft(z, axis=1)) < 2e-15 * np.log2(n) * 4
+    x = rng.random((5, 2 * n)) - 0.5
+    pr = e // r3 >= 2
+    assert rel(f3.run(shape, "r2c", x, True, 1.0, pair=pr), ref_r2c(x, True, 1.0)) < 2e-15 * np.log2(n) * 4
+    X = np.fft.rfft(x, axis=1)
+    assert rel(f3.run(shape, "c2r", X, False, 0.5 / n, pair=True), x) < 2e-15 * np.log2(n) * 4

@@ -413,7 +413,8 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
     rng = np.random.default_rng(21)
     used = set()
     for dt, cdt in ((np.float64, np.complex128), (np.float32, np.complex64)):
-        for n in (16, 32, 64, 128, 256, 500, 512, 1000, 1024, 1944, 2048, 4096, 8192):
+        more = (1536, 2000, 4000) if os.environ.get("IMPULSE_FFT_MORE_SHAPES", "0") == "1" else ()   # shapes not yet on by default
+        for n in (16, 32, 64, 128, 256, 500, 512, 1000, 1024, 1944, 2048, 4096, 8192) + more:
             for rows in (1, 37, 301) + ((5000,) if n <= 128 else ()):
                 x = rnd(rng, (rows, n), cdt)
                 xd = torch_mod.from_numpy(x).cuda()
@@ -421,7 +422,7 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
                     got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], fwd, 0.7).cpu().numpy()
                     used.add(ib.last_kernel())
                     assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.7)) <= tol(n, dt), (n, rows, fwd, dt)
-        for n in (32, 64, 128, 256, 512, 1024, 2048, 1000, 3888, 4096, 8192, 16384):
+        for n in (32, 64, 128, 256, 512, 1024, 2048, 1000, 3888, 4096, 8192, 16384) + tuple(2 * m for m in more):
             for rows in (1, 53) + ((1001,) if n <= 2048 else ()):
                 r = rnd(rng, (rows, n), dt)
                 rd = torch_mod.from_numpy(r).cuda()
