@@ -240,6 +240,23 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
   const NdPlan &nd = p->nd;
   if (nd.empty) return 0;
   const bool inplace = (in == out);
+  // IMPULSE_FFT_ZEROCOPY=1 (prepared, not yet measured): a single-launch plan on PINNED host buffers (cudaHostAlloc /
+  // cudaHostRegister memory is mapped into the device's address space under UVA) runs the kernel directly on them, so
+  // the row loads and stores cross PCIe themselves — no staging copies, no pipeline fill and drain.  Pageable
+  // memory, multi-launch plans and everything else take the staged paths below.
+  static const bool zero_copy = [] { const char *e = std::getenv("IMPULSE_FFT_ZEROCOPY"); return e && std::atoi(e) != 0; }();
+  if (zero_copy && nd.steps.size() == 1 && !nd.steps[0].aux && !nd.steps[0].combine && nd.tmp_bytes == 0 && nd.tmp2_bytes == 0 &&
+      nd.tmp3_bytes == 0 && nd.tmp4_bytes == 0) {
+    cudaPointerAttributes ai, ao;
+    if (cudaPointerGetAttributes(&ai, in) == cudaSuccess && cudaPointerGetAttributes(&ao, out) == cudaSuccess &&
+        ai.type == cudaMemoryTypeHost && ao.type == cudaMemoryTypeHost && ai.devicePointer && ao.devicePointer) {
+      int rc = run_device(p, ai.devicePointer, ao.devicePointer, fct, nullptr);
+      cudaError_t se = cudaStreamSynchronize(nullptr);
+      if (!rc && se != cudaSuccess) rc = cuda_fail(se, "zero-copy sync");
+      return rc;
+    }
+    cudaGetLastError();
+  }
   // ---- try the chunked pipeline
   if (nd.steps.size() == 1 && !nd.steps[0].aux && !nd.steps[0].combine && nd.tmp_bytes == 0 && nd.tmp2_bytes == 0 &&
       nd.tmp3_bytes == 0 && nd.tmp4_bytes == 0) {

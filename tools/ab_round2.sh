@@ -2,6 +2,7 @@
 # A/B of the variants prepared at the end of round 1 (env-gated, emulation-validated, not yet measured):
 #   IMPULSE_FFT_F3_DB=1      second exchange buffer in the three-pass kernels (two barriers per row instead of four)
 #   IMPULSE_FFT_FAST4=1      c2c rows of 8192 points on the four-pass 512-thread core (config 4's row pass)
+#   IMPULSE_FFT_ZEROCOPY=1     host-pointer calls on pinned memory run the kernel directly on the mapped host buffers (e2e)
 #   IMPULSE_FFT_MORE_SHAPES=1  three-pass shapes for 1536 / 2000 / 4000 complex points (today: generic engine)
 #   IMPULSE_FFT_BLUE_F32=1   fused Bluestein in float32 (today: generic engine, 3 % of the roofline at 4099)
 #   IMPULSE_FFT_BLUE_FOUR=1  fused Bluestein on the four-pass core (512 threads x 16 points: 16 warps per SM instead of 8)
@@ -37,4 +38,9 @@ done
 IMPULSE_FFT_MORE_SHAPES=1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "register_kernels or c2c_lengths" 2>&1 | tail -n 3
 for mode in 0 1; do
   IMPULSE_FFT_MORE_SHAPES=$mode timeout 120 python tools/size_sweep.py --kinds c2c,r2c,c2r --dtypes f64 --lengths 1536,2000,3072,4000,8000 2>&1 | sed "s/^/more_shapes=$mode /" | tee -a gpurun_out/ab_more_shapes.txt
+done
+IMPULSE_FFT_ZEROCOPY=1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "host_staging or highlevel or golden" 2>&1 | tail -n 3
+for mode in 0 1; do
+  IMPULSE_FFT_ZEROCOPY=$mode timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu 2>/dev/null | \
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('zerocopy=$mode e2e', d['e2e'])" | tee -a gpurun_out/ab_zerocopy.txt
 done
