@@ -21,5 +21,6 @@ struct PerDeviceFlag {
 unsigned int *sched_slot();
 // the three-pass register kernels (fast3_kernels.cu); returns cudaError_t, cudaErrorInvalidValue for other ids
 int launch_fast3_job(const LineJob &job, int sm_count, void *stream);
+int launch_fastblue_job(const LineJob &job, int sm_count, void *stream);   // fastblue_kernels.cu
 
 }  // namespace impulse
