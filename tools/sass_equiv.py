@@ -7,7 +7,9 @@ refactoring that should not change generated code:
 
 Kernels are matched by mangled name; trailing boolean template parameters that the new build added with value false
 (`ELb0` before the closing `EEEv`) are stripped.  Used at the end of round 1 after the register kernels moved into
-headers and a translation unit of their own: 352 kernels, 352 identical instruction streams."""
+headers and a translation unit of their own: 352 kernels, 352 identical instruction streams; and again when the fused
+Bluestein launcher moved from fast_kernels.cu to fastblue_kernels.cu (old fast_kernels.cu vs the two new files: 232 of
+232 identical)."""
 import re
 import subprocess
 import sys
