@@ -50,7 +50,7 @@ EXPORTS = [
     "impulse_fft_plan_get_info", "impulse_fft_launch_count", "impulse_fft_last_error", "impulse_fft_version",
     "impulse_fft_last_kernel",
     "impulse_fft_cmul", "impulse_fft_transpose", "impulse_fft_copy2d", "impulse_fft_cols_from_parts", "impulse_fft_enable_peer_access", "impulse_fft_ipc_alloc", "impulse_fft_ipc_free",
-    "impulse_fft_ipc_open", "impulse_fft_ipc_close",
+    "impulse_fft_ipc_open", "impulse_fft_ipc_close", "impulse_fft_bind_host_to_device",
     # include/pocketfft.h
     "make_cfft_plan", "destroy_cfft_plan", "cfft_backward", "cfft_forward", "cfft_length",
     "make_rfft_plan", "destroy_rfft_plan", "rfft_backward", "rfft_forward", "rfft_length",
@@ -121,6 +121,8 @@ def lib() -> C.CDLL:
     L.impulse_fft_cols_from_parts.restype = C.c_int
     L.impulse_fft_cols_from_parts.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp,
                                               C.c_size_t, C.c_int, C.c_double, vp]
+    L.impulse_fft_bind_host_to_device.restype = C.c_int
+    L.impulse_fft_bind_host_to_device.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.make_cfft_plan.restype = vp
     L.make_cfft_plan.argtypes = [C.c_size_t]
     L.make_rfft_plan.restype = vp
@@ -149,3 +151,11 @@ def last_kernel() -> str:
 
 def launch_count() -> int:
     return int(lib().impulse_fft_launch_count())
+
+
+def bind_host_to_device(device: int):
+    """Bind the calling thread to the CPUs of the NUMA node `device` hangs off (pinned buffers allocated afterwards are
+    local to that GPU).  Returns the node, or None when the box exposes no NUMA information."""
+    node = C.c_int(-1)
+    check(lib().impulse_fft_bind_host_to_device(int(device), C.byref(node)))
+    return None if node.value < 0 else int(node.value)

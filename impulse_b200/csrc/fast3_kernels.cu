@@ -27,11 +27,14 @@ inline bool f3_prefetch_enabled(bool dflt) {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_F3_PF"); return e ? atoi(e) : -1; }();
   return v < 0 ? dflt : v != 0;
 }
-// IMPULSE_FFT_F3_DB=1: second exchange buffer (two barriers per row instead of four) where instantiated.  Not yet
-// measured on the B200 (validated under the thread-level emulation only), hence off by default.
-inline bool f3_double_buffer() {
-  static const int v = [] { const char *e = getenv("IMPULSE_FFT_F3_DB"); return e ? atoi(e) : 0; }();
-  return v != 0;
+// Second exchange buffer (two barriers per row instead of four) where instantiated.  Measured on the B200
+// (profiles/r02_ab_round2.txt): r2c 4096 f64 4.67 -> 5.18 TB/s, c2r 4096 4.77 -> 4.94, the fp32 rows of the same
+// shapes +2-4 %, 1000-point real rows +1 %; r2c 3888 LOSES 7 % (the 18-point shape drops a resident CTA) and c2c
+// 2048 f64 2 %.  So it is the default only for the kinds a shape lists in DBDEF; IMPULSE_FFT_F3_DB=0 / 1 forces it
+// off / on for every instantiated variant (A/B runs).
+inline bool f3_double_buffer(bool dflt) {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_F3_DB"); return e ? atoi(e) : -1; }();
+  return v < 0 ? dflt : v != 0;
 }
 inline bool c2r_pair_enabled() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_C2R_PAIR"); return e ? atoi(e) : 1; }();
@@ -44,7 +47,8 @@ inline bool c2r_pair_enabled() {
 // PFK:   kinds for which the register-prefetch variant is instantiated (same bits as KINDS; real kinds: pair only)
 // PFDEF: kinds for which it is the default
 // DBK:   kinds for which the second-exchange-buffer variant is instantiated (real kinds: pair only)
-template <typename T, int R1, int R2, int R3, int E, int MINB, int KINDS = 7, int PAIRS = 0, int PFK = 0, int PFDEF = 0, int DBK = 0>
+// DBDEF: kinds for which it is the default
+template <typename T, int R1, int R2, int R3, int E, int MINB, int KINDS = 7, int PAIRS = 0, int PFK = 0, int PFDEF = 0, int DBK = 0, int DBDEF = 0>
 int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1, S = sizeof(T) == 8 ? 8 : 16;
   constexpr int P1 = ((M1 + S - 1) / S) * S + 1;
@@ -96,7 +100,7 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
   }
   bool db = false;
   if constexpr (DBK != 0) {
-    if (f3_double_buffer()) {
+    if (f3_double_buffer((DBDEF & (1 << kind)) != 0)) {
       if constexpr ((DBK & 1) != 0 && (KINDS & 1) != 0) {
         if (kind == F3_C2C) { db = true; k = bwd ? (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, true, MINB, false, false, true> : (kern_t)fast3_kernel<T, R1, R2, R3, E, F3_C2C, false, MINB, false, false, true>; }
       }
@@ -154,18 +158,18 @@ int launch_fast3_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3R_1024_F32: g_last_kernel = "fast3_kernel<float,16,8,8,E16>"; return launch_fast3<float, 16, 8, 8, 16, 12, 6, 1>(J, sm_count, s);
     case FAST3_2048_F64:
       if (f3_minb4()) { g_last_kernel = "fast3_kernel<double,16,16,8,E16,minb4>"; return launch_fast3<double, 16, 16, 8, 16, 4, 7, 1, 3, 1>(J, sm_count, s); }
-      g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3, 1, 3>(J, sm_count, s);
+      g_last_kernel = "fast3_kernel<double,16,16,8,E16>"; return launch_fast3<double, 16, 16, 8, 16, 3, 7, 1, 3, 1, 3, 2>(J, sm_count, s);
     case FAST3_4096_F64: g_last_kernel = "fast3_kernel<double,16,16,16,E16>"; return launch_fast3<double, 16, 16, 16, 16, 2, 7, 0>(J, sm_count, s);
     case FAST3_8192_F64: g_last_kernel = "fast3_kernel<double,16,16,32,E32>"; return launch_fast3<double, 16, 16, 32, 32, 1, 7, 0>(J, sm_count, s);
-    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8, 7, 4, 0, 0, 4>(J, sm_count, s);
+    case FAST3_500_F64: g_last_kernel = "fast3_kernel<double,5,10,10,E10>"; return launch_fast3<double, 5, 10, 10, 10, 8, 7, 4, 0, 0, 4, 4>(J, sm_count, s);
     case FAST3_1944_F64: g_last_kernel = "fast3_kernel<double,6,18,18,E18>"; return launch_fast3<double, 6, 18, 18, 18, 4, 7, 4, 0, 0, 4>(J, sm_count, s);
     case FAST3_1000_F64: g_last_kernel = "fast3_kernel<double,10,10,10,E10>"; return launch_fast3<double, 10, 10, 10, 10, 5, 7, 0>(J, sm_count, s);
-    case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10>"; return launch_fast3<double, 10, 10, 5, 10, 8, 2, 2, 2, 0, 2>(J, sm_count, s);
+    case FAST3R_500_F64: g_last_kernel = "fast3_kernel<double,10,10,5,E10>"; return launch_fast3<double, 10, 10, 5, 10, 8, 2, 2, 2, 0, 2, 2>(J, sm_count, s);
     case FAST3R_1944_F64: g_last_kernel = "fast3_kernel<double,18,18,6,E18>"; return launch_fast3<double, 18, 18, 6, 18, 4, 2, 2, 0, 0, 2>(J, sm_count, s);
     case FAST3C_2048_F64:
       if (f3_minb4()) { g_last_kernel = "fast3_kernel<double,8,16,16,E16,minb4>"; return launch_fast3<double, 8, 16, 16, 16, 4, 4, 8>(J, sm_count, s); }
-      g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8, 0, 0, 4>(J, sm_count, s);
-    case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8, 0, 0, 4>(J, sm_count, s);
+      g_last_kernel = "fast3_kernel<double,8,16,16,E16>"; return launch_fast3<double, 8, 16, 16, 16, 3, 4, 8, 0, 0, 4, 4>(J, sm_count, s);
+    case FAST3C_2048_F32: g_last_kernel = "fast3_kernel<float,8,16,16,E16>"; return launch_fast3<float, 8, 16, 16, 16, 4, 4, 8, 0, 0, 4, 4>(J, sm_count, s);
     case FAST3C_1024_F64: g_last_kernel = "fast3_kernel<double,8,8,16,E16>"; return launch_fast3<double, 8, 8, 16, 16, 8, 4, 8>(J, sm_count, s);
     case FAST3C_1024_F32: g_last_kernel = "fast3_kernel<float,8,8,16,E16>"; return launch_fast3<float, 8, 8, 16, 16, 12, 4, 8>(J, sm_count, s);
     case FAST3_500_F32: g_last_kernel = "fast3_kernel<float,5,10,10,E10>"; return launch_fast3<float, 5, 10, 10, 10, 16, 7, 4>(J, sm_count, s);
@@ -176,7 +180,7 @@ int launch_fast3_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3P_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E16>"; return launch_fast3<double, 8, 8, 8, 16, 16, 6, 10>(J, sm_count, s);
     case FAST3P_512_F32: g_last_kernel = "fast3_kernel<float,8,8,8,E16>"; return launch_fast3<float, 8, 8, 8, 16, 24, 6, 10>(J, sm_count, s);
     case FAST3_8192_F32: g_last_kernel = "fast3_kernel<float,16,16,32,E32>"; return launch_fast3<float, 16, 16, 32, 32, 2, 7, 0>(J, sm_count, s);
-    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, 7, 1, 3, 0, 3>(J, sm_count, s);
+    case FAST3_2048_F32: g_last_kernel = "fast3_kernel<float,16,16,8,E16>"; return launch_fast3<float, 16, 16, 8, 16, 4, 7, 1, 3, 0, 3, 3>(J, sm_count, s);
     case FAST3_4096_F32: g_last_kernel = "fast3_kernel<float,16,16,16,E16>"; return launch_fast3<float, 16, 16, 16, 16, 3, 7, 0>(J, sm_count, s);
     case FAST3_1536_F64: g_last_kernel = "fast3_kernel<double,8,24,8,E24>"; return launch_fast3<double, 8, 24, 8, 24, 4, 7, 5>(J, sm_count, s);
     case FAST3_2000_F64: g_last_kernel = "fast3_kernel<double,10,20,10,E20>"; return launch_fast3<double, 10, 20, 10, 20, 3, 7, 5>(J, sm_count, s);

@@ -27,10 +27,11 @@ inline bool blue_bf_early() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_BF_EARLY"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
-// IMPULSE_FFT_BLUE_FOUR=1: the 8192-point work array on the four-pass core (512 threads x 16 points, 16 warps per SM).
-// Validated under the thread-level emulation only, not yet measured on the B200: off by default.
+// The 8192-point work array on the four-pass core (512 threads x 16 points, 16 warps per SM instead of 8).  Measured
+// on config 3c (profiles/r02_ab_round2.txt): r2c 1.277 -> 1.142 ms, c2r 1.386 -> 1.135 ms.  IMPULSE_FFT_BLUE_FOUR=0
+// restores the three-pass 256-thread core.
 inline bool blue_four_pass() {
-  static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_FOUR"); return e ? atoi(e) : 0; }();
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_FOUR"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
 template <typename T, int R1, int R2, int R3, int E>

@@ -601,8 +601,8 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   }
   // fused Bluestein on the register core: complex Bluestein lengths up to 4104 points, and odd real
   // lengths in that range with two rows packed per complex line (Hermitian layout); contiguous rows
-  // (float32: written and emulation-validated, not yet measured on the B200 — IMPULSE_FFT_BLUE_F32=1 selects it)
-  if (E->blue && (f64 || env_int("IMPULSE_FFT_BLUE_F32", 0)) && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
+  // (float32 measured on the B200: 2.0-3.5x the generic engine, profiles/r02_ab_round2.txt; IMPULSE_FFT_BLUE_F32=0: off)
+  if (E->blue && (f64 || env_int("IMPULSE_FFT_BLUE_F32", 1)) && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && !s.blue_stage && s.es_in == 1 && s.es_out == 1 &&
       J->bdim[1] == 1 && J->bdim[2] == 1 && !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_NO_FASTBLUE", 0)) {
     const bool okc = s.kind == KIND_C2C;
     const bool okr = (s.kind == KIND_R2C || s.kind == KIND_C2R) && !even && s.layout == RL_HERMITIAN;
@@ -641,10 +641,10 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       else if (L == 500) { id = f64 ? FAST3_500_F64 : FAST3_500_F32; r1 = 5; r2 = 10; r3 = 10; }
       else if (L == 1944) { id = f64 ? FAST3_1944_F64 : FAST3_1944_F32; r1 = 6; r2 = 18; r3 = 18; }
       else if (L == 1000) { id = f64 ? FAST3_1000_F64 : FAST3_1000_F32; r1 = 10; r2 = 10; r3 = 10; }
-      // more mixed-radix shapes: written and emulation-validated, not yet measured on the B200 (IMPULSE_FFT_MORE_SHAPES=1)
-      else if (L == 1536 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 0)) { id = FAST3_1536_F64; r1 = 8; r2 = 24; r3 = 8; }
-      else if (L == 2000 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 0)) { id = FAST3_2000_F64; r1 = 10; r2 = 20; r3 = 10; }
-      else if (L == 4000 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 0)) { id = FAST3_4000_F64; r1 = 10; r2 = 20; r3 = 20; }
+      // more mixed-radix shapes (measured 2.6-3.2x the generic engine, profiles/r02_ab_round2.txt; IMPULSE_FFT_MORE_SHAPES=0: off)
+      else if (L == 1536 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_1536_F64; r1 = 8; r2 = 24; r3 = 8; }
+      else if (L == 2000 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_2000_F64; r1 = 10; r2 = 20; r3 = 10; }
+      else if (L == 4000 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_4000_F64; r1 = 10; r2 = 20; r3 = 20; }
       else if (!c2c && (L == 16 || L == 32 || L == 64 || L == 128) && J->tw_r) {
         // short real rows: two-pass warp kernel (fast2r_kernel), tables = the engine's own W_L^m and W_N^k
         J->fast_id = (L == 16 ? FAST2R_16_F64 : L == 32 ? FAST2R_32_F64 : L == 64 ? FAST2R_64_F64 : FAST2R_128_F64) + (f64 ? 0 : 4);

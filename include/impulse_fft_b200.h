@@ -187,6 +187,12 @@ int impulse_fft_ipc_close(void *ptr);
  * pointers into other GPUs' memory. */
 int impulse_fft_enable_peer_access(int peer_device);
 
+/* Host-side placement for host-pointer calls: binds the CALLING thread (and threads it creates later) to the CPUs of
+ * the NUMA node that `device`'s PCIe root belongs to (sysfs), so that pinned buffers allocated afterwards are local to
+ * the GPU that will DMA them.  With one process per GPU this keeps 8 ranks from sharing node 0.  *numa_node receives
+ * the node, or -1 when the box exposes no NUMA information (nothing is changed then; not an error). */
+int impulse_fft_bind_host_to_device(int device, int *numa_node);
+
 /* Introspection (tests, benchmarks). */
 typedef struct {
   uint32_t n_steps;        /* kernel launches per execute                       */

@@ -298,15 +298,21 @@ def test_errors(ib):
 
 
 # ---- BASELINE configs at full size: properties that need no full-size oracle ------------------
+def _all_threads(checker):
+    return max(1, checker.hardware_threads())
+
+
 def test_config2_full_size_properties(ib, torch_mod, checker):
-    """65536 x 1024 complex128: parity on a sampled subset of rows, round trip on all, linearity."""
+    """65536 x 1024 complex128: EVERY row against the oracle (all host threads: the dynamic row scheduler
+    could skip or repeat a row that a sampled comparison never sees), round trip on all rows, Parseval."""
     g = torch_mod.Generator(device="cuda").manual_seed(1234)
     x = torch_mod.rand((65536, 1024, 2), generator=g, device="cuda", dtype=torch_mod.float64) - 0.5
     x = torch_mod.view_as_complex(x)
-    y = ib.fft(x)
-    rows = [0, 1, 777, 32768, 65535]
-    want = checker.cfft_rows(x[rows].cpu().numpy().copy(), True, 1.0)
-    assert oracle.max_row_rel_l2(y[rows].cpu().numpy(), want) <= tol(1024)
+    y = torch_mod.full_like(x, float("nan"))          # a row that is never written stays NaN
+    apply_nd(ib, "c2c", x, y, [1])
+    want = checker.cfft_rows(x.cpu().numpy().copy(), True, 1.0, nthreads=_all_threads(checker))
+    assert oracle.max_row_rel_l2(y.cpu().numpy(), want) <= tol(1024)
+    del want
     back = ib.ifft(y)
     num = torch_mod.linalg.vector_norm(back - x, dim=1)
     den = torch_mod.linalg.vector_norm(x, dim=1)
@@ -318,17 +324,21 @@ def test_config2_full_size_properties(ib, torch_mod, checker):
 
 
 def test_config1_and_3_shapes(ib, torch_mod, checker):
-    """r2c 1024x4096 (config 1) and r2c/c2r round trips at 16384 x {1000, 3888, 4099} (config 3)."""
+    """r2c 1024x4096 (config 1) and r2c/c2r at 16384 x {1000, 3888, 4099} (config 3): every row of both directions
+    against the oracle, and the r2c -> c2r round trip."""
     g = torch_mod.Generator(device="cuda").manual_seed(1234)
+    nt = _all_threads(checker)
     for rows, n in ((1024, 4096), (16384, 1000), (16384, 3888), (16384, 4099)):
         x = torch_mod.rand((rows, n), generator=g, device="cuda", dtype=torch_mod.float64) - 0.5
-        spec = torch_mod.empty((rows, n // 2 + 1), dtype=torch_mod.complex128, device="cuda")
+        spec = torch_mod.full((rows, n // 2 + 1), float("nan"), dtype=torch_mod.complex128, device="cuda")
         apply_nd(ib, "r2c", x, spec, [1])
-        sel = [0, 5, rows // 2, rows - 1]
-        want = checker.r2c(x[sel].cpu().numpy(), [1], True, 1.0)
-        assert oracle.max_row_rel_l2(spec[sel].cpu().numpy(), want) <= tol(n), n
-        back = torch_mod.empty_like(x)
+        xh = x.cpu().numpy()
+        want = checker.r2c(xh, [1], True, 1.0, nthreads=nt)
+        assert oracle.max_row_rel_l2(spec.cpu().numpy(), want) <= tol(n), n
+        back = torch_mod.full_like(x, float("nan"))
         apply_nd(ib, "c2r", spec, back, [1], False, 1.0 / n)
+        wantb = checker.c2r(want, xh.shape, [1], False, 1.0 / n, nthreads=nt)   # the oracle's own inverse of its spectrum
+        assert oracle.max_row_rel_l2(back.cpu().numpy(), wantb) <= tol(n), n
         num = torch_mod.linalg.vector_norm(back - x, dim=1)
         den = torch_mod.linalg.vector_norm(x, dim=1)
         assert float((num / den).max()) <= 2e-15 * np.log2(n), n
@@ -360,12 +370,18 @@ def test_four_step_long_and_strided_lines(ib, torch_mod, checker):
     assert oracle.rel_l2(got, checker.c2c(f32, [0])) <= tol(4096, np.float32)
 
 
-def test_config4_full_size_properties(ib, torch_mod):
-    """fft2 8192 x 8192 complex128 on one GPU: round trip, Parseval and a DC/impulse check."""
+def test_config4_full_size_properties(ib, torch_mod, checker):
+    """fft2 8192 x 8192 complex128 on one GPU: the WHOLE array against the oracle (all host threads), then round
+    trip, Parseval and the DC bin."""
     g = torch_mod.Generator(device="cuda").manual_seed(1234)
     x = torch_mod.view_as_complex(torch_mod.rand((8192, 8192, 2), generator=g, device="cuda", dtype=torch_mod.float64) - 0.5)
-    y = torch_mod.empty_like(x)
+    y = torch_mod.full_like(x, float("nan"))
     apply_nd(ib, "c2c", x, y, [0, 1])
+    want = checker.c2c(x.cpu().numpy(), [0, 1], True, 1.0, nthreads=0)
+    got = y.cpu().numpy()
+    assert oracle.rel_l2(got, want) <= tol(8192)
+    assert oracle.max_row_rel_l2(got, want) <= tol(8192)
+    del want, got
     e_in = float((x.abs() ** 2).sum())
     e_out = float((y.abs() ** 2).sum()) / (8192.0 * 8192.0)
     assert abs(e_in - e_out) / e_in <= 1e-13
@@ -413,7 +429,7 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
     rng = np.random.default_rng(21)
     used = set()
     for dt, cdt in ((np.float64, np.complex128), (np.float32, np.complex64)):
-        more = (1536, 2000, 4000) if os.environ.get("IMPULSE_FFT_MORE_SHAPES", "0") == "1" else ()   # shapes not yet on by default
+        more = (1536, 2000, 4000) if os.environ.get("IMPULSE_FFT_MORE_SHAPES", "1") == "1" else ()   # shapes not yet on by default
         for n in (16, 32, 64, 128, 256, 500, 512, 1000, 1024, 1944, 2048, 4096, 8192) + more:
             for rows in (1, 37, 301) + ((5000,) if n <= 128 else ()):
                 x = rnd(rng, (rows, n), cdt)
@@ -540,7 +556,7 @@ def test_fused_bluestein(ib, torch_mod, checker):
     # float32 instances of the fused kernel: selected (and checked here) with IMPULSE_FFT_BLUE_F32=1 until they are
     # measured and become the default
     used32 = set()
-    for n in ((1021, 2051, 4099) if os.environ.get("IMPULSE_FFT_BLUE_F32", "0") == "1" else ()):
+    for n in ((1021, 2051, 4099) if os.environ.get("IMPULSE_FFT_BLUE_F32", "1") == "1" else ()):
         for rows in (1, 5, 32):
             x = rnd(rng, (rows, n), np.complex64)
             xd = torch_mod.from_numpy(x).cuda()
@@ -557,7 +573,7 @@ def test_fused_bluestein(ib, torch_mod, checker):
             assert oracle.max_row_rel_l2(back, r) <= tol(n, np.float32), (n, rows)
     print(sorted(used), sorted(used32))
     assert any(k.startswith("fastblue") for k in used)
-    if os.environ.get("IMPULSE_FFT_BLUE_F32", "0") == "1":
+    if os.environ.get("IMPULSE_FFT_BLUE_F32", "1") == "1":
         assert any(k.startswith("fastblue_kernel<float") for k in used32), used32
 
 
@@ -618,7 +634,7 @@ def test_cols_from_parts_single_gpu(ib, torch_mod, checker):
             assert oracle.rel_l2(out.cpu().numpy(), want) <= tol(nparts * rpp), (nparts, rpp, cols, col0, ncols, fwd)
 
 
-def test_config5_full_image_size_properties(ib, torch_mod):
+def test_config5_full_image_size_properties(ib, torch_mod, checker):
     """BASELINE config 5 at the full 4096 x 4096 float32 image size (batch reduced to 4): identity kernel
     returns the image (2-D r2c -> c2r round trip), a 31x31 kernel matches the direct sum at sampled
     pixels, and the transform is linear."""
@@ -641,6 +657,19 @@ def test_config5_full_image_size_properties(ib, torch_mod):
         cc = (c - (np.arange(31) - 15)) % 4096
         direct = float((kn * im0[np.ix_(rr, cc)]).sum())
         assert abs(float(out[1, r, c]) - direct) <= 2e-5, (r, c)
+    # every pixel of every image against the same composition on the oracle (float32 pocketfft, all host threads)
+    pad = np.zeros((4096, 4096), np.float32)
+    ii = (np.arange(31) - 15) % 4096
+    pad[np.ix_(ii, ii)] = ker.cpu().numpy()
+    kspec = checker.r2c(pad, [0, 1], True, 1.0, nthreads=0)
+    imgs = img.cpu().numpy()
+    spec = checker.r2c(imgs, [1, 2], True, 1.0, nthreads=0) * kspec[None]
+    want = checker.c2r(np.ascontiguousarray(spec), imgs.shape, [1, 2], False, 1.0 / (4096.0 * 4096.0), nthreads=0)
+    got = out.cpu().numpy()
+    for b in range(4):
+        assert oracle.rel_l2(got[b], want[b]) <= 1e-5 * 12, b
+    assert float(np.abs(got - want).max()) <= 2e-5
+    del spec, want, got, imgs
     lin = f.apply(2.0 * img[:2] + img[2:4])
     ref = 2.0 * out[:2] + out[2:4]
     assert float(torch_mod.linalg.vector_norm(lin - ref) / torch_mod.linalg.vector_norm(ref)) <= 1e-5
