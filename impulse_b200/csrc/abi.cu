@@ -116,6 +116,8 @@ int get_ctx(DeviceCtx **out) {
   }
   int rc = configure_kernels(prop.sharedMemPerBlockOptin);
   if (rc) return cuda_fail((cudaError_t)rc, "cudaFuncSetAttribute");
+  rc = init_sched_slots();
+  if (rc) return cuda_fail((cudaError_t)rc, "row-scheduler allocation");
   *out = c.get();
   g_ctx[dev] = std::move(c);
   return 0;
@@ -390,7 +392,7 @@ struct OneShotKey {
   }
 };
 std::mutex g_os_mu;
-std::map<OneShotKey, std::shared_ptr<impulse_fft_plan_s>> g_os;
+LruMap<OneShotKey, std::shared_ptr<impulse_fft_plan_s>> g_os;   // evicts the least recently used plan, one at a time
 constexpr size_t kOneShotCap = 64;
 
 int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *sin,
@@ -412,8 +414,7 @@ int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, 
   std::shared_ptr<impulse_fft_plan_s> plan;
   {
     std::lock_guard<std::mutex> lk(g_os_mu);
-    auto it = g_os.find(key);
-    if (it != g_os.end()) plan = it->second;
+    if (auto *hit = g_os.find(key)) plan = *hit;
   }
   if (!plan) {
     impulse_fft_plan raw = nullptr;
@@ -421,8 +422,7 @@ int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, 
     if (rc) return rc;
     plan.reset(raw);
     std::lock_guard<std::mutex> lk(g_os_mu);
-    if (g_os.size() >= kOneShotCap) g_os.clear();  // plans are cheap to rebuild: tables stay cached per device
-    g_os[key] = plan;
+    g_os.insert(key, plan, kOneShotCap);   // a thread still executing an evicted plan holds its own reference
   }
   if (umul_mod) {  // fused-multiply plans: device pointers, dense output
     if (!in || !out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
@@ -758,10 +758,19 @@ cfft_plan make_cfft_plan(size_t length) {
   if (length == 0) { g_err = "zero-length transform"; return nullptr; }
   DeviceCtx *ctx = nullptr;
   if (get_ctx(&ctx)) return nullptr;
-  // build (and cache) both directions now so that execute cannot fail on planning
-  const Engine1D *e = nullptr;
-  std::string err;
-  if (length > 0xffffffffull || ctx->cache->status_engine((uint32_t)length, DT_F64, &e, &err)) { g_err = err; return nullptr; }
+  // plan the transform now, exactly as execute will (tables land in the per-device cache; lengths that run split
+  // build only their sub-transform tables), so that a length this build cannot run fails HERE with a NULL plan
+  if (length > 0xffffffffull) { g_err = "length exceeds 2^32-1"; return nullptr; }
+  {
+    NdDesc d;
+    d.kind = KIND_C2C; d.dtype = DT_F64; d.layout = RL_HERMITIAN; d.forward = true;
+    d.shape = {1, length};
+    d.stride_in = d.stride_out = {(ptrdiff_t)(length * 16), 16};
+    d.axes = {1};
+    impulse_fft_plan raw = nullptr;
+    if (create_plan(&raw, d)) return nullptr;
+    delete raw;
+  }
   cfft_plan p = new cfft_plan_i;
   p->length = length;
   return p;
@@ -779,10 +788,17 @@ rfft_plan make_rfft_plan(size_t length) {
   if (length == 0) { g_err = "zero-length transform"; return nullptr; }
   DeviceCtx *ctx = nullptr;
   if (get_ctx(&ctx)) return nullptr;
-  const Engine1D *e = nullptr;
-  std::string err;
-  const size_t L = (length % 2 == 0) ? length / 2 : length;
-  if (length > 0xffffffffull || ctx->cache->status_engine((uint32_t)L, DT_F64, &e, &err)) { g_err = err; return nullptr; }
+  if (length > 0xffffffffull) { g_err = "length exceeds 2^32-1"; return nullptr; }
+  {
+    NdDesc d;
+    d.kind = KIND_R2C; d.dtype = DT_F64; d.layout = RL_HALFCOMPLEX; d.forward = true;
+    d.shape = {1, length};
+    d.stride_in = d.stride_out = {(ptrdiff_t)(length * 8), 8};
+    d.axes = {1};
+    impulse_fft_plan raw = nullptr;
+    if (create_plan(&raw, d)) return nullptr;
+    delete raw;
+  }
   rfft_plan p = new rfft_plan_i;
   p->length = length;
   return p;

@@ -4,6 +4,7 @@
 // build container.  The emulation is test infrastructure; the product runs this code on the device only.
 #pragma once
 #include "fft_device.cuh"
+#include "tma_device.cuh"
 
 namespace impulse {
 
@@ -108,7 +109,18 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t byte
 #endif
 }
 
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB, bool PAIR = false, bool PF = false, bool DB = false>
+// TMA: the NEXT claimed row is staged into shared memory by one cp.async.bulk (issued by thread 0 right after the first
+// exchange, when every thread has consumed the current staged row; completion on an mbarrier) and the threads read
+// their points from the staging buffer instead of global memory.  The row's HBM latency is hidden behind passes 2
+// and 3 of the row before it, independent of the register budget — what took the two-pass kernel from 61 % to
+// 81 % DRAM utilisation (fast2p_kernel).  Needs 16-byte aligned rows (the launcher checks and falls back).
+template <typename T, int N, int KIND> struct F3Stage {
+  static constexpr uint32_t ROW_BYTES = (uint32_t)((KIND == F3_C2R ? (N + 1) : N) * sizeof(cx<T>));
+  static constexpr uint32_t BYTES = (ROW_BYTES + 15u) & ~15u;   // copied (a padded row stride makes the tail readable)
+};
+
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, int MINB, bool PAIR = false, bool PF = false, bool DB = false,
+          bool TMA = false>
 __global__ void __launch_bounds__((R1 * R2 * R3) / E, MINB)
 fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
              const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, const cx<T> *__restrict__ twr, T fct,
@@ -131,7 +143,14 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
   cx<T> *buf2 = DB ? buf + BUFN : buf;
   unsigned int *s_row = reinterpret_cast<unsigned int *>(buf + (DB ? 2 : 1) * BUFN);  // [2] (+2 pad)
   cx<T> *s_tw2 = reinterpret_cast<cx<T> *>(s_row + 4);                 // [R2][R3]
+  static_assert(!TMA || !PF, "staged rows replace the register prefetch");
+  static_assert(!TMA || KIND != F3_C2R || PAIR, "the staged c2r needs the direct-load (pair) variant");
+  // staging buffer of the next row + its mbarrier, behind the tables (128-byte aligned)
+  unsigned char *stg_raw = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(s_tw2 + R2 * R3) + 127) & ~(uintptr_t)127);
+  const cx<T> *stg = reinterpret_cast<const cx<T> *>(stg_raw);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(stg_raw + F3Stage<T, R1 * R2 * R3, KIND>::BYTES);
   const int t = threadIdx.x;
+  if (TMA && t == 0) { mbar_init(s_bar, 1); mbar_init_fence(); }
   if (t == 0) { s_row[0] = atomicAdd(&sched[0], 1u); s_row[1] = atomicAdd(&sched[0], 1u); }
   for (int idx = t; idx < R2 * R3; idx += TT) s_tw2[idx] = tw2[idx];
   cx<T> twA[3], twB[3];
@@ -149,10 +168,20 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
   // 2-13 % SLOWER on the B200 — more live registers, spills on the 18-point shapes.)
   static_assert(!PF || KIND == F3_C2C || (KIND == F3_R2C && PAIR), "register prefetch needs the direct-load variants");
   cx<T> x[E];
+  auto row_ptr = [&](const uint64_t r) -> const cx<T> * {
+    return KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)r * rs_in)
+                          : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)r * rs_in;
+  };
+  auto stage_row = [&](const uint64_t r) {   // thread 0 only; every reader of the staging buffer is behind a barrier
+    fence_proxy_async();
+    mbar_expect_tx(s_bar, F3Stage<T, R1 * R2 * R3, KIND>::BYTES);
+    bulk_g2s(stg_raw, row_ptr(r), F3Stage<T, R1 * R2 * R3, KIND>::BYTES, s_bar);
+  };
+  if (TMA && t == 0 && s_row[0] < nrows) stage_row(s_row[0]);
+  uint32_t stg_phase = 0u;
   auto load_row = [&](const uint64_t r) {
     if constexpr (KIND != F3_C2R) {
-      const cx<T> *src = KIND == F3_R2C ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in_v) + (int64_t)r * rs_in)
-                                        : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)r * rs_in;
+      const cx<T> *src = TMA ? stg : row_ptr(r);
 #pragma unroll
       for (int q = 0; q < E; ++q) {
         x[q] = src[t + TT * q];
@@ -164,7 +193,8 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
   for (unsigned it = 0;; ++it) {
     const uint64_t row = s_row[it & 1];
     if (row >= nrows) break;
-    if (t == 0) {  // pull the next claimed row into L2 while this one is transformed
+    if (TMA) { mbar_wait(s_bar, stg_phase); stg_phase ^= 1u; }   // this row has landed in the staging buffer
+    if (!TMA && t == 0) {  // pull the next claimed row into L2 while this one is transformed
       const uint64_t nxt = s_row[(it + 1) & 1];
       if (nxt < nrows) {
         const char *p = KIND == F3_R2C ? reinterpret_cast<const char *>(reinterpret_cast<const T *>(in_v) + (int64_t)nxt * rs_in)
@@ -186,7 +216,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
       // Unit 0 = butterflies 0 and M1/2, which mirror into themselves.  (backward = conj(FFT(conj z)).)
       static_assert(M1 % 2 == 0, "pair units need an even N/R1");
       constexpr int UNITS = M1 / 2, NU = (UNITS + TT - 1) / TT;
-      const cx<T> *src = reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
+      const cx<T> *src = TMA ? stg : reinterpret_cast<const cx<T> *>(in_v) + (int64_t)row * rs_in;
       auto pass1 = [&](cx<T> (&y)[R1], const int i1) {
         RegFFT<T, R1>::run(y);
 #pragma unroll
@@ -291,6 +321,10 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
     }
     __syncthreads();
     if ((KIND != F3_C2R || PAIR) && t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);  // everyone has read s_row[it&1]
+    if (TMA && t == 0) {   // ... and its points out of the staging buffer: the next row can stream in behind passes 2 and 3
+      const uint64_t nxt = s_row[(it + 1) & 1];
+      if (nxt < nrows) stage_row(nxt);
+    }
     // ---------------- pass 2 ----------------
 #pragma unroll
     for (int m = 0; m < NB2; ++m) {

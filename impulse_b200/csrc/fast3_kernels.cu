@@ -149,6 +149,10 @@ static int f3_minb4() {
 
 int launch_fast3_job(const LineJob &J, int sm_count, void *stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    const int rc = launch_fast3_staged_job(J, sm_count, stream);   // rows staged by bulk copies where that variant exists
+    if (rc != -1) return rc;
+  }
   switch (J.fast_id) {
     case FAST3R_256_F64: g_last_kernel = "fast3_kernel<double,8,8,4,E8>"; return launch_fast3<double, 8, 8, 4, 8, 16, 6, 1>(J, sm_count, s);
     case FAST3R_512_F64: g_last_kernel = "fast3_kernel<double,8,8,8,E8>"; return launch_fast3<double, 8, 8, 8, 8, 8, 6, 0>(J, sm_count, s);

@@ -19,8 +19,11 @@ struct PerDeviceFlag {
 };
 // a zero-initialised pair of device words {next row, CTAs done} for one launch with dynamic row claims (fast_kernels.cu)
 unsigned int *sched_slot();
+int init_sched_slots();   // once per device, before the first launch (abi.cu: get_ctx)
 // the three-pass register kernels (fast3_kernels.cu); returns cudaError_t, cudaErrorInvalidValue for other ids
 int launch_fast3_job(const LineJob &job, int sm_count, void *stream);
+// staged (TMA) variants, fast3t_kernels.cu: -1 = none for this job, launch the direct-load kernel
+int launch_fast3_staged_job(const LineJob &job, int sm_count, void *stream);
 int launch_fastblue_job(const LineJob &job, int sm_count, void *stream);   // fastblue_kernels.cu
 
 }  // namespace impulse

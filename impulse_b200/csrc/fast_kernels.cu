@@ -26,6 +26,7 @@
 #include "fastblue_device.cuh"
 #include "fft_device.cuh"
 #include "fft_kernels.h"
+#include "tma_device.cuh"
 
 namespace impulse {
 
@@ -246,31 +247,6 @@ int launch_fast2r(const LineJob &J, int sm_count, cudaStream_t s) {
 }  // namespace
 
 
-// ---- TMA helpers (1-D bulk copy global -> shared, completion on an mbarrier) ------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // Two-pass kernel with TMA row prefetch.  Each warp owns two shared buffers: while it computes
 // row r out of buffer b (first as the staged input, then as the exchange buffer), one elected
 // lane has already issued a cp.async.bulk for row r+1 into buffer b^1.  Global-load latency is
@@ -375,17 +351,31 @@ fast2p_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nr
   }
 }
 
-// scheduler slots: zero-initialised device words, one pair per in-flight launch (ring); shared with fast3_kernels.cu
+// scheduler slots: zero-initialised device words, one pair per in-flight launch (ring); shared with fast3_kernels.cu.
+// The ring of the current device is allocated and zeroed by init_sched_slots(), which the ABI layer calls once per
+// device under its context lock and BEFORE any launch (cudaMemset + cudaDeviceSynchronize: the zeros are visible to
+// every stream, including non-blocking ones, and nothing is allocated lazily under a CUDA-graph capture).
+namespace {
+constexpr int kSchedSlots = 65536;  // a slot is reused after this many launches: far more than can be queued across streams
+unsigned int *g_sched_base[kMaxDevices] = {};
+unsigned g_sched_next = 0;
+}  // namespace
+int init_sched_slots() {
+  unsigned int *&base = g_sched_base[cur_dev()];
+  if (base) return 0;
+  unsigned int *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, sizeof(unsigned int) * 2 * kSchedSlots);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemset(p, 0, sizeof(unsigned int) * 2 * kSchedSlots);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(p); return (int)e; }
+  __atomic_store_n(&base, p, __ATOMIC_RELEASE);
+  return 0;
+}
 unsigned int *sched_slot() {
-  constexpr int kSchedSlots = 65536;  // a slot is reused after this many launches: far more than can be queued across streams
-  static unsigned int *bases[kMaxDevices] = {};
-  static unsigned next = 0;
-  unsigned int *&base = bases[cur_dev()];
-  if (!base) {
-    if (cudaMalloc(&base, sizeof(unsigned int) * 2 * kSchedSlots) != cudaSuccess) { base = nullptr; return nullptr; }
-    cudaMemset(base, 0, sizeof(unsigned int) * 2 * kSchedSlots);
-  }
-  const unsigned s = __atomic_fetch_add(&next, 1u, __ATOMIC_RELAXED) % kSchedSlots;
+  unsigned int *base = __atomic_load_n(&g_sched_base[cur_dev()], __ATOMIC_ACQUIRE);
+  if (!base) return nullptr;
+  const unsigned s = __atomic_fetch_add(&g_sched_next, 1u, __ATOMIC_RELAXED) % kSchedSlots;
   return base + 2 * s;
 }
 

@@ -10,6 +10,7 @@ namespace impulse {
 extern thread_local const char *g_last_kernel;
 // raise the dynamic shared-memory limit of every kernel (once per device); returns cudaError_t
 int configure_kernels(size_t max_dyn_smem);
+int init_sched_slots();   // row-scheduler words of the register kernels (fast_kernels.cu); once per device
 // enqueue one LineJob on `stream` (a cudaStream_t); returns cudaError_t
 int launch_line_job(const LineJob &job, int threads, size_t smem_bytes, uint64_t n_tiles, void *stream);
 // specialised kernels selected by LineJob::fast_id (fast_kernels.cu); returns cudaError_t

@@ -155,25 +155,32 @@ std::vector<uint32_t> dif_positions(uint32_t n, const std::vector<uint32_t> &rad
   return pos;
 }
 
-PlanCache::~PlanCache() {
-  for (auto &kv : engines_) {
-    Engine1D *e = kv.second.get();
-    for (void *p : {e->d_tw, e->d_perm, e->d_bk, e->d_bkf, e->d_bkf_nat}) if (p) alloc_->release(p);
-  }
-  for (auto &kv : real_tw_) if (kv.second) alloc_->release(kv.second);
-  for (auto &kv : r2r_tw_) if (kv.second) alloc_->release(kv.second);
-  for (auto &kv : tw4_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
-  for (auto &kv : f3_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
-  for (auto &kv : fb_) { alloc_->release(kv.second.first); alloc_->release(kv.second.second); }
+// the plan under construction on this thread collects references to every table it looks up
+static thread_local std::vector<std::shared_ptr<void>> *tl_keep = nullptr;
+
+PlanCache::PlanCache(TableAlloc *alloc) : alloc_(alloc) {
+  const int c = env_int("IMPULSE_FFT_TABLE_CACHE", -1);
+  if (c >= 0) capacity = (size_t)c;
 }
+PlanCache::~PlanCache() {}   // entries release their tables when the last reference goes
+
+size_t PlanCache::entries() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  return engines_.m.size() + real_tw_.m.size() + r2r_tw_.m.size() + tw4_.m.size() + f3_.m.size() + fb_.m.size();
+}
+TableRef PlanCache::own(void *dev) {
+  TableAlloc *a = alloc_;
+  return TableRef(dev, [a](void *p) { if (p) a->release(p); });
+}
+void PlanCache::pin(const TableRef &r) { if (tl_keep && r) tl_keep->push_back(r); }
 
 int PlanCache::status_engine(uint32_t L, int dtype, const Engine1D **out, std::string *err) {
   std::lock_guard<std::mutex> lk(mu_);
   auto key = std::make_pair(L, dtype);
-  auto it = engines_.find(key);
-  if (it != engines_.end()) { *out = it->second.get(); return ST_OK; }
+  if (auto *hit = engines_.find(key)) { pin(*hit); *out = hit->get(); return ST_OK; }
   if (L == 0) { *err = "zero-length transform"; return ERR_INVALID; }
-  std::unique_ptr<Engine1D> e(new Engine1D);
+  std::shared_ptr<Engine1D> e(new Engine1D);
+  e->owner = alloc_;
   e->L = L;
   e->radices = choose_radices(L);
   e->blue = (L > 1 && e->radices.empty());
@@ -212,7 +219,8 @@ int PlanCache::status_engine(uint32_t L, int dtype, const Engine1D **out, std::s
     if (!e->d_bk || !e->d_bkf) { *err = "table upload failed"; return ERR_NOMEM; }
   }
   *out = e.get();
-  engines_[key] = std::move(e);
+  pin(e);
+  engines_.insert(key, std::move(e), capacity);
   return ST_OK;
 }
 
@@ -221,7 +229,9 @@ int PlanCache::bluestein_natural_table(uint32_t L, int dtype, const void **out, 
   int rc = status_engine(L, dtype, &ce, err);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(mu_);
-  Engine1D *e = engines_[std::make_pair(L, dtype)].get();
+  // (the entry found by status_engine is pinned by the plan under construction, or still cached: const_cast only
+  // to fill in the on-demand table under the lock)
+  Engine1D *e = const_cast<Engine1D *>(ce);
   if (!e->blue) { *err = "not a Bluestein length"; return ERR_INVALID; }
   if (!e->d_bkf_nat) {
     if (dtype == DT_F64) {
@@ -246,8 +256,7 @@ int PlanCache::fastblue_tables(uint32_t L, uint32_t M, int dtype, const void **b
   if (d > 16 || L > M) { *err = "work length too short for the fused Bluestein"; return ERR_UNSUPPORTED; }
   std::lock_guard<std::mutex> lk(mu_);
   auto key = std::make_pair(((uint64_t)L << 32) | M, dtype);
-  auto it = fb_.find(key);
-  if (it != fb_.end()) { *bf = it->second.first; *corr = it->second.second; return ST_OK; }
+  if (auto *hit = fb_.find(key)) { pin(hit->first); pin(hit->second); *bf = hit->first.get(); *corr = hit->second.get(); return ST_OK; }
   std::vector<cld> b(L), bw(M, cld(0, 0));
   uint64_t coeff = 0;
   for (uint32_t m = 0; m < L; ++m) {
@@ -266,7 +275,8 @@ int PlanCache::fastblue_tables(uint32_t L, uint32_t M, int dtype, const void **b
     }
   void *dbf = upload_cplx(alloc_, bw, dtype), *dcr = upload_cplx(alloc_, cr, dtype);
   if (!dbf || !dcr) { *err = "table upload failed"; return ERR_NOMEM; }
-  fb_[key] = std::make_pair(dbf, dcr);
+  auto &ent = fb_.insert(key, std::make_pair(own(dbf), own(dcr)), capacity);
+  pin(ent.first); pin(ent.second);
   *bf = dbf; *corr = dcr;
   return ST_OK;
 }
@@ -276,8 +286,7 @@ int PlanCache::fast3_tables(uint32_t N, uint32_t R1, uint32_t R2, uint32_t R3, i
                             std::string *err) {
   std::lock_guard<std::mutex> lk(mu_);
   auto key = std::make_pair(((uint64_t)N << 32) | (R1 << 16) | (R2 << 8) | R3, dtype);
-  auto it = f3_.find(key);
-  if (it != f3_.end()) { *tw1 = it->second.first; *tw2 = it->second.second; return ST_OK; }
+  if (auto *hit = f3_.find(key)) { pin(hit->first); pin(hit->second); *tw1 = hit->first.get(); *tw2 = hit->second.get(); return ST_OK; }
   const uint32_t M1 = N / R1;
   std::vector<cld> a((size_t)R1 * M1), b((size_t)R2 * R3);
   for (uint32_t k1 = 0; k1 < R1; ++k1)
@@ -286,7 +295,8 @@ int PlanCache::fast3_tables(uint32_t N, uint32_t R1, uint32_t R2, uint32_t R3, i
     for (uint32_t i2 = 0; i2 < R3; ++i2) b[(size_t)k2 * R3 + i2] = std::conj(unit_root((uint64_t)R1 * i2 * k2, N));
   void *da = upload_cplx(alloc_, a, dtype), *db = upload_cplx(alloc_, b, dtype);
   if (!da || !db) { *err = "table upload failed"; return ERR_NOMEM; }
-  f3_[key] = std::make_pair(da, db);
+  auto &ent = f3_.insert(key, std::make_pair(own(da), own(db)), capacity);
+  pin(ent.first); pin(ent.second);
   *tw1 = da; *tw2 = db;
   return ST_OK;
 }
@@ -297,15 +307,15 @@ int PlanCache::four_step_tables(uint32_t N, int dtype, const void **hi, const vo
   while ((1ull << (2 * sh)) < N) ++sh;  // B = 2^sh >= sqrt(N)
   *shift = sh;
   auto key = std::make_pair(N, dtype);
-  auto it = tw4_.find(key);
-  if (it != tw4_.end()) { *hi = it->second.first; *lo = it->second.second; return ST_OK; }
+  if (auto *hit = tw4_.find(key)) { pin(hit->first); pin(hit->second); *hi = hit->first.get(); *lo = hit->second.get(); return ST_OK; }
   const uint32_t B = 1u << sh, nhi = (N + B - 1) / B;
   std::vector<cld> vh(nhi), vl(B);
   for (uint32_t j = 0; j < nhi; ++j) vh[j] = std::conj(unit_root((uint64_t)j * B, N));
   for (uint32_t j = 0; j < B; ++j) vl[j] = std::conj(unit_root(j, N));
   void *dh = upload_cplx(alloc_, vh, dtype), *dl = upload_cplx(alloc_, vl, dtype);
   if (!dh || !dl) { *err = "table upload failed"; return ERR_NOMEM; }
-  tw4_[key] = std::make_pair(dh, dl);
+  auto &ent = tw4_.insert(key, std::make_pair(own(dh), own(dl)), capacity);
+  pin(ent.first); pin(ent.second);
   *hi = dh; *lo = dl;
   return ST_OK;
 }
@@ -314,13 +324,12 @@ int PlanCache::four_step_tables(uint32_t N, int dtype, const void **hi, const vo
 int PlanCache::r2r_twiddle(uint32_t N, int dtype, const void **out, std::string *err) {
   std::lock_guard<std::mutex> lk(mu_);
   auto key = std::make_pair(N, dtype);
-  auto it = r2r_tw_.find(key);
-  if (it != r2r_tw_.end()) { *out = it->second; return ST_OK; }
+  if (auto *hit = r2r_tw_.find(key)) { pin(*hit); *out = hit->get(); return ST_OK; }
   std::vector<cld> w(2 * (size_t)N + 2);
   for (uint32_t m = 0; m < 2 * N + 2; ++m) w[m] = std::conj(unit_root(m, 8 * (uint64_t)N));
   void *d = upload_cplx(alloc_, w, dtype);
   if (!d) { *err = "table upload failed"; return ERR_NOMEM; }
-  r2r_tw_[key] = d;
+  pin(r2r_tw_.insert(key, own(d), capacity));
   *out = d;
   return ST_OK;
 }
@@ -328,13 +337,12 @@ int PlanCache::r2r_twiddle(uint32_t N, int dtype, const void **out, std::string 
 int PlanCache::real_twiddle(uint32_t N, int dtype, const void **out, std::string *err) {
   std::lock_guard<std::mutex> lk(mu_);
   auto key = std::make_pair(N, dtype);
-  auto it = real_tw_.find(key);
-  if (it != real_tw_.end()) { *out = it->second; return ST_OK; }
+  if (auto *hit = real_tw_.find(key)) { pin(*hit); *out = hit->get(); return ST_OK; }
   std::vector<cld> w(N / 2 + 1);
   for (uint32_t k = 0; k <= N / 2; ++k) w[k] = std::conj(unit_root(k, N));
   void *d = upload_cplx(alloc_, w, dtype);
   if (!d) { *err = "table upload failed"; return ERR_NOMEM; }
-  real_tw_[key] = d;
+  pin(real_tw_.insert(key, own(d), capacity));
   *out = d;
   return ST_OK;
 }
@@ -689,6 +697,12 @@ void span_of(const std::vector<size_t> &shape, const std::vector<ptrdiff_t> &str
 int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
   plan->desc = d;
   plan->steps.clear();
+  plan->keep.clear();
+  struct KeepScope {   // every table looked up while this plan is built is pinned by the plan
+    std::vector<std::shared_ptr<void>> *prev;
+    explicit KeepScope(std::vector<std::shared_ptr<void>> *k) : prev(tl_keep) { tl_keep = k; }
+    ~KeepScope() { tl_keep = prev; }
+  } keep_scope(&plan->keep);
   plan->tmp_bytes = 0;
   plan->tmp2_bytes = 0;
   plan->tmp3_bytes = 0;

@@ -60,6 +60,10 @@ struct Engine1D {
   void *d_tw = nullptr, *d_perm = nullptr, *d_bk = nullptr, *d_bkf = nullptr;
   void *d_bkf_nat = nullptr;  // FFT(b)/n2 in natural order (multi-launch Bluestein), uploaded on demand
   std::vector<double> bkf_nat_host;  // interleaved re,im in double; kept for the on-demand upload
+  TableAlloc *owner = nullptr;       // releases the tables when the last reference (cache entry or plan) goes
+  ~Engine1D() {
+    if (owner) for (void *p : {d_tw, d_perm, d_bk, d_bkf, d_bkf_nat}) if (p) owner->release(p);
+  }
 };
 
 struct LaunchCfg {
@@ -127,12 +131,46 @@ struct NdPlan {
   ptrdiff_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
   bool empty = false;  // zero-size array: nothing to do
   bool out_dense = true;  // the output span has no gaps between elements
+  // the cached device tables the steps point into: held for the life of the plan, so that the table cache can
+  // evict entries without invalidating plans
+  std::vector<std::shared_ptr<void>> keep;
 };
+
+// Least-recently-used map with an access counter, the policy of get_plan (pocketfft_hdronly.h:2655-2706: 16 entries
+// per type, `last_access` stamped on every hit, the oldest entry replaced).  Values are shared_ptrs: eviction only
+// drops the CACHE's reference — a plan that was built from an entry keeps it alive (NdPlan::keep) until the plan is
+// destroyed, so no launch ever sees a freed table.
+template <typename K, typename V> struct LruMap {
+  struct Ent { V v; uint64_t used = 0; };
+  std::map<K, Ent> m;
+  uint64_t clock = 0;
+  V *find(const K &k) {
+    auto it = m.find(k);
+    if (it == m.end()) return nullptr;
+    it->second.used = ++clock;
+    return &it->second.v;
+  }
+  V &insert(const K &k, V v, size_t cap) {
+    while (cap && m.size() >= cap) {
+      auto old = m.begin();
+      for (auto it = m.begin(); it != m.end(); ++it) if (it->second.used < old->second.used) old = it;
+      m.erase(old);
+    }
+    Ent &e = m[k];
+    e.v = std::move(v);
+    e.used = ++clock;
+    return e.v;
+  }
+};
+using TableRef = std::shared_ptr<void>;
 
 class PlanCache {
  public:
-  explicit PlanCache(TableAlloc *alloc) : alloc_(alloc) {}
+  explicit PlanCache(TableAlloc *alloc);
   ~PlanCache();
+  // entries kept per table family and precision-independent key (IMPULSE_FFT_TABLE_CACHE overrides; 0 = unbounded)
+  size_t capacity = 64;
+  size_t entries() const;   // tables currently referenced by the cache (tests)
   // max shared memory per CTA the engine may use (bytes), set by the backend
   size_t max_smem = 227 * 1024;
   // the fused convolution pass exists as a register kernel only; the host emulator turns it off
@@ -148,14 +186,16 @@ class PlanCache {
   int build_nd(const NdDesc &d, NdPlan *plan, std::string *err);
 
  private:
+  TableRef own(void *dev);          // device table -> reference-counted handle that releases it
+  void pin(const TableRef &r);      // remember the table in the plan being built (if any)
   TableAlloc *alloc_;
-  std::mutex mu_;
-  std::map<std::pair<uint32_t, int>, std::unique_ptr<Engine1D>> engines_;
-  std::map<std::pair<uint32_t, int>, void *> real_tw_;
-  std::map<std::pair<uint32_t, int>, void *> r2r_tw_;
-  std::map<std::pair<uint32_t, int>, std::pair<void *, void *>> tw4_;
-  std::map<std::pair<uint64_t, int>, std::pair<void *, void *>> f3_;
-  std::map<std::pair<uint64_t, int>, std::pair<void *, void *>> fb_;
+  mutable std::mutex mu_;
+  LruMap<std::pair<uint32_t, int>, std::shared_ptr<Engine1D>> engines_;
+  LruMap<std::pair<uint32_t, int>, TableRef> real_tw_;
+  LruMap<std::pair<uint32_t, int>, TableRef> r2r_tw_;
+  LruMap<std::pair<uint32_t, int>, std::pair<TableRef, TableRef>> tw4_;
+  LruMap<std::pair<uint64_t, int>, std::pair<TableRef, TableRef>> f3_;
+  LruMap<std::pair<uint64_t, int>, std::pair<TableRef, TableRef>> fb_;
 };
 
 // planner utilities exposed for tests

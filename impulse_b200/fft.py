@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import collections
 import threading
 
 import numpy as np
@@ -54,16 +55,28 @@ def _fct(kind: str, forward: bool, value: float, length: int) -> float:
 
 # ---- plan cache (the reference rebuilds a plan on every call, NC:285,300; on a GPU the tables
 # ---- must be cached) ---------------------------------------------------------
-_plans: dict = {}
+class _Plan:
+    """A cached plan handle with a use count: a plan evicted while another thread is inside impulse_fft_execute is
+    destroyed by that thread when it returns, never under it (include/impulse_fft_b200.h allows concurrent executes)."""
+    __slots__ = ("h", "users", "evicted")
+
+    def __init__(self, h):
+        self.h, self.users, self.evicted = h, 0, False
+
+
+_PLAN_CAP = 256
+_plans: "collections.OrderedDict" = collections.OrderedDict()   # least recently used first
 _plans_lock = threading.Lock()
 
 
-def _plan(kind, layout, code, shape, sin, sout, axes, forward):
+def _acquire_plan(kind, layout, code, shape, sin, sout, axes, forward) -> _Plan:
     key = (kind, layout, code, tuple(shape), tuple(sin), tuple(sout), tuple(axes), bool(forward), _device_key())
     with _plans_lock:
-        h = _plans.get(key)
-    if h is not None:
-        return h
+        p = _plans.get(key)
+        if p is not None:
+            _plans.move_to_end(key)
+            p.users += 1
+            return p
     L = _lib.lib()
     d = _lib.Desc()
     d.kind, d.dtype, d.real_layout, d.forward = kind, code, layout, int(forward)
@@ -74,13 +87,34 @@ def _plan(kind, layout, code, shape, sin, sout, axes, forward):
         d.axes[i] = a
     h = C.c_void_p()
     _lib.check(L.impulse_fft_plan_create(C.byref(h), C.byref(d)))
+    doomed = []
     with _plans_lock:
-        if len(_plans) >= 256:
-            for old in _plans.values():
-                L.impulse_fft_plan_destroy(old)
-            _plans.clear()
-        _plans[key] = h
-    return h
+        other = _plans.get(key)
+        if other is not None:               # another thread built the same plan meanwhile: keep theirs
+            doomed.append(h)
+            _plans.move_to_end(key)
+            other.users += 1
+            p = other
+        else:
+            p = _Plan(h)
+            p.users = 1
+            _plans[key] = p
+            while len(_plans) > _PLAN_CAP:  # evict ONE least recently used entry at a time
+                _, old = _plans.popitem(last=False)
+                old.evicted = True
+                if old.users == 0:
+                    doomed.append(old.h)
+    for dh in doomed:
+        L.impulse_fft_plan_destroy(dh)
+    return p
+
+
+def _release_plan(p: _Plan) -> None:
+    with _plans_lock:
+        p.users -= 1
+        destroy = p.evicted and p.users == 0
+    if destroy:
+        _lib.lib().impulse_fft_plan_destroy(p.h)
 
 
 def _device_key():
@@ -98,8 +132,11 @@ def _execute(kind, layout, x, out, real_shape, forward, fct):
     if 0 in real_shape:
         return out
     code = B.dtype_code(x)
-    h = _plan(kind, layout, code, real_shape, B.byte_strides(x), B.byte_strides(out), [len(real_shape) - 1], forward)
-    _lib.check(_lib.lib().impulse_fft_execute(h, B.ptr(x), B.ptr(out), float(fct), B.stream_of(x, out)))
+    p = _acquire_plan(kind, layout, code, real_shape, B.byte_strides(x), B.byte_strides(out), [len(real_shape) - 1], forward)
+    try:
+        _lib.check(_lib.lib().impulse_fft_execute(p.h, B.ptr(x), B.ptr(out), float(fct), B.stream_of(x, out)))
+    finally:
+        _release_plan(p)
     return out
 
 

@@ -49,7 +49,7 @@ template <typename T> std::vector<cx<T>> conv(const std::vector<cld> &v) {
   return r;
 }
 
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool PAIR, bool PF = false, bool DB = false>
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool PAIR, bool PF = false, bool DB = false, bool TMA = false>
 void run(const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
   constexpr int N = R1 * R2 * R3, TT = N / E, M1 = N / R1;
   std::vector<cld> a((size_t)R1 * M1), b((size_t)R2 * R3), r((size_t)N + 1);
@@ -69,7 +69,7 @@ void run(const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_ou
     for (int t = 0; t < TT; ++t)
       th.emplace_back([&, t] {
         threadIdx.x = (unsigned)t;
-        fast3_kernel<T, R1, R2, R3, E, KIND, BWD, 1, PAIR, PF, DB>(in, out, nrows, rs_in, rs_out, tw1.data(), tw2.data(), twr.data(), (T)fct, sched);
+        fast3_kernel<T, R1, R2, R3, E, KIND, BWD, 1, PAIR, PF, DB, TMA>(in, out, nrows, rs_in, rs_out, tw1.data(), tw2.data(), twr.data(), (T)fct, sched);
       });
     for (auto &x : th) x.join();
   }
@@ -79,6 +79,18 @@ void run(const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_ou
 template <typename T, int R1, int R2, int R3, int E>
 int dispatch(int kind, int bwd, int flags, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
   const bool pair = (flags & 1) != 0, pf = (flags & 2) != 0, db = (flags & 4) != 0;   // flags: 1 = pair units, 2 = register prefetch, 4 = second exchange buffer
+  const bool tma = (flags & 8) != 0;                                                  //        8 = next row staged in shared memory by a bulk copy
+#define GOT(K, P, D) (bwd ? run<T, R1, R2, R3, E, K, true, P, false, D, true>(in, out, nrows, rs_in, rs_out, fct, ctas) \
+                          : run<T, R1, R2, R3, E, K, false, P, false, D, true>(in, out, nrows, rs_in, rs_out, fct, ctas))
+  if (tma) {
+    if (pf) return -2;
+    if (kind == F3_C2C) { if (db) GOT(F3_C2C, false, true); else GOT(F3_C2C, false, false); return 0; }
+    if (!pair) return -2;
+    if (kind == F3_R2C) { if constexpr ((R1 * R2) % 2 == 0) { if (db) GOT(F3_R2C, true, true); else GOT(F3_R2C, true, false); return 0; } return -2; }
+    if constexpr ((R2 * R3) % 2 == 0) { if (db) GOT(F3_C2R, true, true); else GOT(F3_C2R, true, false); return 0; }
+    return -2;
+  }
+#undef GOT
 #define GO(K, B, P, F) run<T, R1, R2, R3, E, K, B, P, F>(in, out, nrows, rs_in, rs_out, fct, ctas)
 #define GO2(K, P, F) (bwd ? GO(K, true, P, F) : GO(K, false, P, F))
 #define GODB(K, P) (bwd ? run<T, R1, R2, R3, E, K, true, P, false, true>(in, out, nrows, rs_in, rs_out, fct, ctas) \

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(HERE, "libimpulse_fast3_emu.so")
 SRC = os.path.join(HERE, "emu_fast3.cpp")
 DEPS = [SRC] + [os.path.join(ROOT, "impulse_b200", "csrc", f) for f in
-                ("fast3_device.cuh", "fft_device.cuh", "fft_types.h", "trig_tables.h")]
+                ("fast3_device.cuh", "fft_device.cuh", "fft_types.h", "trig_tables.h", "tma_device.cuh")]
 KIND = {"c2c": 0, "r2c": 1, "c2r": 2}
 
 
@@ -36,7 +36,7 @@ def lib():
     return _lib
 
 
-def run(shape, kind, x, forward=True, fct=1.0, pair=False, ctas=2, prefetch=False, double_buffer=False):
+def run(shape, kind, x, forward=True, fct=1.0, pair=False, ctas=2, prefetch=False, double_buffer=False, staged=False):
     """shape = (R1, R2, R3, E); x = [rows, n] array (real for r2c, complex otherwise).  Returns the transform the
     kernel would write (rows are `forward` transforms; backward = the reference's forward=False semantics)."""
     r1, r2, r3, e = shape
@@ -65,7 +65,7 @@ def run(shape, kind, x, forward=True, fct=1.0, pair=False, ctas=2, prefetch=Fals
     # the kernel's BWD flag: c2c / r2c = backward transform; c2r = "conjugate the input" = forward=True (F_CONJ_IN)
     bwd = (1 if forward else 0) if kind == "c2r" else (0 if forward else 1)
     rc = lib().emu_fast3(r1 * 1000000 + r2 * 10000 + r3 * 100 + e, 1 if f64 else 0, KIND[kind], bwd,
-                         (1 if pair else 0) | (2 if prefetch else 0) | (4 if double_buffer else 0), x.ctypes.data, out.ctypes.data, rows, x.shape[1], out.shape[1], fct, ctas)
+                         (1 if pair else 0) | (2 if prefetch else 0) | (4 if double_buffer else 0) | (8 if staged else 0), x.ctypes.data, out.ctypes.data, rows, x.shape[1], out.shape[1], fct, ctas)
     if rc:
         raise RuntimeError(f"emu_fast3 rc={rc}")
     if not (np.isnan(flat[:pad]).all() and np.isnan(flat[-pad:]).all()):

@@ -187,3 +187,45 @@ def test_more_mixed_radix_shapes(shape):
     assert rel(f3.run(shape, "r2c", x, True, 1.0, pair=pr), ref_r2c(x, True, 1.0)) < 2e-15 * np.log2(n) * 4
     X = np.fft.rfft(x, axis=1)
     assert rel(f3.run(shape, "c2r", X, False, 0.5 / n, pair=True), x) < 2e-15 * np.log2(n) * 4
+
+
+@pytest.mark.parametrize("db", [False, True])
+@pytest.mark.parametrize("shape,kind", [((16, 16, 8, 16), "r2c"), ((18, 18, 6, 18), "r2c"), ((10, 10, 5, 10), "r2c"),
+                                        ((8, 16, 16, 16), "c2r"), ((6, 18, 18, 18), "c2r"), ((5, 10, 10, 10), "c2r"),
+                                        ((16, 16, 8, 16), "c2c"), ((16, 16, 16, 16), "c2c")])
+def test_rows_staged_by_bulk_copy(shape, kind, db):
+    """TMA variant: the next claimed row is copied into a shared staging buffer (cp.async.bulk + mbarrier on the GPU, a
+    memcpy + phase word here) while the current row is transformed.  11 rows over 3 CTAs, both directions, repeated:
+    a copy issued before every reader has left the staging buffer, or a wrong phase, shows up as a wrong row."""
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    if db and kind == "c2c" and shape == (16, 16, 16, 16):
+        pytest.skip("no second exchange buffer for 4096-point complex rows")
+    rng = np.random.default_rng(3 * n + db)
+    for rep in range(2):
+        for fwd in (True, False):
+            if kind == "r2c":
+                x = rng.random((11, 2 * n)) - 0.5
+                want = ref_r2c(x, fwd, 0.5)
+            elif kind == "c2r":
+                x = np.fft.rfft(rng.random((11, 2 * n)) - 0.5, axis=1)
+                x[:, 0] += 0.125j                       # ignored imaginary parts
+                want = ref_c2r(np.where(np.arange(n + 1) % n == 0, x.real, x), 2 * n, fwd, 0.5)
+            else:
+                x = rng.random((11, n)) - 0.5 + 1j * (rng.random((11, n)) - 0.5)
+                want = (np.fft.fft(x, axis=1) if fwd else np.fft.ifft(x, axis=1) * n) * 0.5
+            got = f3.run(shape, kind, x, fwd, 0.5, pair=kind != "c2c", ctas=3, double_buffer=db, staged=True)
+            assert not np.isnan(got.view(np.float64)).any()
+            for r in range(11):
+                assert rel(got[r], want[r]) < 2e-15 * np.log2(n) * 4, (rep, fwd, r)
+
+
+def test_rows_staged_by_bulk_copy_f32():
+    rng = np.random.default_rng(99)
+    n = 2048
+    x = (rng.random((7, 2 * n)) - 0.5).astype(np.float32)
+    got = f3.run((16, 16, 8, 16), "r2c", x, True, 1.0, pair=True, ctas=2, staged=True)
+    assert rel(got.astype(np.complex128), ref_r2c(x, True, 1.0)) < 1e-6 * np.log2(n)
+    X = np.fft.rfft(x.astype(np.float64), axis=1).astype(np.complex64)
+    got = f3.run((8, 16, 16, 16), "c2r", X, False, 0.5 / n, pair=True, ctas=2, staged=True, double_buffer=True)
+    assert rel(got.astype(np.float64), x.astype(np.float64)) < 1e-6 * np.log2(n)
