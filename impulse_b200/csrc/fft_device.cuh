@@ -529,7 +529,7 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e,
     } break;
     case ST_HC_EVEN: {
       cx<T> v = r2c_even_bin<T>(J, S, e);
-      v.x *= f; v.y *= f;
+      v.x *= f; v.y *= cres ? -f : f;   // r2c with forward=false packs the conjugate spectrum
       if (e == 0) outr[off] = v.x;
       else if (e == J.n_seq) outr[off + (int64_t)(J.n_real - 1) * es] = v.x;
       else { outr[off + (2 * (int64_t)e - 1) * es] = v.x; outr[off + (2 * (int64_t)e) * es] = v.y; }
@@ -544,7 +544,7 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e,
     } break;
     case ST_HC_FULL: {
       cx<T> v = read_bin<T>(J, S, e);
-      v.x *= f; v.y *= f;
+      v.x *= f; v.y *= cres ? -f : f;   // r2c with forward=false packs the conjugate spectrum
       if (e == 0) outr[off] = v.x;
       else { outr[off + (2 * (int64_t)e - 1) * es] = v.x; outr[off + (2 * (int64_t)e) * es] = v.y; }
     } break;
