@@ -51,6 +51,7 @@ EXPORTS = [
     "impulse_fft_last_kernel",
     "impulse_fft_cmul", "impulse_fft_transpose", "impulse_fft_copy2d", "impulse_fft_cols_from_parts", "impulse_fft_enable_peer_access", "impulse_fft_ipc_alloc", "impulse_fft_ipc_free",
     "impulse_fft_ipc_open", "impulse_fft_ipc_close", "impulse_fft_bind_host_to_device",
+    "impulse_fft_dist_create", "impulse_fft_dist_execute", "impulse_fft_dist_execute_parts", "impulse_fft_dist_shard", "impulse_fft_dist_destroy",
     # include/pocketfft.h
     "make_cfft_plan", "destroy_cfft_plan", "cfft_backward", "cfft_forward", "cfft_length",
     "make_rfft_plan", "destroy_rfft_plan", "rfft_backward", "rfft_forward", "rfft_length",
@@ -123,6 +124,16 @@ def lib() -> C.CDLL:
                                               C.c_size_t, C.c_int, C.c_double, vp]
     L.impulse_fft_bind_host_to_device.restype = C.c_int
     L.impulse_fft_bind_host_to_device.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    L.impulse_fft_dist_create.restype = C.c_int
+    L.impulse_fft_dist_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Desc), C.c_int, C.POINTER(C.c_int)]
+    L.impulse_fft_dist_execute.restype = C.c_int
+    L.impulse_fft_dist_execute.argtypes = [vp, vp, vp, C.c_double]
+    L.impulse_fft_dist_execute_parts.restype = C.c_int
+    L.impulse_fft_dist_execute_parts.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_double]
+    L.impulse_fft_dist_shard.restype = C.c_int
+    L.impulse_fft_dist_shard.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.impulse_fft_dist_destroy.restype = C.c_int
+    L.impulse_fft_dist_destroy.argtypes = [vp]
     L.make_cfft_plan.restype = vp
     L.make_cfft_plan.argtypes = [C.c_size_t]
     L.make_rfft_plan.restype = vp

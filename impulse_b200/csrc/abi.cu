@@ -16,6 +16,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -748,6 +749,262 @@ int impulse_fft_cols_from_parts(int dtype, size_t nparts, const void *const *par
   }
   // the first part stands in for `in` (only its alignment is looked at; every load goes through seg_base)
   return run_device(plan.get(), (const unsigned char *)parts[0] + col0 * csz, out, fct, static_cast<cudaStream_t>(stream));
+}
+
+// ---- single-process multi-GPU driver (impulse_fft_dist_create / execute / destroy) -----------------
+// The caller of the C ABI is ONE process (a Nim / C / C++ host), so the devices are driven from here: one stream per
+// device, peer access between all pairs, events for the only cross-device dependency (row slabs complete -> column
+// pass).  BATCH_SHARD has no communication at all; SLAB_2D exchanges through the column kernels' peer loads
+// (impulse_fft_cols_from_parts) — there is no pack step and no all-to-all buffer.  The reference's analogue is
+// general_nd handing line ranges to its thread pool (pocketfft_hdronly.h:3012-3050).
+}  // extern "C"
+
+struct impulse_fft_dist_s {
+  int mode = 0;
+  NdDesc desc;
+  std::vector<int> devs;
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> ev_rows;
+  std::vector<impulse_fft_plan> plans;         // BATCH_SHARD: the shard's plan; SLAB_2D: the row pass of the slab
+  std::vector<size_t> lo, hi;                  // rows of dimension 0 per device
+  std::vector<void *> rowbuf;                  // SLAB_2D: row-FFT output [R/G, C], read by every peer
+  std::vector<void *> stage_in, stage_out;     // SLAB_2D host path: device copies of the row slab / column slab
+  size_t esz = 0;
+};
+
+namespace {
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { cudaGetDevice(&prev); }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void dist_free(impulse_fft_dist h) {
+  for (size_t g = 0; g < h->devs.size(); ++g) {
+    if (cudaSetDevice(h->devs[g]) != cudaSuccess) { cudaGetLastError(); continue; }
+    cudaDeviceSynchronize();
+    if (g < h->plans.size() && h->plans[g]) delete h->plans[g];
+    if (g < h->rowbuf.size() && h->rowbuf[g]) cudaFree(h->rowbuf[g]);
+    if (g < h->stage_in.size() && h->stage_in[g]) cudaFree(h->stage_in[g]);
+    if (g < h->stage_out.size() && h->stage_out[g]) cudaFree(h->stage_out[g]);
+    if (g < h->ev_rows.size() && h->ev_rows[g]) cudaEventDestroy(h->ev_rows[g]);
+    if (g < h->streams.size() && h->streams[g]) cudaStreamDestroy(h->streams[g]);
+  }
+  delete h;
+}
+
+// SLAB_2D on device pointers: in_parts[g] = row slab of device g (strides of the descriptor), out_parts[g] = dense
+// column slab [R, C/G].  Asynchronous on the per-device streams; the caller synchronises.
+int slab_run(impulse_fft_dist h, const void *const *in_parts, void *const *out_parts, double fct) {
+  const size_t G = h->devs.size(), R = h->desc.shape[0], Cc = h->desc.shape[1], rl = R / G, cb = Cc / G;
+  for (size_t g = 0; g < G; ++g) {
+    cudaError_t e = cudaSetDevice(h->devs[g]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    int rc = run_device(h->plans[g], in_parts[g], h->rowbuf[g], fct, h->streams[g]);
+    if (rc) return rc;
+    e = cudaEventRecord(h->ev_rows[g], h->streams[g]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+  }
+  for (size_t g = 0; g < G; ++g) {
+    cudaError_t e = cudaSetDevice(h->devs[g]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    for (size_t q = 0; q < G; ++q)
+      if (q != g) { e = cudaStreamWaitEvent(h->streams[g], h->ev_rows[q], 0); if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent"); }
+    int rc = impulse_fft_cols_from_parts(h->desc.dtype, G, h->rowbuf.data(), rl, Cc, g * cb, cb, out_parts[g], cb,
+                                         h->desc.forward ? 1 : 0, 1.0, h->streams[g]);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int dist_sync(impulse_fft_dist h) {
+  int rc = 0;
+  for (size_t g = 0; g < h->devs.size(); ++g) {
+    cudaError_t e = cudaSetDevice(h->devs[g]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->streams[g]);
+    if (e != cudaSuccess && !rc) rc = cuda_fail(e, "multi-GPU synchronise");
+  }
+  return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int impulse_fft_dist_create(impulse_fft_dist *out, int mode, const impulse_fft_desc *desc, int ndev, const int *devices) {
+  if (!out || !desc || !devices) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (ndev < 1 || ndev > 8) return fail(IMPULSE_FFT_ERR_INVALID, "1 <= ndev <= 8 (one NVSwitch box)");
+  if (mode != IMPULSE_FFT_DIST_BATCH_SHARD && mode != IMPULSE_FFT_DIST_SLAB_2D) return fail(IMPULSE_FFT_ERR_INVALID, "unknown partitioning mode");
+  if (desc->ndim > IMPULSE_FFT_MAX_DIMS || desc->naxes > IMPULSE_FFT_MAX_DIMS) return fail(IMPULSE_FFT_ERR_INVALID, "too many dimensions");
+  for (int i = 0; i < ndev; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return fail(IMPULSE_FFT_ERR_INVALID, "a device is listed twice");
+  NdDesc d;
+  int rc = make_desc(&d, desc->kind, desc->dtype, desc->real_layout, desc->forward, desc->ndim, desc->shape, desc->stride_in,
+                     desc->stride_out, desc->naxes, desc->axes);
+  if (rc) return rc;
+  const size_t G = (size_t)ndev;
+  if (mode == IMPULSE_FFT_DIST_BATCH_SHARD) {
+    if (d.shape.size() < 2) return fail(IMPULSE_FFT_ERR_INVALID, "batch sharding needs a batch dimension (dimension 0)");
+    for (size_t a : d.axes) if (a == 0) return fail(IMPULSE_FFT_ERR_INVALID, "dimension 0 is the sharded batch dimension: it cannot be a transform axis");
+  } else {
+    if (d.kind != KIND_C2C || d.shape.size() != 2 || d.axes.size() != 2 || d.axes[0] == d.axes[1] || d.axes[0] > 1 || d.axes[1] > 1)
+      return fail(IMPULSE_FFT_ERR_INVALID, "the slab decomposition serves 2-D complex transforms over both axes");
+    if (d.shape[0] % G || d.shape[1] % G) return fail(IMPULSE_FFT_ERR_INVALID, "rows and columns must be divisible by the number of devices");
+  }
+  DeviceGuard guard;
+  std::unique_ptr<impulse_fft_dist_s, void (*)(impulse_fft_dist)> h(new impulse_fft_dist_s, dist_free);
+  h->mode = mode; h->desc = d;
+  h->devs.assign(devices, devices + ndev);
+  h->esz = (d.dtype == DT_F64 ? 8 : 4) * 2;
+  h->streams.assign(G, nullptr); h->ev_rows.assign(G, nullptr); h->plans.assign(G, nullptr);
+  h->rowbuf.assign(G, nullptr); h->stage_in.assign(G, nullptr); h->stage_out.assign(G, nullptr);
+  h->lo.resize(G); h->hi.resize(G);
+  const size_t B = d.shape[0];
+  for (size_t g = 0; g < G; ++g) { h->lo[g] = B * g / G; h->hi[g] = B * (g + 1) / G; }   // contiguous split
+  for (size_t g = 0; g < G; ++g) {
+    cudaError_t e = cudaSetDevice(h->devs[g]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    e = cudaStreamCreateWithFlags(&h->streams[g], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_rows[g], cudaEventDisableTiming);
+    if (e != cudaSuccess) return cuda_fail(e, "stream / event creation");
+    if (mode == IMPULSE_FFT_DIST_SLAB_2D) {
+      for (size_t q = 0; q < G; ++q) {
+        if (q == g) continue;
+        int can = 0;
+        e = cudaDeviceCanAccessPeer(&can, h->devs[g], h->devs[q]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceCanAccessPeer");
+        if (!can) return fail(IMPULSE_FFT_ERR_UNSUPPORTED, "no peer access between the listed devices");
+        e = cudaDeviceEnablePeerAccess(h->devs[q], 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+      }
+    }
+    NdDesc s = d;
+    s.shape[0] = h->hi[g] - h->lo[g];
+    if (mode == IMPULSE_FFT_DIST_SLAB_2D) {   // row pass of the slab into the dense published buffer
+      s.axes = {1};
+      s.stride_out = {(ptrdiff_t)(d.shape[1] * h->esz), (ptrdiff_t)h->esz};
+      e = cudaMalloc(&h->rowbuf[g], s.shape[0] * d.shape[1] * h->esz);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (row slab)");
+    } else if (d.kind == KIND_R2C || d.kind == KIND_C2R) {
+      // (shape is the REAL array's shape on both sides: nothing else to adjust)
+    }
+    if (s.shape[0] == 0) continue;           // more devices than rows: this one idles
+    rc = create_plan(&h->plans[g], s);
+    if (rc) return rc;
+  }
+  *out = h.release();
+  return 0;
+}
+
+int impulse_fft_dist_destroy(impulse_fft_dist h) {
+  if (!h) return 0;
+  DeviceGuard guard;
+  dist_free(h);
+  return 0;
+}
+
+int impulse_fft_dist_shard(impulse_fft_dist h, int index, size_t *lo, size_t *hi) {
+  if (!h || index < 0 || (size_t)index >= h->devs.size() || !lo || !hi) return fail(IMPULSE_FFT_ERR_INVALID, "bad argument");
+  *lo = h->lo[(size_t)index]; *hi = h->hi[(size_t)index];
+  return 0;
+}
+
+int impulse_fft_dist_execute_parts(impulse_fft_dist h, const void *const *in_parts, void *const *out_parts, double fct) {
+  if (!h || !in_parts || !out_parts) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
+  DeviceGuard guard;
+  const size_t G = h->devs.size();
+  for (size_t g = 0; g < G; ++g)
+    if (h->hi[g] > h->lo[g] && (!in_parts[g] || !out_parts[g])) return fail(IMPULSE_FFT_ERR_INVALID, "null shard pointer");
+  int rc = 0;
+  if (h->mode == IMPULSE_FFT_DIST_SLAB_2D) {
+    rc = slab_run(h, in_parts, out_parts, fct);
+  } else {
+    for (size_t g = 0; g < G && !rc; ++g) {
+      if (!h->plans[g]) continue;
+      cudaError_t e = cudaSetDevice(h->devs[g]);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "cudaSetDevice"); break; }
+      rc = impulse_fft_execute(h->plans[g], in_parts[g], out_parts[g], fct, h->streams[g]);
+    }
+  }
+  const int rs = dist_sync(h);
+  return rc ? rc : rs;
+}
+
+int impulse_fft_dist_execute(impulse_fft_dist h, const void *in, void *out, double fct) {
+  if (!h || !in || !out) return fail(IMPULSE_FFT_ERR_INVALID, "null argument");
+  if (is_device_ptr(in) || is_device_ptr(out))
+    return fail(IMPULSE_FFT_ERR_INVALID, "impulse_fft_dist_execute takes HOST arrays (device shards: impulse_fft_dist_execute_parts)");
+  DeviceGuard guard;
+  const size_t G = h->devs.size();
+  const NdDesc &d = h->desc;
+  if (h->mode == IMPULSE_FFT_DIST_BATCH_SHARD) {
+    // every device runs the ordinary host-pointer call on its shard (chunked H2D -> kernel -> D2H pipeline), one host
+    // thread per device so that the PCIe links of all devices are busy at once
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> msgs(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g) {
+      if (!h->plans[g]) continue;
+      th.emplace_back([&, g] {
+        cudaError_t e = cudaSetDevice(h->devs[g]);
+        if (e != cudaSuccess) { rcs[g] = IMPULSE_FFT_ERR_CUDA; msgs[g] = cudaGetErrorString(e); return; }
+        int node = -1;
+        impulse_fft_bind_host_to_device(h->devs[g], &node);   // staging threads run next to their GPU
+        const unsigned char *pi = (const unsigned char *)in + (ptrdiff_t)h->lo[g] * d.stride_in[0];
+        unsigned char *po = (unsigned char *)out + (ptrdiff_t)h->lo[g] * d.stride_out[0];
+        rcs[g] = impulse_fft_execute(h->plans[g], pi, po, fct, nullptr);
+        if (rcs[g]) msgs[g] = g_err;
+      });
+    }
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; ++g) if (rcs[g]) return fail(rcs[g], "device " + std::to_string(h->devs[g]) + ": " + msgs[g]);
+    return 0;
+  }
+  // SLAB_2D from / to host arrays: H2D of each row slab, the two passes, D2H of each column slab into its columns of
+  // the full output array (strided copy) — the result arrives in natural [R, C] layout
+  const size_t R = d.shape[0], Cc = d.shape[1], rl = R / G, cb = Cc / G, esz = h->esz;
+  if (d.stride_in[1] != (ptrdiff_t)esz || d.stride_out[1] != (ptrdiff_t)esz || d.stride_in[0] < (ptrdiff_t)(Cc * esz) ||
+      d.stride_out[0] < (ptrdiff_t)(Cc * esz))
+    return fail(IMPULSE_FFT_ERR_UNSUPPORTED, "the host path of the slab transform takes row-major arrays (unit stride along dimension 1)");
+  std::vector<const void *> ins(G);
+  std::vector<void *> outs(G);
+  int rc = 0;
+  for (size_t g = 0; g < G && !rc; ++g) {
+    cudaError_t e = cudaSetDevice(h->devs[g]);
+    if (e == cudaSuccess && !h->stage_in[g]) e = cudaMalloc(&h->stage_in[g], rl * Cc * esz);
+    if (e == cudaSuccess && !h->stage_out[g]) e = cudaMalloc(&h->stage_out[g], R * cb * esz);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(h->stage_in[g], Cc * esz, (const unsigned char *)in + (ptrdiff_t)(g * rl) * d.stride_in[0], (size_t)d.stride_in[0],
+                            Cc * esz, rl, cudaMemcpyHostToDevice, h->streams[g]);
+    if (e != cudaSuccess) rc = cuda_fail(e, "slab H2D");
+    ins[g] = h->stage_in[g]; outs[g] = h->stage_out[g];
+  }
+  if (!rc) {
+    // the row plans were built for the descriptor's input strides: the staged slab is dense, so plan it that way
+    for (size_t g = 0; g < G && !rc; ++g) {
+      if (d.stride_in[0] == (ptrdiff_t)(Cc * esz)) continue;
+      cudaSetDevice(h->devs[g]);
+      NdDesc s = d;
+      s.shape[0] = rl; s.axes = {1};
+      s.stride_in = s.stride_out = {(ptrdiff_t)(Cc * esz), (ptrdiff_t)esz};
+      impulse_fft_plan p = nullptr;
+      rc = create_plan(&p, s);
+      if (!rc) { delete h->plans[g]; h->plans[g] = p; }
+    }
+    if (!rc) { h->desc.stride_in = {(ptrdiff_t)(Cc * esz), (ptrdiff_t)esz}; }
+  }
+  if (!rc) rc = slab_run(h, ins.data(), outs.data(), fct);
+  for (size_t g = 0; g < G && !rc; ++g) {
+    cudaError_t e = cudaSetDevice(h->devs[g]);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync((unsigned char *)out + g * cb * esz, (size_t)d.stride_out[0], h->stage_out[g], cb * esz, cb * esz, R,
+                            cudaMemcpyDeviceToHost, h->streams[g]);
+    if (e != cudaSuccess) rc = cuda_fail(e, "slab D2H");
+  }
+  const int rs = dist_sync(h);
+  return rc ? rc : rs;
 }
 
 // ---- the ten pocketfft symbols (include/pocketfft.h) -------------------------

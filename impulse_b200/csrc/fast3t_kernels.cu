@@ -72,7 +72,9 @@ int launch_fast3_staged_job(const LineJob &J, int sm_count, void *stream) {
   if (mode == 0) return -1;
   const int kind = J.store_mode == ST_R2C_EVEN ? F3_R2C : J.load_mode == LD_HERM_EVEN ? F3_C2R : F3_C2C;
   const bool bwd = kind == F3_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == F3_R2C ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
-  // per-shape default when mode < 0: DEF = 0 off, 1 = staged, 2 = staged + second exchange buffer
+  // per-shape default when mode < 0: DEF = 0 off, 1 = staged, 2 = staged + second exchange buffer — the better of the
+  // two on the B200 (profiles/r02_ab_tma.txt: r2c 3888 4.12 -> 4.71 TB/s, c2r 3888 4.22 -> 4.58, c2r 4096 4.92 -> 5.48,
+  // r2c 4096 5.19 -> 5.37, real 1000 +3-7 %, c2c 2048 6.17 -> 6.56, r2c 4096 fp32 4.70 -> 5.24)
 #define STAGED(DEF, T, R1, R2, R3, E, KIND, MINB1, MINB2)                                                   \
   {                                                                                                          \
     const int m = mode < 0 ? DEF : mode;                                                                     \
@@ -88,16 +90,16 @@ int launch_fast3_staged_job(const LineJob &J, int sm_count, void *stream) {
   }
   switch (J.fast_id) {
     case FAST3_2048_F64:   // real rows of 4096 points (config 1) and complex rows of 2048
-      if (kind == F3_R2C) STAGED(0, double, 16, 16, 8, 16, F3_R2C, 3, 2)
-      if (kind == F3_C2C) STAGED1(0, double, 16, 16, 8, 16, F3_C2C, 3)
+      if (kind == F3_R2C) STAGED(2, double, 16, 16, 8, 16, F3_R2C, 3, 2)
+      if (kind == F3_C2C) STAGED1(1, double, 16, 16, 8, 16, F3_C2C, 3)
       return -1;
-    case FAST3C_2048_F64: if (kind == F3_C2R) STAGED(0, double, 8, 16, 16, 16, F3_C2R, 3, 2) return -1;
-    case FAST3R_500_F64: if (kind == F3_R2C) STAGED(0, double, 10, 10, 5, 10, F3_R2C, 8, 8) return -1;      // config 3a
-    case FAST3_500_F64: if (kind == F3_C2R) STAGED(0, double, 5, 10, 10, 10, F3_C2R, 8, 8) return -1;
-    case FAST3R_1944_F64: if (kind == F3_R2C) STAGED(0, double, 18, 18, 6, 18, F3_R2C, 3, 2) return -1;     // config 3b
-    case FAST3_1944_F64: if (kind == F3_C2R) STAGED(0, double, 6, 18, 18, 18, F3_C2R, 3, 2) return -1;
-    case FAST3_2048_F32: if (kind == F3_R2C) STAGED(0, float, 16, 16, 8, 16, F3_R2C, 4, 4) return -1;       // config 5 rows
-    case FAST3C_2048_F32: if (kind == F3_C2R) STAGED(0, float, 8, 16, 16, 16, F3_C2R, 4, 4) return -1;
+    case FAST3C_2048_F64: if (kind == F3_C2R) STAGED(1, double, 8, 16, 16, 16, F3_C2R, 3, 2) return -1;
+    case FAST3R_500_F64: if (kind == F3_R2C) STAGED(2, double, 10, 10, 5, 10, F3_R2C, 8, 8) return -1;      // config 3a
+    case FAST3_500_F64: if (kind == F3_C2R) STAGED(2, double, 5, 10, 10, 10, F3_C2R, 8, 8) return -1;
+    case FAST3R_1944_F64: if (kind == F3_R2C) STAGED(1, double, 18, 18, 6, 18, F3_R2C, 3, 2) return -1;     // config 3b
+    case FAST3_1944_F64: if (kind == F3_C2R) STAGED(1, double, 6, 18, 18, 18, F3_C2R, 3, 2) return -1;
+    case FAST3_2048_F32: if (kind == F3_R2C) STAGED(2, float, 16, 16, 8, 16, F3_R2C, 4, 4) return -1;       // config 5 rows
+    case FAST3C_2048_F32: if (kind == F3_C2R) STAGED(2, float, 8, 16, 16, 16, F3_C2R, 4, 4) return -1;
     default: return -1;
   }
 #undef STAGED

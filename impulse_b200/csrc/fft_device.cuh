@@ -704,9 +704,26 @@ IMP_HD void aux_one(const AuxJob &A, uint64_t idx) {
         Z[(int64_t)km * ew] = cadd(s, mul_pi(cmul(wm, d)));
       }
     } break;
-    case AUX_R2C_PRE_ODD:
-      ((cx<T> *)A.out)[ow + (int64_t)e * ew] = mk<T>(((const T *)A.in)[ou + (int64_t)e * eu], (T)0);
-      break;
+    case AUX_R2C_PRE_ODD: {
+      T xv = ((const T *)A.in)[ou + (int64_t)e * eu];
+      if ((A.flags & F_NEG_EVEN_IN) && e > 0 && !(e & 1)) xv = -xv;
+      ((cx<T> *)A.out)[ow + (int64_t)e * ew] = mk<T>(xv, (T)0);
+    } break;
+    case AUX_R2C_PACK_EVEN: {   // e = m in 0..M
+      const T *x = (const T *)A.in + ou;
+      cx<T> v = mk<T>(x[(2 * (int64_t)e) * eu], x[(2 * (int64_t)e + 1) * eu]);
+      if ((A.flags & F_NEG_EVEN_IN) && e > 0) v.x = -v.x;
+      ((cx<T> *)A.out)[ow + (int64_t)e * ew] = v;
+    } break;
+    case AUX_C2R_UNPACK_EVEN: { // e = m in 0..M
+      cx<T> v = ((const cx<T> *)A.in)[ow + (int64_t)e * ew];
+      const T f = (T)A.fct;
+      v.x *= f; v.y *= f;
+      if ((A.flags & F_NEG_EVEN_OUT) && e > 0) v.x = -v.x;
+      T *x = (T *)A.out + ou;
+      x[(2 * (int64_t)e) * eu] = v.x;
+      x[(2 * (int64_t)e + 1) * eu] = v.y;
+    } break;
     case AUX_R2C_POST_ODD:
       aux_store_bin<T>(A, ou, eu, e, ((const cx<T> *)A.in)[ow + (int64_t)e * ew]);
       break;
@@ -716,9 +733,11 @@ IMP_HD void aux_one(const AuxJob &A, uint64_t idx) {
       Z[(int64_t)e * ew] = v;
       if (e > 0) Z[(int64_t)(N - e) * ew] = cconj(v);
     } break;
-    case AUX_C2R_POST_ODD:
-      ((T *)A.out)[ou + (int64_t)e * eu] = ((const cx<T> *)A.in)[ow + (int64_t)e * ew].x * (T)A.fct;
-      break;
+    case AUX_C2R_POST_ODD: {
+      T y = ((const cx<T> *)A.in)[ow + (int64_t)e * ew].x * (T)A.fct;
+      if ((A.flags & F_NEG_EVEN_OUT) && e > 0 && !(e & 1)) y = -y;
+      ((T *)A.out)[ou + (int64_t)e * eu] = y;
+    } break;
     case AUX_BLUE_PRE: {        // e = n in 0..n2
       cx<T> v = mk<T>((T)0, (T)0);
       if (e < N) {

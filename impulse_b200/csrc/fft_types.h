@@ -242,6 +242,10 @@ enum AuxMode : int {
   AUX_C2R_POST_ODD = 6,   // real parts
   AUX_BLUE_PRE = 7,       // w[n] = x[n] * conj(b[n]) (n < L), 0 (L <= n < n2)      pocketfft.c:1954-1968
   AUX_BLUE_POST = 8,      // y[k] = w[k] * conj(b[k]) * fct (k < L)                 pocketfft.c:1993-2005
+  // long even real lines whose real side cannot be addressed as packed complex pairs (strided axis, odd row
+  // stride, negated elements): gather / scatter between the strided real line and the complex work line
+  AUX_R2C_PACK_EVEN = 9,    // Z[m] = (x[2m], x[2m+1]), m < M
+  AUX_C2R_UNPACK_EVEN = 10, // x[2m] = Re Z[m] * fct, x[2m+1] = Im Z[m] * fct
 };
 constexpr int kMaxAuxDims = 8;
 struct AuxJob {

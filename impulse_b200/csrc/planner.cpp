@@ -1047,15 +1047,20 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     }
     // ---- long real lines: the complex transform runs through c2c_line on a work array [lines][L] (or, for
     // even N, directly on the packed view of the real side), with elementwise conversion passes around it
-    if (layout == RL_HALFCOMPLEX_NEG) { *err = "r2r_fftpack with real2hermitian != forward is limited to lines that fit one CTA"; return ERR_UNSUPPORTED; }
     const bool r2c = kind == KIND_R2C;
+    // r2r_fftpack with real2hermitian != forward: elements 2, 4, ... of the REAL side change sign (hdronly.h:3134-3140);
+    // the conversion passes carry that, the spectrum side is plain halfcomplex
+    const bool neg = layout == RL_HALFCOMPLEX_NEG;
+    if (neg) layout = RL_HALFCOMPLEX;
+    const uint32_t neg_in = (neg && r2c) ? (uint32_t)F_NEG_EVEN_IN : 0u, neg_out = (neg && !r2c) ? (uint32_t)F_NEG_EVEN_OUT : 0u;
     const void *twr = nullptr;
     if (even) { rc = real_twiddle(N, d.dtype, &twr, err); if (rc) return rc; }
     uint64_t nlines = 1;
-    std::vector<Dim> d_uw, d_ww, d_view_in, d_view_out;   // (user, work), (work, work), packed complex views of the real side
+    std::vector<Dim> d_uw, d_ww, d_rw, d_view_in, d_view_out;   // (spectrum side, work), (work, work), (real side, work), packed complex views of the real side
     bool view_ok = true;
     for (auto &dm : dims) {
       d_uw.push_back({dm.n, r2c ? dm.sout : dm.sin, (int64_t)(nlines * L)});
+      d_rw.push_back({dm.n, r2c ? dm.sin : dm.sout, (int64_t)(nlines * L)});
       d_ww.push_back({dm.n, (int64_t)(nlines * L), (int64_t)(nlines * L)});
       if ((r2c ? dm.sin : dm.sout) % 2) view_ok = false;
       d_view_in.push_back({dm.n, dm.sin / 2, (int64_t)(nlines * L)});
@@ -1064,27 +1069,36 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     }
     plan->tmp4_bytes = std::max<size_t>(plan->tmp4_bytes, (size_t)nlines * L * csize_g);
     if (even) {
-      if ((r2c ? es_in : es_out) != 1 || !view_ok) {
-        *err = "real lines of more than " + std::to_string(2 * (budget_g / csize_g - S_g - 1)) +
-               " points must be contiguous with even row strides";
-        return ERR_UNSUPPORTED;
-      }
+      // contiguous lines with even row strides: the real side IS a packed complex array (no gather pass).  Anything
+      // else — a strided axis, odd row strides, negated elements — is gathered into / scattered from the work array by
+      // one more elementwise pass, as general_r2c / general_c2r accept any byte stride (hdronly.h:3125-3250).
+      const bool view = (r2c ? es_in : es_out) == 1 && view_ok && !neg && !env_int("IMPULSE_FFT_NO_REAL_VIEW", 0);
       if (r2c) {
-        plan->cplx_view_in = true;
-        rc = c2c_line(true, L, 1, 1, d_view_in, csize_g, csize_g, src, BUF_TMP4, false, 0);
+        if (view) {
+          plan->cplx_view_in = true;
+          rc = c2c_line(true, L, 1, 1, d_view_in, csize_g, csize_g, src, BUF_TMP4, false, 0);
+        } else {
+          rc = emit_aux(AUX_R2C_PACK_EVEN, layout, neg_in, N, L, L, d_rw, es_in, 1, nullptr, src, BUF_TMP4, false);
+          if (rc) return rc;
+          rc = c2c_line(true, L, 1, 1, d_ww, csize_g, csize_g, BUF_TMP4, BUF_TMP4, false, 0);
+        }
         if (rc) return rc;
         return emit_aux(AUX_R2C_POST_EVEN, layout, forward ? 0u : (uint32_t)F_CONJ_RESULT, N, L, L + 1, d_uw, es_out, 1, twr,
                         BUF_TMP4, dst, takes_fct);
       }
-      plan->cplx_view_out = true;
       rc = emit_aux(AUX_C2R_PRE_EVEN, layout, forward ? (uint32_t)F_CONJ_IN : 0u, N, L, L / 2 + 1, d_uw, es_in, 1, twr, src,
                     BUF_TMP4, false);
       if (rc) return rc;
-      return c2c_line(false, L, 1, 1, d_view_out, csize_g, csize_g, BUF_TMP4, dst, takes_fct, 0);
+      if (view) {
+        plan->cplx_view_out = true;
+        return c2c_line(false, L, 1, 1, d_view_out, csize_g, csize_g, BUF_TMP4, dst, takes_fct, 0);
+      }
+      rc = c2c_line(false, L, 1, 1, d_ww, csize_g, csize_g, BUF_TMP4, BUF_TMP4, false, 0);
+      if (rc) return rc;
+      return emit_aux(AUX_C2R_UNPACK_EVEN, layout, neg_out, N, L, L, d_rw, es_out, 1, nullptr, BUF_TMP4, dst, takes_fct);
     }
     if (r2c) {
-      rc = emit_aux(AUX_R2C_PRE_ODD, layout, 0, N, L, N, [&] { std::vector<Dim> v; uint64_t nl = 1; for (auto &dm : dims) { v.push_back({dm.n, dm.sin, (int64_t)(nl * L)}); nl *= dm.n; } return v; }(),
-                    es_in, 1, nullptr, src, BUF_TMP4, false);
+      rc = emit_aux(AUX_R2C_PRE_ODD, layout, neg_in, N, L, N, d_rw, es_in, 1, nullptr, src, BUF_TMP4, false);
       if (rc) return rc;
       rc = c2c_line(true, L, 1, 1, d_ww, csize_g, csize_g, BUF_TMP4, BUF_TMP4, false, 0);
       if (rc) return rc;
@@ -1096,8 +1110,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     if (rc) return rc;
     rc = c2c_line(false, L, 1, 1, d_ww, csize_g, csize_g, BUF_TMP4, BUF_TMP4, false, 0);
     if (rc) return rc;
-    return emit_aux(AUX_C2R_POST_ODD, layout, 0, N, L, N, [&] { std::vector<Dim> v; uint64_t nl = 1; for (auto &dm : dims) { v.push_back({dm.n, dm.sout, (int64_t)(nl * L)}); nl *= dm.n; } return v; }(),
-                    es_out, 1, nullptr, BUF_TMP4, dst, takes_fct);
+    return emit_aux(AUX_C2R_POST_ODD, layout, neg_out, N, L, N, d_rw, es_out, 1, nullptr, BUF_TMP4, dst, takes_fct);
   };
 
   int rc = ST_OK;

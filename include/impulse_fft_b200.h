@@ -187,6 +187,27 @@ int impulse_fft_ipc_close(void *ptr);
  * pointers into other GPUs' memory. */
 int impulse_fft_enable_peer_access(int peer_device);
 
+/* Single-process multi-GPU driver over the devices of one NVSwitch box.  Two partitionings:
+ *   BATCH_SHARD  any transform whose dimension 0 is a batch dimension (not in `axes`): its shape[0] entries are split
+ *                contiguously over the devices, device g holding [g*B/G, (g+1)*B/G); no communication.
+ *   SLAB_2D      one 2-D complex transform over both axes, split into row slabs; row FFTs locally, then every device's
+ *                column kernels load their column block out of all row slabs over NVLink (peer access; no pack, no
+ *                all-to-all buffer).  Rows and columns must be divisible by ndev.
+ * The reference's counterpart is general_nd splitting the lines of one call over its thread pool
+ * (pocketfft_hdronly.h:3012-3050); `desc` is what impulse_fft_plan_create takes, for the WHOLE array.
+ *   execute        whole arrays in HOST memory; every device stages its shard (one host thread per device for
+ *                  BATCH_SHARD).  SLAB_2D returns the result in natural [R, C] layout.  Synchronous.
+ *   execute_parts  per-device DEVICE pointers: in_parts[g] = the shard of device g (strides of `desc`); out_parts[g] =
+ *                  the transformed shard (BATCH_SHARD, strides of `desc`) or the dense column slab [R, C/ndev] holding
+ *                  columns [g*C/ndev, (g+1)*C/ndev) (SLAB_2D).  Returns after every device has finished. */
+typedef struct impulse_fft_dist_s *impulse_fft_dist;
+typedef enum { IMPULSE_FFT_DIST_BATCH_SHARD = 0, IMPULSE_FFT_DIST_SLAB_2D = 1 } impulse_fft_dist_mode;
+int impulse_fft_dist_create(impulse_fft_dist *out, int mode, const impulse_fft_desc *desc, int ndev, const int *devices);
+int impulse_fft_dist_execute(impulse_fft_dist dist, const void *in, void *out, double fct);
+int impulse_fft_dist_execute_parts(impulse_fft_dist dist, const void *const *in_parts, void *const *out_parts, double fct);
+int impulse_fft_dist_shard(impulse_fft_dist dist, int index, size_t *lo, size_t *hi);   /* rows of dimension 0 held by devices[index] */
+int impulse_fft_dist_destroy(impulse_fft_dist dist);
+
 /* Host-side placement for host-pointer calls: binds the CALLING thread (and threads it creates later) to the CPUs of
  * the NUMA node that `device`'s PCIe root belongs to (sysfs), so that pinned buffers allocated afterwards are local to
  * the GPU that will DMA them.  With one process per GPU this keeps 8 ranks from sharing node 0.  *numa_node receives

@@ -104,6 +104,43 @@ def test_halfcomplex_packed_roundtrip_all_classes(checker):
         assert oracle.rel_l2(d[0], odata[:n]) <= 2e-15 * max(1, np.log2(n)), n
 
 
+def test_real_layouts_times_forward_flag(checker, monkeypatch):
+    """Every r2c output layout and c2r input layout with BOTH values of `forward` (include/impulse_fft_b200.h: forward = 0
+    is exp(+...)): r2c(forward=False) stores the conjugate spectrum in the Hermitian, halfcomplex AND full-symmetric
+    layouts, c2r(forward=True) conjugates its input in both input layouts, so r2c(fwd=f) and c2r(fwd=not f) round-trip.
+    Short lines (one launch) and the long-line aux path (IMPULSE_FFT_FORCE_BIGREAL)."""
+    rng = np.random.default_rng(81)
+
+    def pack(spec, n):          # N/2+1 complex bins -> FFTPACK halfcomplex reals
+        out = np.empty(spec.shape[:-1] + (n,))
+        out[..., 0] = spec[..., 0].real
+        k = (n - 1) // 2
+        out[..., 1:2 * k:2] = spec[..., 1:k + 1].real
+        out[..., 2:2 * k + 1:2] = spec[..., 1:k + 1].imag
+        if n % 2 == 0:
+            out[..., n - 1] = spec[..., n // 2].real
+        return out
+
+    for force in ("0", "1"):
+        monkeypatch.setenv("IMPULSE_FFT_FORCE_BIGREAL", force)
+        for n in (8, 9, 30, 64, 89, 100, 191, 256):
+            x = rnd(rng, (3, n), np.float64)
+            for fwd in (True, False):
+                want = checker.r2c(x, [1], fwd, 0.5)          # conjugate spectrum for forward=False (hdronly.h:3152-3155)
+                got = emu.nd("r2c", x, np.zeros((3, n // 2 + 1), np.complex128), x.shape, [1], fwd, 0.5)
+                assert oracle.max_row_rel_l2(got, want) <= tol(n), (n, fwd, "hermitian")
+                hc = emu.nd("r2c", x, np.zeros((3, n)), x.shape, [1], fwd, 0.5, layout="halfcomplex")
+                assert oracle.max_row_rel_l2(hc, pack(want, n)) <= tol(n), (n, fwd, "halfcomplex")
+                full = np.concatenate([want, np.conj(want[:, 1:(n + 1) // 2][:, ::-1])], axis=1)
+                fs = emu.nd("r2c", x, np.zeros((3, n), np.complex128), x.shape, [1], fwd, 0.5, layout="fullsym")
+                assert oracle.max_row_rel_l2(fs, full) <= tol(n), (n, fwd, "fullsym")
+                # the matching inverse: c2r with the opposite flag undoes it in either input layout
+                back = emu.nd("c2r", hc, np.zeros((3, n)), x.shape, [1], not fwd, 2.0 / n, layout="halfcomplex")
+                assert oracle.max_row_rel_l2(back, x) <= tol(n), (n, fwd, "halfcomplex round trip")
+                back = emu.nd("c2r", got, np.zeros((3, n)), x.shape, [1], not fwd, 2.0 / n)
+                assert oracle.max_row_rel_l2(back, x) <= tol(n), (n, fwd, "hermitian round trip")
+
+
 def test_fullsym_layout(checker):
     rng = np.random.default_rng(8)
     for n in (1, 2, 3, 4, 5, 8, 9, 16, 30, 89, 191):
@@ -406,13 +443,45 @@ def test_long_real_path_forced_on_short_lines(n, monkeypatch):
     assert oracle.rel_l2(full, np.fft.fft(x, axis=2)) < 1e-12
     hart = emu.r2r_real("separable_hartley", x, np.empty_like(x), [2])
     assert oracle.rel_l2(hart, oracle.hartley_numpy(x, [2])) < 1e-12
-    y = rng.standard_normal((n, 4))                       # strided axis: only the even-N view needs contiguity
-    if n % 2:
-        spec = emu.nd("r2c", y, np.empty((n // 2 + 1, 4), np.complex128), [n, 4], [0], True, 1.0)
-        assert oracle.rel_l2(spec, np.fft.rfft(y, axis=0)) < 1e-12
-    else:
-        with pytest.raises(emu.EmuError):
-            emu.nd("r2c", y, np.empty((n // 2 + 1, 4), np.complex128), [n, 4], [0], True, 1.0)
+    # strided axis, and rows an odd number of elements apart: even N takes the gather / scatter passes (the packed
+    # complex view of the real side needs contiguous lines and even row strides), as general_r2c / general_c2r accept
+    # any byte stride (pocketfft_hdronly.h:3125-3250)
+    y = rng.standard_normal((n, 4))
+    spec = emu.nd("r2c", y, np.empty((n // 2 + 1, 4), np.complex128), [n, 4], [0], True, 1.0)
+    assert oracle.rel_l2(spec, np.fft.rfft(y, axis=0)) < 1e-12
+    back = emu.nd("c2r", spec, np.empty_like(y), [n, 4], [0], False, 1.0 / n)
+    assert oracle.rel_l2(back, y) < 1e-12
+    wide = rng.standard_normal((3, n + 1))
+    yv = wide[:, :n]                                      # row stride n + 1: odd for even n
+    spec = emu.nd("r2c", yv, np.empty((3, n // 2 + 1), np.complex128), [3, n], [1], False, 2.0)
+    assert oracle.rel_l2(spec, 2.0 * np.conj(np.fft.rfft(yv, axis=1))) < 1e-12
+    outw = np.zeros((3, n + 1))
+    back = emu.nd("c2r", np.conj(spec), outw[:, :n], [3, n], [1], False, 0.5 / n)
+    assert oracle.rel_l2(back, yv) < 1e-12 and not outw[:, n].any()
+    # r2r_fftpack with real2hermitian != forward (negated elements 2, 4, ... of the real side) on this path
+    a = rng.standard_normal((2, n))
+    for r2h in (True, False):
+        for fwd in (True, False):
+            got = emu.r2r_real("fftpack", a, np.empty_like(a), [1], r2h, fwd, 0.25)
+            assert oracle.rel_l2(got, oracle.fftpack_numpy(a, [1], r2h, fwd, 0.25)) < 2e-13, (r2h, fwd)
+
+
+def test_long_even_real_lines_at_any_stride():
+    """r2c over axis 0 of a [40000, 4] array and a [3, 40000] array with an odd row stride used to
+    return ERR_UNSUPPORTED; pocketfft takes any byte stride."""
+    rng = np.random.default_rng(40000)
+    y = rng.standard_normal((40000, 4))
+    spec = emu.nd("r2c", y, np.empty((20001, 4), np.complex128), [40000, 4], [0], True, 1.0)
+    assert oracle.rel_l2(spec, np.fft.rfft(y, axis=0)) < 1e-12 * 16
+    back = emu.nd("c2r", spec, np.empty_like(y), [40000, 4], [0], False, 1.0 / 40000)
+    assert oracle.rel_l2(back, y) < 1e-12 * 16
+    wide = rng.standard_normal((3, 40001))
+    yv = wide[:, :40000]
+    spec = emu.nd("r2c", yv, np.empty((3, 20001), np.complex128), [3, 40000], [1], True, 1.0)
+    assert oracle.rel_l2(spec, np.fft.rfft(yv, axis=1)) < 1e-12 * 16
+    a = rng.standard_normal((1, 32768))                  # r2r_fftpack, real2hermitian != forward, beyond one CTA
+    got = emu.r2r_real("fftpack", a, np.empty_like(a), [1], True, False, 1.0)
+    assert oracle.rel_l2(got, oracle.fftpack_numpy(a, [1], True, False, 1.0)) < 1e-12 * 16
 
 
 @pytest.mark.parametrize("n", [89, 191, 4099, 100003, 20011])
