@@ -582,12 +582,13 @@ def slab_entries(cx: Ctx, steps, warmup):
     out["single_gpu_ms"] = round(ms1, 5)
     # the oracle's answer, once, on rank 0: gather the row slabs
     want = None
-    xs = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
-    dist.gather(x, xs, dst=0)
+    xr = torch.view_as_real(x)           # NCCL has no complex types: gather the (re, im) view
+    xs = [torch.empty_like(xr) for _ in range(world)] if rank == 0 else None
+    dist.gather(xr, xs, dst=0)
     if rank == 0:
         from oracle import oracle
         chk = oracle.load()
-        xfull = torch.cat(xs, dim=0).cpu().numpy()
+        xfull = torch.view_as_complex(torch.cat(xs, dim=0)).cpu().numpy()
         with all_cpus():
             want = chk.c2c(xfull, [0, 1], True, 1.0, nthreads=0)
         del xfull
@@ -600,14 +601,15 @@ def slab_entries(cx: Ctx, steps, warmup):
         ms, launches, _ = time_steps(cx, fn, steps, warmup)
         cols = fn()                                   # [rows, n / world]: this rank's column slab of the result
         torch.cuda.synchronize()
-        parts = [torch.empty_like(cols) for _ in range(world)] if rank == 0 else None
-        dist.gather(cols.contiguous(), parts, dst=0)
+        cr = torch.view_as_real(cols.contiguous())
+        parts = [torch.empty_like(cr) for _ in range(world)] if rank == 0 else None
+        dist.gather(cr, parts, dst=0)
         ent = {"ms_per_step": round(ms, 5), "GB/s": round(total_bytes / (ms * 1e-3) / 1e9, 1), "scaling": "strong",
                "speedup_vs_single_gpu": round(ms1 / ms, 3), "launches_per_step_per_rank": round(launches / steps, 2),
                "result_layout": "column slabs", "how": how}
         if rank == 0:
             from oracle import oracle
-            got = torch.cat(parts, dim=1).cpu().numpy()
+            got = torch.view_as_complex(torch.cat(parts, dim=1)).cpu().numpy()
             err = float(oracle.rel_l2(got, want))
             rowerr = float(oracle.max_row_rel_l2(got, want))
             bound = 1e-12 * 13

@@ -197,3 +197,55 @@ class SlabFFT2P2P:
         _lib.check(L.impulse_fft_cols_from_parts(self.code, self.world, parts, self.rl, self.c, self.rank * self.cb, self.cb,
                                                  out.data_ptr(), self.cb, int(forward), 1.0, stream))
         return out
+
+
+class DistPlan:
+    """The single-process multi-GPU driver of the C ABI (``impulse_fft_dist_create / execute / execute_parts /
+    destroy``, include/impulse_fft_b200.h): what a Nim / C host with several B200s calls — no torch.distributed, no
+    second process.  ``mode`` is "batch" (dimension 0 split over the devices, no communication) or "slab" (one 2-D
+    complex transform, row slabs, exchange fused into the column kernels over peer memory).  Host numpy arrays in and
+    out for ``__call__``; per-device CUDA tensors for ``run_parts``."""
+
+    MODES = {"batch": 0, "slab": 1}
+
+    def __init__(self, mode: str, kind: int, dtype_code: int, shape, stride_in, stride_out, axes, forward: bool, devices,
+                 layout: int = _lib.HERMITIAN):
+        L = self.L = _lib.lib()
+        d = _lib.Desc()
+        d.kind, d.dtype, d.real_layout, d.forward = kind, dtype_code, layout, int(forward)
+        d.ndim, d.naxes = len(shape), len(axes)
+        for i, (s, a, b) in enumerate(zip(shape, stride_in, stride_out)):
+            d.shape[i], d.stride_in[i], d.stride_out[i] = s, a, b
+        for i, a in enumerate(axes):
+            d.axes[i] = a
+        self.devices = [int(x) for x in devices]
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        self.h = C.c_void_p()
+        _lib.check(L.impulse_fft_dist_create(C.byref(self.h), self.MODES[mode], C.byref(d), len(self.devices), devs))
+
+    def shard(self, index: int):
+        lo, hi = C.c_size_t(), C.c_size_t()
+        _lib.check(self.L.impulse_fft_dist_shard(self.h, index, C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def __call__(self, a_in, a_out, fct: float = 1.0):
+        _lib.check(self.L.impulse_fft_dist_execute(self.h, a_in.ctypes.data, a_out.ctypes.data, float(fct)))
+        return a_out
+
+    def run_parts(self, ins, outs, fct: float = 1.0):
+        n = len(self.devices)
+        pi = (C.c_void_p * n)(*[t.data_ptr() if t is not None else None for t in ins])
+        po = (C.c_void_p * n)(*[t.data_ptr() if t is not None else None for t in outs])
+        _lib.check(self.L.impulse_fft_dist_execute_parts(self.h, pi, po, float(fct)))
+        return outs
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            self.L.impulse_fft_dist_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 — interpreter shutdown
+            pass
