@@ -165,6 +165,50 @@ IMP_HD void phase_prolog(const LineJob &J, const TileCtx &tc, uint32_t tid, int6
 // ---------------------------------------------------------------------------
 // LOAD
 // ---------------------------------------------------------------------------
+// DCT / DST embeddings (shared by the line kernel's LOAD phase and the elementwise pass of long lines): element e of the
+// M-point complex line built from the real input line (LD_X_* of fft_types.h).  JB = LineJob or AuxJob (same field names).
+template <typename T, typename JB>
+IMP_HD cx<T> x_embed(const JB &J, int mode, const T *inr, int64_t off, int64_t es, uint32_t e, uint32_t N, uint32_t M) {
+  switch (mode) {
+    case LD_X_ZPAD:
+      return e < N ? mk<T>(inr[off + (int64_t)e * es], (T)0) : mk<T>((T)0, (T)0);
+    case LD_X_TW: {
+      if (e >= N) return mk<T>((T)0, (T)0);
+      const T f = (T)(e == 0 ? J.x_f0 : J.x_f);
+      const cx<T> w = IMP_LDG((const cx<T> *)J.x_tw + 2 * e);
+      const T xv = inr[off + (int64_t)e * es] * f;
+      return mk<T>(xv * w.x, xv * w.y);
+    }
+    case LD_X_TW_SHIFT: {
+      if (e < 1 || e > N) return mk<T>((T)0, (T)0);
+      const T f = (T)(e == N ? J.x_fl : J.x_f) * (T)(e == 1 ? J.x_f0 : 1.0);
+      const cx<T> w = IMP_LDG((const cx<T> *)J.x_tw + 2 * e);
+      const T xv = inr[off + (int64_t)(e - 1) * es] * f;
+      return mk<T>(xv * w.x, xv * w.y);
+    }
+    case LD_X_SYM: {
+      const uint32_t j = e < N ? e : M - e;
+      const T f = (T)((j == 0 || j == N - 1) ? J.x_f0 : 1.0);
+      return mk<T>(inr[off + (int64_t)j * es] * f, (T)0);
+    }
+    default: {  // LD_X_ASYM
+      T xv = (T)0;
+      if (e >= 1 && e <= N) xv = inr[off + (int64_t)(e - 1) * es];
+      else if (e > N + 1) xv = -inr[off + (int64_t)(M - e - 1) * es];
+      return mk<T>(xv, (T)0);
+    }
+  }
+}
+// ... and real output e from bin e + x_shift of the transformed line (ST_X); f = the caller's scale factor
+template <typename T, typename JB>
+IMP_HD T x_extract(const JB &J, cx<T> v, uint32_t e, uint32_t N, T f) {
+  if (J.x_wadd != 0xffffffffu) v = cmul(v, IMP_LDG((const cx<T> *)J.x_tw + (2 * e + J.x_wadd)));
+  T y = (J.x_im ? -v.y : v.x) * (T)J.x_s * f;
+  if (e == 0) y *= (T)J.x_s0;
+  if (e == N - 1) y *= (T)J.x_sn;
+  return y;
+}
+
 template <typename T>
 IMP_HD void load_one(const LineJob &J, cx<T> *S /*line base*/, int64_t off, uint32_t e) {
   const bool cin = J.flags & F_CONJ_IN, cseq = J.flags & F_CONJ_SEQ;
@@ -224,45 +268,9 @@ IMP_HD void load_one(const LineJob &J, cx<T> *S /*line base*/, int64_t off, uint
       S[phys<T>(J, e)] = v;
       if (e > 0) S[phys<T>(J, J.n_real - e)] = cconj(v);
     } break;
-    case LD_X_ZPAD: {
-      const uint32_t N = J.n_real;
-      S[phys<T>(J, e)] = e < N ? mk<T>(inr[off + (int64_t)e * es], (T)0) : mk<T>((T)0, (T)0);
-    } break;
-    case LD_X_TW: {
-      const uint32_t N = J.n_real;
-      cx<T> v = mk<T>((T)0, (T)0);
-      if (e < N) {
-        const T f = (T)(e == 0 ? J.x_f0 : J.x_f);
-        const cx<T> w = IMP_LDG((const cx<T> *)J.x_tw + 2 * e);
-        const T xv = inr[off + (int64_t)e * es] * f;
-        v = mk<T>(xv * w.x, xv * w.y);
-      }
-      S[phys<T>(J, e)] = v;
-    } break;
-    case LD_X_TW_SHIFT: {
-      const uint32_t N = J.n_real;
-      cx<T> v = mk<T>((T)0, (T)0);
-      if (e >= 1 && e <= N) {
-        const T f = (T)(e == N ? J.x_fl : J.x_f) * (T)(e == 1 ? J.x_f0 : 1.0);
-        const cx<T> w = IMP_LDG((const cx<T> *)J.x_tw + 2 * e);
-        const T xv = inr[off + (int64_t)(e - 1) * es] * f;
-        v = mk<T>(xv * w.x, xv * w.y);
-      }
-      S[phys<T>(J, e)] = v;
-    } break;
-    case LD_X_SYM: {
-      const uint32_t N = J.n_real, M = J.n_seq;
-      const uint32_t j = e < N ? e : M - e;
-      const T f = (T)((j == 0 || j == N - 1) ? J.x_f0 : 1.0);
-      S[phys<T>(J, e)] = mk<T>(inr[off + (int64_t)j * es] * f, (T)0);
-    } break;
-    case LD_X_ASYM: {
-      const uint32_t N = J.n_real, M = J.n_seq;
-      T xv = (T)0;
-      if (e >= 1 && e <= N) xv = inr[off + (int64_t)(e - 1) * es];
-      else if (e > N + 1) xv = -inr[off + (int64_t)(M - e - 1) * es];
-      S[phys<T>(J, e)] = mk<T>(xv, (T)0);
-    } break;
+    case LD_X_ZPAD: case LD_X_TW: case LD_X_TW_SHIFT: case LD_X_SYM: case LD_X_ASYM:
+      S[phys<T>(J, e)] = x_embed<T>(J, J.load_mode, inr, off, es, e, J.n_real, J.n_seq);
+      break;
     default: break;
   }
 }
@@ -534,14 +542,9 @@ IMP_HD void store_one(const LineJob &J, const cx<T> *S, int64_t off, uint32_t e,
       else if (e == J.n_seq) outr[off + (int64_t)(J.n_real - 1) * es] = v.x;
       else { outr[off + (2 * (int64_t)e - 1) * es] = v.x; outr[off + (2 * (int64_t)e) * es] = v.y; }
     } break;
-    case ST_X: {
-      cx<T> v = read_bin<T>(J, S, e + J.x_shift);
-      if (J.x_wadd != 0xffffffffu) v = cmul(v, IMP_LDG((const cx<T> *)J.x_tw + (2 * e + J.x_wadd)));
-      T y = (J.x_im ? -v.y : v.x) * (T)J.x_s * f;
-      if (e == 0) y *= (T)J.x_s0;
-      if (e == J.n_real - 1) y *= (T)J.x_sn;
-      outr[off + (int64_t)e * es] = y;
-    } break;
+    case ST_X:
+      outr[off + (int64_t)e * es] = x_extract<T>(J, read_bin<T>(J, S, e + J.x_shift), e, J.n_real, f);
+      break;
     case ST_HC_FULL: {
       cx<T> v = read_bin<T>(J, S, e);
       v.x *= f; v.y *= cres ? -f : f;   // r2c with forward=false packs the conjugate spectrum
@@ -738,6 +741,12 @@ IMP_HD void aux_one(const AuxJob &A, uint64_t idx) {
       if ((A.flags & F_NEG_EVEN_OUT) && e > 0 && !(e & 1)) y = -y;
       ((T *)A.out)[ou + (int64_t)e * eu] = y;
     } break;
+    case AUX_X_EMBED:           // e in 0..M
+      ((cx<T> *)A.out)[ow + (int64_t)e * ew] = x_embed<T>(A, A.x_load, (const T *)A.in, ou, eu, e, N, M);
+      break;
+    case AUX_X_EXTRACT:         // e in 0..N
+      ((T *)A.out)[ou + (int64_t)e * eu] = x_extract<T>(A, ((const cx<T> *)A.in)[ow + (int64_t)(e + A.x_shift) * ew], e, N, (T)A.fct);
+      break;
     case AUX_BLUE_PRE: {        // e = n in 0..n2
       cx<T> v = mk<T>((T)0, (T)0);
       if (e < N) {

@@ -246,6 +246,10 @@ enum AuxMode : int {
   // stride, negated elements): gather / scatter between the strided real line and the complex work line
   AUX_R2C_PACK_EVEN = 9,    // Z[m] = (x[2m], x[2m+1]), m < M
   AUX_C2R_UNPACK_EVEN = 10, // x[2m] = Re Z[m] * fct, x[2m+1] = Im Z[m] * fct
+  // DCT / DST lines whose embedding (2N, 2N-2, 2N+2 complex points) does not fit one CTA: the LOAD / STORE modes of the
+  // line kernel (LD_X_*, ST_X) as elementwise passes around a complex transform of any length
+  AUX_X_EMBED = 11,         // u[e] (e < M) of the embedding selected by x_load, from the real input line
+  AUX_X_EXTRACT = 12,       // real output e (e < N) from the transformed work line
 };
 constexpr int kMaxAuxDims = 8;
 struct AuxJob {
@@ -261,6 +265,11 @@ struct AuxJob {
   const void *tab;                 // real modes: W_N^k (k <= N/2); Bluestein: b[n]
   double fct;
   uint64_t total;
+  // DCT / DST passes: the same parameters as the LineJob fields of these names
+  int x_load;                      // LD_X_* mode of the embedding
+  const void *x_tw;
+  double x_f0, x_f, x_fl, x_s, x_s0, x_sn;
+  uint32_t x_shift, x_wadd, x_im;
 };
 
 // Genuine (non-separable) Hartley transform, last step (pocketfft_hdronly.h:3432-3444): the contiguous

@@ -935,6 +935,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     AuxJob &A = st.aj;
     A.mode = mode; A.dtype = d.dtype; A.layout = layout; A.flags = flags; A.N = N; A.M = M;
     A.in = nullptr; A.out = nullptr; A.tab = tab; A.fct = 1.0;
+    A.x_load = 0; A.x_tw = nullptr; A.x_f0 = A.x_f = A.x_fl = A.x_s = A.x_s0 = A.x_sn = 1.0; A.x_shift = 0; A.x_wadd = 0xffffffffu; A.x_im = 0;
     A.ndim = (int)dims.size() + 1;
     A.total = extent;
     for (size_t i = 0; i < dims.size(); ++i) {
@@ -1007,8 +1008,49 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       dims.push_back({bshape[i], sin[i] / (ptrdiff_t)esz_in, sout[i] / (ptrdiff_t)esz_out});
     }
     const int64_t es_in = sin[axis] / (ptrdiff_t)esz_in, es_out = sout[axis] / (ptrdiff_t)esz_out;
-    if (kind == KIND_DCT || kind == KIND_DST)
-      return emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, nullptr, 0, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
+    if (kind == KIND_DCT || kind == KIND_DST) {
+      const size_t n0 = plan->steps.size();
+      int rc1 = env_int("IMPULSE_FFT_FORCE_BIGR2R", 0) ? (int)ERR_UNSUPPORTED
+                    : emit(kind, layout, forward, N, es_in, es_out, dims, -1, 0, nullptr, 0, 0, esz_in, esz_out, src, dst, 0, 0, takes_fct);
+      if (rc1 != ERR_UNSUPPORTED) return rc1;
+      // ---- the embedding (2N, 2N-2 or 2N+2 complex points, or its Bluestein work array) does not fit one CTA: build it
+      // in a work array with one elementwise pass, transform it with c2c_line (any length), extract with a second pass.
+      // pocketfft's T_dct1 / T_dcst23 / T_dcst4 take any N (pocketfft_hdronly.h:2424-2648).
+      plan->steps.resize(n0);
+      err->clear();
+      LineSpec ls;                       // reuse the line planner's parameter selection for this (kind, type, ortho)
+      ls.kind = kind; ls.dtype = d.dtype; ls.N = 8; ls.r2r_type = d.r2r_type; ls.ortho = d.ortho;
+      LineJob pj; LaunchCfg pc;
+      int rc2 = build_line_job(ls, &pj, &pc, err);
+      if (rc2) return rc2;
+      const uint32_t M = d.r2r_type == 1 ? (kind == KIND_DCT ? 2 * (N - 1) : 2 * (N + 1)) : 2 * N;
+      if (kind == KIND_DCT && d.r2r_type == 1 && N < 2) { *err = "DCT-I needs at least two points"; return ERR_INVALID; }
+      const void *xtw = nullptr;
+      if (d.r2r_type != 1) { rc2 = r2r_twiddle(N, d.dtype, &xtw, err); if (rc2) return rc2; }
+      uint64_t nlines = 1;
+      std::vector<Dim> d_iw, d_ww, d_ow;   // (input, work), (work, work), (output, work)
+      for (auto &dm : dims) {
+        d_iw.push_back({dm.n, dm.sin, (int64_t)(nlines * M)});
+        d_ow.push_back({dm.n, dm.sout, (int64_t)(nlines * M)});
+        d_ww.push_back({dm.n, (int64_t)(nlines * M), (int64_t)(nlines * M)});
+        nlines *= dm.n;
+      }
+      plan->tmp4_bytes = std::max<size_t>(plan->tmp4_bytes, (size_t)nlines * M * csize_g);
+      auto fill = [&](AuxJob &A) {
+        A.x_load = pj.load_mode; A.x_tw = xtw;
+        A.x_f0 = pj.x_f0; A.x_f = pj.x_f; A.x_fl = pj.x_fl; A.x_s = pj.x_s; A.x_s0 = pj.x_s0; A.x_sn = pj.x_sn;
+        A.x_shift = pj.x_shift; A.x_wadd = pj.x_wadd; A.x_im = pj.x_im;
+      };
+      rc2 = emit_aux(AUX_X_EMBED, 0, 0, N, M, M, d_iw, es_in, 1, nullptr, src, BUF_TMP4, false);
+      if (rc2) return rc2;
+      fill(plan->steps.back().aj);
+      rc2 = c2c_line(true, M, 1, 1, d_ww, csize_g, csize_g, BUF_TMP4, BUF_TMP4, false, 0);
+      if (rc2) return rc2;
+      rc2 = emit_aux(AUX_X_EXTRACT, 0, 0, N, M, N, d_ow, es_out, 1, nullptr, BUF_TMP4, dst, takes_fct);
+      if (rc2) return rc2;
+      fill(plan->steps.back().aj);
+      return ST_OK;
+    }
     if (kind == KIND_C2C) return c2c_line(forward, N, es_in, es_out, dims, esz_in, esz_out, src, dst, takes_fct, umul_mod);
     if (umul_mod) { *err = "fused multiply is a c2c option"; return ERR_INVALID; }
     const bool even = N % 2 == 0;

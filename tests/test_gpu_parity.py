@@ -582,13 +582,13 @@ def test_dct_dst(ib, torch_mod, checker):
     every type, both families, host and device buffers, N-D."""
     rng = np.random.default_rng(61)
     for dt, rt in ((np.float64, 1e-12), (np.float32, 1e-5)):
-        for n in (2, 4, 9, 64, 100, 1000, 4096):
+        # 4096 (type I: 8190 / 8194-point embeddings), 8192 and 10000 run as embed -> complex transform -> extract: any N,
+        # as pocketfft's T_dct1 / T_dcst23 / T_dcst4 (pocketfft_hdronly.h:2424-2648)
+        for n in (2, 4, 9, 64, 100, 1000, 4096, 8192, 10000):
             x = rnd(rng, (5, n), dt)
             xd = torch_mod.from_numpy(x).cuda()
             for sine in (False, True):
                 for t in (1, 2, 3, 4):
-                    if t == 1 and n == 4096:
-                        continue  # 2(N+-1) = 8190 / 8194 need a Bluestein work array beyond one CTA: reported unsupported
                     for ortho in (False, True):
                         want = checker.r2r(not sine, t, x, [1], 0.5, ortho)
                         out = torch_mod.empty_like(xd)
@@ -604,10 +604,10 @@ def test_dct_dst(ib, torch_mod, checker):
     out = np.empty_like(a)
     ib.DCTDesc.init(axes=[0, 1], dctType=2, ortho=True).apply(ib.DataDesc.init(out), ib.DataDesc.init(a))
     assert oracle.rel_l2(out, checker.r2r(True, 2, a, [0, 1], 1.0, True)) <= 1e-12 * 5
-    with pytest.raises(ib.FFTError) as ei:   # loud, not wrong: DST-I of 4096 points embeds in 8194 = 2*17*241
-        big = np.zeros((2, 4096))
-        ib.DCTDesc.init(axes=[1], dctType=1, sine=True).apply(ib.DataDesc.init(big.copy()), ib.DataDesc.init(big))
-    assert ei.value.code == -3
+    big = rnd(rng, (40000, 3), np.float64)          # a long strided axis, in place
+    want = checker.r2r(True, 2, big, [0], 1.0, False)
+    ib.DCTDesc.init(axes=[0], dctType=2).apply(ib.DataDesc.init(big), ib.DataDesc.init(big))
+    assert oracle.rel_l2(big, want) <= 1e-12 * 16
     with pytest.raises(ValueError):
         ib.DCTDesc.init(axes=[0], dctType=5)
     with pytest.raises(ib.FFTError):
@@ -830,6 +830,22 @@ def test_long_lines(ib, torch_mod, checker):
         for fwd in (True, False):
             got = apply_nd(ib, "c2c", zd, torch_mod.empty_like(zd), [1], fwd, 0.5).cpu().numpy()
             assert oracle.max_row_rel_l2(got, checker.c2c(z, [1], fwd, 0.5)) <= tol(n), (n, fwd)
+    # long EVEN real lines that are strided or whose rows are an odd number of elements apart (round-1 advice: these
+    # returned ERR_UNSUPPORTED; general_r2c / general_c2r take any byte stride, pocketfft_hdronly.h:3125-3250)
+    y = rng.uniform(-0.5, 0.5, (40000, 4))
+    yd = torch_mod.from_numpy(y).cuda()
+    spec = apply_nd(ib, "r2c", yd, torch_mod.empty((20001, 4), dtype=torch_mod.complex128, device="cuda"), [0], True, 1.0)
+    assert oracle.rel_l2(spec.cpu().numpy(), checker.r2c(y, [0], True, 1.0)) <= tol(40000)
+    back = apply_nd(ib, "c2r", spec, torch_mod.empty_like(yd), [0], False, 1.0 / 40000)
+    assert oracle.rel_l2(back.cpu().numpy(), y) <= 2e-15 * 16
+    wide = torch_mod.from_numpy(rng.uniform(-0.5, 0.5, (3, 40001))).cuda()
+    yv = wide[:, :40000]                                                   # row stride 40001 elements
+    spec = apply_nd(ib, "r2c", yv, torch_mod.empty((3, 20001), dtype=torch_mod.complex128, device="cuda"), [1], True, 1.0)
+    assert oracle.max_row_rel_l2(spec.cpu().numpy(), checker.r2c(np.ascontiguousarray(yv.cpu().numpy()), [1], True, 1.0)) <= tol(40000)
+    a = rng.uniform(-0.5, 0.5, (2, 32768))                                 # r2r_fftpack, real2hermitian != forward, long line
+    got = np.empty_like(a)
+    ib.r2r_fftpack(ib.DataDesc.init(got), ib.DataDesc.init(a), [1], True, False, 1.0)
+    assert oracle.rel_l2(got, oracle.fftpack_numpy(a, [1], True, False, 1.0)) <= tol(32768)
     # 2-D real transform whose last axis is long
     img = rng.uniform(-0.5, 0.5, (6, 40000))
     got = apply_nd(ib, "r2c", torch_mod.from_numpy(img).cuda(), torch_mod.empty((6, 20001), dtype=torch_mod.complex128,
