@@ -169,8 +169,30 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     cudaError_t e = cudaMallocAsync(&tmp, nd.tmp_bytes, stream);
     if (e != cudaSuccess) { if (tmp4) cudaFreeAsync(tmp4, stream); return cuda_fail(e, "cudaMallocAsync(tmp)"); }
   }
-  if (nd.tmp2_bytes) {
-    cudaError_t e = cudaMallocAsync(&tmp2, nd.tmp2_bytes, stream);
+  // pairs of launches that run as one fused kernel keep their intermediate in a small L2-resident ring instead of the
+  // full-size four-step scratch
+  static const bool no_fuse = [] { const char *e = std::getenv("IMPULSE_FFT_NO_COLFUSE"); return e && std::atoi(e) != 0; }();
+  size_t fuse_bytes = 0;
+  bool all_fused = true;   // every pair the planner marked runs fused (then the full-size scratch shrinks to tmp2_bytes_fused)
+  auto can_fuse = [&](size_t i) {
+    return !no_fuse && i + 1 < nd.steps.size() && nd.steps[i].fuse_with_next && !nd.steps[i].job.seg_len &&
+           colfuse_pair_supported(nd.steps[i].job.fast_id, nd.steps[i + 1].job.fast_id);
+  };
+  for (size_t i = 0; i + 1 < nd.steps.size(); ++i) {
+    if (!nd.steps[i].fuse_with_next) continue;
+    if (can_fuse(i))
+      fuse_bytes = std::max(fuse_bytes, colfuse_scratch_bytes(nd.steps[i].job, nd.steps[i + 1].job, nd.steps[i].fuse_tiles, nullptr, nullptr));
+    else
+      all_fused = false;
+  }
+  const size_t tmp2_need = (fuse_bytes && all_fused) ? nd.tmp2_bytes_fused : nd.tmp2_bytes;
+  void *fuse_scratch = nullptr;
+  if (fuse_bytes) {
+    cudaError_t e = cudaMallocAsync(&fuse_scratch, fuse_bytes, stream);
+    if (e != cudaSuccess) { if (tmp) cudaFreeAsync(tmp, stream); if (tmp4) cudaFreeAsync(tmp4, stream); return cuda_fail(e, "cudaMallocAsync(ring)"); }
+  }
+  if (tmp2_need) {
+    cudaError_t e = cudaMallocAsync(&tmp2, tmp2_need, stream);
     if (e != cudaSuccess) { if (tmp) cudaFreeAsync(tmp, stream); if (tmp4) cudaFreeAsync(tmp4, stream); return cuda_fail(e, "cudaMallocAsync(tmp2)"); }
   }
   if (nd.tmp3_bytes) {
@@ -183,7 +205,8 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     }
   }
   int rc = 0;
-  for (const Step &st : nd.steps) {
+  for (size_t si = 0; si < nd.steps.size(); ++si) {
+    const Step &st = nd.steps[si];
     LineJob J = st.job;
     const unsigned char *src = st.src == BUF_IN ? (const unsigned char *)in : st.src == BUF_OUT ? (const unsigned char *)out
                                : st.src == BUF_TMP ? (const unsigned char *)tmp
@@ -214,6 +237,26 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     J.in = src + st.src_off_bytes;
     J.out = dst + st.dst_off_bytes;
     J.fct = st.takes_fct ? fct : 1.0;
+    if (fuse_scratch && can_fuse(si)) {
+      // this launch and the next one as ONE persistent kernel; the intermediate stays in the ring
+      const Step &sb = nd.steps[si + 1];
+      LineJob JB = sb.job;
+      unsigned char *dstb = sb.dst == BUF_OUT ? (unsigned char *)out : sb.dst == BUF_TMP ? (unsigned char *)tmp
+                            : sb.dst == BUF_TMP3 ? (unsigned char *)tmp3 : (unsigned char *)tmp4;
+      JB.out = dstb + sb.dst_off_bytes;
+      JB.fct = sb.takes_fct ? fct : 1.0;
+      {
+        size_t ctrl_off = 0, ctrl_bytes = 0;
+        colfuse_scratch_bytes(J, JB, st.fuse_tiles, &ctrl_off, &ctrl_bytes);
+        cudaError_t me = cudaMemsetAsync((unsigned char *)fuse_scratch + ctrl_off, 0, ctrl_bytes, stream);
+        if (me != cudaSuccess) { rc = cuda_fail(me, "cudaMemsetAsync(ring control)"); break; }
+        int e = launch_colfuse_pair(J, JB, st.fuse_tiles, st.fuse_g0n, fuse_scratch, p->ctx->sm_count, stream);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e) { rc = e == -1 ? fail(IMPULSE_FFT_ERR_UNSUPPORTED, "internal: no fused kernel for a pair marked fusable") : cuda_fail((cudaError_t)e, "kernel launch"); break; }
+        ++si;   // the next step ran inside this launch
+        continue;
+      }
+    }
     if (st.takes_umul) {
       if (!umul) { rc = fail(IMPULSE_FFT_ERR_INVALID, "this plan needs a multiplier array"); break; }
       J.umul = umul;
@@ -233,6 +276,7 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
   if (tmp2) cudaFreeAsync(tmp2, stream);
   if (tmp3) cudaFreeAsync(tmp3, stream);
   if (tmp4) cudaFreeAsync(tmp4, stream);
+  if (fuse_scratch) cudaFreeAsync(fuse_scratch, stream);
   return rc;
 }
 

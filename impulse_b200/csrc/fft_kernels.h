@@ -24,6 +24,12 @@ int launch_transpose(int dtype, const void *in, void *out, size_t rows, size_t c
 // out[b][r][c] = in[b][r][c] for complex matrices with independent leading dimensions / batch strides
 int launch_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
                   size_t batch, size_t bs_in, size_t bs_out, int sm_count, void *stream);
+// both launches of a split column transform as one persistent kernel (colfuse_kernels.cu).  The two jobs carry
+// their final pointers / fct; `scratch` = colfuse_scratch_bytes() bytes of device memory (ring + control words; the
+// control words must be zero).  Returns cudaError_t, or -1 when there is no fused kernel for the pair.
+size_t colfuse_scratch_bytes(const LineJob &a, const LineJob &b, uint32_t tiles, size_t *ctrl_off, size_t *ctrl_bytes);
+int launch_colfuse_pair(const LineJob &a, const LineJob &b, uint32_t tiles, uint32_t g0n, void *scratch, int sm_count, void *stream);
+bool colfuse_pair_supported(uint32_t fast_id_a, uint32_t fast_id_b);
 // elementwise conversion / chirp pass around a long transform (AuxJob)
 int launch_aux(const AuxJob &job, int sm_count, void *stream);
 // genuine Hartley fold of a contiguous half spectrum into the real output (CombineJob)

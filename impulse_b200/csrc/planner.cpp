@@ -1294,7 +1294,42 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     *err = "bad transform kind";
     return ERR_INVALID;
   }
+  if (!rc) mark_fusable_pairs(plan);
   return rc;
+}
+
+// Two consecutive steps  A: source -> four-step scratch (column kernel, store twiddle along batch dim 1)
+//                        B: scratch -> destination (column kernel)
+// over the same groups of adjacent lines are the two launches of ONE split column transform: the device backend runs
+// them as a single persistent kernel whose intermediate never leaves L2 (colfuse_device.cuh).
+void PlanCache::mark_fusable_pairs(NdPlan *plan) {
+  plan->tmp2_bytes_fused = plan->tmp2_bytes;
+  bool other_tmp2_user = false;
+  std::vector<bool> in_pair(plan->steps.size(), false);
+  for (size_t i = 0; i + 1 < plan->steps.size(); ++i) {
+    Step &a = plan->steps[i];
+    const Step &b = plan->steps[i + 1];
+    if (in_pair[i] || a.aux || a.combine || b.aux || b.combine) continue;
+    if (a.dst != BUF_TMP2 || b.src != BUF_TMP2 || a.src == BUF_TMP2 || b.dst == BUF_TMP2) continue;
+    const LineJob &A = a.job, &B = b.job;
+    const bool colA = A.fast_id >= COL2_64_F64 && A.fast_id <= COL2_128_F32 && A.fast_id != COL2_256_F64 && A.fast_id != COL2_256_F32;
+    const bool colB = B.fast_id >= COL2_64_F64 && B.fast_id <= COL2_128_F32 && B.fast_id != COL2_256_F64 && B.fast_id != COL2_256_F32;
+    if (!colA || !colB || A.dtype != B.dtype) continue;
+    if (A.n_fft > B.n_fft) continue;                                   // instantiated pairs: 64x64, 64x128, 128x128
+    if (!A.tw4_n || A.tw4_dim != 1 || B.tw4_n || A.col_in_rows || B.col_in_rows || A.seg_len || B.seg_len) continue;
+    if (A.umul_mod || B.umul_mod || A.mul_tab || B.mul_tab || a.takes_umul || b.takes_umul) continue;
+    if (A.bdim[0] != B.bdim[0] || A.bdim[2] != B.bdim[2] || A.bdim[1] != B.n_fft || B.bdim[1] != A.n_fft) continue;
+    if (A.bdim[0] < 16 || (A.flags & F_CONJ_SEQ) != (B.flags & F_CONJ_SEQ)) continue;
+    const uint64_t g0n = (A.bdim[0] + 15) / 16, tiles = g0n * A.bdim[2];
+    if (tiles > 0x00ffffffull) continue;
+    a.fuse_with_next = true;
+    a.fuse_tiles = (uint32_t)tiles;
+    a.fuse_g0n = (uint32_t)g0n;
+    in_pair[i] = in_pair[i + 1] = true;
+  }
+  for (size_t i = 0; i < plan->steps.size(); ++i)
+    if (!in_pair[i] && (plan->steps[i].src == BUF_TMP2 || plan->steps[i].dst == BUF_TMP2)) other_tmp2_user = true;
+  if (!other_tmp2_user) plan->tmp2_bytes_fused = 0;
 }
 
 }  // namespace impulse

@@ -101,6 +101,11 @@ struct Step {
   AuxJob aj{};
   bool combine = false;     // not a line job: the genuine-Hartley fold `cj` (src/dst as usual)
   CombineJob cj{};
+  // this step and the NEXT one are the two launches of a four-step split that the device backend may run as ONE
+  // persistent kernel with the intermediate in an L2-resident ring (colfuse2_kernel); the emulation and
+  // IMPULSE_FFT_NO_COLFUSE run them as the two launches they are
+  bool fuse_with_next = false;
+  uint32_t fuse_tiles = 0, fuse_g0n = 0;   // tiles = groups of adjacent lines x outer batch index
   bool takes_umul = false;  // this step multiplies its output by the caller's array (impulse_fft_c2c_mul)
   bool takes_fct = false;  // the scaling factor is applied once, in these steps (hdronly.h:3048)
 };
@@ -122,6 +127,7 @@ struct NdPlan {
   std::vector<Step> steps;
   size_t tmp_bytes = 0;   // c2r N-D intermediate (hdronly.h:3384)
   size_t tmp2_bytes = 0;  // four-step scratch
+  size_t tmp2_bytes_fused = 0;  // ... what is left of it when every fusable pair runs fused (device backend)
   size_t tmp3_bytes = 0;  // multi-launch Bluestein work array [lines][n2]
   size_t tmp4_bytes = 0;  // long real transforms: complex work array [lines][L]
   // long even real transforms address the real side as packed complex pairs: the base pointer must be
@@ -184,6 +190,7 @@ class PlanCache {
   int four_step_tables(uint32_t N, int dtype, const void **hi, const void **lo, uint32_t *shift, std::string *err);
   int build_line_job(const LineSpec &s, LineJob *job, LaunchCfg *cfg, std::string *err);
   int build_nd(const NdDesc &d, NdPlan *plan, std::string *err);
+  static void mark_fusable_pairs(NdPlan *plan);
 
  private:
   TableRef own(void *dev);          // device table -> reference-counted handle that releases it
