@@ -15,7 +15,7 @@ namespace {
 template <typename T, int RA1, int RA2, int RB1, int RB2, int LPC>
 int launch_colfuse(const FuseJob &F, int sm_count, cudaStream_t s) {
   constexpr int NA = RA1 * RA2, NB = RB1 * RB2, NMAX = NA > NB ? NA : NB;
-  const size_t smem = sizeof(cx<T>) * (size_t)NMAX * LPC + 16;
+  const size_t smem = sizeof(cx<T>) * (size_t)NMAX * LPC * (sizeof(cx<T>) == 16 ? 2 : 1) + 3 * sizeof(FuseItem);
   const bool bwd = (F.A.flags & F_CONJ_SEQ) != 0;
   auto kf = colfuse2_kernel<T, RA1, RA2, RB1, RB2, LPC, false>;
   auto kb = colfuse2_kernel<T, RA1, RA2, RB1, RB2, LPC, true>;
@@ -49,12 +49,22 @@ int launch_colfuse(const FuseJob &F, int sm_count, cudaStream_t s) {
 }
 }  // namespace
 
-constexpr uint32_t kRingSlots = 8;   // tiles of intermediate kept live: 8 x (N x 16 lines) — 16 MB for 8192-point complex128 columns
+// Queue lag and ring size (tiles): the B items of a tile are queued `lag` rounds after its A items, `lag` rounds holding
+// more items than the grid keeps in flight (three per CTA: in progress, staged, claimed); the ring holds
+// 2*lag tiles so that a slot is rewritten only after its previous tile was consumed a window ago.  IMPULSE_FFT_FUSE_LAG
+// overrides (A/B runs).
+static uint32_t fuse_lag(uint32_t tiles, uint32_t per_round, int sm_count) {
+  static const int env = [] { const char *e = getenv("IMPULSE_FFT_FUSE_LAG"); return e ? atoi(e) : 0; }();
+  uint32_t lag = env > 0 ? (uint32_t)env : (uint32_t)((3ull * (uint64_t)sm_count * 3 + per_round - 1) / per_round) + 1;
+  if (lag > tiles) lag = tiles;
+  return lag ? lag : 1;
+}
+static uint32_t fuse_slots(uint32_t tiles, uint32_t lag) { return tiles < 2 * lag ? tiles : 2 * lag; }
 
 // scratch the fused launch needs: the ring + the control words (which must be zero at launch)
 size_t colfuse_scratch_bytes(const LineJob &a, const LineJob &b, uint32_t tiles, size_t *ctrl_off, size_t *ctrl_bytes) {
   const size_t csz = a.dtype == 1 ? 16 : 8;
-  const uint32_t slots = tiles < kRingSlots ? (tiles ? tiles : 1) : kRingSlots;
+  const uint32_t slots = fuse_slots(tiles ? tiles : 1, fuse_lag(tiles ? tiles : 1, a.n_fft + b.n_fft, 148));
   size_t ring = (size_t)slots * a.n_fft * b.n_fft * 16 * csz;
   ring = (ring + 255) & ~(size_t)255;
   const size_t cb = sizeof(unsigned int) * (2 + 2 * (size_t)tiles);
@@ -71,7 +81,8 @@ int launch_colfuse_pair(const LineJob &a, const LineJob &b, uint32_t tiles, uint
   colfuse_scratch_bytes(a, b, tiles, &ctrl_off, nullptr);
   F.ring = scratch;
   F.ctrl = reinterpret_cast<unsigned int *>(static_cast<unsigned char *>(scratch) + ctrl_off);
-  F.ring_slots = tiles < kRingSlots ? (tiles ? tiles : 1) : kRingSlots;
+  F.lag = fuse_lag(tiles ? tiles : 1, a.n_fft + b.n_fft, 148);   // (sized for a full B200: a smaller grid only waits less)
+  F.ring_slots = fuse_slots(tiles ? tiles : 1, F.lag);
   F.tiles = tiles; F.g0n = g0n;
   F.itemsA = b.n_fft;   // one A item per n2
   F.itemsB = a.n_fft;   // one B item per k1

@@ -195,6 +195,25 @@ int emu_nd_fast_ids(int kind, int dtype, int layout, size_t ndim, const size_t *
   return n;
 }
 
+// which steps the planner marked as the first of a fusable pair (device backend: colfuse2_kernel)
+int emu_nd_fuse_flags(int kind, int dtype, int layout, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
+                      const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, uint32_t *flags, int max_n) {
+  ensure_cache();
+  NdDesc d;
+  d.kind = kind; d.dtype = dtype; d.layout = layout; d.forward = forward != 0;
+  d.shape.assign(shape, shape + ndim);
+  d.stride_in.assign(stride_in, stride_in + ndim);
+  d.stride_out.assign(stride_out, stride_out + ndim);
+  d.axes.assign(axes, axes + naxes);
+  NdPlan plan;
+  int rc = g_cache->build_nd(d, &plan, &g_err);
+  if (rc) return rc;
+  int n = 0;
+  for (const Step &st : plan.steps)
+    if (n < max_n) flags[n++] = st.fuse_with_next ? 1u : 0u;
+  return n;
+}
+
 // plan introspection for tests
 int emu_plan_info(uint32_t L, int dtype, uint32_t *n_fft, int *blue, uint32_t *radices, int max_r) {
   ensure_cache();

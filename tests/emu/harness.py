@@ -155,6 +155,20 @@ def nd_fast_ids(kind, a_in, a_out, shape, axes, forward=True, layout="hermitian"
     return list(ids[:rc])
 
 
+def nd_fuse_flags(kind, a_in, a_out, shape, axes, forward=True, layout="hermitian"):
+    """1 for every step that is the first launch of a fusable pair (two launches of a split column transform)."""
+    L = lib()
+    L.emu_nd_fuse_flags.restype = C.c_int
+    dt = 1 if a_in.dtype in (np.float64, np.complex128) else 0
+    n = len(shape)
+    fl = (C.c_uint32 * 16)()
+    rc = L.emu_nd_fuse_flags(KIND[kind], dt, LAYOUT[layout], C.c_size_t(n), (C.c_size_t * n)(*shape), (C.c_ssize_t * n)(*a_in.strides),
+                             (C.c_ssize_t * n)(*a_out.strides), C.c_size_t(len(axes)), (C.c_size_t * len(axes))(*axes), int(forward), fl, 16)
+    if rc < 0:
+        raise EmuError(rc, L.emu_last_error().decode())
+    return list(fl[:rc])
+
+
 def set_fast_cols(pipe_groups=None):
     """None: every job on the generic engine's phase emulation.  An integer g >= 0: column-kernel jobs (strided axes,
     the four-step split, the fused convolution pass) on the thread-level emulation, colpipe2 with g groups per CTA

@@ -78,3 +78,17 @@ def test_mixed_radix_shapes_measured_in_round_2_are_on_by_default(monkeypatch):
     monkeypatch.setenv("IMPULSE_FFT_MORE_SHAPES", "0")
     monkeypatch.setenv("IMPULSE_FFT_BLUE_F32", "0")
     assert ids_1d("c2c", 1536, 16) == [0] and ids_1d("r2c", 4099, 16, np.float32) == [0]
+
+
+def test_split_column_transform_is_marked_for_the_fused_kernel():
+    """fft2 8192 x 8192 (BASELINE config 4): the two launches of the column split are one fusable pair (colfuse2_kernel on
+    the device, intermediate in an L2-resident ring); the emulation still sees — and runs — two ordinary steps."""
+    a = np.empty((8192, 8192), np.complex128)
+    steps = emu.nd_steps("c2c", a, a, a.shape, [0, 1], True)
+    assert steps == 3
+    info = emu.nd_fuse_flags("c2c", a, a, a.shape, [0, 1], True)
+    assert info == [1, 0, 0], info
+    b = np.empty((4, 4096, 64), np.complex64)      # strided axis of a batch: tiles = column groups x batch
+    assert emu.nd_fuse_flags("c2c", b, b, b.shape, [1], True) == [1, 0]
+    c = np.empty((3, 2048, 32), np.complex128)     # 2048 = 32 x 64: no fused instance for that pair
+    assert sum(emu.nd_fuse_flags("c2c", c, c, c.shape, [1], True)) == 0

@@ -23,6 +23,11 @@ KEYS = [
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "lts__t_sector_hit_rate.pct", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sector_op_read_hit_rate.pct", "lts__t_sector_op_write_hit_rate.pct",
+    "sm__inst_executed.sum", "smsp__inst_executed.sum",
 ]
 
 
