@@ -443,8 +443,9 @@ int launch_colfast2(const LineJob &J, cudaStream_t s) {
   const bool rows_in = J.col_in_rows != 0;
   // (64- and 128-point sub-transforms only: at 256 points the second register set costs more occupancy than
   // the overlap returns — measured 1.80 -> 1.64 TB/s on 65536-point rows)
-  if (sizeof(T) == 8 && R1 * R2 <= 128 && !rows_in && !J.seg_len && !J.umul_mod && col_pipe_groups() && J.bdim[0] >= 2 * LPC) {
-    const uint32_t G = col_pipe_groups();
+  static const int pipe_f32 = [] { const char *e = getenv("IMPULSE_FFT_COL_PIPE_F32"); return e ? atoi(e) : 0; }();   // groups per CTA for complex64 (0 = off)
+  if ((sizeof(T) == 8 || pipe_f32 > 1) && R1 * R2 <= 128 && !rows_in && !J.seg_len && !J.umul_mod && col_pipe_groups() && J.bdim[0] >= 2 * LPC) {
+    const uint32_t G = sizeof(T) == 8 ? col_pipe_groups() : (uint32_t)pipe_f32;
     const size_t smem_p = sizeof(cx<T>) * (size_t)R1 * R2 * LPC;
     const bool bwd_p = (J.flags & F_CONJ_SEQ) != 0;
     auto kpf = colpipe2_kernel<T, (R1 <= 16 ? R1 : 16), R2, LPC, false>;
