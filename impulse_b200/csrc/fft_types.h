@@ -158,9 +158,12 @@ enum FastId : uint32_t {
   FASTBLUE_2048_F32 = 70,  // fused Bluestein in float32 (selected with IMPULSE_FFT_BLUE_F32=1 until measured)
   FASTBLUE_4096_F32 = 71,
   FASTBLUE_8192_F32 = 72,
-  FAST3_1536_F64 = 73,     // more mixed-radix shapes (IMPULSE_FFT_MORE_SHAPES=1 until measured): 8*24*8, 10*20*10, 10*20*20
+  FAST3_1536_F64 = 73,     // more mixed-radix shapes (IMPULSE_FFT_MORE_SHAPES=0 switches them off): 8*24*8, 10*20*10, 10*20*20
   FAST3_2000_F64 = 74,
   FAST3_4000_F64 = 75,
+  FAST3_2187_F64 = 76,     // 3^7 = 27*9*9, 3000 = 10*30*10, 3^8 = 27*27*9 (complex rows; round 2)
+  FAST3_3000_F64 = 77,
+  FAST3_6561_F64 = 78,
 };
 
 struct Phase {

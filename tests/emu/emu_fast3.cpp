@@ -154,6 +154,9 @@ int emu_fast3(int shape, int dtype, int kind, int bwd, int flags, const void *in
   SHAPE(8, 24, 8, 24)
   SHAPE(10, 20, 10, 20)
   SHAPE(10, 20, 20, 20)
+  SHAPE(27, 9, 9, 27)
+  SHAPE(10, 30, 10, 30)
+  SHAPE(27, 27, 9, 27)
 #undef SHAPE
   return -1;
 }

@@ -229,3 +229,17 @@ def test_rows_staged_by_bulk_copy_f32():
     X = np.fft.rfft(x.astype(np.float64), axis=1).astype(np.complex64)
     got = f3.run((8, 16, 16, 16), "c2r", X, False, 0.5 / n, pair=True, ctas=2, staged=True, double_buffer=True)
     assert rel(got.astype(np.float64), x.astype(np.float64)) < 1e-6 * np.log2(n)
+
+
+@pytest.mark.parametrize("shape", [(27, 9, 9, 27), (10, 30, 10, 30), (27, 27, 9, 27)])
+def test_round2_complex_shapes(shape):
+    """3^7 = 27*9*9, 3000 = 10*30*10, 3^8 = 27*27*9: complex rows (radix-27 = 3 x 9 and radix-30 = 5 x 6 composites)."""
+    r1, r2, r3, e = shape
+    n = r1 * r2 * r3
+    rng = np.random.default_rng(n + 1)
+    z = rng.random((4, n)) - 0.5 + 1j * (rng.random((4, n)) - 0.5)
+    got = f3.run(shape, "c2c", z, True, 0.5, ctas=2)
+    want = np.fft.fft(z, axis=1) * 0.5
+    for r in range(4):
+        assert rel(got[r], want[r]) < 2e-15 * np.log2(n) * 4, r
+    assert rel(f3.run(shape, "c2c", z, False, 1.0 / n, ctas=2), np.fft.ifft(z, axis=1)) < 2e-15 * np.log2(n) * 4

@@ -65,7 +65,7 @@ def test_switches_restore_the_previous_shapes(monkeypatch):
     assert ids_1d("c2c", 1024, 64) == [0] and ids_1d("r2c", 1000, 64) == [0]
 
 
-@pytest.mark.parametrize("n", [3000, 5000, 10000])
+@pytest.mark.parametrize("n", [5000, 10000, 12288])
 def test_lengths_without_a_register_kernel_use_the_generic_engine(n):
     assert ids_1d("c2c", n, 16) == [0]
 
@@ -74,6 +74,8 @@ def test_mixed_radix_shapes_measured_in_round_2_are_on_by_default(monkeypatch):
     assert ids_1d("c2c", 1536, 16) == [ID["FAST3_1536_F64"]]
     assert ids_1d("c2c", 2000, 16) == [ID["FAST3_2000_F64"]]
     assert ids_1d("c2c", 4000, 16) == [ID["FAST3_4000_F64"]]
+    assert ids_1d("c2c", 2187, 16) == [ID["FAST3_2187_F64"]] and ids_1d("c2c", 3000, 16) == [ID["FAST3_3000_F64"]]
+    assert ids_1d("c2c", 6561, 16) == [ID["FAST3_6561_F64"]]
     assert ids_1d("r2c", 4099, 16, np.float32) == [ID["FASTBLUE_8192_F32"]]
     monkeypatch.setenv("IMPULSE_FFT_MORE_SHAPES", "0")
     monkeypatch.setenv("IMPULSE_FFT_BLUE_F32", "0")
