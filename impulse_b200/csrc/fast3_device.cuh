@@ -81,6 +81,7 @@ template <typename T> struct RegFFT<T, 10> { static __device__ __forceinline__ v
 template <typename T> struct RegFFT<T, 18> { static __device__ __forceinline__ void run(cx<T> (&x)[18]) { Composite<T, 2, 9>::run(x); } };
 template <typename T> struct RegFFT<T, 20> { static __device__ __forceinline__ void run(cx<T> (&x)[20]) { Composite<T, 4, 5>::run(x); } };
 template <typename T> struct RegFFT<T, 24> { static __device__ __forceinline__ void run(cx<T> (&x)[24]) { Composite<T, 3, 8>::run(x); } };
+template <typename T> struct RegFFT<T, 25> { static __device__ __forceinline__ void run(cx<T> (&x)[25]) { Composite<T, 5, 5>::run(x); } };
 template <typename T> struct RegFFT<T, 27> { static __device__ __forceinline__ void run(cx<T> (&x)[27]) { Composite<T, 3, 9>::run(x); } };
 template <typename T> struct RegFFT<T, 30> { static __device__ __forceinline__ void run(cx<T> (&x)[30]) { Composite<T, 5, 6>::run(x); } };
 template <typename T> struct RegFFT<T, 64> { static __device__ __forceinline__ void run(cx<T> (&x)[64]) { Composite<T, 8, 8>::run(x); } };

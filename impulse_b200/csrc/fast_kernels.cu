@@ -36,8 +36,10 @@ template <typename T, int R1, int R2, int WARPS, int MINB, bool BWD>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fast2_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nrows, int64_t rs_in, int64_t rs_out,
              const cx<T> *__restrict__ twN, T fct) {
+  // R2 threads per row, GPW = floor(32 / R2) rows per warp: R2 need not divide 32 (100 = 10*10: three rows on 30 lanes,
+  // 243 = 27*9: three rows on 27 lanes, 625 = 25*25: one row on 25 lanes); the spare lanes idle
   constexpr int N = R1 * R2, TPR = R2, GPW = 32 / TPR, NB2 = R1 / R2, PITCH = R2 + 1;
-  static_assert(R2 <= 32 && 32 % R2 == 0 && R1 % R2 == 0, "two-pass shape");
+  static_assert(R2 <= 32 && R1 % R2 == 0, "two-pass shape");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *tw = reinterpret_cast<cx<T> *>(smem_raw);
   cx<T> *xbuf = tw + N;
@@ -47,12 +49,13 @@ fast2_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nro
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane / TPR, i = lane % TPR;
+  const bool lane_ok = (32 % TPR == 0) || lane < GPW * TPR;
+  const int g = lane_ok ? lane / TPR : 0, i = lane_ok ? lane % TPR : 0;
   cx<T> *S = xbuf + (size_t)(warp * GPW + g) * (R1 * PITCH);
   constexpr uint64_t RPC = (uint64_t)WARPS * GPW;  // rows per CTA per sweep
   for (uint64_t wrow = (uint64_t)blockIdx.x * RPC + (uint64_t)warp * GPW; wrow < nrows; wrow += (uint64_t)gridDim.x * RPC) {
     const uint64_t row = wrow + g;
-    const bool active = row < nrows;
+    const bool active = lane_ok && row < nrows;
     cx<T> x[R1];
     {
       const cx<T> *src = in + (int64_t)row * rs_in + i;
@@ -65,8 +68,10 @@ fast2_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nro
     RegFFT<T, R1>::run(x);
 #pragma unroll
     for (int k1 = 1; k1 < R1; ++k1) x[k1] = cmul(x[k1], tw[k1 * R2 + i]);
+    if (lane_ok) {
 #pragma unroll
-    for (int k1 = 0; k1 < R1; ++k1) S[k1 * PITCH + i] = x[k1];
+      for (int k1 = 0; k1 < R1; ++k1) S[k1 * PITCH + i] = x[k1];
+    }
     __syncwarp();
     cx<T> *dst = out + (int64_t)row * rs_out;
 #pragma unroll
@@ -602,6 +607,13 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
       if (fast_variant() == 0) { g_last_kernel = "fast2p_kernel<double,16,8,10>"; return launch_fast2p<double, 16, 8, 10>(J, sm_count, s); }
       g_last_kernel = "fast2_kernel<double,16,8,8,4>";
       return launch_fast2<double, 16, 8, 8, 4>(J, sm_count, s);
+    // non-power-of-two short rows: R2 threads per row, floor(32 / R2) rows per warp
+    case FAST2_100_F64: g_last_kernel = "fast2_kernel<double,10,10,8,4>"; return launch_fast2<double, 10, 10, 8, 4>(J, sm_count, s);
+    case FAST2_243_F64: g_last_kernel = "fast2_kernel<double,27,9,4,2>"; return launch_fast2<double, 27, 9, 4, 2>(J, sm_count, s);
+    case FAST2_625_F64: g_last_kernel = "fast2_kernel<double,25,25,4,2>"; return launch_fast2<double, 25, 25, 4, 2>(J, sm_count, s);
+    case FAST2_100_F32: g_last_kernel = "fast2_kernel<float,10,10,8,6>"; return launch_fast2<float, 10, 10, 8, 6>(J, sm_count, s);
+    case FAST2_243_F32: g_last_kernel = "fast2_kernel<float,27,9,4,4>"; return launch_fast2<float, 27, 9, 4, 4>(J, sm_count, s);
+    case FAST2_625_F32: g_last_kernel = "fast2_kernel<float,25,25,4,4>"; return launch_fast2<float, 25, 25, 4, 4>(J, sm_count, s);
     case FAST2_16_F32: g_last_kernel = "fast2_kernel<float,4,4,8,6>"; return launch_fast2<float, 4, 4, 8, 6>(J, sm_count, s);
     case FAST2_32_F32: g_last_kernel = "fast2_kernel<float,8,4,8,6>"; return launch_fast2<float, 8, 4, 8, 6>(J, sm_count, s);
     case FAST2_64_F32: g_last_kernel = "fast2_kernel<float,8,8,8,6>"; return launch_fast2<float, 8, 8, 8, 6>(J, sm_count, s);

@@ -164,6 +164,12 @@ enum FastId : uint32_t {
   FAST3_2187_F64 = 76,     // 3^7 = 27*9*9, 3000 = 10*30*10, 3^8 = 27*27*9 (complex rows; round 2)
   FAST3_3000_F64 = 77,
   FAST3_6561_F64 = 78,
+  FAST2_100_F64 = 79,      // short non-power-of-two rows on the two-pass warp kernel: 10*10, 27*9, 25*25
+  FAST2_243_F64 = 80,
+  FAST2_625_F64 = 81,
+  FAST2_100_F32 = 82,
+  FAST2_243_F32 = 83,
+  FAST2_625_F32 = 84,
 };
 
 struct Phase {

@@ -572,6 +572,9 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       case 256: J->fast_id = f64 ? FAST2_256_F64 : FAST2_256_F32; break;
       case 512: J->fast_id = f64 ? FAST2_512_F64 : FAST2_512_F32; break;
       case 1024: J->fast_id = f64 ? FAST2_1024_F64 : FAST2_1024_F32; break;
+      case 100: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_100_F64 : FAST2_100_F32; break;
+      case 243: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_243_F64 : FAST2_243_F32; break;
+      case 625: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_625_F64 : FAST2_625_F32; break;
       default: break;
     }
   }

@@ -430,7 +430,7 @@ def test_register_kernels_all_kinds(ib, torch_mod, checker):
     used = set()
     for dt, cdt in ((np.float64, np.complex128), (np.float32, np.complex64)):
         more = (1536, 2000, 4000, 2187, 3000, 6561) if os.environ.get("IMPULSE_FFT_MORE_SHAPES", "1") == "1" else ()
-        for n in (16, 32, 64, 128, 256, 500, 512, 1000, 1024, 1944, 2048, 4096, 8192) + more:
+        for n in (16, 32, 64, 100, 128, 243, 256, 500, 512, 625, 1000, 1024, 1944, 2048, 4096, 8192) + more:
             for rows in (1, 37, 301) + ((5000,) if n <= 128 else ()):
                 x = rnd(rng, (rows, n), cdt)
                 xd = torch_mod.from_numpy(x).cuda()

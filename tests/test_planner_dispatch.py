@@ -76,6 +76,8 @@ def test_mixed_radix_shapes_measured_in_round_2_are_on_by_default(monkeypatch):
     assert ids_1d("c2c", 4000, 16) == [ID["FAST3_4000_F64"]]
     assert ids_1d("c2c", 2187, 16) == [ID["FAST3_2187_F64"]] and ids_1d("c2c", 3000, 16) == [ID["FAST3_3000_F64"]]
     assert ids_1d("c2c", 6561, 16) == [ID["FAST3_6561_F64"]]
+    assert ids_1d("c2c", 100, 64) == [ID["FAST2_100_F64"]] and ids_1d("c2c", 243, 64, np.float32) == [ID["FAST2_243_F32"]]
+    assert ids_1d("c2c", 625, 64) == [ID["FAST2_625_F64"]]
     assert ids_1d("r2c", 4099, 16, np.float32) == [ID["FASTBLUE_8192_F32"]]
     monkeypatch.setenv("IMPULSE_FFT_MORE_SHAPES", "0")
     monkeypatch.setenv("IMPULSE_FFT_BLUE_F32", "0")
