@@ -267,7 +267,7 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     if ((J.flags & F_VEC_IN) && ((uintptr_t)J.in % (2 * r))) J.flags &= ~F_VEC_IN;
     if ((J.flags & F_VEC_OUT) && ((uintptr_t)J.out % (2 * r))) J.flags &= ~F_VEC_OUT;
     // the register kernels address real rows as complex pairs: fall back to the generic engine otherwise
-    if (((J.fast_id >= FAST3_2048_F64 && J.fast_id <= FAST3_1000_F64) || (J.fast_id >= FAST3R_256_F64 && J.fast_id <= FAST3P_512_F32) || (J.fast_id >= FAST3_1536_F64 && J.fast_id <= FAST3_6561_F64)) && (((uintptr_t)J.in % (2 * r)) || ((uintptr_t)J.out % (2 * r)))) J.fast_id = FAST_NONE;
+    if (((J.fast_id >= FAST3_2048_F64 && J.fast_id <= FAST3_1000_F64) || (J.fast_id >= FAST3R_256_F64 && J.fast_id <= FAST3P_512_F32) || (J.fast_id >= FAST3_1536_F64 && J.fast_id <= FAST3_6561_F64) || (J.fast_id >= FAST3_1536_F32 && J.fast_id <= FAST3_6561_F32)) && (((uintptr_t)J.in % (2 * r)) || ((uintptr_t)J.out % (2 * r)))) J.fast_id = FAST_NONE;
     int e = launch_line_job(J, st.cfg.threads, st.cfg.smem_bytes, st.cfg.n_tiles, stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e) { rc = cuda_fail((cudaError_t)e, "kernel launch"); break; }
@@ -331,7 +331,23 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
         }();
         uint64_t per = std::max<uint64_t>(1, stage_bytes / std::max<int64_t>(1, sin_b + sout_b));
         per = std::min<uint64_t>(per, (J0.bdim[od] + 3) / 4);
-        const uint64_t nchunks = (J0.bdim[od] + per - 1) / per;
+        // chunk schedule: full-size chunks in the middle, a geometric ramp at both ends — the pipeline's fill (first
+        // H2D with nothing to overlap) and drain (last D2H) shrink from a whole chunk to an eighth of one
+        // (IMPULSE_FFT_STAGE_RAMP=0: equal chunks)
+        static const bool ramp = [] { const char *e = std::getenv("IMPULSE_FFT_STAGE_RAMP"); return !e || std::atoi(e) != 0; }();
+        std::vector<uint64_t> sizes;
+        {
+          const uint64_t total = J0.bdim[od];
+          std::vector<uint64_t> head;
+          if (ramp && per >= 8 && total >= 4 * per)
+            for (uint64_t c = std::max<uint64_t>(1, per / 8); c < per; c *= 2) head.push_back(c);
+          uint64_t used = 0;
+          for (uint64_t c : head) used += 2 * c;           // the ramp appears at both ends
+          for (uint64_t c : head) sizes.push_back(c);
+          uint64_t mid = total - used;
+          while (mid > 0) { const uint64_t c = std::min(per, mid); sizes.push_back(c); mid -= c; }
+          for (size_t i = head.size(); i-- > 0;) sizes.push_back(head[i]);
+        }
         StagePool &sg = p->ctx->stage;
         std::lock_guard<std::mutex> stage_lock(sg.mu);
         const size_t cin = (size_t)((per - 1) * sin_b + in_slab), cout = (size_t)((per - 1) * sout_b + out_slab);
@@ -339,12 +355,14 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
         unsigned char **dbuf_in = sg.in, **dbuf_out = sg.out;
         int rc = 0;
         if (e != cudaSuccess) rc = cuda_fail(e, "staging allocation");
-        for (uint64_t c = 0; c < nchunks && !rc; ++c) {
+        uint64_t lo = 0;
+        for (size_t c = 0; c < sizes.size() && !rc; ++c) {
           const int b = (int)(c & 1);
-          const uint64_t lo = c * per, cnt = std::min<uint64_t>(per, J0.bdim[od] - lo);
+          const uint64_t cnt = sizes[c];
           const size_t bin = (size_t)((cnt - 1) * sin_b + in_slab), bout = (size_t)((cnt - 1) * sout_b + out_slab);
           const unsigned char *hin = (const unsigned char *)in + lo * sin_b;
           unsigned char *hout = (unsigned char *)out + lo * sout_b;
+          lo += cnt;
           e = cudaMemcpyAsync(dbuf_in[b], hin, bin, cudaMemcpyHostToDevice, sg.s[b]);
           // strided output with gaps: preload so the gaps survive the write-back
           if (e == cudaSuccess && !nd.out_dense && !inplace)

@@ -170,6 +170,12 @@ enum FastId : uint32_t {
   FAST2_100_F32 = 82,
   FAST2_243_F32 = 83,
   FAST2_625_F32 = 84,
+  FAST3_1536_F32 = 85,     // float32 complex rows of the round-2 shapes
+  FAST3_2000_F32 = 86,
+  FAST3_4000_F32 = 87,
+  FAST3_2187_F32 = 88,
+  FAST3_3000_F32 = 89,
+  FAST3_6561_F32 = 90,
 };
 
 struct Phase {

@@ -656,9 +656,12 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       else if (L == 1536 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_1536_F64; r1 = 8; r2 = 24; r3 = 8; }
       else if (L == 2000 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_2000_F64; r1 = 10; r2 = 20; r3 = 10; }
       else if (L == 4000 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_4000_F64; r1 = 10; r2 = 20; r3 = 20; }
-      else if (L == 2187 && f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_2187_F64; r1 = 27; r2 = 9; r3 = 9; }
-      else if (L == 3000 && f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_3000_F64; r1 = 10; r2 = 30; r3 = 10; }
-      else if (L == 6561 && f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_6561_F64; r1 = 27; r2 = 27; r3 = 9; }
+      else if (L == 2187 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_2187_F64 : FAST3_2187_F32; r1 = 27; r2 = 9; r3 = 9; }
+      else if (L == 3000 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_3000_F64 : FAST3_3000_F32; r1 = 10; r2 = 30; r3 = 10; }
+      else if (L == 6561 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_6561_F64 : FAST3_6561_F32; r1 = 27; r2 = 27; r3 = 9; }
+      else if (L == 1536 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_1536_F32; r1 = 8; r2 = 24; r3 = 8; }
+      else if (L == 2000 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_2000_F32; r1 = 10; r2 = 20; r3 = 10; }
+      else if (L == 4000 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_4000_F32; r1 = 10; r2 = 20; r3 = 20; }
       else if (!c2c && (L == 16 || L == 32 || L == 64 || L == 128) && J->tw_r) {
         // short real rows: two-pass warp kernel (fast2r_kernel), tables = the engine's own W_L^m and W_N^k
         J->fast_id = (L == 16 ? FAST2R_16_F64 : L == 32 ? FAST2R_32_F64 : L == 64 ? FAST2R_64_F64 : FAST2R_128_F64) + (f64 ? 0 : 4);
