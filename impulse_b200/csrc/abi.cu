@@ -331,10 +331,10 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
         }();
         uint64_t per = std::max<uint64_t>(1, stage_bytes / std::max<int64_t>(1, sin_b + sout_b));
         per = std::min<uint64_t>(per, (J0.bdim[od] + 3) / 4);
-        // chunk schedule: full-size chunks in the middle, a geometric ramp at both ends — the pipeline's fill (first
-        // H2D with nothing to overlap) and drain (last D2H) shrink from a whole chunk to an eighth of one
-        // (IMPULSE_FFT_STAGE_RAMP=0: equal chunks)
-        static const bool ramp = [] { const char *e = std::getenv("IMPULSE_FFT_STAGE_RAMP"); return !e || std::atoi(e) != 0; }();
+        // chunk schedule: equal chunks.  IMPULSE_FFT_STAGE_RAMP=1 adds a geometric ramp at both ends (the pipeline's fill
+        // and drain shrink from a whole chunk to an eighth of one); measured on config 2 it is 0.2 ms SLOWER (23.6 vs
+        // 23.4 ms, profiles/r02_ab_e2e.txt): the 1 GiB each way over PCIe is the floor, not the fill / drain.
+        static const bool ramp = [] { const char *e = std::getenv("IMPULSE_FFT_STAGE_RAMP"); return e && std::atoi(e) != 0; }();
         std::vector<uint64_t> sizes;
         {
           const uint64_t total = J0.bdim[od];
