@@ -1,6 +1,6 @@
 """CPU-only: the reference arm of bench.py (`--impl reference`, the reference's own pocketfft on the host cores) prints
 ONE JSON line with the keys the driver reads; and bench.py refuses to run its own arm without a CUDA device (no CPU
-path).  The GPU arm's line is produced on the B200 only (profiles/r01_bench_default.json is the last one)."""
+path).  The GPU arm's line is produced on the B200 only (profiles/r02_bench_default.json is the last one)."""
 import json
 import os
 import subprocess
@@ -24,7 +24,7 @@ def test_reference_arm_line():
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_default.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_default.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
@@ -32,6 +32,25 @@ def test_committed_gpu_line_has_the_contract_keys():
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and r["traffic"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == d["e2e"]["d2h_bytes_per_step"] == 65536 * 1024 * 16
     assert d["gpu_launches"] == d["steps"]
+    # round 2: every row of the step's output is compared with the oracle, and every other BASELINE config rides along
+    assert d["accuracy"]["pass"] is True and d["accuracy"]["rows_checked"] == 65536
+    cfg = d["configs"]
+    assert set(cfg) == {"1_r2c_1024x4096", "3a_r2c_16384x1000", "3a_c2r_16384x1000", "3b_r2c_16384x3888", "3b_c2r_16384x3888",
+                        "3c_r2c_16384x4099", "3c_c2r_16384x4099", "4_fft2_8192x8192", "5_filter2d_64x4096x4096"}
+    for k, v in cfg.items():
+        assert v["accuracy"]["pass"] is True, k
+        assert v["ms_per_step"] > 0 and 0 < v["frac_8TBps"] < 1.1 and v["e2e"]["value"] > 0 and v["cpu_baseline"]["value"] > 0, k
+    assert d["configs_accuracy_all_pass"] is True
+
+
+def test_committed_multi_gpu_line_carries_the_slab_transform():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n8.json")))
+    assert d["n_gpus"] == 8 and d["scaling"] == "weak"
+    slab = d["configs"]["4_fft2_8192x8192_slab"]
+    for v in ("fft2_slab_p2p", "fft2_slab_nccl"):
+        assert slab[v]["accuracy"]["pass"] is True and slab[v]["accuracy"]["elements_checked"] == 8192 * 8192
+        assert slab[v]["scaling"] == "strong" and slab[v]["ms_per_step"] > 0
+    assert d["configs"]["2_c2c_65536x1024_strong"]["rows_per_gpu"] == 8192
 
 
 def test_own_arm_needs_a_gpu():
