@@ -89,13 +89,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+def committed_traffic(workload, kernel):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture — only while the kernel
+    that serves the workload is still the one the capture was taken on (null otherwise: no stale figure)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
-        return json.load(open(p)).get(workload)
+        ent = json.load(open(p)).get(workload)
+        if isinstance(ent, dict) and ent.get("kernel") == kernel:
+            return ent["bytes"]
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler:
@@ -723,7 +727,7 @@ def main():
                        "elements_per_s": round((1 if strong else world) * rows * n * (n if kind == "filter2d" else 1) / (ms_per_step * 1e-3), 1),
                        "frac_of_8TBps_nominal": round(value / world / 8000.0, 4), "host_numa_node": numa},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": committed_traffic(args.workload),
+                         "frac": round(achieved / peak, 4), "traffic": committed_traffic(args.workload, last_kernel),
                          "peak_source": peak_src, "kernel": last_kernel + (f" (last of {per_step} launches per step)" if per_step > 1 else ""),
                          "algorithmic_bytes_per_launch": int(per_rank_bytes)},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -60,3 +60,17 @@ def test_own_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CPU path" in (out.stderr + out.stdout)
+
+
+def test_roofline_traffic_entries_name_the_kernel_they_were_measured_on():
+    """profiles/roofline_traffic.json: the figure bench.py reports as roofline.traffic is tied to a kernel name, and the
+    one for the default workload is the kernel the committed bench line ran."""
+    t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_default.json")))
+    ent = t[d["config"]["workload"]]
+    assert ent["kernel"] == d["roofline"]["kernel"] and ent["bytes"] == d["roofline"]["traffic"]
+    assert os.path.exists(os.path.join(ROOT, ent["capture"]))
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.committed_traffic(d["config"]["workload"], ent["kernel"]) == ent["bytes"]
+    assert bench.committed_traffic(d["config"]["workload"], "some_other_kernel") is None
