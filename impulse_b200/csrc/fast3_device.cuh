@@ -153,6 +153,7 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
   const cx<T> *stg = reinterpret_cast<const cx<T> *>(stg_raw);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(stg_raw + F3Stage<T, R1 * R2 * R3, KIND>::BYTES);
   const int t = threadIdx.x;
+  griddep_launch_dependents();   // the next launch of the stream may start its own prologue while this grid runs
   if (TMA && t == 0) { mbar_init(s_bar, 1); mbar_init_fence(); }
   if (t == 0) { s_row[0] = atomicAdd(&sched[0], 1u); s_row[1] = atomicAdd(&sched[0], 1u); }
   for (int idx = t; idx < R2 * R3; idx += TT) s_tw2[idx] = tw2[idx];
@@ -162,6 +163,9 @@ fast3_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t n
     for (int a = 1; a < 4; ++a) { twA[a - 1] = tw1[(4 * a) * M1 + t]; twB[a - 1] = tw1[a * M1 + t]; }
   }
   __syncthreads();
+  // everything above read plan-time tables and this launch's own scheduler words; rows may still be written by the
+  // previous kernel of the stream (programmatic dependent launch): wait for it here
+  griddep_wait();
   constexpr uint32_t ROW_BYTES_IN = (KIND == F3_C2R ? (N + 1) : N) * sizeof(cx<T>);
   const int k1 = t % R1, i2b = t / R1;  // pass-2 ownership (T % R1 == 0)
   const cx<T> wt = KIND == F3_C2C ? mk<T>((T)1, (T)0) : __ldg(twr + t);   // real kinds: W_2N^t, this thread's twiddle factor

@@ -58,9 +58,9 @@ int launch_staged(const LineJob &J, int sm_count, cudaStream_t s, bool bwd) {
              PAIR ? "+pair" : "", DBV ? "+db" : "");
     g_last_kernel = name;
   }
-  k<<<(unsigned)grid, TT, smem, s>>>(J.in, J.out, J.n_lines, J.bs_in[0], J.bs_out[0], (const cx<T> *)J.f3_tw1,
-                                      (const cx<T> *)J.f3_tw2, (const cx<T> *)J.tw_r, (T)J.fct, sched);
-  return (int)cudaGetLastError();
+  cudaError_t le = launch_pdl(k, (unsigned)grid, (unsigned)TT, smem, s, (const void *)J.in, (void *)J.out, (uint64_t)J.n_lines, (int64_t)J.bs_in[0],
+                              (int64_t)J.bs_out[0], (const cx<T> *)J.f3_tw1, (const cx<T> *)J.f3_tw2, (const cx<T> *)J.tw_r, (T)J.fct, sched);
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 }  // namespace
 

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "fft_types.h"
 
 namespace impulse {
@@ -17,6 +19,22 @@ struct PerDeviceFlag {
   bool done[kMaxDevices] = {};
   bool &here() { return done[cur_dev()]; }
 };
+// Launch with programmatic stream serialisation (the kernel must call griddep_wait() before it touches row data):
+// the prologue of launch N+1 overlaps the tail of launch N.  IMPULSE_FFT_PDL=0 launches plainly (A/B runs).
+inline bool pdl_enabled() {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_PDL"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*k)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(block, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
+}
 // a zero-initialised pair of device words {next row, CTAs done} for one launch with dynamic row claims (fast_kernels.cu)
 unsigned int *sched_slot();
 int init_sched_slots();   // once per device, before the first launch (abi.cu: get_ctx)

@@ -43,11 +43,13 @@ fast2_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nro
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *tw = reinterpret_cast<cx<T> *>(smem_raw);
   cx<T> *xbuf = tw + N;
+  griddep_launch_dependents();
   for (int idx = threadIdx.x; idx < N; idx += WARPS * 32) {
     const int k1 = idx / R2, i = idx % R2;
     tw[idx] = twN[k1 * i];
   }
   __syncthreads();
+  griddep_wait();   // rows may still be written by the previous kernel of the stream (programmatic dependent launch)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool lane_ok = (32 % TPR == 0) || lane < GPW * TPR;
   const int g = lane_ok ? lane / TPR : 0, i = lane_ok ? lane % TPR : 0;
@@ -118,9 +120,9 @@ int launch_fast2(const LineJob &J, int sm_count, cudaStream_t s) {
   uint64_t grid = (J.n_lines + rpc - 1) / rpc;
   const uint64_t cap = (uint64_t)sm_count * MINB;
   if (grid > cap) grid = cap;
-  (bwd ? kb : kf)<<<(unsigned)grid, WARPS * 32, smem, s>>>((const cx<T> *)J.in, (cx<T> *)J.out, J.n_lines, J.bs_in[0],
-                                                          J.bs_out[0], (const cx<T> *)J.tw, (T)J.fct);
-  return (int)cudaGetLastError();
+  cudaError_t le = launch_pdl(bwd ? kb : kf, (unsigned)grid, (unsigned)(WARPS * 32), smem, s, (const cx<T> *)J.in, (cx<T> *)J.out, (uint64_t)J.n_lines,
+                              (int64_t)J.bs_in[0], (int64_t)J.bs_out[0], (const cx<T> *)J.tw, (T)J.fct);
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 }  // namespace
 
@@ -268,6 +270,7 @@ fast2p_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nr
   cx<T> *bufs = tw + N;                                             // [WARPS][2][GPW][BUF]
   uint64_t *bars = reinterpret_cast<uint64_t *>(bufs + (size_t)WARPS * 2 * GPW * BUF);  // [WARPS][2]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddep_launch_dependents();
   if (lane == 0) { mbar_init(&bars[warp * 2], 1); mbar_init(&bars[warp * 2 + 1], 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int idx = threadIdx.x; idx < N; idx += WARPS * 32) {
@@ -275,6 +278,7 @@ fast2p_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, uint64_t nr
     tw[idx] = twN[k1 * i];
   }
   __syncthreads();
+  griddep_wait();   // rows may still be written by the previous kernel of the stream (programmatic dependent launch)
   const int g = lane / TPR, i = lane % TPR;
   cx<T> *wbuf = bufs + (size_t)warp * 2 * GPW * BUF;
   uint64_t *bar = &bars[warp * 2];
@@ -409,9 +413,9 @@ int launch_fast2p(const LineJob &J, int sm_count, cudaStream_t s) {
   unsigned int *sched = sched_slot();
   if (!sched) return (int)cudaErrorMemoryAllocation;
   if (J.n_lines > 0xfff00000ull) return (int)cudaErrorInvalidValue;  // 32-bit row claims
-  (bwd ? kb : kf)<<<(unsigned)grid, WARPS * 32, smem, s>>>((const cx<T> *)J.in, (cx<T> *)J.out, J.n_lines, J.bs_in[0],
-                                                          J.bs_out[0], (const cx<T> *)J.tw, (T)J.fct, sched);
-  return (int)cudaGetLastError();
+  cudaError_t le = launch_pdl(bwd ? kb : kf, (unsigned)grid, (unsigned)(WARPS * 32), smem, s, (const cx<T> *)J.in, (cx<T> *)J.out, (uint64_t)J.n_lines,
+                              (int64_t)J.bs_in[0], (int64_t)J.bs_out[0], (const cx<T> *)J.tw, (T)J.fct, sched);
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 }  // namespace
 
@@ -557,6 +561,11 @@ static int launch_fast4_8192(const LineJob &J, int sm_count, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+static int fast2p_wide() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST2P_WIDE"); v = e ? atoi(e) : 1; }   // measured: 256 points 4.53 -> 6.63 TB/s, 128 points 4.54 -> 5.86
+  return v;
+}
 static int fast_variant() {  // IMPULSE_FFT_FAST_VARIANT=1 selects the non-TMA kernel (A/B measurements)
   static int v = -1;
   if (v < 0) { const char *e = getenv("IMPULSE_FFT_FAST_VARIANT"); v = e ? atoi(e) : 0; }
@@ -586,6 +595,9 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
       g_last_kernel = "fast2_kernel<double,32,16,4,2>";
       return launch_fast2<double, 32, 16, 4, 2>(J, sm_count, s);
     case FAST2_256_F64:
+      // 32 points per thread, 8 threads per row, four rows (16 KB) per warp iteration — the per-warp shape of the
+      // 1024- and 512-point kernels — against 16 x 16 (IMPULSE_FFT_FAST2P_WIDE=0 restores it)
+      if (fast_variant() == 0 && fast2p_wide()) { g_last_kernel = "fast2p_kernel<double,32,8,6>"; return launch_fast2p<double, 32, 8, 6>(J, sm_count, s); }
       if (fast_variant() == 0) { g_last_kernel = "fast2p_kernel<double,16,16,8>"; return launch_fast2p<double, 16, 16, 8>(J, sm_count, s); }
       g_last_kernel = "fast2_kernel<double,16,16,4,4>";
       return launch_fast2<double, 16, 16, 4, 4>(J, sm_count, s);
@@ -604,6 +616,7 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
       g_last_kernel = "fast2_kernel<double,8,8,8,4>";
       return launch_fast2<double, 8, 8, 8, 4>(J, sm_count, s);
     case FAST2_128_F64:
+      if (fast_variant() == 0 && fast2p_wide()) { g_last_kernel = "fast2p_kernel<double,32,4,5>"; return launch_fast2p<double, 32, 4, 5>(J, sm_count, s); }
       if (fast_variant() == 0) { g_last_kernel = "fast2p_kernel<double,16,8,10>"; return launch_fast2p<double, 16, 8, 10>(J, sm_count, s); }
       g_last_kernel = "fast2_kernel<double,16,8,8,4>";
       return launch_fast2<double, 16, 8, 8, 4>(J, sm_count, s);

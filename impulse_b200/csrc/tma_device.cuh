@@ -7,6 +7,11 @@
 
 #if defined(__CUDACC__)
 namespace impulse {
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may begin
+// (prologue: barrier init, table loads) while the previous kernel of the stream drains; it must not touch data the
+// previous kernel may still write before griddep_wait().  griddep_launch_dependents() lets the NEXT kernel do the same.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -37,6 +42,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #include <cstring>
 #include <thread>
 namespace impulse {
+inline void griddep_wait() {}
+inline void griddep_launch_dependents() {}
 // emulated mbarrier word: low 32 bits = transaction bytes still pending, high 32 bits = completed phases
 inline void mbar_init(uint64_t *bar, uint32_t) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
 inline void mbar_init_fence() {}
