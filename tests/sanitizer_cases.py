@@ -35,8 +35,36 @@ def new_kernels_only():
     ok &= bool(torch.allclose(run("c2r", s, torch.empty_like(x), [1], False, 1.0 / 4099), x, atol=1e-9))
     z = torch.from_numpy(rng.standard_normal((3, 4099)) + 1j * rng.standard_normal((3, 4099))).cuda()
     ok &= bool(torch.allclose(run("c2c", z, torch.empty_like(z), [1]), torch.fft.fft(z, dim=1), rtol=1e-9, atol=1e-8))
+    # ---- round 2: new two- and three-pass shapes (both precisions), wide 128 / 256-point rows, float32 fused Bluestein
+    kernels = set()
+    for n in (100, 128, 243, 256, 625, 1536, 2000, 2187, 3000, 4000, 6561):
+        for cdt, tol in ((np.complex128, 1e-9), (np.complex64, 2e-4)):
+            z = torch.from_numpy((rng.standard_normal((7, n)) + 1j * rng.standard_normal((7, n))).astype(cdt)).cuda()
+            ok &= bool(torch.allclose(run("c2c", z, torch.empty_like(z), [1]), torch.fft.fft(z, dim=1), rtol=tol, atol=tol * n))
+            ok &= bool(torch.allclose(run("c2c", z, torch.empty_like(z), [1], False, 1.0 / n), torch.fft.ifft(z, dim=1), rtol=tol, atol=tol))
+            kernels.add(ib.last_kernel())
+    z32 = torch.from_numpy((rng.standard_normal((4, 4099)) + 1j * rng.standard_normal((4, 4099))).astype(np.complex64)).cuda()
+    ok &= bool(torch.allclose(run("c2c", z32, torch.empty_like(z32), [1]), torch.fft.fft(z32, dim=1), rtol=2e-3, atol=0.2))
+    kernels.add(ib.last_kernel())
+    # fused column transform (both launches of the split in one kernel, intermediate in the L2 ring): 64 x 128 and 64 x 64
+    for shape, cdt, tol in (((8192, 80), np.complex128, 1e-9), ((3, 4096, 48), np.complex64, 2e-3)):
+        z = torch.from_numpy((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cdt)).cuda()
+        ax = len(shape) - 2
+        ok &= bool(torch.allclose(run("c2c", z, torch.empty_like(z), [ax]), torch.fft.fft(z, dim=ax), rtol=tol, atol=tol * 1e3))
+        kernels.add(ib.last_kernel())
+    # long even real lines at any stride (gather / scatter passes), DCT of a length beyond one CTA
+    y = torch.from_numpy(rng.standard_normal((40000, 3))).cuda()
+    s = run("r2c", y, torch.empty((20001, 3), dtype=torch.complex128, device="cuda"), [0])
+    ok &= bool(torch.allclose(s, torch.fft.rfft(y, dim=0), rtol=1e-9, atol=1e-6))
+    ok &= bool(torch.allclose(run("c2r", s, torch.empty_like(y), [0], False, 1.0 / 40000), y, atol=1e-9))
+    d = torch.from_numpy(rng.standard_normal((2, 10000))).cuda()
+    o = torch.empty_like(d)
+    ib.DCTDesc.init(axes=[1], dctType=2).apply(ib.DataDesc.init(o), ib.DataDesc.init(d))
+    back = torch.empty_like(d)
+    ib.DCTDesc.init(axes=[1], dctType=3, scalingFactor=1.0 / 20000).apply(ib.DataDesc.init(back), ib.DataDesc.init(o))
+    ok &= bool(torch.allclose(back, d, atol=1e-9))
     torch.cuda.synchronize()
-    print("sanitizer cases (new kernels):", "ok" if ok else "PARITY FAILURE", "last kernel", ib.last_kernel())
+    print("sanitizer cases (new kernels):", "ok" if ok else "PARITY FAILURE", "kernels", sorted(kernels))
     sys.exit(0 if ok else 1)
 
 
