@@ -53,11 +53,19 @@ __device__ __forceinline__ void col_prefetch(const LineJob &J, const ColGroup &c
 #endif
 }
 
-template <typename T, int R1, int R2, int LPC, bool BWD, bool PF, bool INROWS>
+struct ColYes { static constexpr bool value = true; };
+struct ColNo { static constexpr bool value = false; };
+// PLAIN: the job has no segmented input and no fused multiply (the launcher checks) — those code paths, their uniform
+// tests inside the unrolled loops and the constant-bank loads that feed them are compiled out; the four-step twiddle is
+// selected once per CTA (two copies of the second pass) and global addresses step by a 64-bit stride formed once.
+// Measured on the float32 column passes of config 5 (profiles/r02_colfast2_f32_inst_mix.txt): 588 executed instructions
+// per thread for 8 elements, 30 % of them floating point — constant loads 13 %, branch / reconvergence 10 %.
+template <typename T, int R1, int R2, int LPC, bool BWD, bool PF, bool INROWS, bool PLAIN = false>
 __global__ void __launch_bounds__(LPC * R2)
 colfast2_kernel(const __grid_constant__ LineJob J) {
   constexpr int N = R1 * R2, NB2 = R1 / R2;
   static_assert(R1 % R2 == 0, "column two-pass shape");
+  static_assert(!PLAIN || !INROWS, "the plain variant serves strided lines");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *S = reinterpret_cast<cx<T> *>(smem_raw);
   const int u = threadIdx.x, line = u % LPC, i = u / LPC;
@@ -72,7 +80,7 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
   const cx<T> *in = reinterpret_cast<const cx<T> *>(J.in) + off_in;
   cx<T> *out = reinterpret_cast<cx<T> *>(J.out) + off_out;
   const cx<T> *tw = reinterpret_cast<const cx<T> *>(J.tw);   // W_N^m
-  if (PF && !INROWS && line == 0 && !J.seg_len) col_prefetch(J, cg, LPC, i, R1, R2);
+  if (PF && !INROWS && line == 0 && (PLAIN || !J.seg_len)) col_prefetch(J, cg, LPC, i, R1, R2);
   cx<T> x[R1];
   if (INROWS) {
     // every line is a CONTIGUOUS row (second launch of the split on contiguous data: rows in, transposed out).
@@ -94,6 +102,15 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
       if (BWD) x[j].y = -x[j].y;
     }
     __syncthreads();
+  } else if (PLAIN) {
+    const cx<T> *p = in + (int64_t)i * J.es_in;
+    const int64_t step = (int64_t)R2 * J.es_in;
+#pragma unroll
+    for (int j = 0; j < R1; ++j) {
+      x[j] = valid ? *p : mk<T>((T)0, (T)0);
+      p += step;
+      if (BWD) x[j].y = -x[j].y;
+    }
   } else
 #pragma unroll
   for (int j = 0; j < R1; ++j) {
@@ -107,12 +124,46 @@ colfast2_kernel(const __grid_constant__ LineJob J) {
     if (BWD) x[j].y = -x[j].y;
   }
   RegFFT<T, R1>::run(x);
+  {
+    const cx<T> *pt = tw;
 #pragma unroll
-  for (int k = 1; k < R1; ++k) x[k] = cmul(x[k], __ldg(tw + i * k));
+    for (int k = 1; k < R1; ++k) { pt += i; x[k] = cmul(x[k], __ldg(pt)); }
+  }
 #pragma unroll
   for (int k = 0; k < R1; ++k) S[(k * R2 + i) * LPC + line] = x[k];
   __syncthreads();
   const T f = (T)J.fct;
+  if constexpr (PLAIN) {
+    const int64_t ostep = (int64_t)R1 * J.es_out;
+    // second pass, with (TW) or without the four-step store twiddle W_N^(k*n2): chosen once per CTA
+    auto second = [&](auto TW) {
+      constexpr bool tw4 = decltype(TW)::value;
+      cx<T> wstep = mk<T>((T)1, (T)0);
+      if constexpr (tw4) wstep = four_step_w<T>(J, (uint32_t)R1 * twi);
+#pragma unroll
+      for (int m = 0; m < NB2; ++m) {
+        const int k1 = i + R2 * m;
+        cx<T> y[R2];
+#pragma unroll
+        for (int j = 0; j < R2; ++j) y[j] = S[(k1 * R2 + j) * LPC + line];
+        RegFFT<T, R2>::run(y);
+        cx<T> w = mk<T>((T)1, (T)0);
+        if constexpr (tw4) w = four_step_w<T>(J, (uint32_t)k1 * twi);
+        cx<T> *po = out + (int64_t)k1 * J.es_out;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+          cx<T> v = y[k2];
+          if constexpr (tw4) { v = cmul(v, w); w = cmul(w, wstep); }
+          v.x *= f;
+          v.y *= BWD ? -f : f;
+          if (valid) *po = v;
+          po += ostep;
+        }
+      }
+    };
+    if (J.tw4_n) second(ColYes{}); else second(ColNo{});
+    return;
+  }
   const uint64_t umul_off = J.umul_mod ? (uint64_t)off_out % J.umul_mod : 0;
   // first launch of the split: output k is multiplied by W_N^(k*n2) (n2 = twi).  k = k1 + R1*k2 walks in
   // steps of R1, so one table lookup per k1 plus the step W_N^(R1*n2) replace a lookup per element.

@@ -481,13 +481,18 @@ int launch_colfast2(const LineJob &J, cudaStream_t s) {
   const size_t smem = sizeof(cx<T>) * (rows_in ? (size_t)LPC * (R1 * R2 + 1) : (size_t)R1 * R2 * LPC);
   const bool bwd = (J.flags & F_CONJ_SEQ) != 0;
   const bool pf = !rows_in && sizeof(T) == 4 && col_prefetch_enabled(true);   // fp64: measured slower with it
+  // strided lines without segmented input or a fused multiply run the slimmed (PLAIN) instantiation
+  static const int plain_on = [] { const char *e = getenv("IMPULSE_FFT_COL_PLAIN"); return e ? atoi(e) : 1; }();
+  const bool plain = plain_on && !rows_in && !J.seg_len && !J.umul_mod;
   typedef void (*kern_t)(const LineJob);
   kern_t kf, kb;
   if (rows_in) { kf = colfast2_kernel<T, R1, R2, LPC, false, false, true>; kb = colfast2_kernel<T, R1, R2, LPC, true, false, true>; }
+  else if (plain && pf) { kf = colfast2_kernel<T, R1, R2, LPC, false, sizeof(T) == 4, false, true>; kb = colfast2_kernel<T, R1, R2, LPC, true, sizeof(T) == 4, false, true>; }
+  else if (plain) { kf = colfast2_kernel<T, R1, R2, LPC, false, false, false, true>; kb = colfast2_kernel<T, R1, R2, LPC, true, false, false, true>; }
   else if (pf) { kf = colfast2_kernel<T, R1, R2, LPC, false, sizeof(T) == 4, false>; kb = colfast2_kernel<T, R1, R2, LPC, true, sizeof(T) == 4, false>; }
   else { kf = colfast2_kernel<T, R1, R2, LPC, false, false, false>; kb = colfast2_kernel<T, R1, R2, LPC, true, false, false>; }
-  static PerDeviceFlag flags[3];
-  bool &configured = flags[rows_in ? 2 : pf ? 1 : 0].here();
+  static PerDeviceFlag flags[5];
+  bool &configured = flags[rows_in ? 2 : (plain ? 3 : 0) + (pf ? 1 : 0)].here();
   if (!configured) {
     for (auto k : {kf, kb}) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1325,6 +1325,9 @@ void PlanCache::mark_fusable_pairs(NdPlan *plan) {
     const bool colB = B.fast_id >= COL2_64_F64 && B.fast_id <= COL2_128_F32 && B.fast_id != COL2_256_F64 && B.fast_id != COL2_256_F32;
     if (!colA || !colB || A.dtype != B.dtype) continue;
     if (A.n_fft > B.n_fft) continue;                                   // instantiated pairs: 64x64, 64x128, 128x128
+    // measured (profiles/r02_ab_plain.txt, r02_ab_colfuse.txt): 8192-point columns 1.355 -> 1.275 ms fused, but 4096-point
+    // columns (64 x 64) 0.335 -> 0.396 ms: short tiles leave too little work per dependency round
+    if ((uint64_t)A.n_fft * B.n_fft < (uint64_t)env_int("IMPULSE_FFT_FUSE_MIN_N", 8192)) continue;
     if (!A.tw4_n || A.tw4_dim != 1 || B.tw4_n || A.col_in_rows || B.col_in_rows || A.seg_len || B.seg_len) continue;
     if (A.umul_mod || B.umul_mod || A.mul_tab || B.mul_tab || a.takes_umul || b.takes_umul) continue;
     if (A.bdim[0] != B.bdim[0] || A.bdim[2] != B.bdim[2] || A.bdim[1] != B.n_fft || B.bdim[1] != A.n_fft) continue;

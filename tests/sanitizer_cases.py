@@ -46,8 +46,8 @@ def new_kernels_only():
     z32 = torch.from_numpy((rng.standard_normal((4, 4099)) + 1j * rng.standard_normal((4, 4099))).astype(np.complex64)).cuda()
     ok &= bool(torch.allclose(run("c2c", z32, torch.empty_like(z32), [1]), torch.fft.fft(z32, dim=1), rtol=2e-3, atol=0.2))
     kernels.add(ib.last_kernel())
-    # fused column transform (both launches of the split in one kernel, intermediate in the L2 ring): 64 x 128 and 64 x 64
-    for shape, cdt, tol in (((8192, 80), np.complex128, 1e-9), ((3, 4096, 48), np.complex64, 2e-3)):
+    # fused column transform (both launches of the split in one kernel, intermediate in the L2 ring): 64 x 128 and 128 x 128
+    for shape, cdt, tol in (((8192, 80), np.complex128, 1e-9), ((3, 16384, 48), np.complex64, 2e-3)):
         z = torch.from_numpy((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cdt)).cuda()
         ax = len(shape) - 2
         ok &= bool(torch.allclose(run("c2c", z, torch.empty_like(z), [ax]), torch.fft.fft(z, dim=ax), rtol=tol, atol=tol * 1e3))

@@ -92,7 +92,9 @@ def test_split_column_transform_is_marked_for_the_fused_kernel():
     assert steps == 3
     info = emu.nd_fuse_flags("c2c", a, a, a.shape, [0, 1], True)
     assert info == [1, 0, 0], info
-    b = np.empty((4, 4096, 64), np.complex64)      # strided axis of a batch: tiles = column groups x batch
+    b = np.empty((4, 8192, 64), np.complex64)      # strided axis of a batch: tiles = column groups x batch
     assert emu.nd_fuse_flags("c2c", b, b, b.shape, [1], True) == [1, 0]
+    b = np.empty((4, 4096, 64), np.complex64)      # 64 x 64: measured slower fused, stays two launches
+    assert emu.nd_fuse_flags("c2c", b, b, b.shape, [1], True) == [0, 0]
     c = np.empty((3, 2048, 32), np.complex128)     # 2048 = 32 x 64: no fused instance for that pair
     assert sum(emu.nd_fuse_flags("c2c", c, c, c.shape, [1], True)) == 0
