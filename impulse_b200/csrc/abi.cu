@@ -487,11 +487,10 @@ int one_shot(int kind, int dtype, int layout, size_t ndim, const size_t *shape, 
     std::lock_guard<std::mutex> lk(g_os_mu);
     g_os.insert(key, plan, kOneShotCap);   // a thread still executing an evicted plan holds its own reference
   }
-  if (umul_mod) {  // fused-multiply plans: device pointers, dense output
+  if (umul_mod) {  // fused-multiply plans: device pointers (positive output strides: checked by the entry points)
     if (!in || !out) return fail(IMPULSE_FFT_ERR_INVALID, "null data pointer");
     if (!is_device_ptr(in) || !is_device_ptr(out) || !is_device_ptr(umul))
       return fail(IMPULSE_FFT_ERR_INVALID, "transforms with a fused multiply take device pointers");
-    if (!plan->nd.out_dense) return fail(IMPULSE_FFT_ERR_STRIDE, "the output of a fused multiply must be dense");
     return run_device(plan.get(), in, out, fct, static_cast<cudaStream_t>(stream), umul);
   }
   return impulse_fft_execute(plan.get(), in, out, fct, stream);

@@ -1,0 +1,71 @@
+// Launcher of the whole-axis convolution kernel (colconvw_kernel, colconvw_device.cuh): FFT -> multiply -> inverse FFT
+// along a strided axis in one pass over the data, the axis resident in shared memory.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "colconvw_device.cuh"
+#include "fast_common.h"
+#include "fft_kernels.h"
+
+namespace impulse {
+
+namespace {
+template <typename T, int R1, int R2, int R3, int W, int LP, int TT>
+int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
+  constexpr int N = R1 * R2 * R3;
+  const size_t smem = sizeof(cx<T>) * ((size_t)N * W + (size_t)N + (size_t)R2 * R3);
+  if (!J.umul || !J.umul_mod || !J.f3_tw1 || !J.f3_tw2) return (int)cudaErrorInvalidValue;
+  // the LP lines of a thread move as one vector when every address involved is a multiple of the vector
+  constexpr uint64_t VB = LP * sizeof(cx<T>) >= 16 ? 16 : 8, VE = VB / sizeof(cx<T>) ? VB / sizeof(cx<T>) : 1;
+  auto mult = [&](int64_t v) { return v % (int64_t)VE == 0; };
+  const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (uintptr_t)J.umul % VB == 0 && mult(J.es_in) &&
+                  mult(J.es_out) && mult(J.bs_in[1]) && mult(J.bs_in[2]) && mult(J.bs_out[1]) && mult(J.bs_out[2]) &&
+                  J.umul_mod % VE == 0;
+  auto k = gv ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>;
+  static PerDeviceFlag flag[2];
+  static int ctas_per_sm[2][kMaxDevices] = {};
+  bool &configured = flag[gv].here();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, TT, smem);
+    if (e != cudaSuccess) return (int)e;
+    ctas_per_sm[gv][cur_dev()] = nb > 0 ? nb : 1;
+    configured = true;
+  }
+  const uint64_t tiles = ((J.bdim[0] + W - 1) / W) * J.bdim[1] * J.bdim[2];
+  if (tiles == 0) return 0;
+  if (tiles >= (1ull << 31)) return (int)cudaErrorInvalidValue;
+  uint64_t grid = (uint64_t)sm_count * ctas_per_sm[gv][cur_dev()];
+  if (grid > tiles) grid = tiles;
+  static thread_local char name[96];
+  snprintf(name, sizeof(name), "colconvw_kernel<%s,%d,%d,%d,%d,%d,%d>%s", sizeof(T) == 8 ? "double" : "float", R1, R2, R3, W, LP, TT,
+           gv ? "" : "+scalar");
+  g_last_kernel = name;
+  k<<<(unsigned)grid, TT, smem, s>>>(J);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+
+int launch_colconvw_job(const LineJob &J, int sm_count, void *stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (J.fast_id) {
+    // <T, R1, R2, R3, W lines per tile, LP lines per thread, threads>
+    case COLCONVW_512_F32: return launch_colconvw<float, 8, 8, 8, 8, 2, 256>(J, sm_count, s);
+    case COLCONVW_1024_F32: return launch_colconvw<float, 16, 8, 8, 8, 2, 256>(J, sm_count, s);
+    case COLCONVW_2048_F32: return launch_colconvw<float, 16, 16, 8, 8, 2, 512>(J, sm_count, s);
+    case COLCONVW_4096_F32: return launch_colconvw<float, 16, 16, 16, 4, 2, 512>(J, sm_count, s);
+    case COLCONVW_512_F64: return launch_colconvw<double, 8, 8, 8, 4, 2, 128>(J, sm_count, s);
+    case COLCONVW_1024_F64: return launch_colconvw<double, 16, 8, 8, 4, 2, 128>(J, sm_count, s);
+    case COLCONVW_2048_F64: return launch_colconvw<double, 16, 16, 8, 4, 2, 256>(J, sm_count, s);
+    case COLCONVW_4096_F64: return launch_colconvw<double, 16, 16, 16, 2, 2, 256>(J, sm_count, s);
+    default: return (int)cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace impulse

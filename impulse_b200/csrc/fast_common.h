@@ -43,5 +43,6 @@ int launch_fast3_job(const LineJob &job, int sm_count, void *stream);
 // staged (TMA) variants, fast3t_kernels.cu: -1 = none for this job, launch the direct-load kernel
 int launch_fast3_staged_job(const LineJob &job, int sm_count, void *stream);
 int launch_fastblue_job(const LineJob &job, int sm_count, void *stream);   // fastblue_kernels.cu
+int launch_colconvw_job(const LineJob &job, int sm_count, void *stream);   // colconvw_kernels.cu
 
 }  // namespace impulse

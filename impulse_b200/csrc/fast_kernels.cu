@@ -649,6 +649,9 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FASTBLUE_2048_F64: case FASTBLUE_4096_F64: case FASTBLUE_8192_F64:
     case FASTBLUE_2048_F32: case FASTBLUE_4096_F32: case FASTBLUE_8192_F32:
       return launch_fastblue_job(J, sm_count, stream);   // fastblue_kernels.cu
+    case COLCONVW_512_F32: case COLCONVW_1024_F32: case COLCONVW_2048_F32: case COLCONVW_4096_F32:
+    case COLCONVW_512_F64: case COLCONVW_1024_F64: case COLCONVW_2048_F64: case COLCONVW_4096_F64:
+      return launch_colconvw_job(J, sm_count, stream);   // colconvw_kernels.cu
     case COLCONV_32_F64: g_last_kernel = "colconv2_kernel<double,8,4,8>"; return launch_colconv2<double, 8, 4, 8>(J, s);
     case COLCONV_64_F64: g_last_kernel = "colconv2_kernel<double,8,8,8>"; return launch_colconv2<double, 8, 8, 8>(J, s);
     case COLCONV_128_F64: g_last_kernel = "colconv2_kernel<double,16,8,8>"; return launch_colconv2<double, 16, 8, 8>(J, s);

@@ -176,6 +176,14 @@ enum FastId : uint32_t {
   FAST3_2187_F32 = 88,
   FAST3_3000_F32 = 89,
   FAST3_6561_F32 = 90,
+  COLCONVW_512_F32 = 91,   // whole-axis convolution along a strided axis, the axis resident in shared memory (colconvw_kernel)
+  COLCONVW_1024_F32 = 92,
+  COLCONVW_2048_F32 = 93,
+  COLCONVW_4096_F32 = 94,
+  COLCONVW_512_F64 = 95,
+  COLCONVW_1024_F64 = 96,
+  COLCONVW_2048_F64 = 97,
+  COLCONVW_4096_F64 = 98,
 };
 
 struct Phase {

@@ -610,6 +610,23 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     *err = "no fused convolution kernel for this shape";
     return ERR_UNSUPPORTED;
   }
+  // whole-axis convolution: FFT -> multiply -> inverse FFT of W adjacent strided lines with the full axis in shared
+  // memory (one pass over the data instead of three): power-of-two axes of 512 ... 4096 points
+  if (s.conv_whole) {
+    uint32_t id = FAST_NONE, r1 = 0, r2 = 0, r3 = 0;
+    if (s.kind == KIND_C2C && s.umul_mod && in_lf && out_lf && s.bs_in[0] == 1 && s.bs_out[0] == 1 &&
+        n_lines / J->bdim[0] * ((J->bdim[0] + 1) / 2) < (1ull << 31)) {
+      if (N == 512) { id = f64 ? COLCONVW_512_F64 : COLCONVW_512_F32; r1 = 8; r2 = 8; r3 = 8; }
+      else if (N == 1024) { id = f64 ? COLCONVW_1024_F64 : COLCONVW_1024_F32; r1 = 16; r2 = 8; r3 = 8; }
+      else if (N == 2048) { id = f64 ? COLCONVW_2048_F64 : COLCONVW_2048_F32; r1 = 16; r2 = 16; r3 = 8; }
+      else if (N == 4096) { id = f64 ? COLCONVW_4096_F64 : COLCONVW_4096_F32; r1 = 16; r2 = 16; r3 = 16; }
+    }
+    if (id == FAST_NONE) { *err = "no whole-axis convolution kernel for this shape"; return ERR_UNSUPPORTED; }
+    rc = fast3_tables(N, r1, r2, r3, s.dtype, &J->f3_tw1, &J->f3_tw2, err);
+    if (rc) return rc;
+    J->fast_id = id;
+    return ST_OK;
+  }
   // fused Bluestein on the register core: complex Bluestein lengths up to 4104 points, and odd real
   // lengths in that range with two rows packed per complex line (Hermitian layout); contiguous rows
   // (float32 measured on the B200: 2.0-3.5x the generic engine, profiles/r02_ab_round2.txt; IMPULSE_FFT_BLUE_F32=0: off)
@@ -768,7 +785,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
                   std::vector<Dim> dims, int tw_key /*index into dims of the line-index dim, -1 = none*/, uint32_t tw4_n,
                   const void *mul_tab, uint32_t mul_stride, int blue_stage,
                   size_t esz_in, size_t esz_out, int src, int dst, int64_t src_base, int64_t dst_base,
-                  bool takes_fct, uint64_t umul_mod = 0, bool conv_mid = false) -> int {
+                  bool takes_fct, uint64_t umul_mod = 0, bool conv_mid = false, bool conv_whole = false) -> int {
     std::vector<int> key(dims.size());
     for (size_t i = 0; i < dims.size(); ++i) key[i] = (int)i;
     std::vector<size_t> order(dims.size());
@@ -827,6 +844,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     s.mul_stride = mul_stride;
     s.umul_mod = umul_mod;
     s.conv_mid = conv_mid;
+    s.conv_whole = conv_whole;
     s.blue_stage = blue_stage;
     s.r2r_type = d.r2r_type;
     s.ortho = d.ortho;
@@ -1184,10 +1202,19 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       if (i != ax && d.shape[i] != 1) dims.push_back({d.shape[i], d.stride_in[i] / (ptrdiff_t)csz, d.stride_out[i] / (ptrdiff_t)csz});
     const int64_t es = d.stride_out[ax] / (ptrdiff_t)csz;
     bool fused = false;
+    // the whole axis in shared memory: one launch, no scratch, in place or out of place (colconvw_kernel)
+    if (allow_conv_fusion && es > 1 && d.stride_in[ax] == d.stride_out[ax] && dims.size() <= (size_t)kMaxBatchDims &&
+        env_int("IMPULSE_FFT_CONV_WHOLE", 1) && !env_int("IMPULSE_FFT_NO_CONV_FUSION", 0)) {
+      const size_t n0 = plan->steps.size();
+      rc = emit(KIND_C2C, RL_HERMITIAN, true, N, es, es, dims, -1, 0, nullptr, 0, 0, csz, csz, BUF_IN, BUF_OUT, 0, 0, true,
+                d.umul_mod, false, true);
+      fused = !rc && plan->steps.size() == n0 + 1;
+      if (!fused) { plan->steps.resize(n0); rc = ST_OK; err->clear(); }
+    }
     uint32_t N1 = 1;
     for (uint32_t f = 1; (uint64_t)f * f <= N; ++f) if (N % f == 0) N1 = f;
     const uint32_t N2 = N / N1;
-    if (allow_conv_fusion && d.stride_in == d.stride_out && plan->out_dense && plan->out_lo == 0 && es > 1 && N1 >= 32 &&
+    if (!fused && allow_conv_fusion && d.stride_in == d.stride_out && plan->out_dense && plan->out_lo == 0 && es > 1 && N1 >= 32 &&
         !env_int("IMPULSE_FFT_NO_CONV_FUSION", 0)) {
       // three passes through two scratch arrays that mirror the array's own layout (see colconv2_kernel)
       const size_t n0 = plan->steps.size();

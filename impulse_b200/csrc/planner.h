@@ -87,6 +87,7 @@ struct LineSpec {
   bool ortho = false;
   uint64_t umul_mod = 0;  // caller-supplied multiplier fused into the store (pointer set at execute time)
   bool conv_mid = false;  // fused middle pass of an axis convolution (colconv2_kernel); needs tw4_n and umul_mod
+  bool conv_whole = false;  // whole-axis convolution in one launch (colconvw_kernel); needs umul_mod and adjacent lines
   int blue_stage = 0;  // multi-launch Bluestein: 1 = load+chirp+zero-pad to scratch, 2 = scratch+chirp+store
 };
 

@@ -35,7 +35,13 @@ class FFTFilter2D:
         ii = (torch.arange(kh, device=kernel.device) - kh // 2) % self.h
         jj = (torch.arange(kw, device=kernel.device) - kw // 2) % self.w
         pad[ii[:, None], jj[None, :]] = kernel
-        self.spectrum = torch.empty((self.h, self.w // 2 + 1), dtype=self.cdtype, device=kernel.device)
+        # half spectra live in rows padded to a multiple of four bins: 32-byte aligned runs for the column kernel's
+        # 4-line tiles and 16-byte aligned rows for the staged c2r rows; the multiplier is padded alike, because it is
+        # indexed by element offset
+        wc = self.w // 2 + 1
+        self.pitch = (wc + 3) // 4 * 4
+        self._spectrum_buf = torch.zeros((self.h, self.pitch), dtype=self.cdtype, device=kernel.device)
+        self.spectrum = self._spectrum_buf[:, :wc]
         FFTDesc.init(axes=[0, 1], forward=True).apply(DataDesc.init(self.spectrum), DataDesc.init(pad))
         self._spec_buf = None
 
@@ -49,19 +55,20 @@ class FFTFilter2D:
         b = images.shape[0]
         wc = self.w // 2 + 1
         if self._spec_buf is None or self._spec_buf.shape[0] != b:
-            self._spec_buf = torch.empty((b, self.h, wc), dtype=self.cdtype, device=images.device)
-        spec = self._spec_buf
+            self._spec_buf = torch.empty((b, self.h, self.pitch), dtype=self.cdtype, device=images.device)
+        spec = self._spec_buf[:, :, :wc]
         if out is None:
             out = torch.empty_like(images)
         # rows: real -> half spectrum; columns: FFT -> x filter spectrum -> inverse FFT as one axis convolution
-        # (three passes, the 2-D spectrum is never materialised); rows: half spectrum -> real
+        # (one pass with the whole column in shared memory up to 4096 rows, three passes beyond; the 2-D spectrum is
+        # never materialised); rows: half spectrum -> real
         FFTDesc.init(axes=[2], forward=True).apply(DataDesc.init(spec), DataDesc.init(images))
         stream = C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)
         esz = spec.element_size()
         shape = (C.c_size_t * 3)(b, self.h, wc)
-        st = (C.c_ssize_t * 3)(self.h * wc * esz, wc * esz, esz)
+        st = (C.c_ssize_t * 3)(self.h * self.pitch * esz, self.pitch * esz, esz)
         _lib.check(_lib.lib().impulse_fft_convolve_axis(self.code, 3, shape, st, st, 1, spec.data_ptr(), spec.data_ptr(), 1.0,
-                                                        self.spectrum.data_ptr(), self.h * wc, stream))
+                                                        self._spectrum_buf.data_ptr(), self.h * self.pitch, stream))
         FFTDesc.init(axes=[2], forward=False, scalingFactor=1.0 / (self.h * self.w)).apply(
             DataDesc.init(out), DataDesc.init(spec))
         return out

@@ -114,18 +114,21 @@ int impulse_fft_r2r_genuine_hartley(int dtype, size_t ndim, const size_t *shape,
                                     void *data_out, double fct, size_t nthreads, void *stream);
 
 /* impulse_fft_c2c with a pointwise multiply fused into the store of the last pass: the output element at
- * element offset o of the (dense) output array is multiplied by mul[o % mul_elems] — mul_elems = the
- * size of one image broadcasts one filter spectrum over a batch.  This is the FFT -> multiply half of an
- * FFT convolution without the extra pass over the spectrum.  Device pointers. */
+ * element offset o of the output array (positive strides; o counts padding between rows too, so a padded array
+ * takes a multiplier padded alike) is multiplied by mul[o % mul_elems] — mul_elems = the size of one image
+ * broadcasts one filter spectrum over a batch.  This is the FFT -> multiply half of an FFT convolution without
+ * the extra pass over the spectrum.  Device pointers. */
 int impulse_fft_c2c_mul(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
                         const ptrdiff_t *stride_out, size_t naxes, const size_t *axes, int forward, const void *data_in,
                         void *data_out, double fct, const void *mul, size_t mul_elems, void *stream);
 
 /* Convolution along ONE axis of a complex array in the frequency domain:
  *   out = fct * IFFT_axis( FFT_axis(in) .* mul[o % mul_elems] ),   o = element offset in the output layout.
- * With equal, dense in/out layouts and a strided axis whose length splits into register-kernel factors
- * (1024 ... 16384) this runs as three passes with the spectrum never written to memory; otherwise it is
- * impulse_fft_c2c_mul followed by the inverse transform.  Device pointers; in place allowed. */
+ * A strided power-of-two axis of 512 ... 4096 points over adjacent lines (unit stride across the lines) runs as ONE
+ * pass with the whole axis in shared memory (colconvw_kernel); with equal, dense in/out layouts and a strided axis
+ * whose length splits into register-kernel factors (1024 ... 16384) it runs as three passes; in both the spectrum is
+ * never written to memory.  Otherwise it is impulse_fft_c2c_mul followed by the inverse transform.
+ * Device pointers; in place allowed. */
 int impulse_fft_convolve_axis(int dtype, size_t ndim, const size_t *shape, const ptrdiff_t *stride_in,
                               const ptrdiff_t *stride_out, size_t axis, const void *data_in, void *data_out, double fct,
                               const void *mul, size_t mul_elems, void *stream);

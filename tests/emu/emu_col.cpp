@@ -34,6 +34,7 @@ using std::min;
 namespace impulse { alignas(128) unsigned char smem_raw[256 * 1024]; }
 
 #include "../../impulse_b200/csrc/col_device.cuh"
+#include "../../impulse_b200/csrc/colconvw_device.cuh"
 
 using namespace impulse;
 
@@ -85,6 +86,24 @@ int run_colconv2(const LineJob &J) {
   launch(grid, LPC * R2, [&] { colconv2_kernel<T, R1, R2, LPC, false>(J); });
   return 0;
 }
+
+// whole-axis convolution: persistent CTAs striding over the tiles (three CTAs here, so that the tile loop and the
+// merged "I1 of this tile + F1 of the next" step are exercised)
+template <typename T, int R1, int R2, int R3, int W, int LP, int TT>
+int run_colconvw(const LineJob &J) {
+  if (!J.umul || !J.umul_mod || !J.f3_tw1 || !J.f3_tw2) return -2;
+  const uint64_t tiles = ((J.bdim[0] + W - 1) / W) * J.bdim[1] * J.bdim[2];
+  emu_dim3 grid; grid.x = (unsigned)std::min<uint64_t>(tiles, 3);
+  // the vector / scalar choice of launch_colconvw (colconvw_kernels.cu)
+  constexpr uint64_t VB = LP * sizeof(cx<T>) >= 16 ? 16 : 8, VE = VB / sizeof(cx<T>) ? VB / sizeof(cx<T>) : 1;
+  auto mult = [&](int64_t v) { return v % (int64_t)VE == 0; };
+  const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (uintptr_t)J.umul % VB == 0 && mult(J.es_in) &&
+                  mult(J.es_out) && mult(J.bs_in[1]) && mult(J.bs_in[2]) && mult(J.bs_out[1]) && mult(J.bs_out[2]) &&
+                  J.umul_mod % VE == 0;
+  if (gv) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true>(J); });
+  else launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>(J); });
+  return 0;
+}
 }  // namespace
 
 // returns 0 when the job ran on an emulated column kernel, 1 when its fast_id is not a column kernel, < 0 on error
@@ -106,6 +125,14 @@ int emu_run_col_job(const LineJob &J, unsigned pipe_groups) {
     case COLCONV_32_F32: return run_colconv2<float, 8, 4, 16>(J);
     case COLCONV_64_F32: return run_colconv2<float, 8, 8, 16>(J);
     case COLCONV_128_F32: return run_colconv2<float, 16, 8, 16>(J);
+    case COLCONVW_512_F32: return run_colconvw<float, 8, 8, 8, 8, 2, 256>(J);
+    case COLCONVW_1024_F32: return run_colconvw<float, 16, 8, 8, 8, 2, 256>(J);
+    case COLCONVW_2048_F32: return run_colconvw<float, 16, 16, 8, 8, 2, 512>(J);
+    case COLCONVW_4096_F32: return run_colconvw<float, 16, 16, 16, 4, 2, 512>(J);
+    case COLCONVW_512_F64: return run_colconvw<double, 8, 8, 8, 4, 2, 128>(J);
+    case COLCONVW_1024_F64: return run_colconvw<double, 16, 8, 8, 4, 2, 128>(J);
+    case COLCONVW_2048_F64: return run_colconvw<double, 16, 16, 8, 4, 2, 256>(J);
+    case COLCONVW_4096_F64: return run_colconvw<double, 16, 16, 16, 2, 2, 256>(J);
     default: return 1;
   }
 }

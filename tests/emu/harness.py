@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(HERE, "libimpulse_fft_emu.so")
 SRC = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "emu_col.cpp"), os.path.join(ROOT, "impulse_b200", "csrc", "planner.cpp")]
 DEPS = SRC + [os.path.join(ROOT, "impulse_b200", "csrc", f) for f in
-              ("fft_device.cuh", "fft_types.h", "planner.h", "trig_tables.h", "col_device.cuh", "fast3_device.cuh")]
+              ("fft_device.cuh", "fft_types.h", "planner.h", "trig_tables.h", "col_device.cuh", "colconvw_device.cuh", "fast3_device.cuh")]
 
 KIND = {"c2c": 0, "r2c": 1, "c2r": 2}
 LAYOUT = {"hermitian": 0, "halfcomplex": 1, "fullsym": 2}

@@ -56,7 +56,8 @@ def test_four_step_split_on_the_column_kernels(dt, n, rows):
 
 
 @pytest.mark.parametrize("dt", [np.complex128, np.complex64])
-def test_fused_convolution_middle_pass(dt):
+def test_fused_convolution_middle_pass(dt, monkeypatch):
+    monkeypatch.setenv("IMPULSE_FFT_CONV_WHOLE", "0")   # the three-launch scheme (axes beyond 4096 points on the GPU)
     rng = np.random.default_rng(9)
     shape = (2, 1024, 16)                       # axis of 1024 = 32 x 32: pass A, colconv2, pass B
     x = rnd(rng, shape, dt)
@@ -66,3 +67,39 @@ def test_fused_convolution_middle_pass(dt):
     got = emu.convolve_axis(x, np.empty_like(x), 1, m.reshape(-1), 1.0 / 1024)
     assert rel(got, want) < (1e-13 if dt == np.complex128 else 5e-6)
     assert emu.col_job_count() == 3             # pass A, the fused middle pass, pass B
+
+
+# whole-axis convolution (colconvw_kernel): one launch, the axis resident in shared memory
+@pytest.mark.parametrize("dt,shape", [(np.complex64, (3, 512, 19)), (np.complex64, (2, 1024, 9)), (np.complex64, (2, 2048, 10)),
+                                       (np.complex64, (3, 4096, 5)), (np.complex128, (3, 512, 7)), (np.complex128, (2, 1024, 5)),
+                                       (np.complex128, (2, 2048, 5)), (np.complex128, (2, 4096, 3))])
+def test_whole_axis_convolution(dt, shape):
+    rng = np.random.default_rng(shape[1] + shape[2])
+    x = rnd(rng, shape, dt)
+    m = rnd(rng, shape[1:], dt)
+    want = np.fft.ifft(np.fft.fft(x.astype(np.complex128), axis=1) * m.astype(np.complex128), axis=1) * 0.5
+    emu.set_fast_cols(2)
+    got = emu.convolve_axis(x, np.full_like(x, np.nan), 1, m.reshape(-1), 0.5 / shape[1])
+    tol = 1e-13 if dt == np.complex128 else 5e-6
+    assert rel(got, want) < tol, rel(got, want)
+    assert emu.col_job_count() == 1             # one launch
+    # in place, as FFTFilter2D calls it (every tile reads its whole lines before it writes them)
+    y = x.copy()
+    emu.convolve_axis(y, y, 1, m.reshape(-1), 0.5 / shape[1])
+    assert rel(y, want) < tol
+
+
+def test_whole_axis_convolution_padded_pitch():
+    """the layout FFTFilter2D uses: half spectra in rows padded to a multiple of four bins, multiplier padded alike"""
+    rng = np.random.default_rng(5)
+    b, h, wc, pitch = 2, 512, 9, 12
+    buf = rnd(rng, (b, h, pitch), np.complex64)
+    mbuf = rnd(rng, (h, pitch), np.complex64)
+    x, m = buf[:, :, :wc], mbuf[:, :wc]
+    want = np.fft.ifft(np.fft.fft(x.astype(np.complex128), axis=1) * m.astype(np.complex128), axis=1)
+    keep = buf.copy()
+    emu.set_fast_cols(2)
+    emu.convolve_axis(x, x, 1, mbuf.reshape(-1), 1.0 / h)
+    assert emu.col_job_count() == 1
+    assert rel(buf[:, :, :wc], want) < 5e-6
+    assert np.array_equal(buf[:, :, wc:], keep[:, :, wc:])   # the padding is not touched

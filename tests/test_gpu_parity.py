@@ -756,9 +756,10 @@ def test_fftpack_and_hartley(ib, torch_mod, ref):
 
 
 def test_convolve_axis(ib, torch_mod, checker):
-    """impulse_fft_convolve_axis: IFFT_axis(FFT_axis(x) * m) — the fused three-pass plan (colconv2 kernel) on
-    strided axes of 1024..16384 points, ragged column counts, both precisions, in place and out of place;
-    and the plain two-transform plan everywhere else.  Checked against the oracle's transforms."""
+    """impulse_fft_convolve_axis: IFFT_axis(FFT_axis(x) * m) — the whole-axis kernel (colconvw_kernel, one launch)
+    on strided power-of-two axes of 512..4096 points, the fused three-pass plan (colconv2 kernel) on 8192 / 16384
+    points, ragged column counts, both precisions, in place and out of place; and the plain two-transform plan
+    everywhere else.  Checked against the oracle's transforms."""
     import ctypes as C
     from impulse_b200 import _lib
     L = _lib.lib()
@@ -766,14 +767,16 @@ def test_convolve_axis(ib, torch_mod, checker):
     used = set()
     cases = [((2, 1024, 24), np.complex128), ((2, 2048, 40), np.complex64), ((3, 4096, 29), np.complex64),
              ((2, 4096, 16), np.complex128), ((1, 8192, 16), np.complex64), ((2, 16384, 8), np.complex128),
-             ((4, 64), np.complex128), ((3, 40, 24), np.complex64), ((2, 4099, 8), np.complex128), ((2, 4096), np.complex128)]
+             ((4, 64), np.complex128), ((3, 40, 24), np.complex64), ((2, 4099, 8), np.complex128), ((2, 4096), np.complex128),
+             ((3, 512, 21), np.complex64), ((2, 512, 10), np.complex128), ((2, 1024, 9), np.complex64), ((5, 2048, 9), np.complex128),
+             ((7, 4096, 13), np.complex64), ((2, 3, 4096, 7), np.complex128)]
     for shape, cdt in cases:
-        axis = 1
+        axis = len(shape) - 2 if len(shape) > 2 else 1
         x = rnd(rng, shape, cdt)
-        period = int(np.prod(shape[1:]))
+        period = int(np.prod(shape[axis:]))
         m = rnd(rng, (period,), cdt)
         n = shape[axis]
-        spec = checker.c2c(x, [axis], True, 1.0) * m.reshape(shape[1:])
+        spec = checker.c2c(x, [axis], True, 1.0) * m.reshape(shape[axis:])
         want = checker.c2c(spec.astype(cdt), [axis], False, 1.0 / n)
         xd, md = torch_mod.from_numpy(x).cuda(), torch_mod.from_numpy(m).cuda()
         code = _lib.F64 if cdt == np.complex128 else _lib.F32
@@ -788,14 +791,17 @@ def test_convolve_axis(ib, torch_mod, checker):
             assert oracle.rel_l2(dst.cpu().numpy(), want) <= 3 * tol(n, np.float64 if cdt == np.complex128 else np.float32), \
                 (shape, cdt, inplace)
     print(sorted(used))
-    # the fused path ends on a column register kernel; count its launches: 3 per call
-    before = ib.launch_count()
-    x = torch_mod.zeros((2, 4096, 32), dtype=torch_mod.complex64, device="cuda")
-    m = torch_mod.ones(4096 * 32, dtype=torch_mod.complex64, device="cuda")
-    st = (C.c_ssize_t * 3)(4096 * 32 * 8, 32 * 8, 8)
-    _lib.check(L.impulse_fft_convolve_axis(_lib.F32, 3, (C.c_size_t * 3)(2, 4096, 32), st, st, 1, x.data_ptr(), x.data_ptr(), 1.0,
-                                           m.data_ptr(), 4096 * 32, None))
-    assert ib.launch_count() - before == 3
+    assert any(k.startswith("colconvw_kernel<float,16,16,16") for k in used), used
+    assert any(k.startswith("colconvw_kernel<double,16,16,8") for k in used), used
+    # launches per call: the whole-axis kernel is one, the three-pass plan (pass A, colconv2, pass B) three
+    for n, launches in ((4096, 1), (8192, 3)):
+        before = ib.launch_count()
+        x = torch_mod.zeros((2, n, 32), dtype=torch_mod.complex64, device="cuda")
+        m = torch_mod.ones(n * 32, dtype=torch_mod.complex64, device="cuda")
+        st = (C.c_ssize_t * 3)(n * 32 * 8, 32 * 8, 8)
+        _lib.check(L.impulse_fft_convolve_axis(_lib.F32, 3, (C.c_size_t * 3)(2, n, 32), st, st, 1, x.data_ptr(), x.data_ptr(), 1.0,
+                                               m.data_ptr(), n * 32, None))
+        assert ib.launch_count() - before == launches, (n, ib.launch_count() - before)
 
 
 def test_long_lines(ib, torch_mod, checker):
