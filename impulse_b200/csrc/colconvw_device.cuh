@@ -53,16 +53,19 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
 
   // tile -> (group of W adjacent lines, outer indices); the dimension along which the multiplier repeats (bdim[1])
   // runs fastest, so that one block of multipliers serves every image in turn from L2
+  // J.n_load = GF: GF adjacent groups run fastest of all, i.e. on CTAs that execute side by side, so that the 32-byte
+  // pieces of one 128-byte line are requested together (DRAM row hits instead of one activate per piece)
   const uint32_t g0n = (uint32_t)((J.bdim[0] + W - 1) / W), d1 = (uint32_t)J.bdim[1];
-  const uint32_t ntiles = g0n * d1 * (uint32_t)J.bdim[2];
+  const uint32_t gf = J.n_load ? J.n_load : 1u, ghn = (g0n + gf - 1) / gf;
+  const uint32_t ntiles = ghn * gf * d1 * (uint32_t)J.bdim[2];
   struct Tile { int64_t in0, out0; uint64_t umoff; int nv; };   // offsets of the group's first line; valid lines of this thread
   auto tile_of = [&](const uint32_t id) {
-    const uint32_t r = id / d1, i1 = id - r * d1, i2 = r / g0n, g0 = r - i2 * g0n;
+    const uint32_t ra = id / gf, glo = id - ra * gf, r = ra / d1, i1 = ra - r * d1, i2 = r / ghn, g0 = (r - i2 * ghn) * gf + glo;
     Tile q;
     q.in0 = (int64_t)(g0 * W) + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
     q.out0 = (int64_t)(g0 * W) + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
     q.umoff = (uint64_t)(q.out0 + lp * LP) % J.umul_mod;
-    const int left = (int)((uint32_t)J.bdim[0] - g0 * W) - lp * LP;
+    const int left = (int)J.bdim[0] - (int)(g0 * W) - lp * LP;   // (groups past the end of a ragged last block: nothing valid)
     q.nv = left >= LP ? LP : (left > 0 ? left : 0);
     return q;
   };

@@ -38,7 +38,15 @@ int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
     ctas_per_sm[gv][cur_dev()] = nb > 0 ? nb : 1;
     configured = true;
   }
-  const uint64_t tiles = ((J.bdim[0] + W - 1) / W) * J.bdim[1] * J.bdim[2];
+  // tile order: GF adjacent groups on CTAs that run side by side (IMPULSE_FFT_CONVW_GF overrides: A/B runs)
+  static const int gf_env = [] { const char *e = getenv("IMPULSE_FFT_CONVW_GF"); return e ? atoi(e) : 0; }();
+  // (measured on config 5, 32-byte runs: GF = 1: 9.61 ms, 2: 9.45, 4: 12.5, 8: 11.5, 16: 10.9 — side-by-side requests for
+  // the pieces of one line contend instead of merging; default 1)
+  const uint32_t gf = gf_env > 0 ? (uint32_t)gf_env : 1u;
+  LineJob Jg = J;
+  Jg.n_load = gf;
+  const uint64_t g0n = (J.bdim[0] + W - 1) / W;
+  const uint64_t tiles = (g0n + gf - 1) / gf * gf * J.bdim[1] * J.bdim[2];
   if (tiles == 0) return 0;
   if (tiles >= (1ull << 31)) return (int)cudaErrorInvalidValue;
   uint64_t grid = (uint64_t)sm_count * ctas_per_sm[gv][cur_dev()];
@@ -47,7 +55,7 @@ int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
   snprintf(name, sizeof(name), "colconvw_kernel<%s,%d,%d,%d,%d,%d,%d>%s", sizeof(T) == 8 ? "double" : "float", R1, R2, R3, W, LP, TT,
            gv ? "" : "+scalar");
   g_last_kernel = name;
-  k<<<(unsigned)grid, TT, smem, s>>>(J);
+  k<<<(unsigned)grid, TT, smem, s>>>(Jg);
   return (int)cudaGetLastError();
 }
 }  // namespace
@@ -56,12 +64,13 @@ int launch_colconvw_job(const LineJob &J, int sm_count, void *stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (J.fast_id) {
     // <T, R1, R2, R3, W lines per tile, LP lines per thread, threads>
-    case COLCONVW_512_F32: return launch_colconvw<float, 8, 8, 8, 8, 2, 256>(J, sm_count, s);
-    case COLCONVW_1024_F32: return launch_colconvw<float, 16, 8, 8, 8, 2, 256>(J, sm_count, s);
+    // 512 / 1024 points: 128-byte runs (16 float32 or 8 float64 lines); 2048 / 4096 points fit only 64- / 32-byte runs
+    case COLCONVW_512_F32: return launch_colconvw<float, 8, 8, 8, 16, 2, 512>(J, sm_count, s);
+    case COLCONVW_1024_F32: return launch_colconvw<float, 16, 8, 8, 16, 2, 512>(J, sm_count, s);
     case COLCONVW_2048_F32: return launch_colconvw<float, 16, 16, 8, 8, 2, 512>(J, sm_count, s);
     case COLCONVW_4096_F32: return launch_colconvw<float, 16, 16, 16, 4, 2, 512>(J, sm_count, s);
-    case COLCONVW_512_F64: return launch_colconvw<double, 8, 8, 8, 4, 2, 128>(J, sm_count, s);
-    case COLCONVW_1024_F64: return launch_colconvw<double, 16, 8, 8, 4, 2, 128>(J, sm_count, s);
+    case COLCONVW_512_F64: return launch_colconvw<double, 8, 8, 8, 8, 2, 256>(J, sm_count, s);
+    case COLCONVW_1024_F64: return launch_colconvw<double, 16, 8, 8, 8, 2, 256>(J, sm_count, s);
     case COLCONVW_2048_F64: return launch_colconvw<double, 16, 16, 8, 4, 2, 256>(J, sm_count, s);
     case COLCONVW_4096_F64: return launch_colconvw<double, 16, 16, 16, 2, 2, 256>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;

@@ -618,8 +618,11 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
         n_lines / J->bdim[0] * ((J->bdim[0] + 1) / 2) < (1ull << 31)) {
       if (N == 512) { id = f64 ? COLCONVW_512_F64 : COLCONVW_512_F32; r1 = 8; r2 = 8; r3 = 8; }
       else if (N == 1024) { id = f64 ? COLCONVW_1024_F64 : COLCONVW_1024_F32; r1 = 16; r2 = 8; r3 = 8; }
+      // 2048 points leave room for 64-byte runs (measured 7-9 % ahead of the three-launch scheme), 4096 points for
+      // 32-byte runs only, which HBM serves at 2.0 TB/s (tools/micro/strided_runs.cu; profiles/r02_ab_convw.txt):
+      // slower than the three-launch scheme, so only under IMPULSE_FFT_CONV_WHOLE=2
       else if (N == 2048) { id = f64 ? COLCONVW_2048_F64 : COLCONVW_2048_F32; r1 = 16; r2 = 16; r3 = 8; }
-      else if (N == 4096) { id = f64 ? COLCONVW_4096_F64 : COLCONVW_4096_F32; r1 = 16; r2 = 16; r3 = 16; }
+      else if (N == 4096 && env_int("IMPULSE_FFT_CONV_WHOLE", 1) >= 2) { id = f64 ? COLCONVW_4096_F64 : COLCONVW_4096_F32; r1 = 16; r2 = 16; r3 = 16; }
     }
     if (id == FAST_NONE) { *err = "no whole-axis convolution kernel for this shape"; return ERR_UNSUPPORTED; }
     rc = fast3_tables(N, r1, r2, r3, s.dtype, &J->f3_tw1, &J->f3_tw2, err);
@@ -1214,7 +1217,8 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     uint32_t N1 = 1;
     for (uint32_t f = 1; (uint64_t)f * f <= N; ++f) if (N % f == 0) N1 = f;
     const uint32_t N2 = N / N1;
-    if (!fused && allow_conv_fusion && d.stride_in == d.stride_out && plan->out_dense && plan->out_lo == 0 && es > 1 && N1 >= 32 &&
+    // (positive strides, possibly padded rows: the scratch arrays mirror the layout, padding included)
+    if (!fused && allow_conv_fusion && d.stride_in == d.stride_out && plan->out_lo == 0 && es > 1 && N1 >= 32 &&
         !env_int("IMPULSE_FFT_NO_CONV_FUSION", 0)) {
       // three passes through two scratch arrays that mirror the array's own layout (see colconv2_kernel)
       const size_t n0 = plan->steps.size();

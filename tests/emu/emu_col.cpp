@@ -92,7 +92,10 @@ int run_colconv2(const LineJob &J) {
 template <typename T, int R1, int R2, int R3, int W, int LP, int TT>
 int run_colconvw(const LineJob &J) {
   if (!J.umul || !J.umul_mod || !J.f3_tw1 || !J.f3_tw2) return -2;
-  const uint64_t tiles = ((J.bdim[0] + W - 1) / W) * J.bdim[1] * J.bdim[2];
+  const uint32_t gf = 2;   // the product's default is 1 (IMPULSE_FFT_CONVW_GF); 2 exercises the block decode as well
+  LineJob Jg = J;
+  Jg.n_load = gf;
+  const uint64_t tiles = ((J.bdim[0] + W - 1) / W + gf - 1) / gf * gf * J.bdim[1] * J.bdim[2];
   emu_dim3 grid; grid.x = (unsigned)std::min<uint64_t>(tiles, 3);
   // the vector / scalar choice of launch_colconvw (colconvw_kernels.cu)
   constexpr uint64_t VB = LP * sizeof(cx<T>) >= 16 ? 16 : 8, VE = VB / sizeof(cx<T>) ? VB / sizeof(cx<T>) : 1;
@@ -100,8 +103,8 @@ int run_colconvw(const LineJob &J) {
   const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (uintptr_t)J.umul % VB == 0 && mult(J.es_in) &&
                   mult(J.es_out) && mult(J.bs_in[1]) && mult(J.bs_in[2]) && mult(J.bs_out[1]) && mult(J.bs_out[2]) &&
                   J.umul_mod % VE == 0;
-  if (gv) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true>(J); });
-  else launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>(J); });
+  if (gv) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true>(Jg); });
+  else launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>(Jg); });
   return 0;
 }
 }  // namespace
@@ -125,12 +128,12 @@ int emu_run_col_job(const LineJob &J, unsigned pipe_groups) {
     case COLCONV_32_F32: return run_colconv2<float, 8, 4, 16>(J);
     case COLCONV_64_F32: return run_colconv2<float, 8, 8, 16>(J);
     case COLCONV_128_F32: return run_colconv2<float, 16, 8, 16>(J);
-    case COLCONVW_512_F32: return run_colconvw<float, 8, 8, 8, 8, 2, 256>(J);
-    case COLCONVW_1024_F32: return run_colconvw<float, 16, 8, 8, 8, 2, 256>(J);
+    case COLCONVW_512_F32: return run_colconvw<float, 8, 8, 8, 16, 2, 512>(J);
+    case COLCONVW_1024_F32: return run_colconvw<float, 16, 8, 8, 16, 2, 512>(J);
     case COLCONVW_2048_F32: return run_colconvw<float, 16, 16, 8, 8, 2, 512>(J);
     case COLCONVW_4096_F32: return run_colconvw<float, 16, 16, 16, 4, 2, 512>(J);
-    case COLCONVW_512_F64: return run_colconvw<double, 8, 8, 8, 4, 2, 128>(J);
-    case COLCONVW_1024_F64: return run_colconvw<double, 16, 8, 8, 4, 2, 128>(J);
+    case COLCONVW_512_F64: return run_colconvw<double, 8, 8, 8, 8, 2, 256>(J);
+    case COLCONVW_1024_F64: return run_colconvw<double, 16, 8, 8, 8, 2, 256>(J);
     case COLCONVW_2048_F64: return run_colconvw<double, 16, 16, 8, 4, 2, 256>(J);
     case COLCONVW_4096_F64: return run_colconvw<double, 16, 16, 16, 2, 2, 256>(J);
     default: return 1;

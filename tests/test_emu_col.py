@@ -73,7 +73,8 @@ def test_fused_convolution_middle_pass(dt, monkeypatch):
 @pytest.mark.parametrize("dt,shape", [(np.complex64, (3, 512, 19)), (np.complex64, (2, 1024, 9)), (np.complex64, (2, 2048, 10)),
                                        (np.complex64, (3, 4096, 5)), (np.complex128, (3, 512, 7)), (np.complex128, (2, 1024, 5)),
                                        (np.complex128, (2, 2048, 5)), (np.complex128, (2, 4096, 3))])
-def test_whole_axis_convolution(dt, shape):
+def test_whole_axis_convolution(dt, shape, monkeypatch):
+    monkeypatch.setenv("IMPULSE_FFT_CONV_WHOLE", "2")   # 2048 / 4096 points too (by default they take the three-launch scheme)
     rng = np.random.default_rng(shape[1] + shape[2])
     x = rnd(rng, shape, dt)
     m = rnd(rng, shape[1:], dt)
@@ -103,3 +104,20 @@ def test_whole_axis_convolution_padded_pitch():
     assert emu.col_job_count() == 1
     assert rel(buf[:, :, :wc], want) < 5e-6
     assert np.array_equal(buf[:, :, wc:], keep[:, :, wc:])   # the padding is not touched
+
+
+def test_three_launch_convolution_padded_pitch(monkeypatch):
+    """the same layout on the three-launch scheme (what a 4096-row image takes by default)"""
+    monkeypatch.setenv("IMPULSE_FFT_CONV_WHOLE", "0")
+    rng = np.random.default_rng(6)
+    b, h, wc, pitch = 2, 1024, 17, 20
+    buf = rnd(rng, (b, h, pitch), np.complex64)
+    mbuf = rnd(rng, (h, pitch), np.complex64)
+    x, m = buf[:, :, :wc], mbuf[:, :wc]
+    want = np.fft.ifft(np.fft.fft(x.astype(np.complex128), axis=1) * m.astype(np.complex128), axis=1)
+    keep = buf.copy()
+    emu.set_fast_cols(2)
+    emu.convolve_axis(x, x, 1, mbuf.reshape(-1), 1.0 / h)
+    assert emu.col_job_count() == 3
+    assert rel(buf[:, :, :wc], want) < 5e-6
+    assert np.array_equal(buf[:, :, wc:], keep[:, :, wc:])

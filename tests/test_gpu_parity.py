@@ -755,6 +755,29 @@ def test_fftpack_and_hartley(ib, torch_mod, ref):
     assert float(torch_mod.linalg.vector_norm(h2 - img) / torch_mod.linalg.vector_norm(img)) <= 1e-13
 
 
+def test_convolve_axis_whole_long(ib, torch_mod, checker, monkeypatch):
+    """the whole-axis kernel at 4096 points (32-byte runs: off by default, IMPULSE_FFT_CONV_WHOLE=2) and at 2048"""
+    import ctypes as C
+    from impulse_b200 import _lib
+    monkeypatch.setenv("IMPULSE_FFT_CONV_WHOLE", "2")
+    L = _lib.lib()
+    rng = np.random.default_rng(98)
+    used = set()
+    for shape, cdt in (((3, 2048, 11), np.complex64), ((2, 2048, 6), np.complex128), ((5, 4096, 14), np.complex64), ((3, 4096, 5), np.complex128)):
+        x = rnd(rng, shape, cdt)
+        m = rnd(rng, (shape[1] * shape[2],), cdt)
+        n = shape[1]
+        spec = checker.c2c(x, [1], True, 1.0) * m.reshape(shape[1:])
+        want = checker.c2c(spec.astype(cdt), [1], False, 1.0 / n)
+        xd, md = torch_mod.from_numpy(x).cuda(), torch_mod.from_numpy(m).cuda()
+        st = (C.c_ssize_t * 3)(*x.strides)
+        _lib.check(L.impulse_fft_convolve_axis(_lib.F64 if cdt == np.complex128 else _lib.F32, 3, (C.c_size_t * 3)(*shape), st, st, 1,
+                                               xd.data_ptr(), xd.data_ptr(), 1.0 / n, md.data_ptr(), m.size, None))
+        used.add(ib.last_kernel())
+        assert oracle.rel_l2(xd.cpu().numpy(), want) <= 3 * tol(n, np.float64 if cdt == np.complex128 else np.float32), (shape, cdt)
+    assert all(k.startswith("colconvw_kernel") for k in used), used
+
+
 def test_convolve_axis(ib, torch_mod, checker):
     """impulse_fft_convolve_axis: IFFT_axis(FFT_axis(x) * m) — the whole-axis kernel (colconvw_kernel, one launch)
     on strided power-of-two axes of 512..4096 points, the fused three-pass plan (colconv2 kernel) on 8192 / 16384
@@ -791,10 +814,10 @@ def test_convolve_axis(ib, torch_mod, checker):
             assert oracle.rel_l2(dst.cpu().numpy(), want) <= 3 * tol(n, np.float64 if cdt == np.complex128 else np.float32), \
                 (shape, cdt, inplace)
     print(sorted(used))
-    assert any(k.startswith("colconvw_kernel<float,16,16,16") for k in used), used
-    assert any(k.startswith("colconvw_kernel<double,16,16,8") for k in used), used
+    assert any(k.startswith("colconvw_kernel<float,16,8,8") for k in used), used
+    assert any(k.startswith("colconvw_kernel<double,8,8,8") for k in used), used
     # launches per call: the whole-axis kernel is one, the three-pass plan (pass A, colconv2, pass B) three
-    for n, launches in ((4096, 1), (8192, 3)):
+    for n, launches in ((2048, 1), (4096, 3)):
         before = ib.launch_count()
         x = torch_mod.zeros((2, n, 32), dtype=torch_mod.complex64, device="cuda")
         m = torch_mod.ones(n * 32, dtype=torch_mod.complex64, device="cuda")
