@@ -792,6 +792,7 @@ int impulse_fft_cols_from_parts(int dtype, size_t nparts, const void *const *par
   d.stride_in = {(ptrdiff_t)(ld_part * csz), (ptrdiff_t)csz};
   d.stride_out = {(ptrdiff_t)(ld_out * csz), (ptrdiff_t)csz};
   d.axes = {0};
+  d.no_col_whole = true;   // the whole-axis kernel does not read segmented input
   impulse_fft_plan raw = nullptr;
   int rc = create_plan(&raw, d);
   if (rc) return rc;

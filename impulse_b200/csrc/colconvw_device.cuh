@@ -29,8 +29,12 @@ namespace impulse {
 
 template <typename T, int LP> struct alignas((LP * sizeof(cx<T>)) >= 16 ? 16 : 8) CwVec { cx<T> v[LP]; };
 
+// MODE: CW_CONV = the convolution above; CW_FWD / CW_BWD = the plain transform of the axis (passes F1, F2, F3 and a store
+// straight from the last butterfly's registers; backward = conj(FFT(conj x))): ONE pass over the data for strided
+// power-of-two axes that the four-step split serves in two.
+enum { CW_CONV = 0, CW_FWD = 1, CW_BWD = 2 };
 // GV: the LP lines of a thread are read / written as one vector in global memory (the launcher checks alignment)
-template <typename T, int R1, int R2, int R3, int W, int LP, int TT, bool GV>
+template <typename T, int R1, int R2, int R3, int W, int LP, int TT, bool GV, int MODE = CW_CONV>
 __global__ void __launch_bounds__(TT, 1)
 colconvw_kernel(const __grid_constant__ LineJob J) {
   constexpr int N = R1 * R2 * R3, M1 = R2 * R3, PW = W / LP, TB = TT / PW;
@@ -64,7 +68,7 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
     Tile q;
     q.in0 = (int64_t)(g0 * W) + (int64_t)i1 * J.bs_in[1] + (int64_t)i2 * J.bs_in[2];
     q.out0 = (int64_t)(g0 * W) + (int64_t)i1 * J.bs_out[1] + (int64_t)i2 * J.bs_out[2];
-    q.umoff = (uint64_t)(q.out0 + lp * LP) % J.umul_mod;
+    q.umoff = MODE == CW_CONV ? (uint64_t)(q.out0 + lp * LP) % J.umul_mod : 0;
     const int left = (int)J.bdim[0] - (int)(g0 * W) - lp * LP;   // (groups past the end of a ragged last block: nothing valid)
     q.nv = left >= LP ? LP : (left > 0 ? left : 0);
     return q;
@@ -83,14 +87,21 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
         p += step;
       }
     }
+    if (MODE == CW_BWD) {
+#pragma unroll
+      for (int j = 0; j < R1; ++j)
+#pragma unroll
+        for (int l = 0; l < LP; ++l) x[j].v[l].y = -x[j].v[l].y;
+    }
   };
-  auto gput = [&](cx<T> *p, const int nv, const int64_t step, const Vec (&x)[R1]) {
+  auto gput = [&](cx<T> *p, const int nv, const int64_t step, const auto &x) {   // x: Vec[R1] or Vec[R3]
+    constexpr int R = (int)(sizeof(x) / sizeof(Vec));
     if (GV && nv == LP) {
 #pragma unroll
-      for (int j = 0; j < R1; ++j) { *reinterpret_cast<Vec *>(p) = x[j]; p += step; }
+      for (int j = 0; j < R; ++j) { *reinterpret_cast<Vec *>(p) = x[j]; p += step; }
     } else {
 #pragma unroll
-      for (int j = 0; j < R1; ++j) {
+      for (int j = 0; j < R; ++j) {
 #pragma unroll
         for (int l = 0; l < LP; ++l) if (l < nv) p[l] = x[j].v[l];
         p += step;
@@ -161,14 +172,20 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
   if (tile >= ntiles) return;
   Tile cur = tile_of(tile);
   __syncthreads();   // the tables
+  if (MODE == CW_CONV) {
 #pragma unroll 1
-  for (int m = 0; m < NB1; ++m) f1(cur, tb + TB * m);
+    for (int m = 0; m < NB1; ++m) f1(cur, tb + TB * m);
+  }
   const T f = (T)J.fct;
   for (;;) {
     const uint32_t next = tile + gridDim.x;
     const bool more = next < ntiles;
     Tile nxt = cur;
     if (more) { nxt = tile_of(next); prefetch_tile(nxt); }
+    if (MODE != CW_CONV) {
+#pragma unroll 1
+      for (int m = 0; m < NB1; ++m) f1(cur, tb + TB * m);
+    }
     __syncthreads();
     // ---------------- F2
 #pragma unroll 1
@@ -189,6 +206,30 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
       for (int k = 0; k < R2; ++k) at(base + R3 * k) = y[k];
     }
     __syncthreads();
+    if constexpr (MODE != CW_CONV) {
+      // ---------------- F3 + store: X[k1 + R1 k2 + R1 R2 k3] leaves from the butterfly's registers
+#pragma unroll 1
+      for (int m = 0; m < NB3; ++m) {
+        const int b = tb + TB * m, k2 = b % R2, k1 = b / R2;
+        const uint32_t base = (uint32_t)(k1 * M1 + R3 * k2);
+        Vec y[R3];
+#pragma unroll
+        for (int j = 0; j < R3; ++j) y[j] = at(base + j);
+        fftR3(y);
+        const T fy = MODE == CW_BWD ? -f : f;
+#pragma unroll
+        for (int k3 = 0; k3 < R3; ++k3)
+#pragma unroll
+          for (int l = 0; l < LP; ++l) y[k3].v[l] = mk<T>(y[k3].v[l].x * f, y[k3].v[l].y * fy);
+        gput(reinterpret_cast<cx<T> *>(J.out) + cur.out0 + lp * LP + (int64_t)(k1 + R1 * k2) * J.es_out, cur.nv,
+             (int64_t)(R1 * R2) * J.es_out, y);
+      }
+      if (!more) break;
+      __syncthreads();   // every pass-3 read before the next tile's pass-1 writes
+      cur = nxt;
+      tile = next;
+      continue;
+    }
     // ---------------- F3, multiply, I3
 #pragma unroll 1
     for (int m = 0; m < NB3; ++m) {

@@ -12,21 +12,31 @@
 namespace impulse {
 
 namespace {
-template <typename T, int R1, int R2, int R3, int W, int LP, int TT>
+template <typename T, int R1, int R2, int R3, int W, int LP, int TT, bool PLAIN = false>
 int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3;
   const size_t smem = sizeof(cx<T>) * ((size_t)N * W + (size_t)N + (size_t)R2 * R3);
-  if (!J.umul || !J.umul_mod || !J.f3_tw1 || !J.f3_tw2) return (int)cudaErrorInvalidValue;
+  if (!J.f3_tw1 || !J.f3_tw2) return (int)cudaErrorInvalidValue;
+  if (!PLAIN && (!J.umul || !J.umul_mod)) return (int)cudaErrorInvalidValue;
+  const bool bwd = PLAIN && (J.flags & F_CONJ_SEQ) != 0;
   // the LP lines of a thread move as one vector when every address involved is a multiple of the vector
   constexpr uint64_t VB = LP * sizeof(cx<T>) >= 16 ? 16 : 8, VE = VB / sizeof(cx<T>) ? VB / sizeof(cx<T>) : 1;
   auto mult = [&](int64_t v) { return v % (int64_t)VE == 0; };
-  const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (uintptr_t)J.umul % VB == 0 && mult(J.es_in) &&
+  const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (PLAIN || (uintptr_t)J.umul % VB == 0) && mult(J.es_in) &&
                   mult(J.es_out) && mult(J.bs_in[1]) && mult(J.bs_in[2]) && mult(J.bs_out[1]) && mult(J.bs_out[2]) &&
-                  J.umul_mod % VE == 0;
-  auto k = gv ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>;
-  static PerDeviceFlag flag[2];
-  static int ctas_per_sm[2][kMaxDevices] = {};
-  bool &configured = flag[gv].here();
+                  (PLAIN || J.umul_mod % VE == 0);
+  typedef void (*kern_t)(const LineJob);
+  kern_t k;
+  if constexpr (PLAIN) {
+    k = bwd ? (gv ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_BWD> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_BWD>)
+            : (gv ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_FWD> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_FWD>);
+  } else {
+    k = gv ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>;
+  }
+  static PerDeviceFlag flag[4];
+  static int ctas_per_sm[4][kMaxDevices] = {};
+  const int vi = (gv ? 1 : 0) + (bwd ? 2 : 0);
+  bool &configured = flag[vi].here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -35,7 +45,7 @@ int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
     int nb = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, TT, smem);
     if (e != cudaSuccess) return (int)e;
-    ctas_per_sm[gv][cur_dev()] = nb > 0 ? nb : 1;
+    ctas_per_sm[vi][cur_dev()] = nb > 0 ? nb : 1;
     configured = true;
   }
   // tile order: GF adjacent groups on CTAs that run side by side (IMPULSE_FFT_CONVW_GF overrides: A/B runs)
@@ -49,11 +59,11 @@ int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
   const uint64_t tiles = (g0n + gf - 1) / gf * gf * J.bdim[1] * J.bdim[2];
   if (tiles == 0) return 0;
   if (tiles >= (1ull << 31)) return (int)cudaErrorInvalidValue;
-  uint64_t grid = (uint64_t)sm_count * ctas_per_sm[gv][cur_dev()];
+  uint64_t grid = (uint64_t)sm_count * ctas_per_sm[vi][cur_dev()];
   if (grid > tiles) grid = tiles;
   static thread_local char name[96];
-  snprintf(name, sizeof(name), "colconvw_kernel<%s,%d,%d,%d,%d,%d,%d>%s", sizeof(T) == 8 ? "double" : "float", R1, R2, R3, W, LP, TT,
-           gv ? "" : "+scalar");
+  snprintf(name, sizeof(name), "colconvw_kernel<%s,%d,%d,%d,%d,%d,%d>%s%s", sizeof(T) == 8 ? "double" : "float", R1, R2, R3, W, LP, TT,
+           PLAIN ? (bwd ? "+bwd" : "+fwd") : "", gv ? "" : "+scalar");
   g_last_kernel = name;
   k<<<(unsigned)grid, TT, smem, s>>>(Jg);
   return (int)cudaGetLastError();
@@ -62,6 +72,17 @@ int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
 
 int launch_colconvw_job(const LineJob &J, int sm_count, void *stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // IMPULSE_FFT_CW_NARROW=1 (A/B runs): 1024-point axes as half-width tiles (64-byte runs, two CTAs per SM)
+  static const int narrow = [] { const char *e = getenv("IMPULSE_FFT_CW_NARROW"); return e ? atoi(e) : 0; }();
+  if (narrow) {
+    switch (J.fast_id) {
+      case COLCONVW_1024_F32: return launch_colconvw<float, 16, 8, 8, 8, 2, 256>(J, sm_count, s);
+      case COLCONVW_1024_F64: return launch_colconvw<double, 16, 8, 8, 4, 2, 128>(J, sm_count, s);
+      case COLW_1024_F32: return launch_colconvw<float, 16, 8, 8, 8, 2, 256, true>(J, sm_count, s);
+      case COLW_1024_F64: return launch_colconvw<double, 16, 8, 8, 4, 2, 128, true>(J, sm_count, s);
+      default: break;
+    }
+  }
   switch (J.fast_id) {
     // <T, R1, R2, R3, W lines per tile, LP lines per thread, threads>
     // 512 / 1024 points: 128-byte runs (16 float32 or 8 float64 lines); 2048 / 4096 points fit only 64- / 32-byte runs
@@ -73,6 +94,10 @@ int launch_colconvw_job(const LineJob &J, int sm_count, void *stream) {
     case COLCONVW_1024_F64: return launch_colconvw<double, 16, 8, 8, 8, 2, 256>(J, sm_count, s);
     case COLCONVW_2048_F64: return launch_colconvw<double, 16, 16, 8, 4, 2, 256>(J, sm_count, s);
     case COLCONVW_4096_F64: return launch_colconvw<double, 16, 16, 16, 2, 2, 256>(J, sm_count, s);
+    case COLW_1024_F32: return launch_colconvw<float, 16, 8, 8, 16, 2, 512, true>(J, sm_count, s);
+    case COLW_2048_F32: return launch_colconvw<float, 16, 16, 8, 8, 2, 512, true>(J, sm_count, s);
+    case COLW_1024_F64: return launch_colconvw<double, 16, 8, 8, 8, 2, 256, true>(J, sm_count, s);
+    case COLW_2048_F64: return launch_colconvw<double, 16, 16, 8, 4, 2, 256, true>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;
   }
 }

@@ -651,6 +651,7 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
       return launch_fastblue_job(J, sm_count, stream);   // fastblue_kernels.cu
     case COLCONVW_512_F32: case COLCONVW_1024_F32: case COLCONVW_2048_F32: case COLCONVW_4096_F32:
     case COLCONVW_512_F64: case COLCONVW_1024_F64: case COLCONVW_2048_F64: case COLCONVW_4096_F64:
+    case COLW_1024_F32: case COLW_2048_F32: case COLW_1024_F64: case COLW_2048_F64:
       return launch_colconvw_job(J, sm_count, stream);   // colconvw_kernels.cu
     case COLCONV_32_F64: g_last_kernel = "colconv2_kernel<double,8,4,8>"; return launch_colconv2<double, 8, 4, 8>(J, s);
     case COLCONV_64_F64: g_last_kernel = "colconv2_kernel<double,8,8,8>"; return launch_colconv2<double, 8, 8, 8>(J, s);

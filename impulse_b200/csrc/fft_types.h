@@ -184,6 +184,10 @@ enum FastId : uint32_t {
   COLCONVW_1024_F64 = 96,
   COLCONVW_2048_F64 = 97,
   COLCONVW_4096_F64 = 98,
+  COLW_1024_F32 = 99,      // plain c2c along a strided axis, the axis resident in shared memory (colconvw_kernel, CW_FWD / CW_BWD)
+  COLW_2048_F32 = 100,
+  COLW_1024_F64 = 101,
+  COLW_2048_F64 = 102,
 };
 
 struct Phase {

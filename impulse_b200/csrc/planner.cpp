@@ -610,6 +610,24 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     *err = "no fused convolution kernel for this shape";
     return ERR_UNSUPPORTED;
   }
+  // plain c2c of a strided axis with the whole axis in shared memory: one launch instead of the two of the split
+  if (s.col_whole) {
+    uint32_t id = FAST_NONE, r2 = 0;
+    if (s.kind == KIND_C2C && !s.umul_mod && !s.tw4_n && !s.mul_tab && !s.zero_pad_from && !s.blue_stage && in_lf && out_lf &&
+        s.bs_in[0] == 1 && s.bs_out[0] == 1 && n_lines / J->bdim[0] * ((J->bdim[0] + 1) / 2) < (1ull << 31)) {
+      // measured against the two-launch split (profiles/r02_ab_colw.txt): complex128 1024 points +6...10 %; complex64
+      // 1024 points -3 %, 2048 points -10...-30 % (one resident CTA per SM: load, transform and store do not overlap)
+      // — those only under IMPULSE_FFT_COL_WHOLE=2
+      const bool all = env_int("IMPULSE_FFT_COL_WHOLE", 1) >= 2;
+      if (N == 1024 && (f64 || all)) { id = f64 ? COLW_1024_F64 : COLW_1024_F32; r2 = 8; }
+      else if (N == 2048 && all) { id = f64 ? COLW_2048_F64 : COLW_2048_F32; r2 = 16; }
+    }
+    if (id == FAST_NONE) { *err = "no whole-axis kernel for this shape"; return ERR_UNSUPPORTED; }
+    rc = fast3_tables(N, 16, r2, 8, s.dtype, &J->f3_tw1, &J->f3_tw2, err);
+    if (rc) return rc;
+    J->fast_id = id;
+    return ST_OK;
+  }
   // whole-axis convolution: FFT -> multiply -> inverse FFT of W adjacent strided lines with the full axis in shared
   // memory (one pass over the data instead of three): power-of-two axes of 512 ... 4096 points
   if (s.conv_whole) {
@@ -788,7 +806,8 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
                   std::vector<Dim> dims, int tw_key /*index into dims of the line-index dim, -1 = none*/, uint32_t tw4_n,
                   const void *mul_tab, uint32_t mul_stride, int blue_stage,
                   size_t esz_in, size_t esz_out, int src, int dst, int64_t src_base, int64_t dst_base,
-                  bool takes_fct, uint64_t umul_mod = 0, bool conv_mid = false, bool conv_whole = false) -> int {
+                  bool takes_fct, uint64_t umul_mod = 0, bool conv_mid = false, bool conv_whole = false,
+                  bool col_whole = false) -> int {
     std::vector<int> key(dims.size());
     for (size_t i = 0; i < dims.size(); ++i) key[i] = (int)i;
     std::vector<size_t> order(dims.size());
@@ -848,6 +867,7 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
     s.umul_mod = umul_mod;
     s.conv_mid = conv_mid;
     s.conv_whole = conv_whole;
+    s.col_whole = col_whole;
     s.blue_stage = blue_stage;
     s.r2r_type = d.r2r_type;
     s.ortho = d.ortho;
@@ -913,6 +933,17 @@ int PlanCache::build_nd(const NdDesc &d, NdPlan *plan, std::string *err) {
       if (!split && strided && (N & (N - 1)) == 0 && N >= 1024 && !env_int("IMPULSE_FFT_NO_FAST", 0) &&
           !env_int("IMPULSE_FFT_NO_COLFAST", 0))
         split = true;
+      // ... or, for 1024 / 2048 points over adjacent lines, ONE launch with the whole axis in shared memory
+      // (colconvw_kernel in its plain-transform mode; the device backend only, like the fused convolution)
+      if (split && strided && (N == 1024 || N == 2048) && !mul_tab && !umul_mod && allow_conv_fusion && !d.no_col_whole &&
+          env_int("IMPULSE_FFT_COL_WHOLE", 1) && !env_int("IMPULSE_FFT_NO_FAST", 0) && !env_int("IMPULSE_FFT_FORCE_FOURSTEP", 0)) {
+        const size_t n0 = plan->steps.size();
+        int rcw = emit(KIND_C2C, RL_HERMITIAN, forward, N, es_in, es_out, dims, -1, 0, nullptr, 1, 0, esz_in, esz_out, src, dst,
+                       src_base, dst_base, takes_fct, 0, false, false, true);
+        if (!rcw) return ST_OK;
+        plan->steps.resize(n0);
+        err->clear();
+      }
       if (!split && d.dtype == DT_F32 && (N == 16384 || (N == 8192 && strided)) && !env_int("IMPULSE_FFT_NO_FAST", 0) &&
           !env_int("IMPULSE_FFT_NO_COLFAST", 0))
         split = true;

@@ -87,6 +87,7 @@ struct LineSpec {
   bool ortho = false;
   uint64_t umul_mod = 0;  // caller-supplied multiplier fused into the store (pointer set at execute time)
   bool conv_mid = false;  // fused middle pass of an axis convolution (colconv2_kernel); needs tw4_n and umul_mod
+  bool col_whole = false;   // plain c2c of a strided power-of-two axis in one launch, the axis in shared memory (colconvw_kernel)
   bool conv_whole = false;  // whole-axis convolution in one launch (colconvw_kernel); needs umul_mod and adjacent lines
   int blue_stage = 0;  // multi-launch Bluestein: 1 = load+chirp+zero-pad to scratch, 2 = scratch+chirp+store
 };
@@ -121,6 +122,7 @@ struct NdDesc {
   bool ortho = false;
   bool real2hermitian = true;  // KIND_FFTPACK only
   uint64_t umul_mod = 0;  // c2c only: multiply the result by umul[offset % umul_mod]
+  bool no_col_whole = false;  // keep strided axes on the column kernels that read segmented input (impulse_fft_cols_from_parts)
 };
 
 struct NdPlan {

@@ -89,9 +89,10 @@ int run_colconv2(const LineJob &J) {
 
 // whole-axis convolution: persistent CTAs striding over the tiles (three CTAs here, so that the tile loop and the
 // merged "I1 of this tile + F1 of the next" step are exercised)
-template <typename T, int R1, int R2, int R3, int W, int LP, int TT>
+template <typename T, int R1, int R2, int R3, int W, int LP, int TT, bool PLAIN = false>
 int run_colconvw(const LineJob &J) {
-  if (!J.umul || !J.umul_mod || !J.f3_tw1 || !J.f3_tw2) return -2;
+  if (!J.f3_tw1 || !J.f3_tw2 || (!PLAIN && (!J.umul || !J.umul_mod))) return -2;
+  const bool bwd = PLAIN && (J.flags & F_CONJ_SEQ) != 0;
   const uint32_t gf = 2;   // the product's default is 1 (IMPULSE_FFT_CONVW_GF); 2 exercises the block decode as well
   LineJob Jg = J;
   Jg.n_load = gf;
@@ -100,9 +101,16 @@ int run_colconvw(const LineJob &J) {
   // the vector / scalar choice of launch_colconvw (colconvw_kernels.cu)
   constexpr uint64_t VB = LP * sizeof(cx<T>) >= 16 ? 16 : 8, VE = VB / sizeof(cx<T>) ? VB / sizeof(cx<T>) : 1;
   auto mult = [&](int64_t v) { return v % (int64_t)VE == 0; };
-  const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (uintptr_t)J.umul % VB == 0 && mult(J.es_in) &&
+  const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (PLAIN || (uintptr_t)J.umul % VB == 0) && mult(J.es_in) &&
                   mult(J.es_out) && mult(J.bs_in[1]) && mult(J.bs_in[2]) && mult(J.bs_out[1]) && mult(J.bs_out[2]) &&
-                  J.umul_mod % VE == 0;
+                  (PLAIN || J.umul_mod % VE == 0);
+  if constexpr (PLAIN) {
+    if (bwd && gv) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_BWD>(Jg); });
+    else if (bwd) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_BWD>(Jg); });
+    else if (gv) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_FWD>(Jg); });
+    else launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_FWD>(Jg); });
+    return 0;
+  }
   if (gv) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true>(Jg); });
   else launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>(Jg); });
   return 0;
@@ -136,6 +144,10 @@ int emu_run_col_job(const LineJob &J, unsigned pipe_groups) {
     case COLCONVW_1024_F64: return run_colconvw<double, 16, 8, 8, 8, 2, 256>(J);
     case COLCONVW_2048_F64: return run_colconvw<double, 16, 16, 8, 4, 2, 256>(J);
     case COLCONVW_4096_F64: return run_colconvw<double, 16, 16, 16, 2, 2, 256>(J);
+    case COLW_1024_F32: return run_colconvw<float, 16, 8, 8, 16, 2, 512, true>(J);
+    case COLW_2048_F32: return run_colconvw<float, 16, 16, 8, 8, 2, 512, true>(J);
+    case COLW_1024_F64: return run_colconvw<double, 16, 8, 8, 8, 2, 256, true>(J);
+    case COLW_2048_F64: return run_colconvw<double, 16, 16, 8, 4, 2, 256, true>(J);
     default: return 1;
   }
 }

@@ -121,3 +121,33 @@ def test_three_launch_convolution_padded_pitch(monkeypatch):
     assert emu.col_job_count() == 3
     assert rel(buf[:, :, :wc], want) < 5e-6
     assert np.array_equal(buf[:, :, wc:], keep[:, :, wc:])
+
+
+COLW_IDS = set(range(99, 103))       # COLW_* (fft_types.h)
+
+
+# plain c2c of a strided 1024 / 2048-point axis on the whole-axis kernel: one launch instead of the two of the split
+@pytest.mark.parametrize("dt,shape,axis", [(np.complex64, (1024, 21), 0), (np.complex64, (2, 2048, 9), 1), (np.complex128, (3, 1024, 10), 1),
+                                            (np.complex128, (2048, 5), 0), (np.complex64, (2, 3, 1024, 18), 2)])
+def test_strided_axis_whole(dt, shape, axis, monkeypatch):
+    monkeypatch.setenv("IMPULSE_FFT_COL_WHOLE", "2")    # every instance (the default is complex128 at 1024 points only)
+    rng = np.random.default_rng(sum(shape))
+    x = rnd(rng, shape, dt)
+    emu.set_fast_cols(2)
+    ids = emu.nd_fast_ids("c2c", x, x, shape, [axis], True)
+    assert len(ids) == 1 and ids[0] in COLW_IDS, ids
+    tol = 2e-15 * 12 if dt == np.complex128 else 2e-6
+    for fwd in (True, False):
+        got = emu.nd("c2c", x, np.full_like(x, np.nan), shape, [axis], fwd, 0.5)
+        want = (np.fft.fft(x.astype(np.complex128), axis=axis) if fwd else np.fft.ifft(x.astype(np.complex128), axis=axis) * shape[axis]) * 0.5
+        assert rel(got, want) < tol, (fwd, rel(got, want))
+    y = x.copy()
+    emu.nd("c2c", y, y, shape, [axis], True, 1.0)      # in place
+    assert rel(y, np.fft.fft(x.astype(np.complex128), axis=axis)) < tol
+    assert emu.col_job_count() == 3
+
+
+def test_fft2_of_1024_square_is_two_launches():
+    x = np.zeros((2, 1024, 1024), np.complex128)
+    emu.set_fast_cols(2)
+    assert len(emu.nd_fast_ids("c2c", x, x, x.shape, [1, 2], True)) == 2

@@ -7,7 +7,11 @@ import impulse_b200 as ib
 CASES = [("c2c", "f32", (1024, 256, 256), [1, 2]), ("c2c", "f64", (512, 256, 256), [1, 2]), ("r2c", "f32", (1024, 256, 256), [1, 2]),
          ("r2c", "f32", (256, 512, 512), [1, 2]), ("r2c", "f64", (128, 1024, 1024), [1, 2]), ("c2c", "f32", (64, 1024, 1024), [1, 2]),
          ("c2c", "f32", (64, 64, 64, 64), [1, 2, 3]), ("r2c", "f32", (32, 128, 128, 128), [1, 2, 3]), ("c2c", "f64", (4096, 4096), [0, 1]),
-         ("c2c", "f64", (1000, 1000), [0, 1]), ("r2c", "f64", (2000, 3000), [0, 1]), ("c2c", "f32", (16, 480, 640), [1, 2])]
+         ("c2c", "f64", (1000, 1000), [0, 1]), ("r2c", "f64", (2000, 3000), [0, 1]), ("c2c", "f32", (16, 480, 640), [1, 2]),
+         ("c2c", "f32", (32, 2048, 2048), [1, 2]), ("c2c", "f64", (16, 2048, 2048), [1, 2]), ("r2c", "f32", (64, 2048, 2048), [1, 2]),
+         ("c2c", "f64", (32, 1024, 1024), [1, 2])]
+if len(sys.argv) > 1:
+    CASES = [c for c in CASES if any(str(d) == sys.argv[1] for d in c[2])]
 for kind, dt, shape, axes in CASES:
     rdt = torch.float64 if dt == "f64" else torch.float32
     cdt = torch.complex128 if dt == "f64" else torch.complex64
