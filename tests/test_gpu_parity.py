@@ -755,6 +755,29 @@ def test_fftpack_and_hartley(ib, torch_mod, ref):
     assert float(torch_mod.linalg.vector_norm(h2 - img) / torch_mod.linalg.vector_norm(img)) <= 1e-13
 
 
+def test_strided_axis_whole_instances(ib, torch_mod, checker, monkeypatch):
+    """every instance of the whole-axis kernel in plain-transform mode (IMPULSE_FFT_COL_WHOLE=2; by default only
+    complex128 axes of 1024 points take it), forward and backward, vector and scalar global access, in place"""
+    monkeypatch.setenv("IMPULSE_FFT_COL_WHOLE", "2")
+    rng = np.random.default_rng(99)
+    used = set()
+    for shape, cdt in (((3, 1024, 22), np.complex64), ((2, 1024, 7), np.complex64), ((3, 2048, 12), np.complex64),
+                       ((5, 1024, 6), np.complex128), ((2, 2048, 9), np.complex128), ((1024, 35), np.complex128)):
+        axis = len(shape) - 2
+        x = rnd(rng, shape, cdt)
+        xd = torch_mod.from_numpy(x).cuda()
+        for fwd in (True, False):
+            yd = torch_mod.empty_like(xd)
+            ib.FFTDesc.init(axes=[axis], forward=fwd, scalingFactor=0.5).apply(ib.DataDesc.init(yd), ib.DataDesc.init(xd))
+            used.add(ib.last_kernel())
+            assert oracle.rel_l2(yd.cpu().numpy(), checker.c2c(x, [axis], fwd, 0.5)) <= 2 * tol(shape[axis], np.float64 if cdt == np.complex128 else np.float32), (shape, fwd)
+        zd = xd.clone()
+        ib.FFTDesc.init(axes=[axis], forward=True).apply(ib.DataDesc.init(zd), ib.DataDesc.init(zd))
+        assert oracle.rel_l2(zd.cpu().numpy(), checker.c2c(x, [axis], True, 1.0)) <= 2 * tol(shape[axis], np.float64 if cdt == np.complex128 else np.float32)
+    assert all(k.startswith("colconvw_kernel") for k in used), used
+    assert any("+bwd" in k for k in used) and any("+scalar" in k for k in used), used
+
+
 def test_convolve_axis_whole_long(ib, torch_mod, checker, monkeypatch):
     """the whole-axis kernel at 4096 points (32-byte runs: off by default, IMPULSE_FFT_CONV_WHOLE=2) and at 2048"""
     import ctypes as C
