@@ -155,14 +155,19 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
 #pragma unroll
     for (int k = 0; k < R1; ++k) at((uint32_t)(k * M1 + i1)) = x[k];
   };
-  // ask L2 for a tile: one request per 32-byte piece of every W-line run
+  // ask L2 for a tile (J.n_store: 0 = no, 1 = one prefetch.global.L2 per 32-byte piece of every W-line run, 2 = one bulk
+  // prefetch per run: the TMA unit's queue instead of the load / store unit's; needs 16-byte aligned runs = GV)
   auto prefetch_tile = [&](const Tile &q) {
 #if defined(__CUDA_ARCH__)
-    constexpr int PIECES = (W * (int)sizeof(cx<T>) + 31) / 32;
     const char *base = reinterpret_cast<const char *>(reinterpret_cast<const cx<T> *>(J.in) + q.in0);
     const int64_t step = J.es_in * (int64_t)sizeof(cx<T>);
-    for (int r = t; r < N * PIECES; r += TT)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)(r / PIECES) * step + (r % PIECES) * 32));
+    if (GV && J.n_store == 2) {
+      for (int r = t; r < N; r += TT) prefetch_l2_bulk(base + (int64_t)r * step, (uint32_t)(W * sizeof(cx<T>)));
+    } else if (J.n_store) {
+      constexpr int PIECES = (W * (int)sizeof(cx<T>) + 31) / 32;
+      for (int r = t; r < N * PIECES; r += TT)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)(r / PIECES) * step + (r % PIECES) * 32));
+    }
 #else
     (void)q;
 #endif

@@ -53,8 +53,10 @@ int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
   // (measured on config 5, 32-byte runs: GF = 1: 9.61 ms, 2: 9.45, 4: 12.5, 8: 11.5, 16: 10.9 — side-by-side requests for
   // the pieces of one line contend instead of merging; default 1)
   const uint32_t gf = gf_env > 0 ? (uint32_t)gf_env : 1u;
+  static const int pf_env = [] { const char *e = getenv("IMPULSE_FFT_CONVW_PF"); return e ? atoi(e) : 1; }();
   LineJob Jg = J;
   Jg.n_load = gf;
+  Jg.n_store = (uint32_t)pf_env;
   const uint64_t g0n = (J.bdim[0] + W - 1) / W;
   const uint64_t tiles = (g0n + gf - 1) / gf * gf * J.bdim[1] * J.bdim[2];
   if (tiles == 0) return 0;

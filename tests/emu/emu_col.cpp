@@ -96,6 +96,7 @@ int run_colconvw(const LineJob &J) {
   const uint32_t gf = 2;   // the product's default is 1 (IMPULSE_FFT_CONVW_GF); 2 exercises the block decode as well
   LineJob Jg = J;
   Jg.n_load = gf;
+  Jg.n_store = 1;
   const uint64_t tiles = ((J.bdim[0] + W - 1) / W + gf - 1) / gf * gf * J.bdim[1] * J.bdim[2];
   emu_dim3 grid; grid.x = (unsigned)std::min<uint64_t>(tiles, 3);
   // the vector / scalar choice of launch_colconvw (colconvw_kernels.cu)
