@@ -1,6 +1,7 @@
 """Small cases of every kernel family for compute-sanitizer (memcheck / racecheck) runs:
     compute-sanitizer --tool memcheck python tests/sanitizer_cases.py
 Not collected by pytest (no test_ prefix); exits non-zero on a parity failure."""
+import os
 import sys
 
 import numpy as np
@@ -68,7 +69,49 @@ def new_kernels_only():
     sys.exit(0 if ok else 1)
 
 
+def whole_axis_only():
+    """`--whole`: every instance of the whole-axis kernel (colconvw_kernel): convolution and plain transform, vector and
+    per-line global access, ragged groups, several tiles per CTA — the in-place exchange scheme under racecheck."""
+    import ctypes as C
+    from impulse_b200 import _lib
+    os.environ["IMPULSE_FFT_CONV_WHOLE"] = "2"
+    os.environ["IMPULSE_FFT_COL_WHOLE"] = "2"
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    ok = True
+    kernels = set()
+    for n in (512, 1024, 2048, 4096):
+        for cdt, tol in ((np.complex64, 2e-3), (np.complex128, 1e-9)):
+            for cols in (10, 37):     # even: vector access, ragged last group; odd: per-line access
+                shape = (320 if n <= 1024 else 40, n, cols)   # more tiles than CTAs at the small sizes
+                z = torch.from_numpy((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cdt)).cuda()
+                m = torch.from_numpy((rng.standard_normal(n * cols) + 1j * rng.standard_normal(n * cols)).astype(cdt)).cuda()
+                want = torch.fft.ifft(torch.fft.fft(z, dim=1) * m.view(n, cols), dim=1)
+                esz = z.element_size()
+                st = (C.c_ssize_t * 3)(n * cols * esz, cols * esz, esz)
+                _lib.check(L.impulse_fft_convolve_axis(_lib.F32 if cdt == np.complex64 else _lib.F64, 3, (C.c_size_t * 3)(*shape), st, st, 1,
+                                                       z.data_ptr(), z.data_ptr(), 1.0 / n, m.data_ptr(), n * cols, None))
+                kernels.add(ib.last_kernel())
+                ok &= bool(torch.allclose(z, want, rtol=tol, atol=tol * 10))
+    for n in (1024, 2048):
+        for cdt, tol in ((np.complex64, 2e-3), (np.complex128, 1e-9)):
+            for cols in (12, 21):
+                shape = (200 if n == 1024 else 30, n, cols)
+                z = torch.from_numpy((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cdt)).cuda()
+                for fwd in (True, False):
+                    got = run("c2c", z, torch.empty_like(z), [1], fwd, 1.0)
+                    kernels.add(ib.last_kernel())
+                    ref = torch.fft.fft(z, dim=1) if fwd else torch.fft.ifft(z, dim=1) * n
+                    ok &= bool(torch.allclose(got, ref, rtol=tol, atol=tol * n))
+    torch.cuda.synchronize()
+    ok &= all(k.startswith("colconvw_kernel") for k in kernels)
+    print("sanitizer cases (whole-axis kernel):", "ok" if ok else "PARITY FAILURE", sorted(kernels))
+    sys.exit(0 if ok else 1)
+
+
 def main():
+    if "--whole" in sys.argv:
+        whole_axis_only()
     if "--new" in sys.argv:
         new_kernels_only()
     rng = np.random.default_rng(0)
