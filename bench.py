@@ -597,9 +597,15 @@ def slab_entries(cx: Ctx, steps, warmup):
             want = chk.c2c(xfull, [0, 1], True, 1.0, nthreads=0)
         del xfull
     del xs
-    op = idist.SlabFFT2P2P(hi - lo, n, torch.complex128)
+    op = idist.SlabFFT2P2P(hi - lo, n, torch.complex128, pull_chunks=0)
+    # (2 chunks / 64 copy CTAs measured best on 2 GPUs, profiles/r02_ab_slab_pull_n2.txt — and still behind the fused peer loads)
+    op_pull = idist.SlabFFT2P2P(hi - lo, n, torch.complex128, pull_chunks=int(os.environ.get("IMPULSE_FFT_SLAB_PULL_BENCH", "2")),
+                                copy_ctas=int(os.environ.get("IMPULSE_FFT_SLAB_COPY_CTAS", "64")))
     variants = (("fft2_slab_p2p", lambda: op(x, True, 1.0), "row FFTs -> 1-element all-reduce as barrier -> column kernels load "
                  "the peers' row slabs over NVLink (CUDA IPC); no pack, no all-to-all buffer"),
+                ("fft2_slab_pull", lambda: op_pull(x, True, 1.0), f"row FFTs -> barrier -> {op_pull.pull_chunks} column chunks: a small gather "
+                 "kernel pulls chunk j+1 out of the peers' row slabs over NVLink (side stream) while the column transform of chunk j "
+                 "runs on local memory"),
                 ("fft2_slab_nccl", lambda: idist.fft2_slab(x, True, 1.0), "row FFTs -> pack -> NCCL all_to_all_single -> column FFTs"))
     for key, fn, how in variants:
         ms, launches, _ = time_steps(cx, fn, steps, warmup)
@@ -623,6 +629,7 @@ def slab_entries(cx: Ctx, steps, warmup):
         del parts, cols
         out[key] = ent
     op.close()
+    op_pull.close()
     return out
 
 

@@ -49,7 +49,7 @@ EXPORTS = [
     "impulse_fft_r2r_fftpack", "impulse_fft_r2r_separable_hartley", "impulse_fft_r2r_genuine_hartley", "impulse_fft_cfft_rows", "impulse_fft_rfft_rows",
     "impulse_fft_plan_get_info", "impulse_fft_launch_count", "impulse_fft_last_error", "impulse_fft_version",
     "impulse_fft_last_kernel",
-    "impulse_fft_cmul", "impulse_fft_transpose", "impulse_fft_copy2d", "impulse_fft_cols_from_parts", "impulse_fft_enable_peer_access", "impulse_fft_ipc_alloc", "impulse_fft_ipc_free",
+    "impulse_fft_cmul", "impulse_fft_transpose", "impulse_fft_copy2d", "impulse_fft_cols_from_parts", "impulse_fft_gather_parts", "impulse_fft_enable_peer_access", "impulse_fft_ipc_alloc", "impulse_fft_ipc_free",
     "impulse_fft_ipc_open", "impulse_fft_ipc_close", "impulse_fft_bind_host_to_device",
     "impulse_fft_dist_create", "impulse_fft_dist_execute", "impulse_fft_dist_execute_parts", "impulse_fft_dist_shard", "impulse_fft_dist_destroy",
     # include/pocketfft.h
@@ -122,6 +122,9 @@ def lib() -> C.CDLL:
     L.impulse_fft_cols_from_parts.restype = C.c_int
     L.impulse_fft_cols_from_parts.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp,
                                               C.c_size_t, C.c_int, C.c_double, vp]
+    L.impulse_fft_gather_parts.restype = C.c_int
+    L.impulse_fft_gather_parts.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp,
+                                           C.c_size_t, C.c_int, vp]
     L.impulse_fft_bind_host_to_device.restype = C.c_int
     L.impulse_fft_bind_host_to_device.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.impulse_fft_dist_create.restype = C.c_int

@@ -777,6 +777,27 @@ int impulse_fft_bind_host_to_device(int device, int *numa_node) {
   return 0;
 }
 
+int impulse_fft_gather_parts(int dtype, size_t nparts, const void *const *parts, size_t rows_per_part, size_t ld_part, size_t col0,
+                             size_t ncols, void *out, size_t ld_out, int ctas, void *stream) {
+  if (!parts || !out || nparts < 1 || nparts > 8 || !rows_per_part || !ncols)
+    return fail(IMPULSE_FFT_ERR_INVALID, "bad argument (1 <= nparts <= 8)");
+  if (ld_part < col0 + ncols || ld_out < ncols) return fail(IMPULSE_FFT_ERR_STRIDE, "leading dimension too small");
+  DeviceCtx *ctx = nullptr;
+  int rc = get_ctx(&ctx);
+  if (rc) return rc;
+  const size_t csz = dtype == DT_F64 ? 16 : 8, per16 = 16 / csz;   // elements per 16-byte unit
+  if (ld_part % per16 || col0 % per16 || ncols % per16 || ld_out % per16 || (uintptr_t)out % 16)
+    return fail(IMPULSE_FFT_ERR_STRIDE, "the gather moves 16-byte units: offsets and leading dimensions must be multiples of 16 bytes");
+  for (size_t q = 0; q < nparts; ++q)
+    if (!parts[q] || ((uintptr_t)parts[q] % 16)) return fail(IMPULSE_FFT_ERR_STRIDE, "part pointer null or misaligned");
+  if (rows_per_part > 0xffffffffull || ncols / per16 > 0xffffffffull) return fail(IMPULSE_FFT_ERR_INVALID, "slab too large");
+  int e = launch_gather_parts(parts, (uint32_t)nparts, (uint32_t)rows_per_part, ld_part / per16, col0 / per16,
+                              (uint32_t)(ncols / per16), out, ld_out / per16, ctas, stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e) return cuda_fail((cudaError_t)e, "kernel launch");
+  return 0;
+}
+
 int impulse_fft_cols_from_parts(int dtype, size_t nparts, const void *const *parts, size_t rows_per_part, size_t ld_part,
                                 size_t col0, size_t ncols, void *out, size_t ld_out, int forward, double fct, void *stream) {
   if (!parts || !out || nparts < 1 || nparts > 8 || !rows_per_part || !ncols)

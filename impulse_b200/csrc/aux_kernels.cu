@@ -76,6 +76,49 @@ int launch_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols
   return (int)cudaGetLastError();
 }
 
+// Gather of the column block [col0, col0 + ncols) out of `nparts` row slabs (the peers' row-FFT outputs, mapped through
+// CUDA IPC) into one local [nparts * rpp, ncols] array: the exchange of the slab 2-D transform as a COPY with deep
+// memory-level parallelism (U independent 16-byte loads in flight per thread: NVLink latency is 2-4 k cycles) on a
+// deliberately small grid, so that the column transform of the previous chunk keeps the other SMs.
+struct GatherParts { const void *part[8]; };
+// one warp per row (U rows in flight): lanes walk the row's 16-byte units, so every load instruction is one coalesced
+// 512-byte run and the index arithmetic is one 32-bit division per ROW
+template <int U>
+__global__ void __launch_bounds__(512) gather_parts_kernel(GatherParts P, uint4 *__restrict__ out, uint32_t nparts, uint32_t rpp,
+                                                           uint64_t ld_part16, uint64_t col0_16, uint32_t ncols16, uint64_t ld_out16) {
+  const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t rows = nparts * rpp;
+  for (uint32_t r0 = warp; r0 < rows; r0 += nwarps * U) {
+    const uint4 *src[U];
+    uint4 *dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t r = r0 + nwarps * u, rc = r < rows ? r : r0, q = rc / rpp;
+      src[u] = reinterpret_cast<const uint4 *>(P.part[q]) + (uint64_t)(rc - q * rpp) * ld_part16 + col0_16;
+      dst[u] = out + (uint64_t)rc * ld_out16;
+    }
+    for (uint32_t c = lane; c < ncols16; c += 32) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = src[u][c];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r0 + nwarps * u < rows) dst[u][c] = v[u];
+    }
+  }
+}
+
+// all quantities in 16-byte units (the ABI checks divisibility); ctas = grid size (0: 32)
+int launch_gather_parts(const void *const *parts, uint32_t nparts, uint32_t rpp, uint64_t ld_part16, uint64_t col0_16,
+                        uint32_t ncols16, void *out, uint64_t ld_out16, int ctas, void *stream) {
+  if (!nparts || !rpp || !ncols16) return 0;
+  GatherParts P;
+  for (uint32_t q = 0; q < 8; ++q) P.part[q] = q < nparts ? parts[q] : nullptr;
+  gather_parts_kernel<8><<<(unsigned)(ctas > 0 ? ctas : 32), 512, 0, static_cast<cudaStream_t>(stream)>>>(
+      P, static_cast<uint4 *>(out), nparts, rpp, ld_part16, col0_16, ncols16, ld_out16);
+  return (int)cudaGetLastError();
+}
+
 int launch_cmul(int dtype, const void *a, const void *f, void *out, size_t n_inner, size_t n_batch, double scale,
                 int sm_count, void *stream) {
   const size_t total = n_inner * n_batch;

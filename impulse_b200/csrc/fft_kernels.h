@@ -22,6 +22,8 @@ int launch_cmul(int dtype, const void *a, const void *f, void *out, size_t n_inn
 int launch_transpose(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
                      size_t batch, int sm_count, void *stream);
 // out[b][r][c] = in[b][r][c] for complex matrices with independent leading dimensions / batch strides
+int launch_gather_parts(const void *const *parts, uint32_t nparts, uint32_t rpp, uint64_t ld_part16, uint64_t col0_16,
+                        uint32_t ncols16, void *out, uint64_t ld_out16, int ctas, void *stream);
 int launch_copy2d(int dtype, const void *in, void *out, size_t rows, size_t cols, size_t ld_in, size_t ld_out,
                   size_t batch, size_t bs_in, size_t bs_out, int sm_count, void *stream);
 // both launches of a split column transform as one persistent kernel (colfuse_kernels.cu).  The two jobs carry

@@ -17,6 +17,7 @@ calls the C ABI.  Nothing here falls back to a CPU transform.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 from . import _lib
 
@@ -119,9 +120,15 @@ class SlabFFT2P2P:
     memory has to be mapped into THIS device's address space for kernels to load from it, which the IPC
     tensors of torch.multiprocessing (opened on the owner's device) do not give.  ``torch.distributed``
     carries the 64-byte handles and the barrier.
+
+    ``pull_chunks = J > 0`` selects the PIPELINED exchange instead: the rank's column block is cut into J chunks; a
+    small copy kernel with deep memory-level parallelism (``impulse_fft_gather_parts``, side stream) gathers chunk j+1
+    out of all row slabs into a local staging array while the column transform of chunk j runs on local memory
+    (main stream) — NVLink and the FFT arithmetic overlap chunk by chunk instead of the FFT kernel waiting on every
+    remote load.  ``IMPULSE_FFT_SLAB_PULL`` sets the default (0 = fused peer loads).
     """
 
-    def __init__(self, rows_local: int, cols: int, dtype, group=None):
+    def __init__(self, rows_local: int, cols: int, dtype, group=None, pull_chunks: int | None = None, copy_ctas: int = 0):
         import torch
         import torch.distributed as dist
         self.group = group
@@ -156,6 +163,21 @@ class SlabFFT2P2P:
                 self.peer_base.append(p.value)
         self.flag = torch.zeros(1, device=dev)
         self.step = 0
+        if pull_chunks is None:
+            pull_chunks = int(os.environ.get("IMPULSE_FFT_SLAB_PULL", "0"))
+        per16 = 16 // self.esz
+        while pull_chunks > 1 and (self.cb % pull_chunks or (self.cb // pull_chunks) % max(per16, 16)):
+            pull_chunks -= 1
+        if pull_chunks > 0 and (self.cb % per16 or self.c % per16):
+            pull_chunks = 0
+        self.pull_chunks = max(0, int(pull_chunks))
+        self.copy_ctas = int(copy_ctas) or int(os.environ.get("IMPULSE_FFT_SLAB_COPY_CTAS", "0"))
+        if self.pull_chunks:
+            self.stage = torch.empty((self.world * self.rl, self.cb), dtype=dtype, device=dev)   # the gathered column block
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            self.ev_rows = torch.cuda.Event()
+            self.ev_chunk = [torch.cuda.Event() for _ in range(self.pull_chunks)]
+            self.ev_done = torch.cuda.Event()
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
@@ -194,8 +216,30 @@ class SlabFFT2P2P:
         if out is None:
             out = torch.empty((self.world * self.rl, self.cb), dtype=self.dtype, device=x_local.device)
         parts = (C.c_void_p * self.world)(*[self.peer_base[q] + k * self.buf_bytes for q in range(self.world)])
-        _lib.check(L.impulse_fft_cols_from_parts(self.code, self.world, parts, self.rl, self.c, self.rank * self.cb, self.cb,
-                                                 out.data_ptr(), self.cb, int(forward), 1.0, stream))
+        if not self.pull_chunks:
+            _lib.check(L.impulse_fft_cols_from_parts(self.code, self.world, parts, self.rl, self.c, self.rank * self.cb, self.cb,
+                                                     out.data_ptr(), self.cb, int(forward), 1.0, stream))
+            return out
+        # pipelined exchange: gather chunk j (copy stream) || column transform of chunk j-1 on local memory (main stream)
+        main = torch.cuda.current_stream(x_local.device)
+        self.ev_rows.record(main)                       # rows written everywhere (the all-reduce above has completed here)
+        self.copy_stream.wait_event(self.ev_rows)
+        self.copy_stream.wait_event(self.ev_done)       # the previous call's column transforms have read the staging array
+        cstream = C.c_void_p(self.copy_stream.cuda_stream)
+        J, cw, R = self.pull_chunks, self.cb // self.pull_chunks, self.world * self.rl
+        cshape = (C.c_size_t * 2)(R, cw)
+        cst = (C.c_ssize_t * 2)(self.cb * self.esz, self.esz)
+        caxes = (C.c_size_t * 1)(0)
+        for j in range(J):
+            _lib.check(L.impulse_fft_gather_parts(self.code, self.world, parts, self.rl, self.c, self.rank * self.cb + j * cw, cw,
+                                                  self.stage.data_ptr() + j * cw * self.esz, self.cb, self.copy_ctas, cstream))
+            self.ev_chunk[j].record(self.copy_stream)
+        for j in range(J):
+            main.wait_event(self.ev_chunk[j])
+            off = j * cw * self.esz
+            _lib.check(L.impulse_fft_c2c(self.code, 2, cshape, cst, cst, 1, caxes, int(forward), self.stage.data_ptr() + off,
+                                         out.data_ptr() + off, 1.0, 0, stream))
+        self.ev_done.record(main)
         return out
 
 

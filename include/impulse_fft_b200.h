@@ -176,6 +176,15 @@ int impulse_fft_copy2d(int dtype, const void *in, void *out, size_t rows, size_t
 int impulse_fft_cols_from_parts(int dtype, size_t nparts, const void *const *parts, size_t rows_per_part, size_t ld_part,
                                 size_t col0, size_t ncols, void *out, size_t ld_out, int forward, double fct, void *stream);
 
+/* The exchange of the slab 2-D transform as a copy: the column block [col0, col0 + ncols) of `nparts` row slabs
+ * (rows_per_part rows each, leading dimension ld_part; the peers' slabs mapped through CUDA IPC) is gathered into the
+ * local array out[nparts * rows_per_part][ld_out].  A small grid (`ctas`, 0 = 32) with many loads in flight per thread
+ * keeps NVLink busy and leaves the other SMs to the column transform of the previous column chunk, which is how
+ * SlabFFT2P2P(pull_chunks = J) overlaps exchange and arithmetic.  Offsets and leading dimensions in elements, multiples
+ * of 16 bytes.  Reference analogue: the per-axis line gather of general_nd, pocketfft_hdronly.h:2955-3004. */
+int impulse_fft_gather_parts(int dtype, size_t nparts, const void *const *parts, size_t rows_per_part, size_t ld_part,
+                             size_t col0, size_t ncols, void *out, size_t ld_out, int ctas, void *stream);
+
 /* Device buffers that other PROCESSES of the same box can map (CUDA IPC), for the row slabs of the
  * multi-GPU 2-D transform.  alloc: cudaMalloc + cudaIpcGetMemHandle (handle = 64 opaque bytes to send to the
  * peers).  open: maps a peer's buffer into the CURRENT device's address space with peer access enabled

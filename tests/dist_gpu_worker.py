@@ -38,15 +38,16 @@ def main():
         full = rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)
         lo, hi = idist.shard_rows(shape[0], rank, world)
         local_x = torch.from_numpy(full[lo:hi].copy()).cuda()
-        op = idist.SlabFFT2P2P(hi - lo, shape[1], torch.complex128)
         want = chk.c2c(full, [0, 1], True, 1.0, nthreads=0)
         cb = shape[1] // world
-        for rep in range(3):   # alternating buffers
-            res = op(local_x).cpu().numpy()
-            err = oracle.rel_l2(res, want[:, rank * cb:(rank + 1) * cb])
-            print(f"rank {rank} SlabFFT2P2P {shape} rep {rep} rel_l2={err:.3e}", flush=True)
-            ok = ok and err <= 1e-12 * np.log2(max(shape))
-        op.close()
+        for pull in (0, 1, 4):   # fused peer loads; pipelined exchange (gather kernel + local column transforms), 1 and 4 chunks
+            op = idist.SlabFFT2P2P(hi - lo, shape[1], torch.complex128, pull_chunks=pull)
+            for rep in range(3):   # alternating buffers
+                res = op(local_x).cpu().numpy()
+                err = oracle.rel_l2(res, want[:, rank * cb:(rank + 1) * cb])
+                print(f"rank {rank} SlabFFT2P2P {shape} pull={op.pull_chunks} rep {rep} rel_l2={err:.3e}", flush=True)
+                ok = ok and err <= 1e-12 * np.log2(max(shape))
+            op.close()
     rows = idist.fft_rows_sharded(local_x, True, 1.0).cpu().numpy()
     err = oracle.max_row_rel_l2(rows, chk.c2c(full[lo:hi], [1], True, 1.0))
     ok = ok and err <= 1e-12 * 11
