@@ -24,6 +24,36 @@ __global__ void __launch_bounds__(TT) tile_copy(float4 *a, int B, int H, long pi
     if (dummy) sm[t] = base[0];
   }
 }
+// the same bytes as RUN = 64, but as two instructions of 32-byte runs (adjacent sectors requested back to back by one warp)
+template <int TT>
+__global__ void __launch_bounds__(TT) tile_copy_split(float4 *a, int B, int H, long pitch16, int groups) {
+  constexpr int V = 2, RPI = TT / V;
+  const int t = threadIdx.x, v = t % V, r0 = t / V;
+  const long ntiles = (long)groups * B;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int img = (int)(tile % B), g = (int)(tile / B);
+    float4 *base = a + ((long)img * H) * pitch16 + (long)g * 4 + v;
+    for (int r = r0; r < H; r += RPI * 8) {
+      float4 x[8], y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int rr = r + RPI * j; if (rr < H) { x[j] = base[(long)rr * pitch16]; y[j] = base[(long)rr * pitch16 + 2]; } }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int rr = r + RPI * j; if (rr < H) { x[j].x += 1.f; base[(long)rr * pitch16] = x[j]; base[(long)rr * pitch16 + 2] = y[j]; } }
+    }
+  }
+}
+void run_split(float4 *a, int B, int H, long pitch16, int sms) {
+  constexpr int TT = 512;
+  const int groups = (int)(pitch16 * 16 / 64);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int it = 0; it < 2; ++it) tile_copy_split<TT><<<sms, TT>>>(a, B, H, pitch16, groups);
+  cudaEventRecord(e0);
+  for (int it = 0; it < 5; ++it) tile_copy_split<TT><<<sms, TT>>>(a, B, H, pitch16, groups);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+  const double bytes = 2.0 * B * H * (double)groups * 64;
+  printf("run=2x32 B (two instructions, adjacent)  %.3f ms  %.0f GB/s  (%s)\n", ms, bytes / ms * 1e-6, cudaGetErrorString(cudaGetLastError()));
+}
 template <int RUN> void run(float4 *a, int B, int H, long pitch16, int smem_kb, int sms) {
   constexpr int TT = 512;
   const int groups = (int)(pitch16 * 16 / RUN);
@@ -45,7 +75,8 @@ int main() {
   float4 *a; cudaMalloc(&a, (size_t)B * H * P * 8); cudaMemset(a, 0, (size_t)B * H * P * 8);
   cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
   const int sms = pr.multiProcessorCount;
-  for (int kb : {200, 100, 48}) {
+  run_split(a, B, H, pitch16, sms);
+  for (int kb : {100}) {
     run<32>(a, B, H, pitch16, kb, sms); run<64>(a, B, H, pitch16, kb, sms); run<128>(a, B, H, pitch16, kb, sms);
     run<256>(a, B, H, pitch16, kb, sms); run<512>(a, B, H, pitch16, kb, sms);
   }
