@@ -54,11 +54,60 @@ struct CudaAlloc : TableAlloc {
 
 // Staging resources for host-pointer calls, kept across calls: cudaMalloc/cudaFree and stream
 // creation cost milliseconds, comparable to the PCIe time of a whole step.
+constexpr int kStageRing = 3;
 struct StagePool {
   std::mutex mu;
   cudaStream_t s[2] = {nullptr, nullptr};
   unsigned char *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
   size_t cap_in = 0, cap_out = 0;
+  // ring pipeline: one stream per engine (H2D copies, kernels, D2H copies), kStageRing buffers per side, events per slot
+  cudaStream_t rs[3] = {nullptr, nullptr, nullptr};
+  unsigned char *rin[kStageRing] = {}, *rout[kStageRing] = {};
+  cudaEvent_t ev_in[kStageRing] = {}, ev_k[kStageRing] = {}, ev_out[kStageRing] = {};
+  size_t rcap_in = 0, rcap_out = 0;
+  // whole-span staging (multi-launch plans): buffers kept between calls
+  unsigned char *win = nullptr, *wout = nullptr;
+  size_t wcap_in = 0, wcap_out = 0;
+  cudaError_t ensure_ring(size_t need_in, size_t need_out) {
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+      if (!rs[i]) e = cudaStreamCreateWithFlags(&rs[i], cudaStreamNonBlocking);
+    for (int i = 0; i < kStageRing && e == cudaSuccess; ++i) {
+      if (!ev_in[i]) e = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
+      if (e == cudaSuccess && !ev_k[i]) e = cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming);
+      if (e == cudaSuccess && !ev_out[i]) e = cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess && need_in > rcap_in) {
+      for (int i = 0; i < kStageRing; ++i) { if (rin[i]) cudaFree(rin[i]); rin[i] = nullptr; }
+      rcap_in = 0;
+      for (int i = 0; i < kStageRing && e == cudaSuccess; ++i) e = cudaMalloc(&rin[i], need_in);
+      if (e == cudaSuccess) rcap_in = need_in;
+    }
+    if (e == cudaSuccess && need_out > rcap_out) {
+      for (int i = 0; i < kStageRing; ++i) { if (rout[i]) cudaFree(rout[i]); rout[i] = nullptr; }
+      rcap_out = 0;
+      for (int i = 0; i < kStageRing && e == cudaSuccess; ++i) e = cudaMalloc(&rout[i], need_out);
+      if (e == cudaSuccess) rcap_out = need_out;
+    }
+    return e;
+  }
+  cudaError_t ensure_whole(size_t need_in, size_t need_out) {
+    cudaError_t e = cudaSuccess;
+    if (!rs[0]) e = ensure_ring(0, 0);
+    if (e == cudaSuccess && need_in > wcap_in) {
+      if (win) cudaFree(win);
+      win = nullptr; wcap_in = 0;
+      e = cudaMalloc(&win, need_in);
+      if (e == cudaSuccess) wcap_in = need_in;
+    }
+    if (e == cudaSuccess && need_out > wcap_out) {
+      if (wout) cudaFree(wout);
+      wout = nullptr; wcap_out = 0;
+      e = cudaMalloc(&wout, need_out);
+      if (e == cudaSuccess) wcap_out = need_out;
+    }
+    return e;
+  }
   cudaError_t ensure(size_t need_in, size_t need_out) {
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i)
@@ -351,6 +400,58 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
         StagePool &sg = p->ctx->stage;
         std::lock_guard<std::mutex> stage_lock(sg.mu);
         const size_t cin = (size_t)((per - 1) * sin_b + in_slab), cout = (size_t)((per - 1) * sout_b + out_slab);
+        // IMPULSE_FFT_STAGE_RING (default 1): one stream per engine — H2D copies, kernels, D2H copies — over a ring of
+        // kStageRing buffer pairs with an event per slot, so that neither copy engine ever waits for the OTHER direction
+        // of its own chunk (the two-stream form serialises H2D(c+2) behind D2H(c)); 0 = the two-stream form below
+        static const bool ring = [] { const char *e = std::getenv("IMPULSE_FFT_STAGE_RING"); return !e || std::atoi(e) != 0; }();
+        if (ring) {
+          cudaError_t e = sg.ensure_ring(cin, inplace ? 0 : cout);
+          int rc = 0;
+          if (e != cudaSuccess) rc = cuda_fail(e, "staging allocation");
+          uint64_t lo = 0;
+          for (size_t c = 0; c < sizes.size() && !rc; ++c) {
+            const int b = (int)(c % kStageRing);
+            const bool reuse = c >= (size_t)kStageRing;
+            const uint64_t cnt = sizes[c];
+            const size_t bin = (size_t)((cnt - 1) * sin_b + in_slab), bout = (size_t)((cnt - 1) * sout_b + out_slab);
+            const unsigned char *hin = (const unsigned char *)in + lo * sin_b;
+            unsigned char *hout = (unsigned char *)out + lo * sout_b;
+            lo += cnt;
+            unsigned char *din = sg.rin[b], *dout = inplace ? sg.rin[b] : sg.rout[b];
+            // H2D: the input slot is free once the kernel of chunk c - ring has read it (in place: once its D2H is done)
+            if (reuse) e = cudaStreamWaitEvent(sg.rs[0], inplace ? sg.ev_out[b] : sg.ev_k[b], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(din, hin, bin, cudaMemcpyHostToDevice, sg.rs[0]);
+            if (e == cudaSuccess && !nd.out_dense && !inplace) {   // strided output with gaps: preload so the gaps survive
+              if (reuse) e = cudaStreamWaitEvent(sg.rs[0], sg.ev_out[b], 0);
+              if (e == cudaSuccess) e = cudaMemcpyAsync(dout, hout, bout, cudaMemcpyHostToDevice, sg.rs[0]);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(sg.ev_in[b], sg.rs[0]);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
+            // kernel: input landed, output slot drained
+            e = cudaStreamWaitEvent(sg.rs[1], sg.ev_in[b], 0);
+            if (e == cudaSuccess && reuse) e = cudaStreamWaitEvent(sg.rs[1], sg.ev_out[b], 0);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "stream wait"); break; }
+            LineJob J = J0;
+            J.bdim[od] = cnt;
+            J.n_lines = inner_lines * cnt;
+            J.in = din;
+            J.out = dout;
+            J.fct = st.takes_fct ? fct : 1.0;
+            const uint64_t C = 1ull << J.log_c;
+            int le = launch_line_job(J, st.cfg.threads, st.cfg.smem_bytes, (J.n_lines + C - 1) / C, sg.rs[1]);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (le) { rc = cuda_fail((cudaError_t)le, "kernel launch"); break; }
+            e = cudaEventRecord(sg.ev_k[b], sg.rs[1]);
+            // D2H
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(sg.rs[2], sg.ev_k[b], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(hout, dout, inplace ? bin : bout, cudaMemcpyDeviceToHost, sg.rs[2]);
+            if (e == cudaSuccess) e = cudaEventRecord(sg.ev_out[b], sg.rs[2]);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy"); break; }
+          }
+          for (int i = 0; i < 3; ++i)
+            if (sg.rs[i]) { cudaError_t se = cudaStreamSynchronize(sg.rs[i]); if (se != cudaSuccess && !rc) rc = cuda_fail(se, "staging sync"); }
+          return rc;
+        }
         cudaError_t e = sg.ensure(cin, inplace ? 0 : cout);
         unsigned char **dbuf_in = sg.in, **dbuf_out = sg.out;
         int rc = 0;
@@ -387,31 +488,32 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
       }
     }
   }
-  // ---- whole-span staging
+  // ---- whole-span staging (multi-launch plans: every launch needs the whole array).  The device copies are kept
+  // between calls (two cudaMalloc / cudaFree of the array size per call cost milliseconds and synchronise the device)
+  // and copies and launches run on one stream of the pool.
   const size_t bin = (size_t)(nd.in_hi - nd.in_lo), bout = (size_t)(nd.out_hi - nd.out_lo);
-  unsigned char *din = nullptr, *dout = nullptr;
-  cudaError_t e = cudaMalloc(&din, bin);
+  StagePool &sg = p->ctx->stage;
+  std::lock_guard<std::mutex> stage_lock(sg.mu);
+  cudaError_t e = sg.ensure_whole(bin, inplace ? 0 : bout);
   if (e != cudaSuccess) return cuda_fail(e, "staging allocation");
-  if (!inplace) {
-    e = cudaMalloc(&dout, bout);
-    if (e != cudaSuccess) { cudaFree(din); return cuda_fail(e, "staging allocation"); }
-  }
+  unsigned char *din = sg.win, *dout = inplace ? nullptr : sg.wout;
+  cudaStream_t ws = sg.rs[1];
   int rc = 0;
-  e = cudaMemcpy(din, (const unsigned char *)in + nd.in_lo, bin, cudaMemcpyHostToDevice);
+  e = cudaMemcpyAsync(din, (const unsigned char *)in + nd.in_lo, bin, cudaMemcpyHostToDevice, ws);
   if (e == cudaSuccess && !inplace && !nd.out_dense)  // preserve what lies between strided output elements
-    e = cudaMemcpy(dout, (const unsigned char *)out + nd.out_lo, bout, cudaMemcpyHostToDevice);
+    e = cudaMemcpyAsync(dout, (const unsigned char *)out + nd.out_lo, bout, cudaMemcpyHostToDevice, ws);
   if (e != cudaSuccess) rc = cuda_fail(e, "H2D copy");
   if (!rc) {
     unsigned char *o = inplace ? din : dout;
     const ptrdiff_t olo = inplace ? nd.in_lo : nd.out_lo;
-    rc = run_device(p, din - nd.in_lo, o - olo, fct, nullptr);
+    rc = run_device(p, din - nd.in_lo, o - olo, fct, ws);
     if (!rc) {
-      e = cudaMemcpy((unsigned char *)out + olo, o, inplace ? bin : bout, cudaMemcpyDeviceToHost);
+      e = cudaMemcpyAsync((unsigned char *)out + olo, o, inplace ? bin : bout, cudaMemcpyDeviceToHost, ws);
       if (e != cudaSuccess) rc = cuda_fail(e, "D2H copy");
     }
   }
-  cudaFree(din);
-  if (dout) cudaFree(dout);
+  e = cudaStreamSynchronize(ws);
+  if (e != cudaSuccess && !rc) rc = cuda_fail(e, "staging sync");
   return rc;
 }
 
