@@ -29,12 +29,51 @@ namespace impulse {
 
 template <typename T, int LP> struct alignas((LP * sizeof(cx<T>)) >= 16 ? 16 : 8) CwVec { cx<T> v[LP]; };
 
+// Tensor memory (256 KB per SM, 128 lanes x 512 columns x 32 bit) as LANE-PRIVATE staging storage: warp w owns lanes
+// 32*(w%4)..+31, a thread reads back exactly the columns of its own lane that it stored (tcgen05.st / tcgen05.ld,
+// .32x32b: one 32-bit column per register).  No MMA is involved; it is the only on-chip space left beside a tile that
+// fills the shared memory.  (tools/micro/tmem_stage.cu: 64 words out and back in 460 cycles with 512 threads.)
+// The host emulation (tests/emu) gives every thread a private array.
+#if !defined(__CUDA_ARCH__)
+static thread_local uint32_t cw_emu_tmem[512];
+#endif
+__device__ __forceinline__ void cw_tmem_st8(uint32_t taddr, const uint32_t *v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+#else
+  for (int k = 0; k < 8; ++k) cw_emu_tmem[(taddr & 0xffffu) + k] = v[k];
+#endif
+}
+__device__ __forceinline__ void cw_tmem_ld8(uint32_t taddr, uint32_t *v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+#else
+  for (int k = 0; k < 8; ++k) v[k] = cw_emu_tmem[(taddr & 0xffffu) + k];
+#endif
+}
+__device__ __forceinline__ void cw_tmem_wait_st() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cw_tmem_wait_ld() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#endif
+}
+
 // MODE: CW_CONV = the convolution above; CW_FWD / CW_BWD = the plain transform of the axis (passes F1, F2, F3 and a store
 // straight from the last butterfly's registers; backward = conj(FFT(conj x))): ONE pass over the data for strided
 // power-of-two axes that the four-step split serves in two.
 enum { CW_CONV = 0, CW_FWD = 1, CW_BWD = 2 };
 // GV: the LP lines of a thread are read / written as one vector in global memory (the launcher checks alignment)
-template <typename T, int R1, int R2, int R3, int W, int LP, int TT, bool GV, int MODE = CW_CONV>
+// TM: the CTA's NEXT tile is loaded from HBM while the current one is transformed — half of a thread's points during
+// pass F2, half during I2 (F3 in the plain modes) — and parked in TENSOR MEMORY until pass F1 picks it up: the single
+// resident CTA no longer waits for its loads at every tile boundary (the tile itself fills the shared memory).
+template <typename T, int R1, int R2, int R3, int W, int LP, int TT, bool GV, int MODE = CW_CONV, bool TM = false>
 __global__ void __launch_bounds__(TT, 1)
 colconvw_kernel(const __grid_constant__ LineJob J) {
   constexpr int N = R1 * R2 * R3, M1 = R2 * R3, PW = W / LP, TB = TT / PW;
@@ -48,6 +87,30 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
   cx<T> *s_tw1 = S + (size_t)N * W;   // [R1][M1]: W_N^(i1 k1)
   cx<T> *s_tw2 = s_tw1 + N;           // [R2][R3]: W_M1^(i2 k2)
   const int t = threadIdx.x, lp = t % PW, tb = t / PW;
+  // tensor-memory staging: WV words per Vec, R1 * WV words per thread, (TT / 128) warps per lane quarter side by side
+  constexpr int WV = (int)(sizeof(Vec) / 4), TM_COLS = R1 * WV * (TT / 128), H1 = R1 / 2;
+  static_assert(!TM || (NB1 == 1 && TT % 128 == 0 && WV % 4 == 0 && (H1 * WV) % 8 == 0 && TM_COLS <= 512 && TM_COLS >= 32 &&
+                        (TM_COLS & (TM_COLS - 1)) == 0), "tensor-memory staging shape");
+  uint32_t tm_addr = 0, tm_base = 0;
+  (void)tm_base;
+  if constexpr (TM) {
+    uint32_t *slot = reinterpret_cast<uint32_t *>(s_tw2 + R2 * R3);
+#if defined(__CUDA_ARCH__)
+    if (t < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(slot)),
+                   "n"(TM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    tm_base = *slot;
+    tm_addr = tm_base + ((uint32_t)(((t >> 5) & 3) * 32) << 16) + (uint32_t)(t >> 7) * (R1 * WV);
+#else
+    (void)slot;
+#endif
+  }
+
   const cx<T> *um = reinterpret_cast<const cx<T> *>(J.umul);
   for (int idx = t; idx < N; idx += TT) s_tw1[idx] = reinterpret_cast<const cx<T> *>(J.f3_tw1)[idx];
   for (int idx = t; idx < R2 * R3; idx += TT) s_tw2[idx] = reinterpret_cast<const cx<T> *>(J.f3_tw2)[idx];
@@ -142,9 +205,44 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
       for (int j = 0; j < R3; ++j) x[j].v[l] = y[j];
     }
   };
-  auto f1 = [&](const Tile &q, const int i1) {
+  // rows [j0, j0 + H1) of the thread's butterfly of tile q: HBM -> registers, and registers -> tensor memory
+  auto tm_fetch = [&](const Tile &q, const int j0, Vec (&pre)[H1]) {
+    const cx<T> *p = reinterpret_cast<const cx<T> *>(J.in) + q.in0 + lp * LP + (int64_t)(tb + M1 * j0) * J.es_in;
+    const int64_t step = (int64_t)M1 * J.es_in;
+    if (GV && q.nv == LP) {
+#pragma unroll
+      for (int j = 0; j < H1; ++j) { pre[j] = *reinterpret_cast<const Vec *>(p); p += step; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < H1; ++j) {
+#pragma unroll
+        for (int l = 0; l < LP; ++l) pre[j].v[l] = l < q.nv ? p[l] : mk<T>((T)0, (T)0);
+        p += step;
+      }
+    }
+  };
+  auto tm_park = [&](const int j0, const Vec (&pre)[H1]) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&pre[0]);
+#pragma unroll
+    for (int c = 0; c < H1 * WV; c += 8) cw_tmem_st8(tm_addr + (uint32_t)(j0 * WV + c), w + c);
+  };
+  auto f1 = [&](const Tile &q, const int i1, const bool parked = false) {
     Vec x[R1];
-    gget(reinterpret_cast<const cx<T> *>(J.in) + q.in0 + lp * LP + (int64_t)i1 * J.es_in, q.nv, (int64_t)M1 * J.es_in, x);
+    if (TM && parked) {   // the tile was loaded ahead and waits in tensor memory
+      cw_tmem_wait_st();
+      uint32_t *w = reinterpret_cast<uint32_t *>(&x[0]);
+#pragma unroll
+      for (int c = 0; c < R1 * WV; c += 8) cw_tmem_ld8(tm_addr + (uint32_t)c, w + c);
+      cw_tmem_wait_ld();
+      if (MODE == CW_BWD) {
+#pragma unroll
+        for (int j = 0; j < R1; ++j)
+#pragma unroll
+          for (int l = 0; l < LP; ++l) x[j].v[l].y = -x[j].v[l].y;
+      }
+    } else {
+      gget(reinterpret_cast<const cx<T> *>(J.in) + q.in0 + lp * LP + (int64_t)i1 * J.es_in, q.nv, (int64_t)M1 * J.es_in, x);
+    }
     fftR1(x);
 #pragma unroll
     for (int k = 1; k < R1; ++k) {
@@ -173,8 +271,17 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
 #endif
   };
 
+  auto tm_release = [&]() {   // every thread of the CTA comes here once, after its last tensor-memory access
+    if constexpr (TM) {
+#if defined(__CUDA_ARCH__)
+      asm volatile("tcgen05.fence::before_thread_sync;\n");
+      __syncthreads();
+      if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm_base), "n"(TM_COLS));
+#endif
+    }
+  };
   uint32_t tile = blockIdx.x;
-  if (tile >= ntiles) return;
+  if (tile >= ntiles) { tm_release(); return; }
   Tile cur = tile_of(tile);
   __syncthreads();   // the tables
   if (MODE == CW_CONV) {
@@ -182,6 +289,7 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
     for (int m = 0; m < NB1; ++m) f1(cur, tb + TB * m);
   }
   const T f = (T)J.fct;
+  bool parked = false;   // plain modes: the current tile waits in tensor memory (every tile but the CTA's first)
   for (;;) {
     const uint32_t next = tile + gridDim.x;
     const bool more = next < ntiles;
@@ -189,10 +297,12 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
     if (more) { nxt = tile_of(next); prefetch_tile(nxt); }
     if (MODE != CW_CONV) {
 #pragma unroll 1
-      for (int m = 0; m < NB1; ++m) f1(cur, tb + TB * m);
+      for (int m = 0; m < NB1; ++m) f1(cur, tb + TB * m, parked);
     }
     __syncthreads();
-    // ---------------- F2
+    // ---------------- F2 (with TM: the first half of the next tile's points travels HBM -> registers -> tensor memory meanwhile)
+    Vec pre[TM ? H1 : 1];
+    if constexpr (TM) { if (more) tm_fetch(nxt, 0, pre); }
 #pragma unroll 1
     for (int m = 0; m < NB2; ++m) {
       const int b = tb + TB * m, i2 = b % R3, k1 = b / R3;
@@ -210,8 +320,10 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
 #pragma unroll
       for (int k = 0; k < R2; ++k) at(base + R3 * k) = y[k];
     }
+    if constexpr (TM) { if (more) tm_park(0, pre); }
     __syncthreads();
     if constexpr (MODE != CW_CONV) {
+      if constexpr (TM) { if (more) tm_fetch(nxt, H1, pre); }
       // ---------------- F3 + store: X[k1 + R1 k2 + R1 R2 k3] leaves from the butterfly's registers
 #pragma unroll 1
       for (int m = 0; m < NB3; ++m) {
@@ -230,6 +342,7 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
              (int64_t)(R1 * R2) * J.es_out, y);
       }
       if (!more) break;
+      if constexpr (TM) { tm_park(H1, pre); parked = true; }
       __syncthreads();   // every pass-3 read before the next tile's pass-1 writes
       cur = nxt;
       tile = next;
@@ -280,7 +393,8 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
       for (int i2 = 0; i2 < R3; ++i2) at(base + i2) = y[i2];
     }
     __syncthreads();
-    // ---------------- I2
+    // ---------------- I2 (with TM: the second half of the next tile's points)
+    if constexpr (TM) { if (more) tm_fetch(nxt, H1, pre); }
 #pragma unroll 1
     for (int m = 0; m < NB2; ++m) {
       const int b = tb + TB * m, i2 = b % R3, k1 = b / R3;
@@ -298,6 +412,7 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
 #pragma unroll
       for (int j = 0; j < R2; ++j) at(base + R3 * j) = y[j];
     }
+    if constexpr (TM) { if (more) tm_park(H1, pre); }
     __syncthreads();
     // ---------------- I1 + store, then F1 of this CTA's next tile on the same thread-private positions
 #pragma unroll 1
@@ -314,12 +429,13 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
           for (int l = 0; l < LP; ++l) y[j].v[l] = mk<T>(y[j].v[l].x * f, -y[j].v[l].y * f);
         gput(reinterpret_cast<cx<T> *>(J.out) + cur.out0 + lp * LP + (int64_t)i1 * J.es_out, cur.nv, (int64_t)M1 * J.es_out, y);
       }
-      if (more) f1(nxt, i1);
+      if (more) f1(nxt, i1, TM);
     }
     if (!more) break;
     cur = nxt;
     tile = next;
   }
+  tm_release();
 }
 
 }  // namespace impulse

@@ -15,7 +15,7 @@ namespace {
 template <typename T, int R1, int R2, int R3, int W, int LP, int TT, bool PLAIN = false>
 int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
   constexpr int N = R1 * R2 * R3;
-  const size_t smem = sizeof(cx<T>) * ((size_t)N * W + (size_t)N + (size_t)R2 * R3);
+  const size_t smem = sizeof(cx<T>) * ((size_t)N * W + (size_t)N + (size_t)R2 * R3) + 16;   // + the tensor-memory address slot
   if (!J.f3_tw1 || !J.f3_tw2) return (int)cudaErrorInvalidValue;
   if (!PLAIN && (!J.umul || !J.umul_mod)) return (int)cudaErrorInvalidValue;
   const bool bwd = PLAIN && (J.flags & F_CONJ_SEQ) != 0;
@@ -25,17 +25,26 @@ int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
   const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (PLAIN || (uintptr_t)J.umul % VB == 0) && mult(J.es_in) &&
                   mult(J.es_out) && mult(J.bs_in[1]) && mult(J.bs_in[2]) && mult(J.bs_out[1]) && mult(J.bs_out[2]) &&
                   (PLAIN || J.umul_mod % VE == 0);
+  // The next tile staged in tensor memory while the current one is transformed (aligned arrays).  Measured
+  // (profiles/r02_ab_convw_tmem.txt): complex128, whose 256-thread CTAs have registers to spare for the points in flight,
+  // gains 1-3 % on the convolution and 3-13 % on the plain transform; complex64 (512 threads, 128 registers: the staged
+  // points spill) loses 1-8 %.  IMPULSE_FFT_CONVW_TMEM = 0: off, 1 (default): complex128, 2: both.
+  static const int tm_env = [] { const char *e = getenv("IMPULSE_FFT_CONVW_TMEM"); return e ? atoi(e) : 1; }();
+  const bool tm = gv && (tm_env >= 2 || (tm_env == 1 && sizeof(T) == 8));
   typedef void (*kern_t)(const LineJob);
   kern_t k;
   if constexpr (PLAIN) {
-    k = bwd ? (gv ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_BWD> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_BWD>)
-            : (gv ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_FWD> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_FWD>);
+    k = bwd ? (gv ? (tm ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_BWD, true> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_BWD>)
+                  : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_BWD>)
+            : (gv ? (tm ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_FWD, true> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_FWD>)
+                  : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_FWD>);
   } else {
-    k = gv ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>;
+    k = gv ? (tm ? colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_CONV, true> : colconvw_kernel<T, R1, R2, R3, W, LP, TT, true>)
+           : colconvw_kernel<T, R1, R2, R3, W, LP, TT, false>;
   }
-  static PerDeviceFlag flag[4];
-  static int ctas_per_sm[4][kMaxDevices] = {};
-  const int vi = (gv ? 1 : 0) + (bwd ? 2 : 0);
+  static PerDeviceFlag flag[8];
+  static int ctas_per_sm[8][kMaxDevices] = {};
+  const int vi = (gv ? 1 : 0) + (bwd ? 2 : 0) + (tm ? 4 : 0);
   bool &configured = flag[vi].here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -65,7 +74,7 @@ int launch_colconvw(const LineJob &J, int sm_count, cudaStream_t s) {
   if (grid > tiles) grid = tiles;
   static thread_local char name[96];
   snprintf(name, sizeof(name), "colconvw_kernel<%s,%d,%d,%d,%d,%d,%d>%s%s", sizeof(T) == 8 ? "double" : "float", R1, R2, R3, W, LP, TT,
-           PLAIN ? (bwd ? "+bwd" : "+fwd") : "", gv ? "" : "+scalar");
+           PLAIN ? (bwd ? "+bwd" : "+fwd") : "", gv ? (tm ? "+tmem" : "") : "+scalar");
   g_last_kernel = name;
   k<<<(unsigned)grid, TT, smem, s>>>(Jg);
   return (int)cudaGetLastError();

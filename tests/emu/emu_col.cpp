@@ -105,6 +105,17 @@ int run_colconvw(const LineJob &J) {
   const bool gv = (uintptr_t)J.in % VB == 0 && (uintptr_t)J.out % VB == 0 && (PLAIN || (uintptr_t)J.umul % VB == 0) && mult(J.es_in) &&
                   mult(J.es_out) && mult(J.bs_in[1]) && mult(J.bs_in[2]) && mult(J.bs_out[1]) && mult(J.bs_out[2]) &&
                   (PLAIN || J.umul_mod % VE == 0);
+  const int tm_env = getenv("IMPULSE_FFT_CONVW_TMEM") ? atoi(getenv("IMPULSE_FFT_CONVW_TMEM")) : 1;   // as launch_colconvw
+  const bool tm = gv && (tm_env >= 2 || (tm_env == 1 && sizeof(T) == 8));
+  if (tm) {   // the tensor-memory staging logic, with a thread-private array standing in for the lanes' columns
+    if constexpr (PLAIN) {
+      if (bwd) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_BWD, true>(Jg); });
+      else launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_FWD, true>(Jg); });
+    } else {
+      launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_CONV, true>(Jg); });
+    }
+    return 0;
+  }
   if constexpr (PLAIN) {
     if (bwd && gv) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, true, CW_BWD>(Jg); });
     else if (bwd) launch(grid, TT, [&] { colconvw_kernel<T, R1, R2, R3, W, LP, TT, false, CW_BWD>(Jg); });

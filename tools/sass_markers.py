@@ -1,5 +1,6 @@
 """profiles/sass_markers.txt: per kernel family, the SASS mnemonics that show what the hardware path is
-(UBLKCP = cp.async.bulk / TMA bulk copy, SYNCS = mbarrier, LDGSTS = cp.async, LDG/STG .128 = 128-bit global accesses,
+(UBLKCP = cp.async.bulk / TMA bulk copy, SYNCS = mbarrier, LDTM / STTM = tcgen05.ld / tcgen05.st (tensor memory used as
+staging storage by the whole-axis kernel), LDGSTS = cp.async, LDG/STG .128 = 128-bit global accesses,
 DFMA/DADD/DMUL = fp64 pipe, FFMA = fp32; UTC*MMA / UTMALDG would be tensor-core MMA / tensor-map TMA: an FFT has no
 contraction, none is expected).  Usage: python tools/sass_markers.py > profiles/sass_markers.txt"""
 import collections, glob, os, re, subprocess, sys
@@ -30,7 +31,7 @@ for obj in sorted(glob.glob(os.path.join(ROOT, "impulse_b200", "csrc", "build", 
                 c[base + ".128"] += 1
 print(__doc__.split("Usage")[0].strip())
 print()
-keys = ["UBLKCP", "UTMALDG", "SYNCS", "LDGSTS", "LDG", "LDG.128", "STG", "STG.128", "LDS.128", "STS.128", "DFMA", "DADD", "DMUL", "FFMA", "FADD", "BAR", "ATOMG", "REDG", "MEMBAR", "ERRBAR"]
+keys = ["UBLKCP", "UTMALDG", "SYNCS", "LDTM", "STTM", "LDGSTS", "LDG", "LDG.128", "STG", "STG.128", "LDS.128", "STS.128", "DFMA", "DADD", "DMUL", "FFMA", "FADD", "BAR", "ATOMG", "REDG", "MEMBAR", "ERRBAR"]
 print(f"{'object':24s} {'kernel family':48s} {'inst':>5s} " + " ".join(f"{k:>8s}" for k in keys))
 for (obj, k), (n, c) in fam.items():
     print(f"{obj:24s} {k:48s} {n:5d} " + " ".join(f"{c[x]:8d}" for x in keys))
@@ -39,4 +40,5 @@ for (_, _), (n, c) in fam.items():
     tot.update(c)
 print()
 print("any tensor-core MMA (UTC*MMA/HMMA):", sum(v for k, v in tot.items() if "MMA" in k), "| tensor-map TMA (UTMALDG/UTMASTG):", tot["UTMALDG"] + tot["UTMASTG"],
-      "| bulk TMA copies (UBLKCP):", tot["UBLKCP"], "| mbarrier ops (SYNCS):", tot["SYNCS"], "| cp.async (LDGSTS):", tot["LDGSTS"])
+      "| bulk TMA copies (UBLKCP):", tot["UBLKCP"], "| mbarrier ops (SYNCS):", tot["SYNCS"], "| cp.async (LDGSTS):", tot["LDGSTS"],
+      "| tensor-memory loads / stores (LDTM / STTM):", tot["LDTM"], "/", tot["STTM"])
