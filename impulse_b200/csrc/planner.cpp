@@ -615,12 +615,13 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
     uint32_t id = FAST_NONE, r2 = 0;
     if (s.kind == KIND_C2C && !s.umul_mod && !s.tw4_n && !s.mul_tab && !s.zero_pad_from && !s.blue_stage && in_lf && out_lf &&
         s.bs_in[0] == 1 && s.bs_out[0] == 1 && n_lines / J->bdim[0] * ((J->bdim[0] + 1) / 2) < (1ull << 31)) {
-      // measured against the two-launch split (profiles/r02_ab_colw.txt): complex128 1024 points +6...10 %; complex64
-      // 1024 points -3 %, 2048 points -10...-30 % (one resident CTA per SM: load, transform and store do not overlap)
-      // — those only under IMPULSE_FFT_COL_WHOLE=2
+      // measured against the two-launch split (profiles/r02_ab_colw.txt, r02_ab_convw_tmem.txt): complex128, with the
+      // next tile staged in tensor memory, +6...13 % at 1024 points and +4 % at 2048; complex64 -3 % at 1024 and
+      // -15...-30 % at 2048 points (one resident CTA per SM and no registers to spare for the staging: load,
+      // transform and store do not overlap) — those only under IMPULSE_FFT_COL_WHOLE=2
       const bool all = env_int("IMPULSE_FFT_COL_WHOLE", 1) >= 2;
       if (N == 1024 && (f64 || all)) { id = f64 ? COLW_1024_F64 : COLW_1024_F32; r2 = 8; }
-      else if (N == 2048 && all) { id = f64 ? COLW_2048_F64 : COLW_2048_F32; r2 = 16; }
+      else if (N == 2048 && (f64 || all)) { id = f64 ? COLW_2048_F64 : COLW_2048_F32; r2 = 16; }
     }
     if (id == FAST_NONE) { *err = "no whole-axis kernel for this shape"; return ERR_UNSUPPORTED; }
     rc = fast3_tables(N, 16, r2, 8, s.dtype, &J->f3_tw1, &J->f3_tw2, err);
