@@ -514,6 +514,19 @@ int run_host(impulse_fft_plan p, const void *in, void *out, double fct) {
   }
   e = cudaStreamSynchronize(ws);
   if (e != cudaSuccess && !rc) rc = cuda_fail(e, "staging sync");
+  // the buffers stay for the next call up to IMPULSE_FFT_STAGE_KEEP_MB (default 4096 MiB for the pair); larger ones are
+  // returned at once, so that one huge host transform does not hold device memory for the life of the process
+  static const size_t keep_bytes = [] {
+    const char *v = std::getenv("IMPULSE_FFT_STAGE_KEEP_MB");
+    const long mb = v ? std::atol(v) : 4096;
+    return (size_t)(mb > 0 ? mb : 0) << 20;
+  }();
+  if (sg.wcap_in + sg.wcap_out > keep_bytes) {
+    if (sg.win) cudaFree(sg.win);
+    if (sg.wout) cudaFree(sg.wout);
+    sg.win = sg.wout = nullptr;
+    sg.wcap_in = sg.wcap_out = 0;
+  }
   return rc;
 }
 
