@@ -24,46 +24,11 @@
 // DRAM round trip), and W_N^(i1 k1) lives in shared memory beside the tile (the streamed tile evicted it from L1).
 #pragma once
 #include "fast3_device.cuh"
+#include "tmem_device.cuh"
 
 namespace impulse {
 
 template <typename T, int LP> struct alignas((LP * sizeof(cx<T>)) >= 16 ? 16 : 8) CwVec { cx<T> v[LP]; };
-
-// Tensor memory (256 KB per SM, 128 lanes x 512 columns x 32 bit) as LANE-PRIVATE staging storage: warp w owns lanes
-// 32*(w%4)..+31, a thread reads back exactly the columns of its own lane that it stored (tcgen05.st / tcgen05.ld,
-// .32x32b: one 32-bit column per register).  No MMA is involved; it is the only on-chip space left beside a tile that
-// fills the shared memory.  (tools/micro/tmem_stage.cu: 64 words out and back in 460 cycles with 512 threads.)
-// The host emulation (tests/emu) gives every thread a private array.
-#if !defined(__CUDA_ARCH__)
-static thread_local uint32_t cw_emu_tmem[512];
-#endif
-__device__ __forceinline__ void cw_tmem_st8(uint32_t taddr, const uint32_t *v) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
-               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
-#else
-  for (int k = 0; k < 8; ++k) cw_emu_tmem[(taddr & 0xffffu) + k] = v[k];
-#endif
-}
-__device__ __forceinline__ void cw_tmem_ld8(uint32_t taddr, uint32_t *v) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr));
-#else
-  for (int k = 0; k < 8; ++k) v[k] = cw_emu_tmem[(taddr & 0xffffu) + k];
-#endif
-}
-__device__ __forceinline__ void cw_tmem_wait_st() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void cw_tmem_wait_ld() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#endif
-}
 
 // MODE: CW_CONV = the convolution above; CW_FWD / CW_BWD = the plain transform of the axis (passes F1, F2, F3 and a store
 // straight from the last butterfly's registers; backward = conj(FFT(conj x))): ONE pass over the data for strided
@@ -94,21 +59,8 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
   uint32_t tm_addr = 0, tm_base = 0;
   (void)tm_base;
   if constexpr (TM) {
-    uint32_t *slot = reinterpret_cast<uint32_t *>(s_tw2 + R2 * R3);
-#if defined(__CUDA_ARCH__)
-    if (t < 32) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(slot)),
-                   "n"(TM_COLS));
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n");
-    tm_base = *slot;
+    tm_base = cw_tmem_acquire<TM_COLS>(reinterpret_cast<uint32_t *>(s_tw2 + R2 * R3), t);
     tm_addr = tm_base + ((uint32_t)(((t >> 5) & 3) * 32) << 16) + (uint32_t)(t >> 7) * (R1 * WV);
-#else
-    (void)slot;
-#endif
   }
 
   const cx<T> *um = reinterpret_cast<const cx<T> *>(J.umul);
@@ -272,13 +224,7 @@ colconvw_kernel(const __grid_constant__ LineJob J) {
   };
 
   auto tm_release = [&]() {   // every thread of the CTA comes here once, after its last tensor-memory access
-    if constexpr (TM) {
-#if defined(__CUDA_ARCH__)
-      asm volatile("tcgen05.fence::before_thread_sync;\n");
-      __syncthreads();
-      if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm_base), "n"(TM_COLS));
-#endif
-    }
+    if constexpr (TM) cw_tmem_release<TM_COLS>(tm_base, t);
   };
   uint32_t tile = blockIdx.x;
   if (tile >= ntiles) { tm_release(); return; }

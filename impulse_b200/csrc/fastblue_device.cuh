@@ -2,6 +2,7 @@
 // tests/emu/emu_fastblue.cpp can compile the SAME kernel body for the host (thread-level emulation, test
 // infrastructure only); the product runs it on the device only.
 #pragma once
+#include "tmem_device.cuh"
 #include "fast3_device.cuh"
 
 namespace impulse {
@@ -120,10 +121,12 @@ template <typename T>
 struct Fft4_8192 {
   static constexpr int N = 8192, E = 16, TT = 512, M1 = 512, P1 = 513, BUFN = 16 * P1;
   static constexpr bool TW1_REGS = true;
-  template <bool MUL = false>
+  // TMB: the thread's 16 multipliers mul[t + 512 q] — the same for every unit — wait in its own tensor-memory columns
+  // (tm_mul; written once per CTA) instead of being streamed from L2 for every unit
+  template <bool MUL = false, bool TMB = false>
   static __device__ __forceinline__ void run(cx<T> (&x)[16], cx<T> *buf, const cx<T> *__restrict__ /*tw1*/,
                                              const cx<T> *s_tw2, const cx<T> (&twA)[3], const cx<T> (&twB)[3], int t,
-                                             const cx<T> *__restrict__ mul = nullptr) {
+                                             const cx<T> *__restrict__ mul = nullptr, uint32_t tm_mul = 0) {
     // ---- pass 1
     RegFFT<T, 16>::run(x);
 #pragma unroll
@@ -161,7 +164,13 @@ struct Fft4_8192 {
     for (int k = 0; k < 16; ++k) buf[i3 * 4096 + klow2 + 256 * k] = x[k];
     // the row registers are free here: with MUL, all 16 multipliers are requested before the barrier and the radix-2 pass
     cx<T> w[MUL ? 16 : 1];
-    if constexpr (MUL) {
+    if constexpr (MUL && TMB) {
+      constexpr int WC = (int)(sizeof(cx<T>) / 4);
+      uint32_t *ww = reinterpret_cast<uint32_t *>(&w[0]);
+#pragma unroll
+      for (int c = 0; c < 16 * WC; c += 8) cw_tmem_ld8(tm_mul + (uint32_t)c, ww + c);
+      cw_tmem_wait_ld();
+    } else if constexpr (MUL) {
 #pragma unroll
       for (int q = 0; q < 16; ++q) w[q] = __ldg(mul + t + TT * q);
     }
@@ -240,7 +249,10 @@ constexpr int kBlueMaxDef = 16;  // largest supported deficiency d
 // copied to shared memory once per CTA instead of being streamed from L2 twice per unit.
 // BFE: FFT(b)/M is multiplied in inside the first transform's last pass, half of it requested ahead of the butterfly.
 // FOUR: the 8192-point work array on Fft4_8192 (instantiate with R1,R2,R3 = 16,16,32 and E = 16: 512 threads).
-template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool BKS = false, bool BFE = false, bool FOUR = false>
+// TMB (four-pass core with BFE): FFT(b)/M lives in TENSOR MEMORY — every thread keeps the 16 entries it multiplies by
+// in its own columns for the life of the CTA (131 KB per unit no longer streamed from L2).
+template <typename T, int R1, int R2, int R3, int E, int KIND, bool BWD, bool BKS = false, bool BFE = false, bool FOUR = false,
+          bool TMB = false>
 __global__ void __launch_bounds__((R1 * R2 * R3) / E, 1)
 fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_t nrows, int64_t rs_in, int64_t rs_out,
                 uint32_t L, uint32_t d, const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2,
@@ -256,6 +268,22 @@ fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_
   cx<T> *s_tail = s_tw2 + R2 * R3;  // a[n], n >= L-d
   cx<T> *s_bk = s_tail + kBlueMaxDef;
   const int t = threadIdx.x;
+  static_assert(!TMB || (FOUR && BFE && BKS && E == 16), "tensor-memory multipliers: four-pass core with the early multiply");
+  constexpr int TMB_WORDS = 16 * (int)(sizeof(cx<T>) / 4), TMB_COLS = TMB_WORDS * (TT / 128);   // 64 x 4 = 256 columns (fp64)
+  uint32_t tmb_base = 0, tmb_addr = 0;
+  (void)tmb_base; (void)tmb_addr;
+  if constexpr (TMB) {
+    static_assert(TMB_COLS <= 512 && (TMB_COLS & (TMB_COLS - 1)) == 0, "tensor-memory columns");
+    tmb_base = cw_tmem_acquire<TMB_COLS>(reinterpret_cast<uint32_t *>(s_bk + L), t);
+    tmb_addr = tmb_base + ((uint32_t)(((t >> 5) & 3) * 32) << 16) + (uint32_t)(t >> 7) * TMB_WORDS;
+    cx<T> w[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) w[q] = __ldg(bf + t + TT * q);
+    const uint32_t *ww = reinterpret_cast<const uint32_t *>(&w[0]);
+#pragma unroll
+    for (int c = 0; c < TMB_WORDS; c += 8) cw_tmem_st8(tmb_addr + (uint32_t)c, ww + c);
+    cw_tmem_wait_st();
+  }
   if (BKS) for (uint32_t idx = t; idx < L; idx += TT) s_bk[idx] = bk[idx];
   const cx<T> *bkp = BKS ? s_bk : bk;
   const uint64_t nunits = KIND == BL_C2C ? nrows : (nrows + 1) / 2;
@@ -319,7 +347,8 @@ fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_
       }
     }
     if constexpr (BFE) {
-      F::template run<true>(x, buf, tw1, s_tw2, twA, twB, t, bf);
+      if constexpr (TMB) F::template run<true, true>(x, buf, tw1, s_tw2, twA, twB, t, bf, tmb_addr);
+      else F::template run<true>(x, buf, tw1, s_tw2, twA, twB, t, bf);
       if (t == 0) s_row[it & 1] = atomicAdd(&sched[0], 1u);
     } else {
       F::run(x, buf, tw1, s_tw2, twA, twB, t);
@@ -394,6 +423,7 @@ fastblue_kernel(const void *__restrict__ in_v, void *__restrict__ out_v, uint64_
     const unsigned done = atomicAdd(&sched[1], 1u);
     if (done == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
   }
+  if constexpr (TMB) cw_tmem_release<TMB_COLS>(tmb_base, t);
 }
 
 }  // namespace impulse

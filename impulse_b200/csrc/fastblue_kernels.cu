@@ -34,18 +34,25 @@ inline bool blue_four_pass() {
   static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_FOUR"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
+// FFT(b)/M in tensor memory (four-pass core with the early multiply): every thread keeps its 16 multipliers in its own
+// columns for the life of the CTA instead of streaming 131 KB per unit from L2.  Measured on config 3c
+// (profiles/r02_ab_blue_tmem.txt): r2c 1.138 -> 1.074 ms, c2r 1.130 -> 1.079 ms.  IMPULSE_FFT_BLUE_TMEM=0 switches it off.
+inline bool blue_tmem() {
+  static const int v = [] { const char *e = getenv("IMPULSE_FFT_BLUE_TMEM"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
 template <typename T, int R1, int R2, int R3, int E>
 int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
   using F = Fft3<T, R1, R2, R3, E>;
   const bool bks = (R1 * R2 * R3 == 8192) && blue_bk_smem();
   const bool bfe = bks && blue_bf_early();
-  const size_t smem = sizeof(cx<T>) * ((size_t)F::BUFN + (size_t)R2 * R3 + kBlueMaxDef + (bks ? (size_t)J.n_seq : 0)) + 16;
+  const size_t smem = sizeof(cx<T>) * ((size_t)F::BUFN + (size_t)R2 * R3 + kBlueMaxDef + (bks ? (size_t)J.n_seq : 0)) + 32;   // + scheduler words, tensor-memory slot
   const int kind = J.store_mode == ST_HERM_HALF ? BL_R2C_PAIR : J.load_mode == LD_HERM_FULL ? BL_C2R_PAIR : BL_C2C;
   const bool bwd = kind == BL_C2C ? (J.flags & F_CONJ_SEQ) != 0 : kind == BL_R2C_PAIR ? (J.flags & F_CONJ_RESULT) != 0 : (J.flags & F_CONJ_IN) != 0;
   typedef void (*kern_t)(const void *, void *, uint64_t, int64_t, int64_t, uint32_t, uint32_t, const cx<T> *, const cx<T> *,
                          const cx<T> *, const cx<T> *, const cx<T> *, T, unsigned int *);
   kern_t k = nullptr;
-  bool four = false;
+  bool four = false, tmb = false;
   switch (kind * 2 + (bwd ? 1 : 0)) {
     case 0: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, false>; break;
     case 1: k = fastblue_kernel<T, R1, R2, R3, E, BL_C2C, true>; break;
@@ -89,6 +96,18 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
             default: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2R_PAIR, true, true, true, true>; break;
           }
           g_last_kernel = "fastblue_kernel<double,16,16,16,2,E16>+bk_smem+bf_early";
+          if (blue_tmem()) {
+            tmb = true;
+            switch (kind * 2 + (bwd ? 1 : 0)) {
+              case 0: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2C, false, true, true, true, true>; break;
+              case 1: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2C, true, true, true, true, true>; break;
+              case 2: k = fastblue_kernel<T, 16, 16, 32, 16, BL_R2C_PAIR, false, true, true, true, true>; break;
+              case 3: k = fastblue_kernel<T, 16, 16, 32, 16, BL_R2C_PAIR, true, true, true, true, true>; break;
+              case 4: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2R_PAIR, false, true, true, true, true>; break;
+              default: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2R_PAIR, true, true, true, true, true>; break;
+            }
+            g_last_kernel = "fastblue_kernel<double,16,16,16,2,E16>+bk_smem+bf_early+bf_tmem";
+          }
         } else {
           switch (kind * 2 + (bwd ? 1 : 0)) {
             case 0: k = fastblue_kernel<T, 16, 16, 32, 16, BL_C2C, false, true, false, true>; break;
@@ -108,8 +127,8 @@ int launch_fastblue(const LineJob &J, int sm_count, cudaStream_t s) {
   // the dynamic shared-memory size depends on L when the chirp table is resident: always raise the limit to the maximum
   const size_t smem_max = bks ? (size_t)227 * 1024 : smem;
   if (smem > smem_max) return (int)cudaErrorInvalidValue;
-  static PerDeviceFlag flags[30];
-  bool &configured_here = flags[(four ? 18 + (bfe ? 6 : 0) : bfe ? 12 : bks ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
+  static PerDeviceFlag flags[36];
+  bool &configured_here = flags[(tmb ? 30 : four ? 18 + (bfe ? 6 : 0) : bfe ? 12 : bks ? 6 : 0) + kind * 2 + (bwd ? 1 : 0)].here();
   if (!configured_here) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return (int)e;

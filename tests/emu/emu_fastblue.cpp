@@ -44,7 +44,7 @@ struct HostAlloc : TableAlloc {
 HostAlloc g_alloc;
 PlanCache *g_cache = nullptr;
 
-template <typename T, int R3, int E, int KIND, bool BWD, bool BKS, bool BFE, bool FOUR = false>
+template <typename T, int R3, int E, int KIND, bool BWD, bool BKS, bool BFE, bool FOUR = false, bool TMB = false>
 int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
   constexpr int M = 16 * 16 * R3, TT = M / E;
   if (!g_cache) g_cache = new PlanCache(&g_alloc);
@@ -66,7 +66,7 @@ int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, in
     for (int t = 0; t < TT; ++t)
       th.emplace_back([&, t] {
         threadIdx.x = (unsigned)t;
-        fastblue_kernel<T, 16, 16, R3, E, KIND, BWD, BKS, BFE, FOUR>(in, out, nrows, rs_in, rs_out, L, d, (const cx<T> *)tw1, (const cx<T> *)tw2,
+        fastblue_kernel<T, 16, 16, R3, E, KIND, BWD, BKS, BFE, FOUR, TMB>(in, out, nrows, rs_in, rs_out, L, d, (const cx<T> *)tw1, (const cx<T> *)tw2,
                                                                      (const cx<T> *)eng->d_bk, (const cx<T> *)bf, (const cx<T> *)corr, (T)fct, sched);
       });
     for (auto &x : th) x.join();
@@ -75,9 +75,9 @@ int run(uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, in
   return 0;
 }
 
-template <typename T, int R3, int E, bool BKS, bool BFE, bool FOUR = false>
+template <typename T, int R3, int E, bool BKS, bool BFE, bool FOUR = false, bool TMB = false>
 int by_kind(int kind, int bwd, uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out, double fct, unsigned ctas) {
-#define GO(K) (bwd ? run<T, R3, E, K, true, BKS, BFE, FOUR>(L, in, out, nrows, rs_in, rs_out, fct, ctas) : run<T, R3, E, K, false, BKS, BFE, FOUR>(L, in, out, nrows, rs_in, rs_out, fct, ctas))
+#define GO(K) (bwd ? run<T, R3, E, K, true, BKS, BFE, FOUR, TMB>(L, in, out, nrows, rs_in, rs_out, fct, ctas) : run<T, R3, E, K, false, BKS, BFE, FOUR, TMB>(L, in, out, nrows, rs_in, rs_out, fct, ctas))
   if (kind == BL_C2C) return GO(BL_C2C);
   if (kind == BL_R2C_PAIR) return GO(BL_R2C_PAIR);
   return GO(BL_C2R_PAIR);
@@ -118,7 +118,7 @@ int emu_fast4_8192(int bwd, const void *in, void *out, uint64_t nrows, int64_t r
   return bwd ? run_fast4<true>(in, out, nrows, rs_in, rs_out, fct, ctas) : run_fast4<false>(in, out, nrows, rs_in, rs_out, fct, ctas);
 }
 // kind: 0 c2c, 1 r2c (row pairs), 2 c2r (row pairs); flags: 1 = chirp table in shared memory, 2 = multipliers inside the
-// first transform's last pass, 4 = four-pass core (512 threads), 8 = float32; row strides in elements of the row's own type (LineJob::bs_in / bs_out)
+// first transform's last pass, 4 = four-pass core (512 threads), 8 = float32, 16 = multipliers in tensor memory (with 2 and 4); row strides in elements of the row's own type (LineJob::bs_in / bs_out)
 int emu_fastblue(int kind, int bwd, int flags, uint32_t L, const void *in, void *out, uint64_t nrows, int64_t rs_in, int64_t rs_out,
                  double fct, unsigned ctas) {
   const uint32_t need = 2 * L - 1;
@@ -135,6 +135,7 @@ int emu_fastblue(int kind, int bwd, int flags, uint32_t L, const void *in, void 
   if (need <= 4096 + 8) return by_kind<double, 16, 16, false, false>(ARGS);
   if (need > 8192 + 8) return -1;
   if (flags & 4) {   // four-pass core: 512 threads x 16 points
+    if (bfe && (flags & 16)) return by_kind<double, 32, 16, true, true, true, true>(ARGS);   // FFT(b)/M in tensor memory
     if (bfe) return by_kind<double, 32, 16, true, true, true>(ARGS);
     return by_kind<double, 32, 16, true, false, true>(ARGS);
   }

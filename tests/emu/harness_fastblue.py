@@ -11,7 +11,7 @@ SO = os.path.join(HERE, "libimpulse_fastblue_emu.so")
 CSRC = os.path.join(ROOT, "impulse_b200", "csrc")
 SRC = [os.path.join(HERE, "emu_fastblue.cpp"), os.path.join(CSRC, "planner.cpp")]
 DEPS = SRC + [os.path.join(CSRC, f) for f in ("fastblue_device.cuh", "fast3_device.cuh", "fft_device.cuh", "fft_types.h",
-                                                "trig_tables.h", "planner.h")]
+                                                "trig_tables.h", "planner.h", "tmem_device.cuh")]
 KIND = {"c2c": 0, "r2c": 1, "c2r": 2}
 
 
@@ -55,7 +55,7 @@ def run_fast4(x, forward=True, fct=1.0, ctas=2):
     return out.copy()
 
 
-def run(kind, x, length, forward=True, fct=1.0, bk_smem=False, bf_early=False, ctas=2, four_pass=False):
+def run(kind, x, length, forward=True, fct=1.0, bk_smem=False, bf_early=False, ctas=2, four_pass=False, bf_tmem=False):
     """x = [rows, L] complex (c2c), [rows, L] real (r2c) or [rows, L//2+1] complex (c2r); float64 or float32.
     `forward` has the reference's meaning (pocketfft_hdronly.h:3125-3250)."""
     x = np.ascontiguousarray(x)
@@ -71,7 +71,7 @@ def run(kind, x, length, forward=True, fct=1.0, bk_smem=False, bf_early=False, c
     pad = 64
     flat = np.full(oshape[0] * oshape[1] + 2 * pad, np.nan, odt)
     out = flat[pad:-pad].reshape(oshape)
-    rc = lib().emu_fastblue(KIND[kind], 1 if bwd else 0, (1 if bk_smem else 0) | (2 if bf_early else 0) | (4 if four_pass else 0) | (8 if f32 else 0), length, x.ctypes.data,
+    rc = lib().emu_fastblue(KIND[kind], 1 if bwd else 0, (1 if bk_smem else 0) | (2 if bf_early else 0) | (4 if four_pass else 0) | (8 if f32 else 0) | (16 if bf_tmem else 0), length, x.ctypes.data,
                             out.ctypes.data, rows, x.shape[1], out.shape[1], fct, ctas)
     if rc:
         raise RuntimeError(f"emu_fastblue rc={rc}")

@@ -12,7 +12,8 @@ def rel(a, b):
 
 
 VARIANTS = [dict(), dict(bk_smem=True), dict(bk_smem=True, bf_early=True),
-            dict(bk_smem=True, four_pass=True), dict(bk_smem=True, bf_early=True, four_pass=True)]
+            dict(bk_smem=True, four_pass=True), dict(bk_smem=True, bf_early=True, four_pass=True),
+            dict(bk_smem=True, bf_early=True, four_pass=True, bf_tmem=True)]   # FFT(b)/M in tensor memory
 
 
 @pytest.mark.parametrize("var", VARIANTS)
