@@ -316,7 +316,7 @@ int run_device(impulse_fft_plan p, const void *in, void *out, double fct, cudaSt
     if ((J.flags & F_VEC_IN) && ((uintptr_t)J.in % (2 * r))) J.flags &= ~F_VEC_IN;
     if ((J.flags & F_VEC_OUT) && ((uintptr_t)J.out % (2 * r))) J.flags &= ~F_VEC_OUT;
     // the register kernels address real rows as complex pairs: fall back to the generic engine otherwise
-    if (((J.fast_id >= FAST3_2048_F64 && J.fast_id <= FAST3_1000_F64) || (J.fast_id >= FAST3R_256_F64 && J.fast_id <= FAST3P_512_F32) || (J.fast_id >= FAST3_1536_F64 && J.fast_id <= FAST3_6561_F64) || (J.fast_id >= FAST3_1536_F32 && J.fast_id <= FAST3_6561_F32)) && (((uintptr_t)J.in % (2 * r)) || ((uintptr_t)J.out % (2 * r)))) J.fast_id = FAST_NONE;
+    if (((J.fast_id >= FAST3_2048_F64 && J.fast_id <= FAST3_1000_F64) || (J.fast_id >= FAST3R_256_F64 && J.fast_id <= FAST3P_512_F32) || (J.fast_id >= FAST3_1536_F64 && J.fast_id <= FAST3_6561_F64) || (J.fast_id >= FAST3_1536_F32 && J.fast_id <= FAST3_6561_F32) || (J.fast_id >= FAST2R_8_F64 && J.fast_id <= FAST2R_4_F32)) && (((uintptr_t)J.in % (2 * r)) || ((uintptr_t)J.out % (2 * r)))) J.fast_id = FAST_NONE;
     int e = launch_line_job(J, st.cfg.threads, st.cfg.smem_bytes, st.cfg.n_tiles, stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e) { rc = cuda_fail((cudaError_t)e, "kernel launch"); break; }

@@ -638,6 +638,14 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST2_128_F32: g_last_kernel = "fast2_kernel<float,16,8,8,4>"; return launch_fast2<float, 16, 8, 8, 4>(J, sm_count, s);
     case FAST2_256_F32: g_last_kernel = "fast2_kernel<float,16,16,8,4>"; return launch_fast2<float, 16, 16, 8, 4>(J, sm_count, s);
     case FAST2_512_F32: g_last_kernel = "fast2_kernel<float,32,16,4,4>"; return launch_fast2<float, 32, 16, 4, 4>(J, sm_count, s);
+    case FAST2_8_F64: g_last_kernel = "fast2_kernel<double,4,2,8,4>"; return launch_fast2<double, 4, 2, 8, 4>(J, sm_count, s);
+    case FAST2_4_F64: g_last_kernel = "fast2_kernel<double,2,2,8,4>"; return launch_fast2<double, 2, 2, 8, 4>(J, sm_count, s);
+    case FAST2_8_F32: g_last_kernel = "fast2_kernel<float,4,2,8,6>"; return launch_fast2<float, 4, 2, 8, 6>(J, sm_count, s);
+    case FAST2_4_F32: g_last_kernel = "fast2_kernel<float,2,2,8,6>"; return launch_fast2<float, 2, 2, 8, 6>(J, sm_count, s);
+    case FAST2R_8_F64: g_last_kernel = "fast2r_kernel<double,4,2>"; return launch_fast2r<double, 4, 2, 8, 4>(J, sm_count, s);
+    case FAST2R_4_F64: g_last_kernel = "fast2r_kernel<double,2,2>"; return launch_fast2r<double, 2, 2, 8, 4>(J, sm_count, s);
+    case FAST2R_8_F32: g_last_kernel = "fast2r_kernel<float,4,2>"; return launch_fast2r<float, 4, 2, 8, 6>(J, sm_count, s);
+    case FAST2R_4_F32: g_last_kernel = "fast2r_kernel<float,2,2>"; return launch_fast2r<float, 2, 2, 8, 6>(J, sm_count, s);
     case FAST2R_16_F64: g_last_kernel = "fast2r_kernel<double,4,4>"; return launch_fast2r<double, 4, 4, 8, 4>(J, sm_count, s);
     case FAST2R_32_F64: g_last_kernel = "fast2r_kernel<double,8,4>"; return launch_fast2r<double, 8, 4, 8, 4>(J, sm_count, s);
     case FAST2R_64_F64: g_last_kernel = "fast2r_kernel<double,8,8>"; return launch_fast2r<double, 8, 8, 8, 4>(J, sm_count, s);

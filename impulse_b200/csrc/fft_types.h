@@ -188,6 +188,14 @@ enum FastId : uint32_t {
   COLW_2048_F32 = 100,
   COLW_1024_F64 = 101,
   COLW_2048_F64 = 102,
+  FAST2_8_F64 = 103,       // tiny rows on the two-pass warp kernels: 8 = 4*2 (16 rows per warp), 4 = 2*2
+  FAST2_4_F64 = 104,
+  FAST2_8_F32 = 105,
+  FAST2_4_F32 = 106,
+  FAST2R_8_F64 = 107,      // real rows of 16 / 8 points
+  FAST2R_4_F64 = 108,
+  FAST2R_8_F32 = 109,
+  FAST2R_4_F32 = 110,
 };
 
 struct Phase {

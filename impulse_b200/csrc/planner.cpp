@@ -565,6 +565,8 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
   if (s.kind == KIND_C2C && !E->blue && !s.tw4_n && !s.zero_pad_from && !s.mul_tab && !s.umul_mod && s.es_in == 1 && s.es_out == 1 && J->bdim[1] == 1 && J->bdim[2] == 1 &&
       !env_int("IMPULSE_FFT_NO_FAST", 0)) {
     switch (N) {
+      case 4: J->fast_id = f64 ? FAST2_4_F64 : FAST2_4_F32; break;
+      case 8: J->fast_id = f64 ? FAST2_8_F64 : FAST2_8_F32; break;
       case 16: J->fast_id = f64 ? FAST2_16_F64 : FAST2_16_F32; break;
       case 32: J->fast_id = f64 ? FAST2_32_F64 : FAST2_32_F32; break;
       case 64: J->fast_id = f64 ? FAST2_64_F64 : FAST2_64_F32; break;
@@ -701,6 +703,10 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       else if (L == 1536 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_1536_F32; r1 = 8; r2 = 24; r3 = 8; }
       else if (L == 2000 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_2000_F32; r1 = 10; r2 = 20; r3 = 10; }
       else if (L == 4000 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_4000_F32; r1 = 10; r2 = 20; r3 = 20; }
+      else if (!c2c && (L == 4 || L == 8) && J->tw_r) {
+        // tiny real rows (8 / 16 points): the same warp kernel, 16 rows per warp
+        J->fast_id = L == 8 ? (f64 ? FAST2R_8_F64 : FAST2R_8_F32) : (f64 ? FAST2R_4_F64 : FAST2R_4_F32);
+      }
       else if (!c2c && (L == 16 || L == 32 || L == 64 || L == 128) && J->tw_r) {
         // short real rows: two-pass warp kernel (fast2r_kernel), tables = the engine's own W_L^m and W_N^k
         J->fast_id = (L == 16 ? FAST2R_16_F64 : L == 32 ? FAST2R_32_F64 : L == 64 ? FAST2R_64_F64 : FAST2R_128_F64) + (f64 ? 0 : 4);

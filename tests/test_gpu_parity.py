@@ -130,6 +130,35 @@ def test_c2c_lengths(ib, torch_mod, checker, dtype):
             assert oracle.max_row_rel_l2(got, want) <= tol(n, dtype), (n, fwd)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tiny_rows_many(ib, torch_mod, checker, dtype):
+    """rows of 4 / 8 complex and 8 / 16 real points on the warp kernels (16 rows per warp): more rows than one sweep of
+    the grid, a row count that leaves the last warp ragged, both directions"""
+    rng = np.random.default_rng(21)
+    cdt = np.complex128 if dtype == np.float64 else np.complex64
+    used = set()
+    for n in (4, 8):
+        x = rnd(rng, (100003, n), cdt)
+        xd = torch_mod.from_numpy(x).cuda()
+        for fwd in (True, False):
+            got = apply_nd(ib, "c2c", xd, torch_mod.empty_like(xd), [1], fwd, 0.5).cpu().numpy()
+            used.add(ib.last_kernel())
+            assert oracle.max_row_rel_l2(got, checker.c2c(x, [1], fwd, 0.5)) <= tol(n, dtype), (n, fwd)
+    for n in (8, 16):
+        x = rnd(rng, (70001, n), dtype)
+        xd = torch_mod.from_numpy(x).cuda()
+        for fwd in (True, False):
+            want = checker.r2c(x, [1], fwd, 0.5)
+            sd = apply_nd(ib, "r2c", xd, torch_mod.zeros((70001, n // 2 + 1), dtype=getattr(torch_mod, np.dtype(cdt).name), device="cuda"), [1], fwd, 0.5)
+            used.add(ib.last_kernel())
+            assert oracle.max_row_rel_l2(sd.cpu().numpy(), want) <= tol(n, dtype), (n, fwd)
+        spec = checker.r2c(x, [1], True, 1.0).astype(cdt)
+        back = apply_nd(ib, "c2r", torch_mod.from_numpy(spec).cuda(), torch_mod.empty_like(xd), [1], False, 1.0 / n).cpu().numpy()
+        used.add(ib.last_kernel())
+        assert oracle.max_row_rel_l2(back, x) <= 4 * tol(n, dtype), n
+    assert all(k.startswith("fast2") for k in used), used
+
+
 def test_real_roundtrip_all_lengths(ib, torch_mod, checker):
     """tests/test_fft.nim:29-109 — every length 1..8191, forward then backward(1/N) through the
     packed in-place layout recovers the input; forward parity vs the oracle on every length too.
