@@ -189,15 +189,15 @@ int launch_fast3_job(const LineJob &J, int sm_count, void *stream) {
     case FAST3_1536_F64: g_last_kernel = "fast3_kernel<double,8,24,8,E24>"; return launch_fast3<double, 8, 24, 8, 24, 4, 7, 5>(J, sm_count, s);
     case FAST3_2000_F64: g_last_kernel = "fast3_kernel<double,10,20,10,E20>"; return launch_fast3<double, 10, 20, 10, 20, 3, 7, 5>(J, sm_count, s);
     case FAST3_4000_F64: g_last_kernel = "fast3_kernel<double,10,20,20,E20>"; return launch_fast3<double, 10, 20, 20, 20, 2, 7, 4>(J, sm_count, s);
-    case FAST3_2187_F64: g_last_kernel = "fast3_kernel<double,27,9,9,E27>"; return launch_fast3<double, 27, 9, 9, 27, 2, 1, 0>(J, sm_count, s);
-    case FAST3_3000_F64: g_last_kernel = "fast3_kernel<double,10,30,10,E30>"; return launch_fast3<double, 10, 30, 10, 30, 2, 1, 0>(J, sm_count, s);
-    case FAST3_6561_F64: g_last_kernel = "fast3_kernel<double,27,27,9,E27>"; return launch_fast3<double, 27, 27, 9, 27, 1, 1, 0>(J, sm_count, s);
-    case FAST3_1536_F32: g_last_kernel = "fast3_kernel<float,8,24,8,E24>"; return launch_fast3<float, 8, 24, 8, 24, 6, 1, 0>(J, sm_count, s);
-    case FAST3_2000_F32: g_last_kernel = "fast3_kernel<float,10,20,10,E20>"; return launch_fast3<float, 10, 20, 10, 20, 5, 1, 0>(J, sm_count, s);
-    case FAST3_4000_F32: g_last_kernel = "fast3_kernel<float,10,20,20,E20>"; return launch_fast3<float, 10, 20, 20, 20, 3, 1, 0>(J, sm_count, s);
-    case FAST3_2187_F32: g_last_kernel = "fast3_kernel<float,27,9,9,E27>"; return launch_fast3<float, 27, 9, 9, 27, 4, 1, 0>(J, sm_count, s);
-    case FAST3_3000_F32: g_last_kernel = "fast3_kernel<float,10,30,10,E30>"; return launch_fast3<float, 10, 30, 10, 30, 4, 1, 0>(J, sm_count, s);
-    case FAST3_6561_F32: g_last_kernel = "fast3_kernel<float,27,27,9,E27>"; return launch_fast3<float, 27, 27, 9, 27, 2, 1, 0>(J, sm_count, s);
+    case FAST3_2187_F64: g_last_kernel = "fast3_kernel<double,27,9,9,E27>"; return launch_fast3<double, 27, 9, 9, 27, 2, 7, 0>(J, sm_count, s);
+    case FAST3_3000_F64: g_last_kernel = "fast3_kernel<double,10,30,10,E30>"; return launch_fast3<double, 10, 30, 10, 30, 2, 7, 0>(J, sm_count, s);
+    case FAST3_6561_F64: g_last_kernel = "fast3_kernel<double,27,27,9,E27>"; return launch_fast3<double, 27, 27, 9, 27, 1, 7, 0>(J, sm_count, s);
+    case FAST3_1536_F32: g_last_kernel = "fast3_kernel<float,8,24,8,E24>"; return launch_fast3<float, 8, 24, 8, 24, 6, 7, 0>(J, sm_count, s);
+    case FAST3_2000_F32: g_last_kernel = "fast3_kernel<float,10,20,10,E20>"; return launch_fast3<float, 10, 20, 10, 20, 5, 7, 0>(J, sm_count, s);
+    case FAST3_4000_F32: g_last_kernel = "fast3_kernel<float,10,20,20,E20>"; return launch_fast3<float, 10, 20, 20, 20, 3, 7, 0>(J, sm_count, s);
+    case FAST3_2187_F32: g_last_kernel = "fast3_kernel<float,27,9,9,E27>"; return launch_fast3<float, 27, 9, 9, 27, 4, 7, 0>(J, sm_count, s);
+    case FAST3_3000_F32: g_last_kernel = "fast3_kernel<float,10,30,10,E30>"; return launch_fast3<float, 10, 30, 10, 30, 4, 7, 0>(J, sm_count, s);
+    case FAST3_6561_F32: g_last_kernel = "fast3_kernel<float,27,27,9,E27>"; return launch_fast3<float, 27, 27, 9, 27, 2, 7, 0>(J, sm_count, s);
     default: return (int)cudaErrorInvalidValue;
   }
 }

@@ -697,12 +697,12 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       else if (L == 1536 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_1536_F64; r1 = 8; r2 = 24; r3 = 8; }
       else if (L == 2000 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_2000_F64; r1 = 10; r2 = 20; r3 = 10; }
       else if (L == 4000 && f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_4000_F64; r1 = 10; r2 = 20; r3 = 20; }
-      else if (L == 2187 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_2187_F64 : FAST3_2187_F32; r1 = 27; r2 = 9; r3 = 9; }
-      else if (L == 3000 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_3000_F64 : FAST3_3000_F32; r1 = 10; r2 = 30; r3 = 10; }
-      else if (L == 6561 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_6561_F64 : FAST3_6561_F32; r1 = 27; r2 = 27; r3 = 9; }
-      else if (L == 1536 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_1536_F32; r1 = 8; r2 = 24; r3 = 8; }
-      else if (L == 2000 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_2000_F32; r1 = 10; r2 = 20; r3 = 10; }
-      else if (L == 4000 && !f64 && c2c && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_4000_F32; r1 = 10; r2 = 20; r3 = 20; }
+      else if (L == 2187 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_2187_F64 : FAST3_2187_F32; r1 = 27; r2 = 9; r3 = 9; }
+      else if (L == 3000 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_3000_F64 : FAST3_3000_F32; r1 = 10; r2 = 30; r3 = 10; }
+      else if (L == 6561 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = f64 ? FAST3_6561_F64 : FAST3_6561_F32; r1 = 27; r2 = 27; r3 = 9; }
+      else if (L == 1536 && !f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_1536_F32; r1 = 8; r2 = 24; r3 = 8; }
+      else if (L == 2000 && !f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_2000_F32; r1 = 10; r2 = 20; r3 = 10; }
+      else if (L == 4000 && !f64 && env_int("IMPULSE_FFT_MORE_SHAPES", 1)) { id = FAST3_4000_F32; r1 = 10; r2 = 20; r3 = 20; }
       else if (!c2c && (L == 4 || L == 8) && J->tw_r) {
         // tiny real rows (8 / 16 points): the same warp kernel, 16 rows per warp
         J->fast_id = L == 8 ? (f64 ? FAST2R_8_F64 : FAST2R_8_F32) : (f64 ? FAST2R_4_F64 : FAST2R_4_F32);

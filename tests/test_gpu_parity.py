@@ -194,7 +194,8 @@ def test_r2c_c2r_hermitian(ib, torch_mod, checker, dtype):
     rng = np.random.default_rng(6)
     cdt = np.complex128 if dtype == np.float64 else np.complex64
     lengths = list(range(1, 70)) + [74, 89, 97, 100, 121, 128, 191, 192, 243, 250, 382, 500, 1000, 1024, 2000, 3888,
-                                    4096, 4099, 4126]
+                                    4096, 4099, 4126, 3072, 4000, 4374, 6000, 8000, 13122]   # (the last six: real rows on the
+    # three-pass shapes 1536 / 2000 / 2187 / 3000 / 4000 / 6561 through the shared-memory Hermitian twiddle)
     for n in lengths:
         x = rnd(rng, (3, n), dtype)
         xd = torch_mod.from_numpy(x).cuda()
