@@ -638,6 +638,26 @@ int launch_fast_job(const LineJob &J, int sm_count, void *stream) {
     case FAST2_128_F32: g_last_kernel = "fast2_kernel<float,16,8,8,4>"; return launch_fast2<float, 16, 8, 8, 4>(J, sm_count, s);
     case FAST2_256_F32: g_last_kernel = "fast2_kernel<float,16,16,8,4>"; return launch_fast2<float, 16, 16, 8, 4>(J, sm_count, s);
     case FAST2_512_F32: g_last_kernel = "fast2_kernel<float,32,16,4,4>"; return launch_fast2<float, 32, 16, 4, 4>(J, sm_count, s);
+    case FAST2_50_F64: g_last_kernel = "fast2_kernel<double,10,5,8,4>"; return launch_fast2<double, 10, 5, 8, 4>(J, sm_count, s);
+    case FAST2_50_F32: g_last_kernel = "fast2_kernel<float,10,5,8,6>"; return launch_fast2<float, 10, 5, 8, 6>(J, sm_count, s);
+    case FAST2_72_F64: g_last_kernel = "fast2_kernel<double,24,3,4,2>"; return launch_fast2<double, 24, 3, 4, 2>(J, sm_count, s);
+    case FAST2_72_F32: g_last_kernel = "fast2_kernel<float,24,3,4,4>"; return launch_fast2<float, 24, 3, 4, 4>(J, sm_count, s);
+    case FAST2_81_F64: g_last_kernel = "fast2_kernel<double,9,9,8,4>"; return launch_fast2<double, 9, 9, 8, 4>(J, sm_count, s);
+    case FAST2_81_F32: g_last_kernel = "fast2_kernel<float,9,9,8,6>"; return launch_fast2<float, 9, 9, 8, 6>(J, sm_count, s);
+    case FAST2_96_F64: g_last_kernel = "fast2_kernel<double,24,4,4,2>"; return launch_fast2<double, 24, 4, 4, 2>(J, sm_count, s);
+    case FAST2_96_F32: g_last_kernel = "fast2_kernel<float,24,4,4,4>"; return launch_fast2<float, 24, 4, 4, 4>(J, sm_count, s);
+    case FAST2_192_F64: g_last_kernel = "fast2_kernel<double,24,8,4,2>"; return launch_fast2<double, 24, 8, 4, 2>(J, sm_count, s);
+    case FAST2_192_F32: g_last_kernel = "fast2_kernel<float,24,8,4,4>"; return launch_fast2<float, 24, 8, 4, 4>(J, sm_count, s);
+    case FAST2_200_F64: g_last_kernel = "fast2_kernel<double,20,10,4,3>"; return launch_fast2<double, 20, 10, 4, 3>(J, sm_count, s);
+    case FAST2_200_F32: g_last_kernel = "fast2_kernel<float,20,10,4,4>"; return launch_fast2<float, 20, 10, 4, 4>(J, sm_count, s);
+    case FAST2_400_F64: g_last_kernel = "fast2_kernel<double,20,20,4,3>"; return launch_fast2<double, 20, 20, 4, 3>(J, sm_count, s);
+    case FAST2_400_F32: g_last_kernel = "fast2_kernel<float,20,20,4,4>"; return launch_fast2<float, 20, 20, 4, 4>(J, sm_count, s);
+    case FAST2_576_F64: g_last_kernel = "fast2_kernel<double,24,24,4,2>"; return launch_fast2<double, 24, 24, 4, 2>(J, sm_count, s);
+    case FAST2_576_F32: g_last_kernel = "fast2_kernel<float,24,24,4,4>"; return launch_fast2<float, 24, 24, 4, 4>(J, sm_count, s);
+    case FAST2_729_F64: g_last_kernel = "fast2_kernel<double,27,27,4,2>"; return launch_fast2<double, 27, 27, 4, 2>(J, sm_count, s);
+    case FAST2_729_F32: g_last_kernel = "fast2_kernel<float,27,27,4,4>"; return launch_fast2<float, 27, 27, 4, 4>(J, sm_count, s);
+    case FAST2_900_F64: g_last_kernel = "fast2_kernel<double,30,30,4,2>"; return launch_fast2<double, 30, 30, 4, 2>(J, sm_count, s);
+    case FAST2_900_F32: g_last_kernel = "fast2_kernel<float,30,30,4,4>"; return launch_fast2<float, 30, 30, 4, 4>(J, sm_count, s);
     case FAST2_8_F64: g_last_kernel = "fast2_kernel<double,4,2,8,4>"; return launch_fast2<double, 4, 2, 8, 4>(J, sm_count, s);
     case FAST2_4_F64: g_last_kernel = "fast2_kernel<double,2,2,8,4>"; return launch_fast2<double, 2, 2, 8, 4>(J, sm_count, s);
     case FAST2_8_F32: g_last_kernel = "fast2_kernel<float,4,2,8,6>"; return launch_fast2<float, 4, 2, 8, 6>(J, sm_count, s);

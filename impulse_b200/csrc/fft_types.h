@@ -196,6 +196,27 @@ enum FastId : uint32_t {
   FAST2R_4_F64 = 108,
   FAST2R_8_F32 = 109,
   FAST2R_4_F32 = 110,
+  // more short non-power-of-two complex rows on the two-pass warp kernel (R1 points per thread x R2 threads per row)
+  FAST2_50_F64 = 111,
+  FAST2_72_F64 = 112,
+  FAST2_81_F64 = 113,
+  FAST2_96_F64 = 114,
+  FAST2_192_F64 = 115,
+  FAST2_200_F64 = 116,
+  FAST2_400_F64 = 117,
+  FAST2_576_F64 = 118,
+  FAST2_729_F64 = 119,
+  FAST2_900_F64 = 120,
+  FAST2_50_F32 = 121,
+  FAST2_72_F32 = 122,
+  FAST2_81_F32 = 123,
+  FAST2_96_F32 = 124,
+  FAST2_192_F32 = 125,
+  FAST2_200_F32 = 126,
+  FAST2_400_F32 = 127,
+  FAST2_576_F32 = 128,
+  FAST2_729_F32 = 129,
+  FAST2_900_F32 = 130,
 };
 
 struct Phase {

@@ -574,6 +574,16 @@ int PlanCache::build_line_job(const LineSpec &s, LineJob *J, LaunchCfg *cfg, std
       case 256: J->fast_id = f64 ? FAST2_256_F64 : FAST2_256_F32; break;
       case 512: J->fast_id = f64 ? FAST2_512_F64 : FAST2_512_F32; break;
       case 1024: J->fast_id = f64 ? FAST2_1024_F64 : FAST2_1024_F32; break;
+      case 50: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_50_F64 : FAST2_50_F32; break;
+      case 72: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_72_F64 : FAST2_72_F32; break;
+      case 81: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_81_F64 : FAST2_81_F32; break;
+      case 96: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_96_F64 : FAST2_96_F32; break;
+      case 192: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_192_F64 : FAST2_192_F32; break;
+      case 200: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_200_F64 : FAST2_200_F32; break;
+      case 400: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_400_F64 : FAST2_400_F32; break;
+      case 576: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_576_F64 : FAST2_576_F32; break;
+      case 729: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_729_F64 : FAST2_729_F32; break;
+      case 900: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_900_F64 : FAST2_900_F32; break;
       case 100: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_100_F64 : FAST2_100_F32; break;
       case 243: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_243_F64 : FAST2_243_F32; break;
       case 625: if (env_int("IMPULSE_FFT_MORE_SHAPES", 1)) J->fast_id = f64 ? FAST2_625_F64 : FAST2_625_F32; break;

@@ -116,7 +116,7 @@ def test_pocketfft_c_symbols(ib):
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
 def test_c2c_lengths(ib, torch_mod, checker, dtype):
     rng = np.random.default_rng(5)
-    lengths = list(range(1, 131)) + [144, 169, 187, 191, 243, 256, 289, 343, 360, 361, 500, 512, 529, 625,
+    lengths = list(range(1, 131)) + [144, 169, 187, 191, 192, 200, 243, 256, 289, 343, 360, 361, 400, 500, 512, 529, 576, 625, 900,
                                      729, 841, 961, 1000, 1024, 1331, 2048, 2187, 3125, 3888, 4096, 4099, 6561, 7000]
     if dtype == np.complex64:
         lengths = lengths[::3]
