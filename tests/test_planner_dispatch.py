@@ -98,3 +98,27 @@ def test_split_column_transform_is_marked_for_the_fused_kernel():
     assert emu.nd_fuse_flags("c2c", b, b, b.shape, [1], True) == [0, 0]
     c = np.empty((3, 2048, 32), np.complex128)     # 2048 = 32 x 64: no fused instance for that pair
     assert sum(emu.nd_fuse_flags("c2c", c, c, c.shape, [1], True)) == 0
+
+
+def test_second_session_shapes_are_selected(monkeypatch):
+    """tiny rows, the extra two-pass shapes, real rows on the three-pass shapes, the whole-axis kernels"""
+    assert ids_1d("c2c", 4, 64) == [ID["FAST2_4_F64"]] and ids_1d("c2c", 8, 64, np.float32) == [ID["FAST2_8_F32"]]
+    assert ids_1d("r2c", 16, 64) == [ID["FAST2R_8_F64"]] and ids_1d("c2r", 8, 64, np.float32) == [ID["FAST2R_4_F32"]]
+    for n in (50, 72, 81, 96, 192, 200, 400, 576, 729, 900):
+        assert ids_1d("c2c", n, 64) == [ID[f"FAST2_{n}_F64"]], n
+        assert ids_1d("c2c", n, 64, np.float32) == [ID[f"FAST2_{n}_F32"]], n
+    assert ids_1d("r2c", 6000, 64) == [ID["FAST3_3000_F64"]] and ids_1d("c2r", 4374, 64) == [ID["FAST3_2187_F64"]]
+    assert ids_1d("r2c", 8000, 64, np.float32) == [ID["FAST3_4000_F32"]] and ids_1d("c2r", 13122, 64, np.float32) == [ID["FAST3_6561_F32"]]
+    monkeypatch.setenv("IMPULSE_FFT_MORE_SHAPES", "0")
+    assert ids_1d("c2c", 400, 64) == [0] and ids_1d("r2c", 6000, 64) == [0]        # generic engine
+    monkeypatch.delenv("IMPULSE_FFT_MORE_SHAPES")
+    # strided complex128 axes of 1024 / 2048 points: ONE launch on the whole-axis kernel (the device backend only)
+    emu.set_fast_cols(2)
+    try:
+        for n, name in ((1024, "COLW_1024_F64"), (2048, "COLW_2048_F64")):
+            a = np.empty((2, n, 24), np.complex128)
+            assert emu.nd_fast_ids("c2c", a, a, a.shape, [1], True) == [ID[name]], n
+        a = np.empty((2, 1024, 24), np.complex64)        # complex64: the two-launch split (measured faster)
+        assert len(emu.nd_fast_ids("c2c", a, a, a.shape, [1], True)) == 2
+    finally:
+        emu.set_fast_cols(None)
