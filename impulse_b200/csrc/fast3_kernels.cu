@@ -128,9 +128,7 @@ int launch_fast3(const LineJob &J, int sm_count, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     configured_here = true;
   }
-  uint64_t grid = J.n_lines;
-  const uint64_t cap = (uint64_t)sm_count * MINB;
-  if (grid > cap) grid = cap;
+  const uint64_t grid = f3_grid(J.n_lines, (uint64_t)sm_count * MINB);
   unsigned int *sched = sched_slot();
   if (!sched) return (int)cudaErrorMemoryAllocation;
   if (J.n_lines > 0xfff00000ull) return (int)cudaErrorInvalidValue;

@@ -35,6 +35,16 @@ inline cudaError_t launch_pdl(void (*k)(KArgs...), unsigned grid, unsigned block
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
 }
+// Grid of the row-claiming three-pass kernels: min(rows, resident CTAs).  IMPULSE_FFT_F3_GRID=1 evens out short
+// batches (rows <= 8 x resident CTAs): with r = ceil(rows / cap) rows per CTA anyway, ceil(rows / r) CTAs finish at the
+// same time as cap CTAs would and contend less for HBM (config 1: 1024 rows -> 256 CTAs of 4 rows instead of 296
+// of 3 or 4).  Any grid >= 1 is correct: rows are claimed dynamically.
+inline uint64_t f3_grid(uint64_t rows, uint64_t cap) {
+  static const int mode = [] { const char *e = getenv("IMPULSE_FFT_F3_GRID"); return e ? atoi(e) : 0; }();
+  if (rows <= cap) return rows;
+  if (mode == 1 && rows <= 8 * cap) { const uint64_t r = (rows + cap - 1) / cap; return (rows + r - 1) / r; }
+  return cap;
+}
 // a zero-initialised pair of device words {next row, CTAs done} for one launch with dynamic row claims (fast_kernels.cu)
 unsigned int *sched_slot();
 int init_sched_slots();   // once per device, before the first launch (abi.cu: get_ctx)
